@@ -1,0 +1,295 @@
+/*
+ * rtcore_b200.h — C ABI of the B200-native (sm_100a) renderer core.
+ *
+ * This is the drop-in boundary for the data-parallel hot path of
+ * NullandKale/ILGPU_Raytracing (camera ray generation -> BVH traversal with
+ * ray/sphere + ray/triangle intersection -> material shading with bounce and
+ * RNG -> framebuffer accumulation and tone-map).  Everything ILGPU did for that
+ * path (device buffers, kernel load, kernel launch) is behind these entry
+ * points; the C# Engine (Scene / SceneManager / Camera / RTRenderer /
+ * Framebuffer) keeps its public surface and P/Invokes into this library
+ * (binding shown in INTEGRATION.md, C# source under csharp/).
+ *
+ * All citations are file:line under /root/reference/ILGPU_Raytracing/.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - every function returns RT_OK (0) or a negative RtStatus; rt_last_error()
+ *     returns a thread-local human readable message for the last failure.
+ *     Nothing throws across the ABI (the C# wrapper turns a negative status
+ *     into an exception the way CudaException.ThrowIfFailed does,
+ *     Engine/CudaGlInteropIndexBuffer.cs:56).
+ *   - an rt_ctx is NOT thread safe (the reference is single threaded on the GL
+ *     thread: Engine/RTWindow.cs:148-205).  One rt_ctx drives one GPU; multi-GPU
+ *     is one process (and one rt_ctx) per GPU with screen-tile partitioning.
+ *   - host arrays passed in are borrowed for the duration of the call only.
+ *   - rt_render() is asynchronous on the context's stream; rt_sync() /
+ *     rt_download() synchronise (the reference does one Synchronize() per frame:
+ *     Engine/RTRenderer.cs:233).
+ *   - There is NO CPU fallback: rt_create() fails with RT_ERR_NO_DEVICE when no
+ *     sm_100 CUDA device is usable.
+ */
+#ifndef RTCORE_B200_H
+#define RTCORE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define RT_API __declspec(dllexport)
+#else
+#define RT_API __attribute__((visibility("default")))
+#endif
+
+#define RT_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------- */
+/* Blittable element layouts == the reference's device element layouts.       */
+/* (sizes are static-asserted in csrc/abi_check.cpp and mirrored in C#)       */
+/* ------------------------------------------------------------------------- */
+
+/* Engine/Float3.cs:6-10 (12 B) */
+typedef struct RtFloat3 { float X, Y, Z; } RtFloat3;
+/* Engine/MeshLoaderOBJ.cs:33 (8 B) */
+typedef struct RtFloat2 { float X, Y; } RtFloat2;
+/* Engine/Affine3x4.cs:3-7 (48 B, row major 3x4) */
+typedef struct RtAffine3x4 {
+    float m00, m01, m02, m03;
+    float m10, m11, m12, m13;
+    float m20, m21, m22, m23;
+} RtAffine3x4;
+
+/* TLASNode / BLASNode, Engine/Scene.cs:705-739 (44 B each, identical layout) */
+typedef struct RtBvhNode {
+    RtFloat3 boundsMin;
+    RtFloat3 boundsMax;
+    int32_t left, right, first, count, skipIndex;
+} RtBvhNode;
+
+/* BlasType, Engine/Scene.cs:703 */
+enum { RT_BLAS_SPHERESET = 1, RT_BLAS_TRIMESH = 2 };
+
+/* InstanceRecord, Engine/Scene.cs:716-728 (144 B) */
+typedef struct RtInstanceRecord {
+    int32_t type;            /* RT_BLAS_* */
+    int32_t blasRoot;
+    int32_t blasNodeCount;
+    int32_t primIndexFirst;
+    int32_t primIndexCount;
+    RtAffine3x4 objectToWorld;
+    RtAffine3x4 worldToObject;
+    float uniformScale;
+    RtFloat3 worldBoundsMin;
+    RtFloat3 worldBoundsMax;
+} RtInstanceRecord;
+
+/* Shading codes, Engine/Sphere.cs:5-7, Engine/MeshLoaderOBJ.cs:46-48 */
+enum { RT_SHADING_LAMBERT = 0, RT_SHADING_MIRROR = 1, RT_SHADING_GLASS = 2 };
+
+/* MaterialRecord, Engine/MeshLoaderOBJ.cs:44-63 (44 B; the "48 B" comment there is wrong) */
+typedef struct RtMaterialRecord {
+    RtFloat3 Kd;
+    int32_t HasDiffuseMap;
+    int32_t DiffuseTexIndex;
+    int32_t Shading;
+    float IOR;
+    int32_t HasAlphaMap;
+    int32_t AlphaTexIndex;
+    int32_t TwoSided;
+    float AlphaCutoff;
+} RtMaterialRecord;
+
+/* Sphere, Engine/Sphere.cs:3-15 (80 B) */
+typedef struct RtSphere {
+    RtFloat3 center;
+    float radius;
+    RtFloat3 albedo;
+    RtMaterialRecord material;
+    int32_t shading;
+    float ior;
+} RtSphere;
+
+/* MeshTri / MeshTriUV, Engine/Scene.cs:741, Engine/MeshLoaderOBJ.cs:34 (12 B) */
+typedef struct RtMeshTri { int32_t i0, i1, i2; } RtMeshTri;
+typedef struct RtMeshTriUV { int32_t t0, t1, t2; } RtMeshTriUV;
+/* RGBA32 / TexInfo, Engine/Scene.cs:743-745 */
+typedef struct RtRGBA32 { uint8_t R, G, B, A; } RtRGBA32;
+typedef struct RtTexInfo { int32_t Offset, Width, Height; } RtTexInfo;
+
+/* Camera, Engine/Camera.cs:5-17 (92 B).  The kernels read origin/lowerLeft/
+ * horizontal/vertical (Engine/RTUtils.cs:13-17); forward/right/up/aspect/
+ * fovYRadians only feed temporal reprojection (Engine/RTRay.cs:339-360). */
+typedef struct RtCamera {
+    RtFloat3 origin, lowerLeft, horizontal, vertical;
+    RtFloat3 forward, right, up;
+    float aspect, fovYRadians;
+} RtCamera;
+
+/* The 15 arrays of SceneDeviceViews (Engine/SceneDeviceViews.cs:11-27) as host
+ * pointer + element count, exactly what Scene.UploadAll copies to the device
+ * (Engine/Scene.cs:258-279).  Empty arrays may be passed as (NULL, 0); the
+ * library applies the reference's AllocateOrEmpty rule (one zeroed element,
+ * Engine/Scene.cs:370-377). */
+typedef struct RtSceneDesc {
+    const RtBvhNode*        tlasNodes;           int64_t nTlasNodes;
+    const int32_t*          tlasInstanceIndices; int64_t nTlasInstanceIndices;
+    const RtInstanceRecord* instances;           int64_t nInstances;
+    const RtBvhNode*        blasNodes;           int64_t nBlasNodes;
+    const int32_t*          spherePrimIdx;       int64_t nSpherePrimIdx;
+    const RtSphere*         spheres;             int64_t nSpheres;
+    const int32_t*          triPrimIdx;          int64_t nTriPrimIdx;
+    const RtFloat3*         meshPositions;       int64_t nMeshPositions;
+    const RtMeshTri*        meshTris;            int64_t nMeshTris;
+    const RtFloat2*         meshTexcoords;       int64_t nMeshTexcoords;
+    const RtMeshTriUV*      meshTriUVs;          int64_t nMeshTriUVs;
+    const int32_t*          triMatIndex;         int64_t nTriMatIndex;
+    const RtMaterialRecord* materials;           int64_t nMaterials;
+    const RtRGBA32*         texels;              int64_t nTexels;
+    const RtTexInfo*        texInfos;            int64_t nTexInfos;
+} RtSceneDesc;
+
+/* rt_render flags */
+enum {
+    /* Extension (off = reference-faithful): triangles take shade/ior from their
+     * MaterialRecord instead of the forced Lambert of SceneDeviceViews.cs:61. */
+    RT_FLAG_TRI_MATERIALS = 1u << 0,
+    /* Progressive accumulation (new functionality):
+     * accum.rgb += Lout, accum.w += 1; RGBA8 = PackRGBA8(accum.rgb / accum.w). */
+    RT_FLAG_ACCUMULATE    = 1u << 1,
+    RT_FLAG_RESET_ACCUM   = 1u << 2,
+    /* Keep per-(pixel,sample) parity AOVs: segment count, terminator, path hash. */
+    RT_FLAG_PATH_AOVS     = 1u << 3,
+    /* Count rays / nodes / primitives on the device (slower; for roofline). */
+    RT_FLAG_COUNTERS      = 1u << 4
+};
+
+/* Everything the reference passes in GBufferParams / IntegratorParams
+ * (Engine/RTRay.cs:112-169) that is not a buffer, plus the JIT-specialised
+ * MaxDepth (Engine/RTRenderer.cs:204-205) and the tile partition. */
+typedef struct RtRenderConfig {
+    int32_t width, height, frame;
+    int32_t spp;                 /* IntegratorParams.spp (max(1,spp) samples) */
+    int32_t maxDepth;            /* SpecializedValue<int> MaxDepth; 0 = primary only */
+    int32_t rngLockNoise;        /* IntegratorParams.rngLockNoise (Engine/RTUtils.cs:116-137) */
+    int32_t enableTemporalReuse; /* Engine/RTRay.cs:476 */
+    int32_t enableSpatialReuse;  /* Engine/RTRay.cs:486 */
+    RtFloat3 dirLightDir, dirLightRadiance;   /* Engine/RTRenderer.cs:174-178,191-192 */
+    RtFloat3 skyTintTop, skyTintBottom;       /* Engine/RTRenderer.cs:193-194 */
+    uint32_t flags;              /* RT_FLAG_* */
+    /* Screen-tile partition for multi-GPU: this context renders only tiles with
+     * (tx + 3*ty) % worldSize == rank.  worldSize <= 1 renders the whole image. */
+    int32_t tileSize, rank, worldSize;
+    int32_t samplesPerPass;      /* wavefront batch of samples; 0 = auto */
+    int32_t reserved[3];
+} RtRenderConfig;
+
+/* rt_download / rt_get_device_buffer selectors.  Per-pixel buffers are in the
+ * reference's index order (index = y*width + x, row 0 = bottom scanline,
+ * Engine/RTRay.cs:122-125); with a tile partition the non-owned pixels are
+ * left untouched. */
+enum {
+    RT_BUF_RGBA8        = 0,  /* int32  per px : PackRGBA8 (Engine/RTRay.cs:66-76) */
+    RT_BUF_DEPTH        = 1,  /* float  per px : GpuFramebuffer.depth */
+    RT_BUF_OBJID        = 2,  /* int32  per px : GpuFramebuffer.objectId (tri id, -1 for spheres/miss) */
+    RT_BUF_RADIANCE     = 3,  /* float4 per px : Lout pre-pack (Engine/RTRay.cs:323), w = 1 */
+    RT_BUF_ACCUM        = 4,  /* float4 per px : progressive accumulator */
+    RT_BUF_PRIM_ID      = 5,  /* int32  per px : primary hit sphere index or global tri index, -1 miss */
+    RT_BUF_INST_ID      = 6,  /* int32  per px : primary hit instance index, -1 miss */
+    RT_BUF_PRIMARY_T    = 7,  /* float  per px : primary closestT (1e30 on miss) */
+    RT_BUF_SEG_COUNT    = 8,  /* uint8  per (sample,px): number of TraceNext calls   (RT_FLAG_PATH_AOVS) */
+    RT_BUF_TERM_CODE    = 9,  /* uint8  per (sample,px): RT_TERM_*                   (RT_FLAG_PATH_AOVS) */
+    RT_BUF_PATH_HASH    = 10, /* uint32 per (sample,px): fold of hit prim ids        (RT_FLAG_PATH_AOVS) */
+    RT_BUF_GB_WORLDPOS  = 11, /* float3 per px : GpuGBuffer.worldPos  (Engine/RTRay.cs:80-109) */
+    RT_BUF_GB_NORMAL    = 12, /* float3 per px : GpuGBuffer.normalWS */
+    RT_BUF_GB_BASECOLOR = 13, /* float3 per px : GpuGBuffer.baseColor */
+    RT_BUF_GB_MATID     = 14, /* int32  per px : GpuGBuffer.matId */
+    RT_BUF_TILE_RADIANCE = 15 /* float4 per OWNED px, tile-compacted (multi-GPU gather payload) */
+};
+
+/* Path terminators reported in RT_BUF_TERM_CODE */
+enum {
+    RT_TERM_PRIMARY_MISS = 0, /* hitMask == 0 (Engine/RTRay.cs:214-219) */
+    RT_TERM_MISS         = 1, /* TraceNext missed -> sky (Engine/RTRay.cs:241-242,272-273,314-315) */
+    RT_TERM_MAXDEPTH     = 2, /* depth loop ran out (Engine/RTRay.cs:233) */
+    RT_TERM_ROULETTE     = 3  /* Russian roulette kill (Engine/RTRay.cs:306-312) */
+};
+
+/* Counters (valid after rt_sync; ray counts always, the rest with RT_FLAG_COUNTERS) */
+typedef struct RtStats {
+    uint64_t raysPrimary;   /* primary TraceClosest calls (= pixels rendered) */
+    uint64_t raysBounce;    /* TraceNext calls (Engine/RTRay.cs:659-671) */
+    uint64_t raysShadow;    /* ShadowOcclusion calls (Engine/RTRay.cs:618-624) */
+    uint64_t wideNodes;     /* 80-byte wide nodes fetched */
+    uint64_t trisTested;    /* 48-byte triangle records tested */
+    uint64_t spheresTested; /* 48-byte sphere records tested */
+    uint64_t kernelLaunches;/* kernels launched by the last rt_render */
+    float    lastRenderMs;  /* CUDA-event time of the last rt_render on its stream */
+    float    lastTraceMs;   /* of which: extend (closest + shadow) kernels */
+    uint64_t bvhWideNodeCount, bvhPrimCount, bvhBytes;
+    uint64_t reserved[4];
+} RtStats;
+
+typedef struct rt_ctx rt_ctx;
+
+typedef enum RtStatus {
+    RT_OK = 0,
+    RT_ERR_INVALID_ARGUMENT = -1, /* ArgumentNull/ArgumentOutOfRange analogue */
+    RT_ERR_NO_DEVICE        = -2, /* no usable sm_100 CUDA device: there is no CPU fallback */
+    RT_ERR_CUDA             = -3, /* a CUDA runtime call failed (message has the cudaError) */
+    RT_ERR_INVALID_STATE    = -4, /* InvalidOperationException analogue (e.g. render before scene upload) */
+    RT_ERR_UNSUPPORTED      = -5, /* feature outside the hot-path scope built so far */
+    RT_ERR_OUT_OF_MEMORY    = -6
+} RtStatus;
+
+/* ---- lifetime: replaces Context.Create(...Cuda()...) + CreateCudaAccelerator(deviceIndex)
+ *      (Engine/RTRenderer.cs:66-68) and Dispose (Engine/RTRenderer.cs:347-375). ---- */
+RT_API int rt_abi_version(void);
+RT_API const char* rt_last_error(void);
+RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out); /* nDev must be 1 */
+RT_API int rt_destroy(rt_ctx* ctx);
+/* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+RT_API int rt_set_stream(rt_ctx* ctx, void* cudaStream);
+
+/* ---- scene commit: replaces Scene.UploadAll (Engine/Scene.cs:258-279) reached through
+ *      SceneManager.Commit -> BvhManager.BuildOrRefit (Engine/BvhManager.cs:27).
+ *      Copies the arrays, derives the reference's traversal order from the BVH2
+ *      arrays (tie-break ranks) and builds the compressed 8-wide BVH. ---- */
+RT_API int rt_scene_upload(rt_ctx* ctx, const RtSceneDesc* scene);
+
+/* ---- per-frame hot path: replaces the two kernel launches of
+ *      RTRenderer.RenderDirectToPbo (Engine/RTRenderer.cs:152-153 PrimaryVisibilityKernel,
+ *      :181-205 PathTraceKernel).  prevCam may be NULL when temporal reuse is off. ---- */
+RT_API int rt_render(rt_ctx* ctx, const RtCamera* cam, const RtCamera* prevCam,
+                     const RtRenderConfig* cfg);
+RT_API int rt_sync(rt_ctx* ctx); /* _cuda.Synchronize(), Engine/RTRenderer.cs:233 */
+
+/* ---- read-back: replaces Framebuffer.DownloadToCpu / CpuColor / CpuDepth / CpuObjectId
+ *      (Engine/Framebuffer.cs:148-160).  bytes must equal the buffer's size. ---- */
+RT_API int rt_download(rt_ctx* ctx, int which, void* dstHost, size_t bytes);
+RT_API int rt_buffer_bytes(rt_ctx* ctx, int which, size_t* bytes);
+/* Device pointer of an output buffer (for NCCL / torch plumbing, no copy). */
+RT_API int rt_get_device_buffer(rt_ctx* ctx, int which, void** devPtr, size_t* bytes);
+/* Write packed RGBA8 into a caller-owned device buffer (CUDA-mapped PBO):
+ * replaces Framebuffer.GetGpuWithExternalColor (Engine/Framebuffer.cs:112-124). NULL unmaps. */
+RT_API int rt_map_external_color(rt_ctx* ctx, void* devPtr, size_t bytes);
+
+/* ---- multi-GPU finish on the gathering rank: scatter the tile-compacted float4
+ *      payloads of all ranks (concatenated rank-major, as NCCL gather delivers them)
+ *      into the full image, and write Lout float4 + RGBA8 for every pixel. ---- */
+RT_API int rt_tiles_owned_pixels(int width, int height, int tileSize, int rank, int worldSize,
+                                 int64_t* nPixels);
+RT_API int rt_deinterleave_tiles(rt_ctx* ctx, const void* gatheredDev, const int64_t* rankOffsetsPx,
+                                 int worldSize, int width, int height, int tileSize,
+                                 void* outRadianceDev /* float4*w*h or NULL */,
+                                 void* outRgba8Dev   /* int32*w*h or NULL */);
+
+RT_API int rt_get_stats(rt_ctx* ctx, RtStats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTCORE_B200_H */
