@@ -1,0 +1,349 @@
+// rt_bvh.cpp — host-side scene flattening: reference BVH2 arrays -> ranked primitive list ->
+// binned-SAH binary BVH -> compressed 8-wide BVH (80-byte nodes) + 48-byte primitive records.
+//
+// Replaces, as the acceleration structure the device walks, the TLAS/BLAS pair built by
+// Scene.BuildTLASNodeRecursive / BuildBLASNodeRecursive (Engine/Scene.cs:405-510).  The reference
+// arrays are still the INPUT (rt_scene_upload receives what Scene.UploadAll uploads, Scene.cs:258-279):
+// they define which (instance, primitive) pairs exist and the order in which the reference visits
+// them, which is the tie-break rank for equal-t hits.
+#include "rt_bvh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace rtx {
+
+namespace {
+
+struct Aabb {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; a++) { lo[a] = std::numeric_limits<float>::max(); hi[a] = -std::numeric_limits<float>::max(); } }
+    void grow(const Aabb& b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    void grow(const float* p) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.0f;
+        return 2.0f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+struct BuildPrim { Aabb box; float c[3]; PrimRec rec; };
+
+struct B2Node { Aabb box; int left, right, first, count; };
+
+bool is_identity(const RtInstanceRecord& ir) {
+    const RtAffine3x4& m = ir.worldToObject;
+    const RtAffine3x4& n = ir.objectToWorld;
+    auto id = [](const RtAffine3x4& a) {
+        return a.m00 == 1.0f && a.m01 == 0.0f && a.m02 == 0.0f && a.m03 == 0.0f && a.m10 == 0.0f && a.m11 == 1.0f && a.m12 == 0.0f && a.m13 == 0.0f &&
+               a.m20 == 0.0f && a.m21 == 0.0f && a.m22 == 1.0f && a.m23 == 0.0f;
+    };
+    return id(m) && id(n) && ir.uniformScale == 1.0f;
+}
+
+// inverse of the 3x4 affine worldToObject in double precision: where does an object-space point live in the world?
+bool invert_affine(const RtAffine3x4& m, double inv[12]) {
+    double a = m.m00, b = m.m01, c = m.m02, d = m.m10, e = m.m11, f = m.m12, g = m.m20, h = m.m21, i = m.m22;
+    double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (!(std::fabs(det) > 1e-30)) return false;
+    double id = 1.0 / det;
+    double r[9] = {(e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id, (c * d - a * f) * id,
+                   (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id};
+    double t[3] = {m.m03, m.m13, m.m23};
+    for (int rr = 0; rr < 3; rr++) {
+        inv[rr * 4 + 0] = r[rr * 3 + 0]; inv[rr * 4 + 1] = r[rr * 3 + 1]; inv[rr * 4 + 2] = r[rr * 3 + 2];
+        inv[rr * 4 + 3] = -(r[rr * 3 + 0] * t[0] + r[rr * 3 + 1] * t[1] + r[rr * 3 + 2] * t[2]);
+    }
+    return true;
+}
+
+struct Builder {
+    std::vector<BuildPrim> prims;
+    std::vector<int> idx;
+    std::vector<B2Node> b2;
+
+    int build_rec(int first, int count) {
+        int ni = (int)b2.size();
+        b2.push_back(B2Node());
+        Aabb box, cb; box.reset(); cb.reset();
+        for (int i = first; i < first + count; i++) { box.grow(prims[idx[i]].box); cb.grow(prims[idx[i]].c); }
+        b2[ni].box = box; b2[ni].left = b2[ni].right = -1; b2[ni].first = first; b2[ni].count = count;
+        if (count == 1) return ni;
+
+        // binned SAH over the centroid bounds
+        const int NB = 16;
+        int bestAxis = -1, bestSplit = -1; float bestCost = std::numeric_limits<float>::max();
+        for (int a = 0; a < 3; a++) {
+            float ext = cb.hi[a] - cb.lo[a];
+            if (!(ext > 0.0f)) continue;
+            Aabb bb[NB]; int bc[NB];
+            for (int b = 0; b < NB; b++) { bb[b].reset(); bc[b] = 0; }
+            float k = (float)NB / ext;
+            for (int i = first; i < first + count; i++) {
+                const BuildPrim& p = prims[idx[i]];
+                int b = std::min(NB - 1, std::max(0, (int)((p.c[a] - cb.lo[a]) * k)));
+                bb[b].grow(p.box); bc[b]++;
+            }
+            float rightArea[NB]; Aabb acc; acc.reset(); int n = 0;
+            for (int b = NB - 1; b > 0; b--) { acc.grow(bb[b]); rightArea[b] = acc.area(); }
+            acc.reset(); int rn = count;
+            for (int b = 0; b < NB - 1; b++) {
+                acc.grow(bb[b]); n += bc[b]; rn = count - n;
+                if (n == 0 || rn == 0) continue;
+                float cost = acc.area() * (float)n + rightArea[b + 1] * (float)rn;
+                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
+            }
+        }
+        // leaf decision: at most 3 primitives per leaf (3-bit unary count in the wide node's meta byte)
+        if (count <= 3) {
+            float leafCost = box.area() * (float)count;
+            if (bestAxis < 0 || bestCost + box.area() * 0.3f >= leafCost) return ni;
+        }
+        int mid;
+        if (bestAxis >= 0) {
+            float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
+            float k = 16.0f / ext; float lo = cb.lo[bestAxis]; int a = bestAxis, sp = bestSplit;
+            auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](int pi) {
+                int b = std::min(15, std::max(0, (int)((prims[pi].c[a] - lo) * k)));
+                return b <= sp;
+            });
+            mid = (int)(it - idx.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        } else {
+            mid = first + count / 2;   // all centroids coincide
+        }
+        int l = build_rec(first, mid - first);
+        int r = build_rec(mid, first + count - mid);
+        b2[ni].left = l; b2[ni].right = r; b2[ni].count = 0;
+        return ni;
+    }
+};
+
+inline uint32_t pack4(const uint8_t* b) { return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24); }
+inline uint32_t fbits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+inline float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+}   // namespace
+
+bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
+    out.nodes.clear(); out.prims.clear(); out.stats = HostBvhStats();
+    Builder B;
+
+    // ---- 1. enumerate (instance, primitive) pairs in the reference's visiting order --------------------------------
+    // TLAS walk with every box test taken (SceneDeviceViews.cs:33-84): leaves in left-first skip-link order.
+    std::vector<int> instOrder;
+    if (d.nTlasNodes > 0) {
+        int64_t guard = 0; int cur = 0;
+        while (cur != -1) {
+            if (cur < 0 || cur >= d.nTlasNodes || ++guard > 4 * d.nTlasNodes + 8) { err = "tlasNodes: bad link"; return false; }
+            const RtBvhNode& n = d.tlasNodes[cur];
+            if (n.count > 0) {
+                for (int i = n.first; i < n.first + n.count; i++) {
+                    if (i < 0 || i >= d.nTlasInstanceIndices) { err = "tlasNodes: leaf range outside tlasInstanceIndices"; return false; }
+                    int ii = d.tlasInstanceIndices[i];
+                    if (ii < 0 || ii >= d.nInstances) { err = "tlasInstanceIndices: bad instance index"; return false; }
+                    instOrder.push_back(ii);
+                }
+                cur = n.skipIndex;
+            } else cur = n.left;
+        }
+    }
+    if (instOrder.size() > (size_t)PRIM_INST_MASK) { err = "too many instances"; return false; }
+
+    uint32_t rank = 0;
+    for (size_t io = 0; io < instOrder.size(); io++) {
+        int ii = instOrder[io];
+        const RtInstanceRecord& ir = d.instances[ii];
+        const bool ident = is_identity(ir);
+        double w2oInv[12];
+        if (!ident && !invert_affine(ir.worldToObject, w2oInv)) { err = "instance worldToObject is singular"; return false; }
+        const bool sph = ir.type == RT_BLAS_SPHERESET;
+        if (!sph && ir.type != RT_BLAS_TRIMESH) { err = "instance: unknown BlasType"; return false; }
+        int blasStart = ir.blasRoot, blasEnd = ir.blasRoot + ir.blasNodeCount;
+        if (blasStart < 0 || blasEnd > d.nBlasNodes) { err = "instance: BLAS range outside blasNodes"; return false; }
+        // BLAS walk with every box test taken (SceneDeviceViews.cs:127-168 / :176-235)
+        int cur = blasStart; int64_t guard = 0;
+        while (cur != -1 && cur < blasEnd) {
+            if (cur < blasStart || ++guard > 4 * (int64_t)ir.blasNodeCount + 8) { err = "blasNodes: bad link"; return false; }
+            const RtBvhNode& n = d.blasNodes[cur];
+            if (n.count > 0) {
+                for (int i = n.first; i < n.first + n.count; i++) {
+                    BuildPrim bp; memset(&bp, 0, sizeof(bp));
+                    uint32_t meta = (uint32_t)ii;
+                    if (!ident) meta |= PRIM_XFORM;
+                    float obb[2][3];
+                    if (sph) {
+                        if (i < 0 || i >= d.nSpherePrimIdx) { err = "BLAS leaf range outside spherePrimIdx"; return false; }
+                        int prim = d.spherePrimIdx[i];
+                        if (prim < 0 || prim >= d.nSpheres) { err = "spherePrimIdx: bad sphere index"; return false; }
+                        const RtSphere& s = d.spheres[prim];
+                        meta |= PRIM_SPHERE;
+                        bp.rec.q0 = make_float4(s.center.X, s.center.Y, s.center.Z, bitsf((uint32_t)prim));
+                        bp.rec.q1 = make_float4(s.radius, 0.0f, 0.0f, bitsf(rank));
+                        bp.rec.q2 = make_float4(0.0f, 0.0f, 0.0f, bitsf(meta));
+                        float r = std::fabs(s.radius);
+                        obb[0][0] = s.center.X - r; obb[0][1] = s.center.Y - r; obb[0][2] = s.center.Z - r;
+                        obb[1][0] = s.center.X + r; obb[1][1] = s.center.Y + r; obb[1][2] = s.center.Z + r;
+                        out.stats.nSpheres++;
+                    } else {
+                        if (i < 0 || i >= d.nTriPrimIdx) { err = "BLAS leaf range outside triPrimIdx"; return false; }
+                        int tri = d.triPrimIdx[i];
+                        if (tri < 0 || tri >= d.nMeshTris) { err = "triPrimIdx: bad triangle index"; return false; }
+                        const RtMeshTri& t = d.meshTris[tri];
+                        if (t.i0 < 0 || t.i1 < 0 || t.i2 < 0 || t.i0 >= d.nMeshPositions || t.i1 >= d.nMeshPositions || t.i2 >= d.nMeshPositions) { err = "meshTris: bad vertex index"; return false; }
+                        if (tri >= d.nTriMatIndex || tri >= d.nMeshTriUVs) { err = "triMatIndex/meshTriUVs shorter than meshTris"; return false; }
+                        int mi = d.triMatIndex[tri];
+                        if (mi < 0 || mi >= d.nMaterials) { err = "triMatIndex: bad material index"; return false; }
+                        const RtMeshTriUV& tuv = d.meshTriUVs[tri];
+                        if (tuv.t0 < 0 || tuv.t1 < 0 || tuv.t2 < 0 || tuv.t0 >= d.nMeshTexcoords || tuv.t1 >= d.nMeshTexcoords || tuv.t2 >= d.nMeshTexcoords) { err = "meshTriUVs: bad texcoord index"; return false; }
+                        const RtMaterialRecord& m = d.materials[mi];
+                        int64_t nTexLen = d.nTexInfos > 0 ? d.nTexInfos : 1;   // AllocateOrEmpty (Scene.cs:370-377)
+                        bool alphaMap = m.HasAlphaMap != 0 && m.AlphaTexIndex >= 0 && m.AlphaTexIndex < nTexLen;
+                        if (alphaMap) meta |= PRIM_ALPHA;
+                        else if (1.0f < m.AlphaCutoff) meta |= PRIM_NO_CLOSEST;
+                        const RtFloat3 &v0 = d.meshPositions[t.i0], &v1 = d.meshPositions[t.i1], &v2 = d.meshPositions[t.i2];
+                        bp.rec.q0 = make_float4(v0.X, v0.Y, v0.Z, bitsf((uint32_t)tri));
+                        bp.rec.q1 = make_float4(v1.X, v1.Y, v1.Z, bitsf(rank));
+                        bp.rec.q2 = make_float4(v2.X, v2.Y, v2.Z, bitsf(meta));
+                        obb[0][0] = std::min(v0.X, std::min(v1.X, v2.X)); obb[0][1] = std::min(v0.Y, std::min(v1.Y, v2.Y)); obb[0][2] = std::min(v0.Z, std::min(v1.Z, v2.Z));
+                        obb[1][0] = std::max(v0.X, std::max(v1.X, v2.X)); obb[1][1] = std::max(v0.Y, std::max(v1.Y, v2.Y)); obb[1][2] = std::max(v0.Z, std::max(v1.Z, v2.Z));
+                        out.stats.nTris++;
+                    }
+                    for (int a = 0; a < 3; a++) if (!std::isfinite(obb[0][a]) || !std::isfinite(obb[1][a])) { err = "non-finite primitive bounds"; return false; }
+                    bp.box.reset();
+                    if (ident) { bp.box.grow(obb[0]); bp.box.grow(obb[1]); }
+                    else {
+                        for (int c = 0; c < 8; c++) {
+                            double p[3] = {obb[c & 1][0], obb[(c >> 1) & 1][1], obb[(c >> 2) & 1][2]};
+                            float w[3];
+                            for (int r = 0; r < 3; r++) w[r] = (float)(w2oInv[r * 4] * p[0] + w2oInv[r * 4 + 1] * p[1] + w2oInv[r * 4 + 2] * p[2] + w2oInv[r * 4 + 3]);
+                            bp.box.grow(w);
+                        }
+                    }
+                    B.prims.push_back(bp);
+                    rank++;
+                }
+                cur = n.skipIndex;
+            } else cur = n.left;
+        }
+    }
+    const int N = (int)B.prims.size();
+    out.stats.nPrims = N;
+    if (N == 0) return true;   // empty scene: everything misses
+
+    // ---- 2. conservative padding (rounding of the exact primitive tests and of the quantised slab test) ----------
+    float sceneAbs = 0.0f;
+    for (auto& p : B.prims) for (int a = 0; a < 3; a++) sceneAbs = std::max(sceneAbs, std::max(std::fabs(p.box.lo[a]), std::fabs(p.box.hi[a])));
+    for (auto& p : B.prims) {
+        bool xf = (fbits(p.rec.q2.w) & PRIM_XFORM) != 0;
+        for (int a = 0; a < 3; a++) {
+            float mag = std::max(std::fabs(p.box.lo[a]), std::fabs(p.box.hi[a]));
+            float pad = 2e-6f * sceneAbs + (xf ? 2e-5f : 2e-6f) * mag + 1e-30f;
+            p.box.lo[a] -= pad; p.box.hi[a] += pad;
+            p.c[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
+        }
+    }
+
+    // ---- 3. binary BVH (binned SAH, leaves of <= 3 primitives) ---------------------------------------------------
+    B.idx.resize((size_t)N);
+    for (int i = 0; i < N; i++) B.idx[i] = i;
+    B.b2.reserve((size_t)2 * N);
+    B.build_rec(0, N);
+
+    // ---- 4. collapse to 8-wide, assign slots by octant, quantise, emit -------------------------------------------
+    struct Work { int b2; int wide; };
+    std::vector<Work> queue;
+    out.nodes.reserve((size_t)N / 3 + 16);
+    out.prims.reserve((size_t)N);
+    out.nodes.push_back(WideNode());
+    queue.push_back({0, 0});
+    int maxDepthSeen = 0;
+    std::vector<int> depthOf; depthOf.push_back(1);
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        const Work w = queue[qi];
+        const B2Node& root = B.b2[w.b2];
+        int ch[8]; int nch = 0;
+        if (root.count > 0) { ch[nch++] = w.b2; }   // a single-leaf tree: one leaf child
+        else {
+            ch[nch++] = root.left; ch[nch++] = root.right;
+            for (;;) {
+                int pick = -1; float bestA = -1.0f;
+                for (int i = 0; i < nch; i++) if (B.b2[ch[i]].count == 0) { float a = B.b2[ch[i]].box.area(); if (a > bestA) { bestA = a; pick = i; } }
+                if (pick < 0 || nch >= 8) break;
+                int c = ch[pick];
+                ch[pick] = B.b2[c].left; ch[nch++] = B.b2[c].right;
+            }
+        }
+        // slot assignment: slot s prefers the child lying furthest "against" the direction (sx,sy,sz), bit a of s set = negative axis a
+        Aabb nb = root.box;
+        float ncx[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]), 0.5f * (nb.lo[2] + nb.hi[2])};
+        float cost[8][8]; int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false}; bool chDone[8] = {false, false, false, false, false, false, false, false};
+        for (int c = 0; c < nch; c++) {
+            const Aabb& cb = B.b2[ch[c]].box;
+            float cc[3] = {0.5f * (cb.lo[0] + cb.hi[0]) - ncx[0], 0.5f * (cb.lo[1] + cb.hi[1]) - ncx[1], 0.5f * (cb.lo[2] + cb.hi[2]) - ncx[2]};
+            for (int s = 0; s < 8; s++) cost[c][s] = cc[0] * ((s & 1) ? -1.0f : 1.0f) + cc[1] * ((s & 2) ? -1.0f : 1.0f) + cc[2] * ((s & 4) ? -1.0f : 1.0f);
+        }
+        for (int k = 0; k < nch; k++) {
+            int bc = -1, bs = -1; float bv = std::numeric_limits<float>::max();
+            for (int c = 0; c < nch; c++) if (!chDone[c]) for (int s = 0; s < 8; s++) if (!slotUsed[s] && cost[c][s] < bv) { bv = cost[c][s]; bc = c; bs = s; }
+            chDone[bc] = true; slotUsed[bs] = true; slotOf[bc] = bs;
+        }
+        int childAt[8]; for (int s = 0; s < 8; s++) childAt[s] = -1;
+        for (int c = 0; c < nch; c++) childAt[slotOf[c]] = ch[c];
+
+        // quantisation frame
+        uint8_t eb[3]; double scale[3];
+        for (int a = 0; a < 3; a++) {
+            double ext = (double)nb.hi[a] - (double)nb.lo[a];
+            int e = -126;
+            if (ext > 0.0) { e = (int)std::ceil(std::log2(ext / 255.0)); while (ext / std::ldexp(1.0, e) > 255.0) e++; }
+            e = std::max(-126, std::min(127, e));
+            eb[a] = (uint8_t)(e + 127); scale[a] = std::ldexp(1.0, e);
+        }
+        uint8_t meta[8], qlo[3][8], qhi[3][8]; uint32_t imask = 0;
+        uint32_t childBase = (uint32_t)out.nodes.size(), primBase = (uint32_t)out.prims.size();
+        int primOff = 0;
+        for (int s = 0; s < 8; s++) {
+            meta[s] = 0; for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }
+            int c = childAt[s];
+            if (c < 0) continue;
+            const B2Node& cn = B.b2[c];
+            for (int a = 0; a < 3; a++) {
+                double l = std::floor(((double)cn.box.lo[a] - (double)nb.lo[a]) / scale[a]);
+                double h = std::ceil(((double)cn.box.hi[a] - (double)nb.lo[a]) / scale[a]);
+                qlo[a][s] = (uint8_t)std::max(0.0, std::min(255.0, l));
+                qhi[a][s] = (uint8_t)std::max(0.0, std::min(255.0, h));
+            }
+            if (cn.count == 0) {
+                imask |= 1u << s;
+                meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+                int wi = (int)out.nodes.size();
+                out.nodes.push_back(WideNode());
+                depthOf.push_back(depthOf[w.wide] + 1);
+                maxDepthSeen = std::max(maxDepthSeen, depthOf[w.wide] + 1);
+                queue.push_back({c, wi});
+            } else {
+                uint32_t unary = cn.count == 1 ? 1u : (cn.count == 2 ? 3u : 7u);
+                meta[s] = (uint8_t)((unary << 5) | (uint32_t)primOff);
+                for (int i = 0; i < cn.count; i++) out.prims.push_back(B.prims[B.idx[cn.first + i]].rec);
+                primOff += cn.count;
+            }
+        }
+        WideNode& wn = out.nodes[w.wide];
+        wn.n0 = make_uint4(fbits(nb.lo[0]), fbits(nb.lo[1]), fbits(nb.lo[2]), (uint32_t)eb[0] | ((uint32_t)eb[1] << 8) | ((uint32_t)eb[2] << 16) | (imask << 24));
+        wn.n1 = make_uint4(childBase, primBase, pack4(meta), pack4(meta + 4));
+        wn.n2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
+        wn.n3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
+        wn.n4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+    }
+    out.stats.nWideNodes = (int64_t)out.nodes.size();
+    out.stats.maxDepth = std::max(1, maxDepthSeen);
+    for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = B.b2[0].box.lo[a]; out.stats.sceneHi[a] = B.b2[0].box.hi[a]; }
+    if (out.stats.maxDepth > RT_STACK_TOTAL - 2) { err = "wide BVH deeper than the traversal stack"; return false; }
+    if ((int64_t)out.prims.size() != (int64_t)N) { err = "internal: primitive count mismatch"; return false; }
+    return true;
+}
+
+}   // namespace rtx

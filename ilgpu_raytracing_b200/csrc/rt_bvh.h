@@ -1,0 +1,27 @@
+// rt_bvh.h — host-side flattening of the reference scene arrays into the wide-BVH device layout.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "rt_core.h"
+#include "rt_traverse.h"
+
+namespace rtx {
+
+struct HostBvhStats {
+    int64_t nPrims = 0, nTris = 0, nSpheres = 0, nWideNodes = 0;
+    int maxDepth = 0;
+    float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0};
+};
+
+struct HostBvh {
+    std::vector<WideNode> nodes;   // nodes[0] is the root
+    std::vector<PrimRec> prims;    // leaf order
+    HostBvhStats stats;
+};
+
+// Validates the reference arrays (every index the device code will follow), derives the reference's
+// visiting order and builds the wide BVH.  Returns false with a message on malformed input.
+bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err);
+
+}   // namespace rtx

@@ -1,0 +1,287 @@
+// rt_wavefront.h — the wavefront split of the reference's two megakernels.
+//
+//   PrimaryVisibilityKernel (RTRay.cs:188-201)  ->  generate_primary + [extend] + primary_finish
+//   PathTraceKernel         (RTRay.cs:203-325)  ->  per sample batch:
+//        shade_first, then for every depth: [extend closest] + [extend shadow -> connect] + shade_next,
+//        then accumulate (per-pixel sum over samples in sample order, SafeColor, mean, PackRGBA8).
+//
+// Each function below is the body of one kernel for one work item; rt_kernels.cu wraps them in
+// grid-stride / persistent __global__ kernels, tests/hostsim wraps them in plain loops.
+// Per-path arithmetic order is exactly the reference's, so Li and the RNG stream are bit-identical
+// to a per-pixel loop no matter how the wavefront schedules the paths.
+#pragma once
+#include "rt_core.h"
+#include "rt_traverse.h"
+
+namespace rtx {
+
+struct FrameConst {
+    int width, height, frame, spp, maxDepth, rngLockNoise;
+    uint32_t flags;
+    f3 camOrigin, camLowerLeft, camHorizontal, camVertical;   // the four Camera fields the kernels read (RTUtils.cs:13-17)
+    LightEnv env;
+    int npx;                 // pixels owned by this context (whole image or its screen tiles)
+    const int* pixelMap;     // owned index -> global pixel index y*width+x (8x4 micro-tile order for ray coherence)
+};
+
+struct WaveBuffers {
+    // per owned pixel
+    float4 *gbPosHit, *gbNrmMat, *gbAlbObj;   // GpuGBuffer (RTRay.cs:80-109): worldPos|hitMask, normalWS|matId, baseColor|objId
+    int *primId, *instId; float* primaryT;    // parity taps of the primary hit
+    float4* lframe;                           // Lframe (RTRay.cs:208) across sample batches
+    float4* tileRadiance;                     // Lout per owned pixel, tile-compacted (multi-GPU gather payload)
+    // per global pixel
+    int* rgba8; float* depth; int* objId; float4* radiance; float4* accum;
+    // per path slot (path j = sampleInBatch * npx + ownedPixel)
+    float4* stThr;    // throughput.xyz | rng state
+    float4* stLi;     // Li.xyz | segCount (bits 0-7), terminator (bits 8-15)
+    uint32_t* pathHash;
+    // parity AOVs per (sample, global pixel); null unless RT_FLAG_PATH_AOVS
+    uint8_t *segCountOut, *termCodeOut; uint32_t* pathHashOut;
+};
+
+struct RayQueue { float4* o; float4* d; };                 // o.w = path slot (int bits)
+struct ShadowQueue { float4* o; float4* d; float4* c; };   // c.xyz = throughput * f_over_p * W
+
+RT_HD uint32_t fnv_fold(uint32_t h, uint32_t v) { return (h ^ v) * 16777619u; }
+
+// queue slot allocation: warp-aggregated atomic on the device, plain increment in the host simulator
+RT_HD int queue_alloc(int* counter) {
+#if defined(__CUDA_ARCH__)
+    const unsigned m = __activemask();
+    const int lane = (int)(threadIdx.x & 31u);
+    const int leader = __ffs((int)m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(m, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+#else
+    return (*counter)++;
+#endif
+}
+
+RT_HD void pixel_xy(const FrameConst& fc, int pix, int* x, int* y) { *x = pix % fc.width; *y = pix / fc.width; }   // RTRay.cs:122
+RT_HD f3 primary_dir(const FrameConst& fc, int x, int y) {   // GBufferParams.PrimaryRay RTRay.cs:120-126 + Ray.GenerateRay RTUtils.cs:13-17
+    float u = ((float)x + 0.5f) / (float)max(1, fc.width);
+    float v = ((float)y + 0.5f) / (float)max(1, fc.height);
+    return normalize(fc.camLowerLeft + fc.camHorizontal * u + fc.camVertical * v - fc.camOrigin);
+}
+
+// ------------------------------------------------------------------------------------------------ generate
+RT_HD void generate_primary(const FrameConst& fc, const RayQueue& q, int i) {
+    int x, y; pixel_xy(fc, fc.pixelMap[i], &x, &y);
+    f3 d = primary_dir(fc, x, y);
+    q.o[i] = make_float4(fc.camOrigin.x, fc.camOrigin.y, fc.camOrigin.z, u2f((uint32_t)i));
+    q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------ primary finish
+// PrimaryVisibilityKernel after TraceClosest (RTRay.cs:197-200) + GpuGBuffer.StoreHit/StoreMiss (:90-108);
+// also the depth / objectId halves of GpuFramebuffer.Store (:59-64, :324), which depend on the G-buffer only.
+RT_HD void primary_finish(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, const RayQueue& q, const HitRec* hits, int i) {
+    const float4 ro = q.o[i], rd = q.d[i];
+    const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
+    const HitRec h = hits[i];
+    const int pix = fc.pixelMap[i];
+    f3 pos; int oid;
+    if (!(h.t < 1e29f)) {
+        pos = o + d * 1e6f;
+        wb.gbPosHit[i] = make_float4(pos.x, pos.y, pos.z, u2f(0u));
+        wb.gbNrmMat[i] = make_float4(0.0f, 1.0f, 0.0f, u2f(0xFFFFFFFFu));
+        wb.gbAlbObj[i] = make_float4(0.0f, 0.0f, 0.0f, u2f(0xFFFFFFFFu));
+        wb.primId[i] = -1; wb.instId[i] = -1; wb.primaryT[i] = h.t;
+        oid = -1;
+    } else {
+        const Surface s = eval_surface(sc, o, d, h);
+        pos = o + d * h.t;
+        const int packedMat = (s.shade & 0xFFFF) | (float_to_i16(s.ior) << 16);
+        wb.gbPosHit[i] = make_float4(pos.x, pos.y, pos.z, u2f(1u));
+        wb.gbNrmMat[i] = make_float4(s.normal.x, s.normal.y, s.normal.z, u2f((uint32_t)packedMat));
+        wb.gbAlbObj[i] = make_float4(s.albedo.x, s.albedo.y, s.albedo.z, u2f((uint32_t)s.objId));
+        wb.primId[i] = s.primId; wb.instId[i] = s.instId; wb.primaryT[i] = h.t;
+        oid = s.objId;
+    }
+    const f3 dc = pos - fc.camOrigin;   // IntegratorParams.DistanceFromCamera RTRay.cs:158-162
+    wb.depth[pix] = sqrtf(dc.x * dc.x + dc.y * dc.y + dc.z * dc.z);
+    wb.objId[pix] = oid;
+}
+
+// ------------------------------------------------------------------------------------------------ shade
+struct PathVertex { f3 pos, nrm, alb, I; int shade; float ior; };
+
+// One iteration of the depth loop of PathTraceKernel up to (not including) TraceNext (RTRay.cs:233-317).
+// Pushes the continuation ray and, for a Lambert vertex, the ReSTIR-selected shadow ray.
+// Returns false when Russian roulette killed the path.
+RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, int path, f3& thr, uint32_t& rng,
+                        const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+    RayOD ray;
+    if (v.shade == RT_SHADING_MIRROR) {   // :235-244
+        f3 dirR = reflect3(v.I, v.nrm);
+        ray = make_ray_normal_offset(v.pos, v.nrm, dirR);
+        thr = thr * v.alb;
+    } else if (v.shade == RT_SHADING_GLASS) {   // :246-275
+        f3 Nuse = v.nrm;
+        bool outside = dot(v.I, v.nrm) < 0.0f;
+        if (!outside) Nuse = Nuse * -1.0f;
+        float etaI = outside ? 1.0f : (v.ior > 0.0f ? v.ior : 1.5f);
+        float etaT = outside ? (v.ior > 0.0f ? v.ior : 1.5f) : 1.0f;
+        f3 dirR = reflect3(v.I, Nuse);
+        f3 dirT;
+        bool refrOk = refract3(v.I, Nuse, etaI, etaT, &dirT);
+        float cosI = fabsf(dot(v.I, Nuse));
+        float Fr = schlick_fresnel(cosI, etaI, etaT);
+        float xi = rng_next_f(rng);
+        ray = (!refrOk || xi < Fr) ? make_ray_normal_offset(v.pos, Nuse, dirR) : make_ray_normal_offset(v.pos, neg(Nuse), dirT);
+        if (refrOk && xi >= Fr) {
+            f3 transTint = (v.alb.x == 0.0f && v.alb.y == 0.0f && v.alb.z == 0.0f) ? mk3(1.0f, 1.0f, 1.0f) : v.alb;
+            float etaScale = (etaI * etaI) / (etaT * etaT);
+            thr = thr * transTint * etaScale;
+        }
+    } else {   // Lambert: ReSTIR-DI + cosine bounce (:277-317)
+        f3 wiSel, contrib;
+        if (restir_direct_candidates(fc.env, v.nrm, v.alb, rng, &wiSel, &contrib)) {
+            RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
+            f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
+            int k = queue_alloc(shCount);
+            shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)path));
+            shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, 0.0f);
+            shQ.c[k] = make_float4(c.x, c.y, c.z, 0.0f);
+        }
+        f3 wi = sample_hemisphere_cosine(v.nrm, rng);   // :302
+        ray = make_ray_normal_offset(v.pos, v.nrm, wi);
+        thr = thr * v.alb;
+        if (depth >= 3) {   // :306-312
+            float maxC = fmaxf(thr.x, fmaxf(thr.y, thr.z));
+            maxC = fmaxf(fminf(maxC, 0.98f), 0.05f);   // XMath.Clamp
+            if (rng_next_f(rng) > maxC) { thr = mk3(0.0f, 0.0f, 0.0f); return false; }
+            thr = thr * (1.0f / maxC);
+        }
+    }
+    int k = queue_alloc(nextCount);
+    nextQ.o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f((uint32_t)path));
+    nextQ.d[k] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+    return true;
+}
+
+RT_HD uint32_t pack_aov(int seg, int term) { return (uint32_t)(seg & 0xFF) | ((uint32_t)(term & 0xFF) << 8); }
+
+// depth 0: start every path of the batch from the G-buffer (RTRay.cs:210-232)
+RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBase, int j,
+                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+    const int i = j % fc.npx;
+    const int s = sampleBase + j / fc.npx;
+    int x, y; pixel_xy(fc, fc.pixelMap[i], &x, &y);
+    uint32_t rng = rng_seed_pixel((uint32_t)x, (uint32_t)y, fc.frame, (uint32_t)s, 0xC0FFEEu, fc.rngLockNoise);   // :212
+    if (wb.pathHash) wb.pathHash[j] = 0x811C9DC5u;
+    const float4 ph = wb.gbPosHit[i];
+    if (f2u(ph.w) == 0u) {   // :214-219 — the sky for primary misses is added by accumulate()
+        wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_PRIMARY_MISS)));
+        return;
+    }
+    f3 thr = mk3(1.0f, 1.0f, 1.0f);
+    if (fc.maxDepth <= 0) {
+        wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_MAXDEPTH)));
+        return;
+    }
+    const float4 nm = wb.gbNrmMat[i], ao = wb.gbAlbObj[i];
+    PathVertex v;
+    v.pos = mk3(ph.x, ph.y, ph.z);
+    v.nrm = normalize(mk3(nm.x, nm.y, nm.z));          // :222
+    v.alb = mk3(ao.x, ao.y, ao.z);
+    const int packedMat = (int)f2u(nm.w);
+    v.shade = packedMat & 0xFFFF;                      // :225
+    v.ior = i16_to_float((packedMat >> 16) & 0xFFFF);  // :226
+    v.I = normalize(v.pos - fc.camOrigin);             // ViewDirFromCam :156,230
+    bool alive = shade_vertex(fc, v, 0, j, thr, rng, nextQ, nextCount, shQ, shCount);
+    wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
+    wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+}
+
+// depth >= 1: consume the closest-hit result of the ray traced at depth-1 (TraceNext, RTRay.cs:659-671) and shade the new vertex.
+RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, int depth,
+                      const RayQueue& curQ, const HitRec* hits, int k,
+                      const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+    const float4 ro = curQ.o[k], rd = curQ.d[k];
+    const int j = (int)f2u(ro.w);
+    const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
+    const HitRec h = hits[k];
+    const float4 st = wb.stThr[j];
+    float4 li4 = wb.stLi[j];
+    f3 thr = mk3(st.x, st.y, st.z), Li = mk3(li4.x, li4.y, li4.z);
+    uint32_t rng = f2u(st.w);
+    int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
+    if (!(h.t < 1e29f)) {   // miss: "Li += throughput * SkyWeighted(ray.dir); break" (:242,273,315)
+        Li = Li + thr * sky_weighted(fc.env, d);
+        if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
+        wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, RT_TERM_MISS)));
+        return;
+    }
+    if (wb.pathHash || depth < fc.maxDepth) {
+        const Surface s = eval_surface(sc, o, d, h);
+        if (wb.pathHash) wb.pathHash[j] = fnv_fold(fnv_fold(wb.pathHash[j], (uint32_t)s.instId), (uint32_t)s.primId);
+        if (depth < fc.maxDepth) {
+            PathVertex v;
+            v.pos = o + d * h.t;            // :665
+            v.nrm = normalize(s.normal);   // :666
+            v.alb = s.albedo; v.shade = s.shade; v.ior = s.ior;
+            v.I = d;                        // "I = ray.dir" :243,274,316
+            bool alive = shade_vertex(fc, v, depth, j, thr, rng, nextQ, nextCount, shQ, shCount);
+            wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
+            wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+            return;
+        }
+    }
+    // depth == maxDepth: the depth loop has run out (:233); nothing more is added
+    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, RT_TERM_MAXDEPTH)));
+}
+
+// connect: add the pending direct-light term of an unoccluded shadow ray (RTRay.cs:526-537, 286/291)
+RT_HD void connect_shadow(const WaveBuffers& wb, const ShadowQueue& shQ, int k, bool occluded) {
+    const int j = (int)f2u(shQ.o[k].w);
+    if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (occluded ? 0u : 1u));
+    if (occluded) return;
+    const float4 c = shQ.c[k];
+    float4 li4 = wb.stLi[j];
+    li4.x = li4.x + c.x; li4.y = li4.y + c.y; li4.z = li4.z + c.z;
+    wb.stLi[j] = li4;
+}
+
+// ------------------------------------------------------------------------------------------------ accumulate
+// "Lframe += SafeColor(Li)" over the samples of this batch in sample order (RTRay.cs:217,320); on the last
+// batch: Lout = Lframe / max(1,spp), float4 radiance, progressive accumulator and PackRGBA8 (:323-324, :66-76).
+RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBase, int nSamples, bool last, int i) {
+    const int pix = fc.pixelMap[i];
+    f3 L = mk3(0.0f, 0.0f, 0.0f);
+    if (sampleBase > 0) { const float4 l4 = wb.lframe[i]; L = mk3(l4.x, l4.y, l4.z); }
+    f3 skyMiss = mk3(0.0f, 0.0f, 0.0f);
+    const bool primaryMiss = f2u(wb.gbPosHit[i].w) == 0u;
+    if (primaryMiss) { int x, y; pixel_xy(fc, pix, &x, &y); skyMiss = safe_color(sky_weighted(fc.env, primary_dir(fc, x, y))); }   // :216-217
+    const size_t plane = (size_t)fc.width * (size_t)fc.height;
+    for (int s = 0; s < nSamples; s++) {
+        const int j = s * fc.npx + i;
+        const float4 li4 = wb.stLi[j];
+        L = L + (primaryMiss ? skyMiss : safe_color(mk3(li4.x, li4.y, li4.z)));
+        if (wb.segCountOut) {
+            const uint32_t a = f2u(li4.w);
+            const size_t oi = (size_t)(sampleBase + s) * plane + (size_t)pix;
+            wb.segCountOut[oi] = (uint8_t)(a & 0xFFu);
+            wb.termCodeOut[oi] = (uint8_t)((a >> 8) & 0xFFu);
+            wb.pathHashOut[oi] = wb.pathHash[j];
+        }
+    }
+    if (!last) { wb.lframe[i] = make_float4(L.x, L.y, L.z, 0.0f); return; }
+    const f3 Lout = L * (1.0f / (float)max(1, fc.spp));   // :323
+    wb.radiance[pix] = make_float4(Lout.x, Lout.y, Lout.z, 1.0f);
+    wb.tileRadiance[i] = make_float4(Lout.x, Lout.y, Lout.z, 1.0f);
+    f3 shown = Lout;
+    if (fc.flags & RT_FLAG_ACCUMULATE) {
+        float4 a = (fc.flags & RT_FLAG_RESET_ACCUM) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : wb.accum[pix];
+        a.x = a.x + Lout.x; a.y = a.y + Lout.y; a.z = a.z + Lout.z; a.w = a.w + 1.0f;
+        wb.accum[pix] = a;
+        const float inv = 1.0f / a.w;
+        shown = mk3(a.x * inv, a.y * inv, a.z * inv);
+    }
+    wb.rgba8[pix] = pack_rgba8(shown);
+}
+
+}   // namespace rtx

@@ -1,0 +1,656 @@
+// rtcore.cu — sm_100a kernels and the C-ABI implementation (include/rtcore_b200.h).
+//
+// Kernels (one per wavefront stage; bodies in rt_wavefront.h, traversal in rt_traverse.h):
+//   k_generate_primary   camera rays                         (RTUtils.cs:13-17, RTRay.cs:120-126)
+//   k_extend<ANY>        persistent-thread wide-BVH traversal (replaces SceneDeviceViews.cs:30-327)
+//   k_primary_finish     G-buffer + depth/objId              (RTRay.cs:90-108,188-201)
+//   k_shade_first/next   material switch, ReSTIR-DI candidates, bounce, RNG (RTRay.cs:203-317,438-543)
+//   k_accumulate         per-pixel sample sum, mean, float4 radiance, accumulator, PackRGBA8 (RTRay.cs:320-324,66-76)
+//   k_deinterleave       multi-GPU: scatter gathered tile payloads into the full image
+//
+// Compiled with --fmad=false: every mul/add below is a separate IEEE operation unless written rt_fma().
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_bvh.h"
+#include "rt_tiles.h"
+#include "rt_wavefront.h"
+
+using namespace rtx;
+
+// ------------------------------------------------------------------------------------------------ kernels
+#ifndef RT_EXTEND_THREADS
+#define RT_EXTEND_THREADS 128
+#endif
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 5
+#endif
+#define RT_EXTEND_BATCH 96   // ray indices a warp takes from the global queue per atomic
+
+struct DeviceStats {   // zeroed at the start of every rt_render
+    unsigned long long raysPrimary, raysBounce, raysShadow, wideNodes, tris, spheres;
+};
+
+struct ExtendArgs {
+    DeviceScene sc;
+    const float4* rayO; const float4* rayD;
+    const int* count;          // number of rays in the queue (device memory: written by the producing kernel)
+    int* work;                 // global fetch cursor for this launch (zeroed per frame)
+    HitRec* hits;              // closest: one record per ray
+    ShadowQueue shq;           // any-hit: the queue itself (o/d alias rayO/rayD) ...
+    WaveBuffers wb;            // ... and the path state connect() updates
+    DeviceStats* stats;
+    int statSlot;              // 0 primary, 1 bounce, 2 shadow
+};
+
+__global__ void k_generate_primary(FrameConst fc, RayQueue q, int* countOut) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) generate_primary(fc, q, i);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *countOut = fc.npx;
+}
+
+// Persistent threads: the grid is sized to the machine, every warp pulls RT_EXTEND_BATCH consecutive ray
+// indices per atomic and hands them to lanes as they go idle (ballot + popc rank), so a finished ray is
+// replaced at the next step instead of idling until the slowest lane of its batch is done.
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend(ExtendArgs a) {
+    extern __shared__ uint2 smemStack[];
+    LaneStack stack;
+    stack.smem = smemStack + threadIdx.x;
+    stack.stride = RT_EXTEND_THREADS;
+    stack.sp = 0;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = (int)(threadIdx.x & 31u);
+    const unsigned ltMask = (1u << lane) - 1u;
+    const int n = *a.count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long* slot = a.statSlot == 0 ? &a.stats->raysPrimary : (a.statSlot == 1 ? &a.stats->raysBounce : &a.stats->raysShadow);
+        atomicAdd(slot, (unsigned long long)n);
+    }
+    if (n <= 0 || a.sc.nNodes <= 0) {
+        if (!ANY_HIT) {   // empty scene: everything misses
+            const int stride = gridDim.x * blockDim.x;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { HitRec h; h.t = 1e30f; h.prim = -1; h.bu = 0.0f; h.bv = 0.0f; a.hits[i] = h; }
+        } else {
+            const int stride = gridDim.x * blockDim.x;
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) connect_shadow(a.wb, a.shq, i, false);
+        }
+        return;
+    }
+    Traversal<ANY_HIT, COUNT> tr;
+    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0; cnt.spheres = 0;
+    bool active = false, exhausted = false;
+    int myRay = -1;
+    int poolNext = 0, poolEnd = 0;   // warp-uniform
+
+    for (;;) {
+        // ---- refill idle lanes (warp-uniform control flow) ----
+        for (;;) {
+            const unsigned idle = __ballot_sync(FULL, !active);
+            if (idle == 0u || exhausted) break;
+            if (poolNext >= poolEnd) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(a.work, RT_EXTEND_BATCH);
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) { exhausted = true; break; }
+                poolNext = base;
+                poolEnd = min(base + RT_EXTEND_BATCH, n);
+            }
+            const int nIdle = __popc(idle);
+            const int take = min(nIdle, poolEnd - poolNext);
+            if (!active) {
+                const int r = __popc(idle & ltMask);
+                if (r < take) {
+                    myRay = poolNext + r;
+                    const float4 ro = __ldcs(a.rayO + myRay), rd = __ldcs(a.rayD + myRay);
+                    tr.init(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ANY_HIT ? 1e29f : 1e30f, stack);   // shadow tMax: RTRay.cs:623
+                    active = true;
+                }
+            }
+            poolNext += take;
+            if (take == nIdle) break;
+        }
+        if (__ballot_sync(FULL, active) == 0u) break;
+
+        // ---- one traversal step per active lane ----
+        if (active) {
+            if (tr.step(a.sc, stack, &cnt)) {
+                if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
+                else { const HitRec h = tr.result(); __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv)); }
+                active = false;
+            }
+        }
+    }
+    if (COUNT) {
+        unsigned nn = cnt.nodes, tt = cnt.tris, ss = cnt.spheres;
+        for (int o = 16; o > 0; o >>= 1) { nn += __shfl_xor_sync(FULL, nn, o); tt += __shfl_xor_sync(FULL, tt, o); ss += __shfl_xor_sync(FULL, ss, o); }
+        if (lane == 0) { atomicAdd(&a.stats->wideNodes, (unsigned long long)nn); atomicAdd(&a.stats->tris, (unsigned long long)tt); atomicAdd(&a.stats->spheres, (unsigned long long)ss); }
+    }
+}
+
+__global__ void k_primary_finish(FrameConst fc, DeviceScene sc, WaveBuffers wb, RayQueue q, const HitRec* hits) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) primary_finish(fc, sc, wb, q, hits, i);
+}
+
+__global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount);
+}
+
+__global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, const HitRec* hits, const int* curCount,
+                                                   RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
+    const int n = *curCount;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) shade_next(fc, sc, wb, depth, curQ, hits, k, nextQ, nextCount, shq, shCount);
+}
+
+__global__ void k_accumulate(FrameConst fc, WaveBuffers wb, int sampleBase, int nSamples, int last) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) accumulate(fc, wb, sampleBase, nSamples, last != 0, i);
+}
+
+__global__ void k_copy_color(const int* src, int* dst, const int* pixelMap, int npx) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) { const int p = pixelMap[i]; dst[p] = src[p]; }
+}
+
+// scatter a per-owned-pixel array to global pixel order (read-back of G-buffer / AOV taps)
+template <typename T> __global__ void k_scatter(const T* src, T* dst, const int* pixelMap, int npx) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) dst[pixelMap[i]] = src[i];
+}
+__global__ void k_scatter_f4_to_f3(const float4* src, float* dst, const int* pixelMap, int npx) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) { const float4 v = src[i]; const size_t p = (size_t)pixelMap[i] * 3; dst[p] = v.x; dst[p + 1] = v.y; dst[p + 2] = v.z; }
+}
+__global__ void k_scatter_f4_w(const float4* src, int* dst, const int* pixelMap, int npx) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) dst[pixelMap[i]] = __float_as_int(src[i].w);
+}
+
+// multi-GPU finish: payload[k] (float4 Lout of the k-th owned pixel of some rank) -> full image
+__global__ void k_deinterleave(const float4* payload, const int* pixelMap, int npx, float4* outRadiance, int* outRgba8) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) {
+        const float4 v = __ldcs(payload + i);
+        const int p = pixelMap[i];
+        if (outRadiance) outRadiance[p] = v;
+        if (outRgba8) outRgba8[p] = pack_rgba8(mk3(v.x, v.y, v.z));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static thread_local std::string g_lastError;
+static int fail(int code, const std::string& msg) { g_lastError = msg; return code; }
+#define CUDA_TRY(expr)                                                                                                 \
+    do {                                                                                                               \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess) return fail(_e == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA,       \
+                                           std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; n = 0; }
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+struct rt_ctx {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t ownStream = nullptr, stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    bool rendered = false, hasScene = false;
+
+    // scene
+    DevBuf<WideNode> nodes; DevBuf<PrimRec> prims; DevBuf<RtInstanceRecord> instances; DevBuf<RtSphere> spheres;
+    DevBuf<RtFloat2> texcoords; DevBuf<RtMeshTriUV> triUVs; DevBuf<int32_t> triMat; DevBuf<RtMaterialRecord> materials;
+    DevBuf<RtRGBA32> texels; DevBuf<RtTexInfo> texInfos;
+    DeviceScene ds;
+    HostBvhStats bvhStats; size_t bvhBytes = 0;
+
+    // frame geometry
+    int width = 0, height = 0, tileSize = 0, rank = 0, worldSize = 1, npx = 0, spp = 1;
+    bool aovs = false;
+    DevBuf<int> pixelMap;
+    // per owned pixel
+    DevBuf<float4> gbPosHit, gbNrmMat, gbAlbObj, lframe, tileRadiance; DevBuf<int> primId, instId; DevBuf<float> primaryT;
+    // per global pixel
+    DevBuf<int> rgba8, objId; DevBuf<float> depth; DevBuf<float4> radiance, accum;
+    // per path
+    size_t pathCap = 0;
+    DevBuf<float4> stThr, stLi, qO[2], qD[2], shO, shD, shC; DevBuf<HitRec> hits; DevBuf<uint32_t> pathHash;
+    // AOV outputs
+    DevBuf<uint8_t> segOut, termOut; DevBuf<uint32_t> hashOut;
+    // scratch for scattered read-backs
+    DevBuf<float> scratch;
+    // counters
+    DevBuf<int> counters; DevBuf<DeviceStats> dstats;
+    DeviceStats hstats; unsigned long long launches = 0;
+    // kernel timing (extend kernels)
+    std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool timeKernels = false;
+    int* extColor = nullptr; size_t extColorBytes = 0;
+    int extendBlocks = 0;
+    size_t extendSmem = 0;
+};
+
+template <typename T> static cudaError_t upload_or_one(DevBuf<T>& dst, const T* src, int64_t n, cudaStream_t st, int* lenOut) {
+    // AllocateOrEmpty (Scene.cs:370-377): an empty array becomes one zeroed element
+    size_t cnt = (src && n > 0) ? (size_t)n : 1;
+    cudaError_t e = dst.ensure(cnt);
+    if (e != cudaSuccess) return e;
+    if (src && n > 0) e = cudaMemcpyAsync(dst.p, src, cnt * sizeof(T), cudaMemcpyHostToDevice, st);
+    else e = cudaMemsetAsync(dst.p, 0, sizeof(T), st);
+    if (lenOut) *lenOut = (int)cnt;
+    return e;
+}
+
+static cudaError_t trace_event(rt_ctx* c) {
+    if (!c->timeKernels) return cudaSuccess;
+    if (c->traceEventsUsed == c->traceEvents.size()) { cudaEvent_t ev; cudaError_t e = cudaEventCreate(&ev); if (e != cudaSuccess) return e; c->traceEvents.push_back(ev); }
+    return cudaEventRecord(c->traceEvents[c->traceEventsUsed++], c->stream);
+}
+
+template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs& a, bool count) {
+    cudaError_t e = trace_event(c);
+    if (e != cudaSuccess) return e;
+    if (count) k_extend<ANY, true><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
+    else k_extend<ANY, false><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
+    c->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return trace_event(c);
+}
+
+extern "C" {
+
+RT_API int rt_abi_version(void) { return RT_ABI_VERSION; }
+RT_API const char* rt_last_error(void) { return g_lastError.c_str(); }
+
+RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
+    if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_create: out is null");
+    *out = nullptr;
+    if (nDev != 1 && !(nDev == 0 && deviceIds == nullptr))
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_create: one context drives one GPU (nDev must be 1); use one process per GPU for multi-GPU");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return fail(RT_ERR_NO_DEVICE, std::string("rt_create: no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU fallback");
+    int dev = (deviceIds && nDev == 1) ? deviceIds[0] : 0;
+    if (dev < 0 || dev >= count) return fail(RT_ERR_INVALID_ARGUMENT, "rt_create: device index out of range");
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10) return fail(RT_ERR_NO_DEVICE, std::string("rt_create: device '") + prop.name + "' is not sm_100 class; the kernels are built for sm_100a only");
+    CUDA_TRY(cudaSetDevice(dev));
+    rt_ctx* c = new rt_ctx();
+    c->device = dev; c->smCount = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+    c->stream = c->ownStream;
+    CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
+    c->extendSmem = (size_t)RT_SMEM_STACK * RT_EXTEND_THREADS * sizeof(uint2);
+    int perSm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
+    if (perSm < 1) perSm = 1;
+    c->extendBlocks = perSm * c->smCount;
+    memset(&c->ds, 0, sizeof(c->ds)); memset(&c->hstats, 0, sizeof(c->hstats));
+    *out = c;
+    return RT_OK;
+}
+
+RT_API int rt_destroy(rt_ctx* c) {
+    if (!c) return RT_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->nodes.release(); c->prims.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
+    c->materials.release(); c->texels.release(); c->texInfos.release(); c->pixelMap.release();
+    c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
+    c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
+    c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); } c->shO.release(); c->shD.release(); c->shC.release();
+    c->hits.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release();
+    for (auto ev : c->traceEvents) cudaEventDestroy(ev);
+    if (c->evStart) cudaEventDestroy(c->evStart);
+    if (c->evStop) cudaEventDestroy(c->evStop);
+    if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    delete c;
+    return RT_OK;
+}
+
+RT_API int rt_set_stream(rt_ctx* c, void* s) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_set_stream: ctx is null");
+    c->stream = s ? (cudaStream_t)s : c->ownStream;
+    return RT_OK;
+}
+
+RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
+    if (!c || !d) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: null argument");
+    const void* ptrs[15] = {d->tlasNodes, d->tlasInstanceIndices, d->instances, d->blasNodes, d->spherePrimIdx, d->spheres, d->triPrimIdx, d->meshPositions,
+                            d->meshTris, d->meshTexcoords, d->meshTriUVs, d->triMatIndex, d->materials, d->texels, d->texInfos};
+    const int64_t cnts[15] = {d->nTlasNodes, d->nTlasInstanceIndices, d->nInstances, d->nBlasNodes, d->nSpherePrimIdx, d->nSpheres, d->nTriPrimIdx, d->nMeshPositions,
+                              d->nMeshTris, d->nMeshTexcoords, d->nMeshTriUVs, d->nTriMatIndex, d->nMaterials, d->nTexels, d->nTexInfos};
+    for (int i = 0; i < 15; i++) {
+        if (cnts[i] < 0 || cnts[i] > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: array length out of range");
+        if (cnts[i] > 0 && !ptrs[i]) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: null array with non-zero length");
+    }
+    for (int64_t i = 0; i < d->nTexInfos; i++) {
+        const RtTexInfo& ti = d->texInfos[i];
+        if (ti.Width > 0 && ti.Height > 0 && (ti.Offset < 0 || (int64_t)ti.Offset + (int64_t)ti.Width * ti.Height > d->nTexels))
+            return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: texInfos entry addresses texels out of range");
+    }
+    HostBvh bvh; std::string err;
+    if (!build_wide_bvh(*d, bvh, err)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // nothing in flight may still read the old scene
+    cudaStream_t st = c->stream;
+    DeviceScene& ds = c->ds;
+    CUDA_TRY(c->nodes.ensure(std::max<size_t>(1, bvh.nodes.size())));
+    CUDA_TRY(c->prims.ensure(std::max<size_t>(1, bvh.prims.size())));
+    if (!bvh.nodes.empty()) CUDA_TRY(cudaMemcpyAsync(c->nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, st));
+    if (!bvh.prims.empty()) CUDA_TRY(cudaMemcpyAsync(c->prims.p, bvh.prims.data(), bvh.prims.size() * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
+    ds.nodes = c->nodes.p; ds.nNodes = bvh.prims.empty() ? 0 : (int)bvh.nodes.size(); ds.prims = c->prims.p; ds.nPrims = (int)bvh.prims.size();
+    CUDA_TRY(upload_or_one(c->instances, d->instances, d->nInstances, st, &ds.nInstances)); ds.instances = c->instances.p;
+    CUDA_TRY(upload_or_one(c->spheres, d->spheres, d->nSpheres, st, &ds.nSpheres)); ds.spheres = c->spheres.p;
+    CUDA_TRY(upload_or_one(c->texcoords, d->meshTexcoords, d->nMeshTexcoords, st, nullptr)); ds.texcoords = c->texcoords.p;
+    CUDA_TRY(upload_or_one(c->triUVs, d->meshTriUVs, d->nMeshTriUVs, st, nullptr)); ds.triUVs = c->triUVs.p;
+    CUDA_TRY(upload_or_one(c->triMat, d->triMatIndex, d->nTriMatIndex, st, nullptr)); ds.triMatIndex = c->triMat.p;
+    CUDA_TRY(upload_or_one(c->materials, d->materials, d->nMaterials, st, &ds.nMaterials)); ds.materials = c->materials.p;
+    CUDA_TRY(upload_or_one(c->texels, d->texels, d->nTexels, st, nullptr)); ds.texels = c->texels.p;
+    CUDA_TRY(upload_or_one(c->texInfos, d->texInfos, d->nTexInfos, st, &ds.nTexInfos)); ds.texInfos = c->texInfos.p;
+    ds.triMaterials = 0;
+    CUDA_TRY(cudaStreamSynchronize(st));   // host arrays are only borrowed for the duration of the call
+    c->bvhStats = bvh.stats;
+    c->bvhBytes = bvh.nodes.size() * sizeof(WideNode) + bvh.prims.size() * sizeof(PrimRec);
+    c->hasScene = true;
+    return RT_OK;
+}
+
+static inline int grid_for(const rt_ctx* c, size_t n, int threads) {
+    size_t blocks = (n + threads - 1) / threads;
+    size_t cap = (size_t)c->smCount * 16;
+    return (int)std::max<size_t>(1, std::min(blocks, cap));
+}
+
+static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
+    const int W = cfg->width, H = cfg->height;
+    const int T = effective_tile_size(cfg->tileSize);
+    const int world = cfg->worldSize > 1 ? cfg->worldSize : 1;
+    const int rank = world > 1 ? cfg->rank : 0;
+    if (c->width != W || c->height != H || c->tileSize != T || c->rank != rank || c->worldSize != world || !c->pixelMap.p) {
+        std::vector<int> pm; build_pixel_map(W, H, T, rank, world, pm);
+        CUDA_TRY(c->pixelMap.ensure(std::max<size_t>(1, pm.size())));
+        if (!pm.empty()) CUDA_TRY(cudaMemcpyAsync(c->pixelMap.p, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->width = W; c->height = H; c->tileSize = T; c->rank = rank; c->worldSize = world; c->npx = (int)pm.size();
+        const size_t n = std::max<size_t>(1, (size_t)c->npx), g = (size_t)W * H;
+        CUDA_TRY(c->gbPosHit.ensure(n)); CUDA_TRY(c->gbNrmMat.ensure(n)); CUDA_TRY(c->gbAlbObj.ensure(n)); CUDA_TRY(c->lframe.ensure(n)); CUDA_TRY(c->tileRadiance.ensure(n));
+        CUDA_TRY(c->primId.ensure(n)); CUDA_TRY(c->instId.ensure(n)); CUDA_TRY(c->primaryT.ensure(n));
+        CUDA_TRY(c->rgba8.ensure(g)); CUDA_TRY(c->objId.ensure(g)); CUDA_TRY(c->depth.ensure(g)); CUDA_TRY(c->radiance.ensure(g)); CUDA_TRY(c->accum.ensure(g));
+        CUDA_TRY(cudaMemsetAsync(c->rgba8.p, 0, g * sizeof(int), c->stream)); CUDA_TRY(cudaMemsetAsync(c->objId.p, 0, g * sizeof(int), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->depth.p, 0, g * sizeof(float), c->stream)); CUDA_TRY(cudaMemsetAsync(c->radiance.p, 0, g * sizeof(float4), c->stream));
+        CUDA_TRY(cudaMemsetAsync(c->accum.p, 0, g * sizeof(float4), c->stream));
+    }
+    const size_t P = std::max<size_t>(1, (size_t)c->npx * S);
+    if (P > c->pathCap) {
+        CUDA_TRY(c->stThr.ensure(P)); CUDA_TRY(c->stLi.ensure(P));
+        for (int b = 0; b < 2; b++) { CUDA_TRY(c->qO[b].ensure(P)); CUDA_TRY(c->qD[b].ensure(P)); }
+        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->shC.ensure(P)); CUDA_TRY(c->hits.ensure(P));
+        c->pathCap = P;
+    }
+    c->aovs = (cfg->flags & RT_FLAG_PATH_AOVS) != 0;
+    c->spp = cfg->spp > 1 ? cfg->spp : 1;
+    if (c->aovs) {
+        const size_t g = (size_t)W * H * c->spp;
+        CUDA_TRY(c->pathHash.ensure(P)); CUDA_TRY(c->segOut.ensure(g)); CUDA_TRY(c->termOut.ensure(g)); CUDA_TRY(c->hashOut.ensure(g));
+        CUDA_TRY(cudaMemsetAsync(c->segOut.p, 0, g, c->stream)); CUDA_TRY(cudaMemsetAsync(c->termOut.p, 0, g, c->stream)); CUDA_TRY(cudaMemsetAsync(c->hashOut.p, 0, g * 4, c->stream));
+    }
+    return RT_OK;
+}
+
+RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, const RtRenderConfig* cfg) {
+    (void)prevCam;
+    if (!c || !cam || !cfg) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null argument");
+    if (!c->hasScene) return fail(RT_ERR_INVALID_STATE, "rt_render: no scene uploaded (call rt_scene_upload first)");
+    if (cfg->width <= 0 || cfg->height <= 0 || (int64_t)cfg->width * cfg->height > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: bad image size");
+    if (cfg->maxDepth < 0 || cfg->maxDepth > 255) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: maxDepth must be in [0, 255]");
+    if (cfg->worldSize > 1 && (cfg->rank < 0 || cfg->rank >= cfg->worldSize)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: rank outside [0, worldSize)");
+    if (cfg->enableTemporalReuse || cfg->enableSpatialReuse)
+        return fail(RT_ERR_UNSUPPORTED, "rt_render: ReSTIR temporal/spatial reuse (RTRay.cs:476-516) is not built yet; pass enableTemporalReuse = enableSpatialReuse = 0");
+    CUDA_TRY(cudaSetDevice(c->device));
+
+    const int spp = cfg->spp > 1 ? cfg->spp : 1;
+    const int64_t npxOwned = count_owned_pixels(cfg->width, cfg->height, cfg->tileSize, cfg->worldSize > 1 ? cfg->rank : 0, cfg->worldSize > 1 ? cfg->worldSize : 1);
+    int S = cfg->samplesPerPass;
+    if (S <= 0) { const int64_t target = 16ll << 20; S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned))); }
+    S = std::min(S, spp);
+    if ((int64_t)npxOwned * S > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: samplesPerPass * pixels exceeds 2^31 paths");
+    int rc = ensure_frame_buffers(c, cfg, S);
+    if (rc != RT_OK) return rc;
+    const int npx = c->npx;
+    const int nPasses = (spp + S - 1) / S;
+    const bool count = (cfg->flags & RT_FLAG_COUNTERS) != 0;
+    c->timeKernels = count;   // per-launch event pairs around the extend kernels (roofline measurements)
+    c->traceEventsUsed = 0;
+    c->launches = 0;
+    c->ds.triMaterials = (cfg->flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
+
+    // device counters: [0] primary ray count, then per (pass, depth): nextCount, shCount, workClosest, workShadow; +1 work cursor for primary
+    const size_t nCounters = 2 + (size_t)nPasses * (cfg->maxDepth + 1) * 4;
+    CUDA_TRY(c->counters.ensure(nCounters));
+    CUDA_TRY(c->dstats.ensure(1));
+    cudaStream_t st = c->stream;
+    CUDA_TRY(cudaEventRecord(c->evStart, st));
+    CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, nCounters * sizeof(int), st));
+    CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, sizeof(DeviceStats), st));
+
+    FrameConst fc; memset(&fc, 0, sizeof(fc));
+    fc.width = cfg->width; fc.height = cfg->height; fc.frame = cfg->frame; fc.spp = cfg->spp; fc.maxDepth = cfg->maxDepth; fc.rngLockNoise = cfg->rngLockNoise; fc.flags = cfg->flags;
+    fc.camOrigin = mk3(cam->origin); fc.camLowerLeft = mk3(cam->lowerLeft); fc.camHorizontal = mk3(cam->horizontal); fc.camVertical = mk3(cam->vertical);
+    fc.env.dirLightDir = mk3(cfg->dirLightDir); fc.env.dirLightRadiance = mk3(cfg->dirLightRadiance); fc.env.skyTop = mk3(cfg->skyTintTop); fc.env.skyBottom = mk3(cfg->skyTintBottom);
+    fc.npx = npx; fc.pixelMap = c->pixelMap.p;
+
+    WaveBuffers wb; memset(&wb, 0, sizeof(wb));
+    wb.gbPosHit = c->gbPosHit.p; wb.gbNrmMat = c->gbNrmMat.p; wb.gbAlbObj = c->gbAlbObj.p; wb.primId = c->primId.p; wb.instId = c->instId.p; wb.primaryT = c->primaryT.p;
+    wb.lframe = c->lframe.p; wb.tileRadiance = c->tileRadiance.p; wb.rgba8 = c->rgba8.p; wb.depth = c->depth.p; wb.objId = c->objId.p; wb.radiance = c->radiance.p; wb.accum = c->accum.p;
+    wb.stThr = c->stThr.p; wb.stLi = c->stLi.p;
+    if (c->aovs) { wb.pathHash = c->pathHash.p; wb.segCountOut = c->segOut.p; wb.termCodeOut = c->termOut.p; wb.pathHashOut = c->hashOut.p; }
+
+    if (npx > 0) {
+        // ---- primary visibility -------------------------------------------------------------------------------------
+        RayQueue q0 = {c->qO[0].p, c->qD[0].p};
+        int* primaryCount = c->counters.p + 0;
+        int* primaryWork = c->counters.p + 1;
+        k_generate_primary<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, q0, primaryCount); c->launches++;
+        ExtendArgs ea; memset(&ea, 0, sizeof(ea));
+        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = c->hits.p; ea.wb = wb; ea.stats = c->dstats.p; ea.statSlot = 0;
+        CUDA_TRY(launch_extend<false>(c, ea, count));
+        k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, c->hits.p); c->launches++;
+
+        // ---- integrator: batches of S samples, one wavefront iteration per depth ---------------------------------
+        ShadowQueue shq = {c->shO.p, c->shD.p, c->shC.p};
+        for (int pass = 0; pass < nPasses; pass++) {
+            const int s0 = pass * S, ns = std::min(S, spp - s0);
+            const size_t nPaths = (size_t)npx * ns;
+            int* ctr = c->counters.p + 2 + (size_t)pass * (cfg->maxDepth + 1) * 4;
+            int cur = 0;
+            RayQueue nq = {c->qO[cur].p, c->qD[cur].p};
+            k_shade_first<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1); c->launches++;
+            for (int depth = 1; depth <= cfg->maxDepth; depth++) {
+                int* prev = ctr + (size_t)(depth - 1) * 4;   // counts produced by the shade of depth-1
+                int* mine = ctr + (size_t)depth * 4;
+                RayQueue cq = {c->qO[cur].p, c->qD[cur].p};
+                ExtendArgs sa; memset(&sa, 0, sizeof(sa));
+                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.count = prev + 1; sa.work = prev + 3; sa.shq = shq; sa.wb = wb; sa.stats = c->dstats.p; sa.statSlot = 2;
+                CUDA_TRY(launch_extend<true>(c, sa, count));
+                ExtendArgs ca; memset(&ca, 0, sizeof(ca));
+                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
+                CUDA_TRY(launch_extend<false>(c, ca, count));
+                RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p};
+                k_shade_next<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1); c->launches++;
+                cur ^= 1;
+            }
+            k_accumulate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
+        }
+        if (c->extColor) {
+            if (c->extColorBytes < (size_t)cfg->width * cfg->height * sizeof(int)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: mapped external colour buffer is smaller than the image");
+            k_copy_color<<<grid_for(c, npx, 256), 256, 0, st>>>(c->rgba8.p, c->extColor, c->pixelMap.p, npx); c->launches++;
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(c->evStop, st));
+    CUDA_TRY(cudaMemcpyAsync(&c->hstats, c->dstats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
+    c->rendered = true;
+    return RT_OK;
+}
+
+RT_API int rt_sync(rt_ctx* c) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_sync: ctx is null");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return RT_OK;
+}
+
+static int buffer_info(rt_ctx* c, int which, size_t* bytes) {
+    const size_t g = (size_t)c->width * c->height;
+    switch (which) {
+        case RT_BUF_RGBA8: case RT_BUF_OBJID: case RT_BUF_PRIM_ID: case RT_BUF_INST_ID: case RT_BUF_GB_MATID: *bytes = g * 4; return RT_OK;
+        case RT_BUF_DEPTH: case RT_BUF_PRIMARY_T: *bytes = g * 4; return RT_OK;
+        case RT_BUF_RADIANCE: case RT_BUF_ACCUM: *bytes = g * 16; return RT_OK;
+        case RT_BUF_GB_WORLDPOS: case RT_BUF_GB_NORMAL: case RT_BUF_GB_BASECOLOR: *bytes = g * 12; return RT_OK;
+        case RT_BUF_SEG_COUNT: case RT_BUF_TERM_CODE: *bytes = g * c->spp; return RT_OK;
+        case RT_BUF_PATH_HASH: *bytes = g * c->spp * 4; return RT_OK;
+        case RT_BUF_TILE_RADIANCE: *bytes = (size_t)c->npx * 16; return RT_OK;
+    }
+    return fail(RT_ERR_INVALID_ARGUMENT, "unknown buffer selector");
+}
+
+RT_API int rt_buffer_bytes(rt_ctx* c, int which, size_t* bytes) {
+    if (!c || !bytes) return fail(RT_ERR_INVALID_ARGUMENT, "rt_buffer_bytes: null argument");
+    if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_buffer_bytes: nothing rendered yet");
+    return buffer_info(c, which, bytes);
+}
+
+RT_API int rt_get_device_buffer(rt_ctx* c, int which, void** devPtr, size_t* bytes) {
+    if (!c || !devPtr || !bytes) return fail(RT_ERR_INVALID_ARGUMENT, "rt_get_device_buffer: null argument");
+    if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_get_device_buffer: nothing rendered yet");
+    int rc = buffer_info(c, which, bytes);
+    if (rc != RT_OK) return rc;
+    switch (which) {
+        case RT_BUF_RGBA8: *devPtr = c->rgba8.p; return RT_OK;
+        case RT_BUF_DEPTH: *devPtr = c->depth.p; return RT_OK;
+        case RT_BUF_OBJID: *devPtr = c->objId.p; return RT_OK;
+        case RT_BUF_RADIANCE: *devPtr = c->radiance.p; return RT_OK;
+        case RT_BUF_ACCUM: *devPtr = c->accum.p; return RT_OK;
+        case RT_BUF_TILE_RADIANCE: *devPtr = c->tileRadiance.p; return RT_OK;
+        case RT_BUF_SEG_COUNT: if (!c->aovs) break; *devPtr = c->segOut.p; return RT_OK;
+        case RT_BUF_TERM_CODE: if (!c->aovs) break; *devPtr = c->termOut.p; return RT_OK;
+        case RT_BUF_PATH_HASH: if (!c->aovs) break; *devPtr = c->hashOut.p; return RT_OK;
+        default: return fail(RT_ERR_UNSUPPORTED, "rt_get_device_buffer: this buffer is stored per owned pixel; use rt_download");
+    }
+    return fail(RT_ERR_INVALID_STATE, "rt_get_device_buffer: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
+}
+
+RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
+    if (!c || !dst) return fail(RT_ERR_INVALID_ARGUMENT, "rt_download: null argument");
+    if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_download: nothing rendered yet");
+    size_t need = 0;
+    int rc = buffer_info(c, which, &need);
+    if (rc != RT_OK) return rc;
+    if (bytes != need) return fail(RT_ERR_INVALID_ARGUMENT, "rt_download: bytes does not match the buffer size");
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    const void* src = nullptr;
+    const int npx = c->npx;
+    const size_t g = (size_t)c->width * c->height;
+    auto scatterPrep = [&](size_t floats) -> cudaError_t {
+        cudaError_t e = c->scratch.ensure(floats);
+        if (e != cudaSuccess) return e;
+        return cudaMemsetAsync(c->scratch.p, 0, floats * sizeof(float), st);
+    };
+    switch (which) {
+        case RT_BUF_RGBA8: src = c->rgba8.p; break;
+        case RT_BUF_DEPTH: src = c->depth.p; break;
+        case RT_BUF_OBJID: src = c->objId.p; break;
+        case RT_BUF_RADIANCE: src = c->radiance.p; break;
+        case RT_BUF_ACCUM: src = c->accum.p; break;
+        case RT_BUF_TILE_RADIANCE: src = c->tileRadiance.p; break;
+        case RT_BUF_SEG_COUNT: case RT_BUF_TERM_CODE: case RT_BUF_PATH_HASH:
+            if (!c->aovs) return fail(RT_ERR_INVALID_STATE, "rt_download: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
+            src = which == RT_BUF_SEG_COUNT ? (const void*)c->segOut.p : (which == RT_BUF_TERM_CODE ? (const void*)c->termOut.p : (const void*)c->hashOut.p);
+            break;
+        case RT_BUF_PRIM_ID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<int><<<grid_for(c, npx, 256), 256, 0, st>>>(c->primId.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_INST_ID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<int><<<grid_for(c, npx, 256), 256, 0, st>>>(c->instId.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_PRIMARY_T: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<float><<<grid_for(c, npx, 256), 256, 0, st>>>(c->primaryT.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_WORLDPOS: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbPosHit.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_NORMAL: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbNrmMat.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_BASECOLOR: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbAlbObj.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_MATID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter_f4_w<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbNrmMat.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        default: return fail(RT_ERR_INVALID_ARGUMENT, "rt_download: unknown buffer selector");
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+RT_API int rt_map_external_color(rt_ctx* c, void* devPtr, size_t bytes) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_map_external_color: ctx is null");
+    c->extColor = (int*)devPtr; c->extColorBytes = devPtr ? bytes : 0;
+    return RT_OK;
+}
+
+RT_API int rt_tiles_owned_pixels(int width, int height, int tileSize, int rank, int worldSize, int64_t* nPixels) {
+    if (!nPixels || width <= 0 || height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_tiles_owned_pixels: bad argument");
+    if (worldSize > 1 && (rank < 0 || rank >= worldSize)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_tiles_owned_pixels: rank outside [0, worldSize)");
+    *nPixels = count_owned_pixels(width, height, tileSize, worldSize > 1 ? rank : 0, worldSize > 1 ? worldSize : 1);
+    return RT_OK;
+}
+
+RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64_t* rankOffsetsPx, int worldSize, int width, int height, int tileSize,
+                                 void* outRadianceDev, void* outRgba8Dev) {
+    if (!c || !gatheredDev || !rankOffsetsPx || worldSize < 1 || width <= 0 || height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_deinterleave_tiles: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    DevBuf<int> pm;
+    for (int r = 0; r < worldSize; r++) {
+        std::vector<int> m; build_pixel_map(width, height, tileSize, r, worldSize, m);
+        if (m.empty()) continue;
+        CUDA_TRY(pm.ensure(m.size()));
+        CUDA_TRY(cudaMemcpyAsync(pm.p, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        k_deinterleave<<<grid_for(c, m.size(), 256), 256, 0, c->stream>>>((const float4*)gatheredDev + rankOffsetsPx[r], pm.p, (int)m.size(), (float4*)outRadianceDev, (int*)outRgba8Dev);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // m / pm are reused by the next rank
+    }
+    pm.release();
+    return RT_OK;
+}
+
+RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
+    if (!c || !out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_get_stats: null argument");
+    memset(out, 0, sizeof(*out));
+    out->bvhWideNodeCount = (uint64_t)c->bvhStats.nWideNodes; out->bvhPrimCount = (uint64_t)c->bvhStats.nPrims; out->bvhBytes = (uint64_t)c->bvhBytes;
+    if (!c->rendered) return RT_OK;
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    out->raysPrimary = c->hstats.raysPrimary; out->raysBounce = c->hstats.raysBounce; out->raysShadow = c->hstats.raysShadow;
+    out->wideNodes = c->hstats.wideNodes; out->trisTested = c->hstats.tris; out->spheresTested = c->hstats.spheres;
+    out->kernelLaunches = c->launches;
+    float ms = 0.0f;
+    if (cudaEventElapsedTime(&ms, c->evStart, c->evStop) == cudaSuccess) out->lastRenderMs = ms;
+    float tr = 0.0f;
+    for (size_t i = 0; i + 1 < c->traceEventsUsed; i += 2) { float m = 0.0f; if (cudaEventElapsedTime(&m, c->traceEvents[i], c->traceEvents[i + 1]) == cudaSuccess) tr += m; }
+    out->lastTraceMs = tr;
+    out->reserved[0] = (uint64_t)(c->traceEventsUsed / 2);   // number of extend launches timed
+    return RT_OK;
+}
+
+}   // extern "C"

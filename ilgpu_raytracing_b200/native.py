@@ -1,0 +1,153 @@
+"""ctypes binding of the C ABI (include/rtcore_b200.h) — the same entry points the C# P/Invoke layer binds.
+
+The library is loaded from the package directory.  There is no fallback of any kind: a missing
+library or a machine without an sm_100 CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import layouts as L
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_PKG, "librtcore_b200.so")
+
+EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
+           "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
+           "rt_deinterleave_tiles", "rt_get_stats"]
+
+
+class RtError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"rtcore_b200 status {status}: {message}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise ImportError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). The renderer core has no CPU or pure-Python fallback.")
+    l = C.CDLL(_LIB_PATH)
+    l.rt_abi_version.restype = C.c_int
+    l.rt_last_error.restype = C.c_char_p
+    l.rt_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+    l.rt_destroy.argtypes = [C.c_void_p]
+    l.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    l.rt_scene_upload.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
+    l.rt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig)]
+    l.rt_sync.argtypes = [C.c_void_p]
+    l.rt_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
+    l.rt_buffer_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
+    l.rt_get_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    l.rt_map_external_color.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    l.rt_tiles_owned_pixels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
+    l.rt_deinterleave_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    l.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(L.RtStats)]
+    for name in EXPORTS:
+        if name not in ("rt_last_error",):
+            getattr(l, name).restype = C.c_int
+    l.rt_last_error.restype = C.c_char_p
+    _lib = l
+    return l
+
+
+def check(status: int) -> None:
+    if status != L.RT_OK:
+        raise RtError(status, (lib().rt_last_error() or b"").decode(errors="replace"))
+
+
+_BUF_DTYPES = {L.RT_BUF_RGBA8: (np.int32, 1), L.RT_BUF_DEPTH: (np.float32, 1), L.RT_BUF_OBJID: (np.int32, 1), L.RT_BUF_RADIANCE: (np.float32, 4),
+               L.RT_BUF_ACCUM: (np.float32, 4), L.RT_BUF_PRIM_ID: (np.int32, 1), L.RT_BUF_INST_ID: (np.int32, 1), L.RT_BUF_PRIMARY_T: (np.float32, 1),
+               L.RT_BUF_SEG_COUNT: (np.uint8, 1), L.RT_BUF_TERM_CODE: (np.uint8, 1), L.RT_BUF_PATH_HASH: (np.uint32, 1),
+               L.RT_BUF_GB_WORLDPOS: (np.float32, 3), L.RT_BUF_GB_NORMAL: (np.float32, 3), L.RT_BUF_GB_BASECOLOR: (np.float32, 3),
+               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4)}
+
+
+class Context:
+    """Owns one rt_ctx (one GPU)."""
+
+    def __init__(self, device: int = 0):
+        self._l = lib()
+        self.h = C.c_void_p()
+        dev = (C.c_int * 1)(device)
+        check(self._l.rt_create(dev, 1, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self._l.rt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr: int | None):
+        check(self._l.rt_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def scene_upload(self, arrays: dict):
+        desc, keep = L.scene_desc_from_arrays(arrays)
+        check(self._l.rt_scene_upload(self.h, C.byref(desc)))
+        del keep
+
+    def scene_upload_desc(self, desc: L.RtSceneDesc):
+        check(self._l.rt_scene_upload(self.h, C.byref(desc)))
+
+    def render(self, cam: np.ndarray, cfg: L.RtRenderConfig, prev_cam: np.ndarray | None = None):
+        cam = np.ascontiguousarray(cam, dtype=L.CAMERA)
+        pc = None if prev_cam is None else np.ascontiguousarray(prev_cam, dtype=L.CAMERA)
+        check(self._l.rt_render(self.h, cam.ctypes.data, None if pc is None else pc.ctypes.data, C.byref(cfg)))
+
+    def sync(self):
+        check(self._l.rt_sync(self.h))
+
+    def buffer_bytes(self, which: int) -> int:
+        n = C.c_size_t()
+        check(self._l.rt_buffer_bytes(self.h, which, C.byref(n)))
+        return n.value
+
+    def download(self, which: int, out: np.ndarray | None = None) -> np.ndarray:
+        dt, comps = _BUF_DTYPES[which]
+        nbytes = self.buffer_bytes(which)
+        n = nbytes // (np.dtype(dt).itemsize * comps)
+        if out is None:
+            out = np.empty((n, comps) if comps > 1 else (n,), dtype=dt)
+        assert out.nbytes == nbytes and out.flags.c_contiguous
+        check(self._l.rt_download(self.h, which, out.ctypes.data, nbytes))
+        return out
+
+    def device_buffer(self, which: int) -> tuple[int, int]:
+        p, n = C.c_void_p(), C.c_size_t()
+        check(self._l.rt_get_device_buffer(self.h, which, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def map_external_color(self, dev_ptr: int | None, nbytes: int = 0):
+        check(self._l.rt_map_external_color(self.h, C.c_void_p(dev_ptr or 0), nbytes))
+
+    def deinterleave_tiles(self, gathered_ptr: int, rank_offsets_px, world_size, width, height, tile_size, out_radiance_ptr=None, out_rgba8_ptr=None):
+        offs = (C.c_int64 * world_size)(*[int(o) for o in rank_offsets_px])
+        check(self._l.rt_deinterleave_tiles(self.h, C.c_void_p(gathered_ptr), offs, world_size, width, height, tile_size,
+                                            C.c_void_p(out_radiance_ptr or 0), C.c_void_p(out_rgba8_ptr or 0)))
+
+    def stats(self) -> dict:
+        s = L.RtStats()
+        check(self._l.rt_get_stats(self.h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in L.RtStats._fields_ if k != "reserved"}
+        d["extendLaunchesTimed"] = int(s.reserved[0])
+        return d
+
+
+def tiles_owned_pixels(width, height, tile_size, rank, world_size) -> int:
+    n = C.c_int64()
+    check(lib().rt_tiles_owned_pixels(width, height, tile_size, rank, world_size, C.byref(n)))
+    return n.value

@@ -1,0 +1,161 @@
+// hostsim.cpp — TEST HARNESS ONLY (never a product path, never loaded by ilgpu_raytracing_b200).
+//
+// Compiles the renderer core's __host__ __device__ stage bodies (rt_core.h / rt_traverse.h /
+// rt_wavefront.h) and the host BVH builder for the CPU and runs the wavefront as plain loops, so
+// that `pytest -m "not gpu"` can check the wide-BVH build, the traversal, the tie-break rule and the
+// wavefront state machine against the oracle in a container without a GPU.  The warp-level
+// machinery (persistent fetch, ballot/shuffle refill, atomics, shared-memory stacks) exists only in
+// rt_kernels.cu and is covered by the -m gpu tests.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../ilgpu_raytracing_b200/csrc/rt_bvh.h"
+#include "../../ilgpu_raytracing_b200/csrc/rt_tiles.h"
+#include "../../ilgpu_raytracing_b200/csrc/rt_wavefront.h"
+
+using namespace rtx;
+
+#define HS_API extern "C" __attribute__((visibility("default")))
+
+struct HsScene {
+    HostBvh bvh;
+    std::vector<RtInstanceRecord> instances; std::vector<RtSphere> spheres; std::vector<RtFloat2> texcoords; std::vector<RtMeshTriUV> triUVs;
+    std::vector<int32_t> triMat; std::vector<RtMaterialRecord> materials; std::vector<RtRGBA32> texels; std::vector<RtTexInfo> texInfos;
+    DeviceScene ds;
+    std::string err;
+};
+
+template <class T> static void copy_or_one(std::vector<T>& dst, const T* src, int64_t n) {   // AllocateOrEmpty, Scene.cs:370-377
+    if (src && n > 0) dst.assign(src, src + n); else { dst.assign(1, T()); memset(dst.data(), 0, sizeof(T)); }
+}
+
+HS_API HsScene* hs_scene_create(const RtSceneDesc* d) {
+    HsScene* s = new HsScene();
+    if (!build_wide_bvh(*d, s->bvh, s->err)) return s;
+    copy_or_one(s->instances, d->instances, d->nInstances); copy_or_one(s->spheres, d->spheres, d->nSpheres);
+    copy_or_one(s->texcoords, d->meshTexcoords, d->nMeshTexcoords); copy_or_one(s->triUVs, d->meshTriUVs, d->nMeshTriUVs);
+    copy_or_one(s->triMat, d->triMatIndex, d->nTriMatIndex); copy_or_one(s->materials, d->materials, d->nMaterials);
+    copy_or_one(s->texels, d->texels, d->nTexels); copy_or_one(s->texInfos, d->texInfos, d->nTexInfos);
+    DeviceScene& ds = s->ds;
+    ds.nodes = s->bvh.nodes.data(); ds.nNodes = (int)s->bvh.nodes.size(); ds.prims = s->bvh.prims.data(); ds.nPrims = (int)s->bvh.prims.size();
+    ds.instances = s->instances.data(); ds.nInstances = (int)s->instances.size(); ds.spheres = s->spheres.data(); ds.nSpheres = (int)s->spheres.size();
+    ds.texcoords = s->texcoords.data(); ds.triUVs = s->triUVs.data(); ds.triMatIndex = s->triMat.data();
+    ds.materials = s->materials.data(); ds.nMaterials = (int)s->materials.size(); ds.texels = s->texels.data();
+    ds.texInfos = s->texInfos.data(); ds.nTexInfos = (int)s->texInfos.size(); ds.triMaterials = 0;
+    return s;
+}
+HS_API const char* hs_scene_error(HsScene* s) { return s->err.c_str(); }
+HS_API void hs_scene_destroy(HsScene* s) { delete s; }
+HS_API void hs_scene_stats(HsScene* s, int64_t* out6) {
+    out6[0] = s->bvh.stats.nPrims; out6[1] = s->bvh.stats.nTris; out6[2] = s->bvh.stats.nSpheres; out6[3] = s->bvh.stats.nWideNodes; out6[4] = s->bvh.stats.maxDepth; out6[5] = 0;
+}
+// one ray; returns hit flag; out = {t, primId, instId, bu, bv}, counters = {nodes, tris, spheres}
+HS_API int hs_trace(HsScene* s, const float* o, const float* d, int anyHit, float tMax, unsigned flags, float* out5, uint32_t* counters3) {
+    s->ds.triMaterials = (flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
+    LaneStack st; TraceCounters c = {0, 0, 0}; HitRec h; h.t = 1e30f; h.prim = -1; h.bu = h.bv = 0;
+    bool r;
+    f3 ro = mk3(o[0], o[1], o[2]), rd = mk3(d[0], d[1], d[2]);
+    if (anyHit) r = trace_wide<true, true>(s->ds, ro, rd, tMax, st, &h, &c);
+    else r = trace_wide<false, true>(s->ds, ro, rd, tMax, st, &h, &c);
+    out5[0] = h.t; out5[1] = -1; out5[2] = -1; out5[3] = h.bu; out5[4] = h.bv;
+    if (!anyHit && r) { Surface sf = eval_surface(s->ds, ro, rd, h); out5[1] = (float)sf.primId; out5[2] = (float)sf.instId; }
+    if (counters3) { counters3[0] = c.nodes; counters3[1] = c.tris; counters3[2] = c.spheres; }
+    return r ? 1 : 0;
+}
+
+struct HsOutputs {
+    int32_t* rgba8; float* depth; int32_t* objId; float* radiance4; float* accum4;
+    int32_t* primId; int32_t* instId; float* primaryT;           // per GLOBAL pixel (scattered through the pixel map)
+    float* gbPos; float* gbNrm; float* gbAlb; int32_t* gbMat;   // per global pixel, 3 floats each
+    uint8_t* segCount; uint8_t* termCode; uint32_t* pathHash;   // [spp][W*H]
+    uint64_t counters[8];                                        // raysPrimary, raysBounce, raysShadow, nodes, tris, spheres
+};
+
+// The whole frame as plain loops; mirrors the launch sequence of rt_render() in rt_api.cu.
+HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg, HsOutputs* out) {
+    if (cfg->enableTemporalReuse || cfg->enableSpatialReuse) return RT_ERR_UNSUPPORTED;
+    const int W = cfg->width, H = cfg->height;
+    std::vector<int> pmap; build_pixel_map(W, H, cfg->tileSize, cfg->rank, cfg->worldSize, pmap);
+    const int npx = (int)pmap.size();
+    const int spp = cfg->spp > 1 ? cfg->spp : 1;
+    int S = cfg->samplesPerPass > 0 ? cfg->samplesPerPass : 2;
+    if (S > spp) S = spp;
+    const size_t P = (size_t)npx * S;
+    s->ds.triMaterials = (cfg->flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
+
+    FrameConst fc; memset(&fc, 0, sizeof(fc));
+    fc.width = W; fc.height = H; fc.frame = cfg->frame; fc.spp = cfg->spp; fc.maxDepth = cfg->maxDepth; fc.rngLockNoise = cfg->rngLockNoise; fc.flags = cfg->flags;
+    fc.camOrigin = mk3(cam->origin); fc.camLowerLeft = mk3(cam->lowerLeft); fc.camHorizontal = mk3(cam->horizontal); fc.camVertical = mk3(cam->vertical);
+    fc.env.dirLightDir = mk3(cfg->dirLightDir); fc.env.dirLightRadiance = mk3(cfg->dirLightRadiance); fc.env.skyTop = mk3(cfg->skyTintTop); fc.env.skyBottom = mk3(cfg->skyTintBottom);
+    fc.npx = npx; fc.pixelMap = pmap.data();
+
+    std::vector<float4> gbPosHit(npx), gbNrmMat(npx), gbAlbObj(npx), lframe(npx), tileRad(npx), stThr(P), stLi(P);
+    std::vector<int> primId(npx), instId(npx); std::vector<float> primaryT(npx);
+    std::vector<uint32_t> pathHash(P);
+    std::vector<float4> radiance((size_t)W * H), accum((size_t)W * H);
+    std::vector<float4> qo[2], qd[2], so(P), sd(P), scv(P);
+    for (int b = 0; b < 2; b++) { qo[b].resize(P); qd[b].resize(P); }
+    std::vector<HitRec> hits(P);
+    std::vector<int32_t> dummyI((size_t)W * H); std::vector<float> dummyF((size_t)W * H);
+
+    WaveBuffers wb; memset(&wb, 0, sizeof(wb));
+    wb.gbPosHit = gbPosHit.data(); wb.gbNrmMat = gbNrmMat.data(); wb.gbAlbObj = gbAlbObj.data();
+    wb.primId = primId.data(); wb.instId = instId.data(); wb.primaryT = primaryT.data(); wb.lframe = lframe.data(); wb.tileRadiance = tileRad.data();
+    wb.rgba8 = out->rgba8 ? out->rgba8 : dummyI.data(); wb.depth = out->depth ? out->depth : dummyF.data(); wb.objId = out->objId ? out->objId : dummyI.data();
+    wb.radiance = radiance.data(); wb.accum = out->accum4 ? (float4*)out->accum4 : accum.data();
+    wb.stThr = stThr.data(); wb.stLi = stLi.data();
+    const bool aov = (cfg->flags & RT_FLAG_PATH_AOVS) && out->segCount && out->termCode && out->pathHash;
+    if (aov) { wb.pathHash = pathHash.data(); wb.segCountOut = out->segCount; wb.termCodeOut = out->termCode; wb.pathHashOut = out->pathHash; }
+
+    TraceCounters tc = {0, 0, 0}; uint64_t nodes = 0, tris = 0, sph = 0, raysB = 0, raysS = 0;
+    auto flushCnt = [&]() { nodes += tc.nodes; tris += tc.tris; sph += tc.spheres; tc.nodes = tc.tris = tc.spheres = 0; };
+    LaneStack st;
+
+    // primary visibility
+    RayQueue q0 = {qo[0].data(), qd[0].data()};
+    for (int i = 0; i < npx; i++) generate_primary(fc, q0, i);
+    for (int i = 0; i < npx; i++) { f3 o = mk3(q0.o[i].x, q0.o[i].y, q0.o[i].z), d = mk3(q0.d[i].x, q0.d[i].y, q0.d[i].z); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[i], &tc); flushCnt(); }
+    for (int i = 0; i < npx; i++) primary_finish(fc, s->ds, wb, q0, hits.data(), i);
+
+    // integrator, one batch of S samples at a time
+    ShadowQueue shq = {so.data(), sd.data(), scv.data()};
+    for (int s0 = 0; s0 < spp; s0 += S) {
+        const int ns = (s0 + S <= spp) ? S : (spp - s0);
+        int cur = 0; int nNext = 0, nSh = 0;
+        RayQueue nq = {qo[cur].data(), qd[cur].data()};
+        for (int j = 0; j < npx * ns; j++) shade_first(fc, wb, s0, j, nq, &nNext, shq, &nSh);
+        for (int depth = 1; depth <= fc.maxDepth; depth++) {
+            for (int k = 0; k < nSh; k++) {
+                f3 o = mk3(shq.o[k].x, shq.o[k].y, shq.o[k].z), d = mk3(shq.d[k].x, shq.d[k].y, shq.d[k].z);
+                bool occ = trace_wide<true, true>(s->ds, o, d, 1e29f, st, nullptr, &tc); flushCnt();
+                connect_shadow(wb, shq, k, occ);
+            }
+            raysS += (uint64_t)nSh;
+            RayQueue cq = {qo[cur].data(), qd[cur].data()};
+            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[k], &tc); flushCnt(); }
+            raysB += (uint64_t)nNext;
+            const int nCur = nNext; nNext = 0; nSh = 0;
+            RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data()};
+            for (int k = 0; k < nCur; k++) shade_next(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh);
+            cur ^= 1;
+        }
+        const bool last = (s0 + ns >= spp);
+        for (int i = 0; i < npx; i++) accumulate(fc, wb, s0, ns, last, i);
+    }
+
+    for (int i = 0; i < npx; i++) {
+        const int pix = pmap[i];
+        if (out->primId) out->primId[pix] = primId[i];
+        if (out->instId) out->instId[pix] = instId[i];
+        if (out->primaryT) out->primaryT[pix] = primaryT[i];
+        if (out->gbPos) { out->gbPos[3 * pix] = gbPosHit[i].x; out->gbPos[3 * pix + 1] = gbPosHit[i].y; out->gbPos[3 * pix + 2] = gbPosHit[i].z; }
+        if (out->gbNrm) { out->gbNrm[3 * pix] = gbNrmMat[i].x; out->gbNrm[3 * pix + 1] = gbNrmMat[i].y; out->gbNrm[3 * pix + 2] = gbNrmMat[i].z; }
+        if (out->gbAlb) { out->gbAlb[3 * pix] = gbAlbObj[i].x; out->gbAlb[3 * pix + 1] = gbAlbObj[i].y; out->gbAlb[3 * pix + 2] = gbAlbObj[i].z; }
+        if (out->gbMat) out->gbMat[pix] = (int32_t)f2u(gbNrmMat[i].w);
+        if (out->radiance4) memcpy(out->radiance4 + 4 * (size_t)pix, &radiance[pix], 16);
+    }
+    out->counters[0] = (uint64_t)npx; out->counters[1] = raysB; out->counters[2] = raysS; out->counters[3] = nodes; out->counters[4] = tris; out->counters[5] = sph;
+    return 0;
+}

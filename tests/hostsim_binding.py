@@ -1,0 +1,85 @@
+"""ctypes binding of tests/hostsim (CPU build of the core's stage bodies; test harness only)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from ilgpu_raytracing_b200 import layouts as L
+
+_HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+
+
+class HsOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rgba8", "depth", "objId", "radiance4", "accum4", "primId", "instId", "primaryT",
+                                          "gbPos", "gbNrm", "gbAlb", "gbMat", "segCount", "termCode", "pathHash")] + [("counters", C.c_uint64 * 8)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.run(["make", "-C", _HERE, "-s"], check=True)
+        _lib = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
+        _lib.hs_scene_create.restype = C.c_void_p
+        _lib.hs_scene_create.argtypes = [C.POINTER(L.RtSceneDesc)]
+        _lib.hs_scene_error.restype = C.c_char_p
+        _lib.hs_scene_error.argtypes = [C.c_void_p]
+        _lib.hs_scene_destroy.argtypes = [C.c_void_p]
+        _lib.hs_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.hs_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
+        _lib.hs_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs)]
+    return _lib
+
+
+class HostSimScene:
+    def __init__(self, arrays: dict):
+        self.desc, self._keep = L.scene_desc_from_arrays(arrays)
+        self.h = C.c_void_p(lib().hs_scene_create(C.byref(self.desc)))
+        err = lib().hs_scene_error(self.h).decode()
+        if err:
+            raise ValueError(err)
+
+    def __del__(self):
+        try:
+            lib().hs_scene_destroy(self.h)
+        except Exception:
+            pass
+
+    def stats(self):
+        s = np.zeros(6, np.int64)
+        lib().hs_scene_stats(self.h, s.ctypes.data)
+        return dict(nPrims=int(s[0]), nTris=int(s[1]), nSpheres=int(s[2]), nWideNodes=int(s[3]), maxDepth=int(s[4]))
+
+    def trace(self, o, d, any_hit=False, t_max=1e30, flags=0):
+        o = np.ascontiguousarray(o, np.float32)
+        d = np.ascontiguousarray(d, np.float32)
+        out = np.zeros(5, np.float32)
+        cnt = np.zeros(3, np.uint32)
+        hit = lib().hs_trace(self.h, o.ctypes.data, d.ctypes.data, int(any_hit), float(t_max), flags, out.ctypes.data, cnt.ctypes.data)
+        return bool(hit), float(out[0]), int(out[2]), int(out[1]), cnt
+
+    def render(self, cam: np.ndarray, cfg: L.RtRenderConfig, aovs=True):
+        W, H, spp = cfg.width, cfg.height, max(1, cfg.spp)
+        n = W * H
+        r = dict(rgba8=np.zeros(n, np.int32), depth=np.zeros(n, np.float32), objId=np.zeros(n, np.int32), radiance4=np.zeros((n, 4), np.float32),
+                 accum4=np.zeros((n, 4), np.float32), primId=np.full(n, -2, np.int32), instId=np.full(n, -2, np.int32), primaryT=np.zeros(n, np.float32),
+                 gbPos=np.zeros((n, 3), np.float32), gbNrm=np.zeros((n, 3), np.float32), gbAlb=np.zeros((n, 3), np.float32), gbMat=np.zeros(n, np.int32),
+                 segCount=np.zeros((spp, n), np.uint8), termCode=np.zeros((spp, n), np.uint8), pathHash=np.zeros((spp, n), np.uint32))
+        o = HsOutputs()
+        for k, v in r.items():
+            setattr(o, k, v.ctypes.data)
+        if aovs:
+            cfg.flags |= L.RT_FLAG_PATH_AOVS
+        cam = np.ascontiguousarray(cam, dtype=L.CAMERA)
+        rc = lib().hs_render(self.h, cam.ctypes.data, C.byref(cfg), C.byref(o))
+        if rc != 0:
+            raise RuntimeError(f"hs_render: {rc}")
+        names = ["raysPrimary", "raysBounce", "raysShadow", "nodes", "tris", "spheres"]
+        r["counters"] = {k: int(o.counters[i]) for i, k in enumerate(names)}
+        r["radiance"] = r["radiance4"][:, :3]
+        return r
