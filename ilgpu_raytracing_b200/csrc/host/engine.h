@@ -1,0 +1,169 @@
+// engine.h — C++ mirror of the reference's host-side Engine surface for the hot path.
+//
+// The reference host is C# (.NET 8); this image has no .NET toolchain, so the host side that sits
+// above the C ABI is mirrored here in C++ with the reference's class / method names, argument
+// meaning and error behaviour (exceptions -> std::exception subclasses of the same name).  The
+// real drop-in is the C# P/Invoke layer under csharp/ (same calls).
+//
+//   Camera            Engine/Camera.cs:5-230
+//   Scene             Engine/Scene.cs:15-694      (host lists, BVH2 builders, UploadAll -> rt_scene_upload)
+//   BvhManager        Engine/BvhManager.cs:11-51
+//   SceneManager      Engine/SceneManager.cs:10-40
+//   Framebuffer       Engine/Framebuffer.cs:12-210 (DownloadToCpu / CpuColor / CpuDepth / CpuObjectId)
+//   RTRenderer        Engine/RTRenderer.cs:22-376  (RenderDirectToPbo -> rt_render)
+//
+// Out of scope: OBJ/MTL/TGA loading (LoadObjInstance takes decoded arrays here),
+// TAAU / blit / bilinear presentation kernels, OpenGL PBO interop, the fly-camera controller.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/rtcore_b200.h"
+
+namespace ILGPU_Raytracing {
+namespace Engine {
+
+struct ArgumentNullException : std::invalid_argument { using std::invalid_argument::invalid_argument; };
+struct ArgumentOutOfRangeException : std::out_of_range { using std::out_of_range::out_of_range; };
+struct InvalidOperationException : std::logic_error { using std::logic_error::logic_error; };
+struct RtNativeException : std::runtime_error {   // CudaException.ThrowIfFailed analogue (CudaGlInteropIndexBuffer.cs:56)
+    int status;
+    RtNativeException(int s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+typedef RtFloat3 Float3;
+typedef RtFloat2 Float2;
+typedef RtAffine3x4 Affine3x4;
+typedef RtMaterialRecord MaterialRecord;
+typedef RtSphere Sphere;
+typedef RtBvhNode TLASNode;
+typedef RtBvhNode BLASNode;
+typedef RtInstanceRecord InstanceRecord;
+typedef RtMeshTri MeshTri;
+typedef RtMeshTriUV MeshTriUV;
+typedef RtRGBA32 RGBA32;
+typedef RtTexInfo TexInfo;
+
+Affine3x4 AffineIdentity();   // Affine3x4.Identity, Affine3x4.cs:9-14
+
+// Camera.cs:5-230 (the struct is RtCamera; these are its methods)
+struct Camera : RtCamera {
+    static Camera CreateCamera(int width, int height, float fovDegrees);                         // :19-47
+    static Camera CreateCameraAt(int width, int height, float fovDegrees, Float3 origin, Float3 lookAt);   // :19-47 with origin/lookAt as parameters
+    static Camera LookAt(Float3 origin, Float3 lookAt, Float3 up, float vfovDegrees, float aspect, float focusDist = 1.0f);   // ctor :99-119
+    void Translate(Float3 delta);                                                                // :121-126
+    void SetFov(float vfovDegrees, float aspect);                                                // :128-145
+    void RotateYawPitch(float yawDegrees, float pitchDegrees);                                   // :147-180
+    void UpdateDerived(float aspectIn, float fovYRadIn);                                         // :184-191
+};
+
+enum class RebuildPolicy { Auto, ForceRefit, ForceRebuild };   // BvhManager.cs:13-18
+
+class Scene {
+public:
+    explicit Scene(rt_ctx* native);
+    void BuildDefaultScene();                                                                    // Scene.cs:83-142
+    void Reset();                                                                                // empty scene (what SceneManager.ReplaceScene(new Scene) yields, SceneManager.cs:32-36)
+    int AddTexture(int width, int height, const RGBA32* texels);                                 // texel/texInfo append of Scene.cs:98-109,190-218
+    int AddSphere(const Sphere& s);                                                              // Scene.cs:315-321
+    void AddSphereInstance(const int* sphereIds, int n, const Affine3x4& objectToWorld);        // BuildSphereInstance Scene.cs:323-356 + instance append
+    // Scene.LoadObjInstance (Scene.cs:144-256) after MeshLoaderOBJ.Load: decoded mesh arrays; material texture indices are global
+    void LoadMeshInstance(const Float3* positions, int nPositions, const MeshTri* tris, int nTris, const Float2* texcoords, int nTexcoords,
+                          const MeshTriUV* triUVs, const int* triMaterialIndex, const MaterialRecord* materials, int nMaterials,
+                          const Affine3x4& objectToWorld);
+    void RebuildTLAS();                                                                          // Scene.cs:358-368
+    void UploadAll();                                                                            // Scene.cs:258-279 -> rt_scene_upload
+    void FillDesc(RtSceneDesc* d) const;                                                         // GetDeviceViews analogue (host views), Scene.cs:281-313
+    long SortTies() const { return _sortTies; }
+
+    // host lists (Scene.cs:19-38)
+    std::vector<TLASNode> hTLASNodes; std::vector<int> hTLASInstanceIndices; std::vector<InstanceRecord> hInstances;
+    std::vector<BLASNode> hBLASNodes; std::vector<int> hSpherePrimIndices; std::vector<Sphere> hSpheres;
+    std::vector<int> hTriPrimIndices; std::vector<Float3> hMeshPositions; std::vector<MeshTri> hMeshTris;
+    std::vector<Float2> hMeshTexcoords; std::vector<MeshTriUV> hMeshTriUVs; std::vector<int> hTriMaterialIndex;
+    std::vector<MaterialRecord> hMaterials; std::vector<TexInfo> hTexInfos; std::vector<RGBA32> hTexels;
+
+private:
+    rt_ctx* _native;
+    long _sortTies = 0;
+    std::vector<float> _triKey[3];   // centroid keys per axis, CenterOfTriangle (Scene.cs:607-614)
+    void Clear();
+    InstanceRecord BuildSphereInstance(const int* sphereIds, int n, const Affine3x4& objectToWorld);
+    void BuildBLAS_Spheres(int primStart, int primCount);
+    void BuildBLAS_Triangles(int primStart, int primCount);
+    int BuildBLASNodeRecursive(int* idx, int start, int count, const Float3* bminPre, const Float3* bmaxPre, int parentSkip, bool spheres);
+    int BuildTLASNodeRecursive(int* idx, int start, int count, int parentSkip);
+};
+
+class BvhManager {   // BvhManager.cs:11-51
+public:
+    explicit BvhManager(Scene* scene) : _scene(scene) { if (!scene) throw ArgumentNullException("scene"); }
+    void BuildOrRefit(RebuildPolicy) { _scene->UploadAll(); }   // :27 (the policy is ignored by the reference too)
+private:
+    Scene* _scene;
+};
+
+class SceneManager {   // SceneManager.cs:10-40
+public:
+    explicit SceneManager(rt_ctx* native) : _scene(native), _bvh(&_scene) {}
+    Scene& GetScene() { return _scene; }
+    void BuildDefaultScene() { _scene.BuildDefaultScene(); }
+    void Commit(RebuildPolicy p = RebuildPolicy::Auto) { _bvh.BuildOrRefit(p); }
+private:
+    Scene _scene;
+    BvhManager _bvh;
+};
+
+class Framebuffer {   // Framebuffer.cs:12-210 (device buffers are owned by the native context)
+public:
+    explicit Framebuffer(rt_ctx* native) : _native(native) {}
+    void DownloadToCpu(int slot = 0);                                                            // :148-156
+    const std::vector<int>& CpuColor() const { return _cpuColor; }                              // :158
+    const std::vector<float>& CpuDepth() const { return _cpuDepth; }                            // :159
+    const std::vector<int>& CpuObjectId() const { return _cpuObjectId; }                        // :160
+private:
+    rt_ctx* _native;
+    std::vector<int> _cpuColor, _cpuObjectId; std::vector<float> _cpuDepth;
+};
+
+class RTRenderer {   // RTRenderer.cs:22-376
+public:
+    explicit RTRenderer(int deviceIndex = 0, int windowWidth = 1280, int windowHeight = 720);   // :63-92
+    ~RTRenderer();                                                                               // Dispose :347-375
+    RTRenderer(const RTRenderer&) = delete;
+    RTRenderer& operator=(const RTRenderer&) = delete;
+
+    rt_ctx* Native() { return _native; }                         // "Accelerator" analogue (:94)
+    SceneManager& Scenes() { return *_sceneManager; }
+    Framebuffer& Frame() { return *_framebuffer; }
+    Camera& Cam() { return _camera; }
+    void SetSunParams(float speedRadPerSec, float elevationRad) { _sunSpeedRadPerSec = speedRadPerSec; _sunElevation = elevationRad; }   // :99-103
+    // :105-237.  pboDevicePtr: CUDA-mapped PBO (or NULL = keep the image in the native framebuffer only).
+    void RenderDirectToPbo(void* pboDevicePtr, int width, int height, int frame, float dt);
+    void Synchronize();
+
+    // the reference's private knobs (RTRenderer.cs:43-49,204), made settable: benchmark configs fix them
+    float RenderScale = 1.0f;      // reference default 0.67 relies on the TAAU upsampler (out of scope); 1.0 = trace at output size
+    int EnableTemporalReuse = 0, EnableSpatialReuse = 0;   // reference default 1/1; reuse is not built yet (rt_render refuses it)
+    int RngLockNoise = 1;          // reference: 0 -> seed 0, nonzero -> Random.Shared.Next() per frame (:166)
+    int FixedSeed = 1;             // used instead of Random.Shared.Next() when RngLockNoise != 0 (deterministic runs)
+    int Spp = 2;                   // :49
+    int MaxDepth = 3;              // :204
+    unsigned Flags = 0;            // RT_FLAG_*
+    int TileSize = 32, Rank = 0, WorldSize = 1, SamplesPerPass = 0;
+    RtRenderConfig LastConfig() const { return _lastCfg; }
+
+private:
+    rt_ctx* _native = nullptr;
+    SceneManager* _sceneManager = nullptr;
+    Framebuffer* _framebuffer = nullptr;
+    Camera _camera, _prevCamera;
+    float _sunAzimuth = 0.0f, _sunElevation = 0.9f, _sunSpeedRadPerSec = 0.0f;   // :59-61
+    RtRenderConfig _lastCfg;
+};
+
+void BakeCameraDerived(Camera& c, int pixelW, int pixelH);   // RTRenderer.cs:241-263
+
+}   // namespace Engine
+}   // namespace ILGPU_Raytracing

@@ -327,13 +327,69 @@ struct Scene {
         return Float3((v0.X + v1.X + v2.X) / 3.0f, (v0.Y + v1.Y + v2.Y) / 3.0f, (v0.Z + v1.Z + v2.Z) / 3.0f);
     }
 
-    // Array.Sort(idx, start, count, comparer) is an UNSTABLE introsort; equal keys may land in either
-    // order.  We sort stably on the key and count ties so callers can assert the scene has none.
+    // Array.Sort(idx, start, count, comparer) is .NET's UNSTABLE introsort (ArraySortHelper<T>.IntrospectiveSort:
+    // median-of-three quicksort, insertion sort for partitions <= 16, heapsort at depth 2*(log2(n)+1)).  Restated here
+    // (from the published .NET runtime sources, not vendored under /root/reference: UNPINNED) so equal keys land where
+    // the reference's sort would put them; sortTies counts equal neighbours so callers can see whether that matters.
+    template <class KeyFn> struct NetSort {
+        KeyFn key;
+        int cmp(int a, int b) { float va = key(a), vb = key(b); if (va < vb) return -1; if (va > vb) return 1; return 0; }
+        void SwapIfGreater(int* k, int i, int j) { if (cmp(k[i], k[j]) > 0) { int t = k[i]; k[i] = k[j]; k[j] = t; } }
+        void InsertionSort(int* k, int n) {
+            for (int i = 0; i < n - 1; i++) { int t = k[i + 1]; int j = i; while (j >= 0 && cmp(t, k[j]) < 0) { k[j + 1] = k[j]; j--; } k[j + 1] = t; }
+        }
+        void DownHeap(int* k, int i, int n) {
+            int d = k[i - 1];
+            while (i <= n >> 1) {
+                int child = 2 * i;
+                if (child < n && cmp(k[child - 1], k[child]) < 0) child++;
+                if (!(cmp(d, k[child - 1]) < 0)) break;
+                k[i - 1] = k[child - 1]; i = child;
+            }
+            k[i - 1] = d;
+        }
+        void HeapSort(int* k, int n) {
+            for (int i = n >> 1; i >= 1; i--) DownHeap(k, i, n);
+            for (int i = n; i > 1; i--) { int t = k[0]; k[0] = k[i - 1]; k[i - 1] = t; DownHeap(k, 1, i - 1); }
+        }
+        int PickPivotAndPartition(int* k, int n) {
+            int hi = n - 1, middle = hi >> 1;
+            SwapIfGreater(k, 0, middle); SwapIfGreater(k, 0, hi); SwapIfGreater(k, middle, hi);
+            int pivot = k[middle];
+            { int t = k[middle]; k[middle] = k[hi - 1]; k[hi - 1] = t; }
+            int left = 0, right = hi - 1;
+            while (left < right) {
+                while (cmp(k[++left], pivot) < 0) {}
+                while (cmp(pivot, k[--right]) < 0) {}
+                if (left >= right) break;
+                int t = k[left]; k[left] = k[right]; k[right] = t;
+            }
+            if (left != hi - 1) { int t = k[left]; k[left] = k[hi - 1]; k[hi - 1] = t; }
+            return left;
+        }
+        void IntroSort(int* k, int n, int depthLimit) {
+            int partitionSize = n;
+            while (partitionSize > 1) {
+                if (partitionSize <= 16) {
+                    if (partitionSize == 2) { SwapIfGreater(k, 0, 1); return; }
+                    if (partitionSize == 3) { SwapIfGreater(k, 0, 1); SwapIfGreater(k, 0, 2); SwapIfGreater(k, 1, 2); return; }
+                    InsertionSort(k, partitionSize); return;
+                }
+                if (depthLimit == 0) { HeapSort(k, partitionSize); return; }
+                depthLimit--;
+                int p = PickPivotAndPartition(k, partitionSize);
+                IntroSort(k + p + 1, partitionSize - (p + 1), depthLimit);
+                partitionSize = p;
+            }
+        }
+    };
     template <class KeyFn> void SortRange(int* idx, int start, int count, KeyFn key) {
-        std::vector<std::pair<float, int>> tmp((size_t)count);
-        for (int i = 0; i < count; i++) tmp[i] = std::make_pair(key(idx[start + i]), idx[start + i]);
-        std::stable_sort(tmp.begin(), tmp.end(), [](const std::pair<float, int>& a, const std::pair<float, int>& b) { return a.first < b.first; });
-        for (int i = 0; i < count; i++) { idx[start + i] = tmp[i].second; if (i > 0 && tmp[i].first == tmp[i - 1].first) sortTies++; }
+        if (count > 1) {
+            int lg = 0; for (unsigned v = (unsigned)count; v >>= 1;) lg++;
+            NetSort<KeyFn> ns{key};
+            ns.IntroSort(idx + start, count, 2 * (lg + 1));
+        }
+        for (int i = 1; i < count; i++) if (key(idx[start + i]) == key(idx[start + i - 1])) sortTies++;
     }
 
     // Engine/Scene.cs:405-467.  bminPre/bmaxPre are indexed by POSITION i (quirk 1 of SURVEY §8a) exactly as the reference does.
