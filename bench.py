@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native renderer core.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C4|C3|C2|C1]
+
+A "step" is one frame of the hot path (generate -> extend -> shade/bounce -> accumulate/tone-map) of the
+workload BASELINE.json's metric is quoted on: C4 = the synthetic 1 002 528-triangle terrain + 256 mirror /
+glass / diffuse spheres at 3840x2160, 64 spp, 8 bounces (reference-faithful variant: triangles Lambert,
+SURVEY.md §8d).  metric = Mrays/s counting primary + bounce rays (TraceClosest calls; shadow rays are
+reported beside it), value = whole-job rays / device time with the scene resident in HBM.
+
+  e2e          same metric through the engine API (RTRenderer.RenderDirectToPbo + Framebuffer.DownloadToCpu)
+               with host camera/config in and the 12 B/px framebuffer (RGBA8 + depth + objId) read back to
+               pinned host memory every step
+  roofline     extend (wide-BVH traversal) kernels: algorithmic node/primitive/queue bytes per frame divided
+               by their summed CUDA-event duration, against the measured HBM copy bandwidth
+  cpu_baseline the CPU oracle (line-by-line restatement of the reference kernels, all host threads) on a
+               bounded crop of the same frame
+  --impl reference   times only that CPU restatement (the reference itself is C#/.NET + ILGPU + OpenGL and
+               cannot be built or run in this image: no dotnet, no display)
+
+N > 1 (torchrun, one process per GPU): the image is split into interleaved 32x32 screen tiles, the scene is
+replicated, every rank renders its tiles and the float4 tile payloads are gathered to rank 0 over NCCL and
+de-interleaved there, all inside the timed step ("strong" scaling: the frame is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: scene, camera, width, height, spp, depth, oracle crop (x0,y0,x1,y1), oracle spp for the CPU sample
+    "C1": dict(scene="default", cam="C1A", w=1280, h=720, spp=1, depth=1, crop=None, cpu_spp=1),
+    "C2": dict(scene="spheres", cam="C2", w=1920, h=1080, spp=16, depth=4, crop=(480, 270, 1440, 810), cpu_spp=16),
+    "C3": dict(scene="terrain", cam="C3", w=3840, h=2160, spp=1, depth=0, crop=(960, 540, 2880, 1620), cpu_spp=1),
+    "C4": dict(scene="terrain+spheres", cam="C3", w=3840, h=2160, spp=64, depth=8, crop=(1792, 1008, 2048, 1152), cpu_spp=64),
+}
+
+
+def make_spec(kind: str):
+    from ilgpu_raytracing_b200 import scenes
+    if kind == "default":
+        return scenes.default_scene()
+    if kind == "spheres":
+        return scenes.sphere_grid_scene(32)
+    if kind == "terrain":
+        return scenes.terrain_scene(708, 0)
+    if kind == "terrain+spheres":
+        return scenes.terrain_scene(708, 256)
+    raise ValueError(kind)
+
+
+def peaks() -> dict:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=float(d["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self._stop = threading.Event()
+        self._idx = gpu_index
+        self._t = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+        def run():
+            while not self._stop.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self._idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([c.strip() for c in out.split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.2)
+
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def cpu_oracle_sample(wl: dict, threads: int = 0) -> dict:
+    """Time the CPU oracle on the workload's crop: Mrays/s (primary + bounce) over the two passes."""
+    from oracle import orc
+    from tests.util import oracle_camera, oracle_scene_from_spec
+    sc = oracle_scene_from_spec(make_spec(wl["scene"]))
+    cam = oracle_camera(wl["cam"], wl["w"], wl["h"])
+    crop = wl["crop"] or (0, 0, wl["w"], wl["h"])
+    cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop, threads=threads)
+    t0 = time.perf_counter()
+    r = orc.render(sc, cam, cfg, aovs=False)
+    wall = time.perf_counter() - t0
+    secs = r.seconds[0] + r.seconds[1]
+    rays = r.counters["raysPrimary"] + r.counters["raysBounce"]
+    return dict(mrays=rays / secs / 1e6, rays=rays, rays_shadow=r.counters["raysShadow"], seconds=secs, wall=wall,
+                cores=threads or orc.lib().orc_hardware_threads(), counters=r.counters,
+                sample=f"crop {crop[2] - crop[0]}x{crop[3] - crop[1]} of the {wl['w']}x{wl['h']} frame at {wl['cpu_spp']} spp, depth {wl['depth']}", scene=sc, cam=cam)
+
+
+def run_reference(args, wl, name):
+    """--impl reference: the CPU restatement of the reference kernels, all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import orc
+    from tests.util import oracle_camera, oracle_scene_from_spec
+    sc = oracle_scene_from_spec(make_spec(wl["scene"]))
+    cam = oracle_camera(wl["cam"], wl["w"], wl["h"])
+    crop = wl["crop"] or (0, 0, wl["w"], wl["h"])
+    cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop)
+    rays = secs = 0.0
+    for i in range(args.warmup + args.steps):
+        r = orc.render(sc, cam, cfg, aovs=False)
+        if i >= args.warmup:
+            rays += r.counters["raysPrimary"] + r.counters["raysBounce"]
+            secs += r.seconds[0] + r.seconds[1]
+    v = rays / secs / 1e6
+    cores = orc.lib().orc_hardware_threads()
+    sample = f"crop {crop[2] - crop[0]}x{crop[3] - crop[1]} of the {wl['w']}x{wl['h']} frame at {wl['cpu_spp']} spp, depth {wl['depth']} per step"
+    line = {"impl": "reference", "metric": "Mrays/s (primary+bounce) at 4K" if wl["w"] == 3840 else "Mrays/s (primary+bounce)", "value": v, "unit": "Mrays/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": name, "scene": wl["scene"], "width": wl["w"], "height": wl["h"], "spp": wl["spp"], "max_depth": wl["depth"]},
+            "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "CPU restatement of the ILGPU kernels (stand-in for ILGPU CPUAccelerator, which cannot run here)"},
+            "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (debugging; invalidates the headline)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    name = args.workload
+    wl = dict(WORKLOADS[name])
+    if args.spp:
+        wl["spp"] = args.spp
+    if args.impl == "reference":
+        run_reference(args, wl, name)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from ilgpu_raytracing_b200 import engine, layouts as L, native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    W, H, spp, depth = wl["w"], wl["h"], wl["spp"], wl["depth"]
+    tile = 32
+
+    # ---- scene + renderer through the engine API (the reference's host surface) -----------------------------------
+    rdr = engine.RTRenderer(local_rank, W, H)
+    spec = make_spec(wl["scene"])
+    t0 = time.perf_counter()
+    rdr.scene.load_spec(spec)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rdr.Commit()
+    t_commit = time.perf_counter() - t0
+    rdr.camera = engine.config_camera(wl["cam"], W, H)
+    rdr.configure(renderScale=1.0, spp=spp, maxDepth=depth, rngLockNoise=1, fixedSeed=1, flags=0, tileSize=tile, rank=rank, worldSize=world)
+    ctx = rdr.native
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    cam = rdr.camera
+    # bake the derived camera fields exactly as RenderDirectToPbo does before launching
+    engine.lib().eng_camera_bake(cam.ctypes.data_as(__import__("ctypes").c_void_p), W, H)
+
+    def cfg_for(flags=0):
+        return L.make_render_config(W, H, spp=spp, max_depth=depth, rng_lock_noise=1, flags=flags, tile_size=tile, rank=rank, world_size=world)
+
+    npx_all = [native.tiles_owned_pixels(W, H, tile, r, world) for r in range(world)]
+    max_npx = max(npx_all)
+    gathered = payload = None
+    if world > 1:
+        payload = torch.zeros((max_npx, 4), dtype=torch.float32, device="cuda")
+        gathered = [torch.zeros((max_npx, 4), dtype=torch.float32, device="cuda") for _ in range(world)] if rank == 0 else None
+        full = torch.zeros((W * H, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        full_rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda") if rank == 0 else None
+        flat = torch.zeros((world * max_npx, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+
+    class _Dev:   # view of a library-owned device buffer as a torch tensor (no copy)
+        def __init__(self, ptr, nfloat4):
+            self.__cuda_array_interface__ = {"shape": (nfloat4, 4), "typestr": "<f4", "data": (ptr, False), "version": 3}
+
+    def step(cfg):
+        """One frame on this rank (async on `stream`), plus the framebuffer gather for N > 1."""
+        ctx.render(cam, cfg)
+        if world > 1:
+            ptr, nbytes = ctx.device_buffer(L.RT_BUF_TILE_RADIANCE)
+            with torch.cuda.stream(stream):
+                src = torch.as_tensor(_Dev(ptr, nbytes // 16), device="cuda")
+                payload[: src.shape[0]].copy_(src, non_blocking=True)
+                dist.gather(payload, gathered, dst=0)
+                if rank == 0:
+                    torch.stack(gathered, out=flat.view(world, max_npx, 4))
+                    ctx.deinterleave_tiles(flat.data_ptr(), [r * max_npx for r in range(world)], world, W, H, tile, full.data_ptr(), full_rgba.data_ptr())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg = cfg_for(0)
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            step(cfg)
+    barrier()
+    st0 = ctx.stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            step(cfg)
+        ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    st = ctx.stats()
+    rays_pb = st["raysPrimary"] + st["raysBounce"]
+    rays_all = rays_pb + st["raysShadow"]
+    launches = st["kernelLaunches"] * args.steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        r = torch.tensor([rays_pb, rays_all, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        rays_pb, rays_all, launches = (float(x) for x in r.tolist())
+    ms_per_step = ms / args.steps
+    value = rays_pb / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e through the engine API with host buffers (rank-local frame; N > 1 adds the gather above) ---------------
+    n_px = W * H
+    pin = [torch.empty(n_px, dtype=torch.int32).pin_memory(), torch.empty(n_px, dtype=torch.float32).pin_memory(), torch.empty(n_px, dtype=torch.int32).pin_memory()]
+    pin_np = [p.numpy() for p in pin]
+    ctx.set_stream(None)
+
+    def e2e_step():
+        rdr.RenderDirectToPbo(None, W, H, 0, 0.0)    # host camera + knobs in; two launches' worth of work; Synchronize()
+        rdr.DownloadToCpu(*pin_np)                   # Framebuffer.DownloadToCpu: RGBA8 + depth + objId to host
+
+    for _ in range(min(2, args.warmup)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = rays_pb / e2e_s / 1e6
+    h2d = 2 * L.CAMERA.itemsize + __import__("ctypes").sizeof(L.RtRenderConfig)
+    d2h = 12 * n_px
+
+    # ---- roofline of the extend kernels: one frame with per-launch events, one with device counters ---------------
+    ctx.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        ctx.render(cam, cfg_for(L.RT_FLAG_KERNEL_TIMING))
+    torch.cuda.synchronize()
+    st_t = ctx.stats()
+    with torch.cuda.stream(stream):
+        ctx.render(cam, cfg_for(L.RT_FLAG_COUNTERS))
+    torch.cuda.synchronize()
+    st_c = ctx.stats()
+    n_rays = st_c["raysPrimary"] + st_c["raysBounce"] + st_c["raysShadow"]
+    # algorithmic bytes of the traversal: 80 B per wide node fetched, 48 B per primitive record tested,
+    # 32 B ray read per ray, 16 B hit record written per closest ray, 16 B Li read-modify-write x2 per shadow ray
+    alg_bytes = 80 * st_c["wideNodes"] + 48 * (st_c["trisTested"] + st_c["spheresTested"]) + 32 * n_rays + 16 * (st_c["raysPrimary"] + st_c["raysBounce"]) + 48 * st_c["raysShadow"]
+    trace_ms = st_t["lastTraceMs"]
+    n_ext = max(1, st_t["extendLaunchesTimed"])
+    pk = peaks()
+    achieved = alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "peak_source": pk["source"], "traffic": None,
+                "algorithmic_bytes_per_launch": alg_bytes / n_ext, "launches_per_step": n_ext, "avg_launch_ms": trace_ms / n_ext,
+                "extend_share_of_step": trace_ms / st_t["lastRenderMs"] if st_t["lastRenderMs"] else None,
+                "nodes_per_ray": st_c["wideNodes"] / max(1, n_rays), "prims_per_ray": (st_c["trisTested"] + st_c["spheresTested"]) / max(1, n_rays),
+                "note": "node/primitive fetches are served mostly by L1/L2 (the 63 MB BVH is cache resident), so achieved algorithmic GB/s is not DRAM traffic; see DESIGN.md"}
+
+    line = None
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            c = cpu_oracle_sample(wl)
+            cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["cores"], "kind": "port", "sample": c["sample"], "seconds": c["seconds"],
+                   "note": "CPU restatement of the ILGPU kernels (stand-in for ILGPU CPUAccelerator, which cannot run here)"}
+        line = {"metric": "Mrays/s (primary+bounce) at 4K" if W == 3840 else "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": name, "scene": wl["scene"], "triangles": int(len(spec.mesh.tris)) if spec.mesh is not None else 0, "spheres": int(len(spec.spheres)),
+                           "width": W, "height": H, "spp": spp, "max_depth": depth, "variant": "reference-faithful (triangles Lambert)",
+                           "partition": f"interleaved {tile}x{tile} screen tiles x{world}, scene replicated" if world > 1 else "single GPU",
+                           "l2": "no explicit flush: per-step path state + queues (GBs) exceed the 126 MB L2; the BVH is meant to stay resident"},
+                "frames_per_s": 1e3 / ms_per_step, "mrays_per_s_incl_shadow": rays_all / (ms_per_step * 1e-3) / 1e6,
+                "rays_per_step": {"primary_plus_bounce": rays_pb, "all": rays_all},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3},
+                "gpu_launches": int(launches),
+                "roofline": roofline, "cpu_baseline": cpu,
+                "scene_build_s": {"host_bvh2": t_build, "commit_wide_bvh_upload": t_commit}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    rdr.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -439,7 +439,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     const int npx = c->npx;
     const int nPasses = (spp + S - 1) / S;
     const bool count = (cfg->flags & RT_FLAG_COUNTERS) != 0;
-    c->timeKernels = count;   // per-launch event pairs around the extend kernels (roofline measurements)
+    c->timeKernels = (cfg->flags & RT_FLAG_KERNEL_TIMING) != 0;   // per-launch event pairs around the extend kernels (roofline measurements)
     c->traceEventsUsed = 0;
     c->launches = 0;
     c->ds.triMaterials = (cfg->flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;

@@ -164,7 +164,9 @@ enum {
     /* Keep per-(pixel,sample) parity AOVs: segment count, terminator, path hash. */
     RT_FLAG_PATH_AOVS     = 1u << 3,
     /* Count rays / nodes / primitives on the device (slower; for roofline). */
-    RT_FLAG_COUNTERS      = 1u << 4
+    RT_FLAG_COUNTERS      = 1u << 4,
+    /* Bracket every extend (traversal) launch with CUDA events; rt_get_stats reports their sum. */
+    RT_FLAG_KERNEL_TIMING = 1u << 5
 };
 
 /* Everything the reference passes in GBufferParams / IntegratorParams
