@@ -96,11 +96,7 @@ struct Builder {
                 if (cost < bestCost) { bestCost = cost; bestAxis = a; bestSplit = b; }
             }
         }
-        // leaf decision: at most 3 primitives per leaf (3-bit unary count in the wide node's meta byte)
-        if (count <= 3) {
-            float leafCost = box.area() * (float)count;
-            if (bestAxis < 0 || bestCost + box.area() * 0.3f >= leafCost) return ni;
-        }
+        // the binary tree goes down to single primitives; the wide collapse below decides where leaves (<= 3 primitives) form
         int mid;
         if (bestAxis >= 0) {
             float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
@@ -116,7 +112,7 @@ struct Builder {
         }
         int l = build_rec(first, mid - first);
         int r = build_rec(mid, first + count - mid);
-        b2[ni].left = l; b2[ni].right = r; b2[ni].count = 0;
+        b2[ni].left = l; b2[ni].right = r;
         return ni;
     }
 };
@@ -252,10 +248,45 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
     B.b2.reserve((size_t)2 * N);
     B.build_rec(0, N);
 
-    // ---- 4. collapse to 8-wide, assign slots by octant, quantise, emit -------------------------------------------
+    // ---- 4. collapse to 8-wide with the SAH-optimal dynamic program of Ylitie, Karras & Laine (HPG 2017, section 4.1):
+    //   C(n,1) = min(C_leaf(n), C_internal(n)),  C_internal(n) = A_n c_node + min_k C(left,k) + C(right,8-k),
+    //   C(n,i) = min(C(n,i-1), min_k C(left,k) + C(right,i-k)),  i = 2..7,   C_leaf(n) = A_n P_n c_prim if P_n <= 3.
+    const int nb2 = (int)B.b2.size();
+    const float cNode = 1.0f, cPrim = 0.6f, INF = std::numeric_limits<float>::max();
+    std::vector<float> C((size_t)nb2 * 7); std::vector<uint8_t> D((size_t)nb2 * 7);
+    for (int n = nb2 - 1; n >= 0; n--) {   // children have larger indices than their parent
+        const B2Node& bn = B.b2[n];
+        const float A = bn.box.area();
+        float* Cn = &C[(size_t)n * 7]; uint8_t* Dn = &D[(size_t)n * 7];
+        if (bn.left < 0) { for (int i = 0; i < 7; i++) { Cn[i] = A * cPrim; Dn[i] = 0; } continue; }
+        const float* CL = &C[(size_t)bn.left * 7]; const float* CR = &C[(size_t)bn.right * 7];
+        float best = INF; int bk = 1;
+        for (int k = 1; k <= 7; k++) { float c = CL[k - 1] + CR[7 - k]; if (c < best) { best = c; bk = k; } }
+        const float cInt = best + A * cNode;
+        const float cLeaf = bn.count <= 3 ? A * (float)bn.count * cPrim : INF;
+        if (cLeaf <= cInt) { Cn[0] = cLeaf; Dn[0] = 0; } else { Cn[0] = cInt; Dn[0] = (uint8_t)bk; }
+        for (int i = 2; i <= 7; i++) {
+            float bi = Cn[i - 2]; int d = 0;
+            for (int k = 1; k < i; k++) { float c = CL[k - 1] + CR[i - k - 1]; if (c < bi) { bi = c; d = k; } }
+            Cn[i - 1] = bi; Dn[i - 1] = (uint8_t)d;
+        }
+    }
+    struct Child { int b2; bool leaf; };
+    struct Collector {
+        const std::vector<B2Node>& b2; const std::vector<uint8_t>& D;
+        void collect(int n, int i, Child* out, int& cnt) const {
+            const B2Node& bn = b2[n];
+            if (bn.left < 0) { out[cnt++] = {n, true}; return; }
+            if (i == 1) { out[cnt++] = {n, D[(size_t)n * 7] == 0}; return; }
+            int d = D[(size_t)n * 7 + i - 1];
+            if (d == 0) collect(n, i - 1, out, cnt);
+            else { collect(bn.left, d, out, cnt); collect(bn.right, i - d, out, cnt); }
+        }
+    } collector{B.b2, D};
+
     struct Work { int b2; int wide; };
     std::vector<Work> queue;
-    out.nodes.reserve((size_t)N / 3 + 16);
+    out.nodes.reserve((size_t)N / 6 + 16);
     out.prims.reserve((size_t)N);
     out.nodes.push_back(WideNode());
     queue.push_back({0, 0});
@@ -264,24 +295,24 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
     for (size_t qi = 0; qi < queue.size(); qi++) {
         const Work w = queue[qi];
         const B2Node& root = B.b2[w.b2];
-        int ch[8]; int nch = 0;
-        if (root.count > 0) { ch[nch++] = w.b2; }   // a single-leaf tree: one leaf child
+        Child ch[8]; int nch = 0;
+        if (root.left < 0 || (w.wide == 0 && root.count <= 3 && N <= 3)) { ch[nch++] = {w.b2, true}; }   // a tree of <= 3 primitives: one leaf child
         else {
-            ch[nch++] = root.left; ch[nch++] = root.right;
-            for (;;) {
-                int pick = -1; float bestA = -1.0f;
-                for (int i = 0; i < nch; i++) if (B.b2[ch[i]].count == 0) { float a = B.b2[ch[i]].box.area(); if (a > bestA) { bestA = a; pick = i; } }
-                if (pick < 0 || nch >= 8) break;
-                int c = ch[pick];
-                ch[pick] = B.b2[c].left; ch[nch++] = B.b2[c].right;
+            int k = D[(size_t)w.b2 * 7];
+            if (k == 0) {   // only the root can get here with a "leaf" decision: force an internal node
+                const float* CL = &C[(size_t)root.left * 7]; const float* CR = &C[(size_t)root.right * 7];
+                float best = INF; k = 1;
+                for (int kk = 1; kk <= 7; kk++) { float c = CL[kk - 1] + CR[7 - kk]; if (c < best) { best = c; k = kk; } }
             }
+            collector.collect(root.left, k, ch, nch);
+            collector.collect(root.right, 8 - k, ch, nch);
         }
         // slot assignment: slot s prefers the child lying furthest "against" the direction (sx,sy,sz), bit a of s set = negative axis a
         Aabb nb = root.box;
         float ncx[3] = {0.5f * (nb.lo[0] + nb.hi[0]), 0.5f * (nb.lo[1] + nb.hi[1]), 0.5f * (nb.lo[2] + nb.hi[2])};
         float cost[8][8]; int slotOf[8]; bool slotUsed[8] = {false, false, false, false, false, false, false, false}; bool chDone[8] = {false, false, false, false, false, false, false, false};
         for (int c = 0; c < nch; c++) {
-            const Aabb& cb = B.b2[ch[c]].box;
+            const Aabb& cb = B.b2[ch[c].b2].box;
             float cc[3] = {0.5f * (cb.lo[0] + cb.hi[0]) - ncx[0], 0.5f * (cb.lo[1] + cb.hi[1]) - ncx[1], 0.5f * (cb.lo[2] + cb.hi[2]) - ncx[2]};
             for (int s = 0; s < 8; s++) cost[c][s] = cc[0] * ((s & 1) ? -1.0f : 1.0f) + cc[1] * ((s & 2) ? -1.0f : 1.0f) + cc[2] * ((s & 4) ? -1.0f : 1.0f);
         }
@@ -291,32 +322,37 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
             chDone[bc] = true; slotUsed[bs] = true; slotOf[bc] = bs;
         }
         int childAt[8]; for (int s = 0; s < 8; s++) childAt[s] = -1;
-        for (int c = 0; c < nch; c++) childAt[slotOf[c]] = ch[c];
+        for (int c = 0; c < nch; c++) childAt[slotOf[c]] = c;
 
-        // quantisation frame
-        uint8_t eb[3]; double scale[3];
+        // quantisation frame: origin one quantum below the node's min, scale so that the node spans <= 252 quanta.
+        // Every child plane then quantises to 1..254 with room for the 0.01-quantum outward slack that covers the
+        // traversal's 2^-9-quantum decode error (byte_unit_float) without ever clamping at 0 / 255.
+        uint8_t eb[3]; double scale[3]; float pf[3];
         for (int a = 0; a < 3; a++) {
             double ext = (double)nb.hi[a] - (double)nb.lo[a];
             int e = -126;
-            if (ext > 0.0) { e = (int)std::ceil(std::log2(ext / 255.0)); while (ext / std::ldexp(1.0, e) > 255.0) e++; }
-            e = std::max(-126, std::min(127, e));
+            if (ext > 0.0) { e = (int)std::ceil(std::log2(ext / 252.0)); while (ext / std::ldexp(1.0, e) > 252.0) e++; }
+            e = std::max(-126, std::min(100, e));
             eb[a] = (uint8_t)(e + 127); scale[a] = std::ldexp(1.0, e);
+            pf[a] = (float)((double)nb.lo[a] - scale[a]);
+            if ((double)pf[a] > (double)nb.lo[a]) pf[a] = std::nextafterf(pf[a], -std::numeric_limits<float>::infinity());
         }
         uint8_t meta[8], qlo[3][8], qhi[3][8]; uint32_t imask = 0;
         uint32_t childBase = (uint32_t)out.nodes.size(), primBase = (uint32_t)out.prims.size();
         int primOff = 0;
         for (int s = 0; s < 8; s++) {
             meta[s] = 0; for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }
-            int c = childAt[s];
-            if (c < 0) continue;
+            if (childAt[s] < 0) continue;
+            const int c = ch[childAt[s]].b2;
+            const bool leafChild = ch[childAt[s]].leaf;
             const B2Node& cn = B.b2[c];
             for (int a = 0; a < 3; a++) {
-                double l = std::floor(((double)cn.box.lo[a] - (double)nb.lo[a]) / scale[a]);
-                double h = std::ceil(((double)cn.box.hi[a] - (double)nb.lo[a]) / scale[a]);
+                double l = std::floor(((double)cn.box.lo[a] - (double)pf[a]) / scale[a] - 0.01);
+                double h = std::ceil(((double)cn.box.hi[a] - (double)pf[a]) / scale[a] + 0.01);
                 qlo[a][s] = (uint8_t)std::max(0.0, std::min(255.0, l));
                 qhi[a][s] = (uint8_t)std::max(0.0, std::min(255.0, h));
             }
-            if (cn.count == 0) {
+            if (!leafChild) {
                 imask |= 1u << s;
                 meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 int wi = (int)out.nodes.size();
@@ -332,7 +368,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
             }
         }
         WideNode& wn = out.nodes[w.wide];
-        wn.n0 = make_uint4(fbits(nb.lo[0]), fbits(nb.lo[1]), fbits(nb.lo[2]), (uint32_t)eb[0] | ((uint32_t)eb[1] << 8) | ((uint32_t)eb[2] << 16) | (imask << 24));
+        wn.n0 = make_uint4(fbits(pf[0]), fbits(pf[1]), fbits(pf[2]), (uint32_t)eb[0] | ((uint32_t)eb[1] << 8) | ((uint32_t)eb[2] << 16) | (imask << 24));
         wn.n1 = make_uint4(childBase, primBase, pack4(meta), pack4(meta + 4));
         wn.n2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
         wn.n3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));

@@ -11,6 +11,9 @@
 // minimum of (tWorld, [same instance: tObj], rank).
 #pragma once
 #include "rt_core.h"
+#if defined(__CUDACC__)
+#include <cuda_fp16.h>
+#endif
 
 namespace rtx {
 
@@ -112,10 +115,25 @@ GenResult test_prim_general(const DeviceScene& sc, f3 o, f3 d, float4 q0, float4
     return res;
 }
 
-RT_HD float byte_to_float(uint32_t w, int j) { return (float)((w >> (8 * j)) & 0xFFu); }
+// Bytes J and K of w as the floats 1024 + b: ONE byte permute builds the half2 {0x64bb, 0x64bb} (fp16 1024 + b, exact),
+// two HADD2.F32 widen it.  No int->float conversion (slow XU pipe) and half the permutes of a per-byte decode, so the
+// box test leans on the FMA pipe instead of the saturated ALU pipe.  With O = o - 1024 a:  fma(m, a, O) = b * a + o.
+template <int J, int K> RT_HD void byte_pair_1024(uint32_t w, float& fj, float& fk) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t h2 = __byte_perm(w, 0x64646464u, 0x4040u | J | (K << 8));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
+    fj = f.x; fk = f.y;
+#else
+    fj = 1024.0f + (float)((w >> (8 * J)) & 0xFFu);
+    fk = 1024.0f + (float)((w >> (8 * K)) & 0xFFu);
+#endif
+}
 
-// One ray's traversal state.  init() then step() until it returns true.  A step = fetch one wide node,
-// test its 8 quantised child boxes, test the primitives of the leaf children that were hit, pop.
+// One ray's traversal state.  init(), then node_step() / prim_step() until done:
+//   node_step : fetch one wide node, test its 8 quantised child boxes, queue the primitives of the leaf children hit
+//   prim_step : test ONE queued primitive (the reference's exact intersectors and acceptance rules)
+// The kernel votes warp-wide on when to run prim_step so that the exact (expensive, divergent) primitive tests
+// execute with many lanes; step() = node_step + all its prim_steps, for single-ray use.
 // Closest hit: hit()/result() afterwards.  Any hit: occluded afterwards.
 template <bool ANY_HIT, bool COUNT>
 struct Traversal {
@@ -124,12 +142,12 @@ struct Traversal {
     uint32_t octinv;
     uint2 ngroup, tgroup;
     BestHit best;
-    bool occluded;
+    bool occluded, done;
 
     RT_HD void init(f3 o_, f3 d_, float tMax_, LaneStack& stack) {
         o = o_; d = d_; tMax = tMax_;
         best.t = ANY_HIT ? tMax_ : 1e30f; best.tObj = best.t; best.rank = 0xFFFFFFFFu; best.inst = -1; best.prim = -1; best.bu = 0.0f; best.bv = 0.0f;
-        occluded = false;
+        occluded = false; done = false;
         // box-test reciprocal: ours (never inf); the reference's 1e-8 substitution is kept for d == 0 (RTRay.cs:548-549)
         idir.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : (d.x < 0.0f ? -1e-20f : (d.x == 0.0f ? 1e-8f : 1e-20f)));
         idir.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : (d.y < 0.0f ? -1e-20f : (d.y == 0.0f ? 1e-8f : 1e-20f)));
@@ -140,103 +158,122 @@ struct Traversal {
         tgroup = make_uint2(0u, 0u);
     }
 
-    RT_HD bool step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
-        if (ngroup.y > 0x00FFFFFFu) {
-            const uint32_t hits = ngroup.y;
-            const int bit = rt_bfind(hits);
-            const uint32_t base = ngroup.x;
-            ngroup.y &= ~(1u << bit);
-            if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
-            const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
-            const uint32_t imaskP = hits & 0xFFu;
-            const uint32_t rel = (uint32_t)rt_popc(imaskP & ~(0xFFFFFFFFu << slot));
-            const WideNode* np = sc.nodes + (base + rel);
-            if (COUNT) cnt->nodes++;
-            const uint4 n0 = rt_ldg(&np->n0), n1 = rt_ldg(&np->n1), n2 = rt_ldg(&np->n2), n3 = rt_ldg(&np->n3), n4 = rt_ldg(&np->n4);
+    RT_HD bool has_prims() const { return tgroup.y != 0u; }
 
-            const bool nx = idir.x < 0.0f, ny = idir.y < 0.0f, nz = idir.z < 0.0f;
-            const uint32_t octinv4 = octinv * 0x01010101u;
-            const float sx = u2f((n0.w & 0xFFu) << 23), sy = u2f(((n0.w >> 8) & 0xFFu) << 23), sz = u2f(((n0.w >> 16) & 0xFFu) << 23);
-            const float aix = sx * idir.x, aiy = sy * idir.y, aiz = sz * idir.z;
-            const float ox = (u2f(n0.x) - o.x) * idir.x, oy = (u2f(n0.y) - o.y) * idir.y, oz = (u2f(n0.z) - o.z) * idir.z;
-            // near/far plane words chosen by the ray's sign, once per node
-            const uint32_t nearx0 = nx ? n3.z : n2.x, nearx1 = nx ? n3.w : n2.y, farx0 = nx ? n2.x : n3.z, farx1 = nx ? n2.y : n3.w;
-            const uint32_t neary0 = ny ? n4.x : n2.z, neary1 = ny ? n4.y : n2.w, fary0 = ny ? n2.z : n4.x, fary1 = ny ? n2.w : n4.y;
-            const uint32_t nearz0 = nz ? n4.z : n3.x, nearz1 = nz ? n4.w : n3.y, farz0 = nz ? n3.x : n4.z, farz1 = nz ? n3.y : n4.w;
-            const float tFar = best.t;
-            const float tMinRay = 0.001f;   // SceneDeviceViews.cs:37,131 (box tMin)
-            uint32_t hitmask = 0;
-#pragma unroll
-            for (int half = 0; half < 2; half++) {
-                const uint32_t meta4 = half ? n1.w : n1.z;
-                const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-                const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
-                const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
-                const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-                const uint32_t wnx = half ? nearx1 : nearx0, wfx = half ? farx1 : farx0;
-                const uint32_t wny = half ? neary1 : neary0, wfy = half ? fary1 : fary0;
-                const uint32_t wnz = half ? nearz1 : nearz0, wfz = half ? farz1 : farz0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const float t0x = rt_fma(byte_to_float(wnx, j), aix, ox), t1x = rt_fma(byte_to_float(wfx, j), aix, ox);
-                    const float t0y = rt_fma(byte_to_float(wny, j), aiy, oy), t1y = rt_fma(byte_to_float(wfy, j), aiy, oy);
-                    const float t0z = rt_fma(byte_to_float(wnz, j), aiz, oz), t1z = rt_fma(byte_to_float(wfz, j), aiz, oz);
-                    const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, tMinRay));
-                    const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tFar));
-                    // conservative: allow for the rounding of either side
-                    if (tn <= tf * 1.0000007f) {
-                        const uint32_t cb = (childBits4 >> (8 * j)) & 0xFFu;
-                        const uint32_t bi = (bitIndex4 >> (8 * j)) & 0xFFu;
-                        hitmask |= cb << bi;
-                    }
-                }
-            }
-            ngroup.x = n1.x;
-            ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
-            tgroup.x = n1.y;
-            tgroup.y = hitmask & 0x00FFFFFFu;
-        } else {
-            tgroup = ngroup;
-            ngroup = make_uint2(0u, 0u);
-        }
-
-        while (tgroup.y != 0u) {
-            const int bit = rt_bfind(tgroup.y);
-            tgroup.y &= ~(1u << bit);
-            const int pi = (int)tgroup.x + bit;
-            const PrimRec* pp = sc.prims + pi;
-            const float4 q0 = rt_ldg(&pp->q0), q1 = rt_ldg(&pp->q1), q2 = rt_ldg(&pp->q2);
-            const uint32_t meta = f2u(q2.w);
-            if ((meta & (PRIM_SPHERE | PRIM_XFORM | PRIM_ALPHA | PRIM_NO_CLOSEST)) == 0u) {
-                // fast path: plain triangle of an identity instance (object ray == world ray, bit for bit)
-                if (COUNT) cnt->tris++;
-                float t, bu, bv;
-                if (intersect_tri(o, d, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), &t, &bu, &bv)) {
-                    if (ANY_HIT) {
-                        if (t > 0.001f && t < tMax) { occluded = true; return true; }   // SceneDeviceViews.cs:292,317
-                    } else if (t > 0.001f) {                                            // :199
-                        const uint32_t rank = f2u(q1.w);
-                        const int inst = (int)(meta & PRIM_INST_MASK);
-                        if (better_hit(best, t, t, rank, inst)) {
-                            best.t = t; best.tObj = t; best.rank = rank; best.inst = inst; best.prim = pi; best.bu = bu; best.bv = bv;
-                        }
-                    }
-                }
-            } else {
-                if (COUNT) { if (meta & PRIM_SPHERE) cnt->spheres++; else cnt->tris++; }
-                const GenResult r = test_prim_general<ANY_HIT>(sc, o, d, q0, q1, q2, meta, tMax, best.t, best.tObj, best.rank, best.inst);
-                if (r.accept) {
-                    if (ANY_HIT) { occluded = true; return true; }
-                    best.t = r.tW; best.tObj = r.tO; best.rank = f2u(q1.w); best.inst = (int)(meta & PRIM_INST_MASK); best.prim = pi; best.bu = r.bu; best.bv = r.bv;
-                }
-            }
-        }
-
+    // next node group from the stack, or done
+    RT_HD void advance(LaneStack& stack) {
         if (ngroup.y <= 0x00FFFFFFu) {
-            if (stack.sp == 0) return true;
-            ngroup = stack.pop();
+            if (stack.sp == 0) done = true;
+            else ngroup = stack.pop();
         }
-        return false;
+    }
+
+    // one child: slab test on the decoded quantised planes (m = 1024 + q), then its bits into the hit mask
+    template <int J>
+    RT_HD void child_test(float nxq, float fxq, float nyq, float fyq, float nzq, float fzq, float Ax, float Ay, float Az,
+                          float Ox, float Oy, float Oz, float tFar, uint32_t childBits4, uint32_t bitIndex4, uint32_t& hitmask) const {
+        const float t0x = rt_fma(nxq, Ax, Ox), t1x = rt_fma(fxq, Ax, Ox);
+        const float t0y = rt_fma(nyq, Ay, Oy), t1y = rt_fma(fyq, Ay, Oy);
+        const float t0z = rt_fma(nzq, Az, Oz), t1z = rt_fma(fzq, Az, Oz);
+        const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.001f));   // box tMin: SceneDeviceViews.cs:37,131
+        const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tFar));
+        // conservative: allow for the rounding of either side (quantised planes carry >= 0.01 quantum of slack, rt_bvh.cpp)
+        if (tn <= tf * 1.0000007f) {
+            const uint32_t cb = (childBits4 >> (8 * J)) & 0xFFu;
+            const uint32_t bi = (bitIndex4 >> (8 * J)) & 0xFFu;
+            hitmask |= cb << bi;
+        }
+    }
+    // four children whose plane bytes sit in the same six words
+    RT_HD void quad_test(uint32_t wnx, uint32_t wfx, uint32_t wny, uint32_t wfy, uint32_t wnz, uint32_t wfz, uint32_t meta4, uint32_t octinv4,
+                         float Ax, float Ay, float Az, float Ox, float Oy, float Oz, float tFar, uint32_t& hitmask) const {
+        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
+        const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
+        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
+        float nx0, nx1, nx2, nx3, fx0, fx1, fx2, fx3, ny0, ny1, ny2, ny3, fy0, fy1, fy2, fy3, nz0, nz1, nz2, nz3, fz0, fz1, fz2, fz3;
+        byte_pair_1024<0, 1>(wnx, nx0, nx1); byte_pair_1024<2, 3>(wnx, nx2, nx3); byte_pair_1024<0, 1>(wfx, fx0, fx1); byte_pair_1024<2, 3>(wfx, fx2, fx3);
+        byte_pair_1024<0, 1>(wny, ny0, ny1); byte_pair_1024<2, 3>(wny, ny2, ny3); byte_pair_1024<0, 1>(wfy, fy0, fy1); byte_pair_1024<2, 3>(wfy, fy2, fy3);
+        byte_pair_1024<0, 1>(wnz, nz0, nz1); byte_pair_1024<2, 3>(wnz, nz2, nz3); byte_pair_1024<0, 1>(wfz, fz0, fz1); byte_pair_1024<2, 3>(wfz, fz2, fz3);
+        child_test<0>(nx0, fx0, ny0, fy0, nz0, fz0, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
+        child_test<1>(nx1, fx1, ny1, fy1, nz1, fz1, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
+        child_test<2>(nx2, fx2, ny2, fy2, nz2, fz2, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
+        child_test<3>(nx3, fx3, ny3, fy3, nz3, fz3, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
+    }
+
+    // precondition: !done, tgroup.y == 0 (so ngroup.y > 0x00FFFFFF)
+    RT_HD void node_step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
+        const uint32_t hits = ngroup.y;
+        const int bit = rt_bfind(hits);
+        const uint32_t base = ngroup.x;
+        ngroup.y &= ~(1u << bit);
+        if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
+        const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
+        const uint32_t imaskP = hits & 0xFFu;
+        const uint32_t rel = (uint32_t)rt_popc(imaskP & ~(0xFFFFFFFFu << slot));
+        const WideNode* np = sc.nodes + (base + rel);
+        if (COUNT) cnt->nodes++;
+        const uint4 n0 = rt_ldg(&np->n0), n1 = rt_ldg(&np->n1), n2 = rt_ldg(&np->n2), n3 = rt_ldg(&np->n3), n4 = rt_ldg(&np->n4);
+
+        const bool nx = idir.x < 0.0f, ny = idir.y < 0.0f, nz = idir.z < 0.0f;
+        const uint32_t octinv4 = octinv * 0x01010101u;
+        // a = 2^e / d,  O = (p - o) / d - 1024 a   (see byte_pair_1024)
+        const float Ax = u2f((n0.w & 0xFFu) << 23) * idir.x, Ay = u2f(((n0.w >> 8) & 0xFFu) << 23) * idir.y, Az = u2f(((n0.w >> 16) & 0xFFu) << 23) * idir.z;
+        const float Ox = rt_fma(u2f(n0.x) - o.x, idir.x, -1024.0f * Ax), Oy = rt_fma(u2f(n0.y) - o.y, idir.y, -1024.0f * Ay), Oz = rt_fma(u2f(n0.z) - o.z, idir.z, -1024.0f * Az);
+        // near/far plane words chosen by the ray's sign, once per node
+        const uint32_t nearx0 = nx ? n3.z : n2.x, nearx1 = nx ? n3.w : n2.y, farx0 = nx ? n2.x : n3.z, farx1 = nx ? n2.y : n3.w;
+        const uint32_t neary0 = ny ? n4.x : n2.z, neary1 = ny ? n4.y : n2.w, fary0 = ny ? n2.z : n4.x, fary1 = ny ? n2.w : n4.y;
+        const uint32_t nearz0 = nz ? n4.z : n3.x, nearz1 = nz ? n4.w : n3.y, farz0 = nz ? n3.x : n4.z, farz1 = nz ? n3.y : n4.w;
+        const float tFar = best.t;
+        uint32_t hitmask = 0;
+        quad_test(nearx0, farx0, neary0, fary0, nearz0, farz0, n1.z, octinv4, Ax, Ay, Az, Ox, Oy, Oz, tFar, hitmask);
+        quad_test(nearx1, farx1, neary1, fary1, nearz1, farz1, n1.w, octinv4, Ax, Ay, Az, Ox, Oy, Oz, tFar, hitmask);
+        ngroup.x = n1.x;
+        ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+        tgroup.x = n1.y;
+        tgroup.y = hitmask & 0x00FFFFFFu;
+        if (tgroup.y == 0u) advance(stack);
+    }
+
+    // precondition: !done, tgroup.y != 0
+    RT_HD void prim_step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
+        const int bit = rt_bfind(tgroup.y);
+        tgroup.y &= ~(1u << bit);
+        const int pi = (int)tgroup.x + bit;
+        const PrimRec* pp = sc.prims + pi;
+        const float4 q0 = rt_ldg(&pp->q0), q1 = rt_ldg(&pp->q1), q2 = rt_ldg(&pp->q2);
+        const uint32_t meta = f2u(q2.w);
+        if ((meta & (PRIM_SPHERE | PRIM_XFORM | PRIM_ALPHA | PRIM_NO_CLOSEST)) == 0u) {
+            // fast path: plain triangle of an identity instance (object ray == world ray, bit for bit)
+            if (COUNT) cnt->tris++;
+            float t, bu, bv;
+            if (intersect_tri(o, d, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), &t, &bu, &bv)) {
+                if (ANY_HIT) {
+                    if (t > 0.001f && t < tMax) { occluded = true; done = true; return; }   // SceneDeviceViews.cs:292,317
+                } else if (t > 0.001f) {                                                    // :199
+                    const uint32_t rank = f2u(q1.w);
+                    const int inst = (int)(meta & PRIM_INST_MASK);
+                    if (better_hit(best, t, t, rank, inst)) {
+                        best.t = t; best.tObj = t; best.rank = rank; best.inst = inst; best.prim = pi; best.bu = bu; best.bv = bv;
+                    }
+                }
+            }
+        } else {
+            if (COUNT) { if (meta & PRIM_SPHERE) cnt->spheres++; else cnt->tris++; }
+            const GenResult r = test_prim_general<ANY_HIT>(sc, o, d, q0, q1, q2, meta, tMax, best.t, best.tObj, best.rank, best.inst);
+            if (r.accept) {
+                if (ANY_HIT) { occluded = true; done = true; return; }
+                best.t = r.tW; best.tObj = r.tO; best.rank = f2u(q1.w); best.inst = (int)(meta & PRIM_INST_MASK); best.prim = pi; best.bu = r.bu; best.bv = r.bv;
+            }
+        }
+        if (tgroup.y == 0u) advance(stack);
+    }
+
+    // one node and all of its primitives; returns true when the traversal is finished
+    RT_HD bool step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
+        node_step(sc, stack, cnt);
+        while (!done && tgroup.y != 0u) prim_step(sc, stack, cnt);
+        return done;
     }
 
     RT_HD bool hit() const { return best.t < 1e29f; }   // SceneDeviceViews.cs:85

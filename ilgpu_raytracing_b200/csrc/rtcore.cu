@@ -31,6 +31,9 @@ using namespace rtx;
 #define RT_EXTEND_MIN_BLOCKS 5
 #endif
 #define RT_EXTEND_BATCH 96   // ray indices a warp takes from the global queue per atomic
+#ifndef RT_PRIM_VOTE
+#define RT_PRIM_VOTE 12      // lanes that must have a primitive queued before the warp runs a primitive phase
+#endif
 
 struct DeviceStats {   // zeroed at the start of every rt_render
     unsigned long long raysPrimary, raysBounce, raysShadow, wideNodes, tris, spheres;
@@ -117,13 +120,22 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        // ---- one traversal step per active lane ----
-        if (active) {
-            if (tr.step(a.sc, stack, &cnt)) {
-                if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
-                else { const HitRec h = tr.result(); __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv)); }
-                active = false;
+        // ---- node phase: lanes without queued primitives advance by one wide node ----
+        if (active && !tr.has_prims()) tr.node_step(a.sc, stack, &cnt);
+        // ---- primitive phase, voted warp-wide: the exact intersectors are long and divergent, so run them only when
+        //      enough lanes have a primitive queued (or nobody can do node work); lanes holding primitives wait ----
+        const bool wantPrim = active && !tr.done && tr.has_prims();
+        const unsigned pm = __ballot_sync(FULL, wantPrim);
+        if (pm != 0u) {
+            const unsigned nm = __ballot_sync(FULL, active && !tr.done && !tr.has_prims());
+            if (__popc(pm) >= RT_PRIM_VOTE || nm == 0u) {
+                if (wantPrim) tr.prim_step(a.sc, stack, &cnt);
             }
+        }
+        if (active && tr.done) {
+            if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
+            else { const HitRec h = tr.result(); __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv)); }
+            active = false;
         }
     }
     if (COUNT) {

@@ -13,7 +13,8 @@ import numpy as np
 from . import layouts as L
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_PKG, "librtcore_b200.so")
+# RTCORE_B200_LIB: developer override used by the tuning sweeps under tests/ (an alternative BUILD of the same CUDA library)
+_LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b200.so")
 
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",

@@ -1,0 +1,25 @@
+"""One timing run of the currently selected library build (RTCORE_B200_LIB): C3 primary-only and C4 at 4 spp."""
+import json
+import sys
+
+sys.path.insert(0, ".")
+from ilgpu_raytracing_b200 import engine, layouts as L  # noqa: E402
+import bench  # noqa: E402
+
+W, H = 3840, 2160
+rdr = engine.RTRenderer(0, W, H)
+rdr.scene.load_spec(bench.make_spec("terrain+spheres"))
+rdr.Commit()
+cam = engine.config_camera("C3", W, H)
+ctx = rdr.native
+out = {}
+for tag, spp, depth in (("C3", 1, 0), ("C4x4", 4, 8)):
+    cfg = L.make_render_config(W, H, spp=spp, max_depth=depth, flags=L.RT_FLAG_KERNEL_TIMING)
+    best = None
+    for _ in range(4):
+        ctx.render(cam, cfg); ctx.sync(); s = ctx.stats()
+        if best is None or s["lastRenderMs"] < best["lastRenderMs"]:
+            best = s
+    rays = best["raysPrimary"] + best["raysBounce"] + best["raysShadow"]
+    out[tag] = dict(ms=round(best["lastRenderMs"], 3), trace_ms=round(best["lastTraceMs"], 3), grays_all=round(rays / best["lastRenderMs"] / 1e6, 3))
+print(json.dumps(out))

@@ -1,0 +1,25 @@
+"""Manual tuning sweep (under gpurun): build k_extend variants with different macros and time C3 / C4-lite."""
+import json
+import os
+import subprocess
+import sys
+
+sys.path.insert(0, ".")
+from ilgpu_raytracing_b200 import build  # noqa: E402
+
+variants = [a.split(",") for a in sys.argv[1:]] or [["base"]]
+results = {}
+for v in variants:
+    name = "_".join(v)
+    so = f"/tmp/librtcore_{name}.so"
+    defs = [f"-D{d}" for d in v if "=" in d]
+    cmd = ["nvcc"] + build.NVCC_FLAGS + defs + ["-o", so] + build.CORE_SRCS
+    subprocess.run(cmd, check=True)
+    env = dict(os.environ, RTCORE_B200_LIB=so)
+    out = subprocess.run([sys.executable, "tests/gpu_variant_run.py"], env=env, capture_output=True, text=True)
+    try:
+        results[name] = json.loads(out.stdout.strip().splitlines()[-1])
+    except Exception:
+        results[name] = {"error": out.stderr[-400:]}
+    print(name, results[name], flush=True)
+json.dump(results, open("gpurun_out/variants.json", "w"), indent=1)
