@@ -153,6 +153,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
         int ii = instOrder[io];
         const RtInstanceRecord& ir = d.instances[ii];
         const bool ident = is_identity(ir);
+        if (ir.uniformScale > out.stats.maxInstanceScale) out.stats.maxInstanceScale = ir.uniformScale;
         double w2oInv[12];
         if (!ident && !invert_affine(ir.worldToObject, w2oInv)) { err = "instance worldToObject is singular"; return false; }
         const bool sph = ir.type == RT_BLAS_SPHERESET;
@@ -377,7 +378,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
     out.stats.nWideNodes = (int64_t)out.nodes.size();
     out.stats.maxDepth = std::max(1, maxDepthSeen);
     for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = B.b2[0].box.lo[a]; out.stats.sceneHi[a] = B.b2[0].box.hi[a]; }
-    if (out.stats.maxDepth > RT_STACK_TOTAL - 2) { err = "wide BVH deeper than the traversal stack"; return false; }
+    if (out.stats.maxDepth > RT_STACK_ENTRIES - 2) { err = "wide BVH deeper than the traversal stack"; return false; }
     if ((int64_t)out.prims.size() != (int64_t)N) { err = "internal: primitive count mismatch"; return false; }
     return true;
 }

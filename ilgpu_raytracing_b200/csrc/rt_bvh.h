@@ -11,6 +11,7 @@ namespace rtx {
 struct HostBvhStats {
     int64_t nPrims = 0, nTris = 0, nSpheres = 0, nWideNodes = 0;
     int maxDepth = 0;
+    float maxInstanceScale = 1.0f;   // max(1, uniformScale of every instance reached from the TLAS)
     float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0};
 };
 

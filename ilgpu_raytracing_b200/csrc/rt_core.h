@@ -229,6 +229,10 @@ struct DeviceScene {
     const RtRGBA32* texels;
     const RtTexInfo* texInfos;    int nTexInfos;   // "Length" after AllocateOrEmpty (>= 1)
     int triMaterials;             // RT_FLAG_TRI_MATERIALS
+    // max(1, largest instance uniformScale): the reference reports tWorld = tObj / scale (SceneDeviceViews.cs:67) although the
+    // un-normalised object ray already runs in world parameter, so a hit of an instance scaled by s carries t = distance / s;
+    // boxes (true distances) are therefore culled against best.t * tFarScale.  Exactly 1.0 (a no-op) for rigid instances.
+    float tFarScale;
 };
 
 // ----------------------------------------------------------------------------- instance transforms (SceneDeviceViews.cs:475-493)

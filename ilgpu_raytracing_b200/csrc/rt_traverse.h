@@ -19,33 +19,35 @@ namespace rtx {
 
 struct TraceCounters { uint32_t nodes, tris, spheres; };
 
-// Per-lane traversal stack.  Device: first RT_SMEM_STACK entries live in shared memory (strided by
-// the block size so lanes hit distinct banks), the rest spill to local memory.  Host: plain array.
-#ifndef RT_SMEM_STACK
-#define RT_SMEM_STACK 12
+// Per-lane traversal stack: RT_STACK_ENTRIES (node group, hit mask) pairs.  Device: shared memory, strided by the
+// block size so the lanes of a warp hit distinct banks; no local-memory spill path, so push / pop are branch-free
+// (rt_bvh.cpp refuses trees deeper than the stack).  Host (tests/hostsim): plain array.
+#ifndef RT_STACK_ENTRIES
+#define RT_STACK_ENTRIES 20
 #endif
-#define RT_STACK_TOTAL 40
 struct LaneStack {
 #if defined(__CUDACC__)
-    uint2* smem;      // &shared[threadIdx.x], stride = blockDim.x
-    int stride;
-    uint2 spill[RT_STACK_TOTAL - RT_SMEM_STACK];
+    uint2* smem;      // &shared[threadIdx.x]
+    int stride;       // blockDim.x
     int sp;
-    RT_HD void push(uint2 v) {
-        if (sp < RT_SMEM_STACK) smem[sp * stride] = v; else spill[sp - RT_SMEM_STACK] = v;
-        sp++;
-    }
-    RT_HD uint2 pop() {
-        sp--;
-        return (sp < RT_SMEM_STACK) ? smem[sp * stride] : spill[sp - RT_SMEM_STACK];
-    }
+    RT_HD void store_top(uint2 v) { smem[sp * stride] = v; }
+    RT_HD uint2 load_below() const { return smem[(sp > 0 ? sp - 1 : 0) * stride]; }
 #else
-    uint2 all[RT_STACK_TOTAL];
+    uint2 all[RT_STACK_ENTRIES + 1];
     int sp;
-    RT_HD void push(uint2 v) { all[sp++] = v; }
-    RT_HD uint2 pop() { return all[--sp]; }
+    RT_HD void store_top(uint2 v) { all[sp] = v; }
+    RT_HD uint2 load_below() const { return all[sp > 0 ? sp - 1 : 0]; }
 #endif
 };
+
+// box-test reciprocal of a ray direction: ours (never inf); the reference's 1e-8 substitution is kept for d == 0 (RTRay.cs:548-549)
+RT_HD f3 box_idir(f3 d) {
+    f3 i;
+    i.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : (d.x < 0.0f ? -1e-20f : (d.x == 0.0f ? 1e-8f : 1e-20f)));
+    i.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : (d.y < 0.0f ? -1e-20f : (d.y == 0.0f ? 1e-8f : 1e-20f)));
+    i.z = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : (d.z < 0.0f ? -1e-20f : (d.z == 0.0f ? 1e-8f : 1e-20f)));
+    return i;
+}
 
 template <typename T> RT_HD T rt_ldg(const T* p) {
 #if defined(__CUDA_ARCH__)
@@ -144,14 +146,10 @@ struct Traversal {
     BestHit best;
     bool occluded, done;
 
-    RT_HD void init(f3 o_, f3 d_, float tMax_, LaneStack& stack) {
-        o = o_; d = d_; tMax = tMax_;
+    RT_HD void init(f3 o_, f3 d_, f3 idir_, float tMax_, LaneStack& stack) {
+        o = o_; d = d_; idir = idir_; tMax = tMax_;
         best.t = ANY_HIT ? tMax_ : 1e30f; best.tObj = best.t; best.rank = 0xFFFFFFFFu; best.inst = -1; best.prim = -1; best.bu = 0.0f; best.bv = 0.0f;
         occluded = false; done = false;
-        // box-test reciprocal: ours (never inf); the reference's 1e-8 substitution is kept for d == 0 (RTRay.cs:548-549)
-        idir.x = 1.0f / (fabsf(d.x) > 1e-20f ? d.x : (d.x < 0.0f ? -1e-20f : (d.x == 0.0f ? 1e-8f : 1e-20f)));
-        idir.y = 1.0f / (fabsf(d.y) > 1e-20f ? d.y : (d.y < 0.0f ? -1e-20f : (d.y == 0.0f ? 1e-8f : 1e-20f)));
-        idir.z = 1.0f / (fabsf(d.z) > 1e-20f ? d.z : (d.z < 0.0f ? -1e-20f : (d.z == 0.0f ? 1e-8f : 1e-20f)));
         octinv = 7u - ((idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u));
         stack.sp = 0;
         ngroup = make_uint2(0u, 0x80000000u);   // "child 7^octinv of a virtual parent whose child block starts at node 0" = the root
@@ -160,12 +158,13 @@ struct Traversal {
 
     RT_HD bool has_prims() const { return tgroup.y != 0u; }
 
-    // next node group from the stack, or done
+    // next node group from the stack, or done (selects only: every lane of the warp runs this together)
     RT_HD void advance(LaneStack& stack) {
-        if (ngroup.y <= 0x00FFFFFFu) {
-            if (stack.sp == 0) done = true;
-            else ngroup = stack.pop();
-        }
+        const uint2 top = stack.load_below();
+        const bool need = ngroup.y <= 0x00FFFFFFu;
+        const bool empty = stack.sp == 0;
+        done = done || (need && empty);
+        if (need && !empty) { ngroup = top; stack.sp--; }
     }
 
     // one child: slab test on the decoded quantised planes (m = 1024 + q), then its bits into the hit mask
@@ -207,7 +206,8 @@ struct Traversal {
         const int bit = rt_bfind(hits);
         const uint32_t base = ngroup.x;
         ngroup.y &= ~(1u << bit);
-        if (ngroup.y > 0x00FFFFFFu) stack.push(ngroup);
+        stack.store_top(ngroup);                          // unconditional store; it only counts if sp moves
+        stack.sp += (ngroup.y > 0x00FFFFFFu) ? 1 : 0;
         const uint32_t slot = (uint32_t)(bit - 24) ^ octinv;
         const uint32_t imaskP = hits & 0xFFu;
         const uint32_t rel = (uint32_t)rt_popc(imaskP & ~(0xFFFFFFFFu << slot));
@@ -224,7 +224,7 @@ struct Traversal {
         const uint32_t nearx0 = nx ? n3.z : n2.x, nearx1 = nx ? n3.w : n2.y, farx0 = nx ? n2.x : n3.z, farx1 = nx ? n2.y : n3.w;
         const uint32_t neary0 = ny ? n4.x : n2.z, neary1 = ny ? n4.y : n2.w, fary0 = ny ? n2.z : n4.x, fary1 = ny ? n2.w : n4.y;
         const uint32_t nearz0 = nz ? n4.z : n3.x, nearz1 = nz ? n4.w : n3.y, farz0 = nz ? n3.x : n4.z, farz1 = nz ? n3.y : n4.w;
-        const float tFar = best.t;
+        const float tFar = best.t * sc.tFarScale;
         uint32_t hitmask = 0;
         quad_test(nearx0, farx0, neary0, fary0, nearz0, farz0, n1.z, octinv4, Ax, Ay, Az, Ox, Oy, Oz, tFar, hitmask);
         quad_test(nearx1, farx1, neary1, fary1, nearz1, farz1, n1.w, octinv4, Ax, Ay, Az, Ox, Oy, Oz, tFar, hitmask);
@@ -286,7 +286,7 @@ template <bool ANY_HIT, bool COUNT>
 RT_HD bool trace_wide(const DeviceScene& sc, f3 o, f3 d, float tMax, LaneStack& stack, HitRec* out, TraceCounters* cnt) {
     if (sc.nNodes <= 0) { if (!ANY_HIT) { out->t = 1e30f; out->prim = -1; out->bu = 0.0f; out->bv = 0.0f; } return false; }
     Traversal<ANY_HIT, COUNT> tr;
-    tr.init(o, d, tMax, stack);
+    tr.init(o, d, box_idir(d), tMax, stack);
     while (!tr.step(sc, stack, cnt)) {}
     if (ANY_HIT) return tr.occluded;
     *out = tr.result();

@@ -40,8 +40,12 @@ struct WaveBuffers {
     uint8_t *segCountOut, *termCodeOut; uint32_t* pathHashOut;
 };
 
-struct RayQueue { float4* o; float4* d; };                 // o.w = path slot (int bits)
-struct ShadowQueue { float4* o; float4* d; float4* c; };   // c.xyz = throughput * f_over_p * W
+// Ray queues (SoA of float4): o.w = path slot (int bits); inv = the box-test reciprocal of d (box_idir), computed
+// once by the producer so the persistent extend kernel starts a ray with three 128-bit loads and no divisions.
+struct RayQueue { float4* o; float4* d; float4* inv; };
+struct ShadowQueue { float4* o; float4* d; float4* inv; float4* c; };   // c.xyz = throughput * f_over_p * W
+
+RT_HD float4 box_idir4(f3 d) { const f3 i = box_idir(d); return make_float4(i.x, i.y, i.z, 0.0f); }
 
 RT_HD uint32_t fnv_fold(uint32_t h, uint32_t v) { return (h ^ v) * 16777619u; }
 
@@ -73,6 +77,7 @@ RT_HD void generate_primary(const FrameConst& fc, const RayQueue& q, int i) {
     f3 d = primary_dir(fc, x, y);
     q.o[i] = make_float4(fc.camOrigin.x, fc.camOrigin.y, fc.camOrigin.z, u2f((uint32_t)i));
     q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    q.inv[i] = box_idir4(d);
 }
 
 // ------------------------------------------------------------------------------------------------ primary finish
@@ -145,6 +150,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
             int k = queue_alloc(shCount);
             shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)path));
             shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, 0.0f);
+            shQ.inv[k] = box_idir4(s.d);
             shQ.c[k] = make_float4(c.x, c.y, c.z, 0.0f);
         }
         f3 wi = sample_hemisphere_cosine(v.nrm, rng);   // :302
@@ -160,6 +166,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
     int k = queue_alloc(nextCount);
     nextQ.o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f((uint32_t)path));
     nextQ.d[k] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+    nextQ.inv[k] = box_idir4(ray.d);
     return true;
 }
 

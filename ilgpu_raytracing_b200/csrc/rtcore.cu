@@ -31,8 +31,11 @@ using namespace rtx;
 #define RT_EXTEND_MIN_BLOCKS 5
 #endif
 #define RT_EXTEND_BATCH 96   // ray indices a warp takes from the global queue per atomic
+#ifndef RT_NODE_STEPS
+#define RT_NODE_STEPS 2       // node steps per loop iteration (amortises the refill / vote / finalise overhead)
+#endif
 #ifndef RT_PRIM_VOTE
-#define RT_PRIM_VOTE 12      // lanes that must have a primitive queued before the warp runs a primitive phase
+#define RT_PRIM_VOTE 1       // lanes that must have a primitive queued before the warp runs a primitive phase (sweep: 1 is best)
 #endif
 
 struct DeviceStats {   // zeroed at the start of every rt_render
@@ -41,7 +44,7 @@ struct DeviceStats {   // zeroed at the start of every rt_render
 
 struct ExtendArgs {
     DeviceScene sc;
-    const float4* rayO; const float4* rayD;
+    const float4* rayO; const float4* rayD; const float4* rayI;   // origin | path slot, direction, box-test reciprocal
     const int* count;          // number of rays in the queue (device memory: written by the producing kernel)
     int* work;                 // global fetch cursor for this launch (zeroed per frame)
     HitRec* hits;              // closest: one record per ray
@@ -110,8 +113,8 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
                 const int r = __popc(idle & ltMask);
                 if (r < take) {
                     myRay = poolNext + r;
-                    const float4 ro = __ldcs(a.rayO + myRay), rd = __ldcs(a.rayD + myRay);
-                    tr.init(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), ANY_HIT ? 1e29f : 1e30f, stack);   // shadow tMax: RTRay.cs:623
+                    const float4 ro = __ldcs(a.rayO + myRay), rd = __ldcs(a.rayD + myRay), ri = __ldcs(a.rayI + myRay);
+                    tr.init(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), mk3(ri.x, ri.y, ri.z), ANY_HIT ? 1e29f : 1e30f, stack);   // shadow tMax: RTRay.cs:623
                     active = true;
                 }
             }
@@ -120,8 +123,10 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         }
         if (__ballot_sync(FULL, active) == 0u) break;
 
-        // ---- node phase: lanes without queued primitives advance by one wide node ----
-        if (active && !tr.has_prims()) tr.node_step(a.sc, stack, &cnt);
+        // ---- node phase: lanes without queued primitives advance by up to RT_NODE_STEPS wide nodes ----
+#pragma unroll
+        for (int ns = 0; ns < RT_NODE_STEPS; ns++)
+            if (active && !tr.done && !tr.has_prims()) tr.node_step(a.sc, stack, &cnt);
         // ---- primitive phase, voted warp-wide: the exact intersectors are long and divergent, so run them only when
         //      enough lanes have a primitive queued (or nobody can do node work); lanes holding primitives wait ----
         const bool wantPrim = active && !tr.done && tr.has_prims();
@@ -244,7 +249,7 @@ struct rt_ctx {
     DevBuf<int> rgba8, objId; DevBuf<float> depth; DevBuf<float4> radiance, accum;
     // per path
     size_t pathCap = 0;
-    DevBuf<float4> stThr, stLi, qO[2], qD[2], shO, shD, shC; DevBuf<HitRec> hits; DevBuf<uint32_t> pathHash;
+    DevBuf<float4> stThr, stLi, qO[2], qD[2], qI[2], shO, shD, shI, shC; DevBuf<HitRec> hits; DevBuf<uint32_t> pathHash;
     // AOV outputs
     DevBuf<uint8_t> segOut, termOut; DevBuf<uint32_t> hashOut;
     // scratch for scattered read-backs
@@ -311,7 +316,7 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
     c->stream = c->ownStream;
     CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
-    c->extendSmem = (size_t)RT_SMEM_STACK * RT_EXTEND_THREADS * sizeof(uint2);
+    c->extendSmem = (size_t)RT_STACK_ENTRIES * RT_EXTEND_THREADS * sizeof(uint2);
     int perSm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
     if (perSm < 1) perSm = 1;
@@ -329,7 +334,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->pixelMap.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
-    c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); } c->shO.release(); c->shD.release(); c->shC.release();
+    c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); c->qI[b].release(); } c->shO.release(); c->shD.release(); c->shI.release(); c->shC.release();
     c->hits.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release();
     for (auto ev : c->traceEvents) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
@@ -380,6 +385,7 @@ RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
     CUDA_TRY(upload_or_one(c->texels, d->texels, d->nTexels, st, nullptr)); ds.texels = c->texels.p;
     CUDA_TRY(upload_or_one(c->texInfos, d->texInfos, d->nTexInfos, st, &ds.nTexInfos)); ds.texInfos = c->texInfos.p;
     ds.triMaterials = 0;
+    ds.tFarScale = bvh.stats.maxInstanceScale;
     CUDA_TRY(cudaStreamSynchronize(st));   // host arrays are only borrowed for the duration of the call
     c->bvhStats = bvh.stats;
     c->bvhBytes = bvh.nodes.size() * sizeof(WideNode) + bvh.prims.size() * sizeof(PrimRec);
@@ -415,8 +421,8 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
     const size_t P = std::max<size_t>(1, (size_t)c->npx * S);
     if (P > c->pathCap) {
         CUDA_TRY(c->stThr.ensure(P)); CUDA_TRY(c->stLi.ensure(P));
-        for (int b = 0; b < 2; b++) { CUDA_TRY(c->qO[b].ensure(P)); CUDA_TRY(c->qD[b].ensure(P)); }
-        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->shC.ensure(P)); CUDA_TRY(c->hits.ensure(P));
+        for (int b = 0; b < 2; b++) { CUDA_TRY(c->qO[b].ensure(P)); CUDA_TRY(c->qD[b].ensure(P)); CUDA_TRY(c->qI[b].ensure(P)); }
+        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->shI.ensure(P)); CUDA_TRY(c->shC.ensure(P)); CUDA_TRY(c->hits.ensure(P));
         c->pathCap = P;
     }
     c->aovs = (cfg->flags & RT_FLAG_PATH_AOVS) != 0;
@@ -479,35 +485,35 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
 
     if (npx > 0) {
         // ---- primary visibility -------------------------------------------------------------------------------------
-        RayQueue q0 = {c->qO[0].p, c->qD[0].p};
+        RayQueue q0 = {c->qO[0].p, c->qD[0].p, c->qI[0].p};
         int* primaryCount = c->counters.p + 0;
         int* primaryWork = c->counters.p + 1;
         k_generate_primary<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, q0, primaryCount); c->launches++;
         ExtendArgs ea; memset(&ea, 0, sizeof(ea));
-        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = c->hits.p; ea.wb = wb; ea.stats = c->dstats.p; ea.statSlot = 0;
+        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.rayI = q0.inv; ea.count = primaryCount; ea.work = primaryWork; ea.hits = c->hits.p; ea.wb = wb; ea.stats = c->dstats.p; ea.statSlot = 0;
         CUDA_TRY(launch_extend<false>(c, ea, count));
         k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, c->hits.p); c->launches++;
 
         // ---- integrator: batches of S samples, one wavefront iteration per depth ---------------------------------
-        ShadowQueue shq = {c->shO.p, c->shD.p, c->shC.p};
+        ShadowQueue shq = {c->shO.p, c->shD.p, c->shI.p, c->shC.p};
         for (int pass = 0; pass < nPasses; pass++) {
             const int s0 = pass * S, ns = std::min(S, spp - s0);
             const size_t nPaths = (size_t)npx * ns;
             int* ctr = c->counters.p + 2 + (size_t)pass * (cfg->maxDepth + 1) * 4;
             int cur = 0;
-            RayQueue nq = {c->qO[cur].p, c->qD[cur].p};
+            RayQueue nq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
             k_shade_first<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1); c->launches++;
             for (int depth = 1; depth <= cfg->maxDepth; depth++) {
                 int* prev = ctr + (size_t)(depth - 1) * 4;   // counts produced by the shade of depth-1
                 int* mine = ctr + (size_t)depth * 4;
-                RayQueue cq = {c->qO[cur].p, c->qD[cur].p};
+                RayQueue cq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
                 ExtendArgs sa; memset(&sa, 0, sizeof(sa));
-                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.count = prev + 1; sa.work = prev + 3; sa.shq = shq; sa.wb = wb; sa.stats = c->dstats.p; sa.statSlot = 2;
+                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.rayI = shq.inv; sa.count = prev + 1; sa.work = prev + 3; sa.shq = shq; sa.wb = wb; sa.stats = c->dstats.p; sa.statSlot = 2;
                 CUDA_TRY(launch_extend<true>(c, sa, count));
                 ExtendArgs ca; memset(&ca, 0, sizeof(ca));
-                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
+                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.rayI = cq.inv; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
                 CUDA_TRY(launch_extend<false>(c, ca, count));
-                RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p};
+                RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p, c->qI[cur ^ 1].p};
                 k_shade_next<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1); c->launches++;
                 cur ^= 1;
             }
@@ -666,3 +672,12 @@ RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
 }
 
 }   // extern "C"
+
+// ------------------------------------------------------------------------------------------------ ABI layout checks
+// The element layouts are the reference's device layouts; C# mirrors them with
+// [StructLayout(LayoutKind.Sequential)] (csharp/RtNative.cs).
+static_assert(sizeof(RtFloat3) == 12 && sizeof(RtFloat2) == 8 && sizeof(RtAffine3x4) == 48, "ABI layout");
+static_assert(sizeof(RtBvhNode) == 44 && sizeof(RtInstanceRecord) == 144 && sizeof(RtMaterialRecord) == 44 && sizeof(RtSphere) == 80, "ABI layout");
+static_assert(sizeof(RtMeshTri) == 12 && sizeof(RtMeshTriUV) == 12 && sizeof(RtRGBA32) == 4 && sizeof(RtTexInfo) == 12 && sizeof(RtCamera) == 92, "ABI layout");
+static_assert(sizeof(RtSceneDesc) == 15 * 16 && sizeof(RtRenderConfig) == 32 + 48 + 4 + 12 + 4 + 12, "ABI layout");
+static_assert(sizeof(WideNode) == 80 && sizeof(PrimRec) == 48 && sizeof(HitRec) == 16, "device layout");

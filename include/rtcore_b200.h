@@ -49,7 +49,7 @@ extern "C" {
 
 /* ------------------------------------------------------------------------- */
 /* Blittable element layouts == the reference's device element layouts.       */
-/* (sizes are static-asserted in csrc/abi_check.cpp and mirrored in C#)       */
+/* (sizes are static-asserted at the end of csrc/rtcore.cu and mirrored in C#)       */
 /* ------------------------------------------------------------------------- */
 
 /* Engine/Float3.cs:6-10 (12 B) */

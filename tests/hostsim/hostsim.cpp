@@ -43,7 +43,7 @@ HS_API HsScene* hs_scene_create(const RtSceneDesc* d) {
     ds.instances = s->instances.data(); ds.nInstances = (int)s->instances.size(); ds.spheres = s->spheres.data(); ds.nSpheres = (int)s->spheres.size();
     ds.texcoords = s->texcoords.data(); ds.triUVs = s->triUVs.data(); ds.triMatIndex = s->triMat.data();
     ds.materials = s->materials.data(); ds.nMaterials = (int)s->materials.size(); ds.texels = s->texels.data();
-    ds.texInfos = s->texInfos.data(); ds.nTexInfos = (int)s->texInfos.size(); ds.triMaterials = 0;
+    ds.texInfos = s->texInfos.data(); ds.nTexInfos = (int)s->texInfos.size(); ds.triMaterials = 0; ds.tFarScale = s->bvh.stats.maxInstanceScale;
     return s;
 }
 HS_API const char* hs_scene_error(HsScene* s) { return s->err.c_str(); }
@@ -95,8 +95,8 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
     std::vector<int> primId(npx), instId(npx); std::vector<float> primaryT(npx);
     std::vector<uint32_t> pathHash(P);
     std::vector<float4> radiance((size_t)W * H), accum((size_t)W * H);
-    std::vector<float4> qo[2], qd[2], so(P), sd(P), scv(P);
-    for (int b = 0; b < 2; b++) { qo[b].resize(P); qd[b].resize(P); }
+    std::vector<float4> qo[2], qd[2], qi[2], so(P), sd(P), si(P), scv(P);
+    for (int b = 0; b < 2; b++) { qo[b].resize(P); qd[b].resize(P); qi[b].resize(P); }
     std::vector<HitRec> hits(P);
     std::vector<int32_t> dummyI((size_t)W * H); std::vector<float> dummyF((size_t)W * H);
 
@@ -114,17 +114,17 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
     LaneStack st;
 
     // primary visibility
-    RayQueue q0 = {qo[0].data(), qd[0].data()};
+    RayQueue q0 = {qo[0].data(), qd[0].data(), qi[0].data()};
     for (int i = 0; i < npx; i++) generate_primary(fc, q0, i);
     for (int i = 0; i < npx; i++) { f3 o = mk3(q0.o[i].x, q0.o[i].y, q0.o[i].z), d = mk3(q0.d[i].x, q0.d[i].y, q0.d[i].z); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[i], &tc); flushCnt(); }
     for (int i = 0; i < npx; i++) primary_finish(fc, s->ds, wb, q0, hits.data(), i);
 
     // integrator, one batch of S samples at a time
-    ShadowQueue shq = {so.data(), sd.data(), scv.data()};
+    ShadowQueue shq = {so.data(), sd.data(), si.data(), scv.data()};
     for (int s0 = 0; s0 < spp; s0 += S) {
         const int ns = (s0 + S <= spp) ? S : (spp - s0);
         int cur = 0; int nNext = 0, nSh = 0;
-        RayQueue nq = {qo[cur].data(), qd[cur].data()};
+        RayQueue nq = {qo[cur].data(), qd[cur].data(), qi[cur].data()};
         for (int j = 0; j < npx * ns; j++) shade_first(fc, wb, s0, j, nq, &nNext, shq, &nSh);
         for (int depth = 1; depth <= fc.maxDepth; depth++) {
             for (int k = 0; k < nSh; k++) {
@@ -133,11 +133,11 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
                 connect_shadow(wb, shq, k, occ);
             }
             raysS += (uint64_t)nSh;
-            RayQueue cq = {qo[cur].data(), qd[cur].data()};
+            RayQueue cq = {qo[cur].data(), qd[cur].data(), qi[cur].data()};
             for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[k], &tc); flushCnt(); }
             raysB += (uint64_t)nNext;
             const int nCur = nNext; nNext = 0; nSh = 0;
-            RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data()};
+            RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data(), qi[cur ^ 1].data()};
             for (int k = 0; k < nCur; k++) shade_next(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh);
             cur ^= 1;
         }

@@ -72,3 +72,193 @@ def test_empty_scene(gpu_ctx):
     cam = oracle_camera("C1B", 64, 36)
     sc = orc.Scene()
     _run(gpu_ctx, sc, cam, 64, 36, 2, 2, label="empty")
+
+
+@pytest.mark.parametrize("mode", ["identity", "translated"])
+def test_textures_alpha_ties_instances(gpu_ctx, mode):
+    """Textured / alpha-masked / two-sided triangles, duplicated triangles (equal-t ties) and translated instances."""
+    from tests.util import special_camera, special_scene
+    sc = oracle_scene_from_spec(special_scene(mode))
+    gpu_ctx.scene_upload(sc.arrays())
+    _run(gpu_ctx, sc, special_camera(400, 240), 400, 240, 3, 5, label=f"special {mode}")
+
+
+def test_scaled_rotated_instances_vs_cull_free_reference(gpu_ctx):
+    """uniformScale != 1 / rotations: the reference's own culling is visiting-order dependent (see tests/util.special_scene);
+    the core must return the order-independent result = the oracle with every box test taken (primary hits)."""
+    from tests.util import special_camera, special_scene
+    sc = oracle_scene_from_spec(special_scene("scaled"))
+    gpu_ctx.scene_upload(sc.arrays())
+    W, H = 200, 120
+    cam = special_camera(W, H)
+    r = orc.render(sc, cam, orc.make_config(W, H, spp=1, max_depth=0, no_cull=1), aovs=False)
+    gpu_ctx.render(cam, L.make_render_config(W, H, spp=1, max_depth=0))
+    gpu_ctx.sync()
+    assert np.array_equal(gpu_ctx.download(L.RT_BUF_PRIM_ID), r.primId)
+    assert np.array_equal(gpu_ctx.download(L.RT_BUF_INST_ID), r.instId)
+    assert np.array_equal(gpu_ctx.download(L.RT_BUF_PRIMARY_T), r.primaryT)
+    assert np.array_equal(gpu_ctx.download(L.RT_BUF_GB_NORMAL), r.gbNrm)
+
+
+def test_golden_fixtures(gpu_ctx):
+    """Committed input/output pairs (tests/golden, minted from the oracle by make_golden.py) through the C ABI."""
+    import glob
+    import os
+    from tests.golden.make_golden import CASES, make_spec
+    for f in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))):
+        g = np.load(f)
+        kind, camname, W, H, spp, depth, flags = CASES[str(g["name"])]
+        sc = oracle_scene_from_spec(make_spec(kind))
+        gpu_ctx.scene_upload(sc.arrays())
+        gpu_ctx.render(oracle_camera(camname, W, H), L.make_render_config(W, H, spp=spp, max_depth=depth, flags=flags | L.RT_FLAG_PATH_AOVS))
+        gpu_ctx.sync()
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_PRIM_ID), g["primId"]), f
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_SEG_COUNT).reshape(g["segCount"].shape), g["segCount"]), f
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_PATH_HASH).reshape(g["pathHash"].shape), g["pathHash"]), f
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_RADIANCE)[:, :3], g["radiance"]), f
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_RGBA8), g["rgba8"]), f
+
+
+def test_tile_partition_and_deinterleave(gpu_ctx):
+    """Multi-GPU protocol on one device: every rank's tiles rendered in turn, payloads concatenated rank-major as the NCCL
+    gather delivers them, rt_deinterleave_tiles reassembles the frame == the single-context image, bit for bit."""
+    import torch
+    from ilgpu_raytracing_b200 import native
+    sc = oracle_scene_from_spec(scenes.terrain_scene(64, 16))
+    gpu_ctx.scene_upload(sc.arrays())
+    W, H, tile = 520, 296, 32
+    cam = oracle_camera("C3", W, H)
+    gpu_ctx.render(cam, L.make_render_config(W, H, spp=3, max_depth=4))
+    gpu_ctx.sync()
+    full = gpu_ctx.download(L.RT_BUF_RADIANCE).copy()
+    full_rgba = gpu_ctx.download(L.RT_BUF_RGBA8).copy()
+    for world in (2, 8):
+        counts = [native.tiles_owned_pixels(W, H, tile, r, world) for r in range(world)]
+        assert sum(counts) == W * H
+        max_n = max(counts)
+        flat = torch.zeros((world * max_n, 4), dtype=torch.float32, device="cuda")
+        for rank in range(world):
+            gpu_ctx.render(cam, L.make_render_config(W, H, spp=3, max_depth=4, tile_size=tile, rank=rank, world_size=world))
+            gpu_ctx.sync()
+            pay = gpu_ctx.download(L.RT_BUF_TILE_RADIANCE)
+            assert pay.shape == (counts[rank], 4)
+            flat[rank * max_n: rank * max_n + counts[rank]] = torch.from_numpy(pay).cuda()
+        out_rad = torch.zeros((W * H, 4), dtype=torch.float32, device="cuda")
+        out_rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+        gpu_ctx.deinterleave_tiles(flat.data_ptr(), [r * max_n for r in range(world)], world, W, H, tile, out_rad.data_ptr(), out_rgba.data_ptr())
+        torch.cuda.synchronize()
+        assert np.array_equal(out_rad.cpu().numpy(), full)
+        assert np.array_equal(out_rgba.cpu().numpy(), full_rgba)
+
+
+def test_progressive_accumulation(gpu_ctx):
+    """RT_FLAG_ACCUMULATE: accum.rgb = sum of per-frame Lout, accum.w = frame count, RGBA8 = PackRGBA8(accum.rgb / accum.w);
+    with rngLockNoise = 0 every frame draws a different stream (RTUtils.cs:122)."""
+    sc = orc.Scene()
+    sc.build_default()
+    gpu_ctx.scene_upload(sc.arrays())
+    W, H = 256, 144
+    cam = oracle_camera("C1B", W, H)
+    total = np.zeros((W * H, 3), np.float32)
+    frames = []
+    for frame in range(3):
+        flags = L.RT_FLAG_ACCUMULATE | (L.RT_FLAG_RESET_ACCUM if frame == 0 else 0)
+        gpu_ctx.render(cam, L.make_render_config(W, H, spp=2, max_depth=2, frame=frame, rng_lock_noise=0, flags=flags))
+        gpu_ctx.sync()
+        lout = gpu_ctx.download(L.RT_BUF_RADIANCE)[:, :3].copy()
+        ref = orc.render(sc, cam, orc.make_config(W, H, spp=2, max_depth=2, frame=frame, rng_lock_noise=0), aovs=False)
+        assert np.array_equal(lout, ref.radiance)
+        frames.append(lout)
+        total = total + lout
+    assert not np.array_equal(frames[0], frames[1])
+    acc = gpu_ctx.download(L.RT_BUF_ACCUM)
+    assert np.array_equal(acc[:, :3], total) and np.all(acc[:, 3] == 3.0)
+    shown = total * (np.float32(1.0) / acc[:, 3:4])
+    want = (255 << 24) | ((np.float32(255.99) * np.clip(shown[:, 0], 0, 1)).astype(np.int64) << 16) | ((np.float32(255.99) * np.clip(shown[:, 1], 0, 1)).astype(np.int64) << 8) | (np.float32(255.99) * np.clip(shown[:, 2], 0, 1)).astype(np.int64)
+    assert np.array_equal(gpu_ctx.download(L.RT_BUF_RGBA8).astype(np.int64) & 0xFFFFFFFF, want)
+
+
+def test_error_paths(gpu_ctx):
+    from ilgpu_raytracing_b200 import native
+    fresh = native.Context(0)
+    cam = oracle_camera("C1B", 64, 36)
+    with pytest.raises(native.RtError) as e:
+        fresh.render(cam, L.make_render_config(64, 36))
+    assert e.value.status == L.RT_ERR_INVALID_STATE
+    fresh.scene_upload({})
+    for bad in (L.make_render_config(0, 36), L.make_render_config(64, 36, max_depth=-1), L.make_render_config(64, 36, rank=2, world_size=2)):
+        with pytest.raises(native.RtError) as e:
+            fresh.render(cam, bad)
+        assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
+    with pytest.raises(native.RtError) as e:
+        fresh.render(cam, L.make_render_config(64, 36, temporal=1))
+    assert e.value.status == L.RT_ERR_UNSUPPORTED
+    with pytest.raises(native.RtError):
+        fresh.download(L.RT_BUF_RGBA8)
+    fresh.render(cam, L.make_render_config(64, 36))
+    with pytest.raises(native.RtError) as e:
+        fresh.download(L.RT_BUF_SEG_COUNT)   # AOVs not requested
+    assert e.value.status == L.RT_ERR_INVALID_STATE
+    sc = orc.Scene()
+    sc.build_default()
+    a = sc.arrays()
+    a["spherePrimIdx"] = a["spherePrimIdx"].copy()
+    a["spherePrimIdx"][6:] = 1234
+    with pytest.raises(native.RtError) as e:
+        fresh.scene_upload(a)
+    assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
+    fresh.close()
+
+
+def test_engine_api_drop_in(gpu_ctx):
+    """The reference's host surface: RTRenderer ctor (default scene + camera), RenderDirectToPbo into a CUDA 'PBO',
+    Framebuffer.DownloadToCpu -> CpuColor / CpuDepth / CpuObjectId."""
+    import torch
+    from ilgpu_raytracing_b200 import engine
+    W, H = 320, 180
+    rdr = engine.RTRenderer(0, W, H)
+    assert rdr.camera.tobytes() == oracle_camera("C1A", W, H).tobytes()   # CreateCamera + Translate(1,0,-4), RTRenderer.cs:78-79
+    rdr.camera = engine.config_camera("C1B", W, H)
+    rdr.configure(spp=2, maxDepth=3, rngLockNoise=1, fixedSeed=7)
+    pbo = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+    rdr.RenderDirectToPbo(pbo.data_ptr(), W, H, 0, 0.016)
+    color, depth, objid = rdr.DownloadToCpu()
+    sc = orc.Scene()
+    sc.build_default()
+    ref = orc.render(sc, oracle_camera("C1B", W, H), orc.make_config(W, H, spp=2, max_depth=3, rng_lock_noise=7), aovs=False)
+    assert np.array_equal(color, ref.rgba8) and np.array_equal(depth, ref.depth) and np.array_equal(objid, ref.objId)
+    assert np.array_equal(pbo.cpu().numpy(), ref.rgba8)
+    rdr.configure(renderScale=0.67)
+    with pytest.raises(engine.EngineError, match="InvalidOperationException"):
+        rdr.RenderDirectToPbo(pbo.data_ptr(), W, H, 1, 0.016)
+    rdr.RenderDirectToPbo(None, W, H, 1, 0.016)   # traced at round(W*0.67) x round(H*0.67) like RTRenderer.cs:113-116
+    cfg = rdr.last_config()
+    assert (cfg.width, cfg.height) == (214, 121)
+    rdr.close()
+
+
+def test_full_size_properties_c3(gpu_ctx):
+    """BASELINE config C3 at full size (1 002 528 triangles, 3840x2160, primary only) through size-independent properties:
+    idempotence, ray count, every hit id valid and its t reproducing the depth buffer, and an oracle crop."""
+    from ilgpu_raytracing_b200 import engine
+    spec = scenes.terrain_scene(708, 0)
+    e = engine.Scene().load_spec(spec)
+    gpu_ctx.scene_upload(e.arrays())
+    W, H = 3840, 2160
+    cam = engine.config_camera("C3", W, H)
+    cfg = L.make_render_config(W, H, spp=1, max_depth=0)
+    gpu_ctx.render(cam, cfg); gpu_ctx.sync()
+    prim, t, depth, rgba = gpu_ctx.download(L.RT_BUF_PRIM_ID), gpu_ctx.download(L.RT_BUF_PRIMARY_T), gpu_ctx.download(L.RT_BUF_DEPTH), gpu_ctx.download(L.RT_BUF_RGBA8)
+    st = gpu_ctx.stats()
+    assert st["raysPrimary"] == W * H and st["raysBounce"] == 0 and st["raysShadow"] == 0
+    gpu_ctx.render(cam, cfg); gpu_ctx.sync()
+    assert np.array_equal(prim, gpu_ctx.download(L.RT_BUF_PRIM_ID)) and np.array_equal(rgba, gpu_ctx.download(L.RT_BUF_RGBA8))
+    hit = prim >= 0
+    assert 0.3 < hit.mean() < 0.9 and prim.max() < len(spec.mesh.tris)
+    assert np.allclose(depth[hit], t[hit], rtol=1e-5)          # |pos - origin| == t for a unit direction
+    assert np.all(t[~hit] == np.float32(1e30))
+    box = (1700, 900, 1956, 1044)
+    sc = oracle_scene_from_spec(spec)
+    r = orc.render(sc, cam, orc.make_config(W, H, spp=1, max_depth=0, crop=box))
+    from tests.parity import crop
+    assert np.array_equal(crop(prim, W, H, box), r.primId) and np.array_equal(crop(t, W, H, box), r.primaryT)

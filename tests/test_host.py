@@ -1,0 +1,138 @@
+"""not gpu: the C-ABI library loads and exports every symbol include/*.h declares, the layouts agree, the C++ engine
+mirror (Scene / Camera / RTRenderer host logic) restates the reference's builders identically to the oracle, errors
+surface like the reference's exceptions, and nothing falls back to a CPU path."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ilgpu_raytracing_b200 import build, engine, layouts as L, native, scenes
+from oracle import orc
+from tests.util import oracle_camera, oracle_scene_from_spec, special_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    build.build_all()
+
+
+def test_abi_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "rtcore_b200.h")).read()
+    declared = set(re.findall(r"RT_API\s+(?:const\s+)?\w+\*?\s+(\w+)\s*\(", hdr))
+    assert declared == set(native.EXPORTS) and len(declared) == 15
+    lib = native.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.rt_abi_version() == 1
+
+
+def test_layout_sizes():
+    assert C.sizeof(L.RtSceneDesc) == 15 * 16
+    assert C.sizeof(L.RtRenderConfig) == 112
+    assert L.CAMERA.itemsize == 92 and L.SPHERE.itemsize == 80 and L.INSTANCE.itemsize == 144 and L.MATERIAL.itemsize == 44 and L.BVHNODE.itemsize == 44
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device rt_create must fail loudly (RT_ERR_NO_DEVICE); nothing may render on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    with pytest.raises(native.RtError) as e:
+        native.Context(0)
+    assert e.value.status == L.RT_ERR_NO_DEVICE and "no CPU fallback" in str(e.value)
+    with pytest.raises(engine.EngineError) as e2:
+        engine.RTRenderer(0, 64, 64)
+    assert e2.value.status == L.RT_ERR_NO_DEVICE
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ilgpu_raytracing_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".h", ".cu", ".cpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "from oracle" not in src and "import oracle" not in src and "librt_oracle" not in src and not re.search(r'#include\s+"[^"]*oracle', src), f
+
+
+def test_cameras_match_oracle():
+    for name in scenes.CAMERAS:
+        for (w, h) in ((1280, 720), (3840, 2160), (333, 77)):
+            assert engine.config_camera(name, w, h).tobytes() == oracle_camera(name, w, h).tobytes()
+    cam = engine.create_camera(1280, 720, 60.0)
+    assert np.allclose([cam["origin"]["X"], cam["origin"]["Y"], cam["origin"]["Z"]], [0, 1, 3])
+    assert abs(float(cam["fovYRadians"]) - np.deg2rad(60)) < 1e-6 and abs(float(cam["aspect"]) - 1280 / 720) < 1e-6
+    engine.camera_rotate_yaw_pitch(cam, 30.0, -10.0)
+    engine.camera_set_fov(cam, 45.0, 16 / 9)
+    f = np.array([cam["forward"]["X"], cam["forward"]["Y"], cam["forward"]["Z"]])
+    assert abs(np.linalg.norm(f) - 1) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["default", "spheres", "terrain", "terrain_mats", "special"])
+def test_engine_builders_match_oracle(kind):
+    """Two independent restatements of Scene.cs (BLAS/TLAS builders incl. .NET's introsort, instance records, TLAS) -> identical bytes."""
+    if kind == "default":
+        e = engine.Scene()
+        e.BuildDefaultScene()
+        o = orc.Scene()
+        o.build_default()
+    else:
+        spec = {"spheres": lambda: scenes.sphere_grid_scene(16), "terrain": lambda: scenes.terrain_scene(80, 25),
+                "terrain_mats": lambda: scenes.terrain_scene(64, 0, True), "special": lambda: special_scene("scaled")}[kind]()
+        e = engine.Scene().load_spec(spec)
+        o = oracle_scene_from_spec(spec)
+    ea, oa = e.arrays(), o.arrays()
+    for k in ea:
+        assert ea[k].tobytes() == oa[k].tobytes(), k
+    assert e.sort_ties() == o.sort_ties()
+
+
+def test_default_scene_spec_equals_builtin():
+    a = engine.Scene()
+    a.BuildDefaultScene()
+    b = engine.Scene().load_spec(scenes.default_scene())
+    aa, bb = a.arrays(), b.arrays()
+    for k in aa:
+        assert aa[k].tobytes() == bb[k].tobytes(), k
+
+
+def test_engine_errors_follow_reference_exceptions():
+    s = engine.Scene()
+    with pytest.raises(engine.EngineError, match="ArgumentOutOfRangeException"):
+        s.AddSphereInstance([5])
+    with pytest.raises(engine.EngineError, match="ArgumentOutOfRangeException"):
+        s.AddSphereInstance([])
+    m = scenes.terrain_mesh(4)
+    bad = m.tris.copy()
+    bad[0, 0] = 10 ** 6
+    with pytest.raises(engine.EngineError, match="ArgumentOutOfRangeException"):
+        s.LoadMeshInstance(m.positions, bad, m.texcoords, m.tri_uvs, m.tri_mat, m.materials)
+    s.LoadMeshInstance(m.positions, m.tris, m.texcoords, m.tri_uvs, m.tri_mat, m.materials)
+    with pytest.raises(engine.EngineError, match="InvalidOperationException"):   # reference quirk 2: one mesh per scene
+        s.LoadMeshInstance(m.positions, m.tris, m.texcoords, m.tri_uvs, m.tri_mat, m.materials)
+    with pytest.raises(engine.EngineError, match="InvalidOperationException"):   # host-only scene has nothing to upload to
+        s.UploadAll()
+
+
+def test_tile_ownership_partitions_the_image():
+    for (w, h, t) in ((3840, 2160, 32), (7680, 4320, 32), (200, 104, 32), (33, 17, 8)):
+        for world in (1, 2, 4, 8):
+            counts = [native.tiles_owned_pixels(w, h, t, r, world) for r in range(world)]
+            assert sum(counts) == w * h
+            if world > 1 and w * h > 10 ** 6:
+                assert max(counts) / min(counts) < 1.02   # interleaving balances the load
+    with pytest.raises(native.RtError):
+        native.tiles_owned_pixels(64, 64, 32, 3, 2)
+
+
+def test_terrain_scene_shape():
+    """C3/C4 mesh: 708 x 708 quads = 1 002 528 triangles, 709^2 vertices, up-facing."""
+    m = scenes.terrain_mesh(708)
+    assert len(m.tris) == 1002528 and len(m.positions) == 709 * 709
+    p = m.positions[m.tris[:1000]]
+    n = np.cross(p[:, 1] - p[:, 0], p[:, 2] - p[:, 0])
+    assert (n[:, 1] > 0).all()
+    assert abs(m.positions[:, 0]).max() < 50.1 and abs(m.positions[:, 1]).max() < 6.5

@@ -1,0 +1,151 @@
+"""not gpu: the renderer core's stage bodies (wide-BVH build, traversal, tie-break rule, wavefront state machine),
+compiled for the CPU by tests/hostsim, against the oracle.  The same bodies run inside the CUDA kernels; the -m gpu
+tests repeat these comparisons through the C ABI on the device."""
+import numpy as np
+import pytest
+
+from ilgpu_raytracing_b200 import layouts as L
+from ilgpu_raytracing_b200 import scenes
+from oracle import orc
+from tests.hostsim_binding import HostSimScene
+from tests.util import oracle_camera, oracle_scene_from_spec, special_camera, special_scene
+
+
+def _compare(r, h, label=""):
+    for k in ("primId", "instId", "primaryT", "gbPos", "gbNrm", "gbAlb", "gbMat", "objId", "depth", "segCount", "termCode", "pathHash", "rgba8"):
+        assert np.array_equal(getattr(r, k), h[k]), f"{label}: {k} differs"
+    assert np.array_equal(r.radiance, h["radiance"]), f"{label}: radiance not bit-identical"
+
+
+@pytest.mark.parametrize("spp,depth", [(1, 0), (1, 1), (3, 4), (2, 8)])
+def test_default_scene(spp, depth):
+    sc = orc.Scene()
+    sc.build_default()
+    hs = HostSimScene(sc.arrays())
+    for camname in ("C1A", "C1B"):
+        cam = oracle_camera(camname, 192, 108)
+        r = orc.render(sc, cam, orc.make_config(192, 108, spp=spp, max_depth=depth))
+        h = hs.render(cam, L.make_render_config(192, 108, spp=spp, max_depth=depth))
+        _compare(r, h, f"default {camname} {spp}spp d{depth}")
+        assert h["counters"]["raysBounce"] == r.counters["raysBounce"] and h["counters"]["raysShadow"] == r.counters["raysShadow"]
+
+
+def test_sphere_grid_with_roulette():
+    sc = oracle_scene_from_spec(scenes.sphere_grid_scene(12))
+    hs = HostSimScene(sc.arrays())
+    cam = oracle_camera("C2", 160, 90)
+    r = orc.render(sc, cam, orc.make_config(160, 90, spp=6, max_depth=6))
+    h = hs.render(cam, L.make_render_config(160, 90, spp=6, max_depth=6, samples_per_pass=4))
+    _compare(r, h, "sphere grid")
+    assert (r.termCode == 3).sum() > 0
+
+
+@pytest.mark.parametrize("flags", [0, L.RT_FLAG_TRI_MATERIALS])
+def test_terrain(flags):
+    sc = oracle_scene_from_spec(scenes.terrain_scene(64, 16, patch_materials=bool(flags)))
+    hs = HostSimScene(sc.arrays())
+    st = hs.stats()
+    assert st["nPrims"] == 2 * 64 * 64 + 16 and st["nWideNodes"] < st["nPrims"] / 5
+    cam = oracle_camera("C3", 160, 90)
+    r = orc.render(sc, cam, orc.make_config(160, 90, spp=2, max_depth=8, flags=flags & 1))
+    h = hs.render(cam, L.make_render_config(160, 90, spp=2, max_depth=8, flags=flags))
+    _compare(r, h, "terrain")
+    # the wide BVH visits far fewer nodes than the reference's BVH2
+    assert h["counters"]["nodes"] < r.counters["nodes"] / 3
+
+
+@pytest.mark.parametrize("transformed", ["identity", "translated"])
+def test_textures_alpha_ties_instances(transformed):
+    """Textured / alpha-masked / two-sided triangles, duplicated triangles (equal-t ties) and translated instances."""
+    sc = oracle_scene_from_spec(special_scene(transformed))
+    hs = HostSimScene(sc.arrays())
+    cam = special_camera(200, 120)
+    r = orc.render(sc, cam, orc.make_config(200, 120, spp=3, max_depth=5))
+    h = hs.render(cam, L.make_render_config(200, 120, spp=3, max_depth=5))
+    _compare(r, h, f"special transformed={transformed}")
+    assert (r.hitMask > 0).mean() > 0.5 and len(np.unique(r.instId)) >= 5
+
+
+def test_tie_break_prefers_reference_visiting_order():
+    """Two coincident triangles: the reference keeps the first it visits (strict '<'); the wide traversal must agree."""
+    spec = special_scene("identity")
+    sc = oracle_scene_from_spec(spec)
+    hs = HostSimScene(sc.arrays())
+    m = spec.mesh
+    n_orig = len(m.tris) - 20
+    on_pair = 0
+    for k in range(20):
+        tri = m.tris[n_orig + k]
+        c = m.positions[tri].mean(axis=0)
+        o = (c + np.array([0.01, 5.0, 0.02], np.float32)).astype(np.float32)
+        d = (c - o) / np.linalg.norm(c - o)
+        hit_o, t_o, inst_o, prim_o = sc.trace_closest(o, d.astype(np.float32))
+        hit_h, t_h, inst_h, prim_h, _ = hs.trace(o, d.astype(np.float32))
+        assert hit_o and hit_h and (t_o, inst_o, prim_o) == (t_h, inst_h, prim_h)
+        on_pair += prim_o in (40 + k, n_orig + k)   # (a sphere may sit in front of some of them)
+    assert on_pair >= 10
+
+
+def test_any_hit_matches_shadow_occlusion():
+    sc = oracle_scene_from_spec(special_scene("translated"))
+    hs = HostSimScene(sc.arrays())
+    cam = special_camera(96, 54)
+    # shadow visibility is folded into the path hash (0x100 | visible): one Lambert bounce is enough to cover it
+    r = orc.render(sc, cam, orc.make_config(96, 54, spp=2, max_depth=1))
+    h = hs.render(cam, L.make_render_config(96, 54, spp=2, max_depth=1))
+    assert np.array_equal(r.pathHash, h["pathHash"]) and r.counters["raysShadow"] == h["counters"]["raysShadow"] > 0
+
+
+def test_scaled_instances_match_cull_free_reference():
+    """uniformScale != 1: the reference reports tWorld = tObj / scale, which makes its own box culling depend on the visiting
+    order (a sphere found first can cull a scaled mesh whose reported t is smaller).  The core returns the order-independent
+    minimum of the reference's own hit rule = the oracle with every box test taken."""
+    sc = oracle_scene_from_spec(special_scene("scaled"))
+    hs = HostSimScene(sc.arrays())
+    rs = np.random.RandomState(1)
+    differs = 0
+    for _ in range(1500):
+        o = np.array([rs.uniform(-8, 8), rs.uniform(1, 6), rs.uniform(-8, 8)], np.float32)
+        t = np.array([rs.uniform(-4, 4), rs.uniform(-0.5, 1.5), rs.uniform(-4, 4)], np.float32)
+        d = ((t - o) / np.linalg.norm(t - o)).astype(np.float32)
+        want = sc.trace_closest(o, d, cull=False)
+        hit, tt, inst, prim, _ = hs.trace(o, d)
+        assert (hit, tt, inst, prim) == want
+        differs += want != sc.trace_closest(o, d, cull=True)
+    assert differs > 0   # the reference's culled walk really is order dependent on this scene
+
+
+def test_tile_partition_is_exact():
+    """Interleaved screen tiles: the union of the ranks' pixels is the single-context image, bit for bit."""
+    sc = oracle_scene_from_spec(scenes.terrain_scene(32, 9))
+    hs = HostSimScene(sc.arrays())
+    W, H = 200, 104   # not multiples of the tile size
+    cam = oracle_camera("C3", W, H)
+    full = hs.render(cam, L.make_render_config(W, H, spp=2, max_depth=3))
+    for world in (2, 3):
+        acc = np.zeros((W * H, 3), np.float32)
+        owned = np.zeros(W * H, np.int32)
+        for rank in range(world):
+            part = hs.render(cam, L.make_render_config(W, H, spp=2, max_depth=3, tile_size=32, rank=rank, world_size=world))
+            mine = part["primId"] != -2   # hostsim initialises untouched pixels to -2
+            owned += mine
+            acc[mine] = part["radiance"][mine]
+            assert np.array_equal(part["rgba8"][mine], full["rgba8"][mine])
+        assert np.all(owned == 1)
+        assert np.array_equal(acc, full["radiance"])
+
+
+def test_malformed_scene_is_rejected():
+    sc = orc.Scene()
+    sc.build_default()
+    a = sc.arrays()
+    bad = dict(a)
+    bad["tlasInstanceIndices"] = a["tlasInstanceIndices"].copy()
+    bad["tlasInstanceIndices"][0] = 99
+    with pytest.raises(ValueError):
+        HostSimScene(bad)
+    bad = dict(a)
+    bad["spherePrimIdx"] = a["spherePrimIdx"].copy()
+    bad["spherePrimIdx"][6:] = 77
+    with pytest.raises(ValueError):
+        HostSimScene(bad)
