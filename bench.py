@@ -212,10 +212,10 @@ def main():
     gathered = payload = None
     if world > 1:
         payload = torch.zeros((max_npx, 4), dtype=torch.float32, device="cuda")
-        gathered = [torch.zeros((max_npx, 4), dtype=torch.float32, device="cuda") for _ in range(world)] if rank == 0 else None
+        flat = torch.zeros((world * max_npx, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
+        gathered = [flat[r * max_npx:(r + 1) * max_npx] for r in range(world)] if rank == 0 else None   # NCCL writes straight into the flat buffer
         full = torch.zeros((W * H, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
         full_rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda") if rank == 0 else None
-        flat = torch.zeros((world * max_npx, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
 
     class _Dev:   # view of a library-owned device buffer as a torch tensor (no copy)
         def __init__(self, ptr, nfloat4):
@@ -231,7 +231,6 @@ def main():
                 payload[: src.shape[0]].copy_(src, non_blocking=True)
                 dist.gather(payload, gathered, dst=0)
                 if rank == 0:
-                    torch.stack(gathered, out=flat.view(world, max_npx, 4))
                     ctx.deinterleave_tiles(flat.data_ptr(), [r * max_npx for r in range(world)], world, W, H, tile, full.data_ptr(), full_rgba.data_ptr())
 
     def barrier():

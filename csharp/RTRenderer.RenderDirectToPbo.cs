@@ -1,0 +1,93 @@
+// RTRenderer.RenderDirectToPbo.cs — the patched hot entry point of Engine/RTRenderer.cs (lines cited are the reference's).
+//
+// What changes in RTRenderer:
+//   * fields  _context/_cuda/_stream, _primaryKernel, _integratorKernel, _lowColor/... (RTRenderer.cs:25-27,37-38,53-56) -> IntPtr _rt
+//   * ctor    Context.Create(...) + CreateCudaAccelerator(deviceIndex) + LoadAutoGroupedStreamKernel x2 (:66-68,85-86)        -> _rt = RtNative.Create(deviceIndex)
+//   * Scene   keeps its host lists and builders verbatim; UploadAll (Scene.cs:258-279) pins the 15 lists and calls rt_scene_upload (below)
+//   * Dispose (:347-375)                                                                                                       -> RtNative.rt_destroy(_rt)
+// Everything else in the Engine (SceneManager, BvhManager, Camera, CameraController, RTWindow, Program.cs) is untouched.
+// NOTE: shipped as source; this image has no .NET toolchain, so it has not been compiled here.
+using System;
+using ILGPU.Algorithms;
+
+namespace ILGPU_Raytracing.Engine
+{
+    public sealed unsafe partial class RTRenderer
+    {
+        private IntPtr _rt;
+
+        public void RenderDirectToPbo(CudaGlInteropIndexBuffer pbo, int width, int height, int frame, float dt)
+        {
+            if (pbo is null) throw new ArgumentNullException(nameof(pbo));
+            int outW = Math.Max(1, width), outH = Math.Max(1, height);
+            int inW = Math.Max(1, (int)XMath.Round(outW * _renderScale));       // :113-116
+            int inH = Math.Max(1, (int)XMath.Round(outH * _renderScale));
+
+            BakeCameraDerived(ref _camera, inW, inH);                            // :123-124
+            BakeCameraDerived(ref _prevCamera, inW, inH);
+
+            int temporalSeed = (_rngLockNoise == 0) ? 0 : Random.Shared.Next(int.MinValue, int.MaxValue);   // :166
+            float dtClamped = XMath.Clamp(dt, 0f, 0.1f);                         // :169-172
+            _sunAzimuth += _sunSpeedRadPerSec * dtClamped;
+            const float TwoPi = 6.28318530717958647692f;
+            if (_sunAzimuth >= TwoPi) _sunAzimuth -= TwoPi; else if (_sunAzimuth < 0f) _sunAzimuth += TwoPi;
+            Float3 sunDir = Float3.Normalize(new Float3(XMath.Cos(_sunAzimuth) * XMath.Cos(_sunElevation), XMath.Sin(_sunElevation), XMath.Sin(_sunAzimuth) * XMath.Cos(_sunElevation)));   // :174-178
+
+            var cfg = new RtRenderConfig
+            {
+                width = inW, height = inH, frame = frame, spp = _spp, maxDepth = 3,                        // :181-205 (maxDepth was SpecializedValue.New(3), :204)
+                rngLockNoise = temporalSeed,
+                enableTemporalReuse = _enableTemporalReuse, enableSpatialReuse = _enableSpatialReuse,
+                dirLightDir = sunDir, dirLightRadiance = new Float3(10, 10, 10),
+                skyTintTop = new Float3(0.5f, 0.7f, 1.0f), skyTintBottom = new Float3(1.0f, 1.0f, 1.0f),
+                flags = (uint)RtFlags.None, tileSize = 32, rank = 0, worldSize = 1, samplesPerPass = 0
+            };
+
+            pbo.MapCuda(_stream);                                                                          // :208-209
+            bool direct = inW == outW && inH == outH && !_enableTAAU;
+            RtNative.ThrowIfFailed(RtNative.rt_map_external_color(_rt, direct ? pbo.DevicePointer : IntPtr.Zero, (UIntPtr)((long)outW * outH * 4)));
+
+            Camera cam = _camera, prev = _prevCamera;
+            RtNative.ThrowIfFailed(RtNative.rt_render(_rt, &cam, &prev, &cfg));    // replaces _primaryKernel(...) :152-153 and _integratorKernel(...) :205
+
+            if (!direct)
+            {
+                // TAAU / bilinear present (:211-231) keep running on the RGBA8 the core produced: fetch its device pointer
+                RtNative.ThrowIfFailed(RtNative.rt_get_device_buffer(_rt, (int)RtBuffer.Rgba8, out IntPtr lowColor, out _));
+                RtNative.ThrowIfFailed(RtNative.rt_get_device_buffer(_rt, (int)RtBuffer.ObjId, out IntPtr lowObjId, out _));
+                PresentWithTaauOrUpsample(pbo, lowColor, lowObjId, inW, inH, outW, outH, frame);           // the reference's RTTaa / BilinearUpsampleKernel, unchanged
+            }
+
+            RtNative.ThrowIfFailed(RtNative.rt_sync(_rt));                          // _cuda.Synchronize() :233
+            pbo.UnmapCuda(_stream);
+            _prevCamera = _camera;                                                  // :236
+        }
+    }
+
+    public sealed unsafe partial class Scene
+    {
+        // Scene.UploadAll (Scene.cs:258-279): same 15 lists, same element layouts; the native side copies them, derives the
+        // reference's visiting order from the BVH2 arrays and builds its compressed 8-wide BVH.
+        public void UploadAll()
+        {
+            var tlas = _hTLASNodes ?? Array.Empty<TLASNode>(); var tlasIdx = _hTLASInstanceIndices ?? Array.Empty<int>(); var inst = _hInstances ?? Array.Empty<InstanceRecord>();
+            var blas = _hBLASNodes.ToArray(); var sIdx = _hSpherePrimIndices.ToArray(); var sph = _hSpheres.ToArray(); var tIdx = _hTriPrimIndices.ToArray();
+            var pos = _hMeshPositions.ToArray(); var tris = _hMeshTris.ToArray(); var uvs = _hMeshTexcoords.ToArray(); var tuv = _hMeshTriUVs.ToArray();
+            var tmat = _hTriMaterialIndex.ToArray(); var mats = _hMaterials.ToArray(); var tex = _hTexels.ToArray(); var ti = _hTexInfos.ToArray();
+            fixed (TLASNode* p0 = tlas) fixed (int* p1 = tlasIdx) fixed (InstanceRecord* p2 = inst) fixed (BLASNode* p3 = blas) fixed (int* p4 = sIdx)
+            fixed (Sphere* p5 = sph) fixed (int* p6 = tIdx) fixed (Float3* p7 = pos) fixed (MeshTri* p8 = tris) fixed (Float2* p9 = uvs)
+            fixed (MeshTriUV* p10 = tuv) fixed (int* p11 = tmat) fixed (MaterialRecord* p12 = mats) fixed (RGBA32* p13 = tex) fixed (TexInfo* p14 = ti)
+            {
+                var d = new RtSceneDesc
+                {
+                    tlasNodes = p0, nTlasNodes = tlas.Length, tlasInstanceIndices = p1, nTlasInstanceIndices = tlasIdx.Length, instances = p2, nInstances = inst.Length,
+                    blasNodes = p3, nBlasNodes = blas.Length, spherePrimIdx = p4, nSpherePrimIdx = sIdx.Length, spheres = p5, nSpheres = sph.Length,
+                    triPrimIdx = p6, nTriPrimIdx = tIdx.Length, meshPositions = p7, nMeshPositions = pos.Length, meshTris = p8, nMeshTris = tris.Length,
+                    meshTexcoords = p9, nMeshTexcoords = uvs.Length, meshTriUVs = p10, nMeshTriUVs = tuv.Length, triMatIndex = p11, nTriMatIndex = tmat.Length,
+                    materials = p12, nMaterials = mats.Length, texels = p13, nTexels = tex.Length, texInfos = p14, nTexInfos = ti.Length
+                };
+                RtNative.ThrowIfFailed(RtNative.rt_scene_upload(_rt, &d));
+            }
+        }
+    }
+}

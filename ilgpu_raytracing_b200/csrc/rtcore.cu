@@ -260,6 +260,8 @@ struct rt_ctx {
     // kernel timing (extend kernels)
     std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool timeKernels = false;
     int* extColor = nullptr; size_t extColorBytes = 0;
+    // multi-GPU finish: cached owned-pixel lists of every rank
+    DevBuf<int> deintMap; std::vector<int64_t> deintStart; int deintW = 0, deintH = 0, deintT = 0, deintWorld = 0;
     int extendBlocks = 0;
     size_t extendSmem = 0;
 };
@@ -335,7 +337,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
     c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); c->qI[b].release(); } c->shO.release(); c->shD.release(); c->shI.release(); c->shC.release();
-    c->hits.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release();
+    c->hits.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release(); c->deintMap.release();
     for (auto ev : c->traceEvents) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
@@ -638,17 +640,28 @@ RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64
                                  void* outRadianceDev, void* outRgba8Dev) {
     if (!c || !gatheredDev || !rankOffsetsPx || worldSize < 1 || width <= 0 || height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_deinterleave_tiles: bad argument");
     CUDA_TRY(cudaSetDevice(c->device));
-    DevBuf<int> pm;
-    for (int r = 0; r < worldSize; r++) {
-        std::vector<int> m; build_pixel_map(width, height, tileSize, r, worldSize, m);
-        if (m.empty()) continue;
-        CUDA_TRY(pm.ensure(m.size()));
-        CUDA_TRY(cudaMemcpyAsync(pm.p, m.data(), m.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        k_deinterleave<<<grid_for(c, m.size(), 256), 256, 0, c->stream>>>((const float4*)gatheredDev + rankOffsetsPx[r], pm.p, (int)m.size(), (float4*)outRadianceDev, (int*)outRgba8Dev);
-        CUDA_TRY(cudaGetLastError());
-        CUDA_TRY(cudaStreamSynchronize(c->stream));   // m / pm are reused by the next rank
+    const int T = effective_tile_size(tileSize);
+    if (c->deintW != width || c->deintH != height || c->deintT != T || c->deintWorld != worldSize) {
+        // every rank's owned-pixel list, concatenated; built once per (image, tile, world) and kept on the device
+        std::vector<int> all; all.reserve((size_t)width * height);
+        c->deintStart.assign((size_t)worldSize + 1, 0);
+        for (int r = 0; r < worldSize; r++) {
+            std::vector<int> m; build_pixel_map(width, height, T, r, worldSize, m);
+            all.insert(all.end(), m.begin(), m.end());
+            c->deintStart[(size_t)r + 1] = (int64_t)all.size();
+        }
+        CUDA_TRY(c->deintMap.ensure(std::max<size_t>(1, all.size())));
+        CUDA_TRY(cudaMemcpyAsync(c->deintMap.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        c->deintW = width; c->deintH = height; c->deintT = T; c->deintWorld = worldSize;
     }
-    pm.release();
+    for (int r = 0; r < worldSize; r++) {
+        const int64_t n = c->deintStart[(size_t)r + 1] - c->deintStart[(size_t)r];
+        if (n <= 0) continue;
+        k_deinterleave<<<grid_for(c, (size_t)n, 256), 256, 0, c->stream>>>((const float4*)gatheredDev + rankOffsetsPx[r], c->deintMap.p + c->deintStart[(size_t)r], (int)n,
+                                                                          (float4*)outRadianceDev, (int*)outRgba8Dev);
+    }
+    CUDA_TRY(cudaGetLastError());
     return RT_OK;
 }
 
