@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -253,7 +254,9 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
     //   C(n,1) = min(C_leaf(n), C_internal(n)),  C_internal(n) = A_n c_node + min_k C(left,k) + C(right,8-k),
     //   C(n,i) = min(C(n,i-1), min_k C(left,k) + C(right,i-k)),  i = 2..7,   C_leaf(n) = A_n P_n c_prim if P_n <= 3.
     const int nb2 = (int)B.b2.size();
-    const float cNode = 1.0f, cPrim = 0.6f, INF = std::numeric_limits<float>::max();
+    float cPrimTune = 1.6f;   // cost of one exact primitive test relative to one wide-node step (tuning sweeps: RT_BVH_CPRIM)
+    if (const char* e = getenv("RT_BVH_CPRIM")) { float v = (float)atof(e); if (v > 0.0f) cPrimTune = v; }
+    const float cNode = 1.0f, cPrim = cPrimTune, INF = std::numeric_limits<float>::max();
     std::vector<float> C((size_t)nb2 * 7); std::vector<uint8_t> D((size_t)nb2 * 7);
     for (int n = nb2 - 1; n >= 0; n--) {   // children have larger indices than their parent
         const B2Node& bn = B.b2[n];

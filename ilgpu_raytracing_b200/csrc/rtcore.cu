@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -233,7 +234,8 @@ struct rt_ctx {
     bool rendered = false, hasScene = false;
 
     // scene
-    DevBuf<WideNode> nodes; DevBuf<PrimRec> prims; DevBuf<RtInstanceRecord> instances; DevBuf<RtSphere> spheres;
+    DevBuf<unsigned char> bvhBlob;   // wide nodes then primitive records in ONE allocation: a single L2 persisting window covers both
+    DevBuf<RtInstanceRecord> instances; DevBuf<RtSphere> spheres;
     DevBuf<RtFloat2> texcoords; DevBuf<RtMeshTriUV> triUVs; DevBuf<int32_t> triMat; DevBuf<RtMaterialRecord> materials;
     DevBuf<RtRGBA32> texels; DevBuf<RtTexInfo> texInfos;
     DeviceScene ds;
@@ -263,6 +265,7 @@ struct rt_ctx {
     // multi-GPU finish: cached owned-pixel lists of every rank
     DevBuf<int> deintMap; std::vector<int64_t> deintStart; int deintW = 0, deintH = 0, deintT = 0, deintWorld = 0;
     int extendBlocks = 0;
+    size_t l2PersistMax = 0, l2WindowMax = 0, l2Persist = 0, l2Window = 0; cudaStream_t l2WindowStream = nullptr;
     size_t extendSmem = 0;
 };
 
@@ -315,6 +318,7 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     CUDA_TRY(cudaSetDevice(dev));
     rt_ctx* c = new rt_ctx();
     c->device = dev; c->smCount = prop.multiProcessorCount;
+    c->l2PersistMax = (size_t)prop.persistingL2CacheMaxSize; c->l2WindowMax = (size_t)prop.accessPolicyMaxWindowSize;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
     c->stream = c->ownStream;
     CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
@@ -332,7 +336,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     if (!c) return RT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->nodes.release(); c->prims.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
+    c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->pixelMap.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
@@ -373,11 +377,22 @@ RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // nothing in flight may still read the old scene
     cudaStream_t st = c->stream;
     DeviceScene& ds = c->ds;
-    CUDA_TRY(c->nodes.ensure(std::max<size_t>(1, bvh.nodes.size())));
-    CUDA_TRY(c->prims.ensure(std::max<size_t>(1, bvh.prims.size())));
-    if (!bvh.nodes.empty()) CUDA_TRY(cudaMemcpyAsync(c->nodes.p, bvh.nodes.data(), bvh.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, st));
-    if (!bvh.prims.empty()) CUDA_TRY(cudaMemcpyAsync(c->prims.p, bvh.prims.data(), bvh.prims.size() * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
-    ds.nodes = c->nodes.p; ds.nNodes = bvh.prims.empty() ? 0 : (int)bvh.nodes.size(); ds.prims = c->prims.p; ds.nPrims = (int)bvh.prims.size();
+    const size_t nodeBytes = (std::max<size_t>(1, bvh.nodes.size()) * sizeof(WideNode) + 255) / 256 * 256;
+    const size_t primBytes = std::max<size_t>(1, bvh.prims.size()) * sizeof(PrimRec);
+    CUDA_TRY(c->bvhBlob.ensure(nodeBytes + primBytes));
+    WideNode* dNodes = reinterpret_cast<WideNode*>(c->bvhBlob.p);
+    PrimRec* dPrims = reinterpret_cast<PrimRec*>(c->bvhBlob.p + nodeBytes);
+    if (!bvh.nodes.empty()) CUDA_TRY(cudaMemcpyAsync(dNodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, st));
+    if (!bvh.prims.empty()) CUDA_TRY(cudaMemcpyAsync(dPrims, bvh.prims.data(), bvh.prims.size() * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
+    ds.nodes = dNodes; ds.nNodes = bvh.prims.empty() ? 0 : (int)bvh.nodes.size(); ds.prims = dPrims; ds.nPrims = (int)bvh.prims.size();
+    // keep the BVH resident in L2 while GBs of path state stream past it: persisting carve-out + access-policy window (applied per stream in rt_render)
+    c->l2Window = 0;
+    if (!bvh.prims.empty() && c->l2PersistMax > 0 && getenv("RT_NO_L2_PERSIST") == nullptr) {
+        const size_t want = std::min(nodeBytes + primBytes, c->l2PersistMax);
+        if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2Window = std::min(nodeBytes + primBytes, c->l2WindowMax);
+        c->l2Persist = want;
+    }
+    c->l2WindowStream = nullptr;
     CUDA_TRY(upload_or_one(c->instances, d->instances, d->nInstances, st, &ds.nInstances)); ds.instances = c->instances.p;
     CUDA_TRY(upload_or_one(c->spheres, d->spheres, d->nSpheres, st, &ds.nSpheres)); ds.spheres = c->spheres.p;
     CUDA_TRY(upload_or_one(c->texcoords, d->meshTexcoords, d->nMeshTexcoords, st, nullptr)); ds.texcoords = c->texcoords.p;
@@ -469,6 +484,14 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     CUDA_TRY(c->counters.ensure(nCounters));
     CUDA_TRY(c->dstats.ensure(1));
     cudaStream_t st = c->stream;
+    if (c->l2Window > 0 && c->l2WindowStream != st) {   // (re)attach the persisting window to whichever stream renders
+        cudaStreamAttrValue av; memset(&av, 0, sizeof(av));
+        av.accessPolicyWindow.base_ptr = c->bvhBlob.p; av.accessPolicyWindow.num_bytes = c->l2Window;
+        av.accessPolicyWindow.hitRatio = c->l2Persist >= c->l2Window ? 1.0f : (float)c->l2Persist / (float)c->l2Window;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+        c->l2WindowStream = st;
+    }
     CUDA_TRY(cudaEventRecord(c->evStart, st));
     CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, nCounters * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, sizeof(DeviceStats), st));
