@@ -500,14 +500,18 @@ RT_HD void reservoir_update(Reservoir& r, f3 wi, float pdfSel, f3 Li, float scor
     r.m = r.m + max(1, multiplicity);
 }
 
-// ReSTIR_Direct with both reuse flags off (RTRay.cs:438-473, 518-543), split at the visibility test:
-// returns true when a shadow ray must be traced; *wiSel is its direction and *contrib the value
-// ("f_over_p * W", :535-537) the caller adds to Li (times throughput) if the ray is unoccluded.
-RT_HD bool restir_direct_candidates(const LightEnv& env, f3 n, f3 albedo, uint32_t& rng, f3* wiSel, f3* contrib) {
+// ReSTIR_Direct (RTRay.cs:438-543) in three pieces, so the optional prev-frame imports (:475-516, rt_wavefront.h) can sit
+// between candidate generation and the final selection without touching the common path:
+//   restir_new_candidates : (1) eight cosine-hemisphere sky candidates + (2) the directional delta candidate
+//   restir_finalize       : (5) up to the visibility test: true when a shadow ray must be traced; *wiSel is its direction and
+//                           *contrib the value "f_over_p * W" (:535-537) the caller adds to Li (times throughput) if unoccluded
+#define RTX_MIX_LOCAL (8.0f / 9.0f)   // (float)LocalCandidates / (float)TotalNew, :446
+#define RTX_MIX_DELTA (1.0f / 9.0f)   // :447
+RT_HD void restir_new_candidates(const LightEnv& env, f3 n, f3 albedo, uint32_t& rng, Reservoir& r) {
     const int LocalCandidates = 8, DeltaCandidates = 1, TotalNew = LocalCandidates + DeltaCandidates;
     float mixLocal = (float)LocalCandidates / (float)TotalNew;
     float mixDelta = (float)DeltaCandidates / (float)TotalNew;
-    Reservoir r; r.L = mk3(0, 0, 0); r.wi = mk3(0, 0, 0); r.pdf = 0; r.w = 0; r.wSum = 0; r.m = 0; r.lightId = 0;   // :330-335
+    r.L = mk3(0, 0, 0); r.wi = mk3(0, 0, 0); r.pdf = 0; r.w = 0; r.wSum = 0; r.m = 0; r.lightId = 0;   // :330-335
     for (int i = 0; i < LocalCandidates; i++) {   // (1) :452-462
         f3 wi = sample_hemisphere_cosine(n, rng);
         float nl = fmaxf(0.0f, dot(n, wi));
@@ -527,6 +531,9 @@ RT_HD bool restir_direct_candidates(const LightEnv& env, f3 n, f3 albedo, uint32
         float s = luminance(f_over_p);
         reservoir_update(r, wi, pdfSel, LiDir, s, 1, 2, rng);
     }
+}
+RT_HD bool restir_finalize(const LightEnv& env, f3 n, f3 albedo, const Reservoir& r, f3* wiSel, f3* contrib) {
+    const float mixLocal = 8.0f / 9.0f, mixDelta = 1.0f / 9.0f;   // mixLocal2 / mixDelta2, :528-529
     // (5) :519-539 up to the visibility test
     if (!(r.m > 0 && r.wSum > 0.0f && r.w > 0.0f)) return false;
     f3 wsel = r.wi;

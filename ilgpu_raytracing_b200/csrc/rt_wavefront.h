@@ -144,7 +144,9 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
         }
     } else {   // Lambert: ReSTIR-DI + cosine bounce (:277-317)
         f3 wiSel, contrib;
-        if (restir_direct_candidates(fc.env, v.nrm, v.alb, rng, &wiSel, &contrib)) {
+        Reservoir r;
+        restir_new_candidates(fc.env, v.nrm, v.alb, rng, r);
+        if (restir_finalize(fc.env, v.nrm, v.alb, r, &wiSel, &contrib)) {
             RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
             int k = queue_alloc(shCount);

@@ -107,6 +107,17 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
                 if (base >= n) { exhausted = true; break; }
                 poolNext = base;
                 poolEnd = min(base + RT_EXTEND_BATCH, n);
+                // the batch is consumed over the next few dozen steps: pull its ray records towards the SM now, so a
+                // refilled lane does not stall its whole warp on a DRAM round trip
+#pragma unroll
+                for (int k = 0; k < RT_EXTEND_BATCH / 32; k++) {
+                    const int pi = base + k * 32 + lane;
+                    if (pi < n) {
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rayO + pi));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rayD + pi));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rayI + pi));
+                    }
+                }
             }
             const int nIdle = __popc(idle);
             const int take = min(nIdle, poolEnd - poolNext);
