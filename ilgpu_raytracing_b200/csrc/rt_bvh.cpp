@@ -341,11 +341,10 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
             pf[a] = (float)((double)nb.lo[a] - scale[a]);
             if ((double)pf[a] > (double)nb.lo[a]) pf[a] = std::nextafterf(pf[a], -std::numeric_limits<float>::infinity());
         }
-        uint8_t meta[8], qlo[3][8], qhi[3][8]; uint32_t imask = 0;
+        uint8_t qlo[3][8], qhi[3][8]; uint32_t imask = 0, valid24 = 0;
         uint32_t childBase = (uint32_t)out.nodes.size(), primBase = (uint32_t)out.prims.size();
-        int primOff = 0;
         for (int s = 0; s < 8; s++) {
-            meta[s] = 0; for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }
+            for (int a = 0; a < 3; a++) { qlo[a][s] = 255; qhi[a][s] = 0; }
             if (childAt[s] < 0) continue;
             const int c = ch[childAt[s]].b2;
             const bool leafChild = ch[childAt[s]].leaf;
@@ -358,7 +357,6 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
             }
             if (!leafChild) {
                 imask |= 1u << s;
-                meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
                 int wi = (int)out.nodes.size();
                 out.nodes.push_back(WideNode());
                 depthOf.push_back(depthOf[w.wide] + 1);
@@ -366,17 +364,20 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
                 queue.push_back({c, wi});
             } else {
                 uint32_t unary = cn.count == 1 ? 1u : (cn.count == 2 ? 3u : 7u);
-                meta[s] = (uint8_t)((unary << 5) | (uint32_t)primOff);
+                valid24 |= unary << (3 * s);
                 for (int i = 0; i < cn.count; i++) out.prims.push_back(B.prims[B.idx[cn.first + i]].rec);
-                primOff += cn.count;
             }
         }
+        uint32_t imr = 0;
+        for (int s = 0; s < 8; s++) if (!((imask >> s) & 1u)) imr |= 1u << (7 - s);
+        uint32_t pw[3][4];   // word k of axis a = { qlo[2k], qhi[2k], qlo[2k+1], qhi[2k+1] }
+        for (int a = 0; a < 3; a++) for (int k = 0; k < 4; k++) { const uint8_t b[4] = {qlo[a][2 * k], qhi[a][2 * k], qlo[a][2 * k + 1], qhi[a][2 * k + 1]}; pw[a][k] = pack4(b); }
         WideNode& wn = out.nodes[w.wide];
         wn.n0 = make_uint4(fbits(pf[0]), fbits(pf[1]), fbits(pf[2]), (uint32_t)eb[0] | ((uint32_t)eb[1] << 8) | ((uint32_t)eb[2] << 16) | (imask << 24));
-        wn.n1 = make_uint4(childBase, primBase, pack4(meta), pack4(meta + 4));
-        wn.n2 = make_uint4(pack4(qlo[0]), pack4(qlo[0] + 4), pack4(qlo[1]), pack4(qlo[1] + 4));
-        wn.n3 = make_uint4(pack4(qlo[2]), pack4(qlo[2] + 4), pack4(qhi[0]), pack4(qhi[0] + 4));
-        wn.n4 = make_uint4(pack4(qhi[1]), pack4(qhi[1] + 4), pack4(qhi[2]), pack4(qhi[2] + 4));
+        wn.n1 = make_uint4(childBase, primBase, valid24, imr << 24);
+        wn.n2 = make_uint4(pw[0][0], pw[0][1], pw[0][2], pw[0][3]);
+        wn.n3 = make_uint4(pw[1][0], pw[1][1], pw[1][2], pw[1][3]);
+        wn.n4 = make_uint4(pw[2][0], pw[2][1], pw[2][2], pw[2][3]);
     }
     out.stats.nWideNodes = (int64_t)out.nodes.size();
     out.stats.maxDepth = std::max(1, maxDepthSeen);

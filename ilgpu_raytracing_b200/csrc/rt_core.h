@@ -208,13 +208,15 @@ enum : uint32_t {
     PRIM_NO_CLOSEST  = 1u << 28       // no alpha map and 1 < AlphaCutoff: invisible to closest-hit (:209,218), still occludes
 };
 
-// Compressed 8-wide node, 80 B = 5 x uint4 (layout after Ylitie/Karras/Laine, HPG 2017).
+// Compressed 8-wide node, 80 B = 5 x uint4 (after Ylitie/Karras/Laine, HPG 2017; plane bytes re-ordered for one-PRMT decode).
 //   n0 = px, py, pz (quantisation origin, float bits), ex | ey<<8 | ez<<16 | imask<<24
-//   n1 = childBase, primBase, meta[0..3], meta[4..7]
-//   n2 = qlox[0..3], qlox[4..7], qloy[0..3], qloy[4..7]
-//   n3 = qloz[0..3], qloz[4..7], qhix[0..3], qhix[4..7]
-//   n4 = qhiy[0..3], qhiy[4..7], qhiz[0..3], qhiz[4..7]
-// meta[i]: 0 = empty; internal child: 0b001_11sss (sss = slot i); leaf: (unary prim count 1/3/7)<<5 | offset from primBase.
+//   n1 = childBase, primBase, valid24, imr<<24
+//   n2 = x planes, n3 = y planes, n4 = z planes; word k of an axis = { qlo[2k], qhi[2k], qlo[2k+1], qhi[2k+1] } (children 2k, 2k+1)
+// imask   : bit s set = slot s holds an internal child (children are stored compacted in slot order from childBase).
+// valid24 : 3-bit field per slot (bits 3s..3s+2) = unary primitive count (1/3/7) of a leaf child, 0 otherwise; the node's
+//           primitives are stored compacted in (slot, k) order from primBase, so bit b is record primBase + popc(valid24 & below(b)).
+// imr     : the hit-table index (rt_traverse.h: hit_table_entry) whose hit set is exactly imask, i.e. sum over slots of (!imask_s) << (7-s).
+// Empty slots carry inverted planes (qlo = 255, qhi = 0) and can never be hit.
 struct WideNode { uint4 n0, n1, n2, n3, n4; };
 
 struct DeviceScene {

@@ -27,18 +27,39 @@ struct TraceCounters { uint32_t nodes, tris, spheres; };
 #endif
 struct LaneStack {
 #if defined(__CUDACC__)
-    uint2* smem;      // &shared[threadIdx.x]
-    int stride;       // blockDim.x
+    uint2* smem;           // &shared[threadIdx.x]
+    int stride;            // blockDim.x
     int sp;
+    const uint32_t* lut;   // hit table (RT_HIT_TABLE_WORDS words of shared memory, filled by fill_hit_table)
     RT_HD void store_top(uint2 v) { smem[sp * stride] = v; }
     RT_HD uint2 load_below() const { return smem[(sp > 0 ? sp - 1 : 0) * stride]; }
 #else
     uint2 all[RT_STACK_ENTRIES + 1];
     int sp;
+    const uint32_t* lut;
     RT_HD void store_top(uint2 v) { all[sp] = v; }
     RT_HD uint2 load_below() const { return all[sp > 0 ? sp - 1 : 0]; }
 #endif
 };
+
+// Hit table: turns the 8 box-test results of a node into the traversal's hit mask with one shared-memory load.
+// Index = octinv * 256 + mr, where bit (7 - s) of mr is set when the child in slot s was MISSED (the order in which
+// node_step shifts the sign bits of the eight slab differences together).  Entry:
+//   bits 24..31 : slot s hit -> bit 24 + (s ^ octinv)   (octant-ordered visiting: the highest bit is visited first)
+//   bits  0..23 : slot s hit -> the 3-bit field 3s..3s+2 (masked with the node's valid24 to give the queued primitives)
+#define RT_HIT_TABLE_WORDS 2048
+RT_HD uint32_t hit_table_entry(uint32_t octinv, uint32_t mr) {
+    uint32_t e = 0;
+    for (uint32_t s = 0; s < 8; s++)
+        if (!((mr >> (7u - s)) & 1u)) e |= (1u << (24u + (s ^ octinv))) | (7u << (3u * s));
+    return e;
+}
+#if !defined(__CUDACC__)
+inline const uint32_t* host_hit_table() {
+    static const struct Tab { uint32_t w[RT_HIT_TABLE_WORDS]; Tab() { for (uint32_t i = 0; i < RT_HIT_TABLE_WORDS; i++) w[i] = hit_table_entry(i >> 8, i & 255u); } } tab;
+    return tab.w;
+}
+#endif
 
 // box-test reciprocal of a ray direction: ours (never inf); the reference's 1e-8 substitution is kept for d == 0 (RTRay.cs:548-549)
 RT_HD f3 box_idir(f3 d) {
@@ -117,17 +138,39 @@ GenResult test_prim_general(const DeviceScene& sc, f3 o, f3 d, float4 q0, float4
     return res;
 }
 
-// Bytes J and K of w as the floats 1024 + b: ONE byte permute builds the half2 {0x64bb, 0x64bb} (fp16 1024 + b, exact),
-// two HADD2.F32 widen it.  No int->float conversion (slow XU pipe) and half the permutes of a per-byte decode, so the
-// box test leans on the FMA pipe instead of the saturated ALU pipe.  With O = o - 1024 a:  fma(m, a, O) = b * a + o.
-template <int J, int K> RT_HD void byte_pair_1024(uint32_t w, float& fj, float& fk) {
+// Two plane bytes of a node word as the floats 1024 + b.  sel picks the bytes (PRMT selector: result bytes 0 and 2 from
+// the word, bytes 1 and 3 = 0x64 from the constant), so ONE byte permute builds the half2 {0x64bb, 0x64bb} (fp16 1024 + b,
+// exact) whichever of the word's lo / hi planes the ray's direction sign makes "near"; two HADD2.F32 widen it.  No
+// int->float conversion (slow XU pipe), no per-node near/far selects, and the widening runs on the FMA pipe instead of the
+// saturated ALU pipe.  With O = o - 1024 a:  fma(m, a, O) = b * a + o.
+//   selector 0x4240 = { byte 0, byte 2 } = the qlo planes of the word's two children, 0x4341 = { byte 1, byte 3 } = the qhi planes
+RT_HD void plane_pair_1024(uint32_t w, uint32_t sel, float& fa, float& fb) {
 #if defined(__CUDA_ARCH__)
-    const uint32_t h2 = __byte_perm(w, 0x64646464u, 0x4040u | J | (K << 8));
+    const uint32_t h2 = __byte_perm(w, 0x64646464u, sel);
     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
-    fj = f.x; fk = f.y;
+    fa = f.x; fb = f.y;
 #else
-    fj = 1024.0f + (float)((w >> (8 * J)) & 0xFFu);
-    fk = 1024.0f + (float)((w >> (8 * K)) & 0xFFu);
+    const uint32_t ia = sel & 7u, ib = (sel >> 8) & 7u;
+    fa = 1024.0f + (float)((w >> (8u * ia)) & 0xFFu);
+    fb = 1024.0f + (float)((w >> (8u * ib)) & 0xFFu);
+#endif
+}
+#if defined(__CUDA_ARCH__)
+// (a0, a1) * (b, b) + (c, c) as one packed fma.rn.f32x2 (FFMA2 on sm_100)
+__device__ __forceinline__ void rt_fma2(float a0, float a1, float b, float c, float& d0, float& d1) {
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %4};\n\tmov.b64 rc, {%5, %5};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
+}
+#endif
+#ifndef RT_USE_FFMA2
+#define RT_USE_FFMA2 1
+#endif
+RT_HD uint32_t rt_funnel_l1(uint32_t lo, uint32_t hi) {   // (hi << 1) | (lo >> 31)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, 1);
+#else
+    return (hi << 1) | (lo >> 31);
 #endif
 }
 
@@ -142,7 +185,10 @@ struct Traversal {
     f3 o, d, idir;
     float tMax;
     uint32_t octinv;
+    uint32_t selNx, selNy, selNz;   // PRMT selectors of the near planes per axis (plane_pair_1024); far = near ^ 0x0101
+    const uint32_t* lut;            // this ray's octant slice of the hit table
     uint2 ngroup, tgroup;
+    uint32_t tvalid;                // valid24 of the node whose primitives are queued in tgroup
     BestHit best;
     bool occluded, done;
 
@@ -151,6 +197,13 @@ struct Traversal {
         best.t = ANY_HIT ? tMax_ : 1e30f; best.tObj = best.t; best.rank = 0xFFFFFFFFu; best.inst = -1; best.prim = -1; best.bu = 0.0f; best.bv = 0.0f;
         occluded = false; done = false;
         octinv = 7u - ((idir.x < 0.0f ? 1u : 0u) | (idir.y < 0.0f ? 2u : 0u) | (idir.z < 0.0f ? 4u : 0u));
+        selNx = idir.x < 0.0f ? 0x4341u : 0x4240u; selNy = idir.y < 0.0f ? 0x4341u : 0x4240u; selNz = idir.z < 0.0f ? 0x4341u : 0x4240u;
+#if defined(__CUDACC__)
+        lut = stack.lut + octinv * 256u;
+#else
+        lut = host_hit_table() + octinv * 256u;
+#endif
+        tvalid = 0u;
         stack.sp = 0;
         ngroup = make_uint2(0u, 0x80000000u);   // "child 7^octinv of a virtual parent whose child block starts at node 0" = the root
         tgroup = make_uint2(0u, 0u);
@@ -167,37 +220,41 @@ struct Traversal {
         if (need && !empty) { ngroup = top; stack.sp--; }
     }
 
-    // one child: slab test on the decoded quantised planes (m = 1024 + q), then its bits into the hit mask
-    template <int J>
+    // one child: slab test on the decoded quantised planes (m = 1024 + q); the sign bit of the slab difference is shifted
+    // into mr (set = missed).  No NaN can occur: box_idir keeps |1/d| <= 1e20, so every t is finite.
     RT_HD void child_test(float nxq, float fxq, float nyq, float fyq, float nzq, float fzq, float Ax, float Ay, float Az,
-                          float Ox, float Oy, float Oz, float tFar, uint32_t childBits4, uint32_t bitIndex4, uint32_t& hitmask) const {
+                          float Ox, float Oy, float Oz, float tFar, uint32_t& mr) const {
         const float t0x = rt_fma(nxq, Ax, Ox), t1x = rt_fma(fxq, Ax, Ox);
         const float t0y = rt_fma(nyq, Ay, Oy), t1y = rt_fma(fyq, Ay, Oy);
         const float t0z = rt_fma(nzq, Az, Oz), t1z = rt_fma(fzq, Az, Oz);
         const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.001f));   // box tMin: SceneDeviceViews.cs:37,131
         const float tf = fminf(fminf(t1x, t1y), fminf(t1z, tFar));
-        // conservative: allow for the rounding of either side (quantised planes carry >= 0.01 quantum of slack, rt_bvh.cpp)
-        if (tn <= tf * 1.0000007f) {
-            const uint32_t cb = (childBits4 >> (8 * J)) & 0xFFu;
-            const uint32_t bi = (bitIndex4 >> (8 * J)) & 0xFFu;
-            hitmask |= cb << bi;
-        }
+        // conservative: hit when tn <= tf * (1 + 6 ulp), allowing for the rounding of either side (the quantised planes carry
+        // >= 0.01 quantum of slack on top, rt_bvh.cpp)
+        const float diff = rt_fma(tf, 1.0000007f, -tn);
+        mr = rt_funnel_l1(f2u(diff), mr);
     }
-    // four children whose plane bytes sit in the same six words
-    RT_HD void quad_test(uint32_t wnx, uint32_t wfx, uint32_t wny, uint32_t wfy, uint32_t wnz, uint32_t wfz, uint32_t meta4, uint32_t octinv4,
-                         float Ax, float Ay, float Az, float Ox, float Oy, float Oz, float tFar, uint32_t& hitmask) const {
-        const uint32_t isInner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t innerMask4 = (isInner4 >> 4) * 0xFFu;
-        const uint32_t bitIndex4 = (meta4 ^ (octinv4 & innerMask4)) & 0x1F1F1F1Fu;
-        const uint32_t childBits4 = (meta4 >> 5) & 0x07070707u;
-        float nx0, nx1, nx2, nx3, fx0, fx1, fx2, fx3, ny0, ny1, ny2, ny3, fy0, fy1, fy2, fy3, nz0, nz1, nz2, nz3, fz0, fz1, fz2, fz3;
-        byte_pair_1024<0, 1>(wnx, nx0, nx1); byte_pair_1024<2, 3>(wnx, nx2, nx3); byte_pair_1024<0, 1>(wfx, fx0, fx1); byte_pair_1024<2, 3>(wfx, fx2, fx3);
-        byte_pair_1024<0, 1>(wny, ny0, ny1); byte_pair_1024<2, 3>(wny, ny2, ny3); byte_pair_1024<0, 1>(wfy, fy0, fy1); byte_pair_1024<2, 3>(wfy, fy2, fy3);
-        byte_pair_1024<0, 1>(wnz, nz0, nz1); byte_pair_1024<2, 3>(wnz, nz2, nz3); byte_pair_1024<0, 1>(wfz, fz0, fz1); byte_pair_1024<2, 3>(wfz, fz2, fz3);
-        child_test<0>(nx0, fx0, ny0, fy0, nz0, fz0, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
-        child_test<1>(nx1, fx1, ny1, fy1, nz1, fz1, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
-        child_test<2>(nx2, fx2, ny2, fy2, nz2, fz2, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
-        child_test<3>(nx3, fx3, ny3, fy3, nz3, fz3, Ax, Ay, Az, Ox, Oy, Oz, tFar, childBits4, bitIndex4, hitmask);
+    // the two children whose plane bytes share one word per axis
+    RT_HD void pair_test(uint32_t wx, uint32_t wy, uint32_t wz, uint32_t sFx, uint32_t sFy, uint32_t sFz,
+                         float Ax, float Ay, float Az, float Ox, float Oy, float Oz, float tFar, uint32_t& mr) const {
+        float nxa, nxb, fxa, fxb, nya, nyb, fya, fyb, nza, nzb, fza, fzb;
+        plane_pair_1024(wx, selNx, nxa, nxb); plane_pair_1024(wx, sFx, fxa, fxb);
+        plane_pair_1024(wy, selNy, nya, nyb); plane_pair_1024(wy, sFy, fya, fyb);
+        plane_pair_1024(wz, selNz, nza, nzb); plane_pair_1024(wz, sFz, fza, fzb);
+#if defined(__CUDA_ARCH__) && RT_USE_FFMA2
+        // sm_100 packed fp32: one FFMA2 evaluates the same plane of both children (each half is an ordinary IEEE fma)
+        float t0xa, t0xb, t1xa, t1xb, t0ya, t0yb, t1ya, t1yb, t0za, t0zb, t1za, t1zb;
+        rt_fma2(nxa, nxb, Ax, Ox, t0xa, t0xb); rt_fma2(fxa, fxb, Ax, Ox, t1xa, t1xb);
+        rt_fma2(nya, nyb, Ay, Oy, t0ya, t0yb); rt_fma2(fya, fyb, Ay, Oy, t1ya, t1yb);
+        rt_fma2(nza, nzb, Az, Oz, t0za, t0zb); rt_fma2(fza, fzb, Az, Oz, t1za, t1zb);
+        const float tna = fmaxf(fmaxf(t0xa, t0ya), fmaxf(t0za, 0.001f)), tnb = fmaxf(fmaxf(t0xb, t0yb), fmaxf(t0zb, 0.001f));
+        const float tfa = fminf(fminf(t1xa, t1ya), fminf(t1za, tFar)), tfb = fminf(fminf(t1xb, t1yb), fminf(t1zb, tFar));
+        mr = rt_funnel_l1(f2u(rt_fma(tfa, 1.0000007f, -tna)), mr);
+        mr = rt_funnel_l1(f2u(rt_fma(tfb, 1.0000007f, -tnb)), mr);
+#else
+        child_test(nxa, fxa, nya, fya, nza, fza, Ax, Ay, Az, Ox, Oy, Oz, tFar, mr);
+        child_test(nxb, fxb, nyb, fyb, nzb, fzb, Ax, Ay, Az, Ox, Oy, Oz, tFar, mr);
+#endif
     }
 
     // precondition: !done, tgroup.y == 0 (so ngroup.y > 0x00FFFFFF)
@@ -215,23 +272,23 @@ struct Traversal {
         if (COUNT) cnt->nodes++;
         const uint4 n0 = rt_ldg(&np->n0), n1 = rt_ldg(&np->n1), n2 = rt_ldg(&np->n2), n3 = rt_ldg(&np->n3), n4 = rt_ldg(&np->n4);
 
-        const bool nx = idir.x < 0.0f, ny = idir.y < 0.0f, nz = idir.z < 0.0f;
-        const uint32_t octinv4 = octinv * 0x01010101u;
-        // a = 2^e / d,  O = (p - o) / d - 1024 a   (see byte_pair_1024)
+        const uint32_t pmask = lut[n1.w >> 24];           // octant-ordered bits of the node's internal children (independent of the box tests)
+        // a = 2^e / d,  O = (p - o) / d - 1024 a   (see plane_pair_1024)
         const float Ax = u2f((n0.w & 0xFFu) << 23) * idir.x, Ay = u2f(((n0.w >> 8) & 0xFFu) << 23) * idir.y, Az = u2f(((n0.w >> 16) & 0xFFu) << 23) * idir.z;
         const float Ox = rt_fma(u2f(n0.x) - o.x, idir.x, -1024.0f * Ax), Oy = rt_fma(u2f(n0.y) - o.y, idir.y, -1024.0f * Ay), Oz = rt_fma(u2f(n0.z) - o.z, idir.z, -1024.0f * Az);
-        // near/far plane words chosen by the ray's sign, once per node
-        const uint32_t nearx0 = nx ? n3.z : n2.x, nearx1 = nx ? n3.w : n2.y, farx0 = nx ? n2.x : n3.z, farx1 = nx ? n2.y : n3.w;
-        const uint32_t neary0 = ny ? n4.x : n2.z, neary1 = ny ? n4.y : n2.w, fary0 = ny ? n2.z : n4.x, fary1 = ny ? n2.w : n4.y;
-        const uint32_t nearz0 = nz ? n4.z : n3.x, nearz1 = nz ? n4.w : n3.y, farz0 = nz ? n3.x : n4.z, farz1 = nz ? n3.y : n4.w;
+        const uint32_t sFx = selNx ^ 0x0101u, sFy = selNy ^ 0x0101u, sFz = selNz ^ 0x0101u;
         const float tFar = best.t * sc.tFarScale;
-        uint32_t hitmask = 0;
-        quad_test(nearx0, farx0, neary0, fary0, nearz0, farz0, n1.z, octinv4, Ax, Ay, Az, Ox, Oy, Oz, tFar, hitmask);
-        quad_test(nearx1, farx1, neary1, fary1, nearz1, farz1, n1.w, octinv4, Ax, Ay, Az, Ox, Oy, Oz, tFar, hitmask);
+        uint32_t mr = 0;
+        pair_test(n2.x, n3.x, n4.x, sFx, sFy, sFz, Ax, Ay, Az, Ox, Oy, Oz, tFar, mr);
+        pair_test(n2.y, n3.y, n4.y, sFx, sFy, sFz, Ax, Ay, Az, Ox, Oy, Oz, tFar, mr);
+        pair_test(n2.z, n3.z, n4.z, sFx, sFy, sFz, Ax, Ay, Az, Ox, Oy, Oz, tFar, mr);
+        pair_test(n2.w, n3.w, n4.w, sFx, sFy, sFz, Ax, Ay, Az, Ox, Oy, Oz, tFar, mr);
+        const uint32_t hitmask = lut[mr];
         ngroup.x = n1.x;
-        ngroup.y = (hitmask & 0xFF000000u) | (n0.w >> 24);
+        ngroup.y = (hitmask & pmask & 0xFF000000u) | (n0.w >> 24);
         tgroup.x = n1.y;
-        tgroup.y = hitmask & 0x00FFFFFFu;
+        tvalid = n1.z;
+        tgroup.y = hitmask & n1.z & 0x00FFFFFFu;
         if (tgroup.y == 0u) advance(stack);
     }
 
@@ -239,7 +296,7 @@ struct Traversal {
     RT_HD void prim_step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
         const int bit = rt_bfind(tgroup.y);
         tgroup.y &= ~(1u << bit);
-        const int pi = (int)tgroup.x + bit;
+        const int pi = (int)tgroup.x + rt_popc(tvalid & ~(0xFFFFFFFFu << bit));   // records are compacted: count the valid bits below
         const PrimRec* pp = sc.prims + pi;
         const float4 q0 = rt_ldg(&pp->q0), q1 = rt_ldg(&pp->q1), q2 = rt_ldg(&pp->q2);
         const uint32_t meta = f2u(q2.w);
@@ -255,6 +312,21 @@ struct Traversal {
                     const int inst = (int)(meta & PRIM_INST_MASK);
                     if (better_hit(best, t, t, rank, inst)) {
                         best.t = t; best.tObj = t; best.rank = rank; best.inst = inst; best.prim = pi; best.bu = bu; best.bv = bv;
+                    }
+                }
+            }
+        } else if ((meta & (PRIM_SPHERE | PRIM_XFORM | PRIM_ALPHA | PRIM_NO_CLOSEST)) == PRIM_SPHERE) {
+            // fast path: sphere of an identity instance (scale 1: tWorld = tObj / 1, tMaxObj = tMaxWorld * 1, SceneDeviceViews.cs:67,107)
+            if (COUNT) cnt->spheres++;
+            float t;
+            if (intersect_sphere(o, d, mk3(q0.x, q0.y, q0.z), q1.x, &t)) {
+                if (ANY_HIT) {
+                    if (t > 0.001f && t < tMax) { occluded = true; done = true; return; }   // :257
+                } else if (t > 0.001f) {                                                    // :142
+                    const uint32_t rank = f2u(q1.w);
+                    const int inst = (int)(meta & PRIM_INST_MASK);
+                    if (better_hit(best, t, t, rank, inst)) {
+                        best.t = t; best.tObj = t; best.rank = rank; best.inst = inst; best.prim = pi; best.bu = 0.0f; best.bv = 0.0f;
                     }
                 }
             }

@@ -35,6 +35,9 @@ using namespace rtx;
 #ifndef RT_NODE_STEPS
 #define RT_NODE_STEPS 2       // node steps per loop iteration (amortises the refill / vote / finalise overhead)
 #endif
+#ifndef RT_PRIM_DRAIN
+#define RT_PRIM_DRAIN 0
+#endif
 #ifndef RT_PRIM_VOTE
 #define RT_PRIM_VOTE 1       // lanes that must have a primitive queued before the warp runs a primitive phase (sweep: 1 is best)
 #endif
@@ -66,11 +69,13 @@ __global__ void k_generate_primary(FrameConst fc, RayQueue q, int* countOut) {
 // replaced at the next step instead of idling until the slowest lane of its batch is done.
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend(ExtendArgs a) {
-    extern __shared__ uint2 smemStack[];
+    extern __shared__ uint2 smemStack[];   // [RT_STACK_ENTRIES][RT_EXTEND_THREADS] stack entries, then the hit table
+    uint32_t* hitTable = reinterpret_cast<uint32_t*>(smemStack + RT_STACK_ENTRIES * RT_EXTEND_THREADS);
     LaneStack stack;
     stack.smem = smemStack + threadIdx.x;
     stack.stride = RT_EXTEND_THREADS;
     stack.sp = 0;
+    stack.lut = hitTable;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
@@ -89,6 +94,8 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         }
         return;
     }
+    for (uint32_t i = threadIdx.x; i < RT_HIT_TABLE_WORDS; i += RT_EXTEND_THREADS) hitTable[i] = hit_table_entry(i >> 8, i & 255u);
+    __syncthreads();
     Traversal<ANY_HIT, COUNT> tr;
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0; cnt.spheres = 0;
     bool active = false, exhausted = false;
@@ -141,6 +148,15 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
             if (active && !tr.done && !tr.has_prims()) tr.node_step(a.sc, stack, &cnt);
         // ---- primitive phase, voted warp-wide: the exact intersectors are long and divergent, so run them only when
         //      enough lanes have a primitive queued (or nobody can do node work); lanes holding primitives wait ----
+#if RT_PRIM_DRAIN
+        // drain: run primitive steps until no lane of the warp holds a queued primitive, so that every lane is back to node
+        // work (or finished) when the next node phase starts
+        for (;;) {
+            const bool wantPrim = active && !tr.done && tr.has_prims();
+            if (__ballot_sync(FULL, wantPrim) == 0u) break;
+            if (wantPrim) tr.prim_step(a.sc, stack, &cnt);
+        }
+#else
         const bool wantPrim = active && !tr.done && tr.has_prims();
         const unsigned pm = __ballot_sync(FULL, wantPrim);
         if (pm != 0u) {
@@ -149,6 +165,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
                 if (wantPrim) tr.prim_step(a.sc, stack, &cnt);
             }
         }
+#endif
         if (active && tr.done) {
             if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
             else { const HitRec h = tr.result(); __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv)); }
@@ -333,7 +350,7 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
     c->stream = c->ownStream;
     CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
-    c->extendSmem = (size_t)RT_STACK_ENTRIES * RT_EXTEND_THREADS * sizeof(uint2);
+    c->extendSmem = (size_t)RT_STACK_ENTRIES * RT_EXTEND_THREADS * sizeof(uint2) + (size_t)RT_HIT_TABLE_WORDS * sizeof(uint32_t);
     int perSm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
     if (perSm < 1) perSm = 1;
@@ -477,7 +494,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     const int spp = cfg->spp > 1 ? cfg->spp : 1;
     const int64_t npxOwned = count_owned_pixels(cfg->width, cfg->height, cfg->tileSize, cfg->worldSize > 1 ? cfg->rank : 0, cfg->worldSize > 1 ? cfg->worldSize : 1);
     int S = cfg->samplesPerPass;
-    if (S <= 0) { const int64_t target = 16ll << 20; S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned))); }
+    if (S <= 0) { int64_t target = 16ll << 20; if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) target = v; } S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned))); }
     S = std::min(S, spp);
     if ((int64_t)npxOwned * S > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: samplesPerPass * pixels exceeds 2^31 paths");
     int rc = ensure_frame_buffers(c, cfg, S);
