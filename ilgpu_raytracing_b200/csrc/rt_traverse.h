@@ -210,9 +210,11 @@ struct Traversal {
     }
 
     RT_HD bool has_prims() const { return tgroup.y != 0u; }
+    RT_HD bool has_node_work() const { return ngroup.y > 0x00FFFFFFu; }
+    RT_HD bool can_node_step(const LaneStack&) const { return has_node_work() && tgroup.y == 0u; }
 
     // next node group from the stack, or done (selects only: every lane of the warp runs this together)
-    RT_HD void advance(LaneStack& stack) {
+    RT_HD void advance(const DeviceScene&, LaneStack& stack) {
         const uint2 top = stack.load_below();
         const bool need = ngroup.y <= 0x00FFFFFFu;
         const bool empty = stack.sp == 0;
@@ -257,7 +259,7 @@ struct Traversal {
 #endif
     }
 
-    // precondition: !done, tgroup.y == 0 (so ngroup.y > 0x00FFFFFF)
+    // precondition: !done, can_node_step()
     RT_HD void node_step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
         const uint32_t hits = ngroup.y;
         const int bit = rt_bfind(hits);
@@ -289,7 +291,7 @@ struct Traversal {
         tgroup.x = n1.y;
         tvalid = n1.z;
         tgroup.y = hitmask & n1.z & 0x00FFFFFFu;
-        if (tgroup.y == 0u) advance(stack);
+        if (tgroup.y == 0u) advance(sc, stack);
     }
 
     // precondition: !done, tgroup.y != 0
@@ -338,12 +340,12 @@ struct Traversal {
                 best.t = r.tW; best.tObj = r.tO; best.rank = f2u(q1.w); best.inst = (int)(meta & PRIM_INST_MASK); best.prim = pi; best.bu = r.bu; best.bv = r.bv;
             }
         }
-        if (tgroup.y == 0u) advance(stack);
+        if (tgroup.y == 0u) advance(sc, stack);
     }
 
     // one node and all of its primitives; returns true when the traversal is finished
     RT_HD bool step(const DeviceScene& sc, LaneStack& stack, TraceCounters* cnt) {
-        node_step(sc, stack, cnt);
+        if (has_node_work()) node_step(sc, stack, cnt);
         while (!done && tgroup.y != 0u) prim_step(sc, stack, cnt);
         return done;
     }

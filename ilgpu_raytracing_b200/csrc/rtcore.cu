@@ -31,12 +31,11 @@ using namespace rtx;
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 5
 #endif
+#ifndef RT_EXTEND_BATCH
 #define RT_EXTEND_BATCH 96   // ray indices a warp takes from the global queue per atomic
+#endif
 #ifndef RT_NODE_STEPS
 #define RT_NODE_STEPS 2       // node steps per loop iteration (amortises the refill / vote / finalise overhead)
-#endif
-#ifndef RT_PRIM_DRAIN
-#define RT_PRIM_DRAIN 0
 #endif
 #ifndef RT_PRIM_VOTE
 #define RT_PRIM_VOTE 1       // lanes that must have a primitive queued before the warp runs a primitive phase (sweep: 1 is best)
@@ -69,8 +68,11 @@ __global__ void k_generate_primary(FrameConst fc, RayQueue q, int* countOut) {
 // replaced at the next step instead of idling until the slowest lane of its batch is done.
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend(ExtendArgs a) {
-    extern __shared__ uint2 smemStack[];   // [RT_STACK_ENTRIES][RT_EXTEND_THREADS] stack entries, then the hit table
-    uint32_t* hitTable = reinterpret_cast<uint32_t*>(smemStack + RT_STACK_ENTRIES * RT_EXTEND_THREADS);
+    // dynamic shared memory: hit table | traversal stacks [entries][RT_EXTEND_THREADS], entries = depth of this scene's wide
+    // BVH + 1 (sized by the host, so a shallow tree leaves more of the SM's 228 KB to the L1 cache that serves the node fetches)
+    extern __shared__ __align__(16) uint32_t smemRaw[];
+    uint32_t* hitTable = smemRaw;
+    uint2* smemStack = reinterpret_cast<uint2*>(hitTable + RT_HIT_TABLE_WORDS);
     LaneStack stack;
     stack.smem = smemStack + threadIdx.x;
     stack.stride = RT_EXTEND_THREADS;
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
     int poolNext = 0, poolEnd = 0;   // warp-uniform
 
     for (;;) {
-        // ---- refill idle lanes (warp-uniform control flow) ----
+        // ---- refill idle lanes straight from the queue (warp-uniform control flow) ----
         for (;;) {
             const unsigned idle = __ballot_sync(FULL, !active);
             if (idle == 0u || exhausted) break;
@@ -114,17 +116,6 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
                 if (base >= n) { exhausted = true; break; }
                 poolNext = base;
                 poolEnd = min(base + RT_EXTEND_BATCH, n);
-                // the batch is consumed over the next few dozen steps: pull its ray records towards the SM now, so a
-                // refilled lane does not stall its whole warp on a DRAM round trip
-#pragma unroll
-                for (int k = 0; k < RT_EXTEND_BATCH / 32; k++) {
-                    const int pi = base + k * 32 + lane;
-                    if (pi < n) {
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rayO + pi));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rayD + pi));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(a.rayI + pi));
-                    }
-                }
             }
             const int nIdle = __popc(idle);
             const int take = min(nIdle, poolEnd - poolNext);
@@ -145,27 +136,17 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         // ---- node phase: lanes without queued primitives advance by up to RT_NODE_STEPS wide nodes ----
 #pragma unroll
         for (int ns = 0; ns < RT_NODE_STEPS; ns++)
-            if (active && !tr.done && !tr.has_prims()) tr.node_step(a.sc, stack, &cnt);
+            if (active && !tr.done && tr.can_node_step(stack)) tr.node_step(a.sc, stack, &cnt);
         // ---- primitive phase, voted warp-wide: the exact intersectors are long and divergent, so run them only when
         //      enough lanes have a primitive queued (or nobody can do node work); lanes holding primitives wait ----
-#if RT_PRIM_DRAIN
-        // drain: run primitive steps until no lane of the warp holds a queued primitive, so that every lane is back to node
-        // work (or finished) when the next node phase starts
-        for (;;) {
-            const bool wantPrim = active && !tr.done && tr.has_prims();
-            if (__ballot_sync(FULL, wantPrim) == 0u) break;
-            if (wantPrim) tr.prim_step(a.sc, stack, &cnt);
-        }
-#else
         const bool wantPrim = active && !tr.done && tr.has_prims();
         const unsigned pm = __ballot_sync(FULL, wantPrim);
         if (pm != 0u) {
-            const unsigned nm = __ballot_sync(FULL, active && !tr.done && !tr.has_prims());
+            const unsigned nm = __ballot_sync(FULL, active && !tr.done && tr.can_node_step(stack));
             if (__popc(pm) >= RT_PRIM_VOTE || nm == 0u) {
                 if (wantPrim) tr.prim_step(a.sc, stack, &cnt);
             }
         }
-#endif
         if (active && tr.done) {
             if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
             else { const HitRec h = tr.result(); __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv)); }
@@ -325,10 +306,23 @@ template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs
     return trace_event(c);
 }
 
+// persistent grid of the extend kernels: shared memory for a traversal stack of `entries` per lane, blocks = occupancy x SMs
+static int size_extend_launch(rt_ctx* c, int entries) {
+    entries = std::max(2, std::min(entries, RT_STACK_ENTRIES));
+    c->extendSmem = (size_t)RT_HIT_TABLE_WORDS * sizeof(uint32_t) + (size_t)entries * RT_EXTEND_THREADS * sizeof(uint2);
+    int perSm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
+    if (perSm < 1) perSm = 1;
+    c->extendBlocks = perSm * c->smCount;
+    return RT_OK;
+}
+
 extern "C" {
 
 RT_API int rt_abi_version(void) { return RT_ABI_VERSION; }
 RT_API const char* rt_last_error(void) { return g_lastError.c_str(); }
+
+RT_API int rt_destroy(rt_ctx* c);
 
 RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_create: out is null");
@@ -350,11 +344,8 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
     c->stream = c->ownStream;
     CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
-    c->extendSmem = (size_t)RT_STACK_ENTRIES * RT_EXTEND_THREADS * sizeof(uint2) + (size_t)RT_HIT_TABLE_WORDS * sizeof(uint32_t);
-    int perSm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
-    if (perSm < 1) perSm = 1;
-    c->extendBlocks = perSm * c->smCount;
+    int rc = size_extend_launch(c, RT_STACK_ENTRIES);
+    if (rc != RT_OK) { rt_destroy(c); return rc; }
     memset(&c->ds, 0, sizeof(c->ds)); memset(&c->hstats, 0, sizeof(c->hstats));
     *out = c;
     return RT_OK;
@@ -432,6 +423,8 @@ RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
     ds.triMaterials = 0;
     ds.tFarScale = bvh.stats.maxInstanceScale;
     CUDA_TRY(cudaStreamSynchronize(st));   // host arrays are only borrowed for the duration of the call
+    const int rcSize = size_extend_launch(c, bvh.stats.maxDepth + 1);   // a node step pushes at most one entry per level
+    if (rcSize != RT_OK) return rcSize;
     c->bvhStats = bvh.stats;
     c->bvhBytes = bvh.nodes.size() * sizeof(WideNode) + bvh.prims.size() * sizeof(PrimRec);
     c->hasScene = true;

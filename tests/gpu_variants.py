@@ -16,6 +16,9 @@ for v in variants:
     cmd = ["nvcc"] + build.NVCC_FLAGS + defs + ["-o", so] + build.CORE_SRCS
     subprocess.run(cmd, check=True)
     env = dict(os.environ, RTCORE_B200_LIB=so)
+    if os.environ.get("VARIANT_PYTEST"):   # parity of the variant build: the whole GPU suite against the oracle
+        t = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-x", "-q"], env=env, capture_output=True, text=True)
+        print(name, "pytest:", t.stdout.strip().splitlines()[-1] if t.stdout.strip() else t.stderr[-300:], flush=True)
     out = subprocess.run([sys.executable, "tests/gpu_variant_run.py"], env=env, capture_output=True, text=True)
     try:
         results[name] = json.loads(out.stdout.strip().splitlines()[-1])
