@@ -457,17 +457,24 @@ RT_HD float schlick_fresnel(float c, float etaI, float etaT) {   // :575-583
     float m5 = m2 * m2 * m;
     return r0 + (1.0f - r0) * m5;
 }
-RT_HD f3 sample_hemisphere_cosine(f3 n, uint32_t& rng) {   // :586-606
+// OrthonormalBasis (:601-606) is a pure function of the normal: a vertex evaluates it once for its nine calls of
+// SampleHemisphereCosine (eight ReSTIR candidates + the bounce) instead of once per call; same operations, same bits.
+struct Basis { f3 t, b; };
+RT_HD Basis orthonormal_basis(f3 n) {
+    f3 up = fabsf(n.y) < 0.999f ? mk3(0, 1, 0) : mk3(1, 0, 0);
+    Basis B;
+    B.t = normalize(cross(up, n));
+    B.b = cross(n, B.t);
+    return B;
+}
+RT_HD f3 sample_hemisphere_cosine(f3 n, const Basis& B, uint32_t& rng) {   // :586-598
     float r1 = rng_next_f(rng), r2 = rng_next_f(rng);
     float phi = 2.0f * RTX_PI * r1;
     float cosTheta = sqrtf(1.0f - r2);
     float sinTheta = sqrtf(r2);
     float sphi, cphi; sincos_pi2(phi, &sphi, &cphi);
     float x = cphi * sinTheta, y = sphi * sinTheta, z = cosTheta;
-    f3 up = fabsf(n.y) < 0.999f ? mk3(0, 1, 0) : mk3(1, 0, 0);
-    f3 t = normalize(cross(up, n));
-    f3 b = cross(n, t);
-    f3 v = t * x + b * y + n * z;
+    f3 v = B.t * x + B.b * y + n * z;
     return normalize(v);
 }
 RT_HD float luminance(f3 c) { return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z; }              // :627
@@ -509,13 +516,13 @@ RT_HD void reservoir_update(Reservoir& r, f3 wi, float pdfSel, f3 Li, float scor
 //                           *contrib the value "f_over_p * W" (:535-537) the caller adds to Li (times throughput) if unoccluded
 #define RTX_MIX_LOCAL (8.0f / 9.0f)   // (float)LocalCandidates / (float)TotalNew, :446
 #define RTX_MIX_DELTA (1.0f / 9.0f)   // :447
-RT_HD void restir_new_candidates(const LightEnv& env, f3 n, f3 albedo, uint32_t& rng, Reservoir& r) {
+RT_HD void restir_new_candidates(const LightEnv& env, f3 n, const Basis& B, f3 albedo, uint32_t& rng, Reservoir& r) {
     const int LocalCandidates = 8, DeltaCandidates = 1, TotalNew = LocalCandidates + DeltaCandidates;
     float mixLocal = (float)LocalCandidates / (float)TotalNew;
     float mixDelta = (float)DeltaCandidates / (float)TotalNew;
     r.L = mk3(0, 0, 0); r.wi = mk3(0, 0, 0); r.pdf = 0; r.w = 0; r.wSum = 0; r.m = 0; r.lightId = 0;   // :330-335
     for (int i = 0; i < LocalCandidates; i++) {   // (1) :452-462
-        f3 wi = sample_hemisphere_cosine(n, rng);
+        f3 wi = sample_hemisphere_cosine(n, B, rng);
         float nl = fmaxf(0.0f, dot(n, wi));
         float pdfLocal = fmaxf(RTX_EPS_MIN, cos_hemisphere_pdf(n, wi));
         float pdfSel = fmaxf(RTX_EPS_MIN, pdfLocal * mixLocal);

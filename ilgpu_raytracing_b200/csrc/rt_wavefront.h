@@ -144,8 +144,9 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
         }
     } else {   // Lambert: ReSTIR-DI + cosine bounce (:277-317)
         f3 wiSel, contrib;
+        const Basis B = orthonormal_basis(v.nrm);
         Reservoir r;
-        restir_new_candidates(fc.env, v.nrm, v.alb, rng, r);
+        restir_new_candidates(fc.env, v.nrm, B, v.alb, rng, r);
         if (restir_finalize(fc.env, v.nrm, v.alb, r, &wiSel, &contrib)) {
             RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
@@ -155,7 +156,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
             shQ.inv[k] = box_idir4(s.d);
             shQ.c[k] = make_float4(c.x, c.y, c.z, 0.0f);
         }
-        f3 wi = sample_hemisphere_cosine(v.nrm, rng);   // :302
+        f3 wi = sample_hemisphere_cosine(v.nrm, B, rng);   // :302
         ray = make_ray_normal_offset(v.pos, v.nrm, wi);
         thr = thr * v.alb;
         if (depth >= 3) {   // :306-312
@@ -206,6 +207,20 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
 }
 
+// A bounce ray that left the scene: "Li += throughput * SkyWeighted(ray.dir); break" (RTRay.cs:242,273,315).  On the device
+// this runs inside the extend kernel as a ray finishes (only rays that hit something go on to the shade kernel, so its
+// warps stay full); the host simulator reaches it through shade_next.
+RT_HD void miss_update(const LightEnv& env, const WaveBuffers& wb, int j, f3 d) {
+    const float4 st = wb.stThr[j];
+    const float4 li4 = wb.stLi[j];
+    const f3 thr = mk3(st.x, st.y, st.z);
+    f3 Li = mk3(li4.x, li4.y, li4.z);
+    const int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
+    Li = Li + thr * sky_weighted(env, d);
+    if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
+    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, RT_TERM_MISS)));
+}
+
 // depth >= 1: consume the closest-hit result of the ray traced at depth-1 (TraceNext, RTRay.cs:659-671) and shade the new vertex.
 RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, int depth,
                       const RayQueue& curQ, const HitRec* hits, int k,
@@ -214,17 +229,12 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
     const int j = (int)f2u(ro.w);
     const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
     const HitRec h = hits[k];
+    if (!(h.t < 1e29f)) { miss_update(fc.env, wb, j, d); return; }
     const float4 st = wb.stThr[j];
     float4 li4 = wb.stLi[j];
     f3 thr = mk3(st.x, st.y, st.z), Li = mk3(li4.x, li4.y, li4.z);
     uint32_t rng = f2u(st.w);
     int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
-    if (!(h.t < 1e29f)) {   // miss: "Li += throughput * SkyWeighted(ray.dir); break" (:242,273,315)
-        Li = Li + thr * sky_weighted(fc.env, d);
-        if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
-        wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, RT_TERM_MISS)));
-        return;
-    }
     if (wb.pathHash || depth < fc.maxDepth) {
         const Surface s = eval_surface(sc, o, d, h);
         if (wb.pathHash) wb.pathHash[j] = fnv_fold(fnv_fold(wb.pathHash[j], (uint32_t)s.instId), (uint32_t)s.primId);

@@ -149,7 +149,10 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         }
         if (active && tr.done) {
             if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
-            else { const HitRec h = tr.result(); __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv)); }
+            else {
+                const HitRec h = tr.result();
+                __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv));
+            }
             active = false;
         }
     }
@@ -170,11 +173,42 @@ __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers 
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount);
 }
 
+// Most bounce rays of an open scene leave it, and shading the few hits in place left ~5 of 32 lanes busy.  So each block
+// takes chunks of RT_SHADE_CHUNK consecutive rays and makes two passes over a chunk: (1) every lane looks at one ray at a
+// time: a miss adds the sky to its path right away (short), a hit is appended to a list in shared memory (ballot + one
+// shared-memory atomic per warp: no global atomics, no extra global traffic); (2) the compacted hits are shaded (long:
+// surface evaluation, nine ReSTIR candidates, bounce) with every lane busy.
+#define RT_SHADE_CHUNK 2048
 __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, const HitRec* hits, const int* curCount,
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
+    __shared__ int list[RT_SHADE_CHUNK];
+    __shared__ int listCount;
     const int n = *curCount;
-    const int stride = gridDim.x * blockDim.x;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) shade_next(fc, sc, wb, depth, curQ, hits, k, nextQ, nextCount, shq, shCount);
+    const int nChunks = (n + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK;
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = (int)(threadIdx.x & 31u);
+    for (int ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
+        if (threadIdx.x == 0) listCount = 0;
+        __syncthreads();
+        const int base = ch * RT_SHADE_CHUNK;
+        for (int i = threadIdx.x; i < RT_SHADE_CHUNK; i += 256) {
+            const int k = base + i;
+            const bool valid = k < n;
+            const bool hit = valid && __ldg(&hits[k].t) < 1e29f;
+            if (valid && !hit) { const float4 ro = curQ.o[k], rd = curQ.d[k]; miss_update(fc.env, wb, (int)f2u(ro.w), mk3(rd.x, rd.y, rd.z)); }
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (m != 0u) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(&listCount, __popc(m));
+                b = __shfl_sync(FULL, b, 0);
+                if (hit) list[b + __popc(m & ((1u << lane) - 1u))] = k;
+            }
+        }
+        __syncthreads();
+        const int nh = listCount;
+        for (int i = threadIdx.x; i < nh; i += 256) shade_next(fc, sc, wb, depth, curQ, hits, list[i], nextQ, nextCount, shq, shCount);
+        __syncthreads();
+    }
 }
 
 __global__ void k_accumulate(FrameConst fc, WaveBuffers wb, int sampleBase, int nSamples, int last) {
@@ -274,6 +308,7 @@ struct rt_ctx {
     // multi-GPU finish: cached owned-pixel lists of every rank
     DevBuf<int> deintMap; std::vector<int64_t> deintStart; int deintW = 0, deintH = 0, deintT = 0, deintWorld = 0;
     int extendBlocks = 0;
+    size_t memTotal = 0;
     size_t l2PersistMax = 0, l2WindowMax = 0, l2Persist = 0, l2Window = 0; cudaStream_t l2WindowStream = nullptr;
     size_t extendSmem = 0;
 };
@@ -340,6 +375,7 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     CUDA_TRY(cudaSetDevice(dev));
     rt_ctx* c = new rt_ctx();
     c->device = dev; c->smCount = prop.multiProcessorCount;
+    c->memTotal = (size_t)prop.totalGlobalMem;
     c->l2PersistMax = (size_t)prop.persistingL2CacheMaxSize; c->l2WindowMax = (size_t)prop.accessPolicyMaxWindowSize;
     CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
     c->stream = c->ownStream;
@@ -487,7 +523,15 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     const int spp = cfg->spp > 1 ? cfg->spp : 1;
     const int64_t npxOwned = count_owned_pixels(cfg->width, cfg->height, cfg->tileSize, cfg->worldSize > 1 ? cfg->rank : 0, cfg->worldSize > 1 ? cfg->worldSize : 1);
     int S = cfg->samplesPerPass;
-    if (S <= 0) { int64_t target = 16ll << 20; if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) target = v; } S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned))); }
+    if (S <= 0) {
+        // samples per wavefront pass: as many paths in flight as ~30 % of the device memory holds (208 B of path state and queue
+        // slots each), capped at 256 Mi.  Bigger passes mean fewer, longer launches: C4 on a 180 GB B200 runs 16-32 spp per
+        // pass and is ~18 % faster than with 16 Mi-path passes (launch tails of the deep, nearly empty wavefronts)
+        int64_t target = std::min<int64_t>(256ll << 20, (int64_t)(c->memTotal / 10 * 3 / 208));
+        target = std::max<int64_t>(target, 1ll << 20);
+        if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) target = v; }
+        S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned)));
+    }
     S = std::min(S, spp);
     if ((int64_t)npxOwned * S > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: samplesPerPass * pixels exceeds 2^31 paths");
     int rc = ensure_frame_buffers(c, cfg, S);
@@ -500,8 +544,9 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     c->launches = 0;
     c->ds.triMaterials = (cfg->flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
 
-    // device counters: [0] primary ray count, then per (pass, depth): nextCount, shCount, workClosest, workShadow; +1 work cursor for primary
-    const size_t nCounters = 2 + (size_t)nPasses * (cfg->maxDepth + 1) * 4;
+    // device counters: [0] primary ray count, [1] its work cursor, then per (pass, depth): nextCount, shCount, workClosest, workShadow
+    const int CS = 4;   // ints per (pass, depth)
+    const size_t nCounters = 2 + (size_t)nPasses * (cfg->maxDepth + 1) * CS;
     CUDA_TRY(c->counters.ensure(nCounters));
     CUDA_TRY(c->dstats.ensure(1));
     cudaStream_t st = c->stream;
@@ -545,13 +590,13 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         for (int pass = 0; pass < nPasses; pass++) {
             const int s0 = pass * S, ns = std::min(S, spp - s0);
             const size_t nPaths = (size_t)npx * ns;
-            int* ctr = c->counters.p + 2 + (size_t)pass * (cfg->maxDepth + 1) * 4;
+            int* ctr = c->counters.p + 2 + (size_t)pass * (cfg->maxDepth + 1) * CS;
             int cur = 0;
             RayQueue nq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
             k_shade_first<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1); c->launches++;
             for (int depth = 1; depth <= cfg->maxDepth; depth++) {
-                int* prev = ctr + (size_t)(depth - 1) * 4;   // counts produced by the shade of depth-1
-                int* mine = ctr + (size_t)depth * 4;
+                int* prev = ctr + (size_t)(depth - 1) * CS;   // counts produced by the shade of depth-1
+                int* mine = ctr + (size_t)depth * CS;
                 RayQueue cq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
                 ExtendArgs sa; memset(&sa, 0, sizeof(sa));
                 sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.rayI = shq.inv; sa.count = prev + 1; sa.work = prev + 3; sa.shq = shq; sa.wb = wb; sa.stats = c->dstats.p; sa.statSlot = 2;
@@ -560,7 +605,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.rayI = cq.inv; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
                 CUDA_TRY(launch_extend<false>(c, ca, count));
                 RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p, c->qI[cur ^ 1].p};
-                k_shade_next<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1); c->launches++;
+                k_shade_next<<<grid_for(c, (nPaths + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK, 1), 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1); c->launches++;
                 cur ^= 1;
             }
             k_accumulate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
