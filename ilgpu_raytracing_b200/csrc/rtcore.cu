@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { HitRec h; h.t = 1e30f; h.prim = -1; h.bu = 0.0f; h.bv = 0.0f; a.hits[i] = h; }
         } else {
             const int stride = gridDim.x * blockDim.x;
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) connect_shadow(a.wb, a.shq, i, false);
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a.shq.c[i].w = 1.0f;   // nothing can occlude
         }
         return;
     }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
             }
         }
         if (active && tr.done) {
-            if (ANY_HIT) connect_shadow(a.wb, a.shq, myRay, tr.occluded);
+            if (ANY_HIT) __stcs(&a.shq.c[myRay].w, tr.occluded ? 0.0f : 1.0f);   // visibility of the pending contribution; k_connect adds it to the path
             else {
                 const HitRec h = tr.result();
                 __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv));
@@ -209,6 +209,15 @@ __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene s
         for (int i = threadIdx.x; i < nh; i += 256) shade_next(fc, sc, wb, depth, curQ, hits, list[i], nextQ, nextCount, shq, shCount);
         __syncthreads();
     }
+}
+
+// connect: add the pending direct-light term of every unoccluded shadow ray to its path (RTRay.cs:526-537, 286/291).
+// A dense, high-occupancy pass over the shadow queue; the read-modify-write of the path state would otherwise sit at the end
+// of each ray inside the persistent any-hit kernel, where the whole warp waits on it.
+__global__ void __launch_bounds__(256) k_connect(WaveBuffers wb, ShadowQueue shq, const int* count) {
+    const int n = *count;
+    const int stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) connect_shadow(wb, shq, k, !(__ldcs(&shq.c[k].w) != 0.0f));
 }
 
 __global__ void k_accumulate(FrameConst fc, WaveBuffers wb, int sampleBase, int nSamples, int last) {
@@ -601,6 +610,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 ExtendArgs sa; memset(&sa, 0, sizeof(sa));
                 sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.rayI = shq.inv; sa.count = prev + 1; sa.work = prev + 3; sa.shq = shq; sa.wb = wb; sa.stats = c->dstats.p; sa.statSlot = 2;
                 CUDA_TRY(launch_extend<true>(c, sa, count));
+                k_connect<<<grid_for(c, nPaths, 256), 256, 0, st>>>(wb, shq, prev + 1); c->launches++;
                 ExtendArgs ca; memset(&ca, 0, sizeof(ca));
                 ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.rayI = cq.inv; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
                 CUDA_TRY(launch_extend<false>(c, ca, count));
