@@ -197,7 +197,7 @@ def main():
     rdr.Commit()
     t_commit = time.perf_counter() - t0
     rdr.camera = engine.config_camera(wl["cam"], W, H)
-    rdr.configure(renderScale=1.0, spp=spp, maxDepth=depth, rngLockNoise=1, fixedSeed=1, flags=0, tileSize=tile, rank=rank, worldSize=world)
+    rdr.configure(renderScale=1.0, enableTemporalReuse=0, enableSpatialReuse=0, spp=spp, maxDepth=depth, rngLockNoise=1, fixedSeed=1, flags=0, tileSize=tile, rank=rank, worldSize=world)
     ctx = rdr.native
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)

@@ -22,13 +22,14 @@ namespace ILGPU_Raytracing.Engine
     [Flags]
     public enum RtFlags : uint
     {
-        None = 0, TriMaterials = 1u << 0, Accumulate = 1u << 1, ResetAccum = 1u << 2, PathAovs = 1u << 3, Counters = 1u << 4, KernelTiming = 1u << 5
+        None = 0, TriMaterials = 1u << 0, Accumulate = 1u << 1, ResetAccum = 1u << 2, PathAovs = 1u << 3, Counters = 1u << 4, KernelTiming = 1u << 5,
+        ResetReservoirs = 1u << 6
     }
 
     public enum RtBuffer
     {
         Rgba8 = 0, Depth = 1, ObjId = 2, Radiance = 3, Accum = 4, PrimId = 5, InstId = 6, PrimaryT = 7, SegCount = 8, TermCode = 9, PathHash = 10,
-        GbWorldPos = 11, GbNormal = 12, GbBaseColor = 13, GbMatId = 14, TileRadiance = 15
+        GbWorldPos = 11, GbNormal = 12, GbBaseColor = 13, GbMatId = 14, TileRadiance = 15, Reservoir = 16   // Reservoir: Engine/RTRay.cs:171-179 records
     }
 
     [StructLayout(LayoutKind.Sequential)]

@@ -145,7 +145,7 @@ public:
 
     // the reference's private knobs (RTRenderer.cs:43-49,204), made settable: benchmark configs fix them
     float RenderScale = 1.0f;      // reference default 0.67 relies on the TAAU upsampler (out of scope); 1.0 = trace at output size
-    int EnableTemporalReuse = 0, EnableSpatialReuse = 0;   // reference default 1/1; reuse is not built yet (rt_render refuses it)
+    int EnableTemporalReuse = 1, EnableSpatialReuse = 1;   // RTRenderer.cs:46-47 (benchmarks switch both off)
     int RngLockNoise = 1;          // reference: 0 -> seed 0, nonzero -> Random.Shared.Next() per frame (:166)
     int FixedSeed = 1;             // used instead of Random.Shared.Next() when RngLockNoise != 0 (deterministic runs)
     int Spp = 2;                   // :49

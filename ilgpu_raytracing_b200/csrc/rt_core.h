@@ -118,6 +118,7 @@ RT_HD void sincos_pi2(float x, float* s, float* c) {
     if (x < 0.0f) ss = -ss;
     *s = ss; *c = cc;
 }
+RT_HD float tan_p(float x) { float s, c; sincos_pi2(x, &s, &c); return s / c; }   // XMath.Tan stand-in (RTRay.cs:349)
 RT_HD float atan_pos(float a) {
     float y0;
     if (a > 2.414213562373095f) { y0 = 1.5707963267948966f; a = -(1.0f / a); }
@@ -171,6 +172,7 @@ RT_HD uint32_t pcg_permute(uint32_t x) { x ^= x >> 16; x *= 0x7FEB352Du; x ^= x 
 RT_HD uint32_t hash32(uint32_t x) {   // :77-84 (same mixer as RTRay.cs:637-641)
     x ^= x >> 17; x *= 0xED5AD4BBu; x ^= x >> 11; x *= 0xAC4C1B51u; x ^= x >> 15; x *= 0x31848BABu; x ^= x >> 14; return x;
 }
+RT_HD uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) { return hash32(a ^ hash32(b ^ hash32(c))); }   // RTRay.cs:643
 RT_HD uint32_t rng_seed_pixel(uint32_t px, uint32_t py, int frame, uint32_t sample, uint32_t salt, int lockNoise) {   // :116-137 + :87-97
     uint32_t f = (lockNoise != 0) ? 0u : (uint32_t)frame;
     uint32_t ln = (uint32_t)lockNoise;

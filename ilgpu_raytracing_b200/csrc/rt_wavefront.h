@@ -22,6 +22,11 @@ struct FrameConst {
     LightEnv env;
     int npx;                 // pixels owned by this context (whole image or its screen tiles)
     const int* pixelMap;     // owned index -> global pixel index y*width+x (8x4 micro-tile order for ray coherence)
+    // ReSTIR reuse of the previous frame's reservoirs (RTRay.cs:475-516); everything below is unused when both flags are 0
+    int enableTemporal, enableSpatial;
+    f3 prevOrigin, prevRight, prevUp, prevForward; float prevFovY, prevAspect;   // the prevCam fields ReprojectToPrevPixel reads (:342-351)
+    const int* invPixelMap;                       // global pixel index -> owned index (G-buffer lookups at other pixels, :365-372)
+    const float4 *resPrev0, *resPrev1, *resPrev2; // previous frame's reservoirs per global pixel: L|pdf, wi|w, wSum|m|lightId
 };
 
 struct WaveBuffers {
@@ -36,6 +41,10 @@ struct WaveBuffers {
     float4* stThr;    // throughput.xyz | rng state
     float4* stLi;     // Li.xyz | segCount (bits 0-7), terminator (bits 8-15)
     uint32_t* pathHash;
+    // reservoirs (null unless a reuse flag is set): per path slot, the reservoir of the path's first Lambert vertex ("outRes",
+    // RTRay.cs:289-296), and per global pixel the frame's resCur, which accumulate() fills from the LAST sample that wrote one
+    float4 *resPath0, *resPath1, *resPath2;
+    float4 *resCur0, *resCur1, *resCur2;
     // parity AOVs per (sample, global pixel); null unless RT_FLAG_PATH_AOVS
     uint8_t *segCountOut, *termCodeOut; uint32_t* pathHashOut;
 };
@@ -114,10 +123,90 @@ RT_HD void primary_finish(const FrameConst& fc, const DeviceScene& sc, const Wav
 // ------------------------------------------------------------------------------------------------ shade
 struct PathVertex { f3 pos, nrm, alb, I; int shade; float ior; };
 
+// path flags kept in stLi.w above the parity taps (bits 0-7 segment count, 8-15 terminator)
+enum : uint32_t { PATH_WROTE_RESERVOIR = 1u << 16 };
+
+// ReprojectToPrevPixel (RTRay.cs:339-360)
+RT_HD int reproject_to_prev_pixel(const FrameConst& fc, f3 posWS) {
+    f3 p = posWS - fc.prevOrigin;
+    float x = dot(p, fc.prevRight), y = dot(p, fc.prevUp), z = dot(p, fc.prevForward);
+    if (z <= 1e-4f) return -1;
+    float tanHalfFov = tan_p(0.5f * fc.prevFovY);
+    float ndcX = x / (z * tanHalfFov * fc.prevAspect);
+    float ndcY = y / (z * tanHalfFov);
+    float fx = 0.5f * (ndcX + 1.0f) * (float)fc.width;
+    float fy = 0.5f * (ndcY + 1.0f) * (float)fc.height;
+    int px = (int)fx, py = (int)fy;
+    if ((uint32_t)px >= (uint32_t)fc.width || (uint32_t)py >= (uint32_t)fc.height) return -1;
+    return py * fc.width + px;
+}
+RT_HD float distance_from_camera(const FrameConst& fc, float4 pos) {   // IntegratorParams.DistanceFromCamera RTRay.cs:158-162
+    const f3 d = mk3(pos.x, pos.y, pos.z) - fc.camOrigin;
+    return sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+}
+// SpatialCompatible (RTRay.cs:363-374): compares the CURRENT frame's G-buffer at the two pixel indices; iA / iB are owned indices
+RT_HD bool spatial_compatible(const FrameConst& fc, const WaveBuffers& wb, int iA, int iB, f3 nA) {
+    const int objA = (int)f2u(wb.gbAlbObj[iA].w), objB = (int)f2u(wb.gbAlbObj[iB].w);
+    if (objA == objB) return true;
+    const float4 nb4 = wb.gbNrmMat[iB];
+    const f3 nB = normalize(mk3(nb4.x, nb4.y, nb4.z));
+    const float ndot = dot(nA, nB);
+    if (ndot < 0.85f) return false;
+    const float zA = distance_from_camera(fc, wb.gbPosHit[iA]);
+    const float zB = distance_from_camera(fc, wb.gbPosHit[iB]);
+    const float rel = fabsf(zA - zB) / fmaxf(1e-3f, zA);
+    return rel < 0.05f;
+}
+// ImportFromPrevReservoir (RTRay.cs:408-435); curOwned = owned index of the path's pixel, prevIdx = global pixel index
+RT_HD void import_from_prev_reservoir(const FrameConst& fc, const WaveBuffers& wb, int prevIdx, int curOwned, f3 n, f3 albedo, uint32_t& rng, Reservoir& r) {
+    if (prevIdx < 0 || fc.width * fc.height <= prevIdx) return;
+    if (!spatial_compatible(fc, wb, curOwned, fc.invPixelMap[prevIdx], n)) return;
+    const float4 p1 = fc.resPrev1[prevIdx], p2 = fc.resPrev2[prevIdx];   // (plane 0 = L | pdf is not read by the import)
+    const int prM = (int)f2u(p2.y), prLight = (int)f2u(p2.z);
+    const float prW = p1.w, prWSum = p2.x;
+    if (!(prM > 0 && prW > 0.0f && prWSum > 0.0f)) return;
+    const f3 wi = mk3(p1.x, p1.y, p1.z);
+    const int lid = prLight == 2 ? 2 : 1;
+    const f3 LiImp = (lid == 2) ? fc.env.dirLightRadiance : sky_weighted(fc.env, wi);
+    const float nl = fmaxf(0.0f, dot(n, wi));
+    const float pdfHere = (lid == 2) ? fmaxf(RTX_EPS_MIN, RTX_MIX_DELTA) : fmaxf(RTX_EPS_MIN, cos_hemisphere_pdf(n, wi) * RTX_MIX_LOCAL);
+    const f3 f_over_p = albedo * LiImp * ((nl / pdfHere) * RTX_INV_PI);
+    const float sHere = luminance(f_over_p);
+    const float Wsrc = prWSum / ((float)max(1, prM) * fmaxf(RTX_EPS_MIN, prW));
+    const float eff = sHere * Wsrc;
+    reservoir_update(r, wi, pdfHere, LiImp, eff, 1, lid, rng);
+}
+// steps (3) and (4) of ReSTIR_Direct (RTRay.cs:475-516): temporal import through reprojection, then the 8 rotated neighbours of
+// the PREVIOUS frame.  "index" is the path's global pixel index.
+RT_HD void restir_imports(const FrameConst& fc, const WaveBuffers& wb, int path, f3 pos, f3 n, f3 albedo, uint32_t& rng, Reservoir& r) {
+    const int curOwned = path % fc.npx;
+    const int index = fc.pixelMap[curOwned];
+    if (fc.enableTemporal != 0) {
+        const int prevIdx = reproject_to_prev_pixel(fc, pos);
+        if (prevIdx >= 0) import_from_prev_reservoir(fc, wb, prevIdx, curOwned, n, albedo, rng, r);
+    }
+    if (fc.enableSpatial != 0) {
+        const uint32_t h = hash3((uint32_t)index, (uint32_t)fc.frame, 0xB31F5AB1u);
+        const int rot = (int)(h & 3u);
+        const int rad = 1 + (int)((h >> 2) & 1u);
+        const int x0 = index % fc.width, y0 = index / fc.width;
+        for (int i = 0; i < 8; i++) {   // Neighbor8 (:377-391): (-r,0) (r,0) (0,-r) (0,r) (-r,-r) (r,-r) (-r,r) (r,r), rotated by rot quarter turns
+            const int sx = (i == 0 || i == 4 || i == 6) ? -rad : ((i == 2 || i == 3) ? 0 : rad);
+            const int sy = (i < 2) ? 0 : ((i == 2 || i == 4 || i == 5) ? -rad : rad);
+            const int dx = rot == 0 ? sx : (rot == 1 ? -sy : (rot == 2 ? -sx : sy));
+            const int dy = rot == 0 ? sy : (rot == 1 ? sx : (rot == 2 ? -sy : -sx));
+            const int ni = ((uint32_t)(x0 + dx) < (uint32_t)fc.width && (uint32_t)(y0 + dy) < (uint32_t)fc.height) ? (y0 + dy) * fc.width + (x0 + dx) : -1;
+            import_from_prev_reservoir(fc, wb, ni, curOwned, n, albedo, rng, r);
+        }
+    }
+}
+
 // One iteration of the depth loop of PathTraceKernel up to (not including) TraceNext (RTRay.cs:233-317).
 // Pushes the continuation ray and, for a Lambert vertex, the ReSTIR-selected shadow ray.
 // Returns false when Russian roulette killed the path.
-RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, int path, f3& thr, uint32_t& rng,
+// REUSE = a reuse flag is set (compile-time, so the common path does not carry the import code's registers)
+template <bool REUSE>
+RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathVertex& v, int depth, int path, f3& thr, uint32_t& rng, uint32_t& pflags,
                         const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
     RayOD ray;
     if (v.shade == RT_SHADING_MIRROR) {   // :235-244
@@ -147,6 +236,15 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
         const Basis B = orthonormal_basis(v.nrm);
         Reservoir r;
         restir_new_candidates(fc.env, v.nrm, B, v.alb, rng, r);
+        // only the FIRST Lambert vertex of a sample imports from the previous frame and publishes its reservoir ("wroteReservoir", :280-297)
+        const bool first = (pflags & PATH_WROTE_RESERVOIR) == 0u;
+        if (REUSE && first) restir_imports(fc, wb, path, v.pos, v.nrm, v.alb, rng, r);
+        if (REUSE && first && wb.resPath0) {
+            wb.resPath0[path] = make_float4(r.L.x, r.L.y, r.L.z, r.pdf);
+            wb.resPath1[path] = make_float4(r.wi.x, r.wi.y, r.wi.z, r.w);
+            wb.resPath2[path] = make_float4(r.wSum, u2f((uint32_t)r.m), u2f((uint32_t)r.lightId), 0.0f);
+            pflags |= PATH_WROTE_RESERVOIR;
+        }
         if (restir_finalize(fc.env, v.nrm, v.alb, r, &wiSel, &contrib)) {
             RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
@@ -176,6 +274,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const PathVertex& v, int depth, in
 RT_HD uint32_t pack_aov(int seg, int term) { return (uint32_t)(seg & 0xFF) | ((uint32_t)(term & 0xFF) << 8); }
 
 // depth 0: start every path of the batch from the G-buffer (RTRay.cs:210-232)
+template <bool REUSE = false>
 RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBase, int j,
                        const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
     const int i = j % fc.npx;
@@ -202,9 +301,10 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     v.shade = packedMat & 0xFFFF;                      // :225
     v.ior = i16_to_float((packedMat >> 16) & 0xFFFF);  // :226
     v.I = normalize(v.pos - fc.camOrigin);             // ViewDirFromCam :156,230
-    bool alive = shade_vertex(fc, v, 0, j, thr, rng, nextQ, nextCount, shQ, shCount);
+    uint32_t pflags = 0u;
+    bool alive = shade_vertex<REUSE>(fc, wb, v, 0, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount);
     wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
-    wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+    wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pflags | pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
 }
 
 // A bounce ray that left the scene: "Li += throughput * SkyWeighted(ray.dir); break" (RTRay.cs:242,273,315).  On the device
@@ -218,10 +318,11 @@ RT_HD void miss_update(const LightEnv& env, const WaveBuffers& wb, int j, f3 d) 
     const int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
     Li = Li + thr * sky_weighted(env, d);
     if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
-    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, RT_TERM_MISS)));
+    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f((f2u(li4.w) & 0xFFFF0000u) | pack_aov(seg, RT_TERM_MISS)));
 }
 
 // depth >= 1: consume the closest-hit result of the ray traced at depth-1 (TraceNext, RTRay.cs:659-671) and shade the new vertex.
+template <bool REUSE = false>
 RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, int depth,
                       const RayQueue& curQ, const HitRec* hits, int k,
                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
@@ -235,6 +336,7 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
     f3 thr = mk3(st.x, st.y, st.z), Li = mk3(li4.x, li4.y, li4.z);
     uint32_t rng = f2u(st.w);
     int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
+    uint32_t pflags = f2u(li4.w) & 0xFFFF0000u;
     if (wb.pathHash || depth < fc.maxDepth) {
         const Surface s = eval_surface(sc, o, d, h);
         if (wb.pathHash) wb.pathHash[j] = fnv_fold(fnv_fold(wb.pathHash[j], (uint32_t)s.instId), (uint32_t)s.primId);
@@ -244,14 +346,14 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
             v.nrm = normalize(s.normal);   // :666
             v.alb = s.albedo; v.shade = s.shade; v.ior = s.ior;
             v.I = d;                        // "I = ray.dir" :243,274,316
-            bool alive = shade_vertex(fc, v, depth, j, thr, rng, nextQ, nextCount, shQ, shCount);
+            bool alive = shade_vertex<REUSE>(fc, wb, v, depth, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount);
             wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
-            wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+            wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
             return;
         }
     }
     // depth == maxDepth: the depth loop has run out (:233); nothing more is added
-    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pack_aov(seg, RT_TERM_MAXDEPTH)));
+    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, RT_TERM_MAXDEPTH)));
 }
 
 // connect: add the pending direct-light term of an unoccluded shadow ray (RTRay.cs:526-537, 286/291)
@@ -276,9 +378,11 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
     const bool primaryMiss = f2u(wb.gbPosHit[i].w) == 0u;
     if (primaryMiss) { int x, y; pixel_xy(fc, pix, &x, &y); skyMiss = safe_color(sky_weighted(fc.env, primary_dir(fc, x, y))); }   // :216-217
     const size_t plane = (size_t)fc.width * (size_t)fc.height;
+    int resOwner = -1;   // the reference's samples run in order and each overwrites resCur[index] (:294): the last writer's reservoir stays
     for (int s = 0; s < nSamples; s++) {
         const int j = s * fc.npx + i;
         const float4 li4 = wb.stLi[j];
+        if (f2u(li4.w) & PATH_WROTE_RESERVOIR) resOwner = j;
         L = L + (primaryMiss ? skyMiss : safe_color(mk3(li4.x, li4.y, li4.z)));
         if (wb.segCountOut) {
             const uint32_t a = f2u(li4.w);
@@ -288,6 +392,7 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
             wb.pathHashOut[oi] = wb.pathHash[j];
         }
     }
+    if (wb.resCur0 && resOwner >= 0) { wb.resCur0[pix] = wb.resPath0[resOwner]; wb.resCur1[pix] = wb.resPath1[resOwner]; wb.resCur2[pix] = wb.resPath2[resOwner]; }
     if (!last) { wb.lframe[i] = make_float4(L.x, L.y, L.z, 0.0f); return; }
     const f3 Lout = L * (1.0f / (float)max(1, fc.spp));   // :323
     wb.radiance[pix] = make_float4(Lout.x, Lout.y, Lout.z, 1.0f);

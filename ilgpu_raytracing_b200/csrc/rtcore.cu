@@ -168,9 +168,10 @@ __global__ void k_primary_finish(FrameConst fc, DeviceScene sc, WaveBuffers wb, 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) primary_finish(fc, sc, wb, q, hits, i);
 }
 
+template <bool REUSE>
 __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
     const int stride = gridDim.x * blockDim.x;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first<REUSE>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount);
 }
 
 // Most bounce rays of an open scene leave it, and shading the few hits in place left ~5 of 32 lanes busy.  So each block
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers 
 // shared-memory atomic per warp: no global atomics, no extra global traffic); (2) the compacted hits are shaded (long:
 // surface evaluation, nine ReSTIR candidates, bounce) with every lane busy.
 #define RT_SHADE_CHUNK 2048
+template <bool REUSE>
 __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, const HitRec* hits, const int* curCount,
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
     __shared__ int list[RT_SHADE_CHUNK];
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene s
         }
         __syncthreads();
         const int nh = listCount;
-        for (int i = threadIdx.x; i < nh; i += 256) shade_next(fc, sc, wb, depth, curQ, hits, list[i], nextQ, nextCount, shq, shCount);
+        for (int i = threadIdx.x; i < nh; i += 256) shade_next<REUSE>(fc, sc, wb, depth, curQ, hits, list[i], nextQ, nextCount, shq, shCount);
         __syncthreads();
     }
 }
@@ -242,6 +244,16 @@ __global__ void k_scatter_f4_to_f3(const float4* src, float* dst, const int* pix
 __global__ void k_scatter_f4_w(const float4* src, int* dst, const int* pixelMap, int npx) {
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) dst[pixelMap[i]] = __float_as_int(src[i].w);
+}
+
+// reservoir planes (L|pdf, wi|w, wSum|m|lightId) -> the reference's 44-byte Reservoir records (read-back for parity)
+__global__ void k_pack_reservoirs(const float4* res, int g, float* out) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < g; p += stride) {
+        const float4 a = res[p], b = res[(size_t)g + p], c = res[2 * (size_t)g + p];
+        float* o = out + (size_t)p * 11;
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = b.x; o[4] = b.y; o[5] = b.z; o[6] = a.w; o[7] = b.w; o[8] = c.x; o[9] = c.y; o[10] = c.z;
+    }
 }
 
 // multi-GPU finish: payload[k] (float4 Lout of the k-th owned pixel of some rank) -> full image
@@ -296,7 +308,9 @@ struct rt_ctx {
     // frame geometry
     int width = 0, height = 0, tileSize = 0, rank = 0, worldSize = 1, npx = 0, spp = 1;
     bool aovs = false;
-    DevBuf<int> pixelMap;
+    DevBuf<int> pixelMap, invPixelMap;
+    // ReSTIR reservoirs: A/B per global pixel (3 float4 planes each, zero-initialised: frame 0 imports nothing), per-path staging
+    DevBuf<float4> resAB[2]; DevBuf<float4> resPath; size_t resPathCap = 0; int resLastWritten = -1;
     // per owned pixel
     DevBuf<float4> gbPosHit, gbNrmMat, gbAlbObj, lframe, tileRadiance; DevBuf<int> primId, instId; DevBuf<float> primaryT;
     // per global pixel
@@ -401,7 +415,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
-    c->materials.release(); c->texels.release(); c->texInfos.release(); c->pixelMap.release();
+    c->materials.release(); c->texels.release(); c->texInfos.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
     c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); c->qI[b].release(); } c->shO.release(); c->shD.release(); c->shI.release(); c->shC.release();
@@ -493,6 +507,7 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
         if (!pm.empty()) CUDA_TRY(cudaMemcpyAsync(c->pixelMap.p, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->width = W; c->height = H; c->tileSize = T; c->rank = rank; c->worldSize = world; c->npx = (int)pm.size();
+        c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resLastWritten = -1;   // reservoirs belong to one image size (Framebuffer.EnsureLength, Framebuffer.cs:60-83)
         const size_t n = std::max<size_t>(1, (size_t)c->npx), g = (size_t)W * H;
         CUDA_TRY(c->gbPosHit.ensure(n)); CUDA_TRY(c->gbNrmMat.ensure(n)); CUDA_TRY(c->gbAlbObj.ensure(n)); CUDA_TRY(c->lframe.ensure(n)); CUDA_TRY(c->tileRadiance.ensure(n));
         CUDA_TRY(c->primId.ensure(n)); CUDA_TRY(c->instId.ensure(n)); CUDA_TRY(c->primaryT.ensure(n));
@@ -519,14 +534,16 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
 }
 
 RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, const RtRenderConfig* cfg) {
-    (void)prevCam;
     if (!c || !cam || !cfg) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: null argument");
     if (!c->hasScene) return fail(RT_ERR_INVALID_STATE, "rt_render: no scene uploaded (call rt_scene_upload first)");
     if (cfg->width <= 0 || cfg->height <= 0 || (int64_t)cfg->width * cfg->height > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: bad image size");
     if (cfg->maxDepth < 0 || cfg->maxDepth > 255) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: maxDepth must be in [0, 255]");
     if (cfg->worldSize > 1 && (cfg->rank < 0 || cfg->rank >= cfg->worldSize)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: rank outside [0, worldSize)");
-    if (cfg->enableTemporalReuse || cfg->enableSpatialReuse)
-        return fail(RT_ERR_UNSUPPORTED, "rt_render: ReSTIR temporal/spatial reuse (RTRay.cs:476-516) is not built yet; pass enableTemporalReuse = enableSpatialReuse = 0");
+    const bool reuse = cfg->enableTemporalReuse != 0 || cfg->enableSpatialReuse != 0;
+    if (reuse && cfg->worldSize > 1)
+        return fail(RT_ERR_UNSUPPORTED, "rt_render: ReSTIR temporal/spatial reuse reads the previous frame's reservoirs of neighbouring and reprojected pixels, "
+                                        "which a screen-tile partition does not hold; render reuse frames with worldSize = 1");
+    if (cfg->enableTemporalReuse != 0 && !prevCam) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: enableTemporalReuse needs prevCam");
     CUDA_TRY(cudaSetDevice(c->device));
 
     const int spp = cfg->spp > 1 ? cfg->spp : 1;
@@ -547,6 +564,19 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     if (rc != RT_OK) return rc;
     const int npx = c->npx;
     const int nPasses = (spp + S - 1) / S;
+    if (reuse) {
+        const size_t g = (size_t)cfg->width * cfg->height;
+        if (!c->invPixelMap.p) {
+            std::vector<int> pm, inv(g, 0); build_pixel_map(cfg->width, cfg->height, c->tileSize, 0, 1, pm);
+            for (size_t i = 0; i < pm.size(); i++) inv[(size_t)pm[i]] = (int)i;
+            CUDA_TRY(c->invPixelMap.ensure(g));
+            CUDA_TRY(cudaMemcpyAsync(c->invPixelMap.p, inv.data(), g * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        for (int b = 0; b < 2; b++) if (!c->resAB[b].p || (cfg->flags & RT_FLAG_RESET_RESERVOIRS)) { CUDA_TRY(c->resAB[b].ensure(3 * g)); CUDA_TRY(cudaMemsetAsync(c->resAB[b].p, 0, 3 * g * sizeof(float4), c->stream)); }
+        const size_t P = std::max<size_t>(1, (size_t)npx * S);
+        if (P > c->resPathCap) { CUDA_TRY(c->resPath.ensure(3 * P)); c->resPathCap = P; }
+    }
     const bool count = (cfg->flags & RT_FLAG_COUNTERS) != 0;
     c->timeKernels = (cfg->flags & RT_FLAG_KERNEL_TIMING) != 0;   // per-launch event pairs around the extend kernels (roofline measurements)
     c->traceEventsUsed = 0;
@@ -576,11 +606,27 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     fc.camOrigin = mk3(cam->origin); fc.camLowerLeft = mk3(cam->lowerLeft); fc.camHorizontal = mk3(cam->horizontal); fc.camVertical = mk3(cam->vertical);
     fc.env.dirLightDir = mk3(cfg->dirLightDir); fc.env.dirLightRadiance = mk3(cfg->dirLightRadiance); fc.env.skyTop = mk3(cfg->skyTintTop); fc.env.skyBottom = mk3(cfg->skyTintBottom);
     fc.npx = npx; fc.pixelMap = c->pixelMap.p;
+    if (reuse) {
+        const size_t g = (size_t)cfg->width * cfg->height;
+        const RtCamera* pc = prevCam ? prevCam : cam;
+        fc.enableTemporal = cfg->enableTemporalReuse; fc.enableSpatial = cfg->enableSpatialReuse;
+        fc.prevOrigin = mk3(pc->origin); fc.prevRight = mk3(pc->right); fc.prevUp = mk3(pc->up); fc.prevForward = mk3(pc->forward); fc.prevFovY = pc->fovYRadians; fc.prevAspect = pc->aspect;
+        fc.invPixelMap = c->invPixelMap.p;
+        const float4* prev = c->resAB[(cfg->frame & 1) ^ 1].p;   // GetReservoirPair (Framebuffer.cs:127-146): even frame: prev = B, cur = A
+        fc.resPrev0 = prev; fc.resPrev1 = prev + g; fc.resPrev2 = prev + 2 * g;
+    }
 
     WaveBuffers wb; memset(&wb, 0, sizeof(wb));
     wb.gbPosHit = c->gbPosHit.p; wb.gbNrmMat = c->gbNrmMat.p; wb.gbAlbObj = c->gbAlbObj.p; wb.primId = c->primId.p; wb.instId = c->instId.p; wb.primaryT = c->primaryT.p;
     wb.lframe = c->lframe.p; wb.tileRadiance = c->tileRadiance.p; wb.rgba8 = c->rgba8.p; wb.depth = c->depth.p; wb.objId = c->objId.p; wb.radiance = c->radiance.p; wb.accum = c->accum.p;
     wb.stThr = c->stThr.p; wb.stLi = c->stLi.p;
+    if (reuse) {
+        const size_t g = (size_t)cfg->width * cfg->height, P = c->resPathCap;
+        float4* cur = c->resAB[cfg->frame & 1].p;
+        wb.resCur0 = cur; wb.resCur1 = cur + g; wb.resCur2 = cur + 2 * g;
+        wb.resPath0 = c->resPath.p; wb.resPath1 = c->resPath.p + P; wb.resPath2 = c->resPath.p + 2 * P;
+        c->resLastWritten = cfg->frame & 1;
+    }
     if (c->aovs) { wb.pathHash = c->pathHash.p; wb.segCountOut = c->segOut.p; wb.termCodeOut = c->termOut.p; wb.pathHashOut = c->hashOut.p; }
 
     if (npx > 0) {
@@ -602,7 +648,9 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             int* ctr = c->counters.p + 2 + (size_t)pass * (cfg->maxDepth + 1) * CS;
             int cur = 0;
             RayQueue nq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
-            k_shade_first<<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1); c->launches++;
+            if (reuse) k_shade_first<true><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1);
+            else k_shade_first<false><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1);
+            c->launches++;
             for (int depth = 1; depth <= cfg->maxDepth; depth++) {
                 int* prev = ctr + (size_t)(depth - 1) * CS;   // counts produced by the shade of depth-1
                 int* mine = ctr + (size_t)depth * CS;
@@ -615,7 +663,10 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.rayI = cq.inv; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
                 CUDA_TRY(launch_extend<false>(c, ca, count));
                 RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p, c->qI[cur ^ 1].p};
-                k_shade_next<<<grid_for(c, (nPaths + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK, 1), 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1); c->launches++;
+                const int shadeGrid = grid_for(c, (nPaths + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK, 1);
+                if (reuse) k_shade_next<true><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1);
+                else k_shade_next<false><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1);
+                c->launches++;
                 cur ^= 1;
             }
             k_accumulate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
@@ -649,6 +700,7 @@ static int buffer_info(rt_ctx* c, int which, size_t* bytes) {
         case RT_BUF_SEG_COUNT: case RT_BUF_TERM_CODE: *bytes = g * c->spp; return RT_OK;
         case RT_BUF_PATH_HASH: *bytes = g * c->spp * 4; return RT_OK;
         case RT_BUF_TILE_RADIANCE: *bytes = (size_t)c->npx * 16; return RT_OK;
+        case RT_BUF_RESERVOIR: *bytes = g * sizeof(RtReservoir); return RT_OK;
     }
     return fail(RT_ERR_INVALID_ARGUMENT, "unknown buffer selector");
 }
@@ -707,6 +759,11 @@ RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
             if (!c->aovs) return fail(RT_ERR_INVALID_STATE, "rt_download: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
             src = which == RT_BUF_SEG_COUNT ? (const void*)c->segOut.p : (which == RT_BUF_TERM_CODE ? (const void*)c->termOut.p : (const void*)c->hashOut.p);
             break;
+        case RT_BUF_RESERVOIR:
+            if (c->resLastWritten < 0) return fail(RT_ERR_INVALID_STATE, "rt_download: no frame with a reuse flag set has written reservoirs yet");
+            CUDA_TRY(scatterPrep(g * 11));
+            k_pack_reservoirs<<<grid_for(c, g, 256), 256, 0, st>>>(c->resAB[c->resLastWritten].p, (int)g, c->scratch.p);
+            src = c->scratch.p; break;
         case RT_BUF_PRIM_ID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<int><<<grid_for(c, npx, 256), 256, 0, st>>>(c->primId.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
         case RT_BUF_INST_ID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<int><<<grid_for(c, npx, 256), 256, 0, st>>>(c->instId.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
         case RT_BUF_PRIMARY_T: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<float><<<grid_for(c, npx, 256), 256, 0, st>>>(c->primaryT.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
@@ -792,4 +849,5 @@ static_assert(sizeof(RtFloat3) == 12 && sizeof(RtFloat2) == 8 && sizeof(RtAffine
 static_assert(sizeof(RtBvhNode) == 44 && sizeof(RtInstanceRecord) == 144 && sizeof(RtMaterialRecord) == 44 && sizeof(RtSphere) == 80, "ABI layout");
 static_assert(sizeof(RtMeshTri) == 12 && sizeof(RtMeshTriUV) == 12 && sizeof(RtRGBA32) == 4 && sizeof(RtTexInfo) == 12 && sizeof(RtCamera) == 92, "ABI layout");
 static_assert(sizeof(RtSceneDesc) == 15 * 16 && sizeof(RtRenderConfig) == 32 + 48 + 4 + 12 + 4 + 12, "ABI layout");
+static_assert(sizeof(RtReservoir) == 44, "ABI layout");
 static_assert(sizeof(WideNode) == 80 && sizeof(PrimRec) == 48 && sizeof(HitRec) == 16, "device layout");

@@ -43,10 +43,13 @@ RT_FLAG_RESET_ACCUM = 1 << 2
 RT_FLAG_PATH_AOVS = 1 << 3
 RT_FLAG_COUNTERS = 1 << 4
 RT_FLAG_KERNEL_TIMING = 1 << 5
+RT_FLAG_RESET_RESERVOIRS = 1 << 6
 
 (RT_BUF_RGBA8, RT_BUF_DEPTH, RT_BUF_OBJID, RT_BUF_RADIANCE, RT_BUF_ACCUM, RT_BUF_PRIM_ID, RT_BUF_INST_ID, RT_BUF_PRIMARY_T,
  RT_BUF_SEG_COUNT, RT_BUF_TERM_CODE, RT_BUF_PATH_HASH, RT_BUF_GB_WORLDPOS, RT_BUF_GB_NORMAL, RT_BUF_GB_BASECOLOR, RT_BUF_GB_MATID,
- RT_BUF_TILE_RADIANCE) = range(16)
+ RT_BUF_TILE_RADIANCE, RT_BUF_RESERVOIR) = range(17)
+# Reservoir (Engine/RTRay.cs:171-179), the element of RT_BUF_RESERVOIR
+RESERVOIR = np.dtype([("L", F3), ("wi", F3), ("pdf", "<f4"), ("w", "<f4"), ("wSum", "<f4"), ("m", "<i4"), ("lightId", "<i4")])
 
 RT_OK, RT_ERR_INVALID_ARGUMENT, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_INVALID_STATE, RT_ERR_UNSUPPORTED, RT_ERR_OUT_OF_MEMORY = 0, -1, -2, -3, -4, -5, -6
 

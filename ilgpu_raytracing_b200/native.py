@@ -70,7 +70,7 @@ _BUF_DTYPES = {L.RT_BUF_RGBA8: (np.int32, 1), L.RT_BUF_DEPTH: (np.float32, 1), L
                L.RT_BUF_ACCUM: (np.float32, 4), L.RT_BUF_PRIM_ID: (np.int32, 1), L.RT_BUF_INST_ID: (np.int32, 1), L.RT_BUF_PRIMARY_T: (np.float32, 1),
                L.RT_BUF_SEG_COUNT: (np.uint8, 1), L.RT_BUF_TERM_CODE: (np.uint8, 1), L.RT_BUF_PATH_HASH: (np.uint32, 1),
                L.RT_BUF_GB_WORLDPOS: (np.float32, 3), L.RT_BUF_GB_NORMAL: (np.float32, 3), L.RT_BUF_GB_BASECOLOR: (np.float32, 3),
-               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4)}
+               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4), L.RT_BUF_RESERVOIR: (L.RESERVOIR, 1)}
 
 
 class Context:

@@ -166,7 +166,10 @@ enum {
     /* Count rays / nodes / primitives on the device (slower; for roofline). */
     RT_FLAG_COUNTERS      = 1u << 4,
     /* Bracket every extend (traversal) launch with CUDA events; rt_get_stats reports their sum. */
-    RT_FLAG_KERNEL_TIMING = 1u << 5
+    RT_FLAG_KERNEL_TIMING = 1u << 5,
+    /* Zero both ReSTIR reservoir buffers before this frame (start of a sequence).  The reference never clears them:
+     * frame 0 with reuse on reads uninitialised memory there (Engine/Framebuffer.cs:85-97); here they start at zero. */
+    RT_FLAG_RESET_RESERVOIRS = 1u << 6
 };
 
 /* Everything the reference passes in GBufferParams / IntegratorParams
@@ -209,8 +212,13 @@ enum {
     RT_BUF_GB_NORMAL    = 12, /* float3 per px : GpuGBuffer.normalWS */
     RT_BUF_GB_BASECOLOR = 13, /* float3 per px : GpuGBuffer.baseColor */
     RT_BUF_GB_MATID     = 14, /* int32  per px : GpuGBuffer.matId */
-    RT_BUF_TILE_RADIANCE = 15 /* float4 per OWNED px, tile-compacted (multi-GPU gather payload) */
+    RT_BUF_TILE_RADIANCE = 15,/* float4 per OWNED px, tile-compacted (multi-GPU gather payload) */
+    RT_BUF_RESERVOIR    = 16  /* RtReservoir per px : the reservoir buffer the last frame wrote ("resCur", Engine/RTRay.cs:23-48,294);
+                                 only frames rendered with a reuse flag set write reservoirs */
 };
+
+/* Reservoir (Engine/RTRay.cs:171-179), the element of RT_BUF_RESERVOIR. */
+typedef struct RtReservoir { RtFloat3 L, wi; float pdf, w, wSum; int32_t m, lightId; } RtReservoir;
 
 /* Path terminators reported in RT_BUF_TERM_CODE */
 enum {

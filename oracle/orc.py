@@ -203,6 +203,12 @@ def camera_create(width, height, fov_deg, origin=(0.0, 1.0, 3.0), look_at=(0.0, 
     return cam
 
 
+def camera_bake(cam: np.ndarray, width: int, height: int, variant="") -> np.ndarray:
+    """RTRenderer.BakeCameraDerived (Engine/RTRenderer.cs:241-263): forward / right / up / fovY / aspect, as the renderer does before every launch."""
+    lib(variant).orc_camera_bake(_p(cam), int(width), int(height))
+    return cam
+
+
 def camera_translate(cam: np.ndarray, dx, dy, dz, variant=""):
     lib(variant).orc_camera_translate(_p(cam), float(dx), float(dy), float(dz))
     return cam

@@ -74,8 +74,10 @@ struct HsOutputs {
 };
 
 // The whole frame as plain loops; mirrors the launch sequence of rt_render() in rt_api.cu.
-HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg, HsOutputs* out) {
-    if (cfg->enableTemporalReuse || cfg->enableSpatialReuse) return RT_ERR_UNSUPPORTED;
+// resPrev / resCur: the reference's Reservoir records per global pixel (ReSTIR reuse frames only; both null otherwise)
+HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prevCam, const RtRenderConfig* cfg, HsOutputs* out, const RtReservoir* resPrev, RtReservoir* resCur) {
+    const bool reuse = cfg->enableTemporalReuse != 0 || cfg->enableSpatialReuse != 0;
+    if (reuse && (!resPrev || !resCur || cfg->worldSize > 1)) return RT_ERR_INVALID_ARGUMENT;
     const int W = cfg->width, H = cfg->height;
     std::vector<int> pmap; build_pixel_map(W, H, cfg->tileSize, cfg->rank, cfg->worldSize, pmap);
     const int npx = (int)pmap.size();
@@ -90,6 +92,22 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
     fc.camOrigin = mk3(cam->origin); fc.camLowerLeft = mk3(cam->lowerLeft); fc.camHorizontal = mk3(cam->horizontal); fc.camVertical = mk3(cam->vertical);
     fc.env.dirLightDir = mk3(cfg->dirLightDir); fc.env.dirLightRadiance = mk3(cfg->dirLightRadiance); fc.env.skyTop = mk3(cfg->skyTintTop); fc.env.skyBottom = mk3(cfg->skyTintBottom);
     fc.npx = npx; fc.pixelMap = pmap.data();
+    const size_t G = (size_t)W * H;
+    std::vector<int> invMap; std::vector<float4> rp0, rp1, rp2, rc0, rc1, rc2, rq0, rq1, rq2;
+    if (reuse) {
+        const RtCamera* pc = prevCam ? prevCam : cam;
+        fc.enableTemporal = cfg->enableTemporalReuse; fc.enableSpatial = cfg->enableSpatialReuse;
+        fc.prevOrigin = mk3(pc->origin); fc.prevRight = mk3(pc->right); fc.prevUp = mk3(pc->up); fc.prevForward = mk3(pc->forward); fc.prevFovY = pc->fovYRadians; fc.prevAspect = pc->aspect;
+        invMap.assign(G, 0); for (int i = 0; i < npx; i++) invMap[(size_t)pmap[i]] = i;
+        fc.invPixelMap = invMap.data();
+        rp0.resize(G); rp1.resize(G); rp2.resize(G); rc0.resize(G); rc1.resize(G); rc2.resize(G);
+        auto split = [](const RtReservoir& r, float4& a, float4& b, float4& c) {
+            a = make_float4(r.L.X, r.L.Y, r.L.Z, r.pdf); b = make_float4(r.wi.X, r.wi.Y, r.wi.Z, r.w); c = make_float4(r.wSum, u2f((uint32_t)r.m), u2f((uint32_t)r.lightId), 0.0f);
+        };
+        for (size_t p = 0; p < G; p++) { split(resPrev[p], rp0[p], rp1[p], rp2[p]); split(resCur[p], rc0[p], rc1[p], rc2[p]); }
+        fc.resPrev0 = rp0.data(); fc.resPrev1 = rp1.data(); fc.resPrev2 = rp2.data();
+        rq0.resize(P); rq1.resize(P); rq2.resize(P);
+    }
 
     std::vector<float4> gbPosHit(npx), gbNrmMat(npx), gbAlbObj(npx), lframe(npx), tileRad(npx), stThr(P), stLi(P);
     std::vector<int> primId(npx), instId(npx); std::vector<float> primaryT(npx);
@@ -107,6 +125,7 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
     wb.radiance = radiance.data(); wb.accum = out->accum4 ? (float4*)out->accum4 : accum.data();
     wb.stThr = stThr.data(); wb.stLi = stLi.data();
     const bool aov = (cfg->flags & RT_FLAG_PATH_AOVS) && out->segCount && out->termCode && out->pathHash;
+    if (reuse) { wb.resPath0 = rq0.data(); wb.resPath1 = rq1.data(); wb.resPath2 = rq2.data(); wb.resCur0 = rc0.data(); wb.resCur1 = rc1.data(); wb.resCur2 = rc2.data(); }
     if (aov) { wb.pathHash = pathHash.data(); wb.segCountOut = out->segCount; wb.termCodeOut = out->termCode; wb.pathHashOut = out->pathHash; }
 
     TraceCounters tc = {0, 0, 0}; uint64_t nodes = 0, tris = 0, sph = 0, raysB = 0, raysS = 0;
@@ -125,7 +144,7 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
         const int ns = (s0 + S <= spp) ? S : (spp - s0);
         int cur = 0; int nNext = 0, nSh = 0;
         RayQueue nq = {qo[cur].data(), qd[cur].data(), qi[cur].data()};
-        for (int j = 0; j < npx * ns; j++) shade_first(fc, wb, s0, j, nq, &nNext, shq, &nSh);
+        for (int j = 0; j < npx * ns; j++) { if (reuse) shade_first<true>(fc, wb, s0, j, nq, &nNext, shq, &nSh); else shade_first<false>(fc, wb, s0, j, nq, &nNext, shq, &nSh); }
         for (int depth = 1; depth <= fc.maxDepth; depth++) {
             for (int k = 0; k < nSh; k++) {
                 f3 o = mk3(shq.o[k].x, shq.o[k].y, shq.o[k].z), d = mk3(shq.d[k].x, shq.d[k].y, shq.d[k].z);
@@ -138,7 +157,7 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
             raysB += (uint64_t)nNext;
             const int nCur = nNext; nNext = 0; nSh = 0;
             RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data(), qi[cur ^ 1].data()};
-            for (int k = 0; k < nCur; k++) shade_next(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh);
+            for (int k = 0; k < nCur; k++) { if (reuse) shade_next<true>(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh); else shade_next<false>(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh); }
             cur ^= 1;
         }
         const bool last = (s0 + ns >= spp);
@@ -156,6 +175,16 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
         if (out->gbMat) out->gbMat[pix] = (int32_t)f2u(gbNrmMat[i].w);
         if (out->radiance4) memcpy(out->radiance4 + 4 * (size_t)pix, &radiance[pix], 16);
     }
+    if (reuse) for (size_t p = 0; p < G; p++) {
+        RtReservoir& r = resCur[p];
+        r.L.X = rc0[p].x; r.L.Y = rc0[p].y; r.L.Z = rc0[p].z; r.pdf = rc0[p].w; r.wi.X = rc1[p].x; r.wi.Y = rc1[p].y; r.wi.Z = rc1[p].z; r.w = rc1[p].w;
+        r.wSum = rc2[p].x; r.m = (int32_t)f2u(rc2[p].y); r.lightId = (int32_t)f2u(rc2[p].z);
+    }
     out->counters[0] = (uint64_t)npx; out->counters[1] = raysB; out->counters[2] = raysS; out->counters[3] = nodes; out->counters[4] = tris; out->counters[5] = sph;
     return 0;
+}
+
+HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg, HsOutputs* out) {
+    if (cfg->enableTemporalReuse || cfg->enableSpatialReuse) return RT_ERR_INVALID_ARGUMENT;   // use hs_render_reuse
+    return hs_render_reuse(s, cam, nullptr, cfg, out, nullptr, nullptr);
 }

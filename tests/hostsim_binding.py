@@ -33,6 +33,7 @@ def lib():
         _lib.hs_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.hs_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
         _lib.hs_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs)]
+        _lib.hs_render_reuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs), C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -63,7 +64,7 @@ class HostSimScene:
         hit = lib().hs_trace(self.h, o.ctypes.data, d.ctypes.data, int(any_hit), float(t_max), flags, out.ctypes.data, cnt.ctypes.data)
         return bool(hit), float(out[0]), int(out[2]), int(out[1]), cnt
 
-    def render(self, cam: np.ndarray, cfg: L.RtRenderConfig, aovs=True):
+    def render(self, cam: np.ndarray, cfg: L.RtRenderConfig, aovs=True, prev_cam=None, res_prev=None, res_cur=None):
         W, H, spp = cfg.width, cfg.height, max(1, cfg.spp)
         n = W * H
         r = dict(rgba8=np.zeros(n, np.int32), depth=np.zeros(n, np.float32), objId=np.zeros(n, np.int32), radiance4=np.zeros((n, 4), np.float32),
@@ -76,7 +77,12 @@ class HostSimScene:
         if aovs:
             cfg.flags |= L.RT_FLAG_PATH_AOVS
         cam = np.ascontiguousarray(cam, dtype=L.CAMERA)
-        rc = lib().hs_render(self.h, cam.ctypes.data, C.byref(cfg), C.byref(o))
+        if res_prev is not None:
+            pc = np.ascontiguousarray(prev_cam if prev_cam is not None else cam, dtype=L.CAMERA)
+            assert res_prev.dtype == L.RESERVOIR and res_cur.dtype == L.RESERVOIR and res_cur.flags.c_contiguous
+            rc = lib().hs_render_reuse(self.h, cam.ctypes.data, pc.ctypes.data, C.byref(cfg), C.byref(o), res_prev.ctypes.data, res_cur.ctypes.data)
+        else:
+            rc = lib().hs_render(self.h, cam.ctypes.data, C.byref(cfg), C.byref(o))
         if rc != 0:
             raise RuntimeError(f"hs_render: {rc}")
         names = ["raysPrimary", "raysBounce", "raysShadow", "nodes", "tris", "spheres"]

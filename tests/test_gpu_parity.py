@@ -191,8 +191,14 @@ def test_error_paths(gpu_ctx):
             fresh.render(cam, bad)
         assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
     with pytest.raises(native.RtError) as e:
-        fresh.render(cam, L.make_render_config(64, 36, temporal=1))
+        fresh.render(cam, L.make_render_config(64, 36, temporal=1))                    # temporal reuse without prevCam
+    assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
+    with pytest.raises(native.RtError) as e:
+        fresh.render(cam, L.make_render_config(64, 36, spatial=1, rank=0, world_size=2))   # reuse needs the neighbours' reservoirs: no tile partition
     assert e.value.status == L.RT_ERR_UNSUPPORTED
+    with pytest.raises(native.RtError) as e:
+        fresh.download(L.RT_BUF_RESERVOIR)
+    assert e.value.status == L.RT_ERR_INVALID_STATE
     with pytest.raises(native.RtError):
         fresh.download(L.RT_BUF_RGBA8)
     fresh.render(cam, L.make_render_config(64, 36))
@@ -235,6 +241,45 @@ def test_engine_api_drop_in(gpu_ctx):
     cfg = rdr.last_config()
     assert (cfg.width, cfg.height) == (214, 121)
     rdr.close()
+
+
+@pytest.mark.parametrize("temporal,spatial", [(1, 1), (1, 0), (0, 1)])
+def test_restir_reuse_sequence(gpu_ctx, temporal, spatial):
+    """ReSTIR temporal + spatial reuse (RTRay.cs:475-516) over a 4-frame sequence with a moving camera: the previous frame's
+    reservoirs (ping-pong by frame parity, Framebuffer.cs:127-146; zero-initialised instead of the reference's uninitialised
+    memory) feed the imports, only the first Lambert vertex of a sample imports and publishes, the last sample's reservoir
+    stays.  Radiance, paths and the reservoir buffers themselves must be bit-identical to the oracle, frame after frame."""
+    W, H, spp, depth = 320, 180, 3, 3
+    sc = orc.Scene()
+    sc.build_default()
+    gpu_ctx.scene_upload(sc.arrays())
+    res = [np.zeros(W * H, orc.RESERVOIR), np.zeros(W * H, orc.RESERVOIR)]   # A, B
+    prev = None
+    for frame in range(4):
+        cam = orc.camera_create(W, H, 60.0, (0.0 + 0.07 * frame, 1.0 + 0.02 * frame, 3.0 - 0.05 * frame), (0.0, 0.5, 0.0))
+        orc.camera_bake(cam, W, H)
+        if prev is None:
+            prev = cam.copy()
+        cur_i = frame & 1
+        ocfg = orc.make_config(W, H, spp=spp, max_depth=depth, frame=frame, rng_lock_noise=0, temporal=temporal, spatial=spatial)
+        r = orc.render(sc, cam, ocfg, prev_cam=prev, res_prev=res[cur_i ^ 1], res_cur=res[cur_i])
+        cfg = L.make_render_config(W, H, spp=spp, max_depth=depth, frame=frame, rng_lock_noise=0, temporal=temporal, spatial=spatial,
+                                   flags=L.RT_FLAG_PATH_AOVS | (L.RT_FLAG_RESET_RESERVOIRS if frame == 0 else 0),
+                                   samples_per_pass=2 if frame == 2 else 0)   # one frame in two passes
+        gpu_ctx.render(cam, cfg, prev_cam=prev)
+        gpu_ctx.sync()
+        prod = download_all(gpu_ctx)
+        assert_parity(r, prod, W, H, spp=spp, label=f"reuse t{temporal} s{spatial} frame {frame}")
+        got = gpu_ctx.download(L.RT_BUF_RESERVOIR)
+        want = res[cur_i]
+        for f in ("m", "lightId", "pdf", "w", "wSum"):
+            assert np.array_equal(got[f], want[f]), f"frame {frame}: reservoir field {f} differs"
+        for f in ("L", "wi"):
+            for c in ("X", "Y", "Z"):
+                assert np.array_equal(got[f][c], want[f][c]), f"frame {frame}: reservoir field {f}.{c} differs"
+        if frame > 0:
+            assert int((want["m"] > 9).sum()) > 0   # imports happened (m counts the 9 new candidates + every accepted import)
+        prev = cam.copy()
 
 
 def test_full_size_properties_c3(gpu_ctx):

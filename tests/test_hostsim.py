@@ -30,6 +30,32 @@ def test_default_scene(spp, depth):
         assert h["counters"]["raysBounce"] == r.counters["raysBounce"] and h["counters"]["raysShadow"] == r.counters["raysShadow"]
 
 
+@pytest.mark.parametrize("temporal,spatial", [(1, 1), (1, 0), (0, 1)])
+def test_restir_reuse_sequence(temporal, spatial):
+    """ReSTIR temporal / spatial reuse (RTRay.cs:475-516) over three frames with a moving camera; see the -m gpu twin."""
+    W, H, spp, depth = 128, 72, 3, 3
+    sc = orc.Scene()
+    sc.build_default()
+    hs = HostSimScene(sc.arrays())
+    ores = [np.zeros(W * H, orc.RESERVOIR), np.zeros(W * H, orc.RESERVOIR)]
+    hres = [np.zeros(W * H, L.RESERVOIR), np.zeros(W * H, L.RESERVOIR)]
+    prev = None
+    for frame in range(3):
+        cam = orc.camera_create(W, H, 60.0, (0.07 * frame, 1.0 + 0.02 * frame, 3.0 - 0.05 * frame), (0.0, 0.5, 0.0))
+        orc.camera_bake(cam, W, H)
+        prev = cam.copy() if prev is None else prev
+        ci = frame & 1
+        r = orc.render(sc, cam, orc.make_config(W, H, spp=spp, max_depth=depth, frame=frame, rng_lock_noise=0, temporal=temporal, spatial=spatial),
+                       prev_cam=prev, res_prev=ores[ci ^ 1], res_cur=ores[ci])
+        h = hs.render(cam, L.make_render_config(W, H, spp=spp, max_depth=depth, frame=frame, rng_lock_noise=0, temporal=temporal, spatial=spatial,
+                                                samples_per_pass=2), prev_cam=prev, res_prev=hres[ci ^ 1], res_cur=hres[ci])
+        _compare(r, h, f"reuse frame {frame}")
+        assert ores[ci].tobytes() == hres[ci].tobytes(), f"frame {frame}: reservoirs differ"
+        if frame > 0:
+            assert int((ores[ci]["m"] > 9).sum()) > 0
+        prev = cam.copy()
+
+
 def test_sphere_grid_with_roulette():
     sc = oracle_scene_from_spec(scenes.sphere_grid_scene(12))
     hs = HostSimScene(sc.arrays())
