@@ -1,7 +1,8 @@
 // RTRenderer.RenderDirectToPbo.cs — the patched hot entry point of Engine/RTRenderer.cs (lines cited are the reference's).
 //
 // What changes in RTRenderer:
-//   * fields  _context/_cuda/_stream, _primaryKernel, _integratorKernel, _lowColor/... (RTRenderer.cs:25-27,37-38,53-56) -> IntPtr _rt
+//   * fields  _context/_cuda/_stream, _primaryKernel, _integratorKernel, _blitKernel, _bilinearUpsampleKernel, _taa, _gbuffer, _framebuffer's device
+//             buffers, _lowColor/... (RTRenderer.cs:25-41,53-56) -> IntPtr _rt (the core owns G-buffer, framebuffer, reservoirs and TAA history)
 //   * ctor    Context.Create(...) + CreateCudaAccelerator(deviceIndex) + LoadAutoGroupedStreamKernel x2 (:66-68,85-86)        -> _rt = RtNative.Create(deviceIndex)
 //   * Scene   keeps its host lists and builders verbatim; UploadAll (Scene.cs:258-279) pins the 15 lists and calls rt_scene_upload (below)
 //   * Dispose (:347-375)                                                                                                       -> RtNative.rt_destroy(_rt)
@@ -43,20 +44,16 @@ namespace ILGPU_Raytracing.Engine
                 flags = (uint)RtFlags.None, tileSize = 32, rank = 0, worldSize = 1, samplesPerPass = 0
             };
 
-            pbo.MapCuda(_stream);                                                                          // :208-209
-            bool direct = inW == outW && inH == outH && !_enableTAAU;
-            RtNative.ThrowIfFailed(RtNative.rt_map_external_color(_rt, direct ? pbo.DevicePointer : IntPtr.Zero, (UIntPtr)((long)outW * outH * 4)));
-
             Camera cam = _camera, prev = _prevCamera;
             RtNative.ThrowIfFailed(RtNative.rt_render(_rt, &cam, &prev, &cfg));    // replaces _primaryKernel(...) :152-153 and _integratorKernel(...) :205
 
-            if (!direct)
+            pbo.MapCuda(_stream);                                                                          // :208-209
+            var pc = new RtPresentConfig
             {
-                // TAAU / bilinear present (:211-231) keep running on the RGBA8 the core produced: fetch its device pointer
-                RtNative.ThrowIfFailed(RtNative.rt_get_device_buffer(_rt, (int)RtBuffer.Rgba8, out IntPtr lowColor, out _));
-                RtNative.ThrowIfFailed(RtNative.rt_get_device_buffer(_rt, (int)RtBuffer.ObjId, out IntPtr lowObjId, out _));
-                PresentWithTaauOrUpsample(pbo, lowColor, lowObjId, inW, inH, outW, outH, frame);           // the reference's RTTaa / BilinearUpsampleKernel, unchanged
-            }
+                mode = (int)(_enableTAAU ? RtPresentMode.Taau : RtPresentMode.Copy),                       // :211-231: RTTaa.ResolveUpsample, or blit / bilinear upsample
+                outWidth = outW, outHeight = outH, feedback = 0.075f, sharpness = 0.10f, clampK = 1.25f    // RTTaa.cs:80-82
+            };
+            RtNative.ThrowIfFailed(RtNative.rt_present(_rt, &pc, pbo.DevicePointer, (UIntPtr)((long)outW * outH * 4)));
 
             RtNative.ThrowIfFailed(RtNative.rt_sync(_rt));                          // _cuda.Synchronize() :233
             pbo.UnmapCuda(_stream);

@@ -29,7 +29,7 @@ namespace ILGPU_Raytracing.Engine
     public enum RtBuffer
     {
         Rgba8 = 0, Depth = 1, ObjId = 2, Radiance = 3, Accum = 4, PrimId = 5, InstId = 6, PrimaryT = 7, SegCount = 8, TermCode = 9, PathHash = 10,
-        GbWorldPos = 11, GbNormal = 12, GbBaseColor = 13, GbMatId = 14, TileRadiance = 15, Reservoir = 16   // Reservoir: Engine/RTRay.cs:171-179 records
+        GbWorldPos = 11, GbNormal = 12, GbBaseColor = 13, GbMatId = 14, TileRadiance = 15, Reservoir = 16, Present = 17   // Reservoir: Engine/RTRay.cs:171-179 records; Present: what rt_present wrote
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -62,6 +62,17 @@ namespace ILGPU_Raytracing.Engine
         public fixed int reserved[3];
     }
 
+    public enum RtPresentMode { Taau = 0, Copy = 1 }   // Copy = BlitKernel when the sizes match, BilinearUpsampleKernel otherwise
+
+    [StructLayout(LayoutKind.Sequential)]
+    public unsafe struct RtPresentConfig   // 44 bytes
+    {
+        public int mode, outWidth, outHeight;
+        public float feedback, sharpness, clampK;   // RTTaa.cs:80-82
+        public int resetHistory;
+        public fixed int reserved[4];
+    }
+
     [StructLayout(LayoutKind.Sequential)]
     public unsafe struct RtStats
     {
@@ -87,6 +98,7 @@ namespace ILGPU_Raytracing.Engine
         [DllImport(Lib)] public static extern int rt_buffer_bytes(IntPtr ctx, int which, out UIntPtr bytes);
         [DllImport(Lib)] public static extern int rt_get_device_buffer(IntPtr ctx, int which, out IntPtr devPtr, out UIntPtr bytes);
         [DllImport(Lib)] public static extern int rt_map_external_color(IntPtr ctx, IntPtr devPtr, UIntPtr bytes);
+        [DllImport(Lib)] public static extern int rt_present(IntPtr ctx, RtPresentConfig* cfg, IntPtr dstDevRgba8, UIntPtr dstBytes);
         [DllImport(Lib)] public static extern int rt_tiles_owned_pixels(int width, int height, int tileSize, int rank, int worldSize, out long nPixels);
         [DllImport(Lib)] public static extern int rt_deinterleave_tiles(IntPtr ctx, IntPtr gatheredDev, long* rankOffsetsPx, int worldSize, int width, int height, int tileSize, IntPtr outRadianceDev, IntPtr outRgba8Dev);
         [DllImport(Lib)] public static extern int rt_get_stats(IntPtr ctx, out RtStats stats);

@@ -482,8 +482,6 @@ void RTRenderer::Synchronize() { check(rt_sync(_native)); }
 void RTRenderer::RenderDirectToPbo(void* pboDevicePtr, int width, int height, int frame, float dt) {   // RTRenderer.cs:105-237
     int outW = std::max(1, width), outH = std::max(1, height);
     int inW = std::max(1, (int)rintf((float)outW * RenderScale)), inH = std::max(1, (int)rintf((float)outH * RenderScale));   // :113-116 (XMath.Round)
-    if (pboDevicePtr && (inW != outW || inH != outH))
-        throw InvalidOperationException("presenting into a PBO at RenderScale != 1 needs the TAAU / bilinear upsample kernels, which are outside the hot-path scope");
     BakeCameraDerived(_camera, inW, inH);              // :123-124
     BakeCameraDerived(_prevCamera, inW, inH);
     int temporalSeed = (RngLockNoise == 0) ? 0 : FixedSeed;   // :166 (Random.Shared.Next() replaced by a caller-chosen seed)
@@ -497,9 +495,14 @@ void RTRenderer::RenderDirectToPbo(void* pboDevicePtr, int width, int height, in
     cfg.enableTemporalReuse = EnableTemporalReuse; cfg.enableSpatialReuse = EnableSpatialReuse;
     cfg.dirLightDir = sunDir; cfg.dirLightRadiance = F3(10, 10, 10); cfg.skyTintTop = F3(0.5f, 0.7f, 1.0f); cfg.skyTintBottom = F3(1.0f, 1.0f, 1.0f);   // :191-194
     cfg.flags = Flags; cfg.tileSize = TileSize; cfg.rank = Rank; cfg.worldSize = WorldSize; cfg.samplesPerPass = SamplesPerPass;
-    check(rt_map_external_color(_native, pboDevicePtr, pboDevicePtr ? (size_t)outW * outH * 4 : 0));   // pbo.MapCuda + Blit (:208-228)
     check(rt_render(_native, &_camera, &_prevCamera, &cfg));   // the two kernel launches :152-153, :181-205
     _lastCfg = cfg;
+    if (WorldSize <= 1) {   // Present (:208-231): TAAU resolve, or blit / bilinear upsample, into the mapped PBO (or the core's own buffer when headless)
+        RtPresentConfig pc; memset(&pc, 0, sizeof(pc));
+        pc.mode = EnableTAAU ? RT_PRESENT_TAAU : RT_PRESENT_COPY; pc.outWidth = outW; pc.outHeight = outH;
+        pc.feedback = 0.075f; pc.sharpness = 0.10f; pc.clampK = 1.25f;   // RTTaa.cs:80-82
+        check(rt_present(_native, &pc, pboDevicePtr, pboDevicePtr ? (size_t)outW * outH * 4 : 0));
+    }
     check(rt_sync(_native));                           // _cuda.Synchronize() :233
     _prevCamera = _camera;                             // :236
 }
@@ -560,10 +563,10 @@ ENG_API void eng_renderer_get_camera(RTRenderer* r, RtCamera* out) { memcpy(out,
 ENG_API void eng_renderer_set_camera(RTRenderer* r, const RtCamera* in) { memcpy(static_cast<RtCamera*>(&r->Cam()), in, sizeof(RtCamera)); }
 ENG_API void eng_renderer_set_sun_params(RTRenderer* r, float speed, float elevation) { r->SetSunParams(speed, elevation); }
 // knobs: 0 RenderScale(float bits not used) ... use a struct instead
-struct EngKnobs { float renderScale; int enableTemporalReuse, enableSpatialReuse, rngLockNoise, fixedSeed, spp, maxDepth; unsigned flags; int tileSize, rank, worldSize, samplesPerPass; };
+struct EngKnobs { float renderScale; int enableTemporalReuse, enableSpatialReuse, rngLockNoise, fixedSeed, spp, maxDepth; unsigned flags; int tileSize, rank, worldSize, samplesPerPass, enableTAAU; };
 ENG_API void eng_renderer_set_knobs(RTRenderer* r, const EngKnobs* k) {
     r->RenderScale = k->renderScale; r->EnableTemporalReuse = k->enableTemporalReuse; r->EnableSpatialReuse = k->enableSpatialReuse; r->RngLockNoise = k->rngLockNoise;
-    r->FixedSeed = k->fixedSeed; r->Spp = k->spp; r->MaxDepth = k->maxDepth; r->Flags = k->flags; r->TileSize = k->tileSize; r->Rank = k->rank; r->WorldSize = k->worldSize; r->SamplesPerPass = k->samplesPerPass;
+    r->FixedSeed = k->fixedSeed; r->Spp = k->spp; r->MaxDepth = k->maxDepth; r->Flags = k->flags; r->TileSize = k->tileSize; r->Rank = k->rank; r->WorldSize = k->worldSize; r->SamplesPerPass = k->samplesPerPass; r->EnableTAAU = k->enableTAAU != 0;
 }
 ENG_API int eng_renderer_render_direct_to_pbo(RTRenderer* r, void* pbo, int w, int h, int frame, float dt) { return guard([&] { r->RenderDirectToPbo(pbo, w, h, frame, dt); }); }
 ENG_API void eng_renderer_last_config(RTRenderer* r, RtRenderConfig* out) { *out = r->LastConfig(); }

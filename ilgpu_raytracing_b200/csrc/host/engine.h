@@ -13,7 +13,7 @@
 //   RTRenderer        Engine/RTRenderer.cs:22-376  (RenderDirectToPbo -> rt_render)
 //
 // Out of scope: OBJ/MTL/TGA loading (LoadObjInstance takes decoded arrays here),
-// TAAU / blit / bilinear presentation kernels, OpenGL PBO interop, the fly-camera controller.
+// OpenGL PBO interop, the fly-camera controller.
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -144,7 +144,8 @@ public:
     void Synchronize();
 
     // the reference's private knobs (RTRenderer.cs:43-49,204), made settable: benchmark configs fix them
-    float RenderScale = 1.0f;      // reference default 0.67 relies on the TAAU upsampler (out of scope); 1.0 = trace at output size
+    float RenderScale = 0.67f;     // :43 (trace at round(out * scale), present at out)
+    bool EnableTAAU = true;        // :44
     int EnableTemporalReuse = 1, EnableSpatialReuse = 1;   // RTRenderer.cs:46-47 (benchmarks switch both off)
     int RngLockNoise = 1;          // reference: 0 -> seed 0, nonzero -> Random.Shared.Next() per frame (:166)
     int FixedSeed = 1;             // used instead of Random.Shared.Next() when RngLockNoise != 0 (deterministic runs)

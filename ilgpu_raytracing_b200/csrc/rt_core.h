@@ -159,6 +159,33 @@ RT_HD float acos_p(float x) {
     return r;
 }
 
+// Stand-in for XMath.Pow (RTTaa.cs:238-253, the sRGB transfer curves of the TAAU resolve), x > 0: exp2(y * log2(x)) with
+//   log2: x = 2^e * m, m in [sqrt(1/2), sqrt(2)], ln m = 2 s (1 + z/3 + z^2/5 + z^3/7 + z^4/9), s = (m-1)/(m+1), z = s^2
+//   exp2: t = k + r, |r| <= 1/2, e^(r ln 2) by its degree-7 Taylor polynomial in Horner form, scaled by 2^k through the exponent bits
+// in + - * / only (relative error ~1e-6; the consumers round to 8 bits).  The oracle carries an independent copy (orc_pow).
+RT_HD float log2_p(float x) {
+    uint32_t b = f2u(x);
+    int e = (int)((b >> 23) & 0xFFu) - 127;
+    float m = u2f((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421356f) { m = m * 0.5f; e = e + 1; }
+    float f = m - 1.0f;
+    float s = f / (2.0f + f);
+    float z = s * s;
+    float p = (((0.1111111111f * z + 0.1428571429f) * z + 0.2f) * z + 0.3333333333f) * z + 1.0f;
+    float ln = 2.0f * s * p;
+    return (float)e + ln * 1.4426950408889634f;
+}
+RT_HD float exp2_p(float t) {
+    if (t < -126.0f) return 0.0f;
+    if (t > 127.0f) t = 127.0f;
+    float kf = floorf(t + 0.5f);
+    float r = t - kf;
+    float u = r * 0.6931471805599453f;
+    float p = ((((((u * (1.0f / 7.0f) + 1.0f) * u * (1.0f / 6.0f) + 1.0f) * u * 0.2f + 1.0f) * u * 0.25f + 1.0f) * u * (1.0f / 3.0f) + 1.0f) * u * 0.5f + 1.0f) * u + 1.0f;
+    return p * u2f((uint32_t)((int)kf + 127) << 23);
+}
+RT_HD float pow_p(float x, float y) { return x > 0.0f ? exp2_p(y * log2_p(x)) : 0.0f; }
+
 // ----------------------------------------------------------------------------- RNG (RTUtils.cs:20-138)
 RT_HD uint32_t rotl32(uint32_t v, int r) { return (v << (r & 31)) | (v >> ((32 - r) & 31)); }   // :100-103
 RT_HD uint32_t splitmix32(uint64_t x) {                                                         // :54-62
@@ -559,6 +586,79 @@ RT_HD bool restir_finalize(const LightEnv& env, f3 n, f3 albedo, const Reservoir
     *contrib = f_over_p * W;
     *wiSel = wsel;
     return true;
+}
+
+// ----------------------------------------------------------------------------- present chain (RTRenderer.cs:281-346, RTTaa.cs:117-258)
+RT_HD f3 unpack_rgb(int rgba8) {   // RTRenderer.cs:322-328
+    float r = (float)((rgba8 >> 16) & 255) * (1.0f / 255.0f), g = (float)((rgba8 >> 8) & 255) * (1.0f / 255.0f), b = (float)(rgba8 & 255) * (1.0f / 255.0f);
+    return mk3(r, g, b);
+}
+RT_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }   // XMath.Clamp(int)
+// BilinearUpsampleKernel (RTRenderer.cs:287-320); PackRGBA8 / ToByte there are the same as RTRay.cs:66-76
+RT_HD int bilinear_upsample_pixel(const int* src, int srcW, int srcH, int dstW, int dstH, int index) {
+    int x = index % dstW, y = index / dstW;
+    float u = (((float)x + 0.5f) * (float)srcW / (float)dstW) - 0.5f;
+    float v = (((float)y + 0.5f) * (float)srcH / (float)dstH) - 0.5f;
+    int x0 = clampi((int)floorf(u), 0, srcW - 1), y0 = clampi((int)floorf(v), 0, srcH - 1);
+    int x1 = clampi(x0 + 1, 0, srcW - 1), y1 = clampi(y0 + 1, 0, srcH - 1);
+    float tx = fminf(1.0f, fmaxf(0.0f, u - (float)x0)), ty = fminf(1.0f, fmaxf(0.0f, v - (float)y0));
+    f3 c00 = unpack_rgb(src[y0 * srcW + x0]), c10 = unpack_rgb(src[y0 * srcW + x1]), c01 = unpack_rgb(src[y1 * srcW + x0]), c11 = unpack_rgb(src[y1 * srcW + x1]);
+    f3 cx0 = c00 * (1.0f - tx) + c10 * tx;
+    f3 cx1 = c01 * (1.0f - tx) + c11 * tx;
+    return pack_rgba8(cx0 * (1.0f - ty) + cx1 * ty);
+}
+// sRGB decode of one 8-bit channel value (RTTaa.cs:236-246).  Only 256 inputs exist: callers may tabulate it.
+RT_HD float srgb_to_linear_u8(int v) {
+    float c = (float)v / 255.0f;
+    return (c <= 0.04045f) ? (c / 12.92f) : pow_p((c + 0.055f) / 1.055f, 2.4f);
+}
+RT_HD int pack_srgb(f3 c) {   // RTTaa.cs:248-262 (XMath.Round = half-to-even)
+    float rL = fmaxf(0.0f, fminf(1.0f, c.x)), gL = fmaxf(0.0f, fminf(1.0f, c.y)), bL = fmaxf(0.0f, fminf(1.0f, c.z));
+    float r = (rL <= 0.0031308f) ? 12.92f * rL : 1.055f * pow_p(rL, 1.0f / 2.4f) - 0.055f;
+    float g = (gL <= 0.0031308f) ? 12.92f * gL : 1.055f * pow_p(gL, 1.0f / 2.4f) - 0.055f;
+    float b = (bL <= 0.0031308f) ? 12.92f * bL : 1.055f * pow_p(bL, 1.0f / 2.4f) - 0.055f;
+    int R = (int)rintf(fmaxf(0.0f, fminf(1.0f, r)) * 255.0f), G = (int)rintf(fmaxf(0.0f, fminf(1.0f, g)) * 255.0f), B = (int)rintf(fmaxf(0.0f, fminf(1.0f, b)) * 255.0f);
+    return (int)((255u << 24) | ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B);
+}
+struct TaaConst { int outW, outH, inW, inH; float feedback, sharpness, clampK; int isFirstFrame; };
+// lut[v] = srgb_to_linear_u8(v), v = 0..255
+RT_HD f3 unpack_srgb_lut(const float* lut, int rgba) { return mk3(lut[(rgba >> 16) & 255], lut[(rgba >> 8) & 255], lut[rgba & 255]); }
+RT_HD f3 catrom2(f3 a, f3 b, float t) { float tt = t * (2.0f - t); return a * (1.0f - tt) + b * tt; }   // RTTaa.cs:228-233
+RT_HD f3 sample_catrom_srgb(const float* lut, const int* a, int w, int h, float x, float y) {   // RTTaa.cs:209-226
+    int x1 = clampi((int)floorf(x), 0, w - 1), y1 = clampi((int)floorf(y), 0, h - 1);
+    float fx = x - (float)x1, fy = y - (float)y1;
+    int xr = min(x1 + 1, w - 1), yr = min(y1 + 1, h - 1);
+    f3 c00 = unpack_srgb_lut(lut, a[y1 * w + x1]), c10 = unpack_srgb_lut(lut, a[y1 * w + xr]);
+    f3 c01 = unpack_srgb_lut(lut, a[yr * w + x1]), c11 = unpack_srgb_lut(lut, a[yr * w + xr]);
+    return catrom2(catrom2(c00, c10, fx), catrom2(c01, c11, fx), fy);
+}
+// TaaResolveKernel (RTTaa.cs:117-179) for one output pixel; returns the packed colour (also the new history) and the object id
+RT_HD int taa_resolve_pixel(const TaaConst& p, const float* lut, const int* inColorLow, const int* inObjIdLow, int histColor, int histObj, int idx, int* objOut) {
+    int px = idx % p.outW, py = idx / p.outW;
+    float sx = ((float)px + 0.5f) * ((float)p.inW / (float)p.outW) - 0.5f;
+    float sy = ((float)py + 0.5f) * ((float)p.inH / (float)p.outH) - 0.5f;
+    f3 cur = sample_catrom_srgb(lut, inColorLow, p.inW, p.inH, sx, sy);
+    f3 nmin = cur, nmax = cur;
+    for (int oy = -1; oy <= 1; oy++)
+        for (int ox = -1; ox <= 1; ox++) {
+            if (ox == 0 && oy == 0) continue;
+            f3 c = sample_catrom_srgb(lut, inColorLow, p.inW, p.inH, sx + (float)ox * 0.5f, sy + (float)oy * 0.5f);
+            nmin = mk3(fminf(nmin.x, c.x), fminf(nmin.y, c.y), fminf(nmin.z, c.z));
+            nmax = mk3(fmaxf(nmax.x, c.x), fmaxf(nmax.y, c.y), fmaxf(nmax.z, c.z));
+        }
+    int ix = clampi((int)rintf(sx), 0, p.inW - 1), iy = clampi((int)rintf(sy), 0, p.inH - 1);   // SampleNearestObj :200-205
+    int objId = inObjIdLow[iy * p.inW + ix];
+    f3 hist = unpack_srgb_lut(lut, histColor);
+    bool reset = (p.isFirstFrame != 0) || (histObj != objId);
+    f3 cmin = mk3(nmin.x - p.clampK * 0.0f, nmin.y - p.clampK * 0.0f, nmin.z - p.clampK * 0.0f);   // Clamp :191-198
+    f3 cmax = mk3(nmax.x + p.clampK * 0.0f, nmax.y + p.clampK * 0.0f, nmax.z + p.clampK * 0.0f);
+    f3 hc = mk3(fminf(cmax.x, fmaxf(cmin.x, hist.x)), fminf(cmax.y, fmaxf(cmin.y, hist.y)), fminf(cmax.z, fmaxf(cmin.z, hist.z)));
+    float a = reset ? 1.0f : p.feedback;
+    f3 accum = hc * (1.0f - a) + cur * a;
+    f3 sharpen = accum * (1.0f + 2.0f * p.sharpness) - (nmin + nmax) * (0.5f * p.sharpness);
+    accum = accum * (1.0f - p.sharpness) + sharpen * p.sharpness;
+    *objOut = objId;
+    return pack_srgb(accum);
 }
 
 }   // namespace rtx

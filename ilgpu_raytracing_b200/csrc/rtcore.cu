@@ -246,6 +246,23 @@ __global__ void k_scatter_f4_w(const float4* src, int* dst, const int* pixelMap,
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) dst[pixelMap[i]] = __float_as_int(src[i].w);
 }
 
+// ---- present chain (RTRenderer.cs:281-320, RTTaa.cs:117-179): one thread per OUTPUT pixel, 4 B written (+ 8 B of history) ----
+__global__ void k_bilinear_upsample(const int* src, int srcW, int srcH, int* dst, int dstW, int dstH) {
+    const int n = dstW * dstH, stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = bilinear_upsample_pixel(src, srcW, srcH, dstW, dstH, i);
+}
+__global__ void __launch_bounds__(256) k_taa_resolve(TaaConst p, const int* lowColor, const int* lowObj, int* histColor, int* histObj, int* out) {
+    __shared__ float lut[256];   // the sRGB decode has 256 possible inputs per channel: tabulate it once per block (same bits as evaluating it in place)
+    lut[threadIdx.x] = srgb_to_linear_u8((int)threadIdx.x);
+    __syncthreads();
+    const int n = p.outW * p.outH, stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int obj;
+        const int c = taa_resolve_pixel(p, lut, lowColor, lowObj, histColor[i], histObj[i], i, &obj);
+        out[i] = c; histColor[i] = c; histObj[i] = obj;
+    }
+}
+
 // reservoir planes (L|pdf, wi|w, wSum|m|lightId) -> the reference's 44-byte Reservoir records (read-back for parity)
 __global__ void k_pack_reservoirs(const float4* res, int g, float* out) {
     const int stride = gridDim.x * blockDim.x;
@@ -328,6 +345,8 @@ struct rt_ctx {
     // kernel timing (extend kernels)
     std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool timeKernels = false;
     int* extColor = nullptr; size_t extColorBytes = 0;
+    // present chain: own output buffer, TAA history (RTTaa._historyColor / _historyObjId), where the last present went
+    DevBuf<int> presentBuf, taaHistColor, taaHistObj; int presentW = 0, presentH = 0; bool taaHistoryValid = false; const int* presentPtr = nullptr;
     // multi-GPU finish: cached owned-pixel lists of every rank
     DevBuf<int> deintMap; std::vector<int64_t> deintStart; int deintW = 0, deintH = 0, deintT = 0, deintWorld = 0;
     int extendBlocks = 0;
@@ -415,7 +434,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
-    c->materials.release(); c->texels.release(); c->texInfos.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
+    c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
     c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); c->qI[b].release(); } c->shO.release(); c->shD.release(); c->shI.release(); c->shC.release();
@@ -701,6 +720,7 @@ static int buffer_info(rt_ctx* c, int which, size_t* bytes) {
         case RT_BUF_PATH_HASH: *bytes = g * c->spp * 4; return RT_OK;
         case RT_BUF_TILE_RADIANCE: *bytes = (size_t)c->npx * 16; return RT_OK;
         case RT_BUF_RESERVOIR: *bytes = g * sizeof(RtReservoir); return RT_OK;
+        case RT_BUF_PRESENT: *bytes = (size_t)c->presentW * c->presentH * 4; return RT_OK;
     }
     return fail(RT_ERR_INVALID_ARGUMENT, "unknown buffer selector");
 }
@@ -759,6 +779,9 @@ RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
             if (!c->aovs) return fail(RT_ERR_INVALID_STATE, "rt_download: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
             src = which == RT_BUF_SEG_COUNT ? (const void*)c->segOut.p : (which == RT_BUF_TERM_CODE ? (const void*)c->termOut.p : (const void*)c->hashOut.p);
             break;
+        case RT_BUF_PRESENT:
+            if (!c->presentPtr) return fail(RT_ERR_INVALID_STATE, "rt_download: rt_present has not run yet");
+            src = c->presentPtr; break;
         case RT_BUF_RESERVOIR:
             if (c->resLastWritten < 0) return fail(RT_ERR_INVALID_STATE, "rt_download: no frame with a reuse flag set has written reservoirs yet");
             CUDA_TRY(scatterPrep(g * 11));
@@ -782,6 +805,41 @@ RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
 RT_API int rt_map_external_color(rt_ctx* c, void* devPtr, size_t bytes) {
     if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_map_external_color: ctx is null");
     c->extColor = (int*)devPtr; c->extColorBytes = devPtr ? bytes : 0;
+    return RT_OK;
+}
+
+RT_API int rt_present(rt_ctx* c, const RtPresentConfig* pc, void* dstDevRgba8, size_t dstBytes) {
+    if (!c || !pc) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: null argument");
+    if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_present: nothing rendered yet");
+    if (c->worldSize > 1) return fail(RT_ERR_UNSUPPORTED, "rt_present: the last frame was rendered as one rank of a tile partition; present on the gathered image's owner");
+    if (pc->outWidth <= 0 || pc->outHeight <= 0 || (int64_t)pc->outWidth * pc->outHeight > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: bad output size");
+    if (pc->mode != RT_PRESENT_TAAU && pc->mode != RT_PRESENT_COPY) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: unknown mode");
+    const size_t outLen = (size_t)pc->outWidth * pc->outHeight;
+    if (dstDevRgba8 && dstBytes < outLen * sizeof(int)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: destination is smaller than the output image");   // Framebuffer.cs:117
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    int* dst = (int*)dstDevRgba8;
+    if (!dst) { CUDA_TRY(c->presentBuf.ensure(outLen)); dst = c->presentBuf.p; }
+    const int inW = c->width, inH = c->height;
+    if (pc->mode == RT_PRESENT_TAAU) {
+        if (c->taaHistColor.n != outLen || !c->taaHistColor.p) {   // RTTaa.Ensure (RTTaa.cs:34-47): a new size drops the history
+            c->taaHistColor.release(); c->taaHistObj.release();
+            CUDA_TRY(c->taaHistColor.ensure(outLen)); CUDA_TRY(c->taaHistObj.ensure(outLen));
+            CUDA_TRY(cudaMemsetAsync(c->taaHistColor.p, 0, outLen * sizeof(int), st)); CUDA_TRY(cudaMemsetAsync(c->taaHistObj.p, 0, outLen * sizeof(int), st));
+            c->taaHistoryValid = false;
+        }
+        if (pc->resetHistory) c->taaHistoryValid = false;
+        TaaConst tc; tc.outW = pc->outWidth; tc.outH = pc->outHeight; tc.inW = inW; tc.inH = inH;
+        tc.feedback = pc->feedback; tc.sharpness = pc->sharpness; tc.clampK = pc->clampK; tc.isFirstFrame = c->taaHistoryValid ? 0 : 1;
+        k_taa_resolve<<<grid_for(c, outLen, 256), 256, 0, st>>>(tc, c->rgba8.p, c->objId.p, c->taaHistColor.p, c->taaHistObj.p, dst);
+        c->taaHistoryValid = true;
+    } else if (inW == pc->outWidth && inH == pc->outHeight) {
+        CUDA_TRY(cudaMemcpyAsync(dst, c->rgba8.p, outLen * sizeof(int), cudaMemcpyDeviceToDevice, st));   // BlitKernel
+    } else {
+        k_bilinear_upsample<<<grid_for(c, outLen, 256), 256, 0, st>>>(c->rgba8.p, inW, inH, dst, pc->outWidth, pc->outHeight);
+    }
+    CUDA_TRY(cudaGetLastError());
+    c->presentW = pc->outWidth; c->presentH = pc->outHeight; c->presentPtr = dst;
     return RT_OK;
 }
 
@@ -849,5 +907,6 @@ static_assert(sizeof(RtFloat3) == 12 && sizeof(RtFloat2) == 8 && sizeof(RtAffine
 static_assert(sizeof(RtBvhNode) == 44 && sizeof(RtInstanceRecord) == 144 && sizeof(RtMaterialRecord) == 44 && sizeof(RtSphere) == 80, "ABI layout");
 static_assert(sizeof(RtMeshTri) == 12 && sizeof(RtMeshTriUV) == 12 && sizeof(RtRGBA32) == 4 && sizeof(RtTexInfo) == 12 && sizeof(RtCamera) == 92, "ABI layout");
 static_assert(sizeof(RtSceneDesc) == 15 * 16 && sizeof(RtRenderConfig) == 32 + 48 + 4 + 12 + 4 + 12, "ABI layout");
+static_assert(sizeof(RtPresentConfig) == 44, "ABI layout");
 static_assert(sizeof(RtReservoir) == 44, "ABI layout");
 static_assert(sizeof(WideNode) == 80 && sizeof(PrimRec) == 48 && sizeof(HitRec) == 16, "device layout");

@@ -30,7 +30,7 @@ class EngineError(RuntimeError):
 class EngKnobs(C.Structure):
     _fields_ = [("renderScale", C.c_float), ("enableTemporalReuse", C.c_int), ("enableSpatialReuse", C.c_int), ("rngLockNoise", C.c_int),
                 ("fixedSeed", C.c_int), ("spp", C.c_int), ("maxDepth", C.c_int), ("flags", C.c_uint), ("tileSize", C.c_int), ("rank", C.c_int),
-                ("worldSize", C.c_int), ("samplesPerPass", C.c_int)]
+                ("worldSize", C.c_int), ("samplesPerPass", C.c_int), ("enableTAAU", C.c_int)]
 
 
 _lib = None
@@ -241,7 +241,7 @@ class RTRenderer:
         self.h = C.c_void_p()
         _check(self._l.eng_renderer_new(device_index, width, height, C.byref(self.h)))
         self.scene = Scene(self._l.eng_renderer_scene(self.h), owner=self)
-        self.knobs = EngKnobs(1.0, 0, 0, 1, 1, 2, 3, 0, 32, 0, 1, 0)
+        self.knobs = EngKnobs(1.0, 0, 0, 1, 1, 2, 3, 0, 32, 0, 1, 0, 0)   # benchmark-style defaults: full-resolution trace, reuse and TAAU off
         self._native_view = None
 
     def close(self):

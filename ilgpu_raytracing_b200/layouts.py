@@ -47,7 +47,8 @@ RT_FLAG_RESET_RESERVOIRS = 1 << 6
 
 (RT_BUF_RGBA8, RT_BUF_DEPTH, RT_BUF_OBJID, RT_BUF_RADIANCE, RT_BUF_ACCUM, RT_BUF_PRIM_ID, RT_BUF_INST_ID, RT_BUF_PRIMARY_T,
  RT_BUF_SEG_COUNT, RT_BUF_TERM_CODE, RT_BUF_PATH_HASH, RT_BUF_GB_WORLDPOS, RT_BUF_GB_NORMAL, RT_BUF_GB_BASECOLOR, RT_BUF_GB_MATID,
- RT_BUF_TILE_RADIANCE, RT_BUF_RESERVOIR) = range(17)
+ RT_BUF_TILE_RADIANCE, RT_BUF_RESERVOIR, RT_BUF_PRESENT) = range(18)
+RT_PRESENT_TAAU, RT_PRESENT_COPY = 0, 1
 # Reservoir (Engine/RTRay.cs:171-179), the element of RT_BUF_RESERVOIR
 RESERVOIR = np.dtype([("L", F3), ("wi", F3), ("pdf", "<f4"), ("w", "<f4"), ("wSum", "<f4"), ("m", "<i4"), ("lightId", "<i4")])
 
@@ -68,6 +69,11 @@ class RtRenderConfig(C.Structure):
                 ("dirLightDir", CFloat3), ("dirLightRadiance", CFloat3), ("skyTintTop", CFloat3), ("skyTintBottom", CFloat3),
                 ("flags", C.c_uint32), ("tileSize", C.c_int32), ("rank", C.c_int32), ("worldSize", C.c_int32),
                 ("samplesPerPass", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class RtPresentConfig(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("outWidth", C.c_int32), ("outHeight", C.c_int32), ("feedback", C.c_float), ("sharpness", C.c_float),
+                ("clampK", C.c_float), ("resetHistory", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class RtStats(C.Structure):

@@ -18,7 +18,7 @@ _LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b
 
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
-           "rt_deinterleave_tiles", "rt_get_stats"]
+           "rt_deinterleave_tiles", "rt_get_stats", "rt_present"]
 
 
 class RtError(RuntimeError):
@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
     l.rt_tiles_owned_pixels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     l.rt_deinterleave_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(L.RtStats)]
+    l.rt_present.argtypes = [C.c_void_p, C.POINTER(L.RtPresentConfig), C.c_void_p, C.c_size_t]
     for name in EXPORTS:
         if name not in ("rt_last_error",):
             getattr(l, name).restype = C.c_int
@@ -70,7 +71,7 @@ _BUF_DTYPES = {L.RT_BUF_RGBA8: (np.int32, 1), L.RT_BUF_DEPTH: (np.float32, 1), L
                L.RT_BUF_ACCUM: (np.float32, 4), L.RT_BUF_PRIM_ID: (np.int32, 1), L.RT_BUF_INST_ID: (np.int32, 1), L.RT_BUF_PRIMARY_T: (np.float32, 1),
                L.RT_BUF_SEG_COUNT: (np.uint8, 1), L.RT_BUF_TERM_CODE: (np.uint8, 1), L.RT_BUF_PATH_HASH: (np.uint32, 1),
                L.RT_BUF_GB_WORLDPOS: (np.float32, 3), L.RT_BUF_GB_NORMAL: (np.float32, 3), L.RT_BUF_GB_BASECOLOR: (np.float32, 3),
-               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4), L.RT_BUF_RESERVOIR: (L.RESERVOIR, 1)}
+               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4), L.RT_BUF_RESERVOIR: (L.RESERVOIR, 1), L.RT_BUF_PRESENT: (np.int32, 1)}
 
 
 class Context:
@@ -134,6 +135,12 @@ class Context:
 
     def map_external_color(self, dev_ptr: int | None, nbytes: int = 0):
         check(self._l.rt_map_external_color(self.h, C.c_void_p(dev_ptr or 0), nbytes))
+
+    def present(self, out_width: int, out_height: int, taau: bool = True, dst_ptr: int | None = None, dst_bytes: int = 0, reset_history: bool = False,
+                feedback: float = 0.075, sharpness: float = 0.10, clamp_k: float = 1.25):
+        """The tail of RenderDirectToPbo (RTRenderer.cs:208-231): TAAU resolve, or blit / bilinear upsample."""
+        pc = L.RtPresentConfig(L.RT_PRESENT_TAAU if taau else L.RT_PRESENT_COPY, out_width, out_height, feedback, sharpness, clamp_k, int(reset_history), (C.c_int32 * 4)(0, 0, 0, 0))
+        check(self._l.rt_present(self.h, C.byref(pc), C.c_void_p(dst_ptr or 0), dst_bytes))
 
     def deinterleave_tiles(self, gathered_ptr: int, rank_offsets_px, world_size, width, height, tile_size, out_radiance_ptr=None, out_rgba8_ptr=None):
         offs = (C.c_int64 * world_size)(*[int(o) for o in rank_offsets_px])

@@ -213,6 +213,7 @@ enum {
     RT_BUF_GB_BASECOLOR = 13, /* float3 per px : GpuGBuffer.baseColor */
     RT_BUF_GB_MATID     = 14, /* int32  per px : GpuGBuffer.matId */
     RT_BUF_TILE_RADIANCE = 15,/* float4 per OWNED px, tile-compacted (multi-GPU gather payload) */
+    RT_BUF_PRESENT      = 17, /* int32 per OUTPUT px : what the last rt_present wrote (its own buffer or the mapped PBO) */
     RT_BUF_RESERVOIR    = 16  /* RtReservoir per px : the reservoir buffer the last frame wrote ("resCur", Engine/RTRay.cs:23-48,294);
                                  only frames rendered with a reuse flag set write reservoirs */
 };
@@ -286,6 +287,23 @@ RT_API int rt_get_device_buffer(rt_ctx* ctx, int which, void** devPtr, size_t* b
 /* Write packed RGBA8 into a caller-owned device buffer (CUDA-mapped PBO):
  * replaces Framebuffer.GetGpuWithExternalColor (Engine/Framebuffer.cs:112-124). NULL unmaps. */
 RT_API int rt_map_external_color(rt_ctx* ctx, void* devPtr, size_t bytes);
+
+/* ---- present: replaces the tail of RTRenderer.RenderDirectToPbo (Engine/RTRenderer.cs:208-231): RTTaa.ResolveUpsample
+ *      (Engine/RTTaa.cs:49-179: two-tap "Catmull-Rom" upsample in linearised sRGB, 3x3 neighbourhood clamp of the history,
+ *      objId disocclusion, temporal blend, light sharpening) when TAAU is on, else BlitKernel / BilinearUpsampleKernel
+ *      (Engine/RTRenderer.cs:281-320).  Input = RGBA8 + objId of the last rt_render (width x height of that frame, whole
+ *      image: no tile partition); output = outWidth x outHeight RGBA8 into dstDevRgba8 (a CUDA-mapped PBO) or, when that
+ *      is NULL, into a buffer of the context (RT_BUF_PRESENT).  The TAA history lives in the context (RTTaa._historyColor /
+ *      _historyObjId) and is dropped when the output size changes or resetHistory != 0. ---- */
+enum { RT_PRESENT_TAAU = 0, RT_PRESENT_COPY = 1 /* blit when the sizes match, bilinear upsample otherwise */ };
+typedef struct RtPresentConfig {
+    int32_t mode;                        /* RT_PRESENT_* (RTRenderer._enableTAAU) */
+    int32_t outWidth, outHeight;
+    float   feedback, sharpness, clampK; /* RTTaa.cs:80-82: 0.075, 0.10, 1.25 */
+    int32_t resetHistory;
+    int32_t reserved[4];
+} RtPresentConfig;
+RT_API int rt_present(rt_ctx* ctx, const RtPresentConfig* cfg, void* dstDevRgba8, size_t dstBytes);
 
 /* ---- multi-GPU finish on the gathering rank: scatter the tile-compacted float4
  *      payloads of all ranks (concatenated rank-major, as NCCL gather delivers them)

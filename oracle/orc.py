@@ -106,6 +106,10 @@ def lib(variant: str = "") -> C.CDLL:
     L.orc_math_acos.argtypes = [C.c_float]
     L.orc_math_acos.restype = C.c_float
     L.orc_sample_hemisphere.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+    L.orc_math_pow.argtypes = [C.c_float, C.c_float]
+    L.orc_math_pow.restype = C.c_float
+    L.orc_bilinear_upsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    L.orc_taa_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
     L.orc_trace_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(OrcConfig), C.POINTER(OrcOutputs)]
     _libs[variant] = L
@@ -236,6 +240,31 @@ class RenderResult:
     pathHash: np.ndarray
     counters: dict
     seconds: tuple
+
+
+def bilinear_upsample(src: np.ndarray, src_w: int, src_h: int, dst_w: int, dst_h: int, variant="") -> np.ndarray:
+    """RTRenderer.BilinearUpsampleKernel (Engine/RTRenderer.cs:287-320) over the whole output image."""
+    src = np.ascontiguousarray(src, np.int32)
+    dst = np.zeros(dst_w * dst_h, np.int32)
+    lib(variant).orc_bilinear_upsample(src.ctypes.data, src_w, src_h, dst.ctypes.data, dst_w, dst_h)
+    return dst
+
+
+class TaaState:
+    """RTTaa (Engine/RTTaa.cs): history colour / object id and the _historyValid flag; resolve() = ResolveUpsample with the reference's tunables."""
+
+    def __init__(self, out_w: int, out_h: int, variant=""):
+        self.w, self.h, self.valid, self.variant = out_w, out_h, False, variant
+        self.hist_color = np.zeros(out_w * out_h, np.int32)
+        self.hist_obj = np.zeros(out_w * out_h, np.int32)
+
+    def resolve(self, low_color: np.ndarray, low_obj: np.ndarray, in_w: int, in_h: int, feedback=0.075, sharpness=0.10, clamp_k=1.25) -> np.ndarray:
+        out = np.zeros(self.w * self.h, np.int32)
+        lc, lo = np.ascontiguousarray(low_color, np.int32), np.ascontiguousarray(low_obj, np.int32)
+        lib(self.variant).orc_taa_resolve(out.ctypes.data, lc.ctypes.data, lo.ctypes.data, in_w, in_h, self.w, self.h, self.hist_color.ctypes.data,
+                                          self.hist_obj.ctypes.data, 0 if self.valid else 1, feedback, sharpness, clamp_k)
+        self.valid = True
+        return out
 
 
 def default_sun_dir(azimuth=0.0, elevation=0.9) -> np.ndarray:

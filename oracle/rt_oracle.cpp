@@ -144,6 +144,41 @@ static inline float orc_acos(float x) {   // x already clamped to [-1,1] by the 
 #endif
 }
 static inline float orc_tan(float x) { float s, c; orc_sincos(x, &s, &c); return s / c; }
+// Stand-in for XMath.Pow (call sites: Engine/RTTaa.cs:241-243,254-256), x > 0: exp2(y * log2 x).
+//   log2: x = 2^e m with m in [sqrt(1/2), sqrt(2)]; ln m = 2s(1 + z/3 + z^2/5 + z^3/7 + z^4/9), s = (m-1)/(m+1), z = s^2.
+//   exp2: t = k + r, |r| <= 1/2; e^(r ln2) from its degree-7 Taylor polynomial (Horner), times 2^k through the exponent field.
+// Only + - * / (documented pinning like orc_sincos; build with -DORC_LIBM to use powf).
+static inline float orc_log2(float x) {
+    uint32_t bits; memcpy(&bits, &x, 4);
+    int e = (int)((bits >> 23) & 0xFFu) - 127;
+    uint32_t mb = (bits & 0x007FFFFFu) | 0x3F800000u;
+    float m; memcpy(&m, &mb, 4);
+    if (m > 1.41421356f) { m = m * 0.5f; e = e + 1; }
+    float f = m - 1.0f;
+    float s = f / (2.0f + f);
+    float z = s * s;
+    float p = (((0.1111111111f * z + 0.1428571429f) * z + 0.2f) * z + 0.3333333333f) * z + 1.0f;
+    float ln = 2.0f * s * p;
+    return (float)e + ln * 1.4426950408889634f;
+}
+static inline float orc_exp2(float t) {
+    if (t < -126.0f) return 0.0f;
+    if (t > 127.0f) t = 127.0f;
+    float kf = floorf(t + 0.5f);
+    float r = t - kf;
+    float u = r * 0.6931471805599453f;
+    float p = ((((((u * (1.0f / 7.0f) + 1.0f) * u * (1.0f / 6.0f) + 1.0f) * u * 0.2f + 1.0f) * u * 0.25f + 1.0f) * u * (1.0f / 3.0f) + 1.0f) * u * 0.5f + 1.0f) * u + 1.0f;
+    uint32_t sb = (uint32_t)((int)kf + 127) << 23;
+    float sc; memcpy(&sc, &sb, 4);
+    return p * sc;
+}
+static inline float orc_pow(float x, float y) {
+#ifdef ORC_LIBM
+    return powf(x, y);
+#else
+    return x > 0.0f ? orc_exp2(y * orc_log2(x)) : 0.0f;
+#endif
+}
 
 // ------------------------------------------------------------------ POD layouts
 struct Float2 { float X, Y; };                                        // Engine/MeshLoaderOBJ.cs:33
@@ -1375,6 +1410,99 @@ ORC_API void orc_camera_translate(Camera* c, float dx, float dy, float dz) {   /
     Float3 d(dx, dy, dz); c->origin = c->origin + d; c->lowerLeft = c->lowerLeft + d; UpdateDerived(*c, c->aspect, c->fovYRadians);
 }
 ORC_API void orc_camera_bake(Camera* c, int w, int h) { BakeCameraDerived(*c, w, h); }
+
+// ---- present chain: RTRenderer.BlitKernel / BilinearUpsampleKernel (Engine/RTRenderer.cs:281-346), RTTaa.TaaResolveKernel (Engine/RTTaa.cs:117-262) ----
+namespace orc {
+static inline Float3 UnpackRGB(int rgba8) {   // RTRenderer.cs:322-328
+    float r = (float)((rgba8 >> 16) & 255) * (1.0f / 255.0f), g = (float)((rgba8 >> 8) & 255) * (1.0f / 255.0f), b = (float)(rgba8 & 255) * (1.0f / 255.0f);
+    return Float3(r, g, b);
+}
+static inline int ClampI(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+static void BilinearUpsampleKernel(int index, const int* srcRGBA8, int srcW, int srcH, int* dstRGBA8, int dstW, int dstH) {   // RTRenderer.cs:287-320
+    int x = index % dstW, y = index / dstW;
+    float u = (((float)x + 0.5f) * (float)srcW / (float)dstW) - 0.5f;
+    float v = (((float)y + 0.5f) * (float)srcH / (float)dstH) - 0.5f;
+    int x0 = ClampI((int)floorf(u), 0, srcW - 1), y0 = ClampI((int)floorf(v), 0, srcH - 1);
+    int x1 = ClampI(x0 + 1, 0, srcW - 1), y1 = ClampI(y0 + 1, 0, srcH - 1);
+    float tx = XClamp(u - (float)x0, 0.0f, 1.0f), ty = XClamp(v - (float)y0, 0.0f, 1.0f);
+    Float3 c00 = UnpackRGB(srcRGBA8[y0 * srcW + x0]), c10 = UnpackRGB(srcRGBA8[y0 * srcW + x1]);
+    Float3 c01 = UnpackRGB(srcRGBA8[y1 * srcW + x0]), c11 = UnpackRGB(srcRGBA8[y1 * srcW + x1]);
+    Float3 cx0 = c00 * (1.0f - tx) + c10 * tx;
+    Float3 cx1 = c01 * (1.0f - tx) + c11 * tx;
+    Float3 c = cx0 * (1.0f - ty) + cx1 * ty;
+    dstRGBA8[index] = PackRGBA8(c);
+}
+static inline Float3 UnpackSRGB(int rgba) {   // RTTaa.cs:236-246
+    float r = (float)((rgba >> 16) & 255) / 255.0f, g = (float)((rgba >> 8) & 255) / 255.0f, b = (float)(rgba & 255) / 255.0f;
+    r = (r <= 0.04045f) ? (r / 12.92f) : orc_pow((r + 0.055f) / 1.055f, 2.4f);
+    g = (g <= 0.04045f) ? (g / 12.92f) : orc_pow((g + 0.055f) / 1.055f, 2.4f);
+    b = (b <= 0.04045f) ? (b / 12.92f) : orc_pow((b + 0.055f) / 1.055f, 2.4f);
+    return Float3(r, g, b);
+}
+static inline int PackSRGB(Float3 c) {   // RTTaa.cs:248-262
+    float rL = XMax(0.0f, XMin(1.0f, c.X)), gL = XMax(0.0f, XMin(1.0f, c.Y)), bL = XMax(0.0f, XMin(1.0f, c.Z));
+    float r = (rL <= 0.0031308f) ? 12.92f * rL : 1.055f * orc_pow(rL, 1.0f / 2.4f) - 0.055f;
+    float g = (gL <= 0.0031308f) ? 12.92f * gL : 1.055f * orc_pow(gL, 1.0f / 2.4f) - 0.055f;
+    float b = (bL <= 0.0031308f) ? 12.92f * bL : 1.055f * orc_pow(bL, 1.0f / 2.4f) - 0.055f;
+    int R = (int)rintf(XMax(0.0f, XMin(1.0f, r)) * 255.0f);   // XMath.Round: half to even
+    int G = (int)rintf(XMax(0.0f, XMin(1.0f, g)) * 255.0f);
+    int B = (int)rintf(XMax(0.0f, XMin(1.0f, b)) * 255.0f);
+    return (int)((255u << 24) | ((uint32_t)R << 16) | ((uint32_t)G << 8) | (uint32_t)B);
+}
+static inline Float3 CatRom(Float3 a, Float3 b, float t) { float tt = t * (2.0f - t); return a * (1.0f - tt) + b * tt; }   // :228-233
+static Float3 SampleCatRomSRGB(const int* a, int w, int h, float x, float y) {   // :209-226
+    int x1 = ClampI((int)floorf(x), 0, w - 1), y1 = ClampI((int)floorf(y), 0, h - 1);
+    float fx = x - (float)x1, fy = y - (float)y1;
+    Float3 c00 = UnpackSRGB(a[y1 * w + x1]);
+    Float3 c10 = UnpackSRGB(a[y1 * w + XMin(x1 + 1, w - 1)]);
+    Float3 c01 = UnpackSRGB(a[XMin(y1 + 1, h - 1) * w + x1]);
+    Float3 c11 = UnpackSRGB(a[XMin(y1 + 1, h - 1) * w + XMin(x1 + 1, w - 1)]);
+    Float3 cx0 = CatRom(c00, c10, fx), cx1 = CatRom(c01, c11, fx);
+    return CatRom(cx0, cx1, fy);
+}
+struct TaaParams { int* outColor; const int* inColorLow; const int* inObjIdLow; int* historyColor; int* historyObjId; int outW, outH, inW, inH; float feedback, sharpness, clampK; int isFirstFrame; };
+static void TaaResolveKernel(int idx, const TaaParams& p) {   // :117-179
+    int outW = p.outW;
+    int px = idx % outW, py = idx / outW;
+    float sx = ((float)px + 0.5f) * ((float)p.inW / (float)outW) - 0.5f;
+    float sy = ((float)py + 0.5f) * ((float)p.inH / (float)p.outH) - 0.5f;
+    Float3 cur = SampleCatRomSRGB(p.inColorLow, p.inW, p.inH, sx, sy);
+    Float3 nmin = cur, nmax = cur;
+    for (int oy = -1; oy <= 1; oy++) for (int ox = -1; ox <= 1; ox++) {
+        if (ox == 0 && oy == 0) continue;
+        Float3 c = SampleCatRomSRGB(p.inColorLow, p.inW, p.inH, sx + (float)ox * 0.5f, sy + (float)oy * 0.5f);
+        nmin = Float3(XMin(nmin.X, c.X), XMin(nmin.Y, c.Y), XMin(nmin.Z, c.Z));
+        nmax = Float3(XMax(nmax.X, c.X), XMax(nmax.Y, c.Y), XMax(nmax.Z, c.Z));
+    }
+    int ix = ClampI((int)rintf(sx), 0, p.inW - 1), iy = ClampI((int)rintf(sy), 0, p.inH - 1);   // SampleNearestObj :200-205
+    int objId = p.inObjIdLow[iy * p.inW + ix];
+    Float3 hist = UnpackSRGB(p.historyColor[idx]);
+    int histObj = p.historyObjId[idx];
+    bool reset = (p.isFirstFrame != 0) || (histObj != objId);
+    float k = p.clampK;
+    Float3 cmin(nmin.X - k * 0.0f, nmin.Y - k * 0.0f, nmin.Z - k * 0.0f), cmax(nmax.X + k * 0.0f, nmax.Y + k * 0.0f, nmax.Z + k * 0.0f);   // Clamp :191-198
+    Float3 histClamped(XMin(cmax.X, XMax(cmin.X, hist.X)), XMin(cmax.Y, XMax(cmin.Y, hist.Y)), XMin(cmax.Z, XMax(cmin.Z, hist.Z)));
+    float a = reset ? 1.0f : p.feedback;
+    Float3 accum = histClamped * (1.0f - a) + cur * a;                                                         // Lerp
+    Float3 sharpen = accum * (1.0f + 2.0f * p.sharpness) - (nmin + nmax) * (0.5f * p.sharpness);
+    accum = accum * (1.0f - p.sharpness) + sharpen * p.sharpness;                                             // Mix
+    p.outColor[idx] = PackSRGB(accum);
+    p.historyColor[idx] = p.outColor[idx];
+    p.historyObjId[idx] = objId;
+}
+}   // namespace orc
+ORC_API float orc_math_pow(float x, float y) { return orc_pow(x, y); }
+// dst may not alias src.  The blit path (RTRenderer.cs:225-226, equal sizes) is a plain copy and needs no oracle.
+ORC_API void orc_bilinear_upsample(const int* src, int srcW, int srcH, int* dst, int dstW, int dstH) {
+    for (int i = 0; i < dstW * dstH; i++) BilinearUpsampleKernel(i, src, srcW, srcH, dst, dstW, dstH);
+}
+// RTTaa.ResolveUpsample (RTTaa.cs:49-96) with its fixed tunables passed in; history arrays are updated in place.
+ORC_API void orc_taa_resolve(int* outColor, const int* lowColor, const int* lowObjId, int inW, int inH, int outW, int outH,
+                             int* historyColor, int* historyObjId, int isFirstFrame, float feedback, float sharpness, float clampK) {
+    TaaParams p; p.outColor = outColor; p.inColorLow = lowColor; p.inObjIdLow = lowObjId; p.historyColor = historyColor; p.historyObjId = historyObjId;
+    p.outW = outW; p.outH = outH; p.inW = inW; p.inH = inH; p.feedback = feedback; p.sharpness = sharpness; p.clampK = clampK; p.isFirstFrame = isFirstFrame;
+    for (int i = 0; i < outW * outH; i++) TaaResolveKernel(i, p);
+}
 
 // KAT taps
 ORC_API uint32_t orc_rng_seed(int px, int py, int frame, uint32_t sample, uint32_t salt, int lockNoise) { return RNG::CreateFromPixel(px, py, frame, sample, salt, lockNoise).state; }

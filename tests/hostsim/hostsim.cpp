@@ -188,3 +188,17 @@ HS_API int hs_render(HsScene* s, const RtCamera* cam, const RtRenderConfig* cfg,
     if (cfg->enableTemporalReuse || cfg->enableSpatialReuse) return RT_ERR_INVALID_ARGUMENT;   // use hs_render_reuse
     return hs_render_reuse(s, cam, nullptr, cfg, out, nullptr, nullptr);
 }
+
+// ---- present chain bodies (rt_core.h) as plain loops ----
+HS_API void hs_bilinear_upsample(const int* src, int srcW, int srcH, int* dst, int dstW, int dstH) {
+    for (int i = 0; i < dstW * dstH; i++) dst[i] = bilinear_upsample_pixel(src, srcW, srcH, dstW, dstH, i);
+}
+HS_API void hs_taa_resolve(int* out, const int* lowColor, const int* lowObj, int inW, int inH, int outW, int outH, int* histColor, int* histObj,
+                           int isFirstFrame, float feedback, float sharpness, float clampK) {
+    float lut[256];
+    for (int v = 0; v < 256; v++) lut[v] = srgb_to_linear_u8(v);
+    TaaConst p; p.outW = outW; p.outH = outH; p.inW = inW; p.inH = inH; p.feedback = feedback; p.sharpness = sharpness; p.clampK = clampK; p.isFirstFrame = isFirstFrame;
+    for (int i = 0; i < outW * outH; i++) { int obj; const int c = taa_resolve_pixel(p, lut, lowColor, lowObj, histColor[i], histObj[i], i, &obj); out[i] = c; histColor[i] = c; histObj[i] = obj; }
+}
+HS_API float hs_pow(float x, float y) { return pow_p(x, y); }
+

@@ -33,6 +33,10 @@ def lib():
         _lib.hs_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
         _lib.hs_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
         _lib.hs_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs)]
+        _lib.hs_bilinear_upsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+        _lib.hs_taa_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+        _lib.hs_pow.argtypes = [C.c_float, C.c_float]
+        _lib.hs_pow.restype = C.c_float
         _lib.hs_render_reuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs), C.c_void_p, C.c_void_p]
     return _lib
 

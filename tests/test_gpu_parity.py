@@ -234,12 +234,20 @@ def test_engine_api_drop_in(gpu_ctx):
     ref = orc.render(sc, oracle_camera("C1B", W, H), orc.make_config(W, H, spp=2, max_depth=3, rng_lock_noise=7), aovs=False)
     assert np.array_equal(color, ref.rgba8) and np.array_equal(depth, ref.depth) and np.array_equal(objid, ref.objId)
     assert np.array_equal(pbo.cpu().numpy(), ref.rgba8)
-    rdr.configure(renderScale=0.67)
-    with pytest.raises(engine.EngineError, match="InvalidOperationException"):
-        rdr.RenderDirectToPbo(pbo.data_ptr(), W, H, 1, 0.016)
-    rdr.RenderDirectToPbo(None, W, H, 1, 0.016)   # traced at round(W*0.67) x round(H*0.67) like RTRenderer.cs:113-116
-    cfg = rdr.last_config()
-    assert (cfg.width, cfg.height) == (214, 121)
+    # the reference's default flow (RTRenderer.cs:43-44,113-116,208-223): trace at round(out * 0.67), TAAU-resolve into the PBO
+    rdr.configure(renderScale=0.67, enableTAAU=1)
+    st = orc.TaaState(W, H)
+    for frame in (1, 2):
+        rdr.RenderDirectToPbo(pbo.data_ptr(), W, H, frame, 0.016)
+        cfg = rdr.last_config()
+        assert (cfg.width, cfg.height) == (214, 121)
+        low = orc.render(sc, oracle_camera("C1B", W, H), orc.make_config(214, 121, spp=2, max_depth=3, frame=frame, rng_lock_noise=7), aovs=False)
+        assert np.array_equal(pbo.cpu().numpy(), st.resolve(low.rgba8, low.objId, 214, 121)), f"TAAU present, frame {frame}"
+    rdr.configure(enableTAAU=0)
+    rdr.RenderDirectToPbo(pbo.data_ptr(), W, H, 3, 0.016)   # bilinear upsample (RTRenderer.cs:227-228)
+    assert np.array_equal(pbo.cpu().numpy(), orc.bilinear_upsample(low.rgba8, 214, 121, W, H))
+    rdr.RenderDirectToPbo(None, W, H, 3, 0.016)             # headless: the presented image stays in the core
+    assert np.array_equal(rdr.native.download(L.RT_BUF_PRESENT), orc.bilinear_upsample(low.rgba8, 214, 121, W, H))
     rdr.close()
 
 
@@ -280,6 +288,39 @@ def test_restir_reuse_sequence(gpu_ctx, temporal, spatial):
         if frame > 0:
             assert int((want["m"] > 9).sum()) > 0   # imports happened (m counts the 9 new candidates + every accepted import)
         prev = cam.copy()
+
+
+def test_present_chain(gpu_ctx):
+    """rt_present = the tail of RenderDirectToPbo (RTRenderer.cs:208-231): TAAU resolve over 3 frames (history, objId disocclusion,
+    sRGB curves), bilinear upsample and blit, into the context's buffer and into a caller-owned 'PBO'; bit-exact vs the oracle."""
+    import torch
+    inW, inH, outW, outH = 214, 121, 320, 180   # round(320 * 0.67), round(180 * 0.67) as RTRenderer.cs:113-116
+    sc = orc.Scene()
+    sc.build_default()
+    gpu_ctx.scene_upload(sc.arrays())
+    st = orc.TaaState(outW, outH)
+    pbo = torch.zeros(outW * outH, dtype=torch.int32, device="cuda")
+    for frame in range(3):
+        cam = orc.camera_create(inW, inH, 60.0, (0.05 * frame, 1.0, 3.0), (0.0, 0.5, 0.0))
+        r = orc.render(sc, cam, orc.make_config(inW, inH, spp=2, max_depth=3, frame=frame, rng_lock_noise=0), aovs=False)
+        gpu_ctx.render(cam, L.make_render_config(inW, inH, spp=2, max_depth=3, frame=frame, rng_lock_noise=0))
+        want = st.resolve(r.rgba8, r.objId, inW, inH)
+        if frame < 2:
+            gpu_ctx.present(outW, outH, taau=True, reset_history=(frame == 0))
+            got = gpu_ctx.download(L.RT_BUF_PRESENT)
+        else:
+            gpu_ctx.present(outW, outH, taau=True, dst_ptr=pbo.data_ptr(), dst_bytes=pbo.numel() * 4)
+            gpu_ctx.sync()
+            got = pbo.cpu().numpy()
+        assert np.array_equal(got, want), f"TAAU frame {frame}: {(got != want).sum()} px differ"
+        gpu_ctx.present(outW, outH, taau=False)
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_PRESENT), orc.bilinear_upsample(r.rgba8, inW, inH, outW, outH))
+        gpu_ctx.present(inW, inH, taau=False)
+        assert np.array_equal(gpu_ctx.download(L.RT_BUF_PRESENT), r.rgba8)   # blit
+    from ilgpu_raytracing_b200 import native
+    with pytest.raises(native.RtError) as e:
+        gpu_ctx.present(outW, outH, taau=True, dst_ptr=pbo.data_ptr(), dst_bytes=16)
+    assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
 
 
 def test_full_size_properties_c3(gpu_ctx):

@@ -23,7 +23,7 @@ def _built():
 def test_abi_exports_match_header():
     hdr = open(os.path.join(ROOT, "include", "rtcore_b200.h")).read()
     declared = set(re.findall(r"RT_API\s+(?:const\s+)?\w+\*?\s+(\w+)\s*\(", hdr))
-    assert declared == set(native.EXPORTS) and len(declared) == 15
+    assert declared == set(native.EXPORTS) and len(declared) == 16
     lib = native.lib()
     for name in declared:
         assert getattr(lib, name) is not None
@@ -32,7 +32,7 @@ def test_abi_exports_match_header():
 
 def test_layout_sizes():
     assert C.sizeof(L.RtSceneDesc) == 15 * 16
-    assert C.sizeof(L.RtRenderConfig) == 112
+    assert C.sizeof(L.RtRenderConfig) == 112 and C.sizeof(L.RtPresentConfig) == 44 and L.RESERVOIR.itemsize == 44
     assert L.CAMERA.itemsize == 92 and L.SPHERE.itemsize == 80 and L.INSTANCE.itemsize == 144 and L.MATERIAL.itemsize == 44 and L.BVHNODE.itemsize == 44
 
 

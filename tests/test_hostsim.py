@@ -56,6 +56,35 @@ def test_restir_reuse_sequence(temporal, spatial):
         prev = cam.copy()
 
 
+def test_present_chain_bodies():
+    """Blit / bilinear upsample / TAAU resolve (RTRenderer.cs:281-320, RTTaa.cs:117-262): the core's stage bodies against the oracle
+    on a rendered low-res frame, three frames of history, and the pow stand-in they share."""
+    from tests.hostsim_binding import lib as hlib
+    import ctypes as C
+    h = hlib()
+    rs = np.random.RandomState(3)
+    for x, y in zip(rs.uniform(1e-4, 4.0, 2000).astype(np.float32), rs.choice(np.array([2.4, 1 / 2.4, 0.5, 3.0], np.float32), 2000)):
+        assert h.hs_pow(float(x), float(y)) == orc.lib().orc_math_pow(float(x), float(y))
+    inW, inH, outW, outH = 86, 48, 128, 72   # renderScale 0.67
+    sc = orc.Scene()
+    sc.build_default()
+    st = orc.TaaState(outW, outH)
+    hc, ho = np.zeros(outW * outH, np.int32), np.zeros(outW * outH, np.int32)
+    for frame in range(3):
+        cam = orc.camera_create(inW, inH, 60.0, (0.05 * frame, 1.0, 3.0), (0.0, 0.5, 0.0))
+        r = orc.render(sc, cam, orc.make_config(inW, inH, spp=1, max_depth=2, frame=frame, rng_lock_noise=0), aovs=False)
+        want = st.resolve(r.rgba8, r.objId, inW, inH)
+        got = np.zeros(outW * outH, np.int32)
+        lc, lo = np.ascontiguousarray(r.rgba8), np.ascontiguousarray(r.objId)
+        h.hs_taa_resolve(got.ctypes.data, lc.ctypes.data, lo.ctypes.data, inW, inH, outW, outH, hc.ctypes.data, ho.ctypes.data, 1 if frame == 0 else 0, 0.075, 0.10, 1.25)
+        assert np.array_equal(got, want), f"TAAU frame {frame}"
+        assert np.array_equal(hc, st.hist_color) and np.array_equal(ho, st.hist_obj)
+        up = np.zeros(outW * outH, np.int32)
+        h.hs_bilinear_upsample(lc.ctypes.data, inW, inH, up.ctypes.data, outW, outH)
+        assert np.array_equal(up, orc.bilinear_upsample(r.rgba8, inW, inH, outW, outH))
+    assert len(np.unique(want)) > 50 and (want >> 24 & 255 == 255).all()
+
+
 def test_sphere_grid_with_roulette():
     sc = oracle_scene_from_spec(scenes.sphere_grid_scene(12))
     hs = HostSimScene(sc.arrays())
