@@ -11,6 +11,7 @@
 // minimum of (tWorld, [same instance: tObj], rank).
 #pragma once
 #include "rt_core.h"
+#include <stdio.h>
 #if defined(__CUDACC__)
 #include <cuda_fp16.h>
 #endif
@@ -31,7 +32,17 @@ struct LaneStack {
     int stride;            // blockDim.x
     int sp;
     const uint32_t* lut;   // hit table (RT_HIT_TABLE_WORDS words of shared memory, filled by fill_hit_table)
+#if RT_DEBUG_BOUNDS
+    int entries;
+    RT_HD void store_top(uint2 v) {
+#if defined(__CUDA_ARCH__)
+        if (sp < 0 || sp >= entries) { printf("stack overflow: sp %d entries %d\n", sp, entries); __trap(); }
+#endif
+        smem[sp * stride] = v;
+    }
+#else
     RT_HD void store_top(uint2 v) { smem[sp * stride] = v; }
+#endif
     RT_HD uint2 load_below() const { return smem[(sp > 0 ? sp - 1 : 0) * stride]; }
 #else
     uint2 all[RT_STACK_ENTRIES + 1];
@@ -163,6 +174,9 @@ __device__ __forceinline__ void rt_fma2(float a0, float a1, float b, float c, fl
         : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b), "f"(c));
 }
 #endif
+#ifndef RT_DEBUG_BOUNDS
+#define RT_DEBUG_BOUNDS 0   // 1: device-side bounds checks of stack / node / primitive indices (debug builds; compute-sanitizer is not available on the pool)
+#endif
 #ifndef RT_USE_FFMA2
 #define RT_USE_FFMA2 1
 #endif
@@ -271,6 +285,9 @@ struct Traversal {
         const uint32_t imaskP = hits & 0xFFu;
         const uint32_t rel = (uint32_t)rt_popc(imaskP & ~(0xFFFFFFFFu << slot));
         const WideNode* np = sc.nodes + (base + rel);
+#if defined(__CUDA_ARCH__) && RT_DEBUG_BOUNDS
+        if ((int)(base + rel) < 0 || (int)(base + rel) >= sc.nNodes) { printf("node index %u + %u outside %d (hits %08x bit %d slot %u)\n", base, rel, sc.nNodes, hits, bit, slot); __trap(); }
+#endif
         if (COUNT) cnt->nodes++;
         const uint4 n0 = rt_ldg(&np->n0), n1 = rt_ldg(&np->n1), n2 = rt_ldg(&np->n2), n3 = rt_ldg(&np->n3), n4 = rt_ldg(&np->n4);
 
@@ -299,6 +316,9 @@ struct Traversal {
         const int bit = rt_bfind(tgroup.y);
         tgroup.y &= ~(1u << bit);
         const int pi = (int)tgroup.x + rt_popc(tvalid & ~(0xFFFFFFFFu << bit));   // records are compacted: count the valid bits below
+#if defined(__CUDA_ARCH__) && RT_DEBUG_BOUNDS
+        if (pi < 0 || pi >= sc.nPrims) { printf("prim index %d outside %d (tgroup %u %08x valid %08x)\n", pi, sc.nPrims, tgroup.x, tgroup.y, tvalid); __trap(); }
+#endif
         const PrimRec* pp = sc.prims + pi;
         const float4 q0 = rt_ldg(&pp->q0), q1 = rt_ldg(&pp->q1), q2 = rt_ldg(&pp->q2);
         const uint32_t meta = f2u(q2.w);

@@ -29,7 +29,7 @@ using namespace rtx;
 #define RT_EXTEND_THREADS 128
 #endif
 #ifndef RT_EXTEND_MIN_BLOCKS
-#define RT_EXTEND_MIN_BLOCKS 5
+#define RT_EXTEND_MIN_BLOCKS 6   // 80 registers per lane: 24 warps per SM (sweep: 6 x 128 and 8 x 96 threads tie, 5 x 128 is 4-5 % slower)
 #endif
 #ifndef RT_EXTEND_BATCH
 #define RT_EXTEND_BATCH 96   // ray indices a warp takes from the global queue per atomic
@@ -55,6 +55,7 @@ struct ExtendArgs {
     WaveBuffers wb;            // ... and the path state connect() updates
     DeviceStats* stats;
     int statSlot;              // 0 primary, 1 bounce, 2 shadow
+    int stackEntries;          // traversal stack entries per lane in shared memory (debug bounds checks)
 };
 
 __global__ void k_generate_primary(FrameConst fc, RayQueue q, int* countOut) {
@@ -78,6 +79,9 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
     stack.stride = RT_EXTEND_THREADS;
     stack.sp = 0;
     stack.lut = hitTable;
+#if RT_DEBUG_BOUNDS
+    stack.entries = a.stackEntries;
+#endif
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
@@ -352,7 +356,7 @@ struct rt_ctx {
     int extendBlocks = 0;
     size_t memTotal = 0;
     size_t l2PersistMax = 0, l2WindowMax = 0, l2Persist = 0, l2Window = 0; cudaStream_t l2WindowStream = nullptr;
-    size_t extendSmem = 0;
+    size_t extendSmem = 0; int stackEntries = 0;
 };
 
 template <typename T> static cudaError_t upload_or_one(DevBuf<T>& dst, const T* src, int64_t n, cudaStream_t st, int* lenOut) {
@@ -372,7 +376,8 @@ static cudaError_t trace_event(rt_ctx* c) {
     return cudaEventRecord(c->traceEvents[c->traceEventsUsed++], c->stream);
 }
 
-template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs& a, bool count) {
+template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs& a0, bool count) {
+    ExtendArgs a = a0; a.stackEntries = c->stackEntries;
     cudaError_t e = trace_event(c);
     if (e != cudaSuccess) return e;
     if (count) k_extend<ANY, true><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
@@ -386,6 +391,7 @@ template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs
 // persistent grid of the extend kernels: shared memory for a traversal stack of `entries` per lane, blocks = occupancy x SMs
 static int size_extend_launch(rt_ctx* c, int entries) {
     entries = std::max(2, std::min(entries, RT_STACK_ENTRIES));
+    c->stackEntries = entries;
     c->extendSmem = (size_t)RT_HIT_TABLE_WORDS * sizeof(uint32_t) + (size_t)entries * RT_EXTEND_THREADS * sizeof(uint2);
     int perSm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
