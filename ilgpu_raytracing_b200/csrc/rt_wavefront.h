@@ -120,6 +120,35 @@ RT_HD void primary_finish(const FrameConst& fc, const DeviceScene& sc, const Wav
     wb.objId[pix] = oid;
 }
 
+// ------------------------------------------------------------------------------------------------ shared sun probe
+// The reference has no sub-pixel jitter: all spp of a pixel start from ONE primary vertex.  When ReSTIR
+// selects the directional ("sun") candidate there, Visible() (RTRay.cs:618-624) traces the very same ray - origin
+// pos + n * EPS_N, direction normalize(dirLightDir) - for every such sample of the pixel.  The device traces that ray once
+// per pixel (sun_probe_generate -> any-hit extend -> sun_probe_store) and the first-vertex shade reads the answer: same
+// bits, ~spp x fewer shadow rays at depth 0.  Flags live in gbPosHit.w next to the hit mask (bit 0).
+enum : uint32_t { GB_HIT = 1u, GB_SUN_KNOWN = 2u, GB_SUN_VISIBLE = 4u };
+RT_HD void sun_probe_generate(const FrameConst& fc, const WaveBuffers& wb, int i, const ShadowQueue& shQ, int* shCount) {
+    const float4 ph = wb.gbPosHit[i];
+    if ((f2u(ph.w) & GB_HIT) == 0u) return;
+    const float4 nm = wb.gbNrmMat[i];
+    if (((int)f2u(nm.w) & 0xFFFF) != RT_SHADING_LAMBERT) return;
+    const f3 n = normalize(mk3(nm.x, nm.y, nm.z));        // v.nrm of shade_first (:222)
+    const f3 wi = normalize(fc.env.dirLightDir);          // the delta candidate's direction (:467)
+    if (!(fmaxf(0.0f, dot(n, wi)) > 0.0f) || !(dot(n, wi) > 0.0f)) return;   // restir_finalize would not trace (:524, :620-621)
+    const RayOD s = make_ray_normal_offset(mk3(ph.x, ph.y, ph.z), n, wi);   // Visible() :622
+    const int k = queue_alloc(shCount);
+    shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)i));
+    shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, 0.0f);
+    shQ.inv[k] = box_idir4(s.d);
+    shQ.c[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+RT_HD void sun_probe_store(const WaveBuffers& wb, const ShadowQueue& shQ, int k) {
+    const int i = (int)f2u(shQ.o[k].w);
+    float4 ph = wb.gbPosHit[i];
+    ph.w = u2f(f2u(ph.w) | GB_SUN_KNOWN | (shQ.c[k].w != 0.0f ? GB_SUN_VISIBLE : 0u));
+    wb.gbPosHit[i] = ph;
+}
+
 // ------------------------------------------------------------------------------------------------ shade
 struct PathVertex { f3 pos, nrm, alb, I; int shade; float ior; };
 
@@ -206,8 +235,10 @@ RT_HD void restir_imports(const FrameConst& fc, const WaveBuffers& wb, int path,
 // Returns false when Russian roulette killed the path.
 // REUSE = a reuse flag is set (compile-time, so the common path does not carry the import code's registers)
 template <bool REUSE>
+// sunFlags: the pixel's GB_SUN_* bits when this is the first vertex of the path and the shared probe applies, else 0;
+// *direct receives "throughput * direct" when the probe answered instead of a shadow ray (else stays 0), *probed counts it.
 RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathVertex& v, int depth, int path, f3& thr, uint32_t& rng, uint32_t& pflags,
-                        const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+                        const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, uint32_t sunFlags = 0u, f3* direct = nullptr, int* probed = nullptr) {
     RayOD ray;
     if (v.shade == RT_SHADING_MIRROR) {   // :235-244
         f3 dirR = reflect3(v.I, v.nrm);
@@ -245,7 +276,12 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
             wb.resPath2[path] = make_float4(r.wSum, u2f((uint32_t)r.m), u2f((uint32_t)r.lightId), 0.0f);
             pflags |= PATH_WROTE_RESERVOIR;
         }
-        if (restir_finalize(fc.env, v.nrm, v.alb, r, &wiSel, &contrib)) {
+        const bool wantShadow = restir_finalize(fc.env, v.nrm, v.alb, r, &wiSel, &contrib);
+        if (wantShadow && (sunFlags & GB_SUN_KNOWN) != 0u && r.lightId == 2) {
+            // the selected sample is the sun: its shadow ray is the pixel's shared probe
+            if (sunFlags & GB_SUN_VISIBLE) *direct = thr * contrib;
+            *probed = (sunFlags & GB_SUN_VISIBLE) ? 2 : 1;
+        } else if (wantShadow) {
             RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
             int k = queue_alloc(shCount);
@@ -276,14 +312,14 @@ RT_HD uint32_t pack_aov(int seg, int term) { return (uint32_t)(seg & 0xFF) | ((u
 // depth 0: start every path of the batch from the G-buffer (RTRay.cs:210-232)
 template <bool REUSE = false>
 RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBase, int j,
-                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, unsigned* probedCount = nullptr) {
     const int i = j % fc.npx;
     const int s = sampleBase + j / fc.npx;
     int x, y; pixel_xy(fc, fc.pixelMap[i], &x, &y);
     uint32_t rng = rng_seed_pixel((uint32_t)x, (uint32_t)y, fc.frame, (uint32_t)s, 0xC0FFEEu, fc.rngLockNoise);   // :212
     if (wb.pathHash) wb.pathHash[j] = 0x811C9DC5u;
     const float4 ph = wb.gbPosHit[i];
-    if (f2u(ph.w) == 0u) {   // :214-219 — the sky for primary misses is added by accumulate()
+    if ((f2u(ph.w) & GB_HIT) == 0u) {   // :214-219 — the sky for primary misses is added by accumulate()
         wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_PRIMARY_MISS)));
         return;
     }
@@ -302,9 +338,15 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     v.ior = i16_to_float((packedMat >> 16) & 0xFFFF);  // :226
     v.I = normalize(v.pos - fc.camOrigin);             // ViewDirFromCam :156,230
     uint32_t pflags = 0u;
-    bool alive = shade_vertex<REUSE>(fc, wb, v, 0, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount);
+    // with reuse on, an imported reservoir may carry another frame's sun direction: every sample traces its own ray then
+    const uint32_t sunFlags = REUSE ? 0u : (f2u(ph.w) & (GB_SUN_KNOWN | GB_SUN_VISIBLE));
+    f3 direct = mk3(0.0f, 0.0f, 0.0f); int probed = 0;
+    bool alive = shade_vertex<REUSE>(fc, wb, v, 0, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount, sunFlags, &direct, &probed);
     wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
-    wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pflags | pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+    // connect_shadow would have run before anything else touches Li: Li = 0 + throughput * direct, and the visibility fold of the path hash
+    if (probed != 0 && wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (probed == 2 ? 1u : 0u));
+    wb.stLi[j] = make_float4(0.0f + direct.x, 0.0f + direct.y, 0.0f + direct.z, u2f(pflags | pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+    if (probedCount && probed != 0) (*probedCount)++;
 }
 
 // A bounce ray that left the scene: "Li += throughput * SkyWeighted(ray.dir); break" (RTRay.cs:242,273,315).  On the device
@@ -375,7 +417,7 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
     f3 L = mk3(0.0f, 0.0f, 0.0f);
     if (sampleBase > 0) { const float4 l4 = wb.lframe[i]; L = mk3(l4.x, l4.y, l4.z); }
     f3 skyMiss = mk3(0.0f, 0.0f, 0.0f);
-    const bool primaryMiss = f2u(wb.gbPosHit[i].w) == 0u;
+    const bool primaryMiss = (f2u(wb.gbPosHit[i].w) & GB_HIT) == 0u;
     if (primaryMiss) { int x, y; pixel_xy(fc, pix, &x, &y); skyMiss = safe_color(sky_weighted(fc.env, primary_dir(fc, x, y))); }   // :216-217
     const size_t plane = (size_t)fc.width * (size_t)fc.height;
     int resOwner = -1;   // the reference's samples run in order and each overwrites resCur[index] (:294): the last writer's reservoir stays

@@ -43,6 +43,8 @@ using namespace rtx;
 
 struct DeviceStats {   // zeroed at the start of every rt_render
     unsigned long long raysPrimary, raysBounce, raysShadow, wideNodes, tris, spheres;
+    unsigned long long raysSunProbe;    // shared sun-visibility probes traced (one per Lambert primary vertex facing the sun)
+    unsigned long long shadowProbed;    // first-vertex shadow rays answered by a probe instead of their own trace
 };
 
 struct ExtendArgs {
@@ -54,7 +56,7 @@ struct ExtendArgs {
     ShadowQueue shq;           // any-hit: the queue itself (o/d alias rayO/rayD) ...
     WaveBuffers wb;            // ... and the path state connect() updates
     DeviceStats* stats;
-    int statSlot;              // 0 primary, 1 bounce, 2 shadow
+    int statSlot;              // 0 primary, 1 bounce, 2 shadow, 3 sun probe
     int stackEntries;          // traversal stack entries per lane in shared memory (debug bounds checks)
 };
 
@@ -87,7 +89,7 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
     const unsigned ltMask = (1u << lane) - 1u;
     const int n = *a.count;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long* slot = a.statSlot == 0 ? &a.stats->raysPrimary : (a.statSlot == 1 ? &a.stats->raysBounce : &a.stats->raysShadow);
+        unsigned long long* slot = a.statSlot == 0 ? &a.stats->raysPrimary : (a.statSlot == 1 ? &a.stats->raysBounce : (a.statSlot == 2 ? &a.stats->raysShadow : &a.stats->raysSunProbe));
         atomicAdd(slot, (unsigned long long)n);
     }
     if (n <= 0 || a.sc.nNodes <= 0) {
@@ -172,10 +174,22 @@ __global__ void k_primary_finish(FrameConst fc, DeviceScene sc, WaveBuffers wb, 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) primary_finish(fc, sc, wb, q, hits, i);
 }
 
-template <bool REUSE>
-__global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
+__global__ void k_sun_generate(FrameConst fc, WaveBuffers wb, ShadowQueue shq, int* shCount) {
     const int stride = gridDim.x * blockDim.x;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first<REUSE>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) sun_probe_generate(fc, wb, i, shq, shCount);
+}
+__global__ void k_sun_store(WaveBuffers wb, ShadowQueue shq, const int* count) {
+    const int n = *count, stride = gridDim.x * blockDim.x;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) sun_probe_store(wb, shq, k);
+}
+
+template <bool REUSE>
+__global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, DeviceStats* stats) {
+    const int stride = gridDim.x * blockDim.x;
+    unsigned probed = 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first<REUSE>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed);
+    for (int o = 16; o > 0; o >>= 1) probed += __shfl_xor_sync(0xFFFFFFFFu, probed, o);
+    if ((threadIdx.x & 31u) == 0u && probed != 0u) atomicAdd(&stats->shadowProbed, (unsigned long long)probed);
 }
 
 // Most bounce rays of an open scene leave it, and shading the few hits in place left ~5 of 32 lanes busy.  So each block
@@ -608,9 +622,10 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     c->launches = 0;
     c->ds.triMaterials = (cfg->flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
 
-    // device counters: [0] primary ray count, [1] its work cursor, then per (pass, depth): nextCount, shCount, workClosest, workShadow
-    const int CS = 4;   // ints per (pass, depth)
-    const size_t nCounters = 2 + (size_t)nPasses * (cfg->maxDepth + 1) * CS;
+    // device counters: [0] primary ray count, [1] its work cursor, [2] sun-probe count, [3] its work cursor, then per (pass, depth):
+    // nextCount, shCount, workClosest, workShadow
+    const int CS = 4, CH = 4;   // ints per (pass, depth); header ints
+    const size_t nCounters = CH + (size_t)nPasses * (cfg->maxDepth + 1) * CS;
     CUDA_TRY(c->counters.ensure(nCounters));
     CUDA_TRY(c->dstats.ensure(1));
     cudaStream_t st = c->stream;
@@ -665,16 +680,26 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         CUDA_TRY(launch_extend<false>(c, ea, count));
         k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, c->hits.p); c->launches++;
 
-        // ---- integrator: batches of S samples, one wavefront iteration per depth ---------------------------------
         ShadowQueue shq = {c->shO.p, c->shD.p, c->shI.p, c->shC.p};
+        // ---- shared sun probe: one any-hit ray per Lambert primary vertex facing the sun, instead of one per sample that selects it
+        if (spp >= 2 && cfg->maxDepth >= 1 && !reuse && getenv("RT_NO_SUN_PROBE") == nullptr) {
+            int* sunCount = c->counters.p + 2;
+            k_sun_generate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, shq, sunCount); c->launches++;
+            ExtendArgs pa; memset(&pa, 0, sizeof(pa));
+            pa.sc = c->ds; pa.rayO = shq.o; pa.rayD = shq.d; pa.rayI = shq.inv; pa.count = sunCount; pa.work = sunCount + 1; pa.shq = shq; pa.wb = wb; pa.stats = c->dstats.p; pa.statSlot = 3;
+            CUDA_TRY(launch_extend<true>(c, pa, count));
+            k_sun_store<<<grid_for(c, npx, 256), 256, 0, st>>>(wb, shq, sunCount); c->launches++;
+        }
+
+        // ---- integrator: batches of S samples, one wavefront iteration per depth ---------------------------------
         for (int pass = 0; pass < nPasses; pass++) {
             const int s0 = pass * S, ns = std::min(S, spp - s0);
             const size_t nPaths = (size_t)npx * ns;
-            int* ctr = c->counters.p + 2 + (size_t)pass * (cfg->maxDepth + 1) * CS;
+            int* ctr = c->counters.p + CH + (size_t)pass * (cfg->maxDepth + 1) * CS;
             int cur = 0;
             RayQueue nq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
-            if (reuse) k_shade_first<true><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1);
-            else k_shade_first<false><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1);
+            if (reuse) k_shade_first<true><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+            else k_shade_first<false><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
             c->launches++;
             for (int depth = 1; depth <= cfg->maxDepth; depth++) {
                 int* prev = ctr + (size_t)(depth - 1) * CS;   // counts produced by the shade of depth-1
@@ -892,7 +917,10 @@ RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
     if (!c->rendered) return RT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    out->raysPrimary = c->hstats.raysPrimary; out->raysBounce = c->hstats.raysBounce; out->raysShadow = c->hstats.raysShadow;
+    out->raysPrimary = c->hstats.raysPrimary; out->raysBounce = c->hstats.raysBounce;
+    out->raysShadow = c->hstats.raysShadow + c->hstats.shadowProbed;   // ShadowOcclusion calls of the reference: own traces + those answered by a shared sun probe
+    out->reserved[1] = c->hstats.raysShadow + c->hstats.raysSunProbe;   // any-hit rays actually traced
+    out->reserved[2] = c->hstats.raysSunProbe;
     out->wideNodes = c->hstats.wideNodes; out->trisTested = c->hstats.tris; out->spheresTested = c->hstats.spheres;
     out->kernelLaunches = c->launches;
     float ms = 0.0f;

@@ -152,6 +152,8 @@ class Context:
         check(self._l.rt_get_stats(self.h, C.byref(s)))
         d = {k: getattr(s, k) for k, _ in L.RtStats._fields_ if k != "reserved"}
         d["extendLaunchesTimed"] = int(s.reserved[0])
+        d["raysAnyHitTraced"] = int(s.reserved[1])   # shadow rays traced individually + shared sun probes (raysShadow counts the reference's ShadowOcclusion calls)
+        d["raysSunProbe"] = int(s.reserved[2])
         return d
 
 
