@@ -45,6 +45,10 @@ WORKLOADS = {
     "C2": dict(scene="spheres", cam="C2", w=1920, h=1080, spp=16, depth=4, crop=(480, 270, 1440, 810), cpu_spp=16),
     "C3": dict(scene="terrain", cam="C3", w=3840, h=2160, spp=1, depth=0, crop=(960, 540, 2880, 1620), cpu_spp=1),
     "C4": dict(scene="terrain+spheres", cam="C3", w=3840, h=2160, spp=64, depth=8, crop=(1536, 864, 2304, 1296), cpu_spp=64, ref_crop=(1792, 1008, 2048, 1152)),
+    # C5: 7680x4320 progressive accumulation, a step = one 16-spp frame of the 16-frame / 256-spp sequence (rngLockNoise = 0,
+    # frame index advancing, float4 accumulator), extension variant of the scene (per-patch Lambert / mirror / glass triangle materials)
+    "C5": dict(scene="terrain+spheres+mats", cam="C3", w=7680, h=4320, spp=16, depth=8, crop=(3712, 2088, 3968, 2232), cpu_spp=16,
+               progressive=True, tri_materials=True),
 }
 
 
@@ -58,6 +62,8 @@ def make_spec(kind: str):
         return scenes.terrain_scene(708, 0)
     if kind == "terrain+spheres":
         return scenes.terrain_scene(708, 256)
+    if kind == "terrain+spheres+mats":
+        return scenes.terrain_scene(708, 256, patch_materials=True)
     raise ValueError(kind)
 
 
@@ -113,7 +119,8 @@ def cpu_oracle_sample(wl: dict, threads: int = 0) -> dict:
     sc = oracle_scene_from_spec(make_spec(wl["scene"]))
     cam = oracle_camera(wl["cam"], wl["w"], wl["h"])
     crop = wl["crop"] or (0, 0, wl["w"], wl["h"])
-    cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop, threads=threads)
+    cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop, threads=threads,
+                          flags=1 if wl.get("tri_materials") else 0, rng_lock_noise=0 if wl.get("progressive") else 1)
     t0 = time.perf_counter()
     r = orc.render(sc, cam, cfg, aovs=False)
     wall = time.perf_counter() - t0
@@ -134,7 +141,8 @@ def run_reference(args, wl, name):
     sc = oracle_scene_from_spec(make_spec(wl["scene"]))
     cam = oracle_camera(wl["cam"], wl["w"], wl["h"])
     crop = wl.get("ref_crop") or wl["crop"] or (0, 0, wl["w"], wl["h"])
-    cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop)
+    cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop,
+                          flags=1 if wl.get("tri_materials") else 0, rng_lock_noise=0 if wl.get("progressive") else 1)
     rays = secs = 0.0
     for i in range(args.warmup + args.steps):
         r = orc.render(sc, cam, cfg, aovs=False)
@@ -197,7 +205,11 @@ def main():
     rdr.Commit()
     t_commit = time.perf_counter() - t0
     rdr.camera = engine.config_camera(wl["cam"], W, H)
-    rdr.configure(renderScale=1.0, enableTemporalReuse=0, enableSpatialReuse=0, spp=spp, maxDepth=depth, rngLockNoise=1, fixedSeed=1, flags=0, tileSize=tile, rank=rank, worldSize=world)
+    progressive = bool(wl.get("progressive"))
+    base_flags = (L.RT_FLAG_TRI_MATERIALS if wl.get("tri_materials") else 0) | (L.RT_FLAG_ACCUMULATE if progressive else 0)
+    lock = 0 if progressive else 1
+    rdr.configure(renderScale=1.0, enableTemporalReuse=0, enableSpatialReuse=0, spp=spp, maxDepth=depth, rngLockNoise=lock, fixedSeed=1, flags=base_flags,
+                  tileSize=tile, rank=rank, worldSize=world)
     ctx = rdr.native
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -205,8 +217,9 @@ def main():
     # bake the derived camera fields exactly as RenderDirectToPbo does before launching
     engine.lib().eng_camera_bake(cam.ctypes.data_as(__import__("ctypes").c_void_p), W, H)
 
-    def cfg_for(flags=0):
-        return L.make_render_config(W, H, spp=spp, max_depth=depth, rng_lock_noise=1, flags=flags, tile_size=tile, rank=rank, world_size=world)
+    def cfg_for(flags=0, frame=0):
+        f = base_flags | flags | (L.RT_FLAG_RESET_ACCUM if progressive and frame == 0 else 0)
+        return L.make_render_config(W, H, spp=spp, max_depth=depth, frame=frame if progressive else 0, rng_lock_noise=lock, flags=f, tile_size=tile, rank=rank, world_size=world)
 
     npx_all = [native.tiles_owned_pixels(W, H, tile, r, world) for r in range(world)]
     max_npx = max(npx_all)
@@ -239,10 +252,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg = cfg_for(0)
     with torch.cuda.stream(stream):
-        for _ in range(args.warmup):
-            step(cfg)
+        for i in range(args.warmup):
+            step(cfg_for(0, i))
     barrier()
     st0 = ctx.stats()
     sampler = ClockSampler(local_rank)
@@ -252,8 +264,8 @@ def main():
     barrier()
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for _ in range(args.steps):
-            step(cfg)
+        for i in range(args.steps):
+            step(cfg_for(0, args.warmup + i))   # progressive workloads advance the frame index (new samples every step)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -278,8 +290,11 @@ def main():
     pin_np = [p.numpy() for p in pin]
     ctx.set_stream(None)
 
+    e2e_frame = [0]
+
     def e2e_step():
-        rdr.RenderDirectToPbo(None, W, H, 0, 0.0)    # host camera + knobs in; two launches' worth of work; Synchronize()
+        rdr.RenderDirectToPbo(None, W, H, e2e_frame[0], 0.0)    # host camera + knobs in; two launches' worth of work; Synchronize()
+        e2e_frame[0] += 1 if progressive else 0
         rdr.DownloadToCpu(*pin_np)                   # Framebuffer.DownloadToCpu: RGBA8 + depth + objId to host
 
     for _ in range(min(2, args.warmup)):
@@ -344,7 +359,9 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
                 "config": {"workload": name, "scene": wl["scene"], "triangles": int(len(spec.mesh.tris)) if spec.mesh is not None else 0, "spheres": int(len(spec.spheres)),
-                           "width": W, "height": H, "spp": spp, "max_depth": depth, "variant": "reference-faithful (triangles Lambert)",
+                           "width": W, "height": H, "spp": spp, "max_depth": depth,
+                           "variant": "extension (RT_FLAG_TRI_MATERIALS: per-patch Lambert / mirror / glass triangles)" if wl.get("tri_materials") else "reference-faithful (triangles Lambert)",
+                           "progressive": "float4 accumulation, one 16-spp frame of the 256-spp sequence per step" if progressive else None,
                            "partition": f"interleaved {tile}x{tile} screen tiles x{world}, scene replicated" if world > 1 else "single GPU",
                            "l2": "no explicit flush: per-step path state + queues (GBs) exceed the 126 MB L2; the BVH is meant to stay resident"},
                 "frames_per_s": 1e3 / ms_per_step, "mrays_per_s_incl_shadow": rays_all / (ms_per_step * 1e-3) / 1e6,

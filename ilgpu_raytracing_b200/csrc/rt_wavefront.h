@@ -438,15 +438,19 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
     if (!last) { wb.lframe[i] = make_float4(L.x, L.y, L.z, 0.0f); return; }
     const f3 Lout = L * (1.0f / (float)max(1, fc.spp));   // :323
     wb.radiance[pix] = make_float4(Lout.x, Lout.y, Lout.z, 1.0f);
-    wb.tileRadiance[i] = make_float4(Lout.x, Lout.y, Lout.z, 1.0f);
     f3 shown = Lout;
+    float nAccum = 1.0f;
     if (fc.flags & RT_FLAG_ACCUMULATE) {
         float4 a = (fc.flags & RT_FLAG_RESET_ACCUM) ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : wb.accum[pix];
         a.x = a.x + Lout.x; a.y = a.y + Lout.y; a.z = a.z + Lout.z; a.w = a.w + 1.0f;
         wb.accum[pix] = a;
         const float inv = 1.0f / a.w;
         shown = mk3(a.x * inv, a.y * inv, a.z * inv);
+        nAccum = a.w;
     }
+    // multi-GPU gather payload: what this pixel shows (the progressive mean when accumulating), so that rank 0's
+    // de-interleaved image packs to the same RGBA8 as a single-GPU run
+    wb.tileRadiance[i] = make_float4(shown.x, shown.y, shown.z, nAccum);
     wb.rgba8[pix] = pack_rgba8(shown);
 }
 

@@ -176,6 +176,34 @@ def test_progressive_accumulation(gpu_ctx):
     shown = total * (np.float32(1.0) / acc[:, 3:4])
     want = (255 << 24) | ((np.float32(255.99) * np.clip(shown[:, 0], 0, 1)).astype(np.int64) << 16) | ((np.float32(255.99) * np.clip(shown[:, 1], 0, 1)).astype(np.int64) << 8) | (np.float32(255.99) * np.clip(shown[:, 2], 0, 1)).astype(np.int64)
     assert np.array_equal(gpu_ctx.download(L.RT_BUF_RGBA8).astype(np.int64) & 0xFFFFFFFF, want)
+    single_rgba = gpu_ctx.download(L.RT_BUF_RGBA8).copy()
+
+    # C5 protocol: the same progressive sequence tile-partitioned over 4 ranks; after the last frame the gathered
+    # payloads (progressive mean per owned pixel) de-interleave to the single-GPU image, bit for bit
+    import torch
+    from ilgpu_raytracing_b200 import native
+    world, tile = 4, 32
+    counts = [native.tiles_owned_pixels(W, H, tile, r, world) for r in range(world)]
+    max_n = max(counts)
+    flat = torch.zeros((world * max_n, 4), dtype=torch.float32, device="cuda")
+    ranks = [native.Context(0) for _ in range(world)]   # one context per rank, as in a real multi-GPU run (each keeps its own accumulator)
+    for rc in ranks:
+        rc.scene_upload(sc.arrays())
+    for frame in range(3):
+        for rank, rc in enumerate(ranks):
+            flags = L.RT_FLAG_ACCUMULATE | (L.RT_FLAG_RESET_ACCUM if frame == 0 else 0)
+            rc.render(cam, L.make_render_config(W, H, spp=2, max_depth=2, frame=frame, rng_lock_noise=0, flags=flags, tile_size=tile, rank=rank, world_size=world))
+            rc.sync()
+            if frame == 2:
+                pay = rc.download(L.RT_BUF_TILE_RADIANCE)
+                assert np.all(pay[:, 3] == 3.0)
+                flat[rank * max_n: rank * max_n + counts[rank]] = torch.from_numpy(pay).cuda()
+    for rc in ranks:
+        rc.close()
+    out_rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda")
+    gpu_ctx.deinterleave_tiles(flat.data_ptr(), [r * max_n for r in range(world)], world, W, H, tile, None, out_rgba.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(out_rgba.cpu().numpy(), single_rgba)
 
 
 def test_error_paths(gpu_ctx):
