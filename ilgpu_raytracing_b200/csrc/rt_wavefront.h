@@ -51,7 +51,7 @@ struct WaveBuffers {
 
 // Ray queues (SoA of float4): o.w = path slot (int bits); inv = the box-test reciprocal of d (box_idir), computed
 // once by the producer so the persistent extend kernel starts a ray with three 128-bit loads and no divisions.
-struct RayQueue { float4* o; float4* d; float4* inv; };
+struct RayQueue { float4* o; float4* d; float4* inv; };   // o.w = d.w = path slot: a consumer that needs only one of the two vectors still gets the slot
 struct ShadowQueue { float4* o; float4* d; float4* inv; float4* c; };   // c.xyz = throughput * f_over_p * W
 
 RT_HD float4 box_idir4(f3 d) { const f3 i = box_idir(d); return make_float4(i.x, i.y, i.z, 0.0f); }
@@ -85,7 +85,7 @@ RT_HD void generate_primary(const FrameConst& fc, const RayQueue& q, int i) {
     int x, y; pixel_xy(fc, fc.pixelMap[i], &x, &y);
     f3 d = primary_dir(fc, x, y);
     q.o[i] = make_float4(fc.camOrigin.x, fc.camOrigin.y, fc.camOrigin.z, u2f((uint32_t)i));
-    q.d[i] = make_float4(d.x, d.y, d.z, 0.0f);
+    q.d[i] = make_float4(d.x, d.y, d.z, u2f((uint32_t)i));
     q.inv[i] = box_idir4(d);
 }
 
@@ -138,7 +138,7 @@ RT_HD void sun_probe_generate(const FrameConst& fc, const WaveBuffers& wb, int i
     const RayOD s = make_ray_normal_offset(mk3(ph.x, ph.y, ph.z), n, wi);   // Visible() :622
     const int k = queue_alloc(shCount);
     shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)i));
-    shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, 0.0f);
+    shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, u2f((uint32_t)i));
     shQ.inv[k] = box_idir4(s.d);
     shQ.c[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
@@ -286,7 +286,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
             int k = queue_alloc(shCount);
             shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)path));
-            shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, 0.0f);
+            shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, u2f((uint32_t)path));
             shQ.inv[k] = box_idir4(s.d);
             shQ.c[k] = make_float4(c.x, c.y, c.z, 0.0f);
         }
@@ -302,7 +302,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
     }
     int k = queue_alloc(nextCount);
     nextQ.o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f((uint32_t)path));
-    nextQ.d[k] = make_float4(ray.d.x, ray.d.y, ray.d.z, 0.0f);
+    nextQ.d[k] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f((uint32_t)path));
     nextQ.inv[k] = box_idir4(ray.d);
     return true;
 }

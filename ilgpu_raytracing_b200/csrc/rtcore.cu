@@ -194,39 +194,64 @@ __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers 
 
 // Most bounce rays of an open scene leave it, and shading the few hits in place left ~5 of 32 lanes busy.  So each block
 // takes chunks of RT_SHADE_CHUNK consecutive rays and makes two passes over a chunk: (1) every lane looks at one ray at a
-// time: a miss adds the sky to its path right away (short), a hit is appended to a list in shared memory (ballot + one
-// shared-memory atomic per warp: no global atomics, no extra global traffic); (2) the compacted hits are shaded (long:
-// surface evaluation, nine ReSTIR candidates, bounce) with every lane busy.
-#define RT_SHADE_CHUNK 2048
+// time: a miss adds the sky to its path right away (short); a hit is classified by the material of what it hit and appended
+// to a list in shared memory - Lambert vertices (long: nine ReSTIR candidates) from the front, mirror / glass vertices
+// (short) from the back - with ballot + one shared-memory atomic per warp: no global atomics, no extra global traffic;
+// (2) the two ends of the list are shaded one after the other, each with every lane busy on the same kind of vertex.
+#ifndef RT_SHADE_CHUNK
+#define RT_SHADE_CHUNK 4096
+#endif
+__device__ __forceinline__ bool hit_is_specular(const DeviceScene& sc, int prim) {   // the "shade" TraceClosest will report (SceneDeviceViews.cs:61,158)
+    const uint32_t meta = __float_as_uint(__ldg(&sc.prims[prim].q2.w));
+    const int primId = (int)__float_as_uint(__ldg(&sc.prims[prim].q0.w));
+    int shade = RT_SHADING_LAMBERT;
+    if (meta & PRIM_SPHERE) shade = sc.spheres[primId].shading;
+    else if (sc.triMaterials) shade = sc.materials[sc.triMatIndex[primId]].Shading;
+    return shade == RT_SHADING_MIRROR || shade == RT_SHADING_GLASS;
+}
 template <bool REUSE>
 __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, const HitRec* hits, const int* curCount,
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
     __shared__ int list[RT_SHADE_CHUNK];
-    __shared__ int listCount;
+    __shared__ int nFront, nBack;
     const int n = *curCount;
     const int nChunks = (n + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
+    const unsigned ltMask = (1u << lane) - 1u;
     for (int ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
-        if (threadIdx.x == 0) listCount = 0;
+        if (threadIdx.x == 0) { nFront = 0; nBack = 0; }
         __syncthreads();
         const int base = ch * RT_SHADE_CHUNK;
         for (int i = threadIdx.x; i < RT_SHADE_CHUNK; i += 256) {
             const int k = base + i;
             const bool valid = k < n;
-            const bool hit = valid && __ldg(&hits[k].t) < 1e29f;
-            if (valid && !hit) { const float4 ro = curQ.o[k], rd = curQ.d[k]; miss_update(fc.env, wb, (int)f2u(ro.w), mk3(rd.x, rd.y, rd.z)); }
-            const unsigned m = __ballot_sync(FULL, hit);
-            if (m != 0u) {
+            HitRec h; h.t = 1e30f; h.prim = -1;
+            if (valid) { const float4 hv = __ldg(reinterpret_cast<const float4*>(hits) + k); h.t = hv.x; h.prim = __float_as_int(hv.y); }
+            const bool hit = valid && h.t < 1e29f;
+            if (valid && !hit) { const float4 rd = __ldcs(curQ.d + k); miss_update(fc.env, wb, (int)f2u(rd.w), mk3(rd.x, rd.y, rd.z)); }   // d.w = path slot
+            const bool spec = hit && depth < fc.maxDepth && hit_is_specular(sc, h.prim);
+            const unsigned mF = __ballot_sync(FULL, hit && !spec), mB = __ballot_sync(FULL, spec);
+            if (mF != 0u) {
                 int b = 0;
-                if (lane == 0) b = atomicAdd(&listCount, __popc(m));
+                if (lane == 0) b = atomicAdd(&nFront, __popc(mF));
                 b = __shfl_sync(FULL, b, 0);
-                if (hit) list[b + __popc(m & ((1u << lane) - 1u))] = k;
+                if (hit && !spec) list[b + __popc(mF & ltMask)] = k;
+            }
+            if (mB != 0u) {
+                int b = 0;
+                if (lane == 0) b = atomicAdd(&nBack, __popc(mB));
+                b = __shfl_sync(FULL, b, 0);
+                if (spec) list[RT_SHADE_CHUNK - 1 - (b + __popc(mB & ltMask))] = k;
             }
         }
         __syncthreads();
-        const int nh = listCount;
-        for (int i = threadIdx.x; i < nh; i += 256) shade_next<REUSE>(fc, sc, wb, depth, curQ, hits, list[i], nextQ, nextCount, shq, shCount);
+        const int nf = nFront, nb = nBack;
+        const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
+        for (int i = threadIdx.x; i < rf + nb; i += 256) {
+            const bool front = i < rf;
+            if (front ? (i < nf) : true) shade_next<REUSE>(fc, sc, wb, depth, curQ, hits, front ? list[i] : list[RT_SHADE_CHUNK - 1 - (i - rf)], nextQ, nextCount, shq, shCount);
+        }
         __syncthreads();
     }
 }
