@@ -18,7 +18,7 @@ CORE_DEPS = CORE_SRCS + [os.path.join(_CSRC, f) for f in ("rt_core.h", "rt_trave
     [os.path.join(_PKG, "..", "include", "rtcore_b200.h")]
 
 ENGINE_SO = os.path.join(_PKG, "librtengine_host.so")
-ENGINE_SRCS = [os.path.join(_CSRC, "host", "engine.cpp")]
+ENGINE_SRCS = [os.path.join(_CSRC, "host", f) for f in ("engine.cpp", "mesh_loader_obj.cpp")]
 ENGINE_DEPS = ENGINE_SRCS + [os.path.join(_CSRC, "host", "engine.h"), os.path.join(_PKG, "..", "include", "rtcore_b200.h")]
 
 

@@ -520,6 +520,10 @@ template <class F> static int guard(F&& f) {
     catch (const ArgumentNullException& e) { g_engErr = std::string("ArgumentNullException: ") + e.what(); return -101; }
     catch (const ArgumentOutOfRangeException& e) { g_engErr = std::string("ArgumentOutOfRangeException: ") + e.what(); return -102; }
     catch (const InvalidOperationException& e) { g_engErr = std::string("InvalidOperationException: ") + e.what(); return -103; }
+    catch (const FileNotFoundException& e) { g_engErr = std::string("FileNotFoundException: ") + e.what(); return -104; }
+    catch (const InvalidDataException& e) { g_engErr = std::string("InvalidDataException: ") + e.what(); return -105; }
+    catch (const EndOfStreamException& e) { g_engErr = std::string("EndOfStreamException: ") + e.what(); return -106; }
+    catch (const FormatException& e) { g_engErr = std::string("FormatException: ") + e.what(); return -107; }
     catch (const std::exception& e) { g_engErr = e.what(); return -100; }
 }
 ENG_API const char* eng_last_error() { return g_engErr.c_str(); }
@@ -533,6 +537,9 @@ ENG_API int eng_scene_add_sphere_instance(Scene* s, const int* ids, int n, const
 ENG_API int eng_scene_load_mesh_instance(Scene* s, const Float3* pos, int nPos, const MeshTri* tris, int nTris, const Float2* uv, int nUV, const MeshTriUV* triUVs,
                                          const int* triMat, const MaterialRecord* mats, int nMats, const Affine3x4* o2w) {
     return guard([&] { s->LoadMeshInstance(pos, nPos, tris, nTris, uv, nUV, triUVs, triMat, mats, nMats, o2w ? *o2w : AffineIdentity()); });
+}
+ENG_API int eng_scene_load_obj_instance(Scene* s, const char* path, const Affine3x4* o2w, float uniformScale) {
+    return guard([&] { if (!path) throw ArgumentNullException("objPath"); s->LoadObjInstance(path, o2w ? *o2w : AffineIdentity(), uniformScale); });
 }
 ENG_API int eng_scene_rebuild_tlas(Scene* s) { return guard([&] { s->RebuildTLAS(); }); }
 ENG_API int eng_scene_upload_all(Scene* s) { return guard([&] { s->UploadAll(); }); }

@@ -12,7 +12,9 @@
 //   Framebuffer       Engine/Framebuffer.cs:12-210 (DownloadToCpu / CpuColor / CpuDepth / CpuObjectId)
 //   RTRenderer        Engine/RTRenderer.cs:22-376  (RenderDirectToPbo -> rt_render)
 //
-// Out of scope: OBJ/MTL/TGA loading (LoadObjInstance takes decoded arrays here),
+//   MeshLoaderOBJ     Engine/MeshLoaderOBJ.cs:67-593 (OBJ / MTL / TGA; mesh_loader_obj.cpp)
+//
+// Out of scope: images the reference decodes through System.Drawing (PNG / JPEG ...),
 // OpenGL PBO interop, the fly-camera controller.
 #pragma once
 #include <stdexcept>
@@ -27,6 +29,10 @@ namespace Engine {
 struct ArgumentNullException : std::invalid_argument { using std::invalid_argument::invalid_argument; };
 struct ArgumentOutOfRangeException : std::out_of_range { using std::out_of_range::out_of_range; };
 struct InvalidOperationException : std::logic_error { using std::logic_error::logic_error; };
+struct FileNotFoundException : std::runtime_error { using std::runtime_error::runtime_error; };    // System.IO
+struct InvalidDataException : std::runtime_error { using std::runtime_error::runtime_error; };
+struct EndOfStreamException : std::runtime_error { using std::runtime_error::runtime_error; };
+struct FormatException : std::runtime_error { using std::runtime_error::runtime_error; };            // float.Parse / int.Parse
 struct RtNativeException : std::runtime_error {   // CudaException.ThrowIfFailed analogue (CudaGlInteropIndexBuffer.cs:56)
     int status;
     RtNativeException(int s, const std::string& m) : std::runtime_error(m), status(s) {}
@@ -58,6 +64,16 @@ struct Camera : RtCamera {
     void UpdateDerived(float aspectIn, float fovYRadIn);                                         // :184-191
 };
 
+// MeshLoaderOBJ.cs:21-42: what the OBJ / MTL / TGA loader hands to Scene.LoadObjInstance
+struct TextureSrc { std::string Path; int Width = 0, Height = 0; std::vector<unsigned char> BGRA; };   // straight alpha, rows top-down
+struct MeshHost {
+    std::vector<Float3> Positions; std::vector<MeshTri> Triangles; std::vector<Float2> Texcoords; std::vector<MeshTriUV> TriUVs;
+    std::vector<int> TriMaterialIndex; std::vector<MaterialRecord> Materials; std::vector<TextureSrc> Textures;
+};
+struct MeshLoaderOBJ {
+    static MeshHost Load(const std::string& path, float scale = 1.0f, bool flipWinding = true);   // MeshLoaderOBJ.cs:67-254
+};
+
 enum class RebuildPolicy { Auto, ForceRefit, ForceRebuild };   // BvhManager.cs:13-18
 
 class Scene {
@@ -72,6 +88,7 @@ public:
     void LoadMeshInstance(const Float3* positions, int nPositions, const MeshTri* tris, int nTris, const Float2* texcoords, int nTexcoords,
                           const MeshTriUV* triUVs, const int* triMaterialIndex, const MaterialRecord* materials, int nMaterials,
                           const Affine3x4& objectToWorld);
+    void LoadObjInstance(const std::string& objPath, const Affine3x4& objectToWorld, float uniformScale = 1.0f);   // Scene.cs:144-256 (mesh_loader_obj.cpp)
     void RebuildTLAS();                                                                          // Scene.cs:358-368
     void UploadAll();                                                                            // Scene.cs:258-279 -> rt_scene_upload
     void FillDesc(RtSceneDesc* d) const;                                                         // GetDeviceViews analogue (host views), Scene.cs:281-313

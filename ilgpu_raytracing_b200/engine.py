@@ -56,6 +56,7 @@ def lib() -> C.CDLL:
     l.eng_scene_add_sphere_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     l.eng_scene_load_mesh_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_int, C.c_void_p]
+    l.eng_scene_load_obj_instance.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_float]
     l.eng_scene_sort_ties.argtypes = [C.c_void_p]
     l.eng_scene_sort_ties.restype = C.c_long
     l.eng_scene_fill_desc.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
@@ -187,6 +188,11 @@ class Scene:
             raise ValueError("tris, tri_uvs and tri_mat must have the same length")
         m = L.affine_identity() if object_to_world is None else np.ascontiguousarray(object_to_world, L.AFFINE)
         _check(self._l.eng_scene_load_mesh_instance(self.h, _p(pos), len(pos), _p(tr), len(tr), _p(uv), len(uv), _p(tuv), _p(tm), _p(mats), len(mats), _p(m)))
+
+    def LoadObjInstance(self, obj_path: str, object_to_world=None, uniform_scale: float = 1.0):
+        """Scene.LoadObjInstance (Engine/Scene.cs:144-256): OBJ + MTL + TGA/BMP textures from disk (MeshLoaderOBJ.cs)."""
+        m = L.affine_identity() if object_to_world is None else np.ascontiguousarray(object_to_world, L.AFFINE)
+        _check(self._l.eng_scene_load_obj_instance(self.h, str(obj_path).encode(), _p(m), float(uniform_scale)))
 
     def RebuildTLAS(self):
         _check(self._l.eng_scene_rebuild_tlas(self.h))
