@@ -180,6 +180,9 @@ __device__ __forceinline__ void rt_fma2(float a0, float a1, float b, float c, fl
 #ifndef RT_USE_FFMA2
 #define RT_USE_FFMA2 1
 #endif
+#ifndef RT_PRIM_SLOTS
+#define RT_PRIM_SLOTS 2   // queued primitive groups per lane (1 or 2), see Traversal::tgroupB
+#endif
 RT_HD uint32_t rt_funnel_l1(uint32_t lo, uint32_t hi) {   // (hi << 1) | (lo >> 31)
 #if defined(__CUDA_ARCH__)
     return __funnelshift_l(lo, hi, 1);
@@ -203,6 +206,10 @@ struct Traversal {
     const uint32_t* lut;            // this ray's octant slice of the hit table
     uint2 ngroup, tgroup;
     uint32_t tvalid;                // valid24 of the node whose primitives are queued in tgroup
+#if RT_PRIM_SLOTS == 2
+    uint2 tgroupB;                  // a second queued primitive group: a lane that found primitives can take ONE more node step
+    uint32_t tvalidB;               // before its primitive tests run (the closest t it culls with is at most one group stale)
+#endif
     BestHit best;
     bool occluded, done;
 
@@ -218,6 +225,9 @@ struct Traversal {
         lut = host_hit_table() + octinv * 256u;
 #endif
         tvalid = 0u;
+#if RT_PRIM_SLOTS == 2
+        tgroupB = make_uint2(0u, 0u); tvalidB = 0u;
+#endif
         stack.sp = 0;
         ngroup = make_uint2(0u, 0x80000000u);   // "child 7^octinv of a virtual parent whose child block starts at node 0" = the root
         tgroup = make_uint2(0u, 0u);
@@ -225,14 +235,21 @@ struct Traversal {
 
     RT_HD bool has_prims() const { return tgroup.y != 0u; }
     RT_HD bool has_node_work() const { return ngroup.y > 0x00FFFFFFu; }
+#if RT_PRIM_SLOTS == 2
+    RT_HD bool can_node_step(const LaneStack&) const { return has_node_work() && tgroupB.y == 0u; }
+    RT_HD bool prims_pending() const { return (tgroup.y | tgroupB.y) != 0u; }
+#else
     RT_HD bool can_node_step(const LaneStack&) const { return has_node_work() && tgroup.y == 0u; }
+    RT_HD bool prims_pending() const { return tgroup.y != 0u; }
+#endif
 
-    // next node group from the stack, or done (selects only: every lane of the warp runs this together)
+    // next node group from the stack; done when there is neither node work nor a queued primitive left
+    // (selects only: every lane of the warp runs this together)
     RT_HD void advance(const DeviceScene&, LaneStack& stack) {
         const uint2 top = stack.load_below();
         const bool need = ngroup.y <= 0x00FFFFFFu;
         const bool empty = stack.sp == 0;
-        done = done || (need && empty);
+        done = done || (need && empty && !prims_pending());
         if (need && !empty) { ngroup = top; stack.sp--; }
     }
 
@@ -305,10 +322,18 @@ struct Traversal {
         const uint32_t hitmask = lut[mr];
         ngroup.x = n1.x;
         ngroup.y = (hitmask & pmask & 0xFF000000u) | (n0.w >> 24);
+#if RT_PRIM_SLOTS == 2
+        const uint32_t found = hitmask & n1.z & 0x00FFFFFFu;
+        const bool toA = tgroup.y == 0u;           // precondition: slot B is free
+        tgroupB.x = n1.y; tvalidB = n1.z; tgroupB.y = toA ? 0u : found;
+        if (toA) { tgroup.x = n1.y; tvalid = n1.z; tgroup.y = found; }
+        advance(sc, stack);
+#else
         tgroup.x = n1.y;
         tvalid = n1.z;
         tgroup.y = hitmask & n1.z & 0x00FFFFFFu;
         if (tgroup.y == 0u) advance(sc, stack);
+#endif
     }
 
     // precondition: !done, tgroup.y != 0
@@ -360,7 +385,12 @@ struct Traversal {
                 best.t = r.tW; best.tObj = r.tO; best.rank = f2u(q1.w); best.inst = (int)(meta & PRIM_INST_MASK); best.prim = pi; best.bu = r.bu; best.bv = r.bv;
             }
         }
+#if RT_PRIM_SLOTS == 2
+        if (tgroup.y == 0u) { tgroup = tgroupB; tvalid = tvalidB; tgroupB.y = 0u; }
+        advance(sc, stack);
+#else
         if (tgroup.y == 0u) advance(sc, stack);
+#endif
     }
 
     // one node and all of its primitives; returns true when the traversal is finished

@@ -69,6 +69,15 @@ __global__ void k_generate_primary(FrameConst fc, RayQueue q, int* countOut) {
 // Persistent threads: the grid is sized to the machine, every warp pulls RT_EXTEND_BATCH consecutive ray
 // indices per atomic and hands them to lanes as they go idle (ballot + popc rank), so a finished ray is
 // replaced at the next step instead of idling until the slowest lane of its batch is done.
+#ifndef RT_PHASE_STATS
+#define RT_PHASE_STATS 0   // 1 (tuning builds, tests/gpu_phase_stats.py): with RT_FLAG_COUNTERS, lane participation of the extend kernel's phases, printed to stderr per frame
+#endif
+#if RT_PHASE_STATS
+__device__ unsigned long long g_phase[32];
+#define PHASE_ADD(i, v) do { if (COUNT && lane == 0) ph[i] += (unsigned)(v); } while (0)   // v must not contain warp-synchronous calls
+#else
+#define PHASE_ADD(i, v) do { } while (0)
+#endif
 template <bool ANY_HIT, bool COUNT>
 __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend(ExtendArgs a) {
     // dynamic shared memory: hit table | traversal stacks [entries][RT_EXTEND_THREADS], entries = depth of this scene's wide
@@ -109,6 +118,9 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
     bool active = false, exhausted = false;
     int myRay = -1;
     int poolNext = 0, poolEnd = 0;   // warp-uniform
+#if RT_PHASE_STATS
+    unsigned long long ph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+#endif
 
     for (;;) {
         // ---- refill idle lanes straight from the queue (warp-uniform control flow) ----
@@ -138,11 +150,18 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
             if (take == nIdle) break;
         }
         if (__ballot_sync(FULL, active) == 0u) break;
+#if RT_PHASE_STATS
+        if (COUNT) { const int held = __popc(__ballot_sync(FULL, active)); PHASE_ADD(0, 1); PHASE_ADD(7, held); }
+#endif
 
         // ---- node phase: lanes without queued primitives advance by up to RT_NODE_STEPS wide nodes ----
 #pragma unroll
-        for (int ns = 0; ns < RT_NODE_STEPS; ns++)
+        for (int ns = 0; ns < RT_NODE_STEPS; ns++) {
+#if RT_PHASE_STATS
+            if (COUNT) { const int nl = __popc(__ballot_sync(FULL, active && !tr.done && tr.can_node_step(stack))); PHASE_ADD(1 + (ns > 0), nl); PHASE_ADD(3 + (ns > 0), nl > 0); }
+#endif
             if (active && !tr.done && tr.can_node_step(stack)) tr.node_step(a.sc, stack, &cnt);
+        }
         // ---- primitive phase, voted warp-wide: the exact intersectors are long and divergent, so run them only when
         //      enough lanes have a primitive queued (or nobody can do node work); lanes holding primitives wait ----
         const bool wantPrim = active && !tr.done && tr.has_prims();
@@ -150,6 +169,9 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         if (pm != 0u) {
             const unsigned nm = __ballot_sync(FULL, active && !tr.done && tr.can_node_step(stack));
             if (__popc(pm) >= RT_PRIM_VOTE || nm == 0u) {
+#if RT_PHASE_STATS
+                if (COUNT) { unsigned q = wantPrim ? (unsigned)__popc(tr.tgroup.y) : 0u; for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(FULL, q, o); const int np = __popc(pm); PHASE_ADD(5, 1); PHASE_ADD(6, np); PHASE_ADD(8, q); }
+#endif
                 if (wantPrim) tr.prim_step(a.sc, stack, &cnt);
             }
         }
@@ -166,6 +188,9 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
         unsigned nn = cnt.nodes, tt = cnt.tris, ss = cnt.spheres;
         for (int o = 16; o > 0; o >>= 1) { nn += __shfl_xor_sync(FULL, nn, o); tt += __shfl_xor_sync(FULL, tt, o); ss += __shfl_xor_sync(FULL, ss, o); }
         if (lane == 0) { atomicAdd(&a.stats->wideNodes, (unsigned long long)nn); atomicAdd(&a.stats->tris, (unsigned long long)tt); atomicAdd(&a.stats->spheres, (unsigned long long)ss); }
+#if RT_PHASE_STATS
+        if (lane == 0) for (int i = 0; i < 9; i++) atomicAdd(&g_phase[(ANY_HIT ? 16 : 0) + i], ph[i]);
+#endif
     }
 }
 
@@ -754,6 +779,20 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->evStop, st));
     CUDA_TRY(cudaMemcpyAsync(&c->hstats, c->dstats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
+#if RT_PHASE_STATS
+    if (count) {
+        unsigned long long h[32], z[32] = {0};
+        CUDA_TRY(cudaStreamSynchronize(st));
+        CUDA_TRY(cudaMemcpyFromSymbol(h, g_phase, sizeof(h)));
+        CUDA_TRY(cudaMemcpyToSymbol(g_phase, z, sizeof(z)));
+        for (int k = 0; k < 2; k++) {
+            const unsigned long long* p = h + 16 * k;
+            fprintf(stderr, "[phase %s] iters %llu  lanes holding a ray %.2f | node step 1: run in %.3f of iters, %.2f lanes; step 2: %.3f, %.2f lanes | prim phase: %.3f of iters, %.2f lanes, %.2f queued prims\n",
+                    k ? "anyhit " : "closest", p[0], (double)p[7] / p[0], (double)p[3] / p[0], (double)p[1] / (p[3] ? p[3] : 1), (double)p[4] / p[0], (double)p[2] / (p[4] ? p[4] : 1),
+                    (double)p[5] / p[0], (double)p[6] / (p[5] ? p[5] : 1), (double)p[8] / (p[5] ? p[5] : 1));
+        }
+    }
+#endif
     c->rendered = true;
     return RT_OK;
 }

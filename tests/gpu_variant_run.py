@@ -13,7 +13,7 @@ ctx = native.Context(0)
 ctx.scene_upload(sc.arrays())
 cam = oracle_camera("C3", W, H)
 out = {}
-for tag, spp, depth in (("C3", 1, 0), ("C4x8", 8, 8)):
+for tag, spp, depth in (("C3", 1, 0), ("C4x8", 8, 8), ("C4x32", 32, 8)):
     cfg = L.make_render_config(W, H, spp=spp, max_depth=depth, flags=L.RT_FLAG_KERNEL_TIMING)
     best = None
     for _ in range(4):
