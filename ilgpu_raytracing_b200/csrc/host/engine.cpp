@@ -458,6 +458,16 @@ void Framebuffer::DownloadToCpu(int slot) {   // Framebuffer.cs:148-156
     check(rt_download(_native, RT_BUF_DEPTH, _cpuDepth.data(), nb));
     check(rt_download(_native, RT_BUF_OBJID, _cpuObjectId.data(), nb));
 }
+void Framebuffer::DownloadToCpu(int slot, int* color, float* depth, int* objectId, size_t n) {
+    if (slot != 0) throw ArgumentOutOfRangeException("slot");
+    if (!color || !depth || !objectId) throw ArgumentNullException("destination");
+    size_t nb = 0;
+    check(rt_buffer_bytes(_native, RT_BUF_RGBA8, &nb));
+    if (nb / 4 != n) throw ArgumentOutOfRangeException("n");
+    check(rt_download(_native, RT_BUF_RGBA8, color, nb));
+    check(rt_download(_native, RT_BUF_DEPTH, depth, nb));
+    check(rt_download(_native, RT_BUF_OBJID, objectId, nb));
+}
 
 // ======================================================================================================= RTRenderer
 RTRenderer::RTRenderer(int deviceIndex, int windowWidth, int windowHeight) {   // RTRenderer.cs:63-92
@@ -579,7 +589,9 @@ ENG_API int eng_renderer_render_direct_to_pbo(RTRenderer* r, void* pbo, int w, i
 ENG_API void eng_renderer_last_config(RTRenderer* r, RtRenderConfig* out) { *out = r->LastConfig(); }
 ENG_API int eng_framebuffer_download_to_cpu(RTRenderer* r, int slot, int* color, float* depth, int* objId, size_t n) {
     return guard([&] {
-        Framebuffer& f = r->Frame(); f.DownloadToCpu(slot);
+        Framebuffer& f = r->Frame();
+        if (color && depth && objId) { f.DownloadToCpu(slot, color, depth, objId, n); return; }
+        f.DownloadToCpu(slot);
         if (f.CpuColor().size() != n) throw ArgumentOutOfRangeException("n");
         if (color) memcpy(color, f.CpuColor().data(), n * 4);
         if (depth) memcpy(depth, f.CpuDepth().data(), n * 4);

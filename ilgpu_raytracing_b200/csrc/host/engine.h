@@ -136,6 +136,8 @@ class Framebuffer {   // Framebuffer.cs:12-210 (device buffers are owned by the 
 public:
     explicit Framebuffer(rt_ctx* native) : _native(native) {}
     void DownloadToCpu(int slot = 0);                                                            // :148-156
+    // the same read-back straight into caller-owned arrays of n pixels each (page-locked ones are filled by DMA without a staging copy)
+    void DownloadToCpu(int slot, int* color, float* depth, int* objectId, size_t n);
     const std::vector<int>& CpuColor() const { return _cpuColor; }                              // :158
     const std::vector<float>& CpuDepth() const { return _cpuDepth; }                            // :159
     const std::vector<int>& CpuObjectId() const { return _cpuObjectId; }                        // :160
