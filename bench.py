@@ -333,12 +333,12 @@ def main():
     achieved = alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
     # DRAM traffic of the same kernels from the committed ncu capture of this workload (profiles/): per launch, like `achieved`
     traffic = issue = None
-    tp = os.path.join(ROOT, "profiles", "r01_extend_traffic_c4.json")
+    tp = os.path.join(ROOT, "profiles", "r01b_extend_traffic_c4.json")
     if name == "C4" and not args.spp and world == 1 and os.path.exists(tp):
         t = json.load(open(tp))
         traffic = t["dram_bytes_per_launch"]
         issue = {"warp_instructions_per_ray": t["warp_instructions"] / max(1, n_rays), "ipc_per_smsp": t["warp_instructions"] / (t["sum_duration_ms"] * 1e-3 * 1.965e9 * 148 * 4),
-                 "source": "profiles/r01_extend_traffic_c4.json (ncu, all 33 extend launches of one C4 frame)"}
+                 "source": "profiles/r01b_extend_traffic_c4.json (ncu, all %d extend launches of one C4 frame)" % t["launches"]}
     roofline = {"bound": "hbm", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "peak_source": pk["source"], "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes / n_ext, "launches_per_step": n_ext, "avg_launch_ms": trace_ms / n_ext,

@@ -457,6 +457,12 @@ static int size_extend_launch(rt_ctx* c, int entries) {
     entries = std::max(2, std::min(entries, RT_STACK_ENTRIES));
     c->stackEntries = entries;
     c->extendSmem = (size_t)RT_HIT_TABLE_WORDS * sizeof(uint32_t) + (size_t)entries * RT_EXTEND_THREADS * sizeof(uint2);
+    if (c->extendSmem > 48u * 1024u) {   // big blocks (tuning builds) need the opt-in
+        CUDA_TRY(cudaFuncSetAttribute(k_extend<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_extend<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
+    }
     int perSm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
     if (perSm < 1) perSm = 1;
