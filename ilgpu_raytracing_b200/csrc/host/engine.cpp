@@ -227,12 +227,14 @@ Scene::Scene(rt_ctx* native) : _native(native) {}
 
 void Scene::Reset() { Clear(); }
 void Scene::Clear() {   // Scene.cs:85-96
+    _topologyVersion++;
     hTLASNodes.clear(); hTLASInstanceIndices.clear(); hInstances.clear(); hBLASNodes.clear(); hSpherePrimIndices.clear(); hSpheres.clear();
     hTriPrimIndices.clear(); hMeshPositions.clear(); hMeshTris.clear(); hMeshTexcoords.clear(); hMeshTriUVs.clear(); hTriMaterialIndex.clear();
     hMaterials.clear(); hTexInfos.clear(); hTexels.clear();
     _sortTies = 0;
 }
 int Scene::AddTexture(int width, int height, const RGBA32* texels) {
+    _topologyVersion++;
     if (!texels) throw ArgumentNullException("texels");
     if (width <= 0 || height <= 0) throw ArgumentOutOfRangeException("texture size");
     TexInfo ti; ti.Offset = (int)hTexels.size(); ti.Width = width; ti.Height = height;
@@ -240,7 +242,7 @@ int Scene::AddTexture(int width, int height, const RGBA32* texels) {
     hTexInfos.push_back(ti);
     return (int)hTexInfos.size() - 1;
 }
-int Scene::AddSphere(const Sphere& s) { int id = (int)hSpheres.size(); hSpheres.push_back(s); hSpherePrimIndices.push_back(id); return id; }   // :315-321
+int Scene::AddSphere(const Sphere& s) { _topologyVersion++; int id = (int)hSpheres.size(); hSpheres.push_back(s); hSpherePrimIndices.push_back(id); return id; }   // :315-321
 
 int Scene::BuildBLASNodeRecursive(int* idx, int start, int count, const Float3* bminPre, const Float3* bmaxPre, int parentSkip, bool spheres) {   // Scene.cs:405-467
     std::vector<int>& primIdx = spheres ? hSpherePrimIndices : hTriPrimIndices;
@@ -326,7 +328,7 @@ InstanceRecord Scene::BuildSphereInstance(const int* sphereIds, int n, const Aff
     inst.objectToWorld = objectToWorld; inst.worldToObject = worldToObject; inst.uniformScale = uniScale; inst.worldBoundsMin = wmin; inst.worldBoundsMax = wmax;
     return inst;
 }
-void Scene::AddSphereInstance(const int* sphereIds, int n, const Affine3x4& objectToWorld) { hInstances.push_back(BuildSphereInstance(sphereIds, n, objectToWorld)); }
+void Scene::AddSphereInstance(const int* sphereIds, int n, const Affine3x4& objectToWorld) { _topologyVersion++; hInstances.push_back(BuildSphereInstance(sphereIds, n, objectToWorld)); }
 
 int Scene::BuildTLASNodeRecursive(int* idx, int start, int count, int parentSkip) {   // Scene.cs:469-510
     int nodeIndex = (int)hTLASNodes.size();
@@ -353,6 +355,7 @@ int Scene::BuildTLASNodeRecursive(int* idx, int start, int count, int parentSkip
     return nodeIndex;
 }
 void Scene::RebuildTLAS() {   // Scene.cs:358-368
+    _topologyVersion++;
     int n = (int)hInstances.size();
     hTLASInstanceIndices.resize((size_t)n);
     for (int i = 0; i < n; i++) hTLASInstanceIndices[i] = i;
@@ -362,6 +365,7 @@ void Scene::RebuildTLAS() {   // Scene.cs:358-368
 void Scene::LoadMeshInstance(const Float3* positions, int nPositions, const MeshTri* tris, int nTris, const Float2* texcoords, int nTexcoords,
                              const MeshTriUV* triUVs, const int* triMaterialIndex, const MaterialRecord* materials, int nMaterials, const Affine3x4& objectToWorld) {   // Scene.cs:144-256
     if (!positions || !tris || !texcoords || !triUVs || !materials) throw ArgumentNullException("mesh arrays");
+    _topologyVersion++;
     if (nPositions <= 0 || nTris <= 0 || nTexcoords <= 0 || nMaterials <= 0) throw ArgumentOutOfRangeException("mesh array length");
     if (!hMeshTris.empty()) throw InvalidOperationException("the reference supports one mesh per scene: a second LoadObjInstance breaks its primIdx identity assumption (Scene.cs:384,401,439-440)");
     int baseVertex = (int)hMeshPositions.size(), baseTri = (int)hMeshTris.size(), baseUV = (int)hMeshTexcoords.size(), baseMat = (int)hMaterials.size();
@@ -398,6 +402,7 @@ void Scene::LoadMeshInstance(const Float3* positions, int nPositions, const Mesh
     RebuildTLAS();
 }
 void Scene::BuildDefaultScene() {   // Scene.cs:83-142
+    _topologyVersion++;
     Clear();
     auto checker = [&](int w, int h, int step, RGBA32 c0, RGBA32 c1) {   // AddCheckerTexture :98-109
         std::vector<RGBA32> px((size_t)w * h);
@@ -445,6 +450,20 @@ void Scene::UploadAll() {   // Scene.cs:258-279
     if (!_native) throw InvalidOperationException("Scene has no native context (host-only scene)");
     RtSceneDesc d; FillDesc(&d);
     check(rt_scene_upload(_native, &d));
+    _uploadedVersion = _topologyVersion;
+}
+// New vertex positions for the loaded mesh, same count and triangles (the reference has no such entry point: its meshes never move;
+// this is what makes RebuildPolicy.ForceRefit mean something, BvhManager.cs:13-27)
+void Scene::SetMeshPositions(const Float3* positions, int nPositions) {
+    if (!positions) throw ArgumentNullException("positions");
+    if ((size_t)nPositions != hMeshPositions.size()) throw ArgumentOutOfRangeException("positions: the vertex count must stay the same");
+    std::copy(positions, positions + nPositions, hMeshPositions.begin());
+}
+bool Scene::CanRefit() const { return _native && _uploadedVersion == _topologyVersion && !hMeshPositions.empty(); }
+void Scene::RefitUpload() {
+    if (!_native) throw InvalidOperationException("Scene has no native context (host-only scene)");
+    if (!CanRefit()) throw InvalidOperationException("refit needs the topology of the last UploadAll");
+    check(rt_scene_refit(_native, hMeshPositions.data(), (int64_t)hMeshPositions.size()));
 }
 
 // ======================================================================================================= Framebuffer
@@ -576,6 +595,14 @@ ENG_API void eng_renderer_free(RTRenderer* r) { delete r; }
 ENG_API rt_ctx* eng_renderer_native(RTRenderer* r) { return r->Native(); }
 ENG_API Scene* eng_renderer_scene(RTRenderer* r) { return &r->Scenes().GetScene(); }
 ENG_API int eng_renderer_commit(RTRenderer* r) { return guard([&] { r->Scenes().Commit(RebuildPolicy::Auto); }); }
+ENG_API int eng_renderer_commit_policy(RTRenderer* r, int policy) {
+    return guard([&] {
+        if (policy < 0 || policy > 2) throw ArgumentOutOfRangeException("policy");
+        r->Scenes().Commit((RebuildPolicy)policy);
+    });
+}
+ENG_API int eng_scene_set_mesh_positions(Scene* s, const Float3* pos, int n) { return guard([&] { s->SetMeshPositions(pos, n); }); }
+ENG_API int eng_scene_can_refit(Scene* s) { return s->CanRefit() ? 1 : 0; }
 ENG_API void eng_renderer_get_camera(RTRenderer* r, RtCamera* out) { memcpy(out, &r->Cam(), sizeof(RtCamera)); }
 ENG_API void eng_renderer_set_camera(RTRenderer* r, const RtCamera* in) { memcpy(static_cast<RtCamera*>(&r->Cam()), in, sizeof(RtCamera)); }
 ENG_API void eng_renderer_set_sun_params(RTRenderer* r, float speed, float elevation) { r->SetSunParams(speed, elevation); }

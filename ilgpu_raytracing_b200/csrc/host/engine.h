@@ -91,6 +91,9 @@ public:
     void LoadObjInstance(const std::string& objPath, const Affine3x4& objectToWorld, float uniformScale = 1.0f);   // Scene.cs:144-256 (mesh_loader_obj.cpp)
     void RebuildTLAS();                                                                          // Scene.cs:358-368
     void UploadAll();                                                                            // Scene.cs:258-279 -> rt_scene_upload
+    void SetMeshPositions(const Float3* positions, int nPositions);                              // extension: moved vertices, same topology
+    bool CanRefit() const;                                                                       // nothing but positions changed since UploadAll
+    void RefitUpload();                                                                          // -> rt_scene_refit (device-side refit of the wide BVH)
     void FillDesc(RtSceneDesc* d) const;                                                         // GetDeviceViews analogue (host views), Scene.cs:281-313
     long SortTies() const { return _sortTies; }
 
@@ -104,6 +107,7 @@ public:
 private:
     rt_ctx* _native;
     long _sortTies = 0;
+    long _topologyVersion = 0, _uploadedVersion = -1;   // bumped by everything that changes more than vertex positions
     std::vector<float> _triKey[3];   // centroid keys per axis, CenterOfTriangle (Scene.cs:607-614)
     void Clear();
     InstanceRecord BuildSphereInstance(const int* sphereIds, int n, const Affine3x4& objectToWorld);
@@ -116,7 +120,9 @@ private:
 class BvhManager {   // BvhManager.cs:11-51
 public:
     explicit BvhManager(Scene* scene) : _scene(scene) { if (!scene) throw ArgumentNullException("scene"); }
-    void BuildOrRefit(RebuildPolicy) { _scene->UploadAll(); }   // :27 (the policy is ignored by the reference too)
+    // :27.  The reference ignores the policy and always re-uploads; here ForceRefit refits the uploaded wide BVH on the device
+    // when only vertex positions changed (Scene::SetMeshPositions), and falls back to the full upload otherwise.
+    void BuildOrRefit(RebuildPolicy p) { if (p == RebuildPolicy::ForceRefit && _scene->CanRefit()) _scene->RefitUpload(); else _scene->UploadAll(); }
 private:
     Scene* _scene;
 };

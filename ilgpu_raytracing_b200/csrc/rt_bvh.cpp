@@ -125,7 +125,9 @@ inline float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 }   // namespace
 
 bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
-    out.nodes.clear(); out.prims.clear(); out.stats = HostBvhStats();
+    out.nodes.clear(); out.prims.clear(); out.levelStart.clear(); out.stats = HostBvhStats();
+    out.instBoxXf.assign((size_t)std::max<int64_t>(0, d.nInstances) * 12, 0.0);
+    for (int64_t i = 0; i < d.nInstances; i++) { out.instBoxXf[(size_t)i * 12 + 0] = 1.0; out.instBoxXf[(size_t)i * 12 + 5] = 1.0; out.instBoxXf[(size_t)i * 12 + 10] = 1.0; }
     Builder B;
 
     // ---- 1. enumerate (instance, primitive) pairs in the reference's visiting order --------------------------------
@@ -157,6 +159,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
         if (ir.uniformScale > out.stats.maxInstanceScale) out.stats.maxInstanceScale = ir.uniformScale;
         double w2oInv[12];
         if (!ident && !invert_affine(ir.worldToObject, w2oInv)) { err = "instance worldToObject is singular"; return false; }
+        if (!ident) for (int k = 0; k < 12; k++) out.instBoxXf[(size_t)ii * 12 + k] = w2oInv[k];
         const bool sph = ir.type == RT_BLAS_SPHERESET;
         if (!sph && ir.type != RT_BLAS_TRIMESH) { err = "instance: unknown BlasType"; return false; }
         int blasStart = ir.blasRoot, blasEnd = ir.blasRoot + ir.blasNodeCount;
@@ -379,6 +382,8 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
         wn.n3 = make_uint4(pw[1][0], pw[1][1], pw[1][2], pw[1][3]);
         wn.n4 = make_uint4(pw[2][0], pw[2][1], pw[2][2], pw[2][3]);
     }
+    for (size_t i = 0; i < depthOf.size(); i++) if (i == 0 || depthOf[i] != depthOf[i - 1]) out.levelStart.push_back((int)i);   // breadth-first: depths never decrease
+    out.levelStart.push_back((int)out.nodes.size());
     out.stats.nWideNodes = (int64_t)out.nodes.size();
     out.stats.maxDepth = std::max(1, maxDepthSeen);
     for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = B.b2[0].box.lo[a]; out.stats.sceneHi[a] = B.b2[0].box.hi[a]; }

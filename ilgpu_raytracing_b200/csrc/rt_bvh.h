@@ -16,8 +16,10 @@ struct HostBvhStats {
 };
 
 struct HostBvh {
-    std::vector<WideNode> nodes;   // nodes[0] is the root
+    std::vector<WideNode> nodes;   // nodes[0] is the root; breadth-first, so every level is one contiguous index range
     std::vector<PrimRec> prims;    // leaf order
+    std::vector<int> levelStart;   // levelStart[l] .. levelStart[l + 1] = the nodes of depth l + 1 (for the device-side refit)
+    std::vector<double> instBoxXf; // per instance: the 3x4 object-to-world transform its primitive boxes were built with (identity for identity instances)
     HostBvhStats stats;
 };
 

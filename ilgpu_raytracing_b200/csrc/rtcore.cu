@@ -353,6 +353,108 @@ __global__ void k_deinterleave(const float4* payload, const int* pixelMap, int n
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+// ------------------------------------------------------------------------------------------------ refit
+// BvhManager.BuildOrRefit(RebuildPolicy.ForceRefit) (BvhManager.cs:13-27) made real: new vertex positions for the SAME mesh
+// topology.  The wide BVH keeps its shape; the device rewrites the triangle records, recomputes every primitive box and then
+// the child boxes / quantisation frames of the wide nodes level by level from the leaves up - the formulas of the host
+// builder (rt_bvh.cpp, sections 2 and 4), so a refitted tree is exactly as conservative as a freshly built one.
+__global__ void k_refit_prims(PrimRec* prims, int nPrims, const RtFloat3* pos, const RtMeshTri* tris, const double* instXf, float4* primBox, unsigned* sceneAbsBits) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float m = 0.0f;
+    if (i < nPrims) {
+        PrimRec r = prims[i];
+        const uint32_t meta = __float_as_uint(r.q2.w);
+        float lo[3], hi[3];
+        if (meta & PRIM_SPHERE) {
+            const float rad = fabsf(r.q1.x);
+            lo[0] = r.q0.x - rad; lo[1] = r.q0.y - rad; lo[2] = r.q0.z - rad; hi[0] = r.q0.x + rad; hi[1] = r.q0.y + rad; hi[2] = r.q0.z + rad;
+        } else {
+            const RtMeshTri t = tris[(int)__float_as_uint(r.q0.w)];
+            const RtFloat3 v0 = pos[t.i0], v1 = pos[t.i1], v2 = pos[t.i2];
+            r.q0.x = v0.X; r.q0.y = v0.Y; r.q0.z = v0.Z; r.q1.x = v1.X; r.q1.y = v1.Y; r.q1.z = v1.Z; r.q2.x = v2.X; r.q2.y = v2.Y; r.q2.z = v2.Z;
+            prims[i] = r;
+            lo[0] = fminf(v0.X, fminf(v1.X, v2.X)); lo[1] = fminf(v0.Y, fminf(v1.Y, v2.Y)); lo[2] = fminf(v0.Z, fminf(v1.Z, v2.Z));
+            hi[0] = fmaxf(v0.X, fmaxf(v1.X, v2.X)); hi[1] = fmaxf(v0.Y, fmaxf(v1.Y, v2.Y)); hi[2] = fmaxf(v0.Z, fmaxf(v1.Z, v2.Z));
+        }
+        if (meta & PRIM_XFORM) {   // world box of the object-space box, as the builder takes it (8 corners, double)
+            const double* x = instXf + (size_t)(meta & PRIM_INST_MASK) * 12;
+            float wl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, wh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+            for (int c = 0; c < 8; c++) {
+                const double p0 = (c & 1) ? hi[0] : lo[0], p1 = (c & 2) ? hi[1] : lo[1], p2 = (c & 4) ? hi[2] : lo[2];
+                for (int a = 0; a < 3; a++) { const float w = (float)(x[a * 4] * p0 + x[a * 4 + 1] * p1 + x[a * 4 + 2] * p2 + x[a * 4 + 3]); wl[a] = fminf(wl[a], w); wh[a] = fmaxf(wh[a], w); }
+            }
+            for (int a = 0; a < 3; a++) { lo[a] = wl[a]; hi[a] = wh[a]; }
+        }
+        primBox[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        primBox[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], (meta & PRIM_XFORM) ? 1.0f : 0.0f);
+        for (int a = 0; a < 3; a++) m = fmaxf(m, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31u) == 0u) atomicMax(sceneAbsBits, __float_as_uint(m));   // non-negative floats order like their bit patterns
+}
+__global__ void k_refit_nodes(WideNode* nodes, int first, int last, const float4* primBox, float4* nodeBox, const unsigned* sceneAbsBits) {
+    const int n = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= last) return;
+    const float sceneAbs = __uint_as_float(*sceneAbsBits);
+    WideNode wn = nodes[n];
+    const uint32_t imask = wn.n0.w >> 24, valid24 = wn.n1.z;
+    float clo[8][3], chi[8][3]; bool used[8];
+    float nlo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, nhi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int s = 0; s < 8; s++) {
+        used[s] = false;
+        for (int a = 0; a < 3; a++) { clo[s][a] = 3.4e38f; chi[s][a] = -3.4e38f; }
+        if ((imask >> s) & 1u) {
+            const int child = (int)wn.n1.x + __popc(imask & ((1u << s) - 1u));
+            const float4 l = nodeBox[2 * child], h = nodeBox[2 * child + 1];
+            clo[s][0] = l.x; clo[s][1] = l.y; clo[s][2] = l.z; chi[s][0] = h.x; chi[s][1] = h.y; chi[s][2] = h.z;
+            used[s] = true;
+        } else {
+            const uint32_t field = (valid24 >> (3 * s)) & 7u;
+            if (field == 0u) continue;
+            const int cnt = __popc(field), start = (int)wn.n1.y + __popc(valid24 & ((1u << (3 * s)) - 1u));
+            for (int k = 0; k < cnt; k++) {
+                const float4 l = primBox[2 * (start + k)], h = primBox[2 * (start + k) + 1];
+                const float lo3[3] = {l.x, l.y, l.z}, hi3[3] = {h.x, h.y, h.z};
+                for (int a = 0; a < 3; a++) {   // conservative padding, rt_bvh.cpp section 2
+                    const float mag = fmaxf(fabsf(lo3[a]), fabsf(hi3[a]));
+                    const float pad = 2e-6f * sceneAbs + (h.w != 0.0f ? 2e-5f : 2e-6f) * mag + 1e-30f;
+                    clo[s][a] = fminf(clo[s][a], lo3[a] - pad); chi[s][a] = fmaxf(chi[s][a], hi3[a] + pad);
+                }
+            }
+            used[s] = true;
+        }
+        for (int a = 0; a < 3; a++) { nlo[a] = fminf(nlo[a], clo[s][a]); nhi[a] = fmaxf(nhi[a], chi[s][a]); }
+    }
+    nodeBox[2 * n] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
+    nodeBox[2 * n + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
+    // quantisation frame and planes, rt_bvh.cpp section 4
+    uint32_t eb[3]; double scale[3]; float pf[3];
+    for (int a = 0; a < 3; a++) {
+        const double ext = (double)nhi[a] - (double)nlo[a];
+        int e = -126;
+        if (ext > 0.0) { e = ilogb(ext / 252.0); if (ldexp(1.0, e) < ext / 252.0) e++; while (ext / ldexp(1.0, e) > 252.0) e++; }
+        e = max(-126, min(100, e));
+        eb[a] = (uint32_t)(e + 127); scale[a] = ldexp(1.0, e);
+        pf[a] = (float)((double)nlo[a] - scale[a]);
+        if ((double)pf[a] > (double)nlo[a]) pf[a] = nextafterf(pf[a], -INFINITY);
+    }
+    uint32_t pw[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+    for (int s = 0; s < 8; s++)
+        for (int a = 0; a < 3; a++) {
+            uint32_t ql = 255u, qh = 0u;
+            if (used[s]) {
+                const double l = floor(((double)clo[s][a] - (double)pf[a]) / scale[a] - 0.01), h = ceil(((double)chi[s][a] - (double)pf[a]) / scale[a] + 0.01);
+                ql = (uint32_t)fmax(0.0, fmin(255.0, l)); qh = (uint32_t)fmax(0.0, fmin(255.0, h));
+            }
+            pw[a][s >> 1] |= (ql | (qh << 8)) << (16 * (s & 1));   // word k of an axis = { qlo[2k], qhi[2k], qlo[2k+1], qhi[2k+1] }
+        }
+    wn.n0 = make_uint4(__float_as_uint(pf[0]), __float_as_uint(pf[1]), __float_as_uint(pf[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
+    wn.n2 = make_uint4(pw[0][0], pw[0][1], pw[0][2], pw[0][3]);
+    wn.n3 = make_uint4(pw[1][0], pw[1][1], pw[1][2], pw[1][3]);
+    wn.n4 = make_uint4(pw[2][0], pw[2][1], pw[2][2], pw[2][3]);
+    nodes[n] = wn;
+}
+
 static thread_local std::string g_lastError;
 static int fail(int code, const std::string& msg) { g_lastError = msg; return code; }
 #define CUDA_TRY(expr)                                                                                                 \
@@ -387,6 +489,10 @@ struct rt_ctx {
     DevBuf<RtInstanceRecord> instances; DevBuf<RtSphere> spheres;
     DevBuf<RtFloat2> texcoords; DevBuf<RtMeshTriUV> triUVs; DevBuf<int32_t> triMat; DevBuf<RtMaterialRecord> materials;
     DevBuf<RtRGBA32> texels; DevBuf<RtTexInfo> texInfos;
+    // refit (rt_scene_refit): the mesh topology, the level ranges of the breadth-first wide BVH, per-instance box transforms, scratch
+    DevBuf<RtMeshTri> meshTris; int64_t nMeshPositions = 0, nMeshTris = 0;
+    std::vector<int> levelStart; DevBuf<double> instBoxXf;
+    DevBuf<RtFloat3> refitPos; DevBuf<float4> refitPrimBox, refitNodeBox; DevBuf<unsigned> refitAbs;
     DeviceScene ds;
     HostBvhStats bvhStats; size_t bvhBytes = 0;
 
@@ -576,12 +682,40 @@ RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
     CUDA_TRY(upload_or_one(c->texInfos, d->texInfos, d->nTexInfos, st, &ds.nTexInfos)); ds.texInfos = c->texInfos.p;
     ds.triMaterials = 0;
     ds.tFarScale = bvh.stats.maxInstanceScale;
+    CUDA_TRY(upload_or_one(c->meshTris, d->meshTris, d->nMeshTris, st, nullptr));
+    CUDA_TRY(upload_or_one(c->instBoxXf, bvh.instBoxXf.data(), (int64_t)bvh.instBoxXf.size(), st, nullptr));
+    c->nMeshPositions = d->nMeshPositions; c->nMeshTris = d->nMeshTris; c->levelStart = bvh.levelStart;
     CUDA_TRY(cudaStreamSynchronize(st));   // host arrays are only borrowed for the duration of the call
     const int rcSize = size_extend_launch(c, bvh.stats.maxDepth + 1);   // a node step pushes at most one entry per level
     if (rcSize != RT_OK) return rcSize;
     c->bvhStats = bvh.stats;
     c->bvhBytes = bvh.nodes.size() * sizeof(WideNode) + bvh.prims.size() * sizeof(PrimRec);
     c->hasScene = true;
+    return RT_OK;
+}
+
+RT_API int rt_scene_refit(rt_ctx* c, const RtFloat3* meshPositions, int64_t nMeshPositions) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_refit: ctx is null");
+    if (!c->hasScene) return fail(RT_ERR_INVALID_STATE, "rt_scene_refit: no scene uploaded yet (rt_scene_upload)");
+    if (nMeshPositions != c->nMeshPositions) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_refit: the vertex count differs from the uploaded mesh (a refit keeps the topology; use rt_scene_upload)");
+    if (nMeshPositions > 0 && !meshPositions) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_refit: null array with non-zero length");
+    for (int64_t i = 0; i < nMeshPositions; i++)
+        if (!std::isfinite(meshPositions[i].X) || !std::isfinite(meshPositions[i].Y) || !std::isfinite(meshPositions[i].Z)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_refit: non-finite vertex position");
+    const int nPrims = c->ds.nPrims, nNodes = c->ds.nNodes;
+    if (nPrims <= 0 || nNodes <= 0) return RT_OK;   // empty scene: nothing to refit
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;   // stream order: frames already queued still see the old geometry
+    CUDA_TRY(upload_or_one(c->refitPos, meshPositions, nMeshPositions, st, nullptr));
+    CUDA_TRY(c->refitPrimBox.ensure(2 * (size_t)nPrims)); CUDA_TRY(c->refitNodeBox.ensure(2 * (size_t)nNodes)); CUDA_TRY(c->refitAbs.ensure(1));
+    CUDA_TRY(cudaMemsetAsync(c->refitAbs.p, 0, sizeof(unsigned), st));
+    WideNode* nodes = const_cast<WideNode*>(c->ds.nodes); PrimRec* prims = const_cast<PrimRec*>(c->ds.prims);
+    k_refit_prims<<<(nPrims + 255) / 256, 256, 0, st>>>(prims, nPrims, c->refitPos.p, c->meshTris.p, c->instBoxXf.p, c->refitPrimBox.p, c->refitAbs.p);
+    for (int l = (int)c->levelStart.size() - 2; l >= 0; l--) {   // leaves first
+        const int first = c->levelStart[l], last = c->levelStart[l + 1];
+        if (last > first) k_refit_nodes<<<(last - first + 127) / 128, 128, 0, st>>>(nodes, first, last, c->refitPrimBox.p, c->refitNodeBox.p, c->refitAbs.p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(st));   // the host array is only borrowed for the duration of the call
     return RT_OK;
 }
 

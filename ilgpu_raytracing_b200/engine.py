@@ -57,6 +57,9 @@ def lib() -> C.CDLL:
     l.eng_scene_load_mesh_instance.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_int, C.c_void_p]
     l.eng_scene_load_obj_instance.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_float]
+    l.eng_scene_set_mesh_positions.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    l.eng_scene_can_refit.argtypes = [C.c_void_p]
+    l.eng_renderer_commit_policy.argtypes = [C.c_void_p, C.c_int]
     l.eng_scene_sort_ties.argtypes = [C.c_void_p]
     l.eng_scene_sort_ties.restype = C.c_long
     l.eng_scene_fill_desc.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
@@ -194,6 +197,14 @@ class Scene:
         m = L.affine_identity() if object_to_world is None else np.ascontiguousarray(object_to_world, L.AFFINE)
         _check(self._l.eng_scene_load_obj_instance(self.h, str(obj_path).encode(), _p(m), float(uniform_scale)))
 
+    def SetMeshPositions(self, positions):
+        """Moved vertices for the loaded mesh (same count, same triangles); Commit(FORCE_REFIT) then refits instead of rebuilding."""
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        _check(self._l.eng_scene_set_mesh_positions(self.h, _p(p), len(p)))
+
+    def CanRefit(self) -> bool:
+        return bool(self._l.eng_scene_can_refit(self.h))
+
     def RebuildTLAS(self):
         _check(self._l.eng_scene_rebuild_tlas(self.h))
 
@@ -272,9 +283,12 @@ class RTRenderer:
             self._native_view = v
         return self._native_view
 
-    def Commit(self):
-        """SceneManager.Commit(RebuildPolicy.Auto) -> BvhManager.BuildOrRefit -> Scene.UploadAll."""
-        _check(self._l.eng_renderer_commit(self.h))
+    AUTO, FORCE_REFIT, FORCE_REBUILD = 0, 1, 2   # RebuildPolicy, Engine/BvhManager.cs:13-18
+
+    def Commit(self, policy: int = 0):
+        """SceneManager.Commit(policy) -> BvhManager.BuildOrRefit: Scene.UploadAll, or the device-side refit for FORCE_REFIT when only
+        vertex positions changed since the last upload."""
+        _check(self._l.eng_renderer_commit_policy(self.h, int(policy)))
 
     def SetSunParams(self, speed_rad_per_sec: float, elevation_rad: float):
         self._l.eng_renderer_set_sun_params(self.h, speed_rad_per_sec, elevation_rad)

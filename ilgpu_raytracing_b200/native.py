@@ -18,7 +18,7 @@ _LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b
 
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
-           "rt_deinterleave_tiles", "rt_get_stats", "rt_present"]
+           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit"]
 
 
 class RtError(RuntimeError):
@@ -44,6 +44,7 @@ def lib() -> C.CDLL:
     l.rt_destroy.argtypes = [C.c_void_p]
     l.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     l.rt_scene_upload.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
+    l.rt_scene_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     l.rt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig)]
     l.rt_sync.argtypes = [C.c_void_p]
     l.rt_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -101,6 +102,11 @@ class Context:
         desc, keep = L.scene_desc_from_arrays(arrays)
         check(self._l.rt_scene_upload(self.h, C.byref(desc)))
         del keep
+
+    def scene_refit(self, positions: np.ndarray):
+        """New vertex positions for the uploaded mesh topology (BvhManager.BuildOrRefit(ForceRefit)): device-side refit of the wide BVH."""
+        p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        check(self._l.rt_scene_refit(self.h, p.ctypes.data, len(p)))
 
     def scene_upload_desc(self, desc: L.RtSceneDesc):
         check(self._l.rt_scene_upload(self.h, C.byref(desc)))

@@ -270,6 +270,11 @@ RT_API int rt_set_stream(rt_ctx* ctx, void* cudaStream);
  *      Copies the arrays, derives the reference's traversal order from the BVH2
  *      arrays (tie-break ranks) and builds the compressed 8-wide BVH. ---- */
 RT_API int rt_scene_upload(rt_ctx* ctx, const RtSceneDesc* scene);
+/* BvhManager.BuildOrRefit(RebuildPolicy.ForceRefit) (Engine/BvhManager.cs:13-27; the reference accepts the policy and
+ * ignores it): new mesh vertex positions for the topology of the last rt_scene_upload (same count, same triangles).
+ * The triangle records and the wide BVH are refitted on the device, bottom-up; tie-break ranks, materials, spheres and
+ * instances are kept.  RT_ERR_INVALID_ARGUMENT when the count differs, RT_ERR_INVALID_STATE without a scene. */
+RT_API int rt_scene_refit(rt_ctx* ctx, const RtFloat3* meshPositions, int64_t nMeshPositions);
 
 /* ---- per-frame hot path: replaces the two kernel launches of
  *      RTRenderer.RenderDirectToPbo (Engine/RTRenderer.cs:152-153 PrimaryVisibilityKernel,

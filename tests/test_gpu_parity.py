@@ -404,3 +404,94 @@ def test_obj_asset_scene_through_engine(gpu_ctx, tmp_path):
         assert np.array_equal(color, ref.rgba8), f"flags {flags}"
         assert (objid >= 0).sum() > W * H // 8       # the asset is actually in view
     rdr.close()
+
+
+def _moved(positions: np.ndarray, step: int) -> np.ndarray:
+    """A large, smooth deformation plus jitter: every triangle moves, many leave their old boxes."""
+    p = positions.astype(np.float32).copy()
+    rs = np.random.RandomState(100 + step)
+    p[:, 1] += (1.5 * np.sin(0.35 * p[:, 0] + step) * np.cos(0.27 * p[:, 2] - step)).astype(np.float32)
+    p[:, 0] += (0.3 * np.sin(0.5 * p[:, 2])).astype(np.float32)
+    p += rs.uniform(-0.05, 0.05, p.shape).astype(np.float32)
+    return p
+
+
+@pytest.mark.parametrize("kind", ["terrain", "special"])
+def test_refit_moved_vertices(gpu_ctx, kind):
+    """SURVEY §8f rank 3 (refit half): rt_scene_refit moves the vertices of the uploaded topology and refits the wide BVH on the
+    device.  The refitted scene must render exactly like (a) the oracle on a scene REBUILT from the moved vertices and (b) a full
+    rt_scene_upload of that scene - hits, counts, G-buffer, radiance, RGBA8 - twice in a row (refit of a refitted tree)."""
+    import dataclasses
+    from tests.util import special_camera, special_scene
+    if kind == "terrain":
+        spec, W, H = scenes.terrain_scene(n_quads=96, n_spheres=24), 448, 252
+        cam = oracle_camera("C3", W, H)
+    else:   # translated (PRIM_XFORM) mesh instance with textured / alpha-tested triangles next to transformed spheres.  The 20 exactly
+        # duplicated triangles are left out: their equal-t ties are broken by the visiting order of the BVH2 that was UPLOADED,
+        # which a refit keeps, while a rebuilt reference re-sorts them (rt_scene_refit's documented difference)
+        spec, W, H = special_scene("translated"), 400, 240
+        m = spec.mesh
+        spec = dataclasses.replace(spec, mesh=dataclasses.replace(m, tris=m.tris[:-20], tri_uvs=m.tri_uvs[:-20], tri_mat=m.tri_mat[:-20]))
+        cam = special_camera(W, H)
+    gpu_ctx.scene_upload(oracle_scene_from_spec(spec).arrays())
+    pos = spec.mesh.positions
+    for step in (1, 2):
+        pos = _moved(pos, step) if kind == "terrain" else (pos + np.float32(0.15 * step) * np.sin(pos[:, ::-1] * 3.0 + step).astype(np.float32)).astype(np.float32)
+        moved = dataclasses.replace(spec, mesh=dataclasses.replace(spec.mesh, positions=pos))
+        sc = oracle_scene_from_spec(moved)
+        gpu_ctx.scene_refit(pos)
+        _, refit, st_refit = _run(gpu_ctx, sc, cam, W, H, 2, 4, label=f"refit {kind} step {step}")
+        gpu_ctx.scene_upload(sc.arrays())
+        _, full, st_full = _run(gpu_ctx, sc, cam, W, H, 2, 4, label=f"rebuilt {kind} step {step}")
+        for k in full:
+            assert np.array_equal(refit[k], full[k]), (k, step)
+        assert st_refit["wideNodes"] >= 0 and st_refit["raysBounce"] == st_full["raysBounce"]
+        if step == 1:   # the next refit starts from the refitted tree, not from the rebuilt one
+            gpu_ctx.scene_upload(oracle_scene_from_spec(spec).arrays())
+            gpu_ctx.scene_refit(pos)
+
+
+def test_refit_errors_and_engine_policy(gpu_ctx):
+    """rt_scene_refit error behaviour, and the engine mirror's RebuildPolicy: ForceRefit refits when only positions changed
+    (Scene.SetMeshPositions) and falls back to the full upload after any other edit."""
+    from ilgpu_raytracing_b200 import engine, native
+    spec = scenes.terrain_scene(n_quads=40, n_spheres=6)
+    gpu_ctx.scene_upload(oracle_scene_from_spec(spec).arrays())
+    n = len(spec.mesh.positions)
+    with pytest.raises(native.RtError) as e:
+        gpu_ctx.scene_refit(spec.mesh.positions[: n - 1])
+    assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
+    bad = spec.mesh.positions.copy(); bad[7, 1] = np.nan
+    with pytest.raises(native.RtError) as e:
+        gpu_ctx.scene_refit(bad)
+    assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
+    fresh = native.Context(0)
+    with pytest.raises(native.RtError) as e:
+        fresh.scene_refit(spec.mesh.positions)
+    assert e.value.status == L.RT_ERR_INVALID_STATE
+    fresh.close()
+
+    W, H = 320, 180
+    rdr = engine.RTRenderer(0, W, H)
+    rdr.scene.load_spec(spec)
+    assert not rdr.scene.CanRefit()
+    rdr.Commit(rdr.FORCE_REFIT)                      # nothing uploaded with this topology yet: full upload
+    assert rdr.scene.CanRefit()
+    cam = engine.config_camera("C3", W, H)
+    rdr.camera = cam
+    rdr.configure(spp=2, maxDepth=3, rngLockNoise=1, fixedSeed=3)
+    pos = _moved(spec.mesh.positions, 5)
+    rdr.scene.SetMeshPositions(pos)
+    assert rdr.scene.CanRefit()
+    rdr.Commit(rdr.FORCE_REFIT)                      # device-side refit
+    rdr.RenderDirectToPbo(None, W, H, 0, 0.0)
+    color, depth, objid = rdr.DownloadToCpu()
+    import dataclasses
+    sc = oracle_scene_from_spec(dataclasses.replace(spec, mesh=dataclasses.replace(spec.mesh, positions=pos)))
+    ref = orc.render(sc, oracle_camera("C3", W, H), orc.make_config(W, H, spp=2, max_depth=3, rng_lock_noise=3), aovs=False)
+    assert np.array_equal(color, ref.rgba8) and np.array_equal(depth, ref.depth) and np.array_equal(objid, ref.objId)
+    with pytest.raises(engine.EngineError, match="ArgumentOutOfRangeException"):
+        rdr.scene.SetMeshPositions(pos[:-1])
+    rdr.scene.AddSphere(scenes.sphere((0, 30, 0), 1.0, (1, 1, 1), 0))   # any other edit ends refit eligibility
+    assert not rdr.scene.CanRefit()
+    rdr.close()
