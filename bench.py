@@ -193,7 +193,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, H, spp, depth = wl["w"], wl["h"], wl["spp"], wl["depth"]
-    tile = 32
+    tile = int(os.environ.get("RT_BENCH_TILE", "32"))   # interleaved screen-tile size (multi-GPU partition)
 
     # ---- scene + renderer through the engine API (the reference's host surface) -----------------------------------
     rdr = engine.RTRenderer(local_rank, W, H)
