@@ -449,7 +449,7 @@ void Scene::FillDesc(RtSceneDesc* d) const {
 void Scene::UploadAll() {   // Scene.cs:258-279
     if (!_native) throw InvalidOperationException("Scene has no native context (host-only scene)");
     RtSceneDesc d; FillDesc(&d);
-    check(rt_scene_upload(_native, &d));
+    check(rt_scene_upload_ex(_native, &d, DeviceBuild ? (uint32_t)RT_BUILD_DEVICE_LBVH : 0u));
     _uploadedVersion = _topologyVersion;
 }
 // New vertex positions for the loaded mesh, same count and triangles (the reference has no such entry point: its meshes never move;
@@ -603,6 +603,7 @@ ENG_API int eng_renderer_commit_policy(RTRenderer* r, int policy) {
 }
 ENG_API int eng_scene_set_mesh_positions(Scene* s, const Float3* pos, int n) { return guard([&] { s->SetMeshPositions(pos, n); }); }
 ENG_API int eng_scene_can_refit(Scene* s) { return s->CanRefit() ? 1 : 0; }
+ENG_API void eng_scene_set_device_build(Scene* s, int on) { s->DeviceBuild = on != 0; }
 ENG_API void eng_renderer_get_camera(RTRenderer* r, RtCamera* out) { memcpy(out, &r->Cam(), sizeof(RtCamera)); }
 ENG_API void eng_renderer_set_camera(RTRenderer* r, const RtCamera* in) { memcpy(static_cast<RtCamera*>(&r->Cam()), in, sizeof(RtCamera)); }
 ENG_API void eng_renderer_set_sun_params(RTRenderer* r, float speed, float elevation) { r->SetSunParams(speed, elevation); }

@@ -124,8 +124,8 @@ inline float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 }   // namespace
 
-bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
-    out.nodes.clear(); out.prims.clear(); out.levelStart.clear(); out.stats = HostBvhStats();
+bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool primsOnly) {
+    out.nodes.clear(); out.prims.clear(); out.levelStart.clear(); out.primBoxes.clear(); out.stats = HostBvhStats();
     out.instBoxXf.assign((size_t)std::max<int64_t>(0, d.nInstances) * 12, 0.0);
     for (int64_t i = 0; i < d.nInstances; i++) { out.instBoxXf[(size_t)i * 12 + 0] = 1.0; out.instBoxXf[(size_t)i * 12 + 5] = 1.0; out.instBoxXf[(size_t)i * 12 + 10] = 1.0; }
     Builder B;
@@ -245,6 +245,18 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err) {
             p.box.lo[a] -= pad; p.box.hi[a] += pad;
             p.c[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
         }
+    }
+
+    if (primsOnly) {
+        out.prims.resize((size_t)N); out.primBoxes.resize((size_t)N * 6);
+        Aabb sb; sb.reset();
+        for (int i = 0; i < N; i++) {
+            out.prims[(size_t)i] = B.prims[(size_t)i].rec;
+            for (int a = 0; a < 3; a++) { out.primBoxes[(size_t)i * 6 + a] = B.prims[(size_t)i].box.lo[a]; out.primBoxes[(size_t)i * 6 + 3 + a] = B.prims[(size_t)i].box.hi[a]; }
+            sb.grow(B.prims[(size_t)i].box);
+        }
+        for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = sb.lo[a]; out.stats.sceneHi[a] = sb.hi[a]; }
+        return true;
     }
 
     // ---- 3. binary BVH (binned SAH, leaves of <= 3 primitives) ---------------------------------------------------

@@ -20,11 +20,14 @@ struct HostBvh {
     std::vector<PrimRec> prims;    // leaf order
     std::vector<int> levelStart;   // levelStart[l] .. levelStart[l + 1] = the nodes of depth l + 1 (for the device-side refit)
     std::vector<double> instBoxXf; // per instance: the 3x4 object-to-world transform its primitive boxes were built with (identity for identity instances)
+    std::vector<float> primBoxes;  // primsOnly builds: padded world box of prims[i], 6 floats (lo, hi), in the reference's visiting order
     HostBvhStats stats;
 };
 
 // Validates the reference arrays (every index the device code will follow), derives the reference's
 // visiting order and builds the wide BVH.  Returns false with a message on malformed input.
-bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err);
+// primsOnly: stop after the primitive stage (validation, visiting-order ranks, records, padded boxes, scene bounds in stats):
+// the tree is then built on the device (rt_build.h).
+bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err, bool primsOnly = false);
 
 }   // namespace rtx

@@ -353,107 +353,7 @@ __global__ void k_deinterleave(const float4* payload, const int* pixelMap, int n
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// ------------------------------------------------------------------------------------------------ refit
-// BvhManager.BuildOrRefit(RebuildPolicy.ForceRefit) (BvhManager.cs:13-27) made real: new vertex positions for the SAME mesh
-// topology.  The wide BVH keeps its shape; the device rewrites the triangle records, recomputes every primitive box and then
-// the child boxes / quantisation frames of the wide nodes level by level from the leaves up - the formulas of the host
-// builder (rt_bvh.cpp, sections 2 and 4), so a refitted tree is exactly as conservative as a freshly built one.
-__global__ void k_refit_prims(PrimRec* prims, int nPrims, const RtFloat3* pos, const RtMeshTri* tris, const double* instXf, float4* primBox, unsigned* sceneAbsBits) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float m = 0.0f;
-    if (i < nPrims) {
-        PrimRec r = prims[i];
-        const uint32_t meta = __float_as_uint(r.q2.w);
-        float lo[3], hi[3];
-        if (meta & PRIM_SPHERE) {
-            const float rad = fabsf(r.q1.x);
-            lo[0] = r.q0.x - rad; lo[1] = r.q0.y - rad; lo[2] = r.q0.z - rad; hi[0] = r.q0.x + rad; hi[1] = r.q0.y + rad; hi[2] = r.q0.z + rad;
-        } else {
-            const RtMeshTri t = tris[(int)__float_as_uint(r.q0.w)];
-            const RtFloat3 v0 = pos[t.i0], v1 = pos[t.i1], v2 = pos[t.i2];
-            r.q0.x = v0.X; r.q0.y = v0.Y; r.q0.z = v0.Z; r.q1.x = v1.X; r.q1.y = v1.Y; r.q1.z = v1.Z; r.q2.x = v2.X; r.q2.y = v2.Y; r.q2.z = v2.Z;
-            prims[i] = r;
-            lo[0] = fminf(v0.X, fminf(v1.X, v2.X)); lo[1] = fminf(v0.Y, fminf(v1.Y, v2.Y)); lo[2] = fminf(v0.Z, fminf(v1.Z, v2.Z));
-            hi[0] = fmaxf(v0.X, fmaxf(v1.X, v2.X)); hi[1] = fmaxf(v0.Y, fmaxf(v1.Y, v2.Y)); hi[2] = fmaxf(v0.Z, fmaxf(v1.Z, v2.Z));
-        }
-        if (meta & PRIM_XFORM) {   // world box of the object-space box, as the builder takes it (8 corners, double)
-            const double* x = instXf + (size_t)(meta & PRIM_INST_MASK) * 12;
-            float wl[3] = {3.4e38f, 3.4e38f, 3.4e38f}, wh[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-            for (int c = 0; c < 8; c++) {
-                const double p0 = (c & 1) ? hi[0] : lo[0], p1 = (c & 2) ? hi[1] : lo[1], p2 = (c & 4) ? hi[2] : lo[2];
-                for (int a = 0; a < 3; a++) { const float w = (float)(x[a * 4] * p0 + x[a * 4 + 1] * p1 + x[a * 4 + 2] * p2 + x[a * 4 + 3]); wl[a] = fminf(wl[a], w); wh[a] = fmaxf(wh[a], w); }
-            }
-            for (int a = 0; a < 3; a++) { lo[a] = wl[a]; hi[a] = wh[a]; }
-        }
-        primBox[2 * i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
-        primBox[2 * i + 1] = make_float4(hi[0], hi[1], hi[2], (meta & PRIM_XFORM) ? 1.0f : 0.0f);
-        for (int a = 0; a < 3; a++) m = fmaxf(m, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
-    }
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
-    if ((threadIdx.x & 31u) == 0u) atomicMax(sceneAbsBits, __float_as_uint(m));   // non-negative floats order like their bit patterns
-}
-__global__ void k_refit_nodes(WideNode* nodes, int first, int last, const float4* primBox, float4* nodeBox, const unsigned* sceneAbsBits) {
-    const int n = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= last) return;
-    const float sceneAbs = __uint_as_float(*sceneAbsBits);
-    WideNode wn = nodes[n];
-    const uint32_t imask = wn.n0.w >> 24, valid24 = wn.n1.z;
-    float clo[8][3], chi[8][3]; bool used[8];
-    float nlo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, nhi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
-    for (int s = 0; s < 8; s++) {
-        used[s] = false;
-        for (int a = 0; a < 3; a++) { clo[s][a] = 3.4e38f; chi[s][a] = -3.4e38f; }
-        if ((imask >> s) & 1u) {
-            const int child = (int)wn.n1.x + __popc(imask & ((1u << s) - 1u));
-            const float4 l = nodeBox[2 * child], h = nodeBox[2 * child + 1];
-            clo[s][0] = l.x; clo[s][1] = l.y; clo[s][2] = l.z; chi[s][0] = h.x; chi[s][1] = h.y; chi[s][2] = h.z;
-            used[s] = true;
-        } else {
-            const uint32_t field = (valid24 >> (3 * s)) & 7u;
-            if (field == 0u) continue;
-            const int cnt = __popc(field), start = (int)wn.n1.y + __popc(valid24 & ((1u << (3 * s)) - 1u));
-            for (int k = 0; k < cnt; k++) {
-                const float4 l = primBox[2 * (start + k)], h = primBox[2 * (start + k) + 1];
-                const float lo3[3] = {l.x, l.y, l.z}, hi3[3] = {h.x, h.y, h.z};
-                for (int a = 0; a < 3; a++) {   // conservative padding, rt_bvh.cpp section 2
-                    const float mag = fmaxf(fabsf(lo3[a]), fabsf(hi3[a]));
-                    const float pad = 2e-6f * sceneAbs + (h.w != 0.0f ? 2e-5f : 2e-6f) * mag + 1e-30f;
-                    clo[s][a] = fminf(clo[s][a], lo3[a] - pad); chi[s][a] = fmaxf(chi[s][a], hi3[a] + pad);
-                }
-            }
-            used[s] = true;
-        }
-        for (int a = 0; a < 3; a++) { nlo[a] = fminf(nlo[a], clo[s][a]); nhi[a] = fmaxf(nhi[a], chi[s][a]); }
-    }
-    nodeBox[2 * n] = make_float4(nlo[0], nlo[1], nlo[2], 0.0f);
-    nodeBox[2 * n + 1] = make_float4(nhi[0], nhi[1], nhi[2], 0.0f);
-    // quantisation frame and planes, rt_bvh.cpp section 4
-    uint32_t eb[3]; double scale[3]; float pf[3];
-    for (int a = 0; a < 3; a++) {
-        const double ext = (double)nhi[a] - (double)nlo[a];
-        int e = -126;
-        if (ext > 0.0) { e = ilogb(ext / 252.0); if (ldexp(1.0, e) < ext / 252.0) e++; while (ext / ldexp(1.0, e) > 252.0) e++; }
-        e = max(-126, min(100, e));
-        eb[a] = (uint32_t)(e + 127); scale[a] = ldexp(1.0, e);
-        pf[a] = (float)((double)nlo[a] - scale[a]);
-        if ((double)pf[a] > (double)nlo[a]) pf[a] = nextafterf(pf[a], -INFINITY);
-    }
-    uint32_t pw[3][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
-    for (int s = 0; s < 8; s++)
-        for (int a = 0; a < 3; a++) {
-            uint32_t ql = 255u, qh = 0u;
-            if (used[s]) {
-                const double l = floor(((double)clo[s][a] - (double)pf[a]) / scale[a] - 0.01), h = ceil(((double)chi[s][a] - (double)pf[a]) / scale[a] + 0.01);
-                ql = (uint32_t)fmax(0.0, fmin(255.0, l)); qh = (uint32_t)fmax(0.0, fmin(255.0, h));
-            }
-            pw[a][s >> 1] |= (ql | (qh << 8)) << (16 * (s & 1));   // word k of an axis = { qlo[2k], qhi[2k], qlo[2k+1], qhi[2k+1] }
-        }
-    wn.n0 = make_uint4(__float_as_uint(pf[0]), __float_as_uint(pf[1]), __float_as_uint(pf[2]), eb[0] | (eb[1] << 8) | (eb[2] << 16) | (imask << 24));
-    wn.n2 = make_uint4(pw[0][0], pw[0][1], pw[0][2], pw[0][3]);
-    wn.n3 = make_uint4(pw[1][0], pw[1][1], pw[1][2], pw[1][3]);
-    wn.n4 = make_uint4(pw[2][0], pw[2][1], pw[2][2], pw[2][3]);
-    nodes[n] = wn;
-}
+#include "rt_build.h"   // device-side refit and build of the wide BVH
 
 static thread_local std::string g_lastError;
 static int fail(int code, const std::string& msg) { g_lastError = msg; return code; }
@@ -576,6 +476,62 @@ static int size_extend_launch(rt_ctx* c, int entries) {
     return RT_OK;
 }
 
+// Device-side build (rt_build.h) of the tree over the host-made primitive records: fills dNodes / dPrims (temporaries of
+// nPrims entries each), the level ranges and the depth.  Returns a cudaError_t; *tooDeep when the tree would not fit the traversal stack.
+static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, DevBuf<WideNode>& dNodes, DevBuf<PrimRec>& dPrims, std::vector<int>& levelStart, int* nNodesOut, bool* tooDeep) {
+    const int n = (int)hb.prims.size();
+    cudaStream_t st = c->stream;
+    cudaError_t e;
+#define BTRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
+    DevBuf<PrimRec> primsIn; DevBuf<float4> primBox; DevBuf<uint64_t> keys, keys2; DevBuf<int> vals, vals2, ints, counters; DevBuf<unsigned char> sortTmp;
+    BTRY(primsIn.ensure(n)); BTRY(primBox.ensure(2 * (size_t)n)); BTRY(keys.ensure(n)); BTRY(keys2.ensure(n)); BTRY(vals.ensure(n)); BTRY(vals2.ensure(n));
+    BTRY(ints.ensure(8 * (size_t)n)); BTRY(counters.ensure(2)); BTRY(dNodes.ensure(n)); BTRY(dPrims.ensure(n));
+    DevBuf<float4> tbox; BTRY(tbox.ensure(2 * (size_t)n));
+    std::vector<float4> hbBox(2 * (size_t)n);
+    for (int i = 0; i < n; i++) {
+        hbBox[2 * (size_t)i] = make_float4(hb.primBoxes[(size_t)i * 6], hb.primBoxes[(size_t)i * 6 + 1], hb.primBoxes[(size_t)i * 6 + 2], 0.0f);
+        hbBox[2 * (size_t)i + 1] = make_float4(hb.primBoxes[(size_t)i * 6 + 3], hb.primBoxes[(size_t)i * 6 + 4], hb.primBoxes[(size_t)i * 6 + 5], 0.0f);
+    }
+    BTRY(cudaMemcpyAsync(primsIn.p, hb.prims.data(), (size_t)n * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
+    BTRY(cudaMemcpyAsync(primBox.p, hbBox.data(), hbBox.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    float3 lo = make_float3(hb.stats.sceneLo[0], hb.stats.sceneLo[1], hb.stats.sceneLo[2]);
+    float3 inv = make_float3(1.0f / fmaxf(hb.stats.sceneHi[0] - lo.x, 1e-30f), 1.0f / fmaxf(hb.stats.sceneHi[1] - lo.y, 1e-30f), 1.0f / fmaxf(hb.stats.sceneHi[2] - lo.z, 1e-30f));
+    k_lbvh_morton<<<(n + 255) / 256, 256, 0, st>>>(primBox.p, n, lo, inv, keys.p, vals.p);
+    size_t tmpBytes = 0;
+    BTRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, st));
+    BTRY(sortTmp.ensure(tmpBytes + 16));
+    BTRY(cub::DeviceRadixSort::SortPairs(sortTmp.p, tmpBytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, st));
+    LbvhTree t;
+    t.left = ints.p; t.right = ints.p + n; t.first = ints.p + 2 * (size_t)n; t.last = ints.p + 3 * (size_t)n; t.visits = ints.p + 4 * (size_t)n; t.parent = ints.p + 5 * (size_t)n;   // parent: 2n - 1 entries
+    int* workB2 = ints.p + 7 * (size_t)n;
+    t.box = tbox.p;
+    BTRY(cudaMemsetAsync(t.visits, 0, (size_t)n * sizeof(int), st));
+    k_lbvh_tree<<<(n + 255) / 256, 256, 0, st>>>(keys2.p, n, t);
+    k_lbvh_boxes<<<(n + 255) / 256, 256, 0, st>>>(vals2.p, primBox.p, n, t);
+    const int init[2] = {1, 0};
+    BTRY(cudaMemcpyAsync(counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    BTRY(cudaMemsetAsync(workB2, 0, sizeof(int), st));   // wide node 0 owns binary node 0
+    int leafMax = 2;   // primitives per leaf child; sweep on C4 (RT_LBVH_LEAF): 1 / 2 / 3 -> 22.5 / 22.2 / 29.1 ms of traversal (host SAH tree: 19.7)
+    if (const char* ev = getenv("RT_LBVH_LEAF")) { const int v = atoi(ev); if (v >= 1 && v <= 3) leafMax = v; }
+    levelStart.assign(1, 0);
+    int first = 0, last = 1;
+    *tooDeep = false;
+    while (first < last) {
+        if ((int)levelStart.size() > RT_STACK_ENTRIES - 2) { *tooDeep = true; break; }
+        k_lbvh_collapse<<<(last - first + 127) / 128, 128, 0, st>>>(first, last, n, t, vals2.p, primBox.p, primsIn.p, dNodes.p, dPrims.p, workB2, counters.p, leafMax);
+        int cnt[2];
+        BTRY(cudaMemcpyAsync(cnt, counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
+        BTRY(cudaStreamSynchronize(st));
+        levelStart.push_back(last);
+        first = last; last = cnt[0];
+    }
+    BTRY(cudaGetLastError());
+    BTRY(cudaStreamSynchronize(st));
+    *nNodesOut = last;
+#undef BTRY
+    return cudaSuccess;
+}
+
 extern "C" {
 
 RT_API int rt_abi_version(void) { return RT_ABI_VERSION; }
@@ -635,8 +591,11 @@ RT_API int rt_set_stream(rt_ctx* c, void* s) {
     return RT_OK;
 }
 
-RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
+RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) { return rt_scene_upload_ex(c, d, 0u); }
+
+RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFlags) {
     if (!c || !d) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: null argument");
+    if (buildFlags & ~(uint32_t)RT_BUILD_DEVICE_LBVH) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload_ex: unknown build flag");
     const void* ptrs[15] = {d->tlasNodes, d->tlasInstanceIndices, d->instances, d->blasNodes, d->spherePrimIdx, d->spheres, d->triPrimIdx, d->meshPositions,
                             d->meshTris, d->meshTexcoords, d->meshTriUVs, d->triMatIndex, d->materials, d->texels, d->texInfos};
     const int64_t cnts[15] = {d->nTlasNodes, d->nTlasInstanceIndices, d->nInstances, d->nBlasNodes, d->nSpherePrimIdx, d->nSpheres, d->nTriPrimIdx, d->nMeshPositions,
@@ -651,19 +610,39 @@ RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
             return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: texInfos entry addresses texels out of range");
     }
     HostBvh bvh; std::string err;
-    if (!build_wide_bvh(*d, bvh, err)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
+    // the device builder needs a few primitives to make a tree of; tiny scenes take the host builder either way
+    bool onDevice = (buildFlags & RT_BUILD_DEVICE_LBVH) != 0;
+    if (!build_wide_bvh(*d, bvh, err, onDevice)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
+    if (onDevice && bvh.prims.size() < 64) { onDevice = false; if (!build_wide_bvh(*d, bvh, err, false)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err); }
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // nothing in flight may still read the old scene
     cudaStream_t st = c->stream;
     DeviceScene& ds = c->ds;
-    const size_t nodeBytes = (std::max<size_t>(1, bvh.nodes.size()) * sizeof(WideNode) + 255) / 256 * 256;
-    const size_t primBytes = std::max<size_t>(1, bvh.prims.size()) * sizeof(PrimRec);
+    DevBuf<WideNode> builtNodes; DevBuf<PrimRec> builtPrims; int builtNodeCount = 0;
+    if (onDevice) {
+        bool tooDeep = false;
+        CUDA_TRY(build_on_device(c, bvh, builtNodes, builtPrims, bvh.levelStart, &builtNodeCount, &tooDeep));
+        if (tooDeep) {   // a degenerate Morton order (very uneven extents): the host builder bounds the depth
+            onDevice = false; builtNodes.release(); builtPrims.release();
+            if (!build_wide_bvh(*d, bvh, err, false)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
+        } else {
+            bvh.stats.nWideNodes = builtNodeCount; bvh.stats.maxDepth = std::max(1, (int)bvh.levelStart.size() - 1);
+        }
+    }
+    const size_t nNodes = onDevice ? (size_t)builtNodeCount : bvh.nodes.size(), nPrims = bvh.prims.size();
+    const size_t nodeBytes = (std::max<size_t>(1, nNodes) * sizeof(WideNode) + 255) / 256 * 256;
+    const size_t primBytes = std::max<size_t>(1, nPrims) * sizeof(PrimRec);
     CUDA_TRY(c->bvhBlob.ensure(nodeBytes + primBytes));
     WideNode* dNodes = reinterpret_cast<WideNode*>(c->bvhBlob.p);
     PrimRec* dPrims = reinterpret_cast<PrimRec*>(c->bvhBlob.p + nodeBytes);
-    if (!bvh.nodes.empty()) CUDA_TRY(cudaMemcpyAsync(dNodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(WideNode), cudaMemcpyHostToDevice, st));
-    if (!bvh.prims.empty()) CUDA_TRY(cudaMemcpyAsync(dPrims, bvh.prims.data(), bvh.prims.size() * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
-    ds.nodes = dNodes; ds.nNodes = bvh.prims.empty() ? 0 : (int)bvh.nodes.size(); ds.prims = dPrims; ds.nPrims = (int)bvh.prims.size();
+    if (onDevice) {
+        CUDA_TRY(cudaMemcpyAsync(dNodes, builtNodes.p, nNodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dPrims, builtPrims.p, nPrims * sizeof(PrimRec), cudaMemcpyDeviceToDevice, st));
+    } else {
+        if (nNodes) CUDA_TRY(cudaMemcpyAsync(dNodes, bvh.nodes.data(), nNodes * sizeof(WideNode), cudaMemcpyHostToDevice, st));
+        if (nPrims) CUDA_TRY(cudaMemcpyAsync(dPrims, bvh.prims.data(), nPrims * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
+    }
+    ds.nodes = dNodes; ds.nNodes = nPrims == 0 ? 0 : (int)nNodes; ds.prims = dPrims; ds.nPrims = (int)nPrims;
     // keep the BVH resident in L2 while GBs of path state stream past it: persisting carve-out + access-policy window (applied per stream in rt_render)
     c->l2Window = 0;
     if (!bvh.prims.empty() && c->l2PersistMax > 0 && getenv("RT_NO_L2_PERSIST") == nullptr) {
@@ -689,7 +668,7 @@ RT_API int rt_scene_upload(rt_ctx* c, const RtSceneDesc* d) {
     const int rcSize = size_extend_launch(c, bvh.stats.maxDepth + 1);   // a node step pushes at most one entry per level
     if (rcSize != RT_OK) return rcSize;
     c->bvhStats = bvh.stats;
-    c->bvhBytes = bvh.nodes.size() * sizeof(WideNode) + bvh.prims.size() * sizeof(PrimRec);
+    c->bvhBytes = nNodes * sizeof(WideNode) + nPrims * sizeof(PrimRec);
     c->hasScene = true;
     return RT_OK;
 }

@@ -59,6 +59,8 @@ def lib() -> C.CDLL:
     l.eng_scene_load_obj_instance.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_float]
     l.eng_scene_set_mesh_positions.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     l.eng_scene_can_refit.argtypes = [C.c_void_p]
+    l.eng_scene_set_device_build.argtypes = [C.c_void_p, C.c_int]
+    l.eng_scene_set_device_build.restype = None
     l.eng_renderer_commit_policy.argtypes = [C.c_void_p, C.c_int]
     l.eng_scene_sort_ties.argtypes = [C.c_void_p]
     l.eng_scene_sort_ties.restype = C.c_long
@@ -201,6 +203,10 @@ class Scene:
         """Moved vertices for the loaded mesh (same count, same triangles); Commit(FORCE_REFIT) then refits instead of rebuilding."""
         p = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
         _check(self._l.eng_scene_set_mesh_positions(self.h, _p(p), len(p)))
+
+    def SetDeviceBuild(self, on: bool):
+        """UploadAll builds the wide BVH on the GPU (Morton-order radix tree + greedy collapse) instead of the host's SAH build."""
+        self._l.eng_scene_set_device_build(self.h, 1 if on else 0)
 
     def CanRefit(self) -> bool:
         return bool(self._l.eng_scene_can_refit(self.h))

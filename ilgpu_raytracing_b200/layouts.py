@@ -37,6 +37,7 @@ SCENE_ARRAYS = [("tlasNodes", BVHNODE), ("tlasInstanceIndices", np.dtype("<i4"))
                 ("meshTris", MESHTRI), ("meshTexcoords", F2), ("meshTriUVs", MESHTRI), ("triMatIndex", np.dtype("<i4")),
                 ("materials", MATERIAL), ("texels", RGBA32), ("texInfos", TEXINFO)]
 
+RT_BUILD_DEVICE_LBVH = 1
 RT_FLAG_TRI_MATERIALS = 1 << 0
 RT_FLAG_ACCUMULATE = 1 << 1
 RT_FLAG_RESET_ACCUM = 1 << 2

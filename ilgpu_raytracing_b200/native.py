@@ -18,7 +18,7 @@ _LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b
 
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
-           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit"]
+           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex"]
 
 
 class RtError(RuntimeError):
@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
     l.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     l.rt_scene_upload.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
     l.rt_scene_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    l.rt_scene_upload_ex.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc), C.c_uint32]
     l.rt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig)]
     l.rt_sync.argtypes = [C.c_void_p]
     l.rt_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
@@ -98,9 +99,13 @@ class Context:
     def set_stream(self, cuda_stream_ptr: int | None):
         check(self._l.rt_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
 
-    def scene_upload(self, arrays: dict):
+    def scene_upload(self, arrays: dict, device_build: bool = False):
+        """rt_scene_upload; device_build=True builds the wide BVH on the GPU (rt_scene_upload_ex, RT_BUILD_DEVICE_LBVH)."""
         desc, keep = L.scene_desc_from_arrays(arrays)
-        check(self._l.rt_scene_upload(self.h, C.byref(desc)))
+        if device_build:
+            check(self._l.rt_scene_upload_ex(self.h, C.byref(desc), L.RT_BUILD_DEVICE_LBVH))
+        else:
+            check(self._l.rt_scene_upload(self.h, C.byref(desc)))
         del keep
 
     def scene_refit(self, positions: np.ndarray):

@@ -270,6 +270,12 @@ RT_API int rt_set_stream(rt_ctx* ctx, void* cudaStream);
  *      Copies the arrays, derives the reference's traversal order from the BVH2
  *      arrays (tie-break ranks) and builds the compressed 8-wide BVH. ---- */
 RT_API int rt_scene_upload(rt_ctx* ctx, const RtSceneDesc* scene);
+/* The same commit with a choice of builder (what RebuildPolicy, Engine/BvhManager.cs:13-18, is there to express):
+ * 0 = the default - binned-SAH binary tree + SAH-optimal 8-wide collapse on the host (best traversal, ~1 s per million
+ * triangles); RT_BUILD_DEVICE_LBVH = Morton-order radix tree + greedy 8-wide collapse on the device (an order of magnitude
+ * faster commit, a slower tree).  The images are the same either way. */
+enum { RT_BUILD_DEVICE_LBVH = 1u };
+RT_API int rt_scene_upload_ex(rt_ctx* ctx, const RtSceneDesc* scene, uint32_t buildFlags);
 /* BvhManager.BuildOrRefit(RebuildPolicy.ForceRefit) (Engine/BvhManager.cs:13-27; the reference accepts the policy and
  * ignores it): new mesh vertex positions for the topology of the last rt_scene_upload (same count, same triangles).
  * The triangle records and the wide BVH are refitted on the device, bottom-up; tie-break ranks, materials, spheres and

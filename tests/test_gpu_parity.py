@@ -490,8 +490,47 @@ def test_refit_errors_and_engine_policy(gpu_ctx):
     sc = oracle_scene_from_spec(dataclasses.replace(spec, mesh=dataclasses.replace(spec.mesh, positions=pos)))
     ref = orc.render(sc, oracle_camera("C3", W, H), orc.make_config(W, H, spp=2, max_depth=3, rng_lock_noise=3), aovs=False)
     assert np.array_equal(color, ref.rgba8) and np.array_equal(depth, ref.depth) and np.array_equal(objid, ref.objId)
+    rdr.scene.SetDeviceBuild(True)                   # the same moved scene, rebuilt on the device: same image
+    rdr.Commit(rdr.FORCE_REBUILD)
+    rdr.RenderDirectToPbo(None, W, H, 0, 0.0)
+    color2, depth2, objid2 = rdr.DownloadToCpu()
+    assert np.array_equal(color2, ref.rgba8) and np.array_equal(depth2, ref.depth) and np.array_equal(objid2, ref.objId)
     with pytest.raises(engine.EngineError, match="ArgumentOutOfRangeException"):
         rdr.scene.SetMeshPositions(pos[:-1])
     rdr.scene.AddSphere(scenes.sphere((0, 30, 0), 1.0, (1, 1, 1), 0))   # any other edit ends refit eligibility
     assert not rdr.scene.CanRefit()
     rdr.close()
+
+
+@pytest.mark.parametrize("kind", ["terrain", "special", "spheres", "terrain_mats"])
+def test_device_built_bvh(gpu_ctx, kind):
+    """SURVEY §8f rank 3 (build half): rt_scene_upload_ex(RT_BUILD_DEVICE_LBVH) builds the wide BVH on the GPU (Morton order,
+    radix tree, greedy 8-wide collapse).  Another tree, the same answers: every output equals the oracle's, including the equal-t
+    ties of duplicated triangles (the visiting-order ranks are made by the same host stage), and a refit of the device-built
+    tree works like a refit of the host-built one."""
+    import dataclasses
+    from tests.util import special_camera, special_scene
+    flags = 0
+    if kind == "terrain":
+        spec, W, H, cam = scenes.terrain_scene(n_quads=128, n_spheres=30), 448, 252, oracle_camera("C3", 448, 252)
+    elif kind == "terrain_mats":
+        spec, W, H, cam, flags = scenes.terrain_scene(n_quads=96, n_spheres=0, patch_materials=True), 384, 216, oracle_camera("C3", 384, 216), L.RT_FLAG_TRI_MATERIALS
+    elif kind == "special":
+        spec, W, H, cam = special_scene("translated"), 400, 240, special_camera(400, 240)
+    else:
+        spec, W, H, cam = scenes.sphere_grid_scene(24), 384, 216, oracle_camera("C2", 384, 216)
+    sc = oracle_scene_from_spec(spec)
+    gpu_ctx.scene_upload(sc.arrays(), device_build=True)
+    st = gpu_ctx.stats()
+    assert st["bvhPrimCount"] > 64 and 0 < st["bvhWideNodeCount"] < st["bvhPrimCount"]
+    _run(gpu_ctx, sc, cam, W, H, 1, 0, flags=flags, label=f"device build {kind} primary")
+    _run(gpu_ctx, sc, cam, W, H, 3, 6, flags=flags, label=f"device build {kind} 6 bounces")
+    if kind == "terrain":
+        pos = _moved(spec.mesh.positions, 3)
+        gpu_ctx.scene_refit(pos)
+        moved = oracle_scene_from_spec(dataclasses.replace(spec, mesh=dataclasses.replace(spec.mesh, positions=pos)))
+        _run(gpu_ctx, moved, cam, W, H, 2, 4, label="refit of a device-built tree")
+    with pytest.raises(Exception):
+        from ilgpu_raytracing_b200 import native
+        desc, keep = L.scene_desc_from_arrays(sc.arrays())
+        native.check(gpu_ctx._l.rt_scene_upload_ex(gpu_ctx.h, __import__("ctypes").byref(desc), 0x80))   # unknown build flag
