@@ -404,6 +404,12 @@ struct Traversal {
     RT_HD HitRec result() const { HitRec h; h.t = best.t; h.prim = best.prim; h.bu = best.bu; h.bv = best.bv; return h; }
 };
 
+#if !defined(__CUDACC__)
+// Host simulator only: 0 = step() (a node step, then all of its primitives); n > 0 = the per-lane schedule of k_extend - up to n
+// node steps while the primitive queue has room, then ONE primitive step - which exercises the queued primitive groups.
+inline int& host_lane_schedule() { static int nodeSteps = 0; return nodeSteps; }
+#endif
+
 // Convenience wrapper: run one ray to completion.
 // Closest hit: returns true and fills *out when something is hit.  Any hit: returns true when occluded.
 template <bool ANY_HIT, bool COUNT>
@@ -411,6 +417,14 @@ RT_HD bool trace_wide(const DeviceScene& sc, f3 o, f3 d, float tMax, LaneStack& 
     if (sc.nNodes <= 0) { if (!ANY_HIT) { out->t = 1e30f; out->prim = -1; out->bu = 0.0f; out->bv = 0.0f; } return false; }
     Traversal<ANY_HIT, COUNT> tr;
     tr.init(o, d, box_idir(d), tMax, stack);
+#if !defined(__CUDACC__)
+    if (const int ns = host_lane_schedule()) {
+        while (!tr.done) {
+            for (int k = 0; k < ns; k++) if (!tr.done && tr.can_node_step(stack)) tr.node_step(sc, stack, cnt);
+            if (!tr.done && tr.has_prims()) tr.prim_step(sc, stack, cnt);
+        }
+    } else
+#endif
     while (!tr.step(sc, stack, cnt)) {}
     if (ANY_HIT) return tr.occluded;
     *out = tr.result();

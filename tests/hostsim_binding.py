@@ -35,10 +35,16 @@ def lib():
         _lib.hs_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs)]
         _lib.hs_bilinear_upsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _lib.hs_taa_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+        _lib.hs_set_lane_schedule.argtypes = [C.c_int]
         _lib.hs_pow.argtypes = [C.c_float, C.c_float]
         _lib.hs_pow.restype = C.c_float
         _lib.hs_render_reuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs), C.c_void_p, C.c_void_p]
     return _lib
+
+
+def set_lane_schedule(node_steps: int):
+    """0: a node step then all of its primitives; n > 0: k_extend's per-lane schedule (n node steps, one primitive step, queued groups)."""
+    lib().hs_set_lane_schedule(int(node_steps))
 
 
 class HostSimScene:

@@ -109,6 +109,26 @@ def test_terrain(flags):
     assert h["counters"]["nodes"] < r.counters["nodes"] / 3
 
 
+@pytest.mark.parametrize("node_steps", [1, 2, 3])
+def test_kernel_lane_schedule_with_queued_primitive_groups(node_steps):
+    """The traversal under k_extend's per-lane schedule (n node steps, then ONE primitive step, primitives of further node steps queued
+    in the second group slot): same hits, same image as the oracle - the closest hit does not depend on when a queued test runs."""
+    from tests.hostsim_binding import set_lane_schedule
+    from tests.util import special_camera, special_scene
+    try:
+        set_lane_schedule(node_steps)
+        sc = oracle_scene_from_spec(scenes.terrain_scene(48, 12))
+        cam = oracle_camera("C3", 128, 72)
+        r = orc.render(sc, cam, orc.make_config(128, 72, spp=2, max_depth=6))
+        _compare(r, HostSimScene(sc.arrays()).render(cam, L.make_render_config(128, 72, spp=2, max_depth=6)), f"schedule {node_steps} terrain")
+        sc = oracle_scene_from_spec(special_scene("translated"))
+        cam = special_camera(120, 72)
+        r = orc.render(sc, cam, orc.make_config(120, 72, spp=2, max_depth=4))
+        _compare(r, HostSimScene(sc.arrays()).render(cam, L.make_render_config(120, 72, spp=2, max_depth=4)), f"schedule {node_steps} special")
+    finally:
+        set_lane_schedule(0)
+
+
 @pytest.mark.parametrize("transformed", ["identity", "translated"])
 def test_textures_alpha_ties_instances(transformed):
     """Textured / alpha-masked / two-sided triangles, duplicated triangles (equal-t ties) and translated instances."""
