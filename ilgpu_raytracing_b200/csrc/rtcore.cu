@@ -364,8 +364,12 @@ static int fail(int code, const std::string& msg) { g_lastError = msg; return co
                                            std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
     } while (0)
 
-template <typename T> struct DevBuf {
+template <typename T> struct DevBuf {   // owning device allocation (freed with its owner: the context, or a scope)
     T* p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t ensure(size_t count) {
         if (count <= n && p) return cudaSuccess;
         if (p) { cudaFree(p); p = nullptr; n = 0; }

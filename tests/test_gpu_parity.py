@@ -534,3 +534,21 @@ def test_device_built_bvh(gpu_ctx, kind):
         from ilgpu_raytracing_b200 import native
         desc, keep = L.scene_desc_from_arrays(sc.arrays())
         native.check(gpu_ctx._l.rt_scene_upload_ex(gpu_ctx.h, __import__("ctypes").byref(desc), 0x80))   # unknown build flag
+
+
+def test_scene_commits_do_not_leak_device_memory(gpu_ctx):
+    """Repeated host builds, device builds and refits of the same scene leave the free device memory where it was."""
+    import torch
+    spec = scenes.terrain_scene(n_quads=200, n_spheres=8)
+    arrays = oracle_scene_from_spec(spec).arrays()
+    for dev in (False, True):
+        gpu_ctx.scene_upload(arrays, device_build=dev)
+        gpu_ctx.scene_refit(spec.mesh.positions)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for it in range(6):
+        gpu_ctx.scene_upload(arrays, device_build=bool(it & 1))
+        gpu_ctx.scene_refit(spec.mesh.positions)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 32 << 20, f"device memory shrank by {(free0 - free1) >> 20} MiB over 6 commits"
