@@ -1,0 +1,498 @@
+"""Test infrastructure: a SECOND, independent restatement of the reference's hot path, written in scalar Python/numpy
+float32 straight from the C# sources (not from oracle/rt_oracle.cpp), for scenes of spheres and one triangle mesh with
+identity instances - the reference's default scene among them.  It pins the C++ oracle where the reference itself cannot (no tests, no fixtures, cannot
+run here): two restatements made separately from the same lines must agree.
+
+  Camera.CreateCamera / Translate            Engine/Camera.cs:19-47, 121-126
+  Ray.GenerateRay, RNG                       Engine/RTUtils.cs:13-17, 20-138
+  IntersectSphere, TraverseBLAS_Sphere       Engine/SceneDeviceViews.cs:517-537, 124-170 (hit acceptance, colour, sphere uv)
+  IntersectTriangleMT_Bary, TraverseBLAS_Tri_Textured, AnyHit_Tri_Textured
+                                             Engine/SceneDeviceViews.cs:540-558, 173-237, 270-327 (textures, alpha cut-out, two-sided)
+  SampleTextureLinear(RGB_A), SampleMaskLinear / Point, TexelRaw
+                                             Engine/SceneDeviceViews.cs:330-472
+  PrimaryVisibilityKernel, PathTraceKernel   Engine/RTRay.cs:188-325 (reuse off), ReSTIR_Direct :438-543, helpers :546-671
+  GpuFramebuffer.Store / PackRGBA8           Engine/RTRay.cs:59-76
+
+Differences by construction: every primitive is tested (no TLAS / BLAS culling: the boxes only prune; scenes with exactly
+coincident primitives, whose equal-t ties the visiting order decides, are therefore out of its reach), and the transcendental
+functions are numpy's, so the comparison partner is the oracle's libm build and radiance is compared with the north-star
+tolerance (1e-4 relative RMS), ids and bounce counts exactly.  Slow (a few ms per path vertex): tiny images only."""
+import math
+
+import numpy as np
+
+f32 = np.float32
+PI = f32(3.14159265358979323846)
+INV_PI = f32(0.31830988618379067154)
+EPS_N = f32(0.0025)
+EPS_MIN = f32(1e-6)
+M32, M64 = 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF
+
+
+# ---------------------------------------------------------------------------------------------------------------- Float3
+class V:
+    __slots__ = ("x", "y", "z")
+
+    def __init__(self, x, y, z):
+        self.x, self.y, self.z = f32(x), f32(y), f32(z)
+
+    def __add__(self, o): return V(self.x + o.x, self.y + o.y, self.z + o.z)
+    def __sub__(self, o): return V(self.x - o.x, self.y - o.y, self.z - o.z)
+    def __neg__(self): return V(-self.x, -self.y, -self.z)
+
+    def __mul__(self, o):
+        if isinstance(o, V):
+            return V(self.x * o.x, self.y * o.y, self.z * o.z)
+        o = f32(o)
+        return V(self.x * o, self.y * o, self.z * o)
+
+
+def dot(a, b): return a.x * b.x + a.y * b.y + a.z * b.z
+def cross(a, b): return V(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x)
+def fmax(a, b): return f32(max(float(a), float(b)))
+def fmin(a, b): return f32(min(float(a), float(b)))
+
+
+def normalize(v):   # Float3.cs:91-95; XMath.Rsqrt = 1 / sqrt
+    inv = f32(1.0) / np.sqrt(fmax(f32(1e-20), v.x * v.x + v.y * v.y + v.z * v.z))
+    return V(v.x * inv, v.y * inv, v.z * inv)
+
+
+# ---------------------------------------------------------------------------------------------------------------- RNG
+def _rotl(v, r): return ((v << (r & 31)) | (v >> ((32 - r) & 31))) & M32
+
+
+def _splitmix32(x):
+    x = (x + 0x9E3779B97F4A7C15) & M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M64
+    x ^= x >> 31
+    return (x ^ (x >> 32)) & M32
+
+
+def _pcg(x):
+    x ^= x >> 16; x = (x * 0x7FEB352D) & M32; x ^= x >> 15; x = (x * 0x846CA68B) & M32; x ^= x >> 16
+    return x
+
+
+def _hash32(x):
+    x ^= x >> 17; x = (x * 0xED5AD4BB) & M32; x ^= x >> 11; x = (x * 0xAC4C1B51) & M32; x ^= x >> 15; x = (x * 0x31848BAB) & M32; x ^= x >> 14
+    return x
+
+
+class RNG:
+    def __init__(self, index, width, height, frame, sample, salt, lock_noise):   # CreateFromIndex1D -> CreateFromPixel -> Create
+        px, py = index % max(1, width), index // max(1, width)
+        f = 0 if lock_noise != 0 else frame & M32
+        ln = lock_noise & M32
+        ln0 = (_hash32(ln) ^ ((ln * 0x1B873593) & M32)) if lock_noise != 0 else 0
+        ln1 = ((_rotl(ln, 7) * 0x85EBCA6B) & M32) if lock_noise != 0 else 0
+        a = px ^ 0xB5297A4D
+        b = ((py * 0x68E31DA4) & M32) ^ ((f * 0x9E3779B1 + 0x85EBCA6B) & M32) ^ ln0
+        c = ((sample ^ 0xC2B2AE35) + _rotl(px, 16)) & M32
+        d = (((salt ^ 0x27D4EB2F) + _rotl(py, 8)) & M32) ^ ln1          # C# precedence: + before ^
+        s0 = _splitmix32((((a << 32) | b) ^ 0xD1B54A32D192ED03) & M64)
+        s1 = _splitmix32((((c << 32) | d) ^ 0x94D049BB133111EB) & M64)
+        s = _pcg(s0 ^ ((_rotl(s1, 13) + 0x9E3779B1) & M32)) | 1
+        self.state = s if s != 0 else 1
+
+    def next_float(self):
+        x = self.state
+        x ^= (x << 13) & M32; x ^= x >> 17; x ^= (x << 5) & M32
+        self.state = x if x != 0 else 1
+        return f32(self.state & 0xFFFFFF) * f32(1.0 / 16777216.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------- camera, rays
+class Camera:
+    def __init__(self, width, height, fov_degrees, translate=None, origin=(0.0, 1.0, 3.0), look_at=(0.0, 0.5, 0.0)):   # CreateCamera (+ Translate); origin / lookAt are constants there
+        aspect = f32(width) / f32(max(1, height))
+        theta = f32(fov_degrees) * (PI / f32(180.0))
+        half_h = f32(np.tan(f32(0.5) * theta))
+        half_w = aspect * half_h
+        origin, look_at, up = V(*origin), V(*look_at), V(0, 1, 0)
+        w = normalize(origin - look_at)
+        u = normalize(cross(up, w))
+        v = cross(w, u)
+        self.origin = origin
+        self.lower_left = origin - u * half_w - v * half_h - w
+        self.horizontal = u * (f32(2.0) * half_w)
+        self.vertical = v * (f32(2.0) * half_h)
+        if translate is not None:
+            d = V(*translate)
+            self.origin = self.origin + d
+            self.lower_left = self.lower_left + d
+
+
+class Ray:
+    def __init__(self, o, d):
+        self.o, self.d = o, d
+
+
+def primary_ray(cam, index, width, height):   # GBufferParams.PrimaryRay + Ray.GenerateRay
+    x, y = index % width, index // width
+    u = (f32(x) + f32(0.5)) / f32(max(1, width))
+    v = (f32(y) + f32(0.5)) / f32(max(1, height))
+    return Ray(cam.origin, normalize(cam.lower_left + cam.horizontal * u + cam.vertical * v - cam.origin))
+
+
+def ray_normal_offset(origin, n, direction):   # MakeRayWithNormalOffset
+    d = normalize(direction)
+    s = f32(1.0) if dot(n, d) >= 0 else f32(-1.0)
+    return Ray(origin + n * (EPS_N * s), d)
+
+
+# ---------------------------------------------------------------------------------------------------------------- scene
+class Scene:
+    """spheres: SPHERE records (one identity instance each); textures: list of (h, w, 4) u8 RGBA; mesh: a MeshSpec with an
+    identity transform (positions, tris, texcoords, tri_uvs, tri_mat, materials) or None."""
+
+    def __init__(self, spheres, textures, mesh=None):
+        self.spheres, self.textures, self.mesh = spheres, textures, mesh
+        if mesh is not None:
+            self.pos = [V(*p) for p in mesh.positions]
+            self.uv = [(f32(t[0]), f32(t[1])) for t in mesh.texcoords]
+
+    def texel(self, tex, x, y):   # TexelRaw: clamp
+        h, w, _ = tex.shape
+        return tex[max(0, min(h - 1, y)), max(0, min(w - 1, x))]
+
+    def sample_rgb(self, tex, u, v):   # SampleTextureLinearRGB_A (colour part)
+        h, w, _ = tex.shape
+        fu = u - np.floor(u)
+        fv = f32(1.0) - (v - np.floor(v))
+        x, y = fu * f32(w - 1), fv * f32(h - 1)
+        x0, y0 = int(np.floor(x)), int(np.floor(y))
+        x1, y1 = min(w - 1, x0 + 1), min(h - 1, y0 + 1)
+        tx, ty = x - f32(x0), y - f32(y0)
+        k = f32(1.0) / f32(255.0)
+
+        def c(px):
+            return V(f32(px[0]) * k, f32(px[1]) * k, f32(px[2]) * k)
+        c00, c10, c01, c11 = c(self.texel(tex, x0, y0)), c(self.texel(tex, x1, y0)), c(self.texel(tex, x0, y1)), c(self.texel(tex, x1, y1))
+        cx0 = c00 * (f32(1.0) - tx) + c10 * tx
+        cx1 = c01 * (f32(1.0) - tx) + c11 * tx
+        return cx0 * (f32(1.0) - ty) + cx1 * ty
+
+    def _texel_luma(self, tex, x, y):   # Luma01(TexelRaw)
+        p = self.texel(tex, x, y)
+        k = f32(1.0) / f32(255.0)
+        return f32(0.2126) * (f32(p[0]) * k) + f32(0.7152) * (f32(p[1]) * k) + f32(0.0722) * (f32(p[2]) * k)
+
+    def sample_mask_linear(self, tex, u, v):   # SampleMaskLinear
+        h, w, _ = tex.shape
+        fu = u - np.floor(u)
+        fv = f32(1.0) - (v - np.floor(v))
+        x, y = fu * f32(w - 1), fv * f32(h - 1)
+        x0, y0 = int(np.floor(x)), int(np.floor(y))
+        x1, y1 = min(w - 1, x0 + 1), min(h - 1, y0 + 1)
+        tx, ty = x - f32(x0), y - f32(y0)
+        a00, a10, a01, a11 = self._texel_luma(tex, x0, y0), self._texel_luma(tex, x1, y0), self._texel_luma(tex, x0, y1), self._texel_luma(tex, x1, y1)
+        ax0 = a00 * (f32(1.0) - tx) + a10 * tx
+        ax1 = a01 * (f32(1.0) - tx) + a11 * tx
+        return ax0 * (f32(1.0) - ty) + ax1 * ty
+
+    def sample_mask_point(self, tex, u, v):   # SampleMaskPoint; XMath.Round = half to even
+        h, w, _ = tex.shape
+        fu = u - np.floor(u)
+        fv = f32(1.0) - (v - np.floor(v))
+        return self._texel_luma(tex, int(np.rint(fu * f32(w - 1))), int(np.rint(fv * f32(h - 1))))
+
+    def _tex(self, has, idx):
+        return self.textures[int(idx)] if (has != 0 and 0 <= idx < len(self.textures)) else None
+
+    def intersect_tri(self, ray, k):   # IntersectTriangleMT_Bary -> (t, n, bu, bv)
+        i0, i1, i2 = (int(v) for v in self.mesh.tris[k])
+        v0, v1, v2 = self.pos[i0], self.pos[i1], self.pos[i2]
+        e1, e2 = v1 - v0, v2 - v0
+        p = cross(ray.d, e2)
+        det = dot(e1, p)
+        if abs(det) < f32(1e-8):
+            return None
+        inv = f32(1.0) / det
+        tv = ray.o - v0
+        bu = dot(tv, p) * inv
+        if bu < 0 or bu > 1:
+            return None
+        q = cross(tv, e1)
+        bv = dot(ray.d, q) * inv
+        if bv < 0 or bu + bv > 1:
+            return None
+        t = dot(e2, q) * inv
+        if t <= 0:
+            return None
+        return t, normalize(cross(e1, e2)), bu, bv
+
+    def _tri_uv(self, k, bu, bv):
+        t0, t1, t2 = (self.uv[int(i)] for i in self.mesh.tri_uvs[k])
+        w = f32(1.0) - bu - bv
+        return t0[0] * w + t1[0] * bu + t2[0] * bv, t0[1] * w + t1[1] * bu + t2[1] * bv
+
+    def closest_tri(self, ray):
+        """TraverseBLAS_Tri_Textured with every box taken: (t, nObj, albedo, tri id) or None."""
+        best, closest = None, f32(1e30)
+        for k in range(len(self.mesh.tris)):
+            hit = self.intersect_tri(ray, k)
+            if hit is None:
+                continue
+            t, nn, bu, bv = hit
+            mat = self.mesh.materials[int(self.mesh.tri_mat[k])]
+            if not (t > f32(0.001) and t < closest):
+                continue
+            uu, vv = self._tri_uv(k, bu, bv)
+            kd = V(*[mat["Kd"][c] for c in "XYZ"])
+            tex = self._tex(mat["HasDiffuseMap"], mat["DiffuseTexIndex"])
+            if tex is not None:
+                kd = self.sample_rgb(tex, uu, vv)          # SampleTextureLinear: the same bilinear RGB fetch
+            alpha = f32(1.0)
+            atex = self._tex(mat["HasAlphaMap"], mat["AlphaTexIndex"])
+            if atex is not None:
+                alpha = self.sample_mask_linear(atex, uu, vv)
+            if alpha < mat["AlphaCutoff"]:
+                continue
+            closest = t
+            if mat["TwoSided"] != 0 and dot(nn, ray.d) > 0:
+                nn = nn * f32(-1.0)
+            best = (t, nn, kd, k)
+        return best
+
+    def any_tri(self, ray, t_max):   # AnyHit_Tri_Textured
+        for k in range(len(self.mesh.tris)):
+            hit = self.intersect_tri(ray, k)
+            if hit is None:
+                continue
+            t, _, bu, bv = hit
+            if t <= f32(0.001) or t >= t_max:
+                continue
+            mat = self.mesh.materials[int(self.mesh.tri_mat[k])]
+            atex = self._tex(mat["HasAlphaMap"], mat["AlphaTexIndex"])
+            if atex is not None:
+                uu, vv = self._tri_uv(k, bu, bv)
+                a_point, cutoff, band = self.sample_mask_point(atex, uu, vv), mat["AlphaCutoff"], f32(0.10)
+                if a_point < cutoff - band:
+                    continue
+                if a_point >= cutoff + band:
+                    return True
+                if self.sample_mask_linear(atex, uu, vv) < cutoff:
+                    continue
+            return True
+        return False
+
+    @staticmethod
+    def intersect_sphere(ray, s):   # IntersectSphere
+        c = V(*[s["center"][k] for k in "XYZ"])
+        oc = ray.o - c
+        a = dot(ray.d, ray.d)
+        b = f32(2.0) * dot(oc, ray.d)
+        cc = dot(oc, oc) - s["radius"] * s["radius"]
+        disc = b * b - f32(4.0) * a * cc
+        if disc < 0:
+            return None
+        sq = np.sqrt(disc)
+        t = (-b - sq) / (f32(2.0) * a)
+        if t < f32(0.001):
+            t = (-b + sq) / (f32(2.0) * a)
+            if t < f32(0.001):
+                return None
+        p = ray.o + ray.d * t
+        return t, normalize(p - c)
+
+    def trace_closest(self, ray):
+        """TraceClosest over identity sphere instances: (t, normal, albedo, shade, ior, sphere id) or None."""
+        best = None
+        closest = f32(1e30)
+        for i, s in enumerate(self.spheres):
+            hit = self.intersect_sphere(ray, s)
+            if hit is None:
+                continue
+            t, nn = hit
+            if not (t > f32(0.001) and t < f32(1e30)):     # TraverseBLAS_Sphere: one sphere per instance, tClosest starts at 1e30
+                continue
+            if not (t / f32(1.0) < closest):               # tWorld = tObj / scale
+                continue
+            m = s["material"]
+            kd = V(*[m["Kd"][k] for k in "XYZ"])
+            col = V(*[s["albedo"][k] for k in "XYZ"]) if (kd.x == 0 and kd.y == 0 and kd.z == 0) else kd
+            if m["HasDiffuseMap"] != 0 and 0 <= m["DiffuseTexIndex"] < len(self.textures):
+                u = f32(0.5) + f32(np.arctan2(nn.z, nn.x)) / (f32(2.0) * PI)
+                v = f32(np.arccos(fmin(f32(1.0), fmax(f32(-1.0), nn.y)))) / PI
+                col = self.sample_rgb(self.textures[int(m["DiffuseTexIndex"])], u, v)
+            closest = t
+            best = (t, normalize(nn), col, int(s["shading"]), s["ior"] if s["ior"] > 0 else f32(1.0), i)   # TransformVector(identity) + Normalize
+        if self.mesh is not None:   # the mesh instance: triangles are always Lambert, ior 1 (TraceClosest :58-62)
+            th = self.closest_tri(ray)
+            if th is not None and th[0] / f32(1.0) < closest:
+                best = (th[0], normalize(th[1]), th[2], 0, f32(1.0), -1 - th[3])   # ids < 0: triangle -1 - id
+        return best
+
+    def occluded(self, ray, t_max):   # ShadowOcclusion / AnyHit_Sphere
+        for s in self.spheres:
+            hit = self.intersect_sphere(ray, s)
+            if hit is not None and hit[0] > f32(0.001) and hit[0] < t_max:
+                return True
+        return self.mesh is not None and self.any_tri(ray, t_max)
+
+
+# ---------------------------------------------------------------------------------------------------------------- integrator
+class Env:
+    def __init__(self, sun_dir):
+        self.dir_light_dir = V(*sun_dir)
+        self.dir_light_radiance = V(10, 10, 10)
+        self.sky_top, self.sky_bottom = V(0.5, 0.7, 1.0), V(1.0, 1.0, 1.0)
+
+    def sky(self, d):   # SkyWeighted
+        t = f32(0.5) * (d.y + f32(1.0))
+        return self.sky_bottom * (f32(1.0) - t) + self.sky_top * t
+
+
+def luminance(c): return f32(0.2126) * c.x + f32(0.7152) * c.y + f32(0.0722) * c.z
+def cos_pdf(n, wi): return fmax(f32(0.0), dot(n, wi)) * INV_PI
+
+
+def sample_hemisphere_cosine(n, rng):
+    r1, r2 = rng.next_float(), rng.next_float()
+    phi = f32(2.0) * PI * r1
+    cos_t, sin_t = np.sqrt(f32(1.0) - r2), np.sqrt(r2)
+    x, y, z = f32(np.cos(phi)) * sin_t, f32(np.sin(phi)) * sin_t, cos_t
+    up = V(0, 1, 0) if abs(n.y) < f32(0.999) else V(1, 0, 0)
+    t = normalize(cross(up, n))
+    b = cross(n, t)
+    return normalize(t * x + b * y + n * z)
+
+
+def restir_direct(scene, env, pos, n, albedo, rng, counters):
+    mix_local, mix_delta = f32(8.0) / f32(9.0), f32(1.0) / f32(9.0)
+    r = dict(L=V(0, 0, 0), wi=V(0, 0, 0), pdf=f32(0), w=f32(0), wsum=f32(0), m=0, light=0)
+
+    def update(wi, pdf_sel, li, s, light):   # ReservoirUpdate
+        new_sum = r["wsum"] + s
+        accept = s / new_sum if new_sum > 0 else f32(0.0)
+        if rng.next_float() < accept:
+            r.update(wi=wi, pdf=pdf_sel, L=li, w=s, light=light)
+        r["wsum"] = new_sum
+        r["m"] += 1
+
+    for _ in range(8):
+        wi = sample_hemisphere_cosine(n, rng)
+        nl = fmax(f32(0.0), dot(n, wi))
+        pdf_sel = fmax(EPS_MIN, fmax(EPS_MIN, cos_pdf(n, wi)) * mix_local)
+        li = env.sky(wi)
+        update(wi, pdf_sel, li, luminance(albedo * li * ((nl / pdf_sel) * INV_PI)), 1)
+    wi = normalize(env.dir_light_dir)
+    nl = fmax(f32(0.0), dot(n, wi))
+    pdf_sel = fmax(EPS_MIN, mix_delta)
+    update(wi, pdf_sel, env.dir_light_radiance, luminance(albedo * env.dir_light_radiance * ((nl / pdf_sel) * INV_PI)), 2)
+
+    contrib = V(0, 0, 0)
+    if r["m"] > 0 and r["wsum"] > 0 and r["w"] > 0:
+        wi = r["wi"]
+        nl = fmax(f32(0.0), dot(n, wi))
+        if nl > 0 and dot(n, wi) > 0:   # Visible(): nl <= 0 -> false, else a shadow ray
+            counters["shadow"] += 1
+            if not scene.occluded(ray_normal_offset(pos, n, wi), f32(1e29)):
+                pdf_sel = fmax(EPS_MIN, mix_delta) if r["light"] == 2 else fmax(EPS_MIN, cos_pdf(n, wi) * mix_local)
+                li = env.dir_light_radiance if r["light"] == 2 else env.sky(wi)
+                f_over_p = albedo * li * ((nl / pdf_sel) * INV_PI)
+                w = r["wsum"] / f32(max(1, r["m"])) / fmax(EPS_MIN, r["w"])
+                contrib = f_over_p * w
+    return contrib
+
+
+def safe_color(c):
+    def one(v):
+        v = v if math.isfinite(float(v)) else f32(0.0)
+        return fmin(f32(1e6), fmax(f32(-1e6), v))
+    return V(one(c.x), one(c.y), one(c.z))
+
+
+def to_byte(x): return int(f32(255.99) * fmin(f32(1.0), fmax(f32(0.0), x)))
+
+
+def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noise=1):
+    """PrimaryVisibilityKernel + PathTraceKernel (reuse off).  Returns dict(rgba8, depth, sphere = primary hit (sphere id, or
+    -1 - triangle id, or -1 for the sky), radiance, seg = TraceNext calls per sample, counters)."""
+    env = Env(sun_dir)
+    n_px = width * height
+    out = dict(rgba8=np.zeros(n_px, np.int32), depth=np.zeros(n_px, np.float32), sphere=np.full(n_px, -1, np.int32), hit=np.zeros(n_px, bool),
+               radiance=np.zeros((n_px, 3), np.float32), seg=np.zeros((spp, n_px), np.uint8))
+    counters = dict(bounce=0, shadow=0)
+    with np.errstate(all="ignore"):
+        for index in range(n_px):
+            ray = primary_ray(cam, index, width, height)
+            hit = scene.trace_closest(ray)
+            l_frame = V(0, 0, 0)
+            if hit is None:
+                gpos = ray.o + ray.d * f32(1e6)        # GpuGBuffer.StoreMiss
+            else:
+                t, gn, galb, gshade, gior, sid = hit
+                gpos = ray.o + ray.d * t
+                out["sphere"][index] = sid
+                out["hit"][index] = True
+                packed_ior = int(fmax(f32(0.0), fmin(f32(65535.0), gior * f32(1000.0)))) & 0xFFFF   # FloatToI16
+            for s in range(max(1, spp)):
+                rng = RNG(index, width, height, frame, s, 0xC0FFEE, lock_noise)
+                if hit is None:
+                    l_frame = l_frame + safe_color(env.sky(primary_ray(cam, index, width, height).d))
+                    continue
+                pos, nrm, alb, shade, ior = gpos, normalize(gn), galb, gshade, f32(packed_ior) / f32(1000.0)
+                li, thr = V(0, 0, 0), V(1, 1, 1)
+                I = normalize(pos - cam.origin)
+                seg = 0
+                for depth in range(max_depth):
+                    if shade == 1:      # mirror
+                        nxt = ray_normal_offset(pos, nrm, I - nrm * (f32(2.0) * dot(I, nrm)))
+                        thr = thr * alb
+                    elif shade == 2:    # glass
+                        n_use = nrm
+                        outside = dot(I, nrm) < 0
+                        if not outside:
+                            n_use = n_use * f32(-1.0)
+                        g = ior if ior > 0 else f32(1.5)
+                        eta_i, eta_t = (f32(1.0), g) if outside else (g, f32(1.0))
+                        dir_r = I - n_use * (f32(2.0) * dot(I, n_use))
+                        eta = eta_i / eta_t
+                        cos_i = -dot(I, n_use)
+                        k = f32(1.0) - eta * eta * (f32(1.0) - cos_i * cos_i)
+                        refr_ok = not (k < 0)
+                        dir_t = normalize(I * eta + n_use * (eta * cos_i - np.sqrt(k))) if refr_ok else V(0, 0, 0)
+                        c = abs(dot(I, n_use))
+                        r0 = (eta_i - eta_t) / (eta_i + eta_t)
+                        r0 = r0 * r0
+                        om = f32(1.0) - c
+                        om2 = om * om
+                        fr = r0 + (f32(1.0) - r0) * (om2 * om2 * om)
+                        xi = rng.next_float()
+                        nxt = ray_normal_offset(pos, n_use, dir_r) if (not refr_ok or xi < fr) else ray_normal_offset(pos, -n_use, dir_t)
+                        if refr_ok and xi >= fr:
+                            tint = V(1, 1, 1) if (alb.x == 0 and alb.y == 0 and alb.z == 0) else alb
+                            thr = thr * tint * ((eta_i * eta_i) / (eta_t * eta_t))
+                    else:               # Lambert: ReSTIR-DI + cosine bounce
+                        li = li + thr * restir_direct(scene, env, pos, nrm, alb, rng, counters)
+                        wi = sample_hemisphere_cosine(nrm, rng)
+                        nxt = ray_normal_offset(pos, nrm, wi)
+                        thr = thr * alb
+                        if depth >= 3:
+                            mc = fmax(thr.x, fmax(thr.y, thr.z))
+                            mc = fmax(fmin(mc, f32(0.98)), f32(0.05))
+                            if rng.next_float() > mc:
+                                thr = V(0, 0, 0)
+                                break
+                            thr = thr * (f32(1.0) / mc)
+                    counters["bounce"] += 1
+                    seg += 1
+                    h2 = scene.trace_closest(nxt)     # TraceNext
+                    if h2 is None:
+                        li = li + thr * env.sky(nxt.d)
+                        break
+                    pos, nrm, alb, shade, ior = nxt.o + nxt.d * h2[0], normalize(h2[1]), h2[2], h2[3], h2[4]
+                    I = nxt.d
+                out["seg"][s, index] = seg
+                l_frame = l_frame + safe_color(li)
+            l_out = l_frame * (f32(1.0) / f32(max(1, spp)))
+            out["radiance"][index] = (l_out.x, l_out.y, l_out.z)
+            dc = gpos - cam.origin
+            out["depth"][index] = np.sqrt(dc.x * dc.x + dc.y * dc.y + dc.z * dc.z)
+            rgba = (255 << 24) | (to_byte(l_out.x) << 16) | (to_byte(l_out.y) << 8) | to_byte(l_out.z)
+            out["rgba8"][index] = rgba - (1 << 32) if rgba >= (1 << 31) else rgba
+    out["counters"] = counters
+    return out
