@@ -10,7 +10,8 @@ run here): two restatements made separately from the same lines must agree.
                                              Engine/SceneDeviceViews.cs:540-558, 173-237, 270-327 (textures, alpha cut-out, two-sided)
   SampleTextureLinear(RGB_A), SampleMaskLinear / Point, TexelRaw
                                              Engine/SceneDeviceViews.cs:330-472
-  PrimaryVisibilityKernel, PathTraceKernel   Engine/RTRay.cs:188-325 (reuse off), ReSTIR_Direct :438-543, helpers :546-671
+  PrimaryVisibilityKernel, PathTraceKernel   Engine/RTRay.cs:188-325, ReSTIR_Direct :438-543 with temporal / spatial reuse
+                                             (:339-435, 475-516; BakeCameraDerived RTRenderer.cs:241-263), helpers :546-671
   GpuFramebuffer.Store / PackRGBA8           Engine/RTRay.cs:59-76
 
 Differences by construction: every primitive is tested (no TLAS / BLAS culling: the boxes only prune; scenes with exactly
@@ -122,6 +123,18 @@ class Camera:
             d = V(*translate)
             self.origin = self.origin + d
             self.lower_left = self.lower_left + d
+        # RTRenderer.BakeCameraDerived (RTRenderer.cs:241-263): what the kernels read of the PREVIOUS camera for reprojection
+        center = self.lower_left + self.horizontal * f32(0.5) + self.vertical * f32(0.5)
+        self.forward = normalize(center - self.origin)
+        self.up = normalize(self.vertical)
+        self.right = normalize(cross(self.forward, self.up))
+
+        def length(v):
+            return np.sqrt(v.x * v.x + v.y * v.y + v.z * v.z)
+        focus, half = length(center - self.origin), f32(0.5) * length(self.vertical)
+        self.fov_y = f32(2.0) * f32(np.arctan(half / focus if focus > f32(1e-6) else half))
+        lh, lv = length(self.horizontal), length(self.vertical)
+        self.aspect = lh / lv if (lh > f32(1e-6) and lv > f32(1e-6)) else f32(width) / f32(max(1, height))
 
 
 class Ray:
@@ -360,7 +373,47 @@ def sample_hemisphere_cosine(n, rng):
     return normalize(t * x + b * y + n * z)
 
 
-def restir_direct(scene, env, pos, n, albedo, rng, counters):
+def _hash(x):   # RTRay.Hash
+    x &= M32
+    x ^= x >> 17; x = (x * 0xED5AD4BB) & M32; x ^= x >> 11; x = (x * 0xAC4C1B51) & M32; x ^= x >> 15; x = (x * 0x31848BAB) & M32; x ^= x >> 14
+    return x
+
+
+class Reuse:
+    """What ReSTIR_Direct reads when a reuse flag is set: the previous camera, the previous frame's reservoirs, the CURRENT
+    frame's G-buffer (SpatialCompatible), the frame number."""
+
+    def __init__(self, temporal, spatial, prev_cam, res_prev, gb, cam, width, height, frame):
+        self.temporal, self.spatial, self.prev_cam, self.res_prev, self.gb, self.cam = temporal, spatial, prev_cam, res_prev, gb, cam
+        self.width, self.height, self.frame = width, height, frame
+
+    def reproject(self, pos):   # ReprojectToPrevPixel
+        c = self.prev_cam
+        p = pos - c.origin
+        x, y, z = dot(p, c.right), dot(p, c.up), dot(p, c.forward)
+        if z <= f32(1e-4):
+            return -1
+        tan_half = f32(np.tan(f32(0.5) * c.fov_y))
+        ndc_x, ndc_y = x / (z * tan_half * c.aspect), y / (z * tan_half)
+        px, py = int(f32(0.5) * (ndc_x + f32(1.0)) * f32(self.width)), int(f32(0.5) * (ndc_y + f32(1.0)) * f32(self.height))
+        if not (0 <= px < self.width and 0 <= py < self.height):
+            return -1
+        return py * self.width + px
+
+    def distance(self, idx):   # DistanceFromCamera(gb.worldPos[idx])
+        d = self.gb["pos"][idx] - self.cam.origin
+        return np.sqrt(d.x * d.x + d.y * d.y + d.z * d.z)
+
+    def compatible(self, a, b, n_a):   # SpatialCompatible
+        if self.gb["obj"][a] == self.gb["obj"][b]:
+            return True
+        if dot(n_a, normalize(self.gb["nrm"][b])) < f32(0.85):
+            return False
+        z_a, z_b = self.distance(a), self.distance(b)
+        return abs(z_a - z_b) / fmax(f32(1e-3), z_a) < f32(0.05)
+
+
+def restir_direct(scene, env, pos, n, albedo, rng, counters, reuse=None, index=0, out_res=None):
     mix_local, mix_delta = f32(8.0) / f32(9.0), f32(1.0) / f32(9.0)
     r = dict(L=V(0, 0, 0), wi=V(0, 0, 0), pdf=f32(0), w=f32(0), wsum=f32(0), m=0, light=0)
 
@@ -382,6 +435,38 @@ def restir_direct(scene, env, pos, n, albedo, rng, counters):
     nl = fmax(f32(0.0), dot(n, wi))
     pdf_sel = fmax(EPS_MIN, mix_delta)
     update(wi, pdf_sel, env.dir_light_radiance, luminance(albedo * env.dir_light_radiance * ((nl / pdf_sel) * INV_PI)), 2)
+
+    def import_prev(prev_idx):   # ImportFromPrevReservoir
+        if prev_idx < 0 or len(reuse.res_prev) <= prev_idx or not reuse.compatible(index, prev_idx, n):
+            return
+        pr = reuse.res_prev[prev_idx]
+        if not (pr["m"] > 0 and pr["w"] > 0 and pr["wSum"] > 0):
+            return
+        wi = V(*[pr["wi"][k] for k in "XYZ"])
+        lid = 2 if pr["lightId"] == 2 else 1
+        li = env.dir_light_radiance if lid == 2 else env.sky(wi)
+        nl = fmax(f32(0.0), dot(n, wi))
+        pdf_here = fmax(EPS_MIN, mix_delta) if lid == 2 else fmax(EPS_MIN, cos_pdf(n, wi) * mix_local)
+        s_here = luminance(albedo * li * ((nl / pdf_here) * INV_PI))
+        w_src = pr["wSum"] / (f32(max(1, int(pr["m"]))) * fmax(EPS_MIN, pr["w"]))
+        update(wi, pdf_here, li, s_here * w_src, lid)
+
+    if reuse is not None and reuse.temporal:
+        prev_idx = reuse.reproject(pos)
+        if prev_idx >= 0:
+            import_prev(prev_idx)
+    if reuse is not None and reuse.spatial:
+        h = _hash(index ^ _hash((reuse.frame & M32) ^ _hash(0xB31F5AB1)))   # Hash3(index, frame, 0xB31F5AB1)
+        rot, r_ = h & 3, 1 + ((h >> 2) & 1)
+        x0, y0 = index % reuse.width, index // reuse.width
+
+        def rx(x, y): return x if rot == 0 else (-y if rot == 1 else (-x if rot == 2 else y))
+        def ry(x, y): return y if rot == 0 else (x if rot == 1 else (-y if rot == 2 else -x))
+        for (ox, oy) in ((-r_, 0), (r_, 0), (0, -r_), (0, r_), (-r_, -r_), (r_, -r_), (-r_, r_), (r_, r_)):   # Neighbor8
+            nx, ny = x0 + rx(ox, oy), y0 + ry(ox, oy)
+            import_prev(ny * reuse.width + nx if (0 <= nx < reuse.width and 0 <= ny < reuse.height) else -1)
+    if out_res is not None:   # "outRes = r" (the reservoir before the visibility test)
+        out_res.update(r)
 
     contrib = V(0, 0, 0)
     if r["m"] > 0 and r["wsum"] > 0 and r["w"] > 0:
@@ -408,7 +493,7 @@ def safe_color(c):
 def to_byte(x): return int(f32(255.99) * fmin(f32(1.0), fmax(f32(0.0), x)))
 
 
-def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noise=1):
+def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noise=1, temporal=0, spatial=0, prev_cam=None, res_prev=None, res_cur=None):
     """PrimaryVisibilityKernel + PathTraceKernel (reuse off).  Returns dict(rgba8, depth, sphere = primary hit (sphere id, or
     -1 - triangle id, or -1 for the sky), radiance, seg = TraceNext calls per sample, counters)."""
     env = Env(sun_dir)
@@ -417,9 +502,18 @@ def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noi
                radiance=np.zeros((n_px, 3), np.float32), seg=np.zeros((spp, n_px), np.uint8))
     counters = dict(bounce=0, shadow=0)
     with np.errstate(all="ignore"):
+        # PrimaryVisibilityKernel over the whole image first: the reuse tests read the G-buffer of OTHER pixels
+        primary = [scene.trace_closest(primary_ray(cam, i, width, height)) for i in range(n_px)]
+        gb = dict(pos=[], nrm=[], obj=[])
+        for i, h0 in enumerate(primary):
+            r0 = primary_ray(cam, i, width, height)
+            gb["pos"].append(r0.o + r0.d * (f32(1e6) if h0 is None else h0[0]))
+            gb["nrm"].append(V(0, 1, 0) if h0 is None else h0[1])                      # StoreMiss: normal (0, 1, 0), objId -1
+            gb["obj"].append(-1 if (h0 is None or h0[5] >= 0) else -1 - h0[5])        # spheres report objId -1, triangles their id
+        reuse = Reuse(temporal, spatial, prev_cam if prev_cam is not None else cam, res_prev, gb, cam, width, height, frame) if (temporal or spatial) else None
         for index in range(n_px):
             ray = primary_ray(cam, index, width, height)
-            hit = scene.trace_closest(ray)
+            hit = primary[index]
             l_frame = V(0, 0, 0)
             if hit is None:
                 gpos = ray.o + ray.d * f32(1e6)        # GpuGBuffer.StoreMiss
@@ -438,6 +532,7 @@ def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noi
                 li, thr = V(0, 0, 0), V(1, 1, 1)
                 I = normalize(pos - cam.origin)
                 seg = 0
+                wrote_reservoir = False
                 for depth in range(max_depth):
                     if shade == 1:      # mirror
                         nxt = ray_normal_offset(pos, nrm, I - nrm * (f32(2.0) * dot(I, nrm)))
@@ -467,7 +562,14 @@ def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noi
                             tint = V(1, 1, 1) if (alb.x == 0 and alb.y == 0 and alb.z == 0) else alb
                             thr = thr * tint * ((eta_i * eta_i) / (eta_t * eta_t))
                     else:               # Lambert: ReSTIR-DI + cosine bounce
-                        li = li + thr * restir_direct(scene, env, pos, nrm, alb, rng, counters)
+                        first = not wrote_reservoir and res_cur is not None      # only the first Lambert vertex of a sample imports and publishes
+                        res = {} if first else None
+                        li = li + thr * restir_direct(scene, env, pos, nrm, alb, rng, counters, reuse if first else None, index, res)
+                        if first:
+                            rc = res_cur[index]
+                            rc["L"], rc["wi"] = (res["L"].x, res["L"].y, res["L"].z), (res["wi"].x, res["wi"].y, res["wi"].z)
+                            rc["pdf"], rc["w"], rc["wSum"], rc["m"], rc["lightId"] = res["pdf"], res["w"], res["wsum"], res["m"], res["light"]
+                            wrote_reservoir = True
                         wi = sample_hemisphere_cosine(nrm, rng)
                         nxt = ray_normal_offset(pos, nrm, wi)
                         thr = thr * alb

@@ -269,3 +269,48 @@ def test_independent_python_restatement_agrees_on_triangles():
         num = np.sqrt(np.mean((got["radiance"].astype(np.float64) - ref.radiance[:, :3]) ** 2))
         assert num / den < 2e-5, (variant, num / den)
         assert (got["rgba8"] != ref.rgba8).mean() < 0.005
+
+
+@pytest.mark.parametrize("temporal,spatial", [(1, 1), (1, 0), (0, 1)])
+def test_independent_python_restatement_agrees_on_restir_reuse(temporal, spatial):
+    """The second restatement with ReSTIR temporal / spatial reuse (ReprojectToPrevPixel, SpatialCompatible, Neighbor8,
+    ImportFromPrevReservoir, the reservoir ping-pong; RTRay.cs:339-435, 475-516) over three frames of a moving camera: the
+    reservoirs every frame leaves behind and the images agree with the oracle."""
+    from tests import pyref
+    from ilgpu_raytracing_b200 import layouts
+    W, H, spp, depth = 40, 24, 2, 3
+    spec = scenes.default_scene()
+    sc = oracle_scene_from_spec(spec)
+    psc = pyref.Scene(spec.spheres, spec.textures)
+    ores = [np.zeros(W * H, orc.RESERVOIR), np.zeros(W * H, orc.RESERVOIR)]
+    pres = [np.zeros(W * H, orc.RESERVOIR), np.zeros(W * H, orc.RESERVOIR)]
+    prev_o = prev_p = None
+    imported = 0
+    for frame in range(3):
+        origin = (0.07 * frame, 1.0 + 0.02 * frame, 3.0 - 0.05 * frame)
+        cam_o = orc.camera_create(W, H, 60.0, origin, (0.0, 0.5, 0.0))
+        orc.camera_bake(cam_o, W, H)
+        cam_p = pyref.Camera(W, H, 60.0, origin=origin, look_at=(0.0, 0.5, 0.0))
+        prev_o = cam_o.copy() if prev_o is None else prev_o
+        prev_p = cam_p if prev_p is None else prev_p
+        ci = frame & 1
+        ref = orc.render(sc, cam_o, orc.make_config(W, H, spp=spp, max_depth=depth, frame=frame, rng_lock_noise=0, temporal=temporal, spatial=spatial),
+                         prev_cam=prev_o, res_prev=ores[ci ^ 1], res_cur=ores[ci])
+        got = pyref.render(psc, cam_p, W, H, spp, depth, layouts.default_sun_dir(), frame=frame, lock_noise=0, temporal=temporal, spatial=spatial,
+                           prev_cam=prev_p, res_prev=pres[ci ^ 1], res_cur=pres[ci])
+        assert np.array_equal(got["seg"], ref.segCount), frame
+        assert got["counters"]["bounce"] == ref.counters["raysBounce"] and got["counters"]["shadow"] == ref.counters["raysShadow"], frame
+        a, b = pres[ci], ores[ci]
+        assert np.array_equal(a["m"], b["m"]) and np.array_equal(a["lightId"], b["lightId"]), frame
+        for f in ("wSum", "w", "pdf"):   # the texture coordinates of the textured spheres go through atan2 / acos: numpy's vs the oracle's kernels
+            assert np.allclose(a[f], b[f], rtol=1e-3, atol=1e-7) and (np.abs(a[f] - b[f]) > 2e-5 * np.abs(b[f]) + 1e-7).mean() < 0.02, (frame, f)
+        for f in ("wi", "L"):
+            for c in "XYZ":
+                assert np.allclose(a[f][c], b[f][c], rtol=2e-5, atol=2e-6), (frame, f, c)
+        den = np.sqrt(np.mean(ref.radiance[:, :3].astype(np.float64) ** 2))
+        num = np.sqrt(np.mean((got["radiance"].astype(np.float64) - ref.radiance[:, :3]) ** 2))
+        assert num / den < 2e-5, (frame, num / den)
+        assert (got["rgba8"] != ref.rgba8).mean() < 0.01
+        imported += int((b["m"] > 9).sum()) if frame > 0 else 0
+        prev_o, prev_p = cam_o.copy(), cam_p
+    assert imported > 0   # frames 1 and 2 really imported previous reservoirs
