@@ -13,6 +13,7 @@ run here): two restatements made separately from the same lines must agree.
   PrimaryVisibilityKernel, PathTraceKernel   Engine/RTRay.cs:188-325, ReSTIR_Direct :438-543 with temporal / spatial reuse
                                              (:339-435, 475-516; BakeCameraDerived RTRenderer.cs:241-263), helpers :546-671
   GpuFramebuffer.Store / PackRGBA8           Engine/RTRay.cs:59-76
+  TaaResolveKernel, BilinearUpsampleKernel   Engine/RTTaa.cs:117-262, Engine/RTRenderer.cs:287-346 (vectorised, end of the file)
 
 Differences by construction: every primitive is tested (no TLAS / BLAS culling: the boxes only prune; scenes with exactly
 coincident primitives, whose equal-t ties the visiting order decides, are therefore out of its reach), and the transcendental
@@ -598,3 +599,102 @@ def render(scene, cam, width, height, spp, max_depth, sun_dir, frame=0, lock_noi
             out["rgba8"][index] = rgba - (1 << 32) if rgba >= (1 << 31) else rgba
     out["counters"] = counters
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------- present chain
+# RTTaa.TaaResolveKernel + helpers (Engine/RTTaa.cs:117-262) and BilinearUpsampleKernel (Engine/RTRenderer.cs:287-346), vectorised
+# over the output image with numpy float32 arrays (every operation still rounds to binary32 like the scalar C#).
+def _unpack_srgb(rgba):
+    out = []
+    for sh in (16, 8, 0):
+        c = ((rgba >> sh) & 255).astype(np.float32) / f32(255.0)
+        lin = np.power((c + f32(0.055)) / f32(1.055), f32(2.4), dtype=np.float32)
+        out.append(np.where(c <= f32(0.04045), c / f32(12.92), lin).astype(np.float32))
+    return out
+
+
+def _pack_srgb(c3):
+    chans = []
+    for c in c3:
+        l = np.maximum(f32(0.0), np.minimum(f32(1.0), c))
+        s = np.where(l <= f32(0.0031308), f32(12.92) * l, f32(1.055) * np.power(l, f32(1.0) / f32(2.4), dtype=np.float32) - f32(0.055)).astype(np.float32)
+        chans.append(np.rint(np.maximum(f32(0.0), np.minimum(f32(1.0), s)) * f32(255.0)).astype(np.int64))   # XMath.Round: half to even
+    v = (255 << 24) | (chans[0] << 16) | (chans[1] << 8) | chans[2]
+    return np.where(v >= (1 << 31), v - (1 << 32), v).astype(np.int32)
+
+
+def _catrom(a, b, t):
+    tt = t * (f32(2.0) - t)
+    return [x * (f32(1.0) - tt) + y * tt for x, y in zip(a, b)]
+
+
+def _sample_catrom_srgb(img, w, h, x, y):
+    x1 = np.clip(np.floor(x).astype(np.int64), 0, w - 1)
+    y1 = np.clip(np.floor(y).astype(np.int64), 0, h - 1)
+    fx, fy = x - x1.astype(np.float32), y - y1.astype(np.float32)
+    x2, y2 = np.minimum(x1 + 1, w - 1), np.minimum(y1 + 1, h - 1)
+    c00, c10, c01, c11 = (_unpack_srgb(img[j * w + i]) for j, i in ((y1, x1), (y1, x2), (y2, x1), (y2, x2)))
+    return _catrom(_catrom(c00, c10, fx), _catrom(c01, c11, fx), fy)
+
+
+class Taa:
+    """RTTaa: history colour / object id, _historyValid; resolve() = ResolveUpsample + TaaResolveKernel with the reference's tunables."""
+
+    def __init__(self, out_w, out_h):
+        self.w, self.h, self.valid = out_w, out_h, False
+        self.hist_color, self.hist_obj = np.zeros(out_w * out_h, np.int32), np.zeros(out_w * out_h, np.int32)
+
+    def resolve(self, low_color, low_obj, in_w, in_h, feedback=0.075, sharpness=0.10):
+        low_color, low_obj = np.asarray(low_color, np.int32).astype(np.int64), np.asarray(low_obj, np.int32)
+        feedback, sharpness = f32(feedback), f32(sharpness)
+        idx = np.arange(self.w * self.h)
+        px, py = (idx % self.w).astype(np.float32), (idx // self.w).astype(np.float32)
+        sx = (px + f32(0.5)) * (f32(in_w) / f32(self.w)) - f32(0.5)
+        sy = (py + f32(0.5)) * (f32(in_h) / f32(self.h)) - f32(0.5)
+        with np.errstate(all="ignore"):
+            cur = _sample_catrom_srgb(low_color, in_w, in_h, sx, sy)
+            nmin, nmax = list(cur), list(cur)
+            for oy in (-1, 0, 1):
+                for ox in (-1, 0, 1):
+                    if ox == 0 and oy == 0:
+                        continue
+                    c = _sample_catrom_srgb(low_color, in_w, in_h, sx + f32(ox) * f32(0.5), sy + f32(oy) * f32(0.5))
+                    nmin = [np.minimum(a, b) for a, b in zip(nmin, c)]
+                    nmax = [np.maximum(a, b) for a, b in zip(nmax, c)]
+            ix = np.clip(np.rint(sx).astype(np.int64), 0, in_w - 1)
+            iy = np.clip(np.rint(sy).astype(np.int64), 0, in_h - 1)
+            obj = low_obj[iy * in_w + ix]
+            hist = _unpack_srgb(self.hist_color.astype(np.int64))
+            reset = (not self.valid) | (self.hist_obj != obj)
+            clamped = [np.minimum(hi, np.maximum(lo, v)) for v, lo, hi in zip(hist, nmin, nmax)]   # Clamp(): k * 0.0f
+            a = np.where(reset, f32(1.0), feedback).astype(np.float32)
+            accum = [h * (f32(1.0) - a) + c * a for h, c in zip(clamped, cur)]
+            sharp = [x * (f32(1.0) + f32(2.0) * sharpness) - (lo + hi) * (f32(0.5) * sharpness) for x, lo, hi in zip(accum, nmin, nmax)]
+            accum = [x * (f32(1.0) - sharpness) + s * sharpness for x, s in zip(accum, sharp)]
+            out = _pack_srgb(accum)
+        self.hist_color, self.hist_obj, self.valid = out.copy(), obj.astype(np.int32), True
+        return out
+
+
+def bilinear_upsample(src, src_w, src_h, dst_w, dst_h):   # BilinearUpsampleKernel
+    src = np.asarray(src, np.int32).astype(np.int64)
+    idx = np.arange(dst_w * dst_h)
+    x, y = (idx % dst_w).astype(np.float32), (idx // dst_w).astype(np.float32)
+    u = ((x + f32(0.5)) * f32(src_w) / f32(dst_w)) - f32(0.5)
+    v = ((y + f32(0.5)) * f32(src_h) / f32(dst_h)) - f32(0.5)
+    x0, y0 = np.clip(np.floor(u).astype(np.int64), 0, src_w - 1), np.clip(np.floor(v).astype(np.int64), 0, src_h - 1)
+    x1, y1 = np.clip(x0 + 1, 0, src_w - 1), np.clip(y0 + 1, 0, src_h - 1)
+    tx = np.clip(u - x0.astype(np.float32), f32(0.0), f32(1.0))
+    ty = np.clip(v - y0.astype(np.float32), f32(0.0), f32(1.0))
+
+    def unpack(p):
+        return [((p >> sh) & 255).astype(np.float32) * (f32(1.0) / f32(255.0)) for sh in (16, 8, 0)]
+    c00, c10, c01, c11 = unpack(src[y0 * src_w + x0]), unpack(src[y0 * src_w + x1]), unpack(src[y1 * src_w + x0]), unpack(src[y1 * src_w + x1])
+    chans = []
+    for k in range(3):
+        cx0 = c00[k] * (f32(1.0) - tx) + c10[k] * tx
+        cx1 = c01[k] * (f32(1.0) - tx) + c11[k] * tx
+        c = cx0 * (f32(1.0) - ty) + cx1 * ty
+        chans.append((f32(255.99) * np.minimum(f32(1.0), np.maximum(f32(0.0), c))).astype(np.int64))
+    val = (255 << 24) | (chans[0] << 16) | (chans[1] << 8) | chans[2]
+    return np.where(val >= (1 << 31), val - (1 << 32), val).astype(np.int32)
