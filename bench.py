@@ -165,7 +165,7 @@ def run_reference(args, wl, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
@@ -342,7 +342,8 @@ def main():
     tp = os.path.join(ROOT, "profiles", "r01b_extend_traffic_c4.json")
     if name == "C4" and not args.spp and world == 1 and os.path.exists(tp):
         t = json.load(open(tp))
-        traffic = t["dram_bytes_per_launch"]
+        # the capture's DRAM bytes of one frame's extend launches, per launch of THIS run (the capture ran the frame in two passes)
+        traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) / max(1, n_ext)
         issue = {"warp_instructions_per_ray": t["warp_instructions"] / max(1, n_rays), "ipc_per_smsp": t["warp_instructions"] / (t["sum_duration_ms"] * 1e-3 * 1.965e9 * 148 * 4),
                  "source": "profiles/r01b_extend_traffic_c4.json (ncu, all %d extend launches of one C4 frame)" % t["launches"]}
     roofline = {"bound": "hbm", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",

@@ -762,10 +762,14 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     const int64_t npxOwned = count_owned_pixels(cfg->width, cfg->height, cfg->tileSize, cfg->worldSize > 1 ? cfg->rank : 0, cfg->worldSize > 1 ? cfg->worldSize : 1);
     int S = cfg->samplesPerPass;
     if (S <= 0) {
-        // samples per wavefront pass: as many paths in flight as ~30 % of the device memory holds (208 B of path state and queue
-        // slots each), capped at 256 Mi.  Bigger passes mean fewer, longer launches: C4 on a 180 GB B200 runs 16-32 spp per
-        // pass and is ~18 % faster than with 16 Mi-path passes (launch tails of the deep, nearly empty wavefronts)
-        int64_t target = std::min<int64_t>(256ll << 20, (int64_t)(c->memTotal / 10 * 3 / 208));
+        // samples per wavefront pass: as many paths in flight as ~60 % of the device memory holds (208 B of path state and queue
+        // slots each), capped at 768 Mi (path indices are 32-bit).  Bigger passes mean fewer, longer launches: C4 on a 180 GB B200
+        // runs its 64 spp (531 M paths, 110 GB) in ONE pass - 191.2 ms against 193.1 ms in two passes of 32 spp, 197.8 ms in four,
+        // 230 ms with 16 Mi-path passes (launch tails of the deep, nearly empty wavefronts)
+        int64_t target = std::min<int64_t>(768ll << 20, (int64_t)(c->memTotal / 10 * 6 / 208));
+        size_t freeB = 0, totalB = 0;   // ... and never more than 85 % of what is free right now (plus what the path buffers already hold)
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) target = std::min<int64_t>(target, (int64_t)((freeB / 100 * 85 + c->pathCap * 208) / 208));
+        else (void)cudaGetLastError();
         target = std::max<int64_t>(target, 1ll << 20);
         if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) target = v; }
         S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned)));
