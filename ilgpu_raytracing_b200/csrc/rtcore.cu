@@ -419,7 +419,8 @@ struct rt_ctx {
     DevBuf<float> scratch;
     // counters
     DevBuf<int> counters; DevBuf<DeviceStats> dstats;
-    DeviceStats hstats; unsigned long long launches = 0;
+    DeviceStats* hstats = nullptr;   // page-locked: the end-of-frame copy of the device counters must not make rt_render wait for the frame
+    unsigned long long launches = 0;
     // kernel timing (extend kernels)
     std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool timeKernels = false;
     int* extColor = nullptr; size_t extColorBytes = 0;
@@ -566,7 +567,9 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
     int rc = size_extend_launch(c, RT_STACK_ENTRIES);
     if (rc != RT_OK) { rt_destroy(c); return rc; }
-    memset(&c->ds, 0, sizeof(c->ds)); memset(&c->hstats, 0, sizeof(c->hstats));
+    memset(&c->ds, 0, sizeof(c->ds));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->hstats), sizeof(DeviceStats), cudaHostAllocDefault));
+    memset(c->hstats, 0, sizeof(DeviceStats));
     *out = c;
     return RT_OK;
 }
@@ -585,6 +588,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
     if (c->ownStream) cudaStreamDestroy(c->ownStream);
+    if (c->hstats) cudaFreeHost(c->hstats);
     delete c;
     return RT_OK;
 }
@@ -767,9 +771,11 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         // runs its 64 spp (531 M paths, 110 GB) in ONE pass - 191.2 ms against 193.1 ms in two passes of 32 spp, 197.8 ms in four,
         // 230 ms with 16 Mi-path passes (launch tails of the deep, nearly empty wavefronts)
         int64_t target = std::min<int64_t>(768ll << 20, (int64_t)(c->memTotal / 10 * 6 / 208));
-        size_t freeB = 0, totalB = 0;   // ... and never more than 85 % of what is free right now (plus what the path buffers already hold)
-        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) target = std::min<int64_t>(target, (int64_t)((freeB / 100 * 85 + c->pathCap * 208) / 208));
-        else (void)cudaGetLastError();
+        if ((size_t)target > c->pathCap) {   // the buffers would have to grow: never beyond 85 % of what is free right now (plus what they already hold)
+            size_t freeB = 0, totalB = 0;
+            if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) target = std::min<int64_t>(target, (int64_t)((freeB / 100 * 85 + c->pathCap * 208) / 208));
+            else (void)cudaGetLastError();
+        }
         target = std::max<int64_t>(target, 1ll << 20);
         if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) target = v; }
         S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned)));
@@ -905,7 +911,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(c->evStop, st));
-    CUDA_TRY(cudaMemcpyAsync(&c->hstats, c->dstats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(c->hstats, c->dstats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
 #if RT_PHASE_STATS
     if (count) {
         unsigned long long h[32], z[32] = {0};
@@ -1108,11 +1114,11 @@ RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
     if (!c->rendered) return RT_OK;
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    out->raysPrimary = c->hstats.raysPrimary; out->raysBounce = c->hstats.raysBounce;
-    out->raysShadow = c->hstats.raysShadow + c->hstats.shadowProbed;   // ShadowOcclusion calls of the reference: own traces + those answered by a shared sun probe
-    out->reserved[1] = c->hstats.raysShadow + c->hstats.raysSunProbe;   // any-hit rays actually traced
-    out->reserved[2] = c->hstats.raysSunProbe;
-    out->wideNodes = c->hstats.wideNodes; out->trisTested = c->hstats.tris; out->spheresTested = c->hstats.spheres;
+    out->raysPrimary = c->hstats->raysPrimary; out->raysBounce = c->hstats->raysBounce;
+    out->raysShadow = c->hstats->raysShadow + c->hstats->shadowProbed;   // ShadowOcclusion calls of the reference: own traces + those answered by a shared sun probe
+    out->reserved[1] = c->hstats->raysShadow + c->hstats->raysSunProbe;   // any-hit rays actually traced
+    out->reserved[2] = c->hstats->raysSunProbe;
+    out->wideNodes = c->hstats->wideNodes; out->trisTested = c->hstats->tris; out->spheresTested = c->hstats->spheres;
     out->kernelLaunches = c->launches;
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, c->evStart, c->evStop) == cudaSuccess) out->lastRenderMs = ms;
