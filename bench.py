@@ -312,6 +312,8 @@ def main():
         ts = time.perf_counter()
         e2e_step()
         per_step.append(time.perf_counter() - ts)
+        if os.environ.get("RT_BENCH_DEBUG"):
+            print(f"e2e step {per_step[-1] * 1e3:.1f} ms, device {ctx.stats()['lastRenderMs']:.1f} ms", file=sys.stderr)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps       # the mean over exactly K steps is the reported number;
     e2e_median_ms = float(np.median(per_step)) * 1e3      # the median is beside it because a shared host adds rare 10-40 ms stalls to single steps

@@ -98,6 +98,7 @@ namespace ILGPU_Raytracing.Engine
         [DllImport(Lib)] public static extern int rt_render(IntPtr ctx, Camera* cam, Camera* prevCam, RtRenderConfig* cfg);
         [DllImport(Lib)] public static extern int rt_sync(IntPtr ctx);
         [DllImport(Lib)] public static extern int rt_download(IntPtr ctx, int which, void* dstHost, UIntPtr bytes);
+        [DllImport(Lib)] public static extern int rt_download_async(IntPtr ctx, int which, void* dstHost, UIntPtr bytes);   // queued; valid after rt_sync
         [DllImport(Lib)] public static extern int rt_buffer_bytes(IntPtr ctx, int which, out UIntPtr bytes);
         [DllImport(Lib)] public static extern int rt_get_device_buffer(IntPtr ctx, int which, out IntPtr devPtr, out UIntPtr bytes);
         [DllImport(Lib)] public static extern int rt_map_external_color(IntPtr ctx, IntPtr devPtr, UIntPtr bytes);

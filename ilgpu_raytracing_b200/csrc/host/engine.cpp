@@ -483,9 +483,10 @@ void Framebuffer::DownloadToCpu(int slot, int* color, float* depth, int* objectI
     size_t nb = 0;
     check(rt_buffer_bytes(_native, RT_BUF_RGBA8, &nb));
     if (nb / 4 != n) throw ArgumentOutOfRangeException("n");
-    check(rt_download(_native, RT_BUF_RGBA8, color, nb));
-    check(rt_download(_native, RT_BUF_DEPTH, depth, nb));
-    check(rt_download(_native, RT_BUF_OBJID, objectId, nb));
+    check(rt_download_async(_native, RT_BUF_RGBA8, color, nb));   // three copies, one wait
+    check(rt_download_async(_native, RT_BUF_DEPTH, depth, nb));
+    check(rt_download_async(_native, RT_BUF_OBJID, objectId, nb));
+    check(rt_sync(_native));
 }
 
 // ======================================================================================================= RTRenderer

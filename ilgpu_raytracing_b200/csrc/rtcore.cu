@@ -979,7 +979,10 @@ RT_API int rt_get_device_buffer(rt_ctx* c, int which, void** devPtr, size_t* byt
     return fail(RT_ERR_INVALID_STATE, "rt_get_device_buffer: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
 }
 
-RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
+static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wait);
+RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) { return download_impl(c, which, dst, bytes, true); }
+RT_API int rt_download_async(rt_ctx* c, int which, void* dst, size_t bytes) { return download_impl(c, which, dst, bytes, false); }
+static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wait) {
     if (!c || !dst) return fail(RT_ERR_INVALID_ARGUMENT, "rt_download: null argument");
     if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_download: nothing rendered yet");
     size_t need = 0;
@@ -991,6 +994,9 @@ RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
     const void* src = nullptr;
     const int npx = c->npx;
     const size_t g = (size_t)c->width * c->height;
+    if (!wait && !(which == RT_BUF_RGBA8 || which == RT_BUF_DEPTH || which == RT_BUF_OBJID || which == RT_BUF_RADIANCE || which == RT_BUF_ACCUM ||
+                   which == RT_BUF_TILE_RADIANCE || which == RT_BUF_PRESENT))
+        return fail(RT_ERR_UNSUPPORTED, "rt_download_async: this buffer is gathered through a shared staging buffer; use rt_download");
     auto scatterPrep = [&](size_t floats) -> cudaError_t {
         cudaError_t e = c->scratch.ensure(floats);
         if (e != cudaSuccess) return e;
@@ -1026,7 +1032,7 @@ RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) {
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (wait) CUDA_TRY(cudaStreamSynchronize(st));
     return RT_OK;
 }
 

@@ -18,7 +18,7 @@ _LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b
 
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
-           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex"]
+           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex", "rt_download_async"]
 
 
 class RtError(RuntimeError):
@@ -44,6 +44,7 @@ def lib() -> C.CDLL:
     l.rt_destroy.argtypes = [C.c_void_p]
     l.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     l.rt_scene_upload.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
+    l.rt_download_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     l.rt_scene_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
     l.rt_scene_upload_ex.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc), C.c_uint32]
     l.rt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig)]

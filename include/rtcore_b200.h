@@ -292,6 +292,10 @@ RT_API int rt_sync(rt_ctx* ctx); /* _cuda.Synchronize(), Engine/RTRenderer.cs:23
 /* ---- read-back: replaces Framebuffer.DownloadToCpu / CpuColor / CpuDepth / CpuObjectId
  *      (Engine/Framebuffer.cs:148-160).  bytes must equal the buffer's size. ---- */
 RT_API int rt_download(rt_ctx* ctx, int which, void* dstHost, size_t bytes);
+/* The same copy queued on the context's stream without waiting (dstHost should be page-locked and must stay valid until
+ * rt_sync): several buffers, one wait.  Framebuffer outputs only (RGBA8, depth, objId, radiance, accumulator, tile payload,
+ * presented image); RT_ERR_UNSUPPORTED for the buffers rt_download gathers through a staging buffer. */
+RT_API int rt_download_async(rt_ctx* ctx, int which, void* dstHost, size_t bytes);
 RT_API int rt_buffer_bytes(rt_ctx* ctx, int which, size_t* bytes);
 /* Device pointer of an output buffer (for NCCL / torch plumbing, no copy). */
 RT_API int rt_get_device_buffer(rt_ctx* ctx, int which, void** devPtr, size_t* bytes);

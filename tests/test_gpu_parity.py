@@ -552,3 +552,25 @@ def test_scene_commits_do_not_leak_device_memory(gpu_ctx):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 32 << 20, f"device memory shrank by {(free0 - free1) >> 20} MiB over 6 commits"
+
+
+def test_download_async(gpu_ctx):
+    """rt_download_async: several read-backs queued, one rt_sync; same bytes as rt_download; staged buffers are refused."""
+    import ctypes as C
+    import torch
+    from ilgpu_raytracing_b200 import native
+    W, H = 160, 90
+    sc = orc.Scene()
+    sc.build_default()
+    gpu_ctx.scene_upload(sc.arrays())
+    gpu_ctx.render(oracle_camera("C1B", W, H), L.make_render_config(W, H, spp=2, max_depth=2))
+    bufs = {w: torch.empty(W * H, dtype=torch.int32).pin_memory() for w in (L.RT_BUF_RGBA8, L.RT_BUF_DEPTH, L.RT_BUF_OBJID)}
+    for which, t in bufs.items():
+        native.check(gpu_ctx._l.rt_download_async(gpu_ctx.h, which, C.c_void_p(t.data_ptr()), t.numel() * 4))
+    gpu_ctx.sync()
+    assert np.array_equal(bufs[L.RT_BUF_RGBA8].numpy(), gpu_ctx.download(L.RT_BUF_RGBA8))
+    assert np.array_equal(bufs[L.RT_BUF_DEPTH].numpy().view(np.float32), gpu_ctx.download(L.RT_BUF_DEPTH))
+    assert np.array_equal(bufs[L.RT_BUF_OBJID].numpy(), gpu_ctx.download(L.RT_BUF_OBJID))
+    with pytest.raises(native.RtError) as e:
+        native.check(gpu_ctx._l.rt_download_async(gpu_ctx.h, L.RT_BUF_PRIM_ID, C.c_void_p(bufs[L.RT_BUF_RGBA8].data_ptr()), W * H * 4))
+    assert e.value.status == L.RT_ERR_UNSUPPORTED
