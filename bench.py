@@ -11,7 +11,8 @@ reported beside it), value = whole-job rays / device time with the scene residen
 
   e2e          same metric through the engine API (RTRenderer.RenderDirectToPbo + Framebuffer.DownloadToCpu)
                with host camera/config in and the 12 B/px framebuffer (RGBA8 + depth + objId) read back to
-               pinned host memory every step
+               pinned host memory every step; at N > 1 the step is render + NCCL gather + de-interleave on rank 0 + the
+               gathered RGBA8 image (4 B/px) read back to pinned host memory on rank 0
   roofline     extend (wide-BVH traversal) kernels: algorithmic node/primitive/queue bytes per frame divided
                by their summed CUDA-event duration, against the measured HBM copy bandwidth
   cpu_baseline the CPU oracle (line-by-line restatement of the reference kernels, all host threads) on a
@@ -290,18 +291,31 @@ def main():
     ms_per_step = ms / args.steps
     value = rays_pb / (ms_per_step * 1e-3) / 1e6
 
-    # ---- e2e through the engine API with host buffers (rank-local frame; N > 1 adds the gather above) ---------------
+    # ---- e2e through the engine API with host buffers --------------------------------------------------------------
     n_px = W * H
     pin = [torch.empty(n_px, dtype=torch.int32).pin_memory(), torch.empty(n_px, dtype=torch.float32).pin_memory(), torch.empty(n_px, dtype=torch.int32).pin_memory()]
     pin_np = [p.numpy() for p in pin]
-    ctx.set_stream(None)
+    ctx.set_stream(None if world == 1 else stream.cuda_stream)   # N > 1: the gather runs on torch's stream, so the frame does too
 
     e2e_frame = [0]
 
     def e2e_step():
         rdr.RenderDirectToPbo(None, W, H, e2e_frame[0], 0.0)    # host camera + knobs in; two launches' worth of work; Synchronize()
         e2e_frame[0] += 1 if progressive else 0
-        rdr.DownloadToCpu(*pin_np)                   # Framebuffer.DownloadToCpu: RGBA8 + depth + objId to host
+        if world == 1:
+            rdr.DownloadToCpu(*pin_np)               # Framebuffer.DownloadToCpu: RGBA8 + depth + objId to host
+            return
+        # N > 1: the frame a user gets is the gathered one - tile payloads to rank 0 over NCCL, de-interleave + tone-map there,
+        # the final RGBA8 image read back to page-locked host memory on rank 0
+        ptr, nbytes = ctx.device_buffer(L.RT_BUF_TILE_RADIANCE)
+        with torch.cuda.stream(stream):
+            src = torch.as_tensor(_Dev(ptr, nbytes // 16), device="cuda")
+            payload[: src.shape[0]].copy_(src, non_blocking=True)
+            dist.gather(payload, gathered, dst=0)
+            if rank == 0:
+                ctx.deinterleave_tiles(flat.data_ptr(), [r * max_npx for r in range(world)], world, W, H, tile, full.data_ptr(), full_rgba.data_ptr())
+                pin[0].copy_(full_rgba, non_blocking=True)
+        stream.synchronize()
 
     for _ in range(min(2, args.warmup)):
         e2e_step()
@@ -323,7 +337,7 @@ def main():
         e2e_s = float(t.item())
     e2e_value = rays_pb / e2e_s / 1e6
     h2d = 2 * L.CAMERA.itemsize + __import__("ctypes").sizeof(L.RtRenderConfig)
-    d2h = 12 * n_px
+    d2h = 12 * n_px if world == 1 else 4 * n_px   # N > 1: rank 0 reads the gathered RGBA8 image
 
     # ---- roofline of the extend kernels: one frame with per-launch events, one with device counters ---------------
     ctx.set_stream(stream.cuda_stream)
