@@ -242,17 +242,35 @@ def main():
         def __init__(self, ptr, nfloat4):
             self.__cuda_array_interface__ = {"shape": (nfloat4, 4), "typestr": "<f4", "data": (ptr, False), "version": 3}
 
+    # N > 1: the gather of frame k runs on its own stream while frame k + 1 renders (two payload buffers, events both ways)
+    overlap = world > 1 and not os.environ.get("RT_BENCH_NO_OVERLAP")
+    comm = torch.cuda.Stream() if world > 1 else None
+    payloads = [payload, torch.zeros_like(payload)] if world > 1 else None
+    ev_ready = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+    ev_done = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
+    step_no = [0]
+
     def step(cfg):
         """One frame on this rank (async on `stream`), plus the framebuffer gather for N > 1."""
         ctx.render(cam, cfg)
         if world > 1:
             ptr, nbytes = ctx.device_buffer(L.RT_BUF_TILE_RADIANCE)
+            b = step_no[0] & 1
+            step_no[0] += 1
+            gstream = comm if overlap else stream
             with torch.cuda.stream(stream):
                 src = torch.as_tensor(_Dev(ptr, nbytes // 16), device="cuda")
-                payload[: src.shape[0]].copy_(src, non_blocking=True)
-                dist.gather(payload, gathered, dst=0)
+                stream.wait_event(ev_done[b])                      # the gather that used this payload buffer two frames ago is through
+                payloads[b][: src.shape[0]].copy_(src, non_blocking=True)
+                ev_ready[b].record(stream)
+            with torch.cuda.stream(gstream):
+                gstream.wait_event(ev_ready[b])
+                dist.gather(payloads[b], gathered, dst=0)
                 if rank == 0:
+                    ctx.set_stream(gstream.cuda_stream)            # the de-interleave belongs to the gather, not to the next frame
                     ctx.deinterleave_tiles(flat.data_ptr(), [r * max_npx for r in range(world)], world, W, H, tile, full.data_ptr(), full_rgba.data_ptr())
+                    ctx.set_stream(stream.cuda_stream)
+                ev_done[b].record(gstream)
 
     def barrier():
         if world > 1:
@@ -273,6 +291,8 @@ def main():
         ev0.record(stream)
         for i in range(args.steps):
             step(cfg_for(0, args.warmup + i))   # progressive workloads advance the frame index (new samples every step)
+        if world > 1:
+            stream.wait_stream(comm)            # the timed region ends when the last gathered image is complete
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
