@@ -22,7 +22,13 @@ reported beside it), value = whole-job rays / device time with the scene residen
 
 N > 1 (torchrun, one process per GPU): the image is split into interleaved 32x32 screen tiles, the scene is
 replicated, every rank renders its tiles and the float4 tile payloads are gathered to rank 0 over NCCL and
-de-interleaved there, all inside the timed step ("strong" scaling: the frame is fixed).
+de-interleaved there, all inside the timed region ("strong" scaling: the frame is fixed); the gather of frame k runs on
+its own stream while frame k + 1 renders, and the region ends when the last gathered image is complete.
+
+Frames are submitted back to back (rt_render does not wait for the frame), so `value` is device throughput; the e2e leg waits
+for every frame, and on a shared host single steps pick up rare 10-40 ms stalls - hence `ms_per_step_median` beside the mean.
+Switches for diagnosis (not for reported numbers): RT_BENCH_TILE, RT_BENCH_NO_OVERLAP, RT_BENCH_NO_CLOCKS, RT_BENCH_NO_REFIT,
+RT_BENCH_DEBUG (per-step e2e wall / device times on stderr).
 """
 from __future__ import annotations
 
