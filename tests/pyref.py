@@ -157,15 +157,65 @@ def ray_normal_offset(origin, n, direction):   # MakeRayWithNormalOffset
 
 
 # ---------------------------------------------------------------------------------------------------------------- scene
-class Scene:
-    """spheres: SPHERE records (one identity instance each); textures: list of (h, w, 4) u8 RGBA; mesh: a MeshSpec with an
-    identity transform (positions, tris, texcoords, tri_uvs, tri_mat, materials) or None."""
+class Xf:
+    """One instance transform: objectToWorld (AFFINE record or None = identity), worldToObject = Scene.InvertRigidOrUniform of it
+    (Scene.cs:616-638: columns normalised and NOT transposed, divided by the mean column length), uniformScale; TransformPoint /
+    TransformVector / TransformRay (SceneDeviceViews.cs:475-493: the direction is not renormalised)."""
 
-    def __init__(self, spheres, textures, mesh=None):
+    def __init__(self, o2w=None):
+        self.identity = o2w is None
+        if self.identity:
+            self.scale = f32(1.0)
+            return
+        m = [[f32(o2w[f"m{r}{c}"]) for c in range(4)] for r in range(3)]
+        self.o2w = m
+
+        def col(c):
+            return V(m[0][c], m[1][c], m[2][c])
+
+        def length(v):
+            return np.sqrt(v.x * v.x + v.y * v.y + v.z * v.z)
+        self.scale = (length(col(0)) + length(col(1)) + length(col(2))) / f32(3.0)
+        inv = f32(1.0) / self.scale if self.scale > 0 else f32(1.0)
+        r0, r1, r2 = normalize(col(0)), normalize(col(1)), normalize(col(2))
+        w = [[r0.x * inv, r1.x * inv, r2.x * inv, f32(0.0)], [r0.y * inv, r1.y * inv, r2.y * inv, f32(0.0)], [r0.z * inv, r1.z * inv, r2.z * inv, f32(0.0)]]
+        it = self._vec(w, V(m[0][3], m[1][3], m[2][3])) * f32(-1.0)
+        w[0][3], w[1][3], w[2][3] = it.x, it.y, it.z
+        self.w2o = w
+
+    @staticmethod
+    def _vec(m, v):
+        return V(m[0][0] * v.x + m[0][1] * v.y + m[0][2] * v.z, m[1][0] * v.x + m[1][1] * v.y + m[1][2] * v.z, m[2][0] * v.x + m[2][1] * v.y + m[2][2] * v.z)
+
+    @staticmethod
+    def _point(m, p):
+        return V(m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3], m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3],
+                 m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3])
+
+    def ray_to_object(self, ray):
+        return ray if self.identity else Ray(self._point(self.w2o, ray.o), self._vec(self.w2o, ray.d))
+
+    def normal_to_world(self, n):   # bestNormal = Normalize(TransformVector(objectToWorld, normalObj))
+        return normalize(n if self.identity else self._vec(self.o2w, n))
+
+    def tmax_scale(self):   # "scale = inst.uniformScale > 0f ? inst.uniformScale : 1f"
+        return self.scale if self.scale > 0 else f32(1.0)
+
+
+class Scene:
+    """spheres: SPHERE records, one instance each (sphere_xf: an AFFINE objectToWorld per sphere, None = identity);
+    textures: list of (h, w, 4) u8 RGBA; mesh: a MeshSpec (positions, tris, texcoords, tri_uvs, tri_mat, materials,
+    object_to_world) or None."""
+
+    def __init__(self, spheres, textures, mesh=None, sphere_xf=None):
         self.spheres, self.textures, self.mesh = spheres, textures, mesh
+        self.sphere_xf = [Xf(None if sphere_xf is None else x) for x in (sphere_xf if sphere_xf is not None else [None] * len(spheres))]
         if mesh is not None:
             self.pos = [V(*p) for p in mesh.positions]
             self.uv = [(f32(t[0]), f32(t[1])) for t in mesh.texcoords]
+            o2w = mesh.object_to_world
+            ident = all(abs(float(o2w[f"m{r}{c}"]) - (1.0 if r == c else 0.0)) == 0.0 for r in range(3) for c in range(4))
+            self.mesh_xf = Xf(None if ident else o2w)
 
     def texel(self, tex, x, y):   # TexelRaw: clamp
         h, w, _ = tex.shape
@@ -316,13 +366,15 @@ class Scene:
         best = None
         closest = f32(1e30)
         for i, s in enumerate(self.spheres):
-            hit = self.intersect_sphere(ray, s)
+            xf = self.sphere_xf[i]
+            hit = self.intersect_sphere(xf.ray_to_object(ray), s)
             if hit is None:
                 continue
             t, nn = hit
             if not (t > f32(0.001) and t < f32(1e30)):     # TraverseBLAS_Sphere: one sphere per instance, tClosest starts at 1e30
                 continue
-            if not (t / f32(1.0) < closest):               # tWorld = tObj / scale
+            t = t / xf.tmax_scale()                        # tWorld = tObj / scale
+            if not (t < closest):
                 continue
             m = s["material"]
             kd = V(*[m["Kd"][k] for k in "XYZ"])
@@ -332,19 +384,20 @@ class Scene:
                 v = f32(np.arccos(fmin(f32(1.0), fmax(f32(-1.0), nn.y)))) / PI
                 col = self.sample_rgb(self.textures[int(m["DiffuseTexIndex"])], u, v)
             closest = t
-            best = (t, normalize(nn), col, int(s["shading"]), s["ior"] if s["ior"] > 0 else f32(1.0), i)   # TransformVector(identity) + Normalize
+            best = (t, xf.normal_to_world(nn), col, int(s["shading"]), s["ior"] if s["ior"] > 0 else f32(1.0), i)
         if self.mesh is not None:   # the mesh instance: triangles are always Lambert, ior 1 (TraceClosest :58-62)
-            th = self.closest_tri(ray)
-            if th is not None and th[0] / f32(1.0) < closest:
-                best = (th[0], normalize(th[1]), th[2], 0, f32(1.0), -1 - th[3])   # ids < 0: triangle -1 - id
+            th = self.closest_tri(self.mesh_xf.ray_to_object(ray))
+            if th is not None and th[0] / self.mesh_xf.tmax_scale() < closest:
+                best = (th[0] / self.mesh_xf.tmax_scale(), self.mesh_xf.normal_to_world(th[1]), th[2], 0, f32(1.0), -1 - th[3])   # ids < 0: triangle -1 - id
         return best
 
-    def occluded(self, ray, t_max):   # ShadowOcclusion / AnyHit_Sphere
-        for s in self.spheres:
-            hit = self.intersect_sphere(ray, s)
-            if hit is not None and hit[0] > f32(0.001) and hit[0] < t_max:
+    def occluded(self, ray, t_max):   # ShadowOcclusion / AnyHit_Sphere: tMaxObj = tMaxWorld * scale
+        for i, s in enumerate(self.spheres):
+            xf = self.sphere_xf[i]
+            hit = self.intersect_sphere(xf.ray_to_object(ray), s)
+            if hit is not None and hit[0] > f32(0.001) and hit[0] < t_max * xf.tmax_scale():
                 return True
-        return self.mesh is not None and self.any_tri(ray, t_max)
+        return self.mesh is not None and self.any_tri(self.mesh_xf.ray_to_object(ray), t_max * self.mesh_xf.tmax_scale())
 
 
 # ---------------------------------------------------------------------------------------------------------------- integrator

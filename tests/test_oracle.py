@@ -336,3 +336,38 @@ def test_independent_python_restatement_agrees_on_present_chain():
         diff = np.stack([np.abs(((a >> sh) & 255) - ((b >> sh) & 255)) for sh in (16, 8, 0)])
         assert diff.max() <= 1 and (diff > 0).mean() < 0.005, (frame, diff.max(), (diff > 0).mean())   # measured: identical on all four frames
         assert ((a >> 24) & 255 == 255).all()
+
+
+@pytest.mark.parametrize("mode", ["translated", "scaled"])
+def test_independent_python_restatement_agrees_on_instances(mode):
+    """The second restatement with instance transforms (TransformRay without renormalising, tWorld = tObj / scale, tMaxObj =
+    tMaxWorld * scale, Scene.InvertRigidOrUniform's un-transposed rotation, normals through objectToWorld): translated instances
+    against the oracle as it is; rotated + scaled ones - where the reference's own box culling depends on the visiting order
+     - against the oracle with every box taken, which is what a brute-force restatement computes."""
+    import dataclasses
+    from tests import pyref
+    from tests.util import SPECIAL_CAMERA, special_scene
+    from ilgpu_raytracing_b200 import layouts
+    W, H, spp, depth = 48, 28, 2, 3
+    spec = special_scene(mode)
+    m = spec.mesh
+    spec = dataclasses.replace(spec, mesh=dataclasses.replace(m, tris=m.tris[:-20], tri_uvs=m.tri_uvs[:-20], tri_mat=m.tri_mat[:-20]))
+    sphere_xf = [None] * len(spec.spheres)
+    for ids, xf in spec.sphere_instances:
+        assert len(ids) == 1
+        sphere_xf[int(ids[0])] = xf
+    psc = pyref.Scene(spec.spheres, spec.textures, spec.mesh, sphere_xf=sphere_xf)
+    got = pyref.render(psc, pyref.Camera(W, H, SPECIAL_CAMERA["fov"], origin=SPECIAL_CAMERA["origin"], look_at=SPECIAL_CAMERA["look_at"]),
+                       W, H, spp, depth, layouts.default_sun_dir())
+    cam_o = orc.camera_create(W, H, SPECIAL_CAMERA["fov"], SPECIAL_CAMERA["origin"], SPECIAL_CAMERA["look_at"])
+    ref = orc.render(oracle_scene_from_spec(spec), cam_o, orc.make_config(W, H, spp=spp, max_depth=depth, no_cull=1 if mode == "scaled" else 0))
+    hit = ref.primId >= 0
+    tri = hit & (ref.objId >= 0)
+    assert tri.sum() > W * H // 10 and (hit & ~tri).sum() > W * H // 50
+    assert np.array_equal(got["hit"], hit)
+    assert np.array_equal(-1 - got["sphere"][tri], ref.primId[tri]) and np.array_equal(got["sphere"][hit & ~tri], ref.primId[hit & ~tri])
+    same = (got["seg"] == ref.segCount).all(axis=0)
+    assert same.mean() > 0.995, same.mean()   # a rotated instance's rays go through sin / cos of the transform: rare last-bit decisions
+    den = np.sqrt(np.mean(ref.radiance[:, :3].astype(np.float64) ** 2))
+    num = np.sqrt(np.mean((got["radiance"][same].astype(np.float64) - ref.radiance[same, :3]) ** 2))
+    assert num / den < 1e-4, num / den
