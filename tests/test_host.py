@@ -199,3 +199,25 @@ def test_obj_loader_errors_follow_reference_exceptions(tmp_path):
     s.LoadObjInstance(obj)
     with pytest.raises(engine.EngineError, match="InvalidOperationException"):
         s.LoadObjInstance(obj)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the arm the driver times beside ours) runs without a GPU and prints ONE JSON line with the
+    contract's keys; the product arm must refuse to run without a CUDA device instead of falling back."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-500:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "C4" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    import torch
+    if not torch.cuda.is_available():
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--no-cpu-baseline"],
+                             capture_output=True, text=True, timeout=600, cwd=ROOT)
+        assert out.returncode != 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
