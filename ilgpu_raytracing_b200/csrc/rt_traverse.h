@@ -155,6 +155,9 @@ GenResult test_prim_general(const DeviceScene& sc, f3 o, f3 d, float4 q0, float4
 // int->float conversion (slow XU pipe), no per-node near/far selects, and the widening runs on the FMA pipe instead of the
 // saturated ALU pipe.  With O = o - 1024 a:  fma(m, a, O) = b * a + o.
 //   selector 0x4240 = { byte 0, byte 2 } = the qlo planes of the word's two children, 0x4341 = { byte 1, byte 3 } = the qhi planes
+#if !defined(__CUDACC__)
+inline float& host_plane_pad() { static float pad = 0.0f; return pad; }
+#endif
 RT_HD void plane_pair_1024(uint32_t w, uint32_t sel, float& fa, float& fb) {
 #if defined(__CUDA_ARCH__)
     const uint32_t h2 = __byte_perm(w, 0x64646464u, sel);
@@ -162,8 +165,11 @@ RT_HD void plane_pair_1024(uint32_t w, uint32_t sel, float& fa, float& fb) {
     fa = f.x; fb = f.y;
 #else
     const uint32_t ia = sel & 7u, ib = (sel >> 8) & 7u;
-    fa = 1024.0f + (float)((w >> (8u * ia)) & 0xFFu);
-    fb = 1024.0f + (float)((w >> (8u * ib)) & 0xFFu);
+    // host_plane_pad(): analysis knob of the host simulator (tests/hostsim) - child boxes widened by that many quanta on every
+    // side, to measure what a coarser (e.g. half-precision) slab test would cost in extra nodes and primitive tests; 0 in every test
+    const float pad = host_plane_pad();
+    fa = 1024.0f + (float)((w >> (8u * ia)) & 0xFFu) + ((ia & 1u) ? pad : -pad);   // odd bytes are the hi planes
+    fb = 1024.0f + (float)((w >> (8u * ib)) & 0xFFu) + ((ib & 1u) ? pad : -pad);
 #endif
 }
 #if defined(__CUDA_ARCH__)

@@ -53,6 +53,7 @@ HS_API void hs_scene_stats(HsScene* s, int64_t* out6) {
 }
 // 0 = node step + all of its primitives; n > 0 = k_extend's lane schedule (n node steps, one primitive step) with queued primitive groups
 HS_API void hs_set_lane_schedule(int nodeSteps) { host_lane_schedule() = nodeSteps < 0 ? 0 : nodeSteps; }
+HS_API void hs_set_plane_pad(float quanta) { host_plane_pad() = quanta < 0.0f ? 0.0f : quanta; }   // analysis knob, see rt_traverse.h
 // one ray; returns hit flag; out = {t, primId, instId, bu, bv}, counters = {nodes, tris, spheres}
 HS_API int hs_trace(HsScene* s, const float* o, const float* d, int anyHit, float tMax, unsigned flags, float* out5, uint32_t* counters3) {
     s->ds.triMaterials = (flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;

@@ -36,6 +36,7 @@ def lib():
         _lib.hs_bilinear_upsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
         _lib.hs_taa_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
         _lib.hs_set_lane_schedule.argtypes = [C.c_int]
+        _lib.hs_set_plane_pad.argtypes = [C.c_float]
         _lib.hs_pow.argtypes = [C.c_float, C.c_float]
         _lib.hs_pow.restype = C.c_float
         _lib.hs_render_reuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs), C.c_void_p, C.c_void_p]
@@ -45,6 +46,11 @@ def lib():
 def set_lane_schedule(node_steps: int):
     """0: a node step then all of its primitives; n > 0: k_extend's per-lane schedule (n node steps, one primitive step, queued groups)."""
     lib().hs_set_lane_schedule(int(node_steps))
+
+
+def set_plane_pad(quanta: float):
+    """Analysis knob: widen every child box of the wide BVH by that many quanta per side (0 = the shipped test)."""
+    lib().hs_set_plane_pad(float(quanta))
 
 
 class HostSimScene:
