@@ -167,7 +167,11 @@ RT_HD void plane_pair_1024(uint32_t w, uint32_t sel, float& fa, float& fb) {
     const uint32_t ia = sel & 7u, ib = (sel >> 8) & 7u;
     // host_plane_pad(): analysis knob of the host simulator (tests/hostsim) - child boxes widened by that many quanta on every
     // side, to measure what a coarser (e.g. half-precision) slab test would cost in extra nodes and primitive tests; 0 in every test
+#if !defined(__CUDACC__)
     const float pad = host_plane_pad();
+#else
+    const float pad = 0.0f;   // nvcc's host pass: the shipped test
+#endif
     fa = 1024.0f + (float)((w >> (8u * ia)) & 0xFFu) + ((ia & 1u) ? pad : -pad);   // odd bytes are the hi planes
     fb = 1024.0f + (float)((w >> (8u * ib)) & 0xFFu) + ((ib & 1u) ? pad : -pad);
 #endif
