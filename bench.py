@@ -392,12 +392,19 @@ def main():
         traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) / max(1, n_ext)
         issue = {"warp_instructions_per_ray": t["warp_instructions"] / max(1, n_rays), "ipc_per_smsp": t["warp_instructions"] / (t["sum_duration_ms"] * 1e-3 * 1.965e9 * 148 * 4),
                  "source": "profiles/r01b_extend_traffic_c4.json (ncu, all %d extend launches of one C4 frame)" % t["launches"]}
+    # FP32 roofline of the same kernels: 8 x 22 flops per wide node (eight slab tests), 51 per triangle test, 40 per
+    # sphere test, against 148 SMs x 128 lanes x 2 (FMA) x 1.965 GHz
+    flops = 176.0 * st_c["wideNodes"] + 51.0 * st_c["trisTested"] + 40.0 * st_c["spheresTested"]
+    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
+    fp32_achieved = flops / (trace_ms * 1e-3) / 1e12 if trace_ms > 0 else None
+    fp32 = {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (fp32_achieved / fp32_peak) if fp32_achieved else None,
+            "flops_per_ray": flops / max(1, n_rays), "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz"}
     roofline = {"bound": "hbm", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "peak_source": pk["source"], "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg_bytes / n_ext, "launches_per_step": n_ext, "avg_launch_ms": trace_ms / n_ext,
                 "extend_share_of_step": trace_ms / st_t["lastRenderMs"] if st_t["lastRenderMs"] else None,
                 "nodes_per_ray": st_c["wideNodes"] / max(1, n_rays), "prims_per_ray": (st_c["trisTested"] + st_c["spheresTested"]) / max(1, n_rays),
-                "issue": issue,
+                "issue": issue, "fp32": fp32,
                 "note": "node/primitive fetches are served by L1/L2 (the 63 MB BVH is cache resident): achieved = ALGORITHMIC bytes / time is cache-served bandwidth, "
                         "DRAM traffic is ~9 % of it; the kernel is bound by instruction issue (see DESIGN.md section 5)"}
 
