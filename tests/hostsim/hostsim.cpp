@@ -54,6 +54,72 @@ HS_API void hs_scene_stats(HsScene* s, int64_t* out6) {
 // 0 = node step + all of its primitives; n > 0 = k_extend's lane schedule (n node steps, one primitive step) with queued primitive groups
 HS_API void hs_set_lane_schedule(int nodeSteps) { host_lane_schedule() = nodeSteps < 0 ? 0 : nodeSteps; }
 HS_API void hs_set_plane_pad(float quanta) { host_plane_pad() = quanta < 0.0f ? 0.0f : quanta; }   // analysis knob, see rt_traverse.h
+// ---- ray capture + SIMT schedule simulator (analysis tool: tests/cpu_simt_schedule.py) ----------------------------------------
+struct CapRay { f3 o, d; int any; int wave; };
+static std::vector<CapRay> g_cap; static bool g_capOn = false; static int g_capWave = 0;
+static inline void cap_ray(f3 o, f3 d, int any) { if (g_capOn) g_cap.push_back({o, d, any, g_capWave}); }
+HS_API void hs_capture(int on) { g_capOn = on != 0; if (on) { g_cap.clear(); g_capWave = 0; } }
+HS_API long long hs_capture_count() { return (long long)g_cap.size(); }
+// Runs the captured waves through k_extend's warp loop on 32-lane warps (rays handed out in batches of 96 from a shared cursor,
+// `warps` warps taking turns one iteration at a time) and charges every executed phase its SASS length.
+//   policy 0: the shipped loop - refill, `nodeSteps` node steps, one primitive step when >= `primVote` lanes hold one (or no lane can step)
+//   policy 1: one phase per iteration, whichever has more ready lanes (node lanes weighted by cN / cP)
+// out: [0] rays, [1] iterations, [2] warp instructions, [3] node phases, [4] node lanes, [5] prim phases, [6] prim lanes, [7] node steps, [8] prim steps
+HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int primVote, int warps, double cRefill, double cNode, double cPrim, double cLoop, double* out) {
+    for (int i = 0; i < 9; i++) out[i] = 0.0;
+    std::vector<size_t> waveStart;
+    for (size_t i = 0; i < g_cap.size(); i++) if (i == 0 || g_cap[i].wave != g_cap[i - 1].wave) waveStart.push_back(i);
+    waveStart.push_back(g_cap.size());
+    struct Lane { Traversal<false, true> c; Traversal<true, true> a; LaneStack st; bool active = false; };
+    struct Warp { std::vector<Lane> lanes; size_t poolNext = 0, poolEnd = 0; bool exhausted = false; };
+    TraceCounters tc = {0, 0, 0};
+    for (size_t w = 0; w + 1 < waveStart.size(); w++) {
+        const size_t b = waveStart[w], e = waveStart[w + 1];
+        if (e == b || (g_cap[b].any != 0) != (anyHit != 0)) continue;
+        size_t cursor = b;
+        std::vector<Warp> ws((size_t)std::max(1, warps));
+        for (auto& wp : ws) wp.lanes.resize(32);
+        size_t live = ws.size();
+        out[0] += (double)(e - b);
+        while (live > 0) {
+            live = 0;
+            for (auto& wp : ws) {
+                // refill
+                int idle = 0; for (auto& l : wp.lanes) idle += l.active ? 0 : 1;
+                bool refilled = false;
+                while (idle > 0 && !wp.exhausted) {
+                    if (wp.poolNext >= wp.poolEnd) { if (cursor >= e) { wp.exhausted = true; break; } wp.poolNext = cursor; wp.poolEnd = std::min(e, cursor + 96); cursor = wp.poolEnd; }
+                    for (auto& l : wp.lanes) {
+                        if (l.active || wp.poolNext >= wp.poolEnd) continue;
+                        const CapRay& r = g_cap[wp.poolNext++];
+                        if (anyHit) l.a.init(r.o, r.d, box_idir(r.d), 1e29f, l.st); else l.c.init(r.o, r.d, box_idir(r.d), 1e30f, l.st);
+                        l.active = true; idle--; refilled = true;
+                    }
+                }
+                int nActive = 0; for (auto& l : wp.lanes) nActive += l.active ? 1 : 0;
+                if (nActive == 0) continue;
+                live++;
+                out[1] += 1.0; out[2] += cLoop + (refilled ? cRefill : 0.0);
+                auto canN = [&](Lane& l) { return l.active && (anyHit ? (!l.a.done && l.a.can_node_step(l.st)) : (!l.c.done && l.c.can_node_step(l.st))); };
+                auto hasP = [&](Lane& l) { return l.active && (anyHit ? (!l.a.done && l.a.has_prims()) : (!l.c.done && l.c.has_prims())); };
+                auto doN = [&]() { int n = 0; for (auto& l : wp.lanes) if (canN(l)) { if (anyHit) l.a.node_step(s->ds, l.st, &tc); else l.c.node_step(s->ds, l.st, &tc); n++; }
+                                   if (n) { out[2] += cNode; out[3] += 1.0; out[4] += n; out[7] += n; } return n; };
+                auto doP = [&]() { int n = 0; for (auto& l : wp.lanes) if (hasP(l)) { if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); n++; }
+                                   if (n) { out[2] += cPrim; out[5] += 1.0; out[6] += n; out[8] += n; } return n; };
+                if (policy == 0) {
+                    for (int k = 0; k < nodeSteps; k++) doN();
+                    int pm = 0, nm = 0; for (auto& l : wp.lanes) { pm += hasP(l) ? 1 : 0; nm += canN(l) ? 1 : 0; }
+                    if (pm > 0 && (pm >= primVote || nm == 0)) doP();
+                } else {
+                    int pm = 0, nm = 0; for (auto& l : wp.lanes) { pm += hasP(l) ? 1 : 0; nm += canN(l) ? 1 : 0; }
+                    if ((double)nm * cPrim >= (double)pm * cNode && nm > 0) doN(); else if (pm > 0) doP(); else doN();
+                }
+                for (auto& l : wp.lanes) if (l.active && (anyHit ? l.a.done : l.c.done)) l.active = false;
+            }
+        }
+    }
+}
+
 // one ray; returns hit flag; out = {t, primId, instId, bu, bv}, counters = {nodes, tris, spheres}
 HS_API int hs_trace(HsScene* s, const float* o, const float* d, int anyHit, float tMax, unsigned flags, float* out5, uint32_t* counters3) {
     s->ds.triMaterials = (flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
@@ -138,7 +204,8 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
     // primary visibility
     RayQueue q0 = {qo[0].data(), qd[0].data(), qi[0].data()};
     for (int i = 0; i < npx; i++) generate_primary(fc, q0, i);
-    for (int i = 0; i < npx; i++) { f3 o = mk3(q0.o[i].x, q0.o[i].y, q0.o[i].z), d = mk3(q0.d[i].x, q0.d[i].y, q0.d[i].z); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[i], &tc); flushCnt(); }
+    for (int i = 0; i < npx; i++) { f3 o = mk3(q0.o[i].x, q0.o[i].y, q0.o[i].z), d = mk3(q0.d[i].x, q0.d[i].y, q0.d[i].z); cap_ray(o, d, 0); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[i], &tc); flushCnt(); }
+    g_capWave++;
     for (int i = 0; i < npx; i++) primary_finish(fc, s->ds, wb, q0, hits.data(), i);
 
     // integrator, one batch of S samples at a time
@@ -151,12 +218,14 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
         for (int depth = 1; depth <= fc.maxDepth; depth++) {
             for (int k = 0; k < nSh; k++) {
                 f3 o = mk3(shq.o[k].x, shq.o[k].y, shq.o[k].z), d = mk3(shq.d[k].x, shq.d[k].y, shq.d[k].z);
+                cap_ray(o, d, 1);
                 bool occ = trace_wide<true, true>(s->ds, o, d, 1e29f, st, nullptr, &tc); flushCnt();
                 connect_shadow(wb, shq, k, occ);
             }
-            raysS += (uint64_t)nSh;
+            raysS += (uint64_t)nSh; g_capWave++;
             RayQueue cq = {qo[cur].data(), qd[cur].data(), qi[cur].data()};
-            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[k], &tc); flushCnt(); }
+            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); cap_ray(o, d, 0); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[k], &tc); flushCnt(); }
+            g_capWave++;
             raysB += (uint64_t)nNext;
             const int nCur = nNext; nNext = 0; nSh = 0;
             RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data(), qi[cur ^ 1].data()};

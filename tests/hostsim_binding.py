@@ -37,6 +37,9 @@ def lib():
         _lib.hs_taa_resolve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
         _lib.hs_set_lane_schedule.argtypes = [C.c_int]
         _lib.hs_set_plane_pad.argtypes = [C.c_float]
+        _lib.hs_capture.argtypes = [C.c_int]
+        _lib.hs_capture_count.restype = C.c_longlong
+        _lib.hs_simulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
         _lib.hs_pow.argtypes = [C.c_float, C.c_float]
         _lib.hs_pow.restype = C.c_float
         _lib.hs_render_reuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs), C.c_void_p, C.c_void_p]
@@ -46,6 +49,23 @@ def lib():
 def set_lane_schedule(node_steps: int):
     """0: a node step then all of its primitives; n > 0: k_extend's per-lane schedule (n node steps, one primitive step, queued groups)."""
     lib().hs_set_lane_schedule(int(node_steps))
+
+
+def capture_rays(on: bool):
+    """Analysis tool: record every ray the next renders trace (wave by wave) for simulate()."""
+    lib().hs_capture(1 if on else 0)
+
+
+def simulate(scene, any_hit: bool, policy=0, node_steps=2, prim_vote=1, warps=256, c_refill=54.0, c_node=250.0, c_prim=200.0, c_loop=45.0) -> dict:
+    """The captured waves through k_extend's warp loop on simulated 32-lane warps (tests/hostsim/hostsim.cpp: hs_simulate)."""
+    out = np.zeros(9, np.float64)
+    lib().hs_simulate(scene.h, int(any_hit), policy, node_steps, prim_vote, warps, c_refill, c_node, c_prim, c_loop, out.ctypes.data)
+    keys = ["rays", "iterations", "warp_instr", "node_phases", "node_lanes", "prim_phases", "prim_lanes", "node_steps", "prim_steps"]
+    d = dict(zip(keys, out.tolist()))
+    d["warp_instr_per_ray"] = d["warp_instr"] / max(1.0, d["rays"])
+    d["lanes_per_node_phase"] = d["node_lanes"] / max(1.0, d["node_phases"])
+    d["lanes_per_prim_phase"] = d["prim_lanes"] / max(1.0, d["prim_phases"])
+    return d
 
 
 def set_plane_pad(quanta: float):
