@@ -18,7 +18,11 @@ for any_hit in (False, True):
     for label, kw in (("shipped: 2 node steps + voted primitive step", dict(policy=0, node_steps=2, prim_vote=1)),
                       ("1 node step", dict(policy=0, node_steps=1)), ("3 node steps", dict(policy=0, node_steps=3)),
                       ("2 node steps, vote 12", dict(policy=0, node_steps=2, prim_vote=12)),
-                      ("one phase per iteration, the fuller one", dict(policy=1))):
+                      ("one phase per iteration, the fuller one", dict(policy=1)),
+                      ("shipped + 50 % of the failing candidates culled for free", dict(pre_cull=0.5)),
+                      ("shipped + 80 % of the failing candidates culled for free", dict(pre_cull=0.8)),
+                      ("shipped + 80 % culled, node step 20 instructions longer", dict(pre_cull=0.8, c_node=270.0))):
         r = simulate(hs, any_hit, warps=128, **kw)
         print(f"  {label:48s} {r['warp_instr_per_ray']:7.1f} warp instr / ray, {r['iterations'] / r['rays']:.3f} iterations / ray, "
-              f"{r['lanes_per_node_phase']:.1f} lanes / node phase, {r['lanes_per_prim_phase']:.1f} lanes / primitive phase", flush=True)
+              f"{r['lanes_per_node_phase']:.1f} lanes / node phase, {r['lanes_per_prim_phase']:.1f} lanes / primitive phase, "
+              f"{r['prim_steps'] / r['rays']:.2f} exact tests / ray of which {r['accepted'] / max(1.0, r['prim_steps']) * 100:.0f} % accept", flush=True)

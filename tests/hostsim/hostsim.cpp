@@ -65,8 +65,11 @@ HS_API long long hs_capture_count() { return (long long)g_cap.size(); }
 //   policy 0: the shipped loop - refill, `nodeSteps` node steps, one primitive step when >= `primVote` lanes hold one (or no lane can step)
 //   policy 1: one phase per iteration, whichever has more ready lanes (node lanes weighted by cN / cP)
 // out: [0] rays, [1] iterations, [2] warp instructions, [3] node phases, [4] node lanes, [5] prim phases, [6] prim lanes, [7] node steps, [8] prim steps
-HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int primVote, int warps, double cRefill, double cNode, double cPrim, double cLoop, double* out) {
-    for (int i = 0; i < 9; i++) out[i] = 0.0;
+//   preCull: probability that a candidate whose exact test would FAIL is removed for free before the primitive phase (what a cheap
+//   conservative pre-test in the node step would do); out[9] = candidates removed that way, out[10] = exact tests that accepted a hit
+HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int primVote, int warps, double cRefill, double cNode, double cPrim, double cLoop, double preCull, double* out) {
+    for (int i = 0; i < 11; i++) out[i] = 0.0;
+    uint32_t lcg = 12345u;
     std::vector<size_t> waveStart;
     for (size_t i = 0; i < g_cap.size(); i++) if (i == 0 || g_cap[i].wave != g_cap[i - 1].wave) waveStart.push_back(i);
     waveStart.push_back(g_cap.size());
@@ -104,10 +107,19 @@ HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int p
                 auto hasP = [&](Lane& l) { return l.active && (anyHit ? (!l.a.done && l.a.has_prims()) : (!l.c.done && l.c.has_prims())); };
                 auto doN = [&]() { int n = 0; for (auto& l : wp.lanes) if (canN(l)) { if (anyHit) l.a.node_step(s->ds, l.st, &tc); else l.c.node_step(s->ds, l.st, &tc); n++; }
                                    if (n) { out[2] += cNode; out[3] += 1.0; out[4] += n; out[7] += n; } return n; };
-                auto doP = [&]() { int n = 0; for (auto& l : wp.lanes) if (hasP(l)) { if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); n++; }
+                auto accepts = [&](Lane& l) {   // would the next exact test of this lane accept a hit?  (run on a copy)
+                    Lane c = l; const int before = anyHit ? (c.a.occluded ? 1 : 0) : c.c.best.prim;
+                    if (anyHit) c.a.prim_step(s->ds, c.st, &tc); else c.c.prim_step(s->ds, c.st, &tc);
+                    return (anyHit ? (c.a.occluded ? 1 : 0) : c.c.best.prim) != before; };
+                auto cull = [&]() { if (preCull <= 0.0) return; for (auto& l : wp.lanes) while (hasP(l)) {
+                                        if (accepts(l)) break;
+                                        lcg = lcg * 1664525u + 1013904223u;
+                                        if ((double)(lcg >> 8) / 16777216.0 >= preCull) break;
+                                        if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); out[9] += 1.0; } };
+                auto doP = [&]() { cull(); int n = 0; for (auto& l : wp.lanes) if (hasP(l)) { if (accepts(l)) out[10] += 1.0; if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); n++; }
                                    if (n) { out[2] += cPrim; out[5] += 1.0; out[6] += n; out[8] += n; } return n; };
                 if (policy == 0) {
-                    for (int k = 0; k < nodeSteps; k++) doN();
+                    for (int k = 0; k < nodeSteps; k++) { doN(); cull(); }
                     int pm = 0, nm = 0; for (auto& l : wp.lanes) { pm += hasP(l) ? 1 : 0; nm += canN(l) ? 1 : 0; }
                     if (pm > 0 && (pm >= primVote || nm == 0)) doP();
                 } else {

@@ -39,7 +39,7 @@ def lib():
         _lib.hs_set_plane_pad.argtypes = [C.c_float]
         _lib.hs_capture.argtypes = [C.c_int]
         _lib.hs_capture_count.restype = C.c_longlong
-        _lib.hs_simulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        _lib.hs_simulate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
         _lib.hs_pow.argtypes = [C.c_float, C.c_float]
         _lib.hs_pow.restype = C.c_float
         _lib.hs_render_reuse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs), C.c_void_p, C.c_void_p]
@@ -56,11 +56,11 @@ def capture_rays(on: bool):
     lib().hs_capture(1 if on else 0)
 
 
-def simulate(scene, any_hit: bool, policy=0, node_steps=2, prim_vote=1, warps=256, c_refill=54.0, c_node=250.0, c_prim=200.0, c_loop=45.0) -> dict:
+def simulate(scene, any_hit: bool, policy=0, node_steps=2, prim_vote=1, warps=256, c_refill=54.0, c_node=250.0, c_prim=200.0, c_loop=45.0, pre_cull=0.0) -> dict:
     """The captured waves through k_extend's warp loop on simulated 32-lane warps (tests/hostsim/hostsim.cpp: hs_simulate)."""
-    out = np.zeros(9, np.float64)
-    lib().hs_simulate(scene.h, int(any_hit), policy, node_steps, prim_vote, warps, c_refill, c_node, c_prim, c_loop, out.ctypes.data)
-    keys = ["rays", "iterations", "warp_instr", "node_phases", "node_lanes", "prim_phases", "prim_lanes", "node_steps", "prim_steps"]
+    out = np.zeros(11, np.float64)
+    lib().hs_simulate(scene.h, int(any_hit), policy, node_steps, prim_vote, warps, c_refill, c_node, c_prim, c_loop, pre_cull, out.ctypes.data)
+    keys = ["rays", "iterations", "warp_instr", "node_phases", "node_lanes", "prim_phases", "prim_lanes", "node_steps", "prim_steps", "pre_culled", "accepted"]
     d = dict(zip(keys, out.tolist()))
     d["warp_instr_per_ray"] = d["warp_instr"] / max(1.0, d["rays"])
     d["lanes_per_node_phase"] = d["node_lanes"] / max(1.0, d["node_phases"])
