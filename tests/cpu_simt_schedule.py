@@ -21,7 +21,9 @@ for any_hit in (False, True):
                       ("one phase per iteration, the fuller one", dict(policy=1)),
                       ("shipped + 50 % of the failing candidates culled for free", dict(pre_cull=0.5)),
                       ("shipped + 80 % of the failing candidates culled for free", dict(pre_cull=0.8)),
-                      ("shipped + 80 % culled, node step 20 instructions longer", dict(pre_cull=0.8, c_node=270.0))):
+                      ("shipped + 80 % culled, node step 20 instructions longer", dict(pre_cull=0.8, c_node=270.0)),
+                      ("shipped + candidates culled by their OWN box, free", dict(pre_cull=-1.0)),
+                      ("shipped + own-box cull, node step 30 instructions longer", dict(pre_cull=-1.0, c_node=280.0))):
         r = simulate(hs, any_hit, warps=128, **kw)
         print(f"  {label:48s} {r['warp_instr_per_ray']:7.1f} warp instr / ray, {r['iterations'] / r['rays']:.3f} iterations / ray, "
               f"{r['lanes_per_node_phase']:.1f} lanes / node phase, {r['lanes_per_prim_phase']:.1f} lanes / primitive phase, "

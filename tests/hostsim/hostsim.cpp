@@ -111,7 +111,22 @@ HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int p
                     Lane c = l; const int before = anyHit ? (c.a.occluded ? 1 : 0) : c.c.best.prim;
                     if (anyHit) c.a.prim_step(s->ds, c.st, &tc); else c.c.prim_step(s->ds, c.st, &tc);
                     return (anyHit ? (c.a.occluded ? 1 : 0) : c.c.best.prim) != before; };
-                auto cull = [&]() { if (preCull <= 0.0) return; for (auto& l : wp.lanes) while (hasP(l)) {
+                auto ownBoxMiss = [&](Lane& l) {   // preCull < 0: the candidate's OWN box (plain triangles only) against the ray, culled at the current closest t
+                    const uint32_t tg = anyHit ? l.a.tgroup.y : l.c.tgroup.y, tgx = anyHit ? l.a.tgroup.x : l.c.tgroup.x, tv = anyHit ? l.a.tvalid : l.c.tvalid;
+                    const int bit = rt_bfind(tg);
+                    const PrimRec& pr = s->ds.prims[(int)tgx + rt_popc(tv & ~(0xFFFFFFFFu << bit))];
+                    if (f2u(pr.q2.w) & (PRIM_SPHERE | PRIM_XFORM)) return false;
+                    const f3 o = anyHit ? l.a.o : l.c.o, id = anyHit ? l.a.idir : l.c.idir;
+                    const float tmax = anyHit ? l.a.tMax : l.c.best.t;
+                    const float lo[3] = {fminf(pr.q0.x, fminf(pr.q1.x, pr.q2.x)), fminf(pr.q0.y, fminf(pr.q1.y, pr.q2.y)), fminf(pr.q0.z, fminf(pr.q1.z, pr.q2.z))};
+                    const float hi[3] = {fmaxf(pr.q0.x, fmaxf(pr.q1.x, pr.q2.x)), fmaxf(pr.q0.y, fmaxf(pr.q1.y, pr.q2.y)), fmaxf(pr.q0.z, fmaxf(pr.q1.z, pr.q2.z))};
+                    const float oo[3] = {o.x, o.y, o.z}, ii[3] = {id.x, id.y, id.z};
+                    float tn = 0.001f, tf = tmax;
+                    for (int a = 0; a < 3; a++) { const float pad = 1e-4f * (fabsf(lo[a]) + fabsf(hi[a]) + 1.0f); const float t1 = (lo[a] - pad - oo[a]) * ii[a], t2 = (hi[a] + pad - oo[a]) * ii[a];
+                                                  tn = fmaxf(tn, fminf(t1, t2)); tf = fminf(tf, fmaxf(t1, t2)); }
+                    return tn > tf * 1.0000007f; };
+                auto cull = [&]() { if (preCull == 0.0) return; for (auto& l : wp.lanes) while (hasP(l)) {
+                                        if (preCull < 0.0) { if (!ownBoxMiss(l)) break; if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); out[9] += 1.0; continue; }
                                         if (accepts(l)) break;
                                         lcg = lcg * 1664525u + 1013904223u;
                                         if ((double)(lcg >> 8) / 16777216.0 >= preCull) break;
