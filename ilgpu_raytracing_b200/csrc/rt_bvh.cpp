@@ -9,6 +9,7 @@
 #include "rt_bvh.h"
 
 #include <algorithm>
+#include <thread>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -65,13 +66,18 @@ struct Builder {
     std::vector<int> idx;
     std::vector<B2Node> b2;
 
-    int build_rec(int first, int count) {
-        int ni = (int)b2.size();
-        b2.push_back(B2Node());
+    // The binary tree goes down to single primitives, so a subtree over n primitives has exactly 2n - 1 nodes: node indices are
+    // known before the subtree is built (depth-first order: node, left subtree, right subtree) and big subtrees can be built by
+    // their own threads into the pre-sized array - the result is the array the sequential recursion would push, byte for byte.
+    void build_all(int n) {
+        b2.assign((size_t)2 * (size_t)n - 1, B2Node());
+        build_at(0, 0, n, 0);
+    }
+    void build_at(int ni, int first, int count, int forks) {
         Aabb box, cb; box.reset(); cb.reset();
         for (int i = first; i < first + count; i++) { box.grow(prims[idx[i]].box); cb.grow(prims[idx[i]].c); }
         b2[ni].box = box; b2[ni].left = b2[ni].right = -1; b2[ni].first = first; b2[ni].count = count;
-        if (count == 1) return ni;
+        if (count == 1) return;
 
         // binned SAH over the centroid bounds
         const int NB = 16;
@@ -111,10 +117,17 @@ struct Builder {
         } else {
             mid = first + count / 2;   // all centroids coincide
         }
-        int l = build_rec(first, mid - first);
-        int r = build_rec(mid, first + count - mid);
+        const int nl = mid - first, l = ni + 1, r = ni + 2 * nl;
         b2[ni].left = l; b2[ni].right = r;
-        return ni;
+        if (count >= (1 << 15) && forks < 4) {   // up to 16 threads at the top of a big tree
+            std::thread t; bool forked = true;
+            try { t = std::thread([=] { build_at(l, first, nl, forks + 1); }); } catch (...) { forked = false; }   // no thread to be had: build it here
+            build_at(r, mid, count - nl, forks + 1);
+            if (forked) t.join(); else build_at(l, first, nl, forks + 1);
+        } else {
+            build_at(l, first, nl, forks);
+            build_at(r, mid, count - nl, forks);
+        }
     }
 };
 
@@ -262,8 +275,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
     // ---- 3. binary BVH (binned SAH, leaves of <= 3 primitives) ---------------------------------------------------
     B.idx.resize((size_t)N);
     for (int i = 0; i < N; i++) B.idx[i] = i;
-    B.b2.reserve((size_t)2 * N);
-    B.build_rec(0, N);
+    B.build_all(N);
 
     // ---- 4. collapse to 8-wide with the SAH-optimal dynamic program of Ylitie, Karras & Laine (HPG 2017, section 4.1):
     //   C(n,1) = min(C_leaf(n), C_internal(n)),  C_internal(n) = A_n c_node + min_k C(left,k) + C(right,8-k),

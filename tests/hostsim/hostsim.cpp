@@ -48,6 +48,13 @@ HS_API HsScene* hs_scene_create(const RtSceneDesc* d) {
 }
 HS_API const char* hs_scene_error(HsScene* s) { return s->err.c_str(); }
 HS_API void hs_scene_destroy(HsScene* s) { delete s; }
+// FNV-1a over the wide nodes and primitive records: builder regression checks compare it across builder versions
+HS_API uint64_t hs_scene_hash(HsScene* s) {
+    uint64_t h = 1469598103934665603ull;
+    auto eat = [&](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; } };
+    eat(s->bvh.nodes.data(), s->bvh.nodes.size() * sizeof(WideNode)); eat(s->bvh.prims.data(), s->bvh.prims.size() * sizeof(PrimRec));
+    return h;
+}
 HS_API void hs_scene_stats(HsScene* s, int64_t* out6) {
     out6[0] = s->bvh.stats.nPrims; out6[1] = s->bvh.stats.nTris; out6[2] = s->bvh.stats.nSpheres; out6[3] = s->bvh.stats.nWideNodes; out6[4] = s->bvh.stats.maxDepth; out6[5] = 0;
 }

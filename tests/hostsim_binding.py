@@ -31,6 +31,8 @@ def lib():
         _lib.hs_scene_error.argtypes = [C.c_void_p]
         _lib.hs_scene_destroy.argtypes = [C.c_void_p]
         _lib.hs_scene_stats.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.hs_scene_hash.argtypes = [C.c_void_p]
+        _lib.hs_scene_hash.restype = C.c_uint64
         _lib.hs_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_uint, C.c_void_p, C.c_void_p]
         _lib.hs_render.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(L.RtRenderConfig), C.POINTER(HsOutputs)]
         _lib.hs_bilinear_upsample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
@@ -91,6 +93,10 @@ class HostSimScene:
         s = np.zeros(6, np.int64)
         lib().hs_scene_stats(self.h, s.ctypes.data)
         return dict(nPrims=int(s[0]), nTris=int(s[1]), nSpheres=int(s[2]), nWideNodes=int(s[3]), maxDepth=int(s[4]))
+
+    def bvh_hash(self) -> int:
+        """FNV-1a of the wide nodes + primitive records the host builder produced."""
+        return int(lib().hs_scene_hash(self.h))
 
     def trace(self, o, d, any_hit=False, t_max=1e30, flags=0):
         o = np.ascontiguousarray(o, np.float32)

@@ -224,3 +224,20 @@ def test_malformed_scene_is_rejected():
     bad["spherePrimIdx"][6:] = 77
     with pytest.raises(ValueError):
         HostSimScene(bad)
+
+
+def test_host_builder_output_is_pinned():
+    """The wide BVH the host builder makes (binned SAH with big subtrees built by their own threads into pre-computed index ranges,
+    SAH-optimal collapse, quantisation) is the one the sequential builder made: FNV-1a of nodes + primitive records, recorded before
+    the threaded build went in.  Same bytes on every run (no race decides an index)."""
+    from tests.util import special_scene
+    sc = orc.Scene()
+    sc.build_default()
+    pinned = {"default": (sc, 0xa435527c2ab62924), "grid32": (oracle_scene_from_spec(scenes.sphere_grid_scene(32)), 0xaeea26dd0c1c73f2),
+              "terrain96": (oracle_scene_from_spec(scenes.terrain_scene(96, 24)), 0x295cb80c41c21634),
+              "special_t": (oracle_scene_from_spec(special_scene("translated")), 0xc28f7b40f58f6a2d),
+              "terrain300": (oracle_scene_from_spec(scenes.terrain_scene(300, 64)), 0xd6dae8d89b51afaf)}   # 180 k triangles: the threaded path
+    for name, (scene, want) in pinned.items():
+        arrays = scene.arrays()
+        for _ in range(2):
+            assert HostSimScene(arrays).bvh_hash() == want, name
