@@ -23,7 +23,11 @@ for any_hit in (False, True):
                       ("shipped + 80 % of the failing candidates culled for free", dict(pre_cull=0.8)),
                       ("shipped + 80 % culled, node step 20 instructions longer", dict(pre_cull=0.8, c_node=270.0)),
                       ("shipped + candidates culled by their OWN box, free", dict(pre_cull=-1.0)),
-                      ("shipped + own-box cull, node step 30 instructions longer", dict(pre_cull=-1.0, c_node=280.0))):
+                      ("shipped + own-box cull, node step 30 instructions longer", dict(pre_cull=-1.0, c_node=280.0)),
+                      ("two-stage: 45-instruction test, exact test at >= 1 survivor", dict(policy=2, pre_cull=-45.0, prim_vote=1)),
+                      ("two-stage: 45-instruction test, exact test at >= 4 survivors", dict(policy=2, pre_cull=-45.0, prim_vote=4)),
+                      ("two-stage: 45-instruction test, exact test at >= 8 survivors", dict(policy=2, pre_cull=-45.0, prim_vote=8)),
+                      ("two-stage: 70-instruction test, exact test at >= 4 survivors", dict(policy=2, pre_cull=-70.0, prim_vote=4))):
         r = simulate(hs, any_hit, warps=128, **kw)
         print(f"  {label:48s} {r['warp_instr_per_ray']:7.1f} warp instr / ray, {r['iterations'] / r['rays']:.3f} iterations / ray, "
               f"{r['lanes_per_node_phase']:.1f} lanes / node phase, {r['lanes_per_prim_phase']:.1f} lanes / primitive phase, "

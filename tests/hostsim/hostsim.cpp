@@ -71,6 +71,10 @@ HS_API long long hs_capture_count() { return (long long)g_cap.size(); }
 // `warps` warps taking turns one iteration at a time) and charges every executed phase its SASS length.
 //   policy 0: the shipped loop - refill, `nodeSteps` node steps, one primitive step when >= `primVote` lanes hold one (or no lane can step)
 //   policy 1: one phase per iteration, whichever has more ready lanes (node lanes weighted by cN / cP)
+//   policy 2: two-stage primitive tests - after the node steps every lane holding a candidate runs a cheap conservative test on ONE
+//             candidate (cost cCheap = -preCull, modelled as exact: it passes exactly the candidates the exact test accepts); a
+//             survivor waits in its lane (which keeps taking node steps) until >= primVote lanes hold one, or nothing else can run,
+//             and only then the exact test (cPrim) is issued
 // out: [0] rays, [1] iterations, [2] warp instructions, [3] node phases, [4] node lanes, [5] prim phases, [6] prim lanes, [7] node steps, [8] prim steps
 //   preCull: probability that a candidate whose exact test would FAIL is removed for free before the primitive phase (what a cheap
 //   conservative pre-test in the node step would do); out[9] = candidates removed that way, out[10] = exact tests that accepted a hit
@@ -80,7 +84,7 @@ HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int p
     std::vector<size_t> waveStart;
     for (size_t i = 0; i < g_cap.size(); i++) if (i == 0 || g_cap[i].wave != g_cap[i - 1].wave) waveStart.push_back(i);
     waveStart.push_back(g_cap.size());
-    struct Lane { Traversal<false, true> c; Traversal<true, true> a; LaneStack st; bool active = false; };
+    struct Lane { Traversal<false, true> c; Traversal<true, true> a; LaneStack st; bool active = false; bool survivor = false; };
     struct Warp { std::vector<Lane> lanes; size_t poolNext = 0, poolEnd = 0; bool exhausted = false; };
     TraceCounters tc = {0, 0, 0};
     for (size_t w = 0; w + 1 < waveStart.size(); w++) {
@@ -103,7 +107,7 @@ HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int p
                         if (l.active || wp.poolNext >= wp.poolEnd) continue;
                         const CapRay& r = g_cap[wp.poolNext++];
                         if (anyHit) l.a.init(r.o, r.d, box_idir(r.d), 1e29f, l.st); else l.c.init(r.o, r.d, box_idir(r.d), 1e30f, l.st);
-                        l.active = true; idle--; refilled = true;
+                        l.active = true; l.survivor = false; idle--; refilled = true;
                     }
                 }
                 int nActive = 0; for (auto& l : wp.lanes) nActive += l.active ? 1 : 0;
@@ -132,7 +136,7 @@ HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int p
                     for (int a = 0; a < 3; a++) { const float pad = 1e-4f * (fabsf(lo[a]) + fabsf(hi[a]) + 1.0f); const float t1 = (lo[a] - pad - oo[a]) * ii[a], t2 = (hi[a] + pad - oo[a]) * ii[a];
                                                   tn = fmaxf(tn, fminf(t1, t2)); tf = fminf(tf, fmaxf(t1, t2)); }
                     return tn > tf * 1.0000007f; };
-                auto cull = [&]() { if (preCull == 0.0) return; for (auto& l : wp.lanes) while (hasP(l)) {
+                auto cull = [&]() { if (preCull == 0.0 || policy == 2) return; for (auto& l : wp.lanes) while (hasP(l)) {
                                         if (preCull < 0.0) { if (!ownBoxMiss(l)) break; if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); out[9] += 1.0; continue; }
                                         if (accepts(l)) break;
                                         lcg = lcg * 1664525u + 1013904223u;
@@ -144,9 +148,25 @@ HS_API void hs_simulate(HsScene* s, int anyHit, int policy, int nodeSteps, int p
                     for (int k = 0; k < nodeSteps; k++) { doN(); cull(); }
                     int pm = 0, nm = 0; for (auto& l : wp.lanes) { pm += hasP(l) ? 1 : 0; nm += canN(l) ? 1 : 0; }
                     if (pm > 0 && (pm >= primVote || nm == 0)) doP();
-                } else {
+                } else if (policy == 1) {
                     int pm = 0, nm = 0; for (auto& l : wp.lanes) { pm += hasP(l) ? 1 : 0; nm += canN(l) ? 1 : 0; }
                     if ((double)nm * cPrim >= (double)pm * cNode && nm > 0) doN(); else if (pm > 0) doP(); else doN();
+                } else {
+                    const double cCheap = -preCull;
+                    for (int k = 0; k < nodeSteps; k++) doN();
+                    int nc = 0;   // cheap stage: one candidate per lane that holds one and has no survivor waiting
+                    for (auto& l : wp.lanes) if (hasP(l) && !l.survivor) {
+                        nc++;
+                        if (accepts(l)) l.survivor = true;
+                        else { if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); out[9] += 1.0; }
+                    }
+                    if (nc) out[2] += cCheap;
+                    int sv = 0, other = 0;
+                    for (auto& l : wp.lanes) { sv += (l.active && l.survivor) ? 1 : 0; other += (canN(l) || (hasP(l) && !l.survivor)) ? 1 : 0; }
+                    if (sv > 0 && (sv >= primVote || other == 0)) {
+                        for (auto& l : wp.lanes) if (l.active && l.survivor) { if (anyHit) l.a.prim_step(s->ds, l.st, &tc); else l.c.prim_step(s->ds, l.st, &tc); l.survivor = false; out[10] += 1.0; }
+                        out[2] += cPrim; out[5] += 1.0; out[6] += sv; out[8] += sv;
+                    }
                 }
                 for (auto& l : wp.lanes) if (l.active && (anyHit ? l.a.done : l.c.done)) l.active = false;
             }
