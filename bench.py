@@ -51,7 +51,9 @@ WORKLOADS = {
     "C1": dict(scene="default", cam="C1A", w=1280, h=720, spp=1, depth=1, crop=None, cpu_spp=1),
     "C2": dict(scene="spheres", cam="C2", w=1920, h=1080, spp=16, depth=4, crop=(480, 270, 1440, 810), cpu_spp=16),
     "C3": dict(scene="terrain", cam="C3", w=3840, h=2160, spp=1, depth=0, crop=(960, 540, 2880, 1620), cpu_spp=1),
-    "C4": dict(scene="terrain+spheres", cam="C3", w=3840, h=2160, spp=64, depth=8, crop=(1536, 864, 2304, 1296), cpu_spp=64, ref_crop=(1792, 1008, 2048, 1152)),
+    # C4: ONE sample for the cpu_baseline leg, the --impl reference arm and the parity block: the central 512x288 of the frame at the
+    # full 64 spp / depth 8 (9.4 M paths, ~7 s on 16 host threads)
+    "C4": dict(scene="terrain+spheres", cam="C3", w=3840, h=2160, spp=64, depth=8, crop=(1664, 936, 2176, 1224), cpu_spp=64),
     # C5: 7680x4320 progressive accumulation, a step = one 16-spp frame of the 16-frame / 256-spp sequence (rngLockNoise = 0,
     # frame index advancing, float4 accumulator), extension variant of the scene (per-patch Lambert / mirror / glass triangle materials)
     "C5": dict(scene="terrain+spheres+mats", cam="C3", w=7680, h=4320, spp=16, depth=8, crop=(3712, 2088, 3968, 2232), cpu_spp=16,
@@ -119,8 +121,9 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
 
 
-def cpu_oracle_sample(wl: dict, threads: int = 0) -> dict:
-    """Time the CPU oracle on the workload's crop: Mrays/s (primary + bounce) over the two passes."""
+def cpu_oracle_sample(wl: dict, threads: int = 0, aovs: bool = False) -> dict:
+    """Time the CPU oracle on the workload's crop: Mrays/s (primary + bounce) over the two passes.  The rendered crop is returned
+    too (`result`): the parity block compares the device's frame with it."""
     from oracle import orc
     from tests.util import oracle_camera, oracle_scene_from_spec
     sc = oracle_scene_from_spec(make_spec(wl["scene"]))
@@ -129,13 +132,40 @@ def cpu_oracle_sample(wl: dict, threads: int = 0) -> dict:
     cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop, threads=threads,
                           flags=1 if wl.get("tri_materials") else 0, rng_lock_noise=0 if wl.get("progressive") else 1)
     t0 = time.perf_counter()
-    r = orc.render(sc, cam, cfg, aovs=False)
+    r = orc.render(sc, cam, cfg, aovs=aovs)
     wall = time.perf_counter() - t0
     secs = r.seconds[0] + r.seconds[1]
     rays = r.counters["raysPrimary"] + r.counters["raysBounce"]
-    return dict(mrays=rays / secs / 1e6, rays=rays, rays_shadow=r.counters["raysShadow"], seconds=secs, wall=wall,
+    return dict(result=r, crop=crop, mrays=rays / secs / 1e6, rays=rays, rays_shadow=r.counters["raysShadow"], seconds=secs, wall=wall,
                 cores=threads or orc.lib().orc_hardware_threads(), counters=r.counters,
                 sample=f"crop {crop[2] - crop[0]}x{crop[3] - crop[1]} of the {wl['w']}x{wl['h']} frame at {wl['cpu_spp']} spp, depth {wl['depth']}", scene=sc, cam=cam)
+
+
+def parity_vs_oracle(ctx, wl: dict, cam, cfg_for, oracle: dict) -> dict:
+    """The device's frame of the TIMED configuration against the oracle crop the cpu_baseline leg rendered (same scene, camera, seed,
+    spp, depth): primary hit ids, depth / objId, float radiance and RGBA8 of the frame exactly as timed, then per-sample bounce
+    counts, terminators and hit-id path hashes from one more frame with RT_FLAG_PATH_AOVS.  Zeros everywhere = bit-exact."""
+    from ilgpu_raytracing_b200 import layouts as L
+    from tests.parity import crop as cut, rel_rms
+    r, box = oracle["result"], oracle["crop"]
+    W, H, spp = wl["w"], wl["h"], max(1, wl["cpu_spp"])
+    ctx.render(cam, cfg_for(0, 0))
+    ctx.sync()
+    prim, inst = cut(ctx.download(L.RT_BUF_PRIM_ID), W, H, box), cut(ctx.download(L.RT_BUF_INST_ID), W, H, box)
+    rgba, rad = cut(ctx.download(L.RT_BUF_RGBA8), W, H, box), cut(ctx.download(L.RT_BUF_RADIANCE)[:, :3], W, H, box)
+    dep, oid = cut(ctx.download(L.RT_BUF_DEPTH), W, H, box), cut(ctx.download(L.RT_BUF_OBJID), W, H, box)
+    out = {"against": "CPU oracle (restatement of Engine/RTRay.cs:188-325), the crop of the cpu_baseline sample", "crop": list(box), "px": int(prim.size), "spp": spp,
+           "id_mismatch": int(((prim != r.primId) | (inst != r.instId)).sum()), "depth_objid_mismatch": int(((dep != r.depth) | (oid != r.objId)).sum()),
+           "rgba8_mismatch": int((rgba != r.rgba8).sum()), "radiance_px_not_bit_identical": int((rad != r.radiance).any(axis=1).sum()), "rel_rms": rel_rms(rad, r.radiance)}
+    if r.segCount.size:
+        ctx.render(cam, cfg_for(L.RT_FLAG_PATH_AOVS, 0))
+        ctx.sync()
+        seg, term, hsh = (cut(ctx.download(w), W, H, box, planes=spp) for w in (L.RT_BUF_SEG_COUNT, L.RT_BUF_TERM_CODE, L.RT_BUF_PATH_HASH))
+        out["paths"] = int(seg.size)
+        out["path_mismatch"] = int(((seg != r.segCount) | (term != r.termCode) | (hsh != r.pathHash)).sum())
+        out["aov_frame_radiance_px_not_bit_identical"] = int((cut(ctx.download(L.RT_BUF_RADIANCE)[:, :3], W, H, box) != r.radiance).any(axis=1).sum())
+    out["ok"] = all(out.get(k, 0) == 0 for k in ("id_mismatch", "depth_objid_mismatch", "rgba8_mismatch", "path_mismatch")) and out["rel_rms"] <= 1e-4
+    return out
 
 
 def run_reference(args, wl, name):
@@ -147,7 +177,7 @@ def run_reference(args, wl, name):
     from tests.util import oracle_camera, oracle_scene_from_spec
     sc = oracle_scene_from_spec(make_spec(wl["scene"]))
     cam = oracle_camera(wl["cam"], wl["w"], wl["h"])
-    crop = wl.get("ref_crop") or wl["crop"] or (0, 0, wl["w"], wl["h"])
+    crop = wl["crop"] or (0, 0, wl["w"], wl["h"])   # the same sample as the b200 arm's cpu_baseline leg
     cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop,
                           flags=1 if wl.get("tri_materials") else 0, rng_lock_noise=0 if wl.get("progressive") else 1)
     rays = secs = 0.0
@@ -283,6 +313,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def gathered_parity():
+        """N > 1: one more frame through the REAL gather path (NCCL), then the same frame rendered by rank 0 alone (worldSize = 1);
+        the two images must be equal word for word.  Every rank takes part in the gather; rank 0 returns the verdict."""
+        ctx.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            step(cfg_for(0, 0))
+            stream.wait_stream(comm)
+        barrier()
+        if rank != 0:
+            return None
+        got = full_rgba.cpu().numpy()
+        got_rad = full.cpu().numpy()
+        f = base_flags | (L.RT_FLAG_RESET_ACCUM if progressive else 0)
+        single = L.make_render_config(W, H, spp=spp, max_depth=depth, frame=0, rng_lock_noise=lock, flags=f, tile_size=tile, rank=0, world_size=1)
+        with torch.cuda.stream(stream):
+            ctx.render(cam, single)
+        ctx.sync()
+        want = ctx.download(L.RT_BUF_RGBA8)
+        want_rad = ctx.download(L.RT_BUF_ACCUM if progressive else L.RT_BUF_RADIANCE)
+        if progressive:
+            want_rad = want_rad.copy(); want_rad[:, :3] *= (np.float32(1.0) / want_rad[:, 3:4])
+        import zlib
+        return {"against": "the same frame rendered by rank 0 alone (worldSize = 1)", "px": int(got.size), "rgba8_mismatch": int((got != want).sum()),
+                "radiance_px_not_bit_identical": int((got_rad[:, :3] != want_rad[:, :3]).any(axis=1).sum()),
+                "crc32_gathered_rgba8": zlib.crc32(got.tobytes()), "crc32_single_gpu_rgba8": zlib.crc32(want.tobytes()), "ok": bool((got == want).all())}
+
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step(cfg_for(0, i))
@@ -409,10 +465,14 @@ def main():
                         "DRAM traffic is ~9 % of it; the kernel is bound by instruction issue (see DESIGN.md section 5)"}
 
     line = None
+    parity = None
+    if world > 1:   # the image the REAL gather delivered against a single-context render of the same frame on rank 0
+        parity = gathered_parity()
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            c = cpu_oracle_sample(wl)
+            c = cpu_oracle_sample(wl, aovs=True)
+            parity = parity_vs_oracle(ctx, wl, cam, cfg_for, c)
             cpu = {"value": c["mrays"], "unit": "Mrays/s", "cores": c["cores"], "kind": "port", "sample": c["sample"], "seconds": c["seconds"],
                    "note": "CPU restatement of the ILGPU kernels (stand-in for ILGPU CPUAccelerator, which cannot run here)"}
         line = {"metric": "Mrays/s (primary+bounce) at 4K" if W == 3840 else "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -429,7 +489,7 @@ def main():
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "ms_per_step_median": e2e_median_ms},
                 "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu,
+                "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
                 "scene_build_s": {"host_bvh2": t_build, "commit_wide_bvh_upload": t_commit, "commit_force_refit": t_refit}}
         print(json.dumps(line))
     if world > 1:

@@ -1,6 +1,7 @@
 """Builds the native libraries in-tree with nvcc for sm_100a (no JIT cache, so the .so travels to the GPU box)."""
 from __future__ import annotations
 
+import glob
 import os
 import subprocess
 
@@ -14,8 +15,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 CORE_SO = os.path.join(_PKG, "librtcore_b200.so")
 CORE_SRCS = [os.path.join(_CSRC, f) for f in ("rtcore.cu", "rt_bvh.cpp")]
-CORE_DEPS = CORE_SRCS + [os.path.join(_CSRC, f) for f in ("rt_core.h", "rt_traverse.h", "rt_wavefront.h", "rt_bvh.h", "rt_tiles.h")] + \
-    [os.path.join(_PKG, "..", "include", "rtcore_b200.h")]
+CORE_DEPS = CORE_SRCS + sorted(glob.glob(os.path.join(_CSRC, "*.h"))) + [os.path.join(_PKG, "..", "include", "rtcore_b200.h")]   # every header counts
 
 ENGINE_SO = os.path.join(_PKG, "librtengine_host.so")
 ENGINE_SRCS = [os.path.join(_CSRC, "host", f) for f in ("engine.cpp", "mesh_loader_obj.cpp")]

@@ -65,6 +65,7 @@ struct Builder {
     std::vector<BuildPrim> prims;
     std::vector<int> idx;
     std::vector<B2Node> b2;
+    bool median = false;   // depth-bounded rebuild: object-median splits along the longest centroid axis (depth = ceil(log2 n))
 
     // The binary tree goes down to single primitives, so a subtree over n primitives has exactly 2n - 1 nodes: node indices are
     // known before the subtree is built (depth-first order: node, left subtree, right subtree) and big subtrees can be built by
@@ -82,7 +83,7 @@ struct Builder {
         // binned SAH over the centroid bounds
         const int NB = 16;
         int bestAxis = -1, bestSplit = -1; float bestCost = std::numeric_limits<float>::max();
-        for (int a = 0; a < 3; a++) {
+        for (int a = 0; a < 3 && !median; a++) {
             float ext = cb.hi[a] - cb.lo[a];
             if (!(ext > 0.0f)) continue;
             Aabb bb[NB]; int bc[NB];
@@ -105,7 +106,15 @@ struct Builder {
         }
         // the binary tree goes down to single primitives; the wide collapse below decides where leaves (<= 3 primitives) form
         int mid;
-        if (bestAxis >= 0) {
+        if (median) {
+            int a = 0;
+            for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[a] - cb.lo[a]) a = k;
+            mid = first + count / 2;
+            std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + first + count, [&](int x, int y) {
+                const float cx = prims[x].c[a], cy = prims[y].c[a];
+                return cx < cy || (cx == cy && x < y);
+            });
+        } else if (bestAxis >= 0) {
             float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
             float k = 16.0f / ext; float lo = cb.lo[bestAxis]; int a = bestAxis, sp = bestSplit;
             auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](int pi) {
@@ -137,7 +146,8 @@ inline float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 }   // namespace
 
-bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool primsOnly) {
+bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool primsOnly, int maxDepth) {
+    if (maxDepth <= 0 || maxDepth > RT_STACK_ENTRIES - 2) maxDepth = RT_STACK_ENTRIES - 2;
     out.nodes.clear(); out.prims.clear(); out.levelStart.clear(); out.primBoxes.clear(); out.stats = HostBvhStats();
     out.instBoxXf.assign((size_t)std::max<int64_t>(0, d.nInstances) * 12, 0.0);
     for (int64_t i = 0; i < d.nInstances; i++) { out.instBoxXf[(size_t)i * 12 + 0] = 1.0; out.instBoxXf[(size_t)i * 12 + 5] = 1.0; out.instBoxXf[(size_t)i * 12 + 10] = 1.0; }
@@ -272,7 +282,15 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
         return true;
     }
 
+    // The SAH tree minimises cost, not depth: a scene with a huge dynamic range (a small detailed mesh on a giant ground plane)
+    // can come out deeper than the traversal stack.  The reference's skip-link walk has no stack and accepts any scene, so a
+    // too-deep tree is rebuilt depth-bounded instead of refusing the commit: object-median splits (binary depth ceil(log2 n))
+    // collapsed three binary levels per wide node (wide depth <= ceil(31 / 3) + 1 for any 32-bit primitive count).
+    for (int attempt = 0; attempt < 2; attempt++) {
+    const bool bounded = attempt == 1;
+    out.nodes.clear(); out.prims.clear(); out.levelStart.clear();
     // ---- 3. binary BVH (binned SAH, leaves of <= 3 primitives) ---------------------------------------------------
+    B.median = bounded;
     B.idx.resize((size_t)N);
     for (int i = 0; i < N; i++) B.idx[i] = i;
     B.build_all(N);
@@ -313,6 +331,13 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
             if (d == 0) collect(n, i - 1, out, cnt);
             else { collect(bn.left, d, out, cnt); collect(bn.right, i - d, out, cnt); }
         }
+        // depth-bounded variant: the subtrees `levels` binary levels below n (a subtree of <= 3 primitives becomes a leaf child)
+        void collect_fixed(int n, int levels, Child* out, int& cnt) const {
+            const B2Node& bn = b2[n];
+            if (bn.count <= 3) { out[cnt++] = {n, true}; return; }
+            if (levels == 0) { out[cnt++] = {n, false}; return; }
+            collect_fixed(bn.left, levels - 1, out, cnt); collect_fixed(bn.right, levels - 1, out, cnt);
+        }
     } collector{B.b2, D};
 
     struct Work { int b2; int wide; };
@@ -328,6 +353,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
         const B2Node& root = B.b2[w.b2];
         Child ch[8]; int nch = 0;
         if (root.left < 0 || (w.wide == 0 && root.count <= 3 && N <= 3)) { ch[nch++] = {w.b2, true}; }   // a tree of <= 3 primitives: one leaf child
+        else if (bounded) { collector.collect_fixed(root.left, 2, ch, nch); collector.collect_fixed(root.right, 2, ch, nch); }
         else {
             int k = D[(size_t)w.b2 * 7];
             if (k == 0) {   // only the root can get here with a "leaf" decision: force an internal node
@@ -411,7 +437,10 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
     out.stats.nWideNodes = (int64_t)out.nodes.size();
     out.stats.maxDepth = std::max(1, maxDepthSeen);
     for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = B.b2[0].box.lo[a]; out.stats.sceneHi[a] = B.b2[0].box.hi[a]; }
-    if (out.stats.maxDepth > RT_STACK_ENTRIES - 2) { err = "wide BVH deeper than the traversal stack"; return false; }
+    out.stats.depthBounded = bounded ? 1 : 0;
+    if (out.stats.maxDepth <= maxDepth) break;
+    if (bounded) { err = "wide BVH deeper than the traversal stack"; return false; }   // unreachable for 32-bit primitive counts
+    }
     if ((int64_t)out.prims.size() != (int64_t)N) { err = "internal: primitive count mismatch"; return false; }
     return true;
 }

@@ -11,6 +11,7 @@ namespace rtx {
 struct HostBvhStats {
     int64_t nPrims = 0, nTris = 0, nSpheres = 0, nWideNodes = 0;
     int maxDepth = 0;
+    int depthBounded = 0;            // 1: the SAH tree was deeper than the traversal stack and the depth-bounded rebuild was taken
     float maxInstanceScale = 1.0f;   // max(1, uniformScale of every instance reached from the TLAS)
     float sceneLo[3] = {0, 0, 0}, sceneHi[3] = {0, 0, 0};
 };
@@ -28,6 +29,8 @@ struct HostBvh {
 // visiting order and builds the wide BVH.  Returns false with a message on malformed input.
 // primsOnly: stop after the primitive stage (validation, visiting-order ranks, records, padded boxes, scene bounds in stats):
 // the tree is then built on the device (rt_build.h).
-bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err, bool primsOnly = false);
+// maxDepth: deepest wide tree the caller's traversal stack takes (0 = RT_STACK_ENTRIES - 2); a deeper SAH tree is rebuilt
+// depth-bounded (median splits, three binary levels per wide node) - the commit never fails for depth.
+bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err, bool primsOnly = false, int maxDepth = 0);
 
 }   // namespace rtx

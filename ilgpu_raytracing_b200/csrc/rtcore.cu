@@ -405,7 +405,7 @@ struct rt_ctx {
     bool aovs = false;
     DevBuf<int> pixelMap, invPixelMap;
     // ReSTIR reservoirs: A/B per global pixel (3 float4 planes each, zero-initialised: frame 0 imports nothing), per-path staging
-    DevBuf<float4> resAB[2]; DevBuf<float4> resPath; size_t resPathCap = 0; int resLastWritten = -1;
+    DevBuf<float4> resAB[2]; DevBuf<float4> resPath; size_t resPathCap = 0; int resLastWritten = -1; bool resValid[2] = {false, false}; int resFrame[2] = {0, 0};
     // per owned pixel
     DevBuf<float4> gbPosHit, gbNrmMat, gbAlbObj, lframe, tileRadiance; DevBuf<int> primId, instId; DevBuf<float> primaryT;
     // per global pixel
@@ -432,6 +432,7 @@ struct rt_ctx {
     size_t memTotal = 0;
     size_t l2PersistMax = 0, l2WindowMax = 0, l2Persist = 0, l2Window = 0; cudaStream_t l2WindowStream = nullptr;
     size_t extendSmem = 0; int stackEntries = 0;
+    bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envLbvhLeaf = 0;   // developer knobs, read once in rt_create
 };
 
 template <typename T> static cudaError_t upload_or_one(DevBuf<T>& dst, const T* src, int64_t n, cudaStream_t st, int* lenOut) {
@@ -517,7 +518,7 @@ static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, DevBuf<WideNode
     BTRY(cudaMemcpyAsync(counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
     BTRY(cudaMemsetAsync(workB2, 0, sizeof(int), st));   // wide node 0 owns binary node 0
     int leafMax = 2;   // primitives per leaf child; sweep on C4 (RT_LBVH_LEAF): 1 / 2 / 3 -> 22.5 / 22.2 / 29.1 ms of traversal (host SAH tree: 19.7)
-    if (const char* ev = getenv("RT_LBVH_LEAF")) { const int v = atoi(ev); if (v >= 1 && v <= 3) leafMax = v; }
+    if (c->envLbvhLeaf) leafMax = c->envLbvhLeaf;
     levelStart.assign(1, 0);
     int first = 0, last = 1;
     *tooDeep = false;
@@ -562,14 +563,23 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     c->device = dev; c->smCount = prop.multiProcessorCount;
     c->memTotal = (size_t)prop.totalGlobalMem;
     c->l2PersistMax = (size_t)prop.persistingL2CacheMaxSize; c->l2WindowMax = (size_t)prop.accessPolicyMaxWindowSize;
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
-    c->stream = c->ownStream;
-    CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
-    int rc = size_extend_launch(c, RT_STACK_ENTRIES);
-    if (rc != RT_OK) { rt_destroy(c); return rc; }
-    memset(&c->ds, 0, sizeof(c->ds));
-    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->hstats), sizeof(DeviceStats), cudaHostAllocDefault));
-    memset(c->hstats, 0, sizeof(DeviceStats));
+    // developer knobs (tuning sweeps under tests/), read ONCE here: nothing on the per-frame path calls getenv
+    c->envNoL2Persist = getenv("RT_NO_L2_PERSIST") != nullptr;
+    c->envNoSunProbe = getenv("RT_NO_SUN_PROBE") != nullptr;
+    if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) c->envPathsPerPass = v; }
+    if (const char* e = getenv("RT_LBVH_LEAF")) { const int v = atoi(e); if (v >= 1 && v <= 3) c->envLbvhLeaf = v; }
+    const int rc = [&]() -> int {   // any failure below releases what the context already holds (rt_destroy)
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
+        c->stream = c->ownStream;
+        CUDA_TRY(cudaEventCreate(&c->evStart)); CUDA_TRY(cudaEventCreate(&c->evStop));
+        const int r = size_extend_launch(c, RT_STACK_ENTRIES);
+        if (r != RT_OK) return r;
+        memset(&c->ds, 0, sizeof(c->ds));
+        CUDA_TRY(cudaHostAlloc(reinterpret_cast<void**>(&c->hstats), sizeof(DeviceStats), cudaHostAllocDefault));
+        memset(c->hstats, 0, sizeof(DeviceStats));
+        return RT_OK;
+    }();
+    if (rc != RT_OK) { const std::string msg = g_lastError; rt_destroy(c); g_lastError = msg; return rc; }
     *out = c;
     return RT_OK;
 }
@@ -625,6 +635,10 @@ RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFla
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // nothing in flight may still read the old scene
     cudaStream_t st = c->stream;
+    // From here on the old scene is torn down buffer by buffer (DevBuf::ensure frees before it allocates): the context has NO
+    // scene until every array of the new one is in place, so a failure half way (out of memory, a CUDA error) leaves a context
+    // that refuses to render (RT_ERR_INVALID_STATE) instead of one that traverses freed or null pointers.
+    c->hasScene = false; c->ds.nNodes = 0; c->ds.nPrims = 0;
     DeviceScene& ds = c->ds;
     DevBuf<WideNode> builtNodes; DevBuf<PrimRec> builtPrims; int builtNodeCount = 0;
     if (onDevice) {
@@ -653,7 +667,7 @@ RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFla
     ds.nodes = dNodes; ds.nNodes = nPrims == 0 ? 0 : (int)nNodes; ds.prims = dPrims; ds.nPrims = (int)nPrims;
     // keep the BVH resident in L2 while GBs of path state stream past it: persisting carve-out + access-policy window (applied per stream in rt_render)
     c->l2Window = 0;
-    if (!bvh.prims.empty() && c->l2PersistMax > 0 && getenv("RT_NO_L2_PERSIST") == nullptr) {
+    if (!bvh.prims.empty() && c->l2PersistMax > 0 && !c->envNoL2Persist) {
         const size_t want = std::min(nodeBytes + primBytes, c->l2PersistMax);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2Window = std::min(nodeBytes + primBytes, c->l2WindowMax);
         c->l2Persist = want;
@@ -723,7 +737,7 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
         if (!pm.empty()) CUDA_TRY(cudaMemcpyAsync(c->pixelMap.p, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->width = W; c->height = H; c->tileSize = T; c->rank = rank; c->worldSize = world; c->npx = (int)pm.size();
-        c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resLastWritten = -1;   // reservoirs belong to one image size (Framebuffer.EnsureLength, Framebuffer.cs:60-83)
+        c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resLastWritten = -1; c->resValid[0] = c->resValid[1] = false;   // reservoirs belong to one image size (Framebuffer.EnsureLength, Framebuffer.cs:60-83)
         const size_t n = std::max<size_t>(1, (size_t)c->npx), g = (size_t)W * H;
         CUDA_TRY(c->gbPosHit.ensure(n)); CUDA_TRY(c->gbNrmMat.ensure(n)); CUDA_TRY(c->gbAlbObj.ensure(n)); CUDA_TRY(c->lframe.ensure(n)); CUDA_TRY(c->tileRadiance.ensure(n));
         CUDA_TRY(c->primId.ensure(n)); CUDA_TRY(c->instId.ensure(n)); CUDA_TRY(c->primaryT.ensure(n));
@@ -755,11 +769,16 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     if (cfg->width <= 0 || cfg->height <= 0 || (int64_t)cfg->width * cfg->height > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: bad image size");
     if (cfg->maxDepth < 0 || cfg->maxDepth > 255) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: maxDepth must be in [0, 255]");
     if (cfg->worldSize > 1 && (cfg->rank < 0 || cfg->rank >= cfg->worldSize)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: rank outside [0, worldSize)");
-    const bool reuse = cfg->enableTemporalReuse != 0 || cfg->enableSpatialReuse != 0;
+    // "reuse" frames run the <REUSE> shade kernels: they publish resCur (RTRay.cs:289-296) and import when a reuse flag is set.
+    // The reference publishes on EVERY frame; here a frame without imports publishes only on request (RT_FLAG_PUBLISH_RESERVOIRS:
+    // 48 B per path of extra traffic), and a reuse frame whose previous-frame buffer was not written by frame - 1 imports zeros.
+    const bool reuse = cfg->enableTemporalReuse != 0 || cfg->enableSpatialReuse != 0 || (cfg->flags & RT_FLAG_PUBLISH_RESERVOIRS) != 0;
     if (reuse && cfg->worldSize > 1)
         return fail(RT_ERR_UNSUPPORTED, "rt_render: ReSTIR temporal/spatial reuse reads the previous frame's reservoirs of neighbouring and reprojected pixels, "
                                         "which a screen-tile partition does not hold; render reuse frames with worldSize = 1");
     if (cfg->enableTemporalReuse != 0 && !prevCam) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: enableTemporalReuse needs prevCam");
+    if (c->extColor && c->extColorBytes < (size_t)cfg->width * cfg->height * sizeof(int))   // Framebuffer.GetGpuWithExternalColor's guard (Framebuffer.cs:117), before anything is queued
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: mapped external colour buffer is smaller than the image");
     CUDA_TRY(cudaSetDevice(c->device));
 
     const int spp = cfg->spp > 1 ? cfg->spp : 1;
@@ -777,7 +796,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             else (void)cudaGetLastError();
         }
         target = std::max<int64_t>(target, 1ll << 20);
-        if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) target = v; }
+        if (c->envPathsPerPass > 0) target = c->envPathsPerPass;
         S = (int)std::max<int64_t>(1, std::min<int64_t>(spp, target / std::max<int64_t>(1, npxOwned)));
     }
     S = std::min(S, spp);
@@ -795,7 +814,16 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             CUDA_TRY(cudaMemcpyAsync(c->invPixelMap.p, inv.data(), g * sizeof(int), cudaMemcpyHostToDevice, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
         }
-        for (int b = 0; b < 2; b++) if (!c->resAB[b].p || (cfg->flags & RT_FLAG_RESET_RESERVOIRS)) { CUDA_TRY(c->resAB[b].ensure(3 * g)); CUDA_TRY(cudaMemsetAsync(c->resAB[b].p, 0, 3 * g * sizeof(float4), c->stream)); }
+        const int prevB = (cfg->frame & 1) ^ 1;
+        for (int b = 0; b < 2; b++) {
+            // zero: a new buffer, an explicit restart, or the "previous frame" buffer when frame - 1 did not write it (reuse was off,
+            // or the frame index jumped): stale reservoirs of some older frame must not be imported as if they were last frame's
+            const bool stale = b == prevB && !(c->resValid[b] && c->resFrame[b] == cfg->frame - 1);
+            if (!c->resAB[b].p || (cfg->flags & RT_FLAG_RESET_RESERVOIRS) || stale) {
+                CUDA_TRY(c->resAB[b].ensure(3 * g)); CUDA_TRY(cudaMemsetAsync(c->resAB[b].p, 0, 3 * g * sizeof(float4), c->stream));
+                c->resValid[b] = false;
+            }
+        }
         const size_t P = std::max<size_t>(1, (size_t)npx * S);
         if (P > c->resPathCap) { CUDA_TRY(c->resPath.ensure(3 * P)); c->resPathCap = P; }
     }
@@ -849,6 +877,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         wb.resCur0 = cur; wb.resCur1 = cur + g; wb.resCur2 = cur + 2 * g;
         wb.resPath0 = c->resPath.p; wb.resPath1 = c->resPath.p + P; wb.resPath2 = c->resPath.p + 2 * P;
         c->resLastWritten = cfg->frame & 1;
+        c->resValid[cfg->frame & 1] = true; c->resFrame[cfg->frame & 1] = cfg->frame;
     }
     if (c->aovs) { wb.pathHash = c->pathHash.p; wb.segCountOut = c->segOut.p; wb.termCodeOut = c->termOut.p; wb.pathHashOut = c->hashOut.p; }
 
@@ -865,7 +894,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
 
         ShadowQueue shq = {c->shO.p, c->shD.p, c->shI.p, c->shC.p};
         // ---- shared sun probe: one any-hit ray per Lambert primary vertex facing the sun, instead of one per sample that selects it
-        if (spp >= 2 && cfg->maxDepth >= 1 && !reuse && getenv("RT_NO_SUN_PROBE") == nullptr) {
+        if (spp >= 2 && cfg->maxDepth >= 1 && !reuse && !c->envNoSunProbe) {
             int* sunCount = c->counters.p + 2;
             k_sun_generate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, shq, sunCount); c->launches++;
             ExtendArgs pa; memset(&pa, 0, sizeof(pa));
@@ -905,7 +934,6 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             k_accumulate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
         }
         if (c->extColor) {
-            if (c->extColorBytes < (size_t)cfg->width * cfg->height * sizeof(int)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: mapped external colour buffer is smaller than the image");
             k_copy_color<<<grid_for(c, npx, 256), 256, 0, st>>>(c->rgba8.p, c->extColor, c->pixelMap.p, npx); c->launches++;
         }
     }

@@ -169,7 +169,12 @@ enum {
     RT_FLAG_KERNEL_TIMING = 1u << 5,
     /* Zero both ReSTIR reservoir buffers before this frame (start of a sequence).  The reference never clears them:
      * frame 0 with reuse on reads uninitialised memory there (Engine/Framebuffer.cs:85-97); here they start at zero. */
-    RT_FLAG_RESET_RESERVOIRS = 1u << 6
+    RT_FLAG_RESET_RESERVOIRS = 1u << 6,
+    /* Publish resCur (the reservoir of every sample's first Lambert vertex, Engine/RTRay.cs:289-296) on a frame that imports
+     * nothing, so that switching reuse on at the NEXT frame finds this frame's reservoirs like the reference does.  Frames with a
+     * reuse flag set always publish.  Without it a reuse frame whose predecessor (frame - 1) did not publish imports zeros
+     * (never stale reservoirs of some older frame). */
+    RT_FLAG_PUBLISH_RESERVOIRS = 1u << 7
 };
 
 /* Everything the reference passes in GBufferParams / IntegratorParams

@@ -31,9 +31,12 @@ template <class T> static void copy_or_one(std::vector<T>& dst, const T* src, in
     if (src && n > 0) dst.assign(src, src + n); else { dst.assign(1, T()); memset(dst.data(), 0, sizeof(T)); }
 }
 
-HS_API HsScene* hs_scene_create(const RtSceneDesc* d) {
+HS_API HsScene* hs_scene_create_ex(const RtSceneDesc* d, int maxDepth);
+HS_API HsScene* hs_scene_create(const RtSceneDesc* d) { return hs_scene_create_ex(d, 0); }
+// maxDepth: the depth limit handed to the builder (0 = the traversal stack's); a small value forces the depth-bounded rebuild
+HS_API HsScene* hs_scene_create_ex(const RtSceneDesc* d, int maxDepth) {
     HsScene* s = new HsScene();
-    if (!build_wide_bvh(*d, s->bvh, s->err)) return s;
+    if (!build_wide_bvh(*d, s->bvh, s->err, false, maxDepth)) return s;
     copy_or_one(s->instances, d->instances, d->nInstances); copy_or_one(s->spheres, d->spheres, d->nSpheres);
     copy_or_one(s->texcoords, d->meshTexcoords, d->nMeshTexcoords); copy_or_one(s->triUVs, d->meshTriUVs, d->nMeshTriUVs);
     copy_or_one(s->triMat, d->triMatIndex, d->nTriMatIndex); copy_or_one(s->materials, d->materials, d->nMaterials);
@@ -56,7 +59,7 @@ HS_API uint64_t hs_scene_hash(HsScene* s) {
     return h;
 }
 HS_API void hs_scene_stats(HsScene* s, int64_t* out6) {
-    out6[0] = s->bvh.stats.nPrims; out6[1] = s->bvh.stats.nTris; out6[2] = s->bvh.stats.nSpheres; out6[3] = s->bvh.stats.nWideNodes; out6[4] = s->bvh.stats.maxDepth; out6[5] = 0;
+    out6[0] = s->bvh.stats.nPrims; out6[1] = s->bvh.stats.nTris; out6[2] = s->bvh.stats.nSpheres; out6[3] = s->bvh.stats.nWideNodes; out6[4] = s->bvh.stats.maxDepth; out6[5] = s->bvh.stats.depthBounded;
 }
 // 0 = node step + all of its primitives; n > 0 = k_extend's lane schedule (n node steps, one primitive step) with queued primitive groups
 HS_API void hs_set_lane_schedule(int nodeSteps) { host_lane_schedule() = nodeSteps < 0 ? 0 : nodeSteps; }

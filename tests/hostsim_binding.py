@@ -27,6 +27,8 @@ def lib():
         _lib = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
         _lib.hs_scene_create.restype = C.c_void_p
         _lib.hs_scene_create.argtypes = [C.POINTER(L.RtSceneDesc)]
+        _lib.hs_scene_create_ex.restype = C.c_void_p
+        _lib.hs_scene_create_ex.argtypes = [C.POINTER(L.RtSceneDesc), C.c_int]
         _lib.hs_scene_error.restype = C.c_char_p
         _lib.hs_scene_error.argtypes = [C.c_void_p]
         _lib.hs_scene_destroy.argtypes = [C.c_void_p]
@@ -76,9 +78,10 @@ def set_plane_pad(quanta: float):
 
 
 class HostSimScene:
-    def __init__(self, arrays: dict):
+    def __init__(self, arrays: dict, max_depth: int = 0):
+        """max_depth: depth limit handed to the wide-BVH builder (0 = the traversal stack's; small values force the depth-bounded rebuild)."""
         self.desc, self._keep = L.scene_desc_from_arrays(arrays)
-        self.h = C.c_void_p(lib().hs_scene_create(C.byref(self.desc)))
+        self.h = C.c_void_p(lib().hs_scene_create_ex(C.byref(self.desc), int(max_depth)))
         err = lib().hs_scene_error(self.h).decode()
         if err:
             raise ValueError(err)
@@ -92,7 +95,7 @@ class HostSimScene:
     def stats(self):
         s = np.zeros(6, np.int64)
         lib().hs_scene_stats(self.h, s.ctypes.data)
-        return dict(nPrims=int(s[0]), nTris=int(s[1]), nSpheres=int(s[2]), nWideNodes=int(s[3]), maxDepth=int(s[4]))
+        return dict(nPrims=int(s[0]), nTris=int(s[1]), nSpheres=int(s[2]), nWideNodes=int(s[3]), maxDepth=int(s[4]), depthBounded=int(s[5]))
 
     def bvh_hash(self) -> int:
         """FNV-1a of the wide nodes + primitive records the host builder produced."""

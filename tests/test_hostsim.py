@@ -241,3 +241,20 @@ def test_host_builder_output_is_pinned():
         arrays = scene.arrays()
         for _ in range(2):
             assert HostSimScene(arrays).bvh_hash() == want, name
+
+
+def test_too_deep_tree_is_rebuilt_depth_bounded():
+    """a SAH tree deeper than the traversal stack must not fail the commit (the reference's skip-link walk has no
+    stack).  Force the case with a small depth limit: the depth-bounded rebuild (median splits, three binary levels per wide
+    node) must respect the limit and render the same image as the oracle."""
+    spec = scenes.terrain_scene(n_quads=48, n_spheres=9)
+    sc = oracle_scene_from_spec(spec)
+    normal = HostSimScene(sc.arrays())
+    limit = 4                                     # 4 617 primitives: the SAH tree has 5 levels, the bounded one 4 (585 nodes = 1 + 8 + 64 + 512)
+    assert normal.stats()["maxDepth"] > limit and normal.stats()["depthBounded"] == 0
+    bounded = HostSimScene(sc.arrays(), max_depth=limit)
+    st = bounded.stats()
+    assert st["depthBounded"] == 1 and st["maxDepth"] <= limit and st["nPrims"] == normal.stats()["nPrims"]
+    cam = oracle_camera("C3", 96, 54)
+    r = orc.render(sc, cam, orc.make_config(96, 54, spp=2, max_depth=4))
+    _compare(r, bounded.render(cam, L.make_render_config(96, 54, spp=2, max_depth=4)), "depth-bounded tree")
