@@ -84,6 +84,55 @@ def peaks() -> dict:
     return dict(hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+RAY_RECORD_BYTES = 48   # what k_extend reads per ray: origin | slot, direction, box-test reciprocal (3 x float4)
+
+
+def csrc_hash() -> str:
+    """sha256 over the kernel sources (csrc/*.cu, *.h, *.cpp, host/ excluded): ties an ncu capture to the code it profiled."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    base = os.path.join(ROOT, "ilgpu_raytracing_b200", "csrc")
+    for f in sorted(glob.glob(os.path.join(base, "*.cu")) + glob.glob(os.path.join(base, "*.h")) + glob.glob(os.path.join(base, "*.cpp"))):
+        h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+CAPTURE_FILE = os.path.join(ROOT, "profiles", "r02_extend_capture_c4.json")
+
+
+def capture_status(name, args, world) -> str:
+    if name != "C4" or args.spp or world != 1:
+        return "no capture for this workload / GPU count (ncu captures are taken for C4 on one GPU)"
+    if not os.path.exists(CAPTURE_FILE):
+        return "no capture committed"
+    t = json.load(open(CAPTURE_FILE))
+    return f"STALE: capture of sources {t.get('csrc_hash')} != current {csrc_hash()} - refused (re-run profiles/capture.py)"
+
+
+def load_capture(name, args, world):
+    """The committed ncu capture of all k_extend launches of one C4 frame (profiles/capture.py), ONLY if it was taken from the
+    kernel sources in this tree: a capture of older kernels is refused, not silently divided by this run's launches."""
+    if name != "C4" or args.spp or world != 1 or not os.path.exists(CAPTURE_FILE):
+        return None
+    t = json.load(open(CAPTURE_FILE))
+    if t.get("csrc_hash") != csrc_hash():
+        return None
+    return {"thread_instructions": float(t["thread_instructions"]), "warp_instructions": float(t["warp_instructions"]),
+            "dram_bytes": float(t["dram_read_bytes"]) + float(t["dram_write_bytes"]), "launches": int(t["launches"]), "file": "profiles/" + os.path.basename(CAPTURE_FILE)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "profiles", "r02_gpu_peaks.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    iss = d.get("issue_lane_inst_per_s_T", {})
+    return {"fp32_ffma_tflops": d.get("fp32_ffma_tflops"), "fp32_unfused_tflops": d.get("fp32_mul_add_unfused_tflops"),
+            "issue_lane_inst_per_s_T": max(v for k, v in iss.items() if k != "ffma2_instructions") if iss else None,
+            "l2_random": d.get("l2_read_gbs_random_80B_records_58MB"), "l2_stream": d.get("l2_read_gbs_stream_58MB")}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
 
@@ -264,80 +313,48 @@ def main():
         f = base_flags | flags | (L.RT_FLAG_RESET_ACCUM if progressive and frame == 0 else 0)
         return L.make_render_config(W, H, spp=spp, max_depth=depth, frame=frame if progressive else 0, rng_lock_noise=lock, flags=f, tile_size=tile, rank=rank, world_size=world)
 
-    npx_all = [native.tiles_owned_pixels(W, H, tile, r, world) for r in range(world)]
-    max_npx = max(npx_all)
-    gathered = payload = None
+    # N > 1: the communicator lives in the LIBRARY (rt_comm_init behind RTRenderer.InitMultiGpu); torch.distributed only hands rank 0's
+    # 128-byte id to the other ranks and does the barrier / max-over-ranks bookkeeping of this script
+    GATHER = L.RT_GATHER_RGBA8 | L.RT_GATHER_DEPTH_OBJID   # what a displayed frame is in the reference: colour + depth + objectId (Engine/RTRay.cs:59-64), 12 B/px
     if world > 1:
-        payload = torch.zeros((max_npx, 4), dtype=torch.float32, device="cuda")
-        flat = torch.zeros((world * max_npx, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
-        gathered = [flat[r * max_npx:(r + 1) * max_npx] for r in range(world)] if rank == 0 else None   # NCCL writes straight into the flat buffer
-        full = torch.zeros((W * H, 4), dtype=torch.float32, device="cuda") if rank == 0 else None
-        full_rgba = torch.zeros(W * H, dtype=torch.int32, device="cuda") if rank == 0 else None
+        ids = [engine.RTRenderer.NewCommunicatorId() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0, device=torch.device("cuda", local_rank))
+        rdr.InitMultiGpu(ids[0], rank, world)
 
-    class _Dev:   # view of a library-owned device buffer as a torch tensor (no copy)
-        def __init__(self, ptr, nfloat4):
-            self.__cuda_array_interface__ = {"shape": (nfloat4, 4), "typestr": "<f4", "data": (ptr, False), "version": 3}
-
-    # N > 1: the gather of frame k runs on its own stream while frame k + 1 renders (two payload buffers, events both ways)
-    overlap = world > 1 and not os.environ.get("RT_BENCH_NO_OVERLAP")
-    comm = torch.cuda.Stream() if world > 1 else None
-    payloads = [payload, torch.zeros_like(payload)] if world > 1 else None
-    ev_ready = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
-    ev_done = [torch.cuda.Event(), torch.cuda.Event()] if world > 1 else None
-    step_no = [0]
-
-    def step(cfg):
-        """One frame on this rank (async on `stream`), plus the framebuffer gather for N > 1."""
+    def step(cfg, what=GATHER):
+        """One frame on this rank (async on `stream`); N > 1: plus rt_gather_frame - grouped ncclSend / ncclRecv of the tile payloads to
+        rank 0 and the fused de-interleave there, on the library's communicator stream, overlapping the next frame's render."""
         ctx.render(cam, cfg)
         if world > 1:
-            ptr, nbytes = ctx.device_buffer(L.RT_BUF_TILE_RADIANCE)
-            b = step_no[0] & 1
-            step_no[0] += 1
-            gstream = comm if overlap else stream
-            with torch.cuda.stream(stream):
-                src = torch.as_tensor(_Dev(ptr, nbytes // 16), device="cuda")
-                stream.wait_event(ev_done[b])                      # the gather that used this payload buffer two frames ago is through
-                payloads[b][: src.shape[0]].copy_(src, non_blocking=True)
-                ev_ready[b].record(stream)
-            with torch.cuda.stream(gstream):
-                gstream.wait_event(ev_ready[b])
-                dist.gather(payloads[b], gathered, dst=0)
-                if rank == 0:
-                    ctx.set_stream(gstream.cuda_stream)            # the de-interleave belongs to the gather, not to the next frame
-                    ctx.deinterleave_tiles(flat.data_ptr(), [r * max_npx for r in range(world)], world, W, H, tile, full.data_ptr(), full_rgba.data_ptr())
-                    ctx.set_stream(stream.cuda_stream)
-                ev_done[b].record(gstream)
+            ctx.gather_frame(0, what)
 
     def barrier():
         if world > 1:
             dist.barrier()
+        ctx.sync()                    # the render stream AND the library's communicator stream
         torch.cuda.synchronize()
 
     def gathered_parity():
-        """N > 1: one more frame through the REAL gather path (NCCL), then the same frame rendered by rank 0 alone (worldSize = 1);
-        the two images must be equal word for word.  Every rank takes part in the gather; rank 0 returns the verdict."""
+        """N > 1: one more frame through the REAL gather path (NCCL inside the library, float4 radiance + depth + objectId), then the
+        same frame rendered by rank 0 alone (worldSize = 1); the two must be equal word for word.  Rank 0 returns the verdict."""
+        import zlib
         ctx.set_stream(stream.cuda_stream)
-        with torch.cuda.stream(stream):
-            step(cfg_for(0, 0))
-            stream.wait_stream(comm)
+        step(cfg_for(0, 0), L.RT_GATHER_RADIANCE | L.RT_GATHER_DEPTH_OBJID)
         barrier()
         if rank != 0:
             return None
-        got = full_rgba.cpu().numpy()
-        got_rad = full.cpu().numpy()
+        got = {k: ctx.download(w).copy() for k, w in (("rgba8", L.RT_BUF_GATHERED_RGBA8), ("depth", L.RT_BUF_GATHERED_DEPTH), ("objId", L.RT_BUF_GATHERED_OBJID), ("radiance", L.RT_BUF_GATHERED_RADIANCE))}
         f = base_flags | (L.RT_FLAG_RESET_ACCUM if progressive else 0)
-        single = L.make_render_config(W, H, spp=spp, max_depth=depth, frame=0, rng_lock_noise=lock, flags=f, tile_size=tile, rank=0, world_size=1)
-        with torch.cuda.stream(stream):
-            ctx.render(cam, single)
+        ctx.render(cam, L.make_render_config(W, H, spp=spp, max_depth=depth, frame=0, rng_lock_noise=lock, flags=f, tile_size=tile, rank=0, world_size=1))
         ctx.sync()
-        want = ctx.download(L.RT_BUF_RGBA8)
-        want_rad = ctx.download(L.RT_BUF_ACCUM if progressive else L.RT_BUF_RADIANCE)
-        if progressive:
-            want_rad = want_rad.copy(); want_rad[:, :3] *= (np.float32(1.0) / want_rad[:, 3:4])
-        import zlib
-        return {"against": "the same frame rendered by rank 0 alone (worldSize = 1)", "px": int(got.size), "rgba8_mismatch": int((got != want).sum()),
-                "radiance_px_not_bit_identical": int((got_rad[:, :3] != want_rad[:, :3]).any(axis=1).sum()),
-                "crc32_gathered_rgba8": zlib.crc32(got.tobytes()), "crc32_single_gpu_rgba8": zlib.crc32(want.tobytes()), "ok": bool((got == want).all())}
+        want = {"rgba8": ctx.download(L.RT_BUF_RGBA8), "depth": ctx.download(L.RT_BUF_DEPTH), "objId": ctx.download(L.RT_BUF_OBJID),
+                "radiance": ctx.download(L.RT_BUF_ACCUM if progressive else L.RT_BUF_RADIANCE)}
+        if progressive:   # the payload is what the pixel shows: the progressive mean (one frame accumulated: Lout * (1 / 1))
+            want["radiance"] = want["radiance"].copy(); want["radiance"][:, :3] *= (np.float32(1.0) / want["radiance"][:, 3:4])
+        mism = {k: int((got[k][:, :3] != want[k][:, :3]).any(axis=1).sum()) if k == "radiance" else int((got[k] != want[k]).sum()) for k in got}
+        return {"against": "the same frame rendered by rank 0 alone (worldSize = 1)", "path": "rt_gather_frame (NCCL send/recv inside the library)", "px": int(got["rgba8"].size),
+                "rgba8_mismatch": mism["rgba8"], "depth_mismatch": mism["depth"], "objid_mismatch": mism["objId"], "radiance_px_not_bit_identical": mism["radiance"],
+                "crc32_gathered_rgba8": zlib.crc32(got["rgba8"].tobytes()), "crc32_single_gpu_rgba8": zlib.crc32(want["rgba8"].tobytes()), "ok": all(v == 0 for v in mism.values())}
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
@@ -354,22 +371,31 @@ def main():
         for i in range(args.steps):
             step(cfg_for(0, args.warmup + i))   # progressive workloads advance the frame index (new samples every step)
         if world > 1:
-            stream.wait_stream(comm)            # the timed region ends when the last gathered image is complete
+            ctx.sync()                          # the timed region ends when the last gathered image is complete on rank 0 (the gather runs on the library's own stream)
         ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     st = ctx.stats()
+    per_rank = None
+    if world > 1:   # per-rank device time of the last frame + the gather: separates tile imbalance from tails
+        t = torch.tensor([st["lastRenderMs"], st["lastGatherMs"]], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rm = [float(x[0]) for x in allt]
+        per_rank = {"last_render_ms": rm, "min": min(rm), "max": max(rm), "imbalance": max(rm) / max(1e-9, float(np.mean(rm))) - 1.0,
+                    "gather_ms_on_root_stream": float(allt[0][1])}
     rays_pb = st["raysPrimary"] + st["raysBounce"]
-    rays_all = rays_pb + st["raysShadow"]
+    rays_all = rays_pb + st["raysAnyHitTraced"]   # rays actually traced (first-vertex shadow rays answered by a shared sun probe are not)
+    rays_ref_calls = rays_pb + st["raysShadow"]   # the reference's TraceClosest + ShadowOcclusion call count for the same frame
     launches = st["kernelLaunches"] * args.steps
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        r = torch.tensor([rays_pb, rays_all, launches], dtype=torch.float64, device="cuda")
+        r = torch.tensor([rays_pb, rays_all, launches, rays_ref_calls], dtype=torch.float64, device="cuda")
         dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        rays_pb, rays_all, launches = (float(x) for x in r.tolist())
+        rays_pb, rays_all, launches, rays_ref_calls = (float(x) for x in r.tolist())
     ms_per_step = ms / args.steps
     value = rays_pb / (ms_per_step * 1e-3) / 1e6
 
@@ -377,27 +403,16 @@ def main():
     n_px = W * H
     pin = [torch.empty(n_px, dtype=torch.int32).pin_memory(), torch.empty(n_px, dtype=torch.float32).pin_memory(), torch.empty(n_px, dtype=torch.int32).pin_memory()]
     pin_np = [p.numpy() for p in pin]
-    ctx.set_stream(None if world == 1 else stream.cuda_stream)   # N > 1: the gather runs on torch's stream, so the frame does too
+    ctx.set_stream(None)
 
     e2e_frame = [0]
 
     def e2e_step():
-        rdr.RenderDirectToPbo(None, W, H, e2e_frame[0], 0.0)    # host camera + knobs in; two launches' worth of work; Synchronize()
+        # host camera + knobs in; rt_render; N > 1: rt_gather_frame (colour + depth + objectId to rank 0); present; Synchronize()
+        rdr.RenderDirectToPbo(None, W, H, e2e_frame[0], 0.0)
         e2e_frame[0] += 1 if progressive else 0
-        if world == 1:
-            rdr.DownloadToCpu(*pin_np)               # Framebuffer.DownloadToCpu: RGBA8 + depth + objId to host
-            return
-        # N > 1: the frame a user gets is the gathered one - tile payloads to rank 0 over NCCL, de-interleave + tone-map there,
-        # the final RGBA8 image read back to page-locked host memory on rank 0
-        ptr, nbytes = ctx.device_buffer(L.RT_BUF_TILE_RADIANCE)
-        with torch.cuda.stream(stream):
-            src = torch.as_tensor(_Dev(ptr, nbytes // 16), device="cuda")
-            payload[: src.shape[0]].copy_(src, non_blocking=True)
-            dist.gather(payload, gathered, dst=0)
-            if rank == 0:
-                ctx.deinterleave_tiles(flat.data_ptr(), [r * max_npx for r in range(world)], world, W, H, tile, full.data_ptr(), full_rgba.data_ptr())
-                pin[0].copy_(full_rgba, non_blocking=True)
-        stream.synchronize()
+        if rank == 0:
+            rdr.DownloadToCpu(*pin_np)               # Framebuffer.DownloadToCpu: RGBA8 + depth + objId (the gathered ones at N > 1) to host: 12 B/px at every N
 
     for _ in range(min(2, args.warmup)):
         e2e_step()
@@ -419,7 +434,7 @@ def main():
         e2e_s = float(t.item())
     e2e_value = rays_pb / e2e_s / 1e6
     h2d = 2 * L.CAMERA.itemsize + __import__("ctypes").sizeof(L.RtRenderConfig)
-    d2h = 12 * n_px if world == 1 else 4 * n_px   # N > 1: rank 0 reads the gathered RGBA8 image
+    d2h = 12 * n_px   # RGBA8 + depth + objectId, the same at every N (N > 1: the gathered image on rank 0)
 
     # ---- roofline of the extend kernels: one frame with per-launch events, one with device counters ---------------
     ctx.set_stream(stream.cuda_stream)
@@ -431,43 +446,68 @@ def main():
         ctx.render(cam, cfg_for(L.RT_FLAG_COUNTERS))
     torch.cuda.synchronize()
     st_c = ctx.stats()
-    n_rays = st_c["raysPrimary"] + st_c["raysBounce"] + st_c["raysShadow"]
-    # algorithmic bytes of the traversal (SURVEY.md §8d, shipped layout): 80 B per wide node fetched, 48 B per primitive record
-    # tested, 48 B ray record (o, d, 1/d) read per ray, 16 B hit record written per closest ray, 4 B visibility flag per shadow ray
-    alg_bytes = 80 * st_c["wideNodes"] + 48 * (st_c["trisTested"] + st_c["spheresTested"]) + 48 * n_rays + 16 * (st_c["raysPrimary"] + st_c["raysBounce"]) + 4 * st_c["raysShadow"]
+    # rays the extend kernels actually TRACED (raysShadow counts the reference's ShadowOcclusion calls, of which the first-vertex
+    # ones answered by a shared sun probe were never traced: they are charged neither bytes nor instructions)
+    n_closest = st_c["raysPrimary"] + st_c["raysBounce"]
+    n_anyhit = st_c["raysAnyHitTraced"]
+    n_traced = n_closest + n_anyhit
+    ray_bytes = RAY_RECORD_BYTES
+    # algorithmic bytes of the traversal (SURVEY.md section 8d, shipped layout): 80 B per wide node fetched, 48 B per primitive record
+    # tested, the ray record read per traced ray, 16 B hit record written per closest ray, 4 B visibility flag per any-hit ray
+    bvh_bytes = 80 * st_c["wideNodes"] + 48 * (st_c["trisTested"] + st_c["spheresTested"])
+    alg_bytes = bvh_bytes + ray_bytes * n_traced + 16 * n_closest + 4 * n_anyhit
     trace_ms = st_t["lastTraceMs"]
+    trace_s = trace_ms * 1e-3
     n_ext = max(1, st_t["extendLaunchesTimed"])
     pk = peaks()
-    achieved = alg_bytes / (trace_ms * 1e-3) / 1e9 if trace_ms > 0 else None
-    # DRAM traffic of the same kernels from the committed ncu capture of this workload (profiles/): per launch, like `achieved`
-    traffic = issue = None
-    tp = os.path.join(ROOT, "profiles", "r01b_extend_traffic_c4.json")
-    if name == "C4" and not args.spp and world == 1 and os.path.exists(tp):
-        t = json.load(open(tp))
-        # the capture's DRAM bytes of one frame's extend launches, per launch of THIS run (the capture ran the frame in two passes)
-        traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) / max(1, n_ext)
-        issue = {"warp_instructions_per_ray": t["warp_instructions"] / max(1, n_rays), "ipc_per_smsp": t["warp_instructions"] / (t["sum_duration_ms"] * 1e-3 * 1.965e9 * 148 * 4),
-                 "source": "profiles/r01b_extend_traffic_c4.json (ncu, all %d extend launches of one C4 frame)" % t["launches"]}
-    # FP32 roofline of the same kernels: 8 x 22 flops per wide node (eight slab tests), 51 per triangle test, 40 per
-    # sphere test, against 148 SMs x 128 lanes x 2 (FMA) x 1.965 GHz
-    flops = 176.0 * st_c["wideNodes"] + 51.0 * st_c["trisTested"] + 40.0 * st_c["spheresTested"]
-    fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12
-    fp32_achieved = flops / (trace_ms * 1e-3) / 1e12 if trace_ms > 0 else None
-    fp32 = {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": (fp32_achieved / fp32_peak) if fp32_achieved else None,
-            "flops_per_ray": flops / max(1, n_rays), "peak_source": "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz"}
-    roofline = {"bound": "hbm", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "peak_source": pk["source"], "traffic": traffic,
+    mp = measured_peaks()
+    cap = load_capture(name, args, world)
+    flops = 176.0 * st_c["wideNodes"] + 51.0 * st_c["trisTested"] + 40.0 * st_c["spheresTested"]   # 8 x 22 per wide node (eight slab tests), 51 per triangle, 40 per sphere test
+    rate = (lambda x, scale: (x / trace_s / scale) if trace_s > 0 else None)
+    frac = (lambda a, p_: (a / p_) if (a is not None and p_) else None)
+    # (1) PRIMARY: instruction issue.  lane-instructions of the extend launches of one frame (ncu smsp__thread_inst_executed.sum from the committed
+    # capture of THESE sources) / their live CUDA-event time, against the measured lane-instruction issue peak = IPC x active lanes / 32
+    issue = None
+    if cap is not None:
+        lane_inst, warp_inst = cap["thread_instructions"], cap["warp_instructions"]
+        issue_peak = mp.get("issue_lane_inst_per_s_T") if mp else None
+        issue = {"achieved": rate(lane_inst, 1e12), "peak": issue_peak or 148 * 4 * 32 * 1.965e9 / 1e12, "unit": "Tlane-inst/s",
+                 "peak_source": "measured: tests/gpu_peaks.py (profiles/r02_gpu_peaks.json), best of FFMA / FMUL+FADD / LOP3+IADD3 issue" if issue_peak else "derived: 148 SM x 4 schedulers x 32 lanes x 1.965 GHz",
+                 "lanes_per_instruction": lane_inst / max(1.0, warp_inst), "warp_instructions_per_traced_ray": warp_inst / max(1, n_traced),
+                 "ipc_per_scheduler_live": (warp_inst / trace_s / (148 * 4 * 1.965e9)) if trace_s > 0 else None, "capture": cap["file"]}
+        issue["frac"] = frac(issue["achieved"], issue["peak"])
+    hbm = {"achieved_algorithmic": rate(alg_bytes, 1e9), "peak": pk["hbm_gbs"], "unit": "GB/s", "peak_source": pk["source"],
+           "dram_traffic_per_launch": (cap["dram_bytes"] / n_ext) if cap else None, "dram_gbs": rate(cap["dram_bytes"], 1e9) if cap else None}
+    hbm["frac_algorithmic"] = frac(hbm["achieved_algorithmic"], pk["hbm_gbs"])
+    hbm["frac_dram"] = frac(hbm["dram_gbs"], pk["hbm_gbs"])
+    l2 = {"achieved": rate(bvh_bytes, 1e9), "unit": "GB/s", "what": "node + primitive record bytes fetched (served by L1 / L2: the BVH is cache resident)",
+          "peak_random_80B_records": mp.get("l2_random") if mp else None, "peak_stream": mp.get("l2_stream") if mp else None,
+          "peak_source": "measured: tests/gpu_peaks.py at a 58 MB working set (profiles/r02_gpu_peaks.json)" if mp else None}
+    l2["frac_of_random_gather_peak"] = frac(l2["achieved"], l2["peak_random_80B_records"])
+    fp32_peak = (mp.get("fp32_ffma_tflops") if mp else None) or 148 * 128 * 2 * 1.965e9 / 1e12
+    fp32 = {"achieved": rate(flops, 1e12), "peak": fp32_peak, "unit": "TFLOP/s", "flops_per_traced_ray": flops / max(1, n_traced),
+            "peak_source": "measured FFMA rate: tests/gpu_peaks.py (profiles/r02_gpu_peaks.json)" if mp and mp.get("fp32_ffma_tflops") else "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz",
+            "peak_unfused_mul_add": mp.get("fp32_unfused_tflops") if mp else None}
+    fp32["frac"] = frac(fp32["achieved"], fp32_peak)
+    primary = issue if issue is not None else {"achieved": l2["achieved"], "peak": l2["peak_random_80B_records"], "unit": "GB/s", "frac": l2["frac_of_random_gather_peak"]}
+    roofline = {"bound": "issue" if issue is not None else "l2-gather", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)",
+                "achieved": primary["achieved"], "peak": primary["peak"], "unit": primary["unit"], "frac": primary["frac"],
+                "peak_source": primary.get("peak_source") or l2["peak_source"], "traffic": hbm["dram_traffic_per_launch"],
                 "algorithmic_bytes_per_launch": alg_bytes / n_ext, "launches_per_step": n_ext, "avg_launch_ms": trace_ms / n_ext,
                 "extend_share_of_step": trace_ms / st_t["lastRenderMs"] if st_t["lastRenderMs"] else None,
-                "nodes_per_ray": st_c["wideNodes"] / max(1, n_rays), "prims_per_ray": (st_c["trisTested"] + st_c["spheresTested"]) / max(1, n_rays),
-                "issue": issue, "fp32": fp32,
-                "note": "node/primitive fetches are served by L1/L2 (the 63 MB BVH is cache resident): achieved = ALGORITHMIC bytes / time is cache-served bandwidth, "
-                        "DRAM traffic is ~9 % of it; the kernel is bound by instruction issue (see DESIGN.md section 5)"}
+                "rays_traced_per_step": {"closest": n_closest, "any_hit": n_anyhit}, "ray_record_bytes": ray_bytes,
+                "nodes_per_ray": st_c["wideNodes"] / max(1, n_traced), "prims_per_ray": (st_c["trisTested"] + st_c["spheresTested"]) / max(1, n_traced),
+                "issue": issue, "hbm": hbm, "l2": l2, "fp32": fp32,
+                "capture_status": "fresh (source hash matches)" if cap else capture_status(name, args, world),
+                "note": "k_extend is bound by instruction issue with partly idle lanes (SIMT divergence), fed from L1 / L2: the primary fraction is lane-instructions per second over the "
+                        "measured issue peak (= IPC x active lanes / 32).  hbm.frac_algorithmic divides ALGORITHMIC bytes by the HBM copy peak and is cache-served bandwidth, not DRAM: "
+                        "hbm.frac_dram is the true DRAM share; l2 compares the node / primitive fetch rate with the measured L2 random-record gather rate."}
 
     line = None
     parity = None
     if world > 1:   # the image the REAL gather delivered against a single-context render of the same frame on rank 0
         parity = gathered_parity()
+        rdr.configure(rank=rank, worldSize=world)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -485,10 +525,10 @@ def main():
                            "partition": f"interleaved {tile}x{tile} screen tiles x{world}, scene replicated" if world > 1 else "single GPU",
                            "l2": "no explicit flush: per-step path state + queues (GBs) exceed the 126 MB L2; the BVH is meant to stay resident"},
                 "frames_per_s": 1e3 / ms_per_step, "mrays_per_s_incl_shadow": rays_all / (ms_per_step * 1e-3) / 1e6,
-                "rays_per_step": {"primary_plus_bounce": rays_pb, "all": rays_all},
+                "rays_per_step": {"primary_plus_bounce": rays_pb, "traced_incl_shadow": rays_all, "reference_calls_incl_shadow": rays_ref_calls},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3, "ms_per_step_median": e2e_median_ms},
-                "gpu_launches": int(launches),
+                "gpu_launches": int(launches), "per_rank": per_rank,
                 "parity": parity, "roofline": roofline, "cpu_baseline": cpu,
                 "scene_build_s": {"host_bvh2": t_build, "commit_wide_bvh_upload": t_commit, "commit_force_refit": t_refit}}
         print(json.dumps(line))

@@ -470,22 +470,24 @@ void Scene::RefitUpload() {
 void Framebuffer::DownloadToCpu(int slot) {   // Framebuffer.cs:148-156
     if (slot != 0) throw ArgumentOutOfRangeException("slot");   // the reference allocates 3 slots but only ever uses slot 0 (RTRenderer.cs:164)
     size_t nb = 0;
-    check(rt_buffer_bytes(_native, RT_BUF_RGBA8, &nb));
+    const int bc = _gathered ? RT_BUF_GATHERED_RGBA8 : RT_BUF_RGBA8, bd = _gathered ? RT_BUF_GATHERED_DEPTH : RT_BUF_DEPTH, bo = _gathered ? RT_BUF_GATHERED_OBJID : RT_BUF_OBJID;
+    check(rt_buffer_bytes(_native, bc, &nb));
     size_t n = nb / 4;
     _cpuColor.resize(n); _cpuDepth.resize(n); _cpuObjectId.resize(n);
-    check(rt_download(_native, RT_BUF_RGBA8, _cpuColor.data(), nb));
-    check(rt_download(_native, RT_BUF_DEPTH, _cpuDepth.data(), nb));
-    check(rt_download(_native, RT_BUF_OBJID, _cpuObjectId.data(), nb));
+    check(rt_download(_native, bc, _cpuColor.data(), nb));
+    check(rt_download(_native, bd, _cpuDepth.data(), nb));
+    check(rt_download(_native, bo, _cpuObjectId.data(), nb));
 }
 void Framebuffer::DownloadToCpu(int slot, int* color, float* depth, int* objectId, size_t n) {
     if (slot != 0) throw ArgumentOutOfRangeException("slot");
     if (!color || !depth || !objectId) throw ArgumentNullException("destination");
     size_t nb = 0;
-    check(rt_buffer_bytes(_native, RT_BUF_RGBA8, &nb));
+    const int bc = _gathered ? RT_BUF_GATHERED_RGBA8 : RT_BUF_RGBA8, bd = _gathered ? RT_BUF_GATHERED_DEPTH : RT_BUF_DEPTH, bo = _gathered ? RT_BUF_GATHERED_OBJID : RT_BUF_OBJID;
+    check(rt_buffer_bytes(_native, bc, &nb));
     if (nb / 4 != n) throw ArgumentOutOfRangeException("n");
-    check(rt_download_async(_native, RT_BUF_RGBA8, color, nb));   // three copies, one wait
-    check(rt_download_async(_native, RT_BUF_DEPTH, depth, nb));
-    check(rt_download_async(_native, RT_BUF_OBJID, objectId, nb));
+    check(rt_download_async(_native, bc, color, nb));   // three copies, one wait
+    check(rt_download_async(_native, bd, depth, nb));
+    check(rt_download_async(_native, bo, objectId, nb));
     check(rt_sync(_native));
 }
 
@@ -508,6 +510,14 @@ RTRenderer::~RTRenderer() {
     if (_native) rt_destroy(_native);
 }
 void RTRenderer::Synchronize() { check(rt_sync(_native)); }
+void RTRenderer::NewCommunicatorId(void* id128) { if (!id128) throw ArgumentNullException("id128"); check(rt_comm_get_unique_id(id128, RT_COMM_ID_BYTES)); }
+void RTRenderer::InitMultiGpu(const void* uniqueId, int rank, int worldSize) {
+    if (!uniqueId) throw ArgumentNullException("uniqueId");
+    if (worldSize < 1 || rank < 0 || rank >= worldSize) throw ArgumentOutOfRangeException("rank");
+    check(rt_comm_init(_native, uniqueId, RT_COMM_ID_BYTES, rank, worldSize));
+    Rank = rank; WorldSize = worldSize; _multiGpu = true;
+    _framebuffer->SetGathered(worldSize > 1);
+}
 
 void RTRenderer::RenderDirectToPbo(void* pboDevicePtr, int width, int height, int frame, float dt) {   // RTRenderer.cs:105-237
     int outW = std::max(1, width), outH = std::max(1, height);
@@ -527,7 +537,9 @@ void RTRenderer::RenderDirectToPbo(void* pboDevicePtr, int width, int height, in
     cfg.flags = Flags; cfg.tileSize = TileSize; cfg.rank = Rank; cfg.worldSize = WorldSize; cfg.samplesPerPass = SamplesPerPass;
     check(rt_render(_native, &_camera, &_prevCamera, &cfg));   // the two kernel launches :152-153, :181-205
     _lastCfg = cfg;
-    if (WorldSize <= 1) {   // Present (:208-231): TAAU resolve, or blit / bilinear upsample, into the mapped PBO (or the core's own buffer when headless)
+    if (WorldSize > 1 && _multiGpu)   // every rank: its tiles' colour + depth + objectId to rank 0 (NCCL, inside the library)
+        check(rt_gather_frame(_native, 0, RT_GATHER_RGBA8 | RT_GATHER_DEPTH_OBJID));
+    if (WorldSize <= 1 || (_multiGpu && Rank == 0)) {   // Present (:208-231): TAAU resolve, or blit / bilinear upsample, into the mapped PBO (or the core's own buffer when headless)
         RtPresentConfig pc; memset(&pc, 0, sizeof(pc));
         pc.mode = EnableTAAU ? RT_PRESENT_TAAU : RT_PRESENT_COPY; pc.outWidth = outW; pc.outHeight = outH;
         pc.feedback = 0.075f; pc.sharpness = 0.10f; pc.clampK = 1.25f;   // RTTaa.cs:80-82
@@ -614,6 +626,8 @@ ENG_API void eng_renderer_set_knobs(RTRenderer* r, const EngKnobs* k) {
     r->RenderScale = k->renderScale; r->EnableTemporalReuse = k->enableTemporalReuse; r->EnableSpatialReuse = k->enableSpatialReuse; r->RngLockNoise = k->rngLockNoise;
     r->FixedSeed = k->fixedSeed; r->Spp = k->spp; r->MaxDepth = k->maxDepth; r->Flags = k->flags; r->TileSize = k->tileSize; r->Rank = k->rank; r->WorldSize = k->worldSize; r->SamplesPerPass = k->samplesPerPass; r->EnableTAAU = k->enableTAAU != 0;
 }
+ENG_API int eng_renderer_new_communicator_id(void* id128) { return guard([&] { RTRenderer::NewCommunicatorId(id128); }); }
+ENG_API int eng_renderer_init_multi_gpu(RTRenderer* r, const void* id128, int rank, int worldSize) { return guard([&] { r->InitMultiGpu(id128, rank, worldSize); }); }
 ENG_API int eng_renderer_render_direct_to_pbo(RTRenderer* r, void* pbo, int w, int h, int frame, float dt) { return guard([&] { r->RenderDirectToPbo(pbo, w, h, frame, dt); }); }
 ENG_API void eng_renderer_last_config(RTRenderer* r, RtRenderConfig* out) { *out = r->LastConfig(); }
 ENG_API int eng_framebuffer_download_to_cpu(RTRenderer* r, int slot, int* color, float* depth, int* objId, size_t n) {

@@ -148,8 +148,10 @@ public:
     const std::vector<int>& CpuColor() const { return _cpuColor; }                              // :158
     const std::vector<float>& CpuDepth() const { return _cpuDepth; }                            // :159
     const std::vector<int>& CpuObjectId() const { return _cpuObjectId; }                        // :160
+    void SetGathered(bool on) { _gathered = on; }   // multi-GPU: the frame lives in the image rt_gather_frame assembled (RT_BUF_GATHERED_*)
 private:
     rt_ctx* _native;
+    bool _gathered = false;
     std::vector<int> _cpuColor, _cpuObjectId; std::vector<float> _cpuDepth;
 };
 
@@ -168,6 +170,12 @@ public:
     // :105-237.  pboDevicePtr: CUDA-mapped PBO (or NULL = keep the image in the native framebuffer only).
     void RenderDirectToPbo(void* pboDevicePtr, int width, int height, int frame, float dt);
     void Synchronize();
+    // Multi-GPU (not in the reference, which drives one device: ctor :63,67): this renderer becomes rank `rank` of `worldSize`
+    // processes, one per GPU; `uniqueId` = the RT_COMM_ID_BYTES rank 0 got from NewCommunicatorId(), handed over by the host.
+    // From then on RenderDirectToPbo renders this rank's screen tiles, gathers colour + depth + objectId on rank 0 and presents there.
+    static void NewCommunicatorId(void* id128);
+    void InitMultiGpu(const void* uniqueId, int rank, int worldSize);
+    bool IsGatherRoot() const { return WorldSize <= 1 || Rank == 0; }
 
     // the reference's private knobs (RTRenderer.cs:43-49,204), made settable: benchmark configs fix them
     float RenderScale = 0.67f;     // :43 (trace at round(out * scale), present at out)
@@ -188,6 +196,7 @@ private:
     Camera _camera, _prevCamera;
     float _sunAzimuth = 0.0f, _sunElevation = 0.9f, _sunSpeedRadPerSec = 0.0f;   // :59-61
     RtRenderConfig _lastCfg;
+    bool _multiGpu = false;
 };
 
 void BakeCameraDerived(Camera& c, int pixelW, int pixelH);   // RTRenderer.cs:241-263

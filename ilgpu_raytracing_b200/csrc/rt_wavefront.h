@@ -35,6 +35,8 @@ struct WaveBuffers {
     int *primId, *instId; float* primaryT;    // parity taps of the primary hit
     float4* lframe;                           // Lframe (RTRay.cs:208) across sample batches
     float4* tileRadiance;                     // Lout per owned pixel, tile-compacted (multi-GPU gather payload)
+    uint2* tileAux;                           // depth (float bits) | objId per owned pixel (gather payload; may be null)
+    int* tileRgba;                            // PackRGBA8 of what the pixel shows, per owned pixel (display-only gather payload; may be null)
     // per global pixel
     int* rgba8; float* depth; int* objId; float4* radiance; float4* accum;
     // per path slot (path j = sampleInBatch * npx + ownedPixel)
@@ -116,8 +118,10 @@ RT_HD void primary_finish(const FrameConst& fc, const DeviceScene& sc, const Wav
         oid = s.objId;
     }
     const f3 dc = pos - fc.camOrigin;   // IntegratorParams.DistanceFromCamera RTRay.cs:158-162
-    wb.depth[pix] = sqrtf(dc.x * dc.x + dc.y * dc.y + dc.z * dc.z);
+    const float dist = sqrtf(dc.x * dc.x + dc.y * dc.y + dc.z * dc.z);
+    wb.depth[pix] = dist;
     wb.objId[pix] = oid;
+    if (wb.tileAux) wb.tileAux[i] = make_uint2(f2u(dist), (uint32_t)oid);
 }
 
 // ------------------------------------------------------------------------------------------------ shared sun probe
@@ -451,7 +455,9 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
     // multi-GPU gather payload: what this pixel shows (the progressive mean when accumulating), so that rank 0's
     // de-interleaved image packs to the same RGBA8 as a single-GPU run
     wb.tileRadiance[i] = make_float4(shown.x, shown.y, shown.z, nAccum);
-    wb.rgba8[pix] = pack_rgba8(shown);
+    const int packed = pack_rgba8(shown);
+    wb.rgba8[pix] = packed;
+    if (wb.tileRgba) wb.tileRgba[i] = packed;
 }
 
 }   // namespace rtx

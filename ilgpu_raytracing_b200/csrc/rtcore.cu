@@ -10,6 +10,8 @@
 //
 // Compiled with --fmad=false: every mul/add below is a separate IEEE operation unless written rt_fma().
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is loaded at run time (nccl_api), nothing links against it
 
 #include <algorithm>
 #include <cstdio>
@@ -352,6 +354,19 @@ __global__ void k_deinterleave(const float4* payload, const int* pixelMap, int n
     }
 }
 
+// rt_gather_frame, receive side: the tile-compacted payloads of one or more ranks (concatenated in rank order, the way their
+// owned-pixel lists are concatenated in `map`) -> the gathered full image.  De-interleave and PackRGBA8 in one pass.
+__global__ void __launch_bounds__(256) k_gather_scatter(const float4* rad, const int* rgba, const uint2* aux, const int* map, int n,
+                                                        float4* outRadiance, int* outRgba8, float* outDepth, int* outObjId) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int p = map[i];
+        if (rad) { const float4 v = __ldcs(rad + i); outRadiance[p] = v; outRgba8[p] = pack_rgba8(mk3(v.x, v.y, v.z)); }
+        else if (rgba) outRgba8[p] = __ldcs(rgba + i);
+        if (aux) { const uint2 a = __ldcs(aux + i); outDepth[p] = __uint_as_float(a.x); outObjId[p] = (int)a.y; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 #include "rt_build.h"   // device-side refit and build of the wide BVH
 
@@ -407,7 +422,9 @@ struct rt_ctx {
     // ReSTIR reservoirs: A/B per global pixel (3 float4 planes each, zero-initialised: frame 0 imports nothing), per-path staging
     DevBuf<float4> resAB[2]; DevBuf<float4> resPath; size_t resPathCap = 0; int resLastWritten = -1; bool resValid[2] = {false, false}; int resFrame[2] = {0, 0};
     // per owned pixel
-    DevBuf<float4> gbPosHit, gbNrmMat, gbAlbObj, lframe, tileRadiance; DevBuf<int> primId, instId; DevBuf<float> primaryT;
+    DevBuf<float4> gbPosHit, gbNrmMat, gbAlbObj, lframe; DevBuf<int> primId, instId; DevBuf<float> primaryT;
+    // gather payloads per owned pixel, double-buffered: frame k + 1 renders into one set while the gather of frame k still reads the other
+    DevBuf<float4> tileRadiance[2]; DevBuf<uint2> tileAux[2]; DevBuf<int> tileRgba[2]; int tileBuf = 0;
     // per global pixel
     DevBuf<int> rgba8, objId; DevBuf<float> depth; DevBuf<float4> radiance, accum;
     // per path
@@ -425,13 +442,19 @@ struct rt_ctx {
     std::vector<cudaEvent_t> traceEvents; size_t traceEventsUsed = 0; bool timeKernels = false;
     int* extColor = nullptr; size_t extColorBytes = 0;
     // present chain: own output buffer, TAA history (RTTaa._historyColor / _historyObjId), where the last present went
-    DevBuf<int> presentBuf, taaHistColor, taaHistObj; int presentW = 0, presentH = 0; bool taaHistoryValid = false; const int* presentPtr = nullptr;
+    DevBuf<int> presentBuf, taaHistColor, taaHistObj; int presentW = 0, presentH = 0; bool taaHistoryValid = false; const int* presentPtr = nullptr; bool presentOnComm = false;
     // multi-GPU finish: cached owned-pixel lists of every rank
     DevBuf<int> deintMap; std::vector<int64_t> deintStart; int deintW = 0, deintH = 0, deintT = 0, deintWorld = 0;
     int extendBlocks = 0;
     size_t memTotal = 0;
     size_t l2PersistMax = 0, l2WindowMax = 0, l2Persist = 0, l2Window = 0; cudaStream_t l2WindowStream = nullptr;
     size_t extendSmem = 0; int stackEntries = 0;
+    // multi-GPU (rt_comm_init / rt_gather_frame): one NCCL communicator, its own stream, the gathered image on the root
+    ncclComm_t comm = nullptr; int commRank = 0, commWorld = 1;
+    cudaStream_t commStream = nullptr; cudaEvent_t evTileReady[2] = {nullptr, nullptr}, evGatherDone[2] = {nullptr, nullptr}, evGatherStart = nullptr, evGatherStop = nullptr;
+    bool gatherPending[2] = {false, false}, gatherTimed = false;
+    DevBuf<unsigned char> gatherStage; DevBuf<int> gRgba8, gObjId; DevBuf<float> gDepth; DevBuf<float4> gRadiance;
+    bool gatheredValid = false; uint32_t gatheredWhat = 0; int gatheredW = 0, gatheredH = 0;
     bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envLbvhLeaf = 0;   // developer knobs, read once in rt_create
 };
 
@@ -544,6 +567,7 @@ RT_API int rt_abi_version(void) { return RT_ABI_VERSION; }
 RT_API const char* rt_last_error(void) { return g_lastError.c_str(); }
 
 RT_API int rt_destroy(rt_ctx* c);
+RT_API int rt_comm_destroy(rt_ctx* c);
 
 RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     if (!out) return fail(RT_ERR_INVALID_ARGUMENT, "rt_create: out is null");
@@ -588,9 +612,10 @@ RT_API int rt_destroy(rt_ctx* c) {
     if (!c) return RT_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    rt_comm_destroy(c);
     c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
-    c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); c->tileRadiance.release(); c->primId.release(); c->instId.release(); c->primaryT.release();
+    c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); for (int b = 0; b < 2; b++) { c->tileRadiance[b].release(); c->tileAux[b].release(); c->tileRgba[b].release(); } c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
     c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); c->qI[b].release(); } c->shO.release(); c->shD.release(); c->shI.release(); c->shC.release();
     c->hits.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release(); c->deintMap.release();
@@ -732,6 +757,8 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
     const int world = cfg->worldSize > 1 ? cfg->worldSize : 1;
     const int rank = world > 1 ? cfg->rank : 0;
     if (c->width != W || c->height != H || c->tileSize != T || c->rank != rank || c->worldSize != world || !c->pixelMap.p) {
+        if (c->commStream) CUDA_TRY(cudaStreamSynchronize(c->commStream));   // a gather in flight still reads the payload buffers about to be re-sized
+        c->gatherPending[0] = c->gatherPending[1] = false;
         std::vector<int> pm; build_pixel_map(W, H, T, rank, world, pm);
         CUDA_TRY(c->pixelMap.ensure(std::max<size_t>(1, pm.size())));
         if (!pm.empty()) CUDA_TRY(cudaMemcpyAsync(c->pixelMap.p, pm.data(), pm.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -739,7 +766,8 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
         c->width = W; c->height = H; c->tileSize = T; c->rank = rank; c->worldSize = world; c->npx = (int)pm.size();
         c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resLastWritten = -1; c->resValid[0] = c->resValid[1] = false;   // reservoirs belong to one image size (Framebuffer.EnsureLength, Framebuffer.cs:60-83)
         const size_t n = std::max<size_t>(1, (size_t)c->npx), g = (size_t)W * H;
-        CUDA_TRY(c->gbPosHit.ensure(n)); CUDA_TRY(c->gbNrmMat.ensure(n)); CUDA_TRY(c->gbAlbObj.ensure(n)); CUDA_TRY(c->lframe.ensure(n)); CUDA_TRY(c->tileRadiance.ensure(n));
+        CUDA_TRY(c->gbPosHit.ensure(n)); CUDA_TRY(c->gbNrmMat.ensure(n)); CUDA_TRY(c->gbAlbObj.ensure(n)); CUDA_TRY(c->lframe.ensure(n));
+        for (int b = 0; b < (world > 1 ? 2 : 1); b++) { CUDA_TRY(c->tileRadiance[b].ensure(n)); CUDA_TRY(c->tileAux[b].ensure(n)); CUDA_TRY(c->tileRgba[b].ensure(n)); }
         CUDA_TRY(c->primId.ensure(n)); CUDA_TRY(c->instId.ensure(n)); CUDA_TRY(c->primaryT.ensure(n));
         CUDA_TRY(c->rgba8.ensure(g)); CUDA_TRY(c->objId.ensure(g)); CUDA_TRY(c->depth.ensure(g)); CUDA_TRY(c->radiance.ensure(g)); CUDA_TRY(c->accum.ensure(g));
         CUDA_TRY(cudaMemsetAsync(c->rgba8.p, 0, g * sizeof(int), c->stream)); CUDA_TRY(cudaMemsetAsync(c->objId.p, 0, g * sizeof(int), c->stream));
@@ -805,6 +833,10 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     if (rc != RT_OK) return rc;
     const int npx = c->npx;
     const int nPasses = (spp + S - 1) / S;
+    if (c->worldSize > 1) {   // the other set of gather payload buffers; the gather that read it two frames ago must be through
+        c->tileBuf ^= 1;
+        if (c->gatherPending[c->tileBuf]) { CUDA_TRY(cudaStreamWaitEvent(c->stream, c->evGatherDone[c->tileBuf], 0)); c->gatherPending[c->tileBuf] = false; }
+    } else c->tileBuf = 0;
     if (reuse) {
         const size_t g = (size_t)cfg->width * cfg->height;
         if (!c->invPixelMap.p) {
@@ -869,7 +901,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
 
     WaveBuffers wb; memset(&wb, 0, sizeof(wb));
     wb.gbPosHit = c->gbPosHit.p; wb.gbNrmMat = c->gbNrmMat.p; wb.gbAlbObj = c->gbAlbObj.p; wb.primId = c->primId.p; wb.instId = c->instId.p; wb.primaryT = c->primaryT.p;
-    wb.lframe = c->lframe.p; wb.tileRadiance = c->tileRadiance.p; wb.rgba8 = c->rgba8.p; wb.depth = c->depth.p; wb.objId = c->objId.p; wb.radiance = c->radiance.p; wb.accum = c->accum.p;
+    wb.lframe = c->lframe.p; wb.tileRadiance = c->tileRadiance[c->tileBuf].p; wb.tileAux = c->tileAux[c->tileBuf].p; wb.tileRgba = c->tileRgba[c->tileBuf].p; wb.rgba8 = c->rgba8.p; wb.depth = c->depth.p; wb.objId = c->objId.p; wb.radiance = c->radiance.p; wb.accum = c->accum.p;
     wb.stThr = c->stThr.p; wb.stLi = c->stLi.p;
     if (reuse) {
         const size_t g = (size_t)cfg->width * cfg->height, P = c->resPathCap;
@@ -962,6 +994,7 @@ RT_API int rt_sync(rt_ctx* c) {
     if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_sync: ctx is null");
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->commStream) CUDA_TRY(cudaStreamSynchronize(c->commStream));   // a gather (and a present of the gathered image) behind the frame
     return RT_OK;
 }
 
@@ -977,6 +1010,8 @@ static int buffer_info(rt_ctx* c, int which, size_t* bytes) {
         case RT_BUF_TILE_RADIANCE: *bytes = (size_t)c->npx * 16; return RT_OK;
         case RT_BUF_RESERVOIR: *bytes = g * sizeof(RtReservoir); return RT_OK;
         case RT_BUF_PRESENT: *bytes = (size_t)c->presentW * c->presentH * 4; return RT_OK;
+        case RT_BUF_GATHERED_RGBA8: case RT_BUF_GATHERED_DEPTH: case RT_BUF_GATHERED_OBJID: *bytes = (size_t)c->gatheredW * c->gatheredH * 4; return RT_OK;
+        case RT_BUF_GATHERED_RADIANCE: *bytes = (size_t)c->gatheredW * c->gatheredH * 16; return RT_OK;
     }
     return fail(RT_ERR_INVALID_ARGUMENT, "unknown buffer selector");
 }
@@ -987,6 +1022,7 @@ RT_API int rt_buffer_bytes(rt_ctx* c, int which, size_t* bytes) {
     return buffer_info(c, which, bytes);
 }
 
+static int gathered_ptr(rt_ctx* c, int which, const void** p);
 RT_API int rt_get_device_buffer(rt_ctx* c, int which, void** devPtr, size_t* bytes) {
     if (!c || !devPtr || !bytes) return fail(RT_ERR_INVALID_ARGUMENT, "rt_get_device_buffer: null argument");
     if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_get_device_buffer: nothing rendered yet");
@@ -998,7 +1034,11 @@ RT_API int rt_get_device_buffer(rt_ctx* c, int which, void** devPtr, size_t* byt
         case RT_BUF_OBJID: *devPtr = c->objId.p; return RT_OK;
         case RT_BUF_RADIANCE: *devPtr = c->radiance.p; return RT_OK;
         case RT_BUF_ACCUM: *devPtr = c->accum.p; return RT_OK;
-        case RT_BUF_TILE_RADIANCE: *devPtr = c->tileRadiance.p; return RT_OK;
+        case RT_BUF_TILE_RADIANCE: *devPtr = c->tileRadiance[c->tileBuf].p; return RT_OK;
+        case RT_BUF_GATHERED_RGBA8: case RT_BUF_GATHERED_DEPTH: case RT_BUF_GATHERED_OBJID: case RT_BUF_GATHERED_RADIANCE: {
+            const int rcg = gathered_ptr(c, which, const_cast<const void**>(devPtr));
+            return rcg;
+        }
         case RT_BUF_SEG_COUNT: if (!c->aovs) break; *devPtr = c->segOut.p; return RT_OK;
         case RT_BUF_TERM_CODE: if (!c->aovs) break; *devPtr = c->termOut.p; return RT_OK;
         case RT_BUF_PATH_HASH: if (!c->aovs) break; *devPtr = c->hashOut.p; return RT_OK;
@@ -1007,6 +1047,18 @@ RT_API int rt_get_device_buffer(rt_ctx* c, int which, void** devPtr, size_t* byt
     return fail(RT_ERR_INVALID_STATE, "rt_get_device_buffer: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
 }
 
+// the gathered image on the root of the last rt_gather_frame (valid on its stream, commStream)
+static int gathered_ptr(rt_ctx* c, int which, const void** p) {
+    if (!c->gatheredValid) return fail(RT_ERR_INVALID_STATE, "no gathered image: this context was not the root of an rt_gather_frame yet");
+    const bool aux = (c->gatheredWhat & RT_GATHER_DEPTH_OBJID) != 0, rad = (c->gatheredWhat & RT_GATHER_RADIANCE) != 0;
+    switch (which) {
+        case RT_BUF_GATHERED_RGBA8: *p = c->gRgba8.p; return RT_OK;
+        case RT_BUF_GATHERED_DEPTH: if (!aux) break; *p = c->gDepth.p; return RT_OK;
+        case RT_BUF_GATHERED_OBJID: if (!aux) break; *p = c->gObjId.p; return RT_OK;
+        case RT_BUF_GATHERED_RADIANCE: if (!rad) break; *p = c->gRadiance.p; return RT_OK;
+    }
+    return fail(RT_ERR_INVALID_STATE, "the last rt_gather_frame did not gather this buffer (RT_GATHER_DEPTH_OBJID / RT_GATHER_RADIANCE)");
+}
 static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wait);
 RT_API int rt_download(rt_ctx* c, int which, void* dst, size_t bytes) { return download_impl(c, which, dst, bytes, true); }
 RT_API int rt_download_async(rt_ctx* c, int which, void* dst, size_t bytes) { return download_impl(c, which, dst, bytes, false); }
@@ -1022,6 +1074,13 @@ static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wai
     const void* src = nullptr;
     const int npx = c->npx;
     const size_t g = (size_t)c->width * c->height;
+    if (which >= RT_BUF_GATHERED_RGBA8 && which <= RT_BUF_GATHERED_RADIANCE) {   // stream-ordered behind the gather that made the image, before the next one
+        rc = gathered_ptr(c, which, &src);
+        if (rc != RT_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->commStream));
+        if (wait) CUDA_TRY(cudaStreamSynchronize(c->commStream));
+        return RT_OK;
+    }
     if (!wait && !(which == RT_BUF_RGBA8 || which == RT_BUF_DEPTH || which == RT_BUF_OBJID || which == RT_BUF_RADIANCE || which == RT_BUF_ACCUM ||
                    which == RT_BUF_TILE_RADIANCE || which == RT_BUF_PRESENT))
         return fail(RT_ERR_UNSUPPORTED, "rt_download_async: this buffer is gathered through a shared staging buffer; use rt_download");
@@ -1036,14 +1095,16 @@ static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wai
         case RT_BUF_OBJID: src = c->objId.p; break;
         case RT_BUF_RADIANCE: src = c->radiance.p; break;
         case RT_BUF_ACCUM: src = c->accum.p; break;
-        case RT_BUF_TILE_RADIANCE: src = c->tileRadiance.p; break;
+        case RT_BUF_TILE_RADIANCE: src = c->tileRadiance[c->tileBuf].p; break;
         case RT_BUF_SEG_COUNT: case RT_BUF_TERM_CODE: case RT_BUF_PATH_HASH:
             if (!c->aovs) return fail(RT_ERR_INVALID_STATE, "rt_download: path AOVs were not requested (RT_FLAG_PATH_AOVS)");
             src = which == RT_BUF_SEG_COUNT ? (const void*)c->segOut.p : (which == RT_BUF_TERM_CODE ? (const void*)c->termOut.p : (const void*)c->hashOut.p);
             break;
         case RT_BUF_PRESENT:
             if (!c->presentPtr) return fail(RT_ERR_INVALID_STATE, "rt_download: rt_present has not run yet");
-            src = c->presentPtr; break;
+            src = c->presentPtr;
+            if (c->presentOnComm) st = c->commStream;   // the present of a gathered frame ran behind the gather
+            break;
         case RT_BUF_RESERVOIR:
             if (c->resLastWritten < 0) return fail(RT_ERR_INVALID_STATE, "rt_download: no frame with a reuse flag set has written reservoirs yet");
             CUDA_TRY(scatterPrep(g * 11));
@@ -1073,16 +1134,22 @@ RT_API int rt_map_external_color(rt_ctx* c, void* devPtr, size_t bytes) {
 RT_API int rt_present(rt_ctx* c, const RtPresentConfig* pc, void* dstDevRgba8, size_t dstBytes) {
     if (!c || !pc) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: null argument");
     if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_present: nothing rendered yet");
-    if (c->worldSize > 1) return fail(RT_ERR_UNSUPPORTED, "rt_present: the last frame was rendered as one rank of a tile partition; present on the gathered image's owner");
+    // a frame rendered as one rank of a tile partition is presented from the image rt_gather_frame assembled on its root
+    const bool fromGather = c->worldSize > 1;
+    if (fromGather && !c->gatheredValid) return fail(RT_ERR_INVALID_STATE, "rt_present: the last frame was rendered as one rank of a tile partition; call rt_gather_frame and present on its root");
+    if (fromGather && pc->mode == RT_PRESENT_TAAU && !(c->gatheredWhat & RT_GATHER_DEPTH_OBJID))
+        return fail(RT_ERR_INVALID_STATE, "rt_present: the TAAU resolve needs objectId (Engine/RTTaa.cs:117-171): gather with RT_GATHER_DEPTH_OBJID");
     if (pc->outWidth <= 0 || pc->outHeight <= 0 || (int64_t)pc->outWidth * pc->outHeight > 0x7FFFFFFF) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: bad output size");
     if (pc->mode != RT_PRESENT_TAAU && pc->mode != RT_PRESENT_COPY) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: unknown mode");
     const size_t outLen = (size_t)pc->outWidth * pc->outHeight;
     if (dstDevRgba8 && dstBytes < outLen * sizeof(int)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_present: destination is smaller than the output image");   // Framebuffer.cs:117
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = c->stream;
+    cudaStream_t st = fromGather ? c->commStream : c->stream;   // behind the gather that made the image
     int* dst = (int*)dstDevRgba8;
     if (!dst) { CUDA_TRY(c->presentBuf.ensure(outLen)); dst = c->presentBuf.p; }
     const int inW = c->width, inH = c->height;
+    const int* srcRgba8 = fromGather ? c->gRgba8.p : c->rgba8.p;
+    const int* srcObjId = fromGather ? c->gObjId.p : c->objId.p;
     if (pc->mode == RT_PRESENT_TAAU) {
         if (c->taaHistColor.n != outLen || !c->taaHistColor.p) {   // RTTaa.Ensure (RTTaa.cs:34-47): a new size drops the history
             c->taaHistColor.release(); c->taaHistObj.release();
@@ -1093,15 +1160,15 @@ RT_API int rt_present(rt_ctx* c, const RtPresentConfig* pc, void* dstDevRgba8, s
         if (pc->resetHistory) c->taaHistoryValid = false;
         TaaConst tc; tc.outW = pc->outWidth; tc.outH = pc->outHeight; tc.inW = inW; tc.inH = inH;
         tc.feedback = pc->feedback; tc.sharpness = pc->sharpness; tc.clampK = pc->clampK; tc.isFirstFrame = c->taaHistoryValid ? 0 : 1;
-        k_taa_resolve<<<grid_for(c, outLen, 256), 256, 0, st>>>(tc, c->rgba8.p, c->objId.p, c->taaHistColor.p, c->taaHistObj.p, dst);
+        k_taa_resolve<<<grid_for(c, outLen, 256), 256, 0, st>>>(tc, srcRgba8, srcObjId, c->taaHistColor.p, c->taaHistObj.p, dst);
         c->taaHistoryValid = true;
     } else if (inW == pc->outWidth && inH == pc->outHeight) {
-        CUDA_TRY(cudaMemcpyAsync(dst, c->rgba8.p, outLen * sizeof(int), cudaMemcpyDeviceToDevice, st));   // BlitKernel
+        CUDA_TRY(cudaMemcpyAsync(dst, srcRgba8, outLen * sizeof(int), cudaMemcpyDeviceToDevice, st));   // BlitKernel
     } else {
-        k_bilinear_upsample<<<grid_for(c, outLen, 256), 256, 0, st>>>(c->rgba8.p, inW, inH, dst, pc->outWidth, pc->outHeight);
+        k_bilinear_upsample<<<grid_for(c, outLen, 256), 256, 0, st>>>(srcRgba8, inW, inH, dst, pc->outWidth, pc->outHeight);
     }
     CUDA_TRY(cudaGetLastError());
-    c->presentW = pc->outWidth; c->presentH = pc->outHeight; c->presentPtr = dst;
+    c->presentW = pc->outWidth; c->presentH = pc->outHeight; c->presentPtr = dst; c->presentOnComm = fromGather;
     return RT_OK;
 }
 
@@ -1112,13 +1179,9 @@ RT_API int rt_tiles_owned_pixels(int width, int height, int tileSize, int rank, 
     return RT_OK;
 }
 
-RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64_t* rankOffsetsPx, int worldSize, int width, int height, int tileSize,
-                                 void* outRadianceDev, void* outRgba8Dev) {
-    if (!c || !gatheredDev || !rankOffsetsPx || worldSize < 1 || width <= 0 || height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_deinterleave_tiles: bad argument");
-    CUDA_TRY(cudaSetDevice(c->device));
-    const int T = effective_tile_size(tileSize);
+// every rank's owned-pixel list, concatenated in rank order; built once per (image, tile, world) and kept on the device
+static int ensure_deint_map(rt_ctx* c, int width, int height, int T, int worldSize) {
     if (c->deintW != width || c->deintH != height || c->deintT != T || c->deintWorld != worldSize) {
-        // every rank's owned-pixel list, concatenated; built once per (image, tile, world) and kept on the device
         std::vector<int> all; all.reserve((size_t)width * height);
         c->deintStart.assign((size_t)worldSize + 1, 0);
         for (int r = 0; r < worldSize; r++) {
@@ -1131,6 +1194,16 @@ RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->deintW = width; c->deintH = height; c->deintT = T; c->deintWorld = worldSize;
     }
+    return RT_OK;
+}
+
+RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64_t* rankOffsetsPx, int worldSize, int width, int height, int tileSize,
+                                 void* outRadianceDev, void* outRgba8Dev) {
+    if (!c || !gatheredDev || !rankOffsetsPx || worldSize < 1 || width <= 0 || height <= 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_deinterleave_tiles: bad argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int T = effective_tile_size(tileSize);
+    const int rcMap = ensure_deint_map(c, width, height, T, worldSize);
+    if (rcMap != RT_OK) return rcMap;
     for (int r = 0; r < worldSize; r++) {
         const int64_t n = c->deintStart[(size_t)r + 1] - c->deintStart[(size_t)r];
         if (n <= 0) continue;
@@ -1138,6 +1211,179 @@ RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64
                                                                           (float4*)outRadianceDev, (int*)outRgba8Dev);
     }
     CUDA_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+
+}   // extern "C"
+
+// ------------------------------------------------------------------------------------------------ multi-GPU behind the ABI
+// NCCL is loaded at run time ("libnccl.so.2": the copy already in the process when the host brought one - e.g. PyTorch's - else
+// the system's), so the library has no link-time dependency and a single-GPU host never touches it.
+struct NcclApi {
+    void* handle = nullptr; std::string err;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr; decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr; decltype(&ncclRecv) Recv = nullptr; decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr; decltype(&ncclGetErrorString) GetErrorString = nullptr; decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api; static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { api.err = std::string("NCCL is not available: ") + dlerror(); return nullptr; }
+    bool ok = true;
+    auto sym = [&](const char* name) -> void* { void* p = dlsym(h, name); if (!p) { ok = false; api.err = std::string("NCCL symbol missing: ") + name; } return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId"); api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy"); api.Send = (decltype(api.Send))sym("ncclSend"); api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart"); api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather"); api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    if (!ok) return nullptr;
+    api.handle = h;
+    return &api;
+}
+static const char* nccl_err() { static NcclApi dummy; NcclApi* a = nccl_api(); (void)dummy; return a ? "" : "NCCL is not available (libnccl.so.2 could not be loaded)"; }
+#define NCCL_TRY(expr)                                                                                                  \
+    do {                                                                                                                \
+        ncclResult_t _r = (expr);                                                                                       \
+        if (_r != ncclSuccess) return fail(RT_ERR_NCCL, std::string(#expr) + ": " + nc->GetErrorString(_r));            \
+    } while (0)
+
+extern "C" {
+
+RT_API int rt_comm_get_unique_id(void* id, size_t bytes) {
+    if (!id || bytes != RT_COMM_ID_BYTES) return fail(RT_ERR_INVALID_ARGUMENT, "rt_comm_get_unique_id: id must point at RT_COMM_ID_BYTES (128) bytes");
+    static_assert(sizeof(ncclUniqueId) == RT_COMM_ID_BYTES, "ncclUniqueId size");
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(RT_ERR_UNSUPPORTED, nccl_err());
+    ncclUniqueId u;
+    NCCL_TRY(nc->GetUniqueId(&u));
+    memcpy(id, &u, sizeof(u));
+    return RT_OK;
+}
+
+RT_API int rt_comm_destroy(rt_ctx* c) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_comm_destroy: ctx is null");
+    cudaSetDevice(c->device);
+    if (c->commStream) cudaStreamSynchronize(c->commStream);
+    if (c->comm) { NcclApi* nc = nccl_api(); if (nc) nc->CommDestroy(c->comm); c->comm = nullptr; }
+    for (int b = 0; b < 2; b++) {
+        if (c->evTileReady[b]) cudaEventDestroy(c->evTileReady[b]);
+        if (c->evGatherDone[b]) cudaEventDestroy(c->evGatherDone[b]);
+        c->evTileReady[b] = c->evGatherDone[b] = nullptr; c->gatherPending[b] = false;
+    }
+    if (c->evGatherStart) cudaEventDestroy(c->evGatherStart);
+    if (c->evGatherStop) cudaEventDestroy(c->evGatherStop);
+    c->evGatherStart = c->evGatherStop = nullptr;
+    if (c->commStream) cudaStreamDestroy(c->commStream);
+    c->commStream = nullptr; c->commRank = 0; c->commWorld = 1; c->gatheredValid = false; c->gatherTimed = false;
+    c->gatherStage.release(); c->gRgba8.release(); c->gObjId.release(); c->gDepth.release(); c->gRadiance.release();
+    return RT_OK;
+}
+
+RT_API int rt_comm_init(rt_ctx* c, const void* id, size_t bytes, int rank, int worldSize) {
+    if (!c || !id || bytes != RT_COMM_ID_BYTES) return fail(RT_ERR_INVALID_ARGUMENT, "rt_comm_init: null context / id, or id is not RT_COMM_ID_BYTES (128) bytes");
+    if (worldSize < 1 || rank < 0 || rank >= worldSize) return fail(RT_ERR_INVALID_ARGUMENT, "rt_comm_init: rank outside [0, worldSize)");
+    if (c->comm) return fail(RT_ERR_INVALID_STATE, "rt_comm_init: the context already has a communicator (rt_comm_destroy first)");
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(RT_ERR_UNSUPPORTED, nccl_err());
+    CUDA_TRY(cudaSetDevice(c->device));
+    ncclUniqueId u; memcpy(&u, id, sizeof(u));
+    NCCL_TRY(nc->CommInitRank(&c->comm, worldSize, u, rank));
+    c->commRank = rank; c->commWorld = worldSize;
+    const int rc = [&]() -> int {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) { CUDA_TRY(cudaEventCreateWithFlags(&c->evTileReady[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->evGatherDone[b], cudaEventDisableTiming)); }
+        CUDA_TRY(cudaEventCreate(&c->evGatherStart)); CUDA_TRY(cudaEventCreate(&c->evGatherStop));
+        return RT_OK;
+    }();
+    if (rc != RT_OK) { const std::string msg = g_lastError; rt_comm_destroy(c); g_lastError = msg; }
+    return rc;
+}
+
+// One exchange per displayed frame: every rank sends the payloads of ITS tiles (what the last rt_render wrote, straight from the
+// buffers the accumulate / primary-finish kernels filled, exact counts, no staging copy) to `root`; the root receives them into a
+// staging buffer and scatters all of them - its own included - into the gathered image (de-interleave + PackRGBA8 fused).  Runs
+// on the communicator's own stream behind the frame, so the next rt_render overlaps it.
+RT_API int rt_gather_frame(rt_ctx* c, int root, uint32_t what) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_gather_frame: ctx is null");
+    if (!c->comm) return fail(RT_ERR_INVALID_STATE, "rt_gather_frame: no communicator (rt_comm_init first)");
+    if (!c->rendered) return fail(RT_ERR_INVALID_STATE, "rt_gather_frame: nothing rendered yet");
+    if (root < 0 || root >= c->commWorld) return fail(RT_ERR_INVALID_ARGUMENT, "rt_gather_frame: root outside [0, worldSize)");
+    if ((what & ~(uint32_t)(RT_GATHER_RGBA8 | RT_GATHER_RADIANCE | RT_GATHER_DEPTH_OBJID)) != 0u || (what & (RT_GATHER_RGBA8 | RT_GATHER_RADIANCE)) == 0u)
+        return fail(RT_ERR_INVALID_ARGUMENT, "rt_gather_frame: `what` must name RT_GATHER_RGBA8 or RT_GATHER_RADIANCE (optionally | RT_GATHER_DEPTH_OBJID)");
+    if (c->worldSize != c->commWorld || c->rank != c->commRank)
+        return fail(RT_ERR_INVALID_STATE, "rt_gather_frame: the last frame was not rendered as this communicator's rank (RtRenderConfig.rank / worldSize must equal rt_comm_init's)");
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(RT_ERR_UNSUPPORTED, nccl_err());
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int W = c->width, H = c->height, world = c->commWorld, b = c->tileBuf;
+    const size_t g = (size_t)W * H;
+    const bool sendRad = (what & RT_GATHER_RADIANCE) != 0, sendRgba = !sendRad, sendAux = (what & RT_GATHER_DEPTH_OBJID) != 0;
+    const bool isRoot = c->commRank == root;
+    cudaStream_t cs = c->commStream;
+    CUDA_TRY(cudaEventRecord(c->evTileReady[b], c->stream));
+    CUDA_TRY(cudaStreamWaitEvent(cs, c->evTileReady[b], 0));
+    CUDA_TRY(cudaEventRecord(c->evGatherStart, cs));
+    // staging on the root: three regions (radiance | rgba | aux), each indexed like the concatenated owned-pixel lists
+    unsigned char* stage = nullptr; size_t offRad = 0, offRgba = 0, offAux = 0;
+    if (isRoot) {
+        const int rcMap = ensure_deint_map(c, W, H, c->tileSize, world);
+        if (rcMap != RT_OK) return rcMap;
+        size_t bytes = 0;
+        offRad = bytes; if (sendRad) bytes += g * sizeof(float4);
+        offRgba = bytes; if (sendRgba) bytes += g * sizeof(int);
+        offAux = bytes; if (sendAux) bytes += g * sizeof(uint2);
+        if (world > 1) CUDA_TRY(c->gatherStage.ensure(bytes));
+        stage = c->gatherStage.p;
+        if (c->gatheredW != W || c->gatheredH != H || !c->gRgba8.p) {
+            CUDA_TRY(c->gRgba8.ensure(g)); CUDA_TRY(c->gObjId.ensure(g)); CUDA_TRY(c->gDepth.ensure(g));
+            CUDA_TRY(cudaMemsetAsync(c->gRgba8.p, 0, g * 4, cs)); CUDA_TRY(cudaMemsetAsync(c->gObjId.p, 0, g * 4, cs)); CUDA_TRY(cudaMemsetAsync(c->gDepth.p, 0, g * 4, cs));
+            c->gatheredW = W; c->gatheredH = H;
+        }
+        if (sendRad && c->gRadiance.n < g) { CUDA_TRY(c->gRadiance.ensure(g)); CUDA_TRY(cudaMemsetAsync(c->gRadiance.p, 0, g * sizeof(float4), cs)); }
+    }
+    if (world > 1) {
+        NCCL_TRY(nc->GroupStart());
+        if (!isRoot) {
+            const size_t n = (size_t)c->npx;
+            if (n > 0) {
+                if (sendRad) NCCL_TRY(nc->Send(c->tileRadiance[b].p, n * 4, ncclFloat, root, c->comm, cs));
+                if (sendRgba) NCCL_TRY(nc->Send(c->tileRgba[b].p, n, ncclInt32, root, c->comm, cs));
+                if (sendAux) NCCL_TRY(nc->Send(c->tileAux[b].p, n * 2, ncclInt32, root, c->comm, cs));
+            }
+        } else {
+            for (int r = 0; r < world; r++) {
+                if (r == root) continue;
+                const size_t start = (size_t)c->deintStart[(size_t)r], n = (size_t)(c->deintStart[(size_t)r + 1] - c->deintStart[(size_t)r]);
+                if (n == 0) continue;
+                if (sendRad) NCCL_TRY(nc->Recv(reinterpret_cast<float4*>(stage + offRad) + start, n * 4, ncclFloat, r, c->comm, cs));
+                if (sendRgba) NCCL_TRY(nc->Recv(reinterpret_cast<int*>(stage + offRgba) + start, n, ncclInt32, r, c->comm, cs));
+                if (sendAux) NCCL_TRY(nc->Recv(reinterpret_cast<uint2*>(stage + offAux) + start, n * 2, ncclInt32, r, c->comm, cs));
+            }
+        }
+        NCCL_TRY(nc->GroupEnd());
+    }
+    if (isRoot) {
+        // scatter: the ranks below the root and those above it are contiguous in the staging regions; the root's own payload is read in place
+        struct Seg { size_t start, n; bool own; };
+        const size_t s0 = (size_t)c->deintStart[(size_t)root], s1 = (size_t)c->deintStart[(size_t)root + 1];
+        const Seg segs[3] = {{0, s0, false}, {s0, s1 - s0, true}, {s1, g - s1, false}};
+        for (const Seg& sg : segs) {
+            if (sg.n == 0) continue;
+            const float4* rad = !sendRad ? nullptr : (sg.own ? c->tileRadiance[b].p : reinterpret_cast<const float4*>(stage + offRad) + sg.start);
+            const int* rgba = !sendRgba ? nullptr : (sg.own ? c->tileRgba[b].p : reinterpret_cast<const int*>(stage + offRgba) + sg.start);
+            const uint2* aux = !sendAux ? nullptr : (sg.own ? c->tileAux[b].p : reinterpret_cast<const uint2*>(stage + offAux) + sg.start);
+            k_gather_scatter<<<grid_for(c, sg.n, 256), 256, 0, cs>>>(rad, rgba, aux, c->deintMap.p + sg.start, (int)sg.n, c->gRadiance.p, c->gRgba8.p, c->gDepth.p, c->gObjId.p);
+        }
+        CUDA_TRY(cudaGetLastError());
+        c->gatheredValid = true; c->gatheredWhat = what;
+    }
+    CUDA_TRY(cudaEventRecord(c->evGatherStop, cs));
+    CUDA_TRY(cudaEventRecord(c->evGatherDone[b], cs));
+    c->gatherPending[b] = true; c->gatherTimed = true;
     return RT_OK;
 }
 
@@ -1160,6 +1406,11 @@ RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
     for (size_t i = 0; i + 1 < c->traceEventsUsed; i += 2) { float m = 0.0f; if (cudaEventElapsedTime(&m, c->traceEvents[i], c->traceEvents[i + 1]) == cudaSuccess) tr += m; }
     out->lastTraceMs = tr;
     out->reserved[0] = (uint64_t)(c->traceEventsUsed / 2);   // number of extend launches timed
+    if (c->gatherTimed && c->commStream) {
+        CUDA_TRY(cudaStreamSynchronize(c->commStream));
+        float gm = 0.0f;
+        if (cudaEventElapsedTime(&gm, c->evGatherStart, c->evGatherStop) == cudaSuccess) out->reserved[3] = (uint64_t)(gm * 1000.0f);
+    }
     return RT_OK;
 }
 

@@ -86,6 +86,8 @@ def lib() -> C.CDLL:
     l.eng_renderer_set_knobs.argtypes = [C.c_void_p, C.POINTER(EngKnobs)]
     l.eng_renderer_render_direct_to_pbo.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
     l.eng_renderer_last_config.argtypes = [C.c_void_p, C.POINTER(L.RtRenderConfig)]
+    l.eng_renderer_new_communicator_id.argtypes = [C.c_void_p]
+    l.eng_renderer_init_multi_gpu.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     l.eng_framebuffer_download_to_cpu.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = l
     return l
@@ -320,6 +322,20 @@ class RTRenderer:
     def RenderDirectToPbo(self, pbo_device_ptr: int | None, width: int, height: int, frame: int = 0, dt: float = 0.0):
         self._l.eng_renderer_set_knobs(self.h, C.byref(self.knobs))
         _check(self._l.eng_renderer_render_direct_to_pbo(self.h, C.c_void_p(pbo_device_ptr or 0), width, height, frame, dt))
+
+    @staticmethod
+    def NewCommunicatorId() -> bytes:
+        """Rank 0: the 128-byte id every rank's InitMultiGpu needs (ncclGetUniqueId behind rt_comm_get_unique_id)."""
+        buf = C.create_string_buffer(L.RT_COMM_ID_BYTES)
+        _check(lib().eng_renderer_new_communicator_id(buf))
+        return buf.raw
+
+    def InitMultiGpu(self, unique_id: bytes, rank: int, world_size: int):
+        """This renderer = rank `rank` of `world_size` processes (one per GPU): RenderDirectToPbo then renders this rank's screen tiles,
+        gathers colour + depth + objectId on rank 0 (NCCL inside the library) and presents there."""
+        buf = C.create_string_buffer(unique_id, L.RT_COMM_ID_BYTES)
+        _check(self._l.eng_renderer_init_multi_gpu(self.h, buf, rank, world_size))
+        self.knobs.rank, self.knobs.worldSize = rank, world_size
 
     def last_config(self) -> L.RtRenderConfig:
         cfg = L.RtRenderConfig()

@@ -50,11 +50,15 @@ RT_FLAG_PUBLISH_RESERVOIRS = 1 << 7
 (RT_BUF_RGBA8, RT_BUF_DEPTH, RT_BUF_OBJID, RT_BUF_RADIANCE, RT_BUF_ACCUM, RT_BUF_PRIM_ID, RT_BUF_INST_ID, RT_BUF_PRIMARY_T,
  RT_BUF_SEG_COUNT, RT_BUF_TERM_CODE, RT_BUF_PATH_HASH, RT_BUF_GB_WORLDPOS, RT_BUF_GB_NORMAL, RT_BUF_GB_BASECOLOR, RT_BUF_GB_MATID,
  RT_BUF_TILE_RADIANCE, RT_BUF_RESERVOIR, RT_BUF_PRESENT) = range(18)
+RT_BUF_GATHERED_RGBA8, RT_BUF_GATHERED_DEPTH, RT_BUF_GATHERED_OBJID, RT_BUF_GATHERED_RADIANCE = 18, 19, 20, 21   # the image rt_gather_frame assembled on its root
+RT_GATHER_RGBA8, RT_GATHER_RADIANCE, RT_GATHER_DEPTH_OBJID = 1, 2, 4
+RT_COMM_ID_BYTES = 128
 RT_PRESENT_TAAU, RT_PRESENT_COPY = 0, 1
 # Reservoir (Engine/RTRay.cs:171-179), the element of RT_BUF_RESERVOIR
 RESERVOIR = np.dtype([("L", F3), ("wi", F3), ("pdf", "<f4"), ("w", "<f4"), ("wSum", "<f4"), ("m", "<i4"), ("lightId", "<i4")])
 
 RT_OK, RT_ERR_INVALID_ARGUMENT, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_INVALID_STATE, RT_ERR_UNSUPPORTED, RT_ERR_OUT_OF_MEMORY = 0, -1, -2, -3, -4, -5, -6
+RT_ERR_NCCL = -7
 
 
 class CFloat3(C.Structure):

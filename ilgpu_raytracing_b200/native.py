@@ -18,7 +18,8 @@ _LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b
 
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
-           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex", "rt_download_async"]
+           "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex", "rt_download_async",
+           "rt_comm_get_unique_id", "rt_comm_init", "rt_comm_destroy", "rt_gather_frame"]
 
 
 class RtError(RuntimeError):
@@ -57,6 +58,10 @@ def lib() -> C.CDLL:
     l.rt_deinterleave_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(L.RtStats)]
     l.rt_present.argtypes = [C.c_void_p, C.POINTER(L.RtPresentConfig), C.c_void_p, C.c_size_t]
+    l.rt_comm_get_unique_id.argtypes = [C.c_void_p, C.c_size_t]
+    l.rt_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    l.rt_comm_destroy.argtypes = [C.c_void_p]
+    l.rt_gather_frame.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
     for name in EXPORTS:
         if name not in ("rt_last_error",):
             getattr(l, name).restype = C.c_int
@@ -74,7 +79,8 @@ _BUF_DTYPES = {L.RT_BUF_RGBA8: (np.int32, 1), L.RT_BUF_DEPTH: (np.float32, 1), L
                L.RT_BUF_ACCUM: (np.float32, 4), L.RT_BUF_PRIM_ID: (np.int32, 1), L.RT_BUF_INST_ID: (np.int32, 1), L.RT_BUF_PRIMARY_T: (np.float32, 1),
                L.RT_BUF_SEG_COUNT: (np.uint8, 1), L.RT_BUF_TERM_CODE: (np.uint8, 1), L.RT_BUF_PATH_HASH: (np.uint32, 1),
                L.RT_BUF_GB_WORLDPOS: (np.float32, 3), L.RT_BUF_GB_NORMAL: (np.float32, 3), L.RT_BUF_GB_BASECOLOR: (np.float32, 3),
-               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4), L.RT_BUF_RESERVOIR: (L.RESERVOIR, 1), L.RT_BUF_PRESENT: (np.int32, 1)}
+               L.RT_BUF_GB_MATID: (np.int32, 1), L.RT_BUF_TILE_RADIANCE: (np.float32, 4), L.RT_BUF_RESERVOIR: (L.RESERVOIR, 1), L.RT_BUF_PRESENT: (np.int32, 1),
+               L.RT_BUF_GATHERED_RGBA8: (np.int32, 1), L.RT_BUF_GATHERED_DEPTH: (np.float32, 1), L.RT_BUF_GATHERED_OBJID: (np.int32, 1), L.RT_BUF_GATHERED_RADIANCE: (np.float32, 4)}
 
 
 class Context:
@@ -159,6 +165,19 @@ class Context:
         check(self._l.rt_deinterleave_tiles(self.h, C.c_void_p(gathered_ptr), offs, world_size, width, height, tile_size,
                                             C.c_void_p(out_radiance_ptr or 0), C.c_void_p(out_rgba8_ptr or 0)))
 
+    # ---- multi-GPU (one process + one context per GPU; the communicator lives in the library) ----
+    def comm_init(self, unique_id: bytes, rank: int, world_size: int):
+        assert len(unique_id) == L.RT_COMM_ID_BYTES
+        buf = C.create_string_buffer(unique_id, L.RT_COMM_ID_BYTES)
+        check(self._l.rt_comm_init(self.h, buf, L.RT_COMM_ID_BYTES, rank, world_size))
+
+    def comm_destroy(self):
+        check(self._l.rt_comm_destroy(self.h))
+
+    def gather_frame(self, root: int = 0, what: int = L.RT_GATHER_RGBA8 | L.RT_GATHER_DEPTH_OBJID):
+        """Tile payloads of the last frame -> the gathered image on `root` (NCCL send / recv + fused de-interleave / PackRGBA8), async."""
+        check(self._l.rt_gather_frame(self.h, root, what))
+
     def stats(self) -> dict:
         s = L.RtStats()
         check(self._l.rt_get_stats(self.h, C.byref(s)))
@@ -166,7 +185,15 @@ class Context:
         d["extendLaunchesTimed"] = int(s.reserved[0])
         d["raysAnyHitTraced"] = int(s.reserved[1])   # shadow rays traced individually + shared sun probes (raysShadow counts the reference's ShadowOcclusion calls)
         d["raysSunProbe"] = int(s.reserved[2])
+        d["lastGatherMs"] = int(s.reserved[3]) / 1000.0
         return d
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 makes it; the host distributes the 128 bytes to every rank)."""
+    buf = C.create_string_buffer(L.RT_COMM_ID_BYTES)
+    check(lib().rt_comm_get_unique_id(buf, L.RT_COMM_ID_BYTES))
+    return buf.raw
 
 
 def tiles_owned_pixels(width, height, tile_size, rank, world_size) -> int:

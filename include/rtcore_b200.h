@@ -21,7 +21,8 @@
  *     Engine/CudaGlInteropIndexBuffer.cs:56).
  *   - an rt_ctx is NOT thread safe (the reference is single threaded on the GL
  *     thread: Engine/RTWindow.cs:148-205).  One rt_ctx drives one GPU; multi-GPU
- *     is one process (and one rt_ctx) per GPU with screen-tile partitioning.
+ *     is one process (and one rt_ctx) per GPU with screen-tile partitioning and an
+ *     NCCL communicator inside the library (rt_comm_init / rt_gather_frame).
  *   - host arrays passed in are borrowed for the duration of the call only.
  *   - rt_render() is asynchronous on the context's stream; rt_sync() /
  *     rt_download() synchronise (the reference does one Synchronize() per frame:
@@ -219,6 +220,11 @@ enum {
     RT_BUF_GB_MATID     = 14, /* int32  per px : GpuGBuffer.matId */
     RT_BUF_TILE_RADIANCE = 15,/* float4 per OWNED px, tile-compacted (multi-GPU gather payload) */
     RT_BUF_PRESENT      = 17, /* int32 per OUTPUT px : what the last rt_present wrote (its own buffer or the mapped PBO) */
+    /* the image rt_gather_frame assembled on its root (whole frame, all ranks' tiles) */
+    RT_BUF_GATHERED_RGBA8    = 18, /* int32  per px */
+    RT_BUF_GATHERED_DEPTH    = 19, /* float  per px (RT_GATHER_DEPTH_OBJID) */
+    RT_BUF_GATHERED_OBJID    = 20, /* int32  per px (RT_GATHER_DEPTH_OBJID) */
+    RT_BUF_GATHERED_RADIANCE = 21, /* float4 per px (RT_GATHER_RADIANCE): what each pixel shows (Lout, or the progressive mean), w = frames accumulated */
     RT_BUF_RESERVOIR    = 16  /* RtReservoir per px : the reservoir buffer the last frame wrote ("resCur", Engine/RTRay.cs:23-48,294);
                                  only frames rendered with a reuse flag set write reservoirs */
 };
@@ -246,7 +252,7 @@ typedef struct RtStats {
     float    lastRenderMs;  /* CUDA-event time of the last rt_render on its stream */
     float    lastTraceMs;   /* of which: extend (closest + shadow) kernels */
     uint64_t bvhWideNodeCount, bvhPrimCount, bvhBytes;
-    uint64_t reserved[4];
+    uint64_t reserved[4];   /* [0] extend launches timed, [1] any-hit rays traced, [2] shared sun probes, [3] last rt_gather_frame in microseconds (on its stream) */
 } RtStats;
 
 typedef struct rt_ctx rt_ctx;
@@ -258,7 +264,8 @@ typedef enum RtStatus {
     RT_ERR_CUDA             = -3, /* a CUDA runtime call failed (message has the cudaError) */
     RT_ERR_INVALID_STATE    = -4, /* InvalidOperationException analogue (e.g. render before scene upload) */
     RT_ERR_UNSUPPORTED      = -5, /* feature outside the hot-path scope built so far */
-    RT_ERR_OUT_OF_MEMORY    = -6
+    RT_ERR_OUT_OF_MEMORY    = -6,
+    RT_ERR_NCCL             = -7  /* an NCCL call failed (message has ncclGetErrorString) */
 } RtStatus;
 
 /* ---- lifetime: replaces Context.Create(...Cuda()...) + CreateCudaAccelerator(deviceIndex)
@@ -334,6 +341,28 @@ RT_API int rt_deinterleave_tiles(rt_ctx* ctx, const void* gatheredDev, const int
                                  int worldSize, int width, int height, int tileSize,
                                  void* outRadianceDev /* float4*w*h or NULL */,
                                  void* outRgba8Dev   /* int32*w*h or NULL */);
+
+/* ---- multi-GPU behind the ABI.  The reference drives ONE device (ctor `RTRenderer(RTWindow, int deviceIndex = 0)`,
+ *      Engine/RTRenderer.cs:63,67) and its framebuffer is colour + depth + objectId (Engine/RTRay.cs:59-64,
+ *      Engine/Framebuffer.cs:112-160).  Here one process (and one rt_ctx) drives one GPU of the box; the contexts of a job share an
+ *      NCCL communicator owned by the library: rank 0 calls rt_comm_get_unique_id, the host hands the 128 bytes to every rank over
+ *      any channel it has (the C# host: a file, a pipe, MPI ...), every rank calls rt_comm_init.  Per frame every rank calls
+ *      rt_render with RtRenderConfig.rank / worldSize equal to the communicator's, then rt_gather_frame: grouped ncclSend / ncclRecv
+ *      of the tile payloads straight from the buffers the frame's kernels wrote (exact counts, no staging copy on the senders), and
+ *      on the root a fused de-interleave + PackRGBA8 into the gathered image: colour, and with RT_GATHER_DEPTH_OBJID depth and
+ *      objectId too, so that rt_present (TAAU needs objectId, Engine/RTTaa.cs:117-171) and Framebuffer.DownloadToCpu work on the root
+ *      exactly as on one GPU (RT_BUF_GATHERED_*).  The gather runs on the communicator's own stream: the next rt_render overlaps it.
+ *      NCCL is loaded at run time (libnccl.so.2); RT_ERR_UNSUPPORTED when it is absent. ---- */
+#define RT_COMM_ID_BYTES 128 /* sizeof(ncclUniqueId) */
+enum {
+    RT_GATHER_RGBA8       = 1u << 0, /* 4 B/px: packed colour only (display) */
+    RT_GATHER_RADIANCE    = 1u << 1, /* 16 B/px: float4 radiance (exact parity); the root packs RGBA8 from it */
+    RT_GATHER_DEPTH_OBJID = 1u << 2  /* + 8 B/px: depth and objectId */
+};
+RT_API int rt_comm_get_unique_id(void* id, size_t bytes /* RT_COMM_ID_BYTES */);
+RT_API int rt_comm_init(rt_ctx* ctx, const void* id, size_t bytes, int rank, int worldSize);
+RT_API int rt_comm_destroy(rt_ctx* ctx);
+RT_API int rt_gather_frame(rt_ctx* ctx, int root, uint32_t what /* RT_GATHER_* */);
 
 RT_API int rt_get_stats(rt_ctx* ctx, RtStats* out);
 

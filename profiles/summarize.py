@@ -7,6 +7,8 @@ launches: `ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --cs
 traffic : `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__inst_executed.sum,
            smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_extend -c 40 --csv --log-file ...
            python tests/gpu_frame_c4.py 64 1`   (every k_extend launch of ONE C4 frame; bench.py reads the JSON for roofline.traffic / issue)
+capture : round 2: `... -k regex:k_extend|k_shade|k_connect -c 80 ... python tests/gpu_frame_c4.py 64 1` + the source hash file written in the same gpurun call
+           (`python -c "import bench; print(bench.csrc_hash())" > gpurun_out/rNN_csrc_hash.txt`): python profiles/summarize.py capture <csv> profiles/r02_extend_capture_c4.json <hash file>
 Profiler times are cold-cache and serialised: compare shares, not absolutes."""
 import collections
 import csv
@@ -72,8 +74,43 @@ def traffic(src, dst):
     print(json.dumps(out, indent=1))
 
 
+def capture(src, dst, hash_file):
+    """Round-2 capture summary (bench.py reads it for roofline.issue / roofline.traffic and REFUSES it when csrc_hash differs
+    from the tree's): every launch of one C4 frame of the kernels named on the ncu command line, summed per kernel family; the
+    top-level fields are the k_extend totals."""
+    rs = rows_of(src)
+    fam = collections.defaultdict(lambda: collections.defaultdict(float))
+    ids = collections.defaultdict(set)
+    for r in rs:
+        k = re.sub(r"<.*$", "", r["kernel"])
+        v = r["value"]
+        if r["metric"] == "gpu__time_duration.sum":
+            v = to_ms(v, r["unit"])
+        elif r["unit"].lower().startswith(("kbyte", "mbyte", "gbyte")):
+            v *= {"k": 1e3, "m": 1e6, "g": 1e9}[r["unit"][0].lower()]
+        fam[k][r["metric"]] += v
+        ids[k].add(r["id"])
+
+    def one(k):
+        a, n = fam[k], len(ids[k])
+        return {"launches": n, "sum_duration_ms": a["gpu__time_duration.sum"], "dram_read_bytes": a["dram__bytes_read.sum"], "dram_write_bytes": a["dram__bytes_write.sum"],
+                "l2_bytes": a["lts__t_bytes.sum"], "warp_instructions": a["smsp__inst_executed.sum"], "thread_instructions": a["smsp__thread_inst_executed.sum"],
+                "lanes_per_instruction": a["smsp__thread_inst_executed.sum"] / max(1.0, a["smsp__inst_executed.sum"]),
+                "issue_active_pct_mean": a["smsp__issue_active.avg.pct_of_peak_sustained_active"] / max(1, n)}
+    out = {"csrc_hash": open(hash_file).read().strip(), "workload": "C4 frame (3840x2160, 64 spp, depth 8), one frame",
+           "command": "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,"
+                      "smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_extend|k_shade|k_connect -c 80 python tests/gpu_frame_c4.py 64 1",
+           "note": "durations under ncu are cold-cache and serialised: compare shares, not absolutes"}
+    out.update(one("k_extend"))
+    out["kernels"] = {k: one(k) for k in sorted(fam)}
+    json.dump(out, open(dst, "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
+    elif sys.argv[1] == "capture":
+        capture(sys.argv[2], sys.argv[3], sys.argv[4])
     else:
         traffic(sys.argv[2], sys.argv[3])
