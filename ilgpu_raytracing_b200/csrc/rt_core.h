@@ -570,6 +570,58 @@ RT_HD void restir_new_candidates(const LightEnv& env, f3 n, const Basis& B, f3 a
         reservoir_update(r, wi, pdfSel, LiDir, s, 1, 2, rng);
     }
 }
+#if defined(__CUDACC__)
+// RT_FLAG_FAST_SHADING (opt-in; north_star asks radiance only to 1e-4 relative RMS): the eight sky candidates of (1) scored with
+// fused multiply-adds and the special-function unit (sin / cos, sqrt, rsqrt, reciprocal to ~1e-7 relative) instead of ~235
+// instructions of exact arithmetic each.  Nothing here decides the path: every candidate still draws exactly three random
+// numbers, and the bounce direction, Russian roulette and all intersections stay exact - so hit ids, bounce counts and the RNG
+// streams are unchanged; only which sky direction wins a near-tie and the last bits of the direct-light term can differ.
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ void restir_new_candidates_fast(const LightEnv& env, f3 n, const Basis& B, f3 albedo, uint32_t& rng, Reservoir& r) {
+    const float mixLocal = 8.0f / 9.0f, mixDelta = 1.0f / 9.0f;
+    r.L = mk3(0, 0, 0); r.wi = mk3(0, 0, 0); r.pdf = 0; r.w = 0; r.wSum = 0; r.m = 0; r.lightId = 0;
+    // luminance(albedo * Li * k) = k * dot(albedo * lumaWeights, Li), Li = skyBottom + (skyTop - skyBottom) * t: two constants per vertex
+    const f3 aw = mk3(0.2126f * albedo.x, 0.7152f * albedo.y, 0.0722f * albedo.z);
+    const f3 dsky = mk3(env.skyTop.x - env.skyBottom.x, env.skyTop.y - env.skyBottom.y, env.skyTop.z - env.skyBottom.z);
+    const float lumB = __fmaf_rn(aw.x, env.skyBottom.x, __fmaf_rn(aw.y, env.skyBottom.y, aw.z * env.skyBottom.z));
+    const float lumD = __fmaf_rn(aw.x, dsky.x, __fmaf_rn(aw.y, dsky.y, aw.z * dsky.z));
+#pragma unroll 2
+    for (int i = 0; i < 8; i++) {
+        const float r1 = rng_next_f(rng), r2 = rng_next_f(rng);
+        float sphi, cphi;
+        __sincosf(2.0f * RTX_PI * r1, &sphi, &cphi);
+        const float sinT = fast_sqrt(r2), cosT = fast_sqrt(1.0f - r2);
+        const float x = cphi * sinT, y = sphi * sinT;
+        f3 v = mk3(__fmaf_rn(B.t.x, x, __fmaf_rn(B.b.x, y, n.x * cosT)), __fmaf_rn(B.t.y, x, __fmaf_rn(B.b.y, y, n.y * cosT)), __fmaf_rn(B.t.z, x, __fmaf_rn(B.b.z, y, n.z * cosT)));
+        const float inv = fast_rsqrt(fmaxf(1e-20f, __fmaf_rn(v.x, v.x, __fmaf_rn(v.y, v.y, v.z * v.z))));
+        const f3 wi = mk3(v.x * inv, v.y * inv, v.z * inv);
+        const float nl = fmaxf(0.0f, __fmaf_rn(n.x, wi.x, __fmaf_rn(n.y, wi.y, n.z * wi.z)));
+        const float pdfSel = fmaxf(RTX_EPS_MIN, fmaxf(RTX_EPS_MIN, nl * RTX_INV_PI) * mixLocal);
+        const float tbg = __fmaf_rn(0.5f, wi.y, 0.5f);
+        const float s = (nl * fast_rcp(pdfSel) * RTX_INV_PI) * __fmaf_rn(lumD, tbg, lumB);
+        // ReservoirUpdate (:394-405)
+        const float newSum = r.wSum + s;
+        const float acceptP = (newSum > 0.0f) ? s * fast_rcp(newSum) : 0.0f;
+        if (rng_next_f(rng) < acceptP) {
+            r.wi = wi; r.pdf = pdfSel; r.w = s; r.lightId = 1;
+            r.L = mk3(__fmaf_rn(dsky.x, tbg, env.skyBottom.x), __fmaf_rn(dsky.y, tbg, env.skyBottom.y), __fmaf_rn(dsky.z, tbg, env.skyBottom.z));
+        }
+        r.wSum = newSum;
+        r.m = r.m + 1;
+    }
+    {   // (2) the directional candidate, exact as in restir_new_candidates (once per vertex)
+        f3 wi = normalize(env.dirLightDir);
+        float nl = fmaxf(0.0f, dot(n, wi));
+        float pdfSel = fmaxf(RTX_EPS_MIN, mixDelta);
+        f3 LiDir = env.dirLightRadiance;
+        f3 f_over_p = albedo * LiDir * ((nl / pdfSel) * RTX_INV_PI);
+        float s = luminance(f_over_p);
+        reservoir_update(r, wi, pdfSel, LiDir, s, 1, 2, rng);
+    }
+}
+#endif
 RT_HD bool restir_finalize(const LightEnv& env, f3 n, f3 albedo, const Reservoir& r, f3* wiSel, f3* contrib) {
     const float mixLocal = 8.0f / 9.0f, mixDelta = 1.0f / 9.0f;   // mixLocal2 / mixDelta2, :528-529
     // (5) :519-539 up to the visibility test

@@ -2,8 +2,14 @@
 //
 //   PrimaryVisibilityKernel (RTRay.cs:188-201)  ->  generate_primary + [extend] + primary_finish
 //   PathTraceKernel         (RTRay.cs:203-325)  ->  per sample batch:
-//        shade_first, then for every depth: [extend closest] + [extend shadow -> connect] + shade_next,
-//        then accumulate (per-pixel sum over samples in sample order, SafeColor, mean, PackRGBA8).
+//        shade_first, then for every depth: [extend closest + shadow rays, one launch] + shade_next (rays that HIT only),
+//        then accumulate (settles what is still pending per path - the last shadow ray's contribution, the sky of a bounce ray
+//        that left the scene -, then the per-pixel sum over samples in sample order, SafeColor, mean, PackRGBA8).
+//
+// Deferred settlement (round 2): the extend kernel never reads path state.  A shadow ray's visibility goes to stC[slot].w and is
+// added to Li by whoever touches the path next (shade_next of the bounce ray's hit, or accumulate); a bounce ray that misses only
+// leaves its direction in missD[slot], and accumulate adds throughput * sky(direction).  Per path the additions happen in the
+// reference's order (direct light of vertex d, then whatever vertex d + 1 adds), so Li is bit-identical.
 //
 // Each function below is the body of one kernel for one work item; rt_kernels.cu wraps them in
 // grid-stride / persistent __global__ kernels, tests/hostsim wraps them in plain loops.
@@ -41,7 +47,9 @@ struct WaveBuffers {
     int* rgba8; float* depth; int* objId; float4* radiance; float4* accum;
     // per path slot (path j = sampleInBatch * npx + ownedPixel)
     float4* stThr;    // throughput.xyz | rng state
-    float4* stLi;     // Li.xyz | segCount (bits 0-7), terminator (bits 8-15)
+    float4* stLi;     // Li.xyz | segCount (bits 0-7), terminator (bits 8-15), path flags (bits 16+)
+    float4* stC;      // pending direct-light term of the path's latest Lambert vertex: throughput * f/p * W | visibility (written by the any-hit extend)
+    float4* missD;    // direction of the path's bounce ray when it left the scene (written by the closest-hit extend) | unused
     uint32_t* pathHash;
     // reservoirs (null unless a reuse flag is set): per path slot, the reservoir of the path's first Lambert vertex ("outRes",
     // RTRay.cs:289-296), and per global pixel the frame's resCur, which accumulate() fills from the LAST sample that wrote one
@@ -51,12 +59,15 @@ struct WaveBuffers {
     uint8_t *segCountOut, *termCodeOut; uint32_t* pathHashOut;
 };
 
-// Ray queues (SoA of float4): o.w = path slot (int bits); inv = the box-test reciprocal of d (box_idir), computed
-// once by the producer so the persistent extend kernel starts a ray with three 128-bit loads and no divisions.
-struct RayQueue { float4* o; float4* d; float4* inv; };   // o.w = d.w = path slot: a consumer that needs only one of the two vectors still gets the slot
-struct ShadowQueue { float4* o; float4* d; float4* inv; float4* c; };   // c.xyz = throughput * f_over_p * W
-
-RT_HD float4 box_idir4(f3 d) { const f3 i = box_idir(d); return make_float4(i.x, i.y, i.z, 0.0f); }
+// Ray queues (SoA of float4): o.w = d.w = path slot (int bits): a consumer that needs only one of the two vectors still gets the
+// slot.  32 B per ray: the box-test reciprocal of d is derived by the extend kernel (three divisions per ray against 32 B of
+// DRAM traffic per ray it cost to store and re-read it; round 1 stored it).
+struct RayQueue { float4* o; float4* d; };
+// What the closest-hit extend writes per ray: the primitive index for EVERY ray (4 B; -1 = miss: all the scan of shade_next reads),
+// and t | bu | bv only for rays that hit (16 B).
+struct HitQueue { int* prim; float4* tuv; };
+RT_HD HitRec load_hit(const HitQueue& h, int k) { const float4 v = h.tuv[k]; HitRec r; r.t = v.x; r.prim = h.prim[k]; r.bu = v.y; r.bv = v.z; return r; }
+struct ShadowQueue { float4* o; float4* d; };   // the pending contribution and the visibility live per PATH (WaveBuffers::stC), not per queue entry
 
 RT_HD uint32_t fnv_fold(uint32_t h, uint32_t v) { return (h ^ v) * 16777619u; }
 
@@ -88,16 +99,16 @@ RT_HD void generate_primary(const FrameConst& fc, const RayQueue& q, int i) {
     f3 d = primary_dir(fc, x, y);
     q.o[i] = make_float4(fc.camOrigin.x, fc.camOrigin.y, fc.camOrigin.z, u2f((uint32_t)i));
     q.d[i] = make_float4(d.x, d.y, d.z, u2f((uint32_t)i));
-    q.inv[i] = box_idir4(d);
 }
 
 // ------------------------------------------------------------------------------------------------ primary finish
 // PrimaryVisibilityKernel after TraceClosest (RTRay.cs:197-200) + GpuGBuffer.StoreHit/StoreMiss (:90-108);
 // also the depth / objectId halves of GpuFramebuffer.Store (:59-64, :324), which depend on the G-buffer only.
-RT_HD void primary_finish(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, const RayQueue& q, const HitRec* hits, int i) {
+RT_HD void primary_finish(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, const RayQueue& q, const HitQueue& hits, int i) {
     const float4 ro = q.o[i], rd = q.d[i];
     const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-    const HitRec h = hits[i];
+    HitRec h; h.prim = hits.prim[i]; h.t = 1e30f; h.bu = 0.0f; h.bv = 0.0f;
+    if (h.prim >= 0) h = load_hit(hits, i);
     const int pix = fc.pixelMap[i];
     f3 pos; int oid;
     if (!(h.t < 1e29f)) {
@@ -143,13 +154,13 @@ RT_HD void sun_probe_generate(const FrameConst& fc, const WaveBuffers& wb, int i
     const int k = queue_alloc(shCount);
     shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)i));
     shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, u2f((uint32_t)i));
-    shQ.inv[k] = box_idir4(s.d);
-    shQ.c[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
+// the probe's visibility arrives where every shadow ray's does: stC[slot].w, slot = the owned pixel (shade_first, which runs after
+// this, overwrites stC for the path slots it uses)
 RT_HD void sun_probe_store(const WaveBuffers& wb, const ShadowQueue& shQ, int k) {
     const int i = (int)f2u(shQ.o[k].w);
     float4 ph = wb.gbPosHit[i];
-    ph.w = u2f(f2u(ph.w) | GB_SUN_KNOWN | (shQ.c[k].w != 0.0f ? GB_SUN_VISIBLE : 0u));
+    ph.w = u2f(f2u(ph.w) | GB_SUN_KNOWN | (wb.stC[i].w != 0.0f ? GB_SUN_VISIBLE : 0u));
     wb.gbPosHit[i] = ph;
 }
 
@@ -157,7 +168,11 @@ RT_HD void sun_probe_store(const WaveBuffers& wb, const ShadowQueue& shQ, int k)
 struct PathVertex { f3 pos, nrm, alb, I; int shade; float ior; };
 
 // path flags kept in stLi.w above the parity taps (bits 0-7 segment count, 8-15 terminator)
-enum : uint32_t { PATH_WROTE_RESERVOIR = 1u << 16 };
+enum : uint32_t {
+    PATH_WROTE_RESERVOIR = 1u << 16,
+    PATH_PENDING_SHADOW  = 1u << 17,   // stC[path] holds a contribution whose shadow ray has been (or is being) traced and not yet added to Li
+    PATH_RAY_IN_FLIGHT   = 1u << 18    // a bounce ray was pushed and no hit of it has been shaded: at accumulate time that means it missed (missD[path])
+};
 
 // ReprojectToPrevPixel (RTRay.cs:339-360)
 RT_HD int reproject_to_prev_pixel(const FrameConst& fc, f3 posWS) {
@@ -238,7 +253,7 @@ RT_HD void restir_imports(const FrameConst& fc, const WaveBuffers& wb, int path,
 // Pushes the continuation ray and, for a Lambert vertex, the ReSTIR-selected shadow ray.
 // Returns false when Russian roulette killed the path.
 // REUSE = a reuse flag is set (compile-time, so the common path does not carry the import code's registers)
-template <bool REUSE>
+template <bool REUSE, bool FAST = false>
 // sunFlags: the pixel's GB_SUN_* bits when this is the first vertex of the path and the shared probe applies, else 0;
 // *direct receives "throughput * direct" when the probe answered instead of a shadow ray (else stays 0), *probed counts it.
 RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathVertex& v, int depth, int path, f3& thr, uint32_t& rng, uint32_t& pflags,
@@ -270,6 +285,10 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
         f3 wiSel, contrib;
         const Basis B = orthonormal_basis(v.nrm);
         Reservoir r;
+#if defined(__CUDA_ARCH__)
+        if (FAST) restir_new_candidates_fast(fc.env, v.nrm, B, v.alb, rng, r);   // RT_FLAG_FAST_SHADING (device only)
+        else
+#endif
         restir_new_candidates(fc.env, v.nrm, B, v.alb, rng, r);
         // only the FIRST Lambert vertex of a sample imports from the previous frame and publishes its reservoir ("wroteReservoir", :280-297)
         const bool first = (pflags & PATH_WROTE_RESERVOIR) == 0u;
@@ -291,8 +310,8 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
             int k = queue_alloc(shCount);
             shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)path));
             shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, u2f((uint32_t)path));
-            shQ.inv[k] = box_idir4(s.d);
-            shQ.c[k] = make_float4(c.x, c.y, c.z, 0.0f);
+            wb.stC[path] = make_float4(c.x, c.y, c.z, 0.0f);
+            pflags |= PATH_PENDING_SHADOW;
         }
         f3 wi = sample_hemisphere_cosine(v.nrm, B, rng);   // :302
         ray = make_ray_normal_offset(v.pos, v.nrm, wi);
@@ -307,26 +326,34 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
     int k = queue_alloc(nextCount);
     nextQ.o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f((uint32_t)path));
     nextQ.d[k] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f((uint32_t)path));
-    nextQ.inv[k] = box_idir4(ray.d);
+    pflags |= PATH_RAY_IN_FLIGHT;
     return true;
+}
+
+// "Li += throughput * direct" when Visible() (RTRay.cs:286,291,526-537) for the shadow ray queued at the path's latest Lambert
+// vertex: runs at the path's next touch, i.e. before anything of the next vertex is added, like the reference's statement order.
+RT_HD void settle_pending_shadow(const WaveBuffers& wb, int j, uint32_t& pflags, f3& Li) {
+    if ((pflags & PATH_PENDING_SHADOW) == 0u) return;
+    pflags &= ~PATH_PENDING_SHADOW;
+    const float4 c = wb.stC[j];
+    const bool visible = c.w != 0.0f;
+    if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (visible ? 1u : 0u));
+    if (visible) { Li.x = Li.x + c.x; Li.y = Li.y + c.y; Li.z = Li.z + c.z; }
 }
 
 RT_HD uint32_t pack_aov(int seg, int term) { return (uint32_t)(seg & 0xFF) | ((uint32_t)(term & 0xFF) << 8); }
 
 // depth 0: start every path of the batch from the G-buffer (RTRay.cs:210-232)
-template <bool REUSE = false>
+template <bool REUSE = false, bool FAST = false>
 RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBase, int j,
                        const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, unsigned* probedCount = nullptr) {
     const int i = j % fc.npx;
     const int s = sampleBase + j / fc.npx;
     int x, y; pixel_xy(fc, fc.pixelMap[i], &x, &y);
     uint32_t rng = rng_seed_pixel((uint32_t)x, (uint32_t)y, fc.frame, (uint32_t)s, 0xC0FFEEu, fc.rngLockNoise);   // :212
-    if (wb.pathHash) wb.pathHash[j] = 0x811C9DC5u;
     const float4 ph = wb.gbPosHit[i];
-    if ((f2u(ph.w) & GB_HIT) == 0u) {   // :214-219 — the sky for primary misses is added by accumulate()
-        wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_PRIMARY_MISS)));
-        return;
-    }
+    if ((f2u(ph.w) & GB_HIT) == 0u) return;   // :214-219 - a primary miss has no path state at all: accumulate() adds the sky per sample from the G-buffer flag alone
+    if (wb.pathHash) wb.pathHash[j] = 0x811C9DC5u;
     f3 thr = mk3(1.0f, 1.0f, 1.0f);
     if (fc.maxDepth <= 0) {
         wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_MAXDEPTH)));
@@ -345,44 +372,42 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     // with reuse on, an imported reservoir may carry another frame's sun direction: every sample traces its own ray then
     const uint32_t sunFlags = REUSE ? 0u : (f2u(ph.w) & (GB_SUN_KNOWN | GB_SUN_VISIBLE));
     f3 direct = mk3(0.0f, 0.0f, 0.0f); int probed = 0;
-    bool alive = shade_vertex<REUSE>(fc, wb, v, 0, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount, sunFlags, &direct, &probed);
+    bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, 0, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount, sunFlags, &direct, &probed);
     wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
-    // connect_shadow would have run before anything else touches Li: Li = 0 + throughput * direct, and the visibility fold of the path hash
+    // a probed shadow ray is settled on the spot, before anything else touches Li: Li = 0 + throughput * direct, and the visibility fold of the path hash
     if (probed != 0 && wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (probed == 2 ? 1u : 0u));
     wb.stLi[j] = make_float4(0.0f + direct.x, 0.0f + direct.y, 0.0f + direct.z, u2f(pflags | pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
     if (probedCount && probed != 0) (*probedCount)++;
 }
 
-// A bounce ray that left the scene: "Li += throughput * SkyWeighted(ray.dir); break" (RTRay.cs:242,273,315).  On the device
-// this runs inside the extend kernel as a ray finishes (only rays that hit something go on to the shade kernel, so its
-// warps stay full); the host simulator reaches it through shade_next.
-RT_HD void miss_update(const LightEnv& env, const WaveBuffers& wb, int j, f3 d) {
-    const float4 st = wb.stThr[j];
-    const float4 li4 = wb.stLi[j];
-    const f3 thr = mk3(st.x, st.y, st.z);
-    f3 Li = mk3(li4.x, li4.y, li4.z);
-    const int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
-    Li = Li + thr * sky_weighted(env, d);
-    if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
-    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f((f2u(li4.w) & 0xFFFF0000u) | pack_aov(seg, RT_TERM_MISS)));
+// What the extend kernels leave behind when a ray is done (the device kernels write the same words with streaming stores):
+//   closest hit: the primitive index for every ray, t | bu | bv for hits, and for a bounce ray that left the scene its direction
+//                under the path's slot (settled by accumulate); any hit: the visibility under the path's slot.
+RT_HD void store_closest_result(const HitQueue& hq, float4* missD, int k, int slot, const HitRec& h, f3 d) {
+    const bool hit = h.t < 1e29f;   // SceneDeviceViews.cs:85
+    hq.prim[k] = hit ? h.prim : -1;
+    if (hit) hq.tuv[k] = make_float4(h.t, h.bu, h.bv, 0.0f);
+    else if (missD) missD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
 }
+RT_HD void store_anyhit_result(float4* stC, int slot, bool occluded) { stC[slot].w = occluded ? 0.0f : 1.0f; }
 
-// depth >= 1: consume the closest-hit result of the ray traced at depth-1 (TraceNext, RTRay.cs:659-671) and shade the new vertex.
-template <bool REUSE = false>
+// depth >= 1: consume the closest-hit result of a ray traced at depth-1 that HIT something (TraceNext, RTRay.cs:659-671) and shade
+// the new vertex.  Rays that missed never come here: accumulate() settles them (settle_miss).
+template <bool REUSE = false, bool FAST = false>
 RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, int depth,
-                      const RayQueue& curQ, const HitRec* hits, int k,
+                      const RayQueue& curQ, const HitQueue& hits, int k,
                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
     const float4 ro = curQ.o[k], rd = curQ.d[k];
     const int j = (int)f2u(ro.w);
     const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
-    const HitRec h = hits[k];
-    if (!(h.t < 1e29f)) { miss_update(fc.env, wb, j, d); return; }
+    const HitRec h = load_hit(hits, k);
     const float4 st = wb.stThr[j];
     float4 li4 = wb.stLi[j];
     f3 thr = mk3(st.x, st.y, st.z), Li = mk3(li4.x, li4.y, li4.z);
     uint32_t rng = f2u(st.w);
     int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
-    uint32_t pflags = f2u(li4.w) & 0xFFFF0000u;
+    uint32_t pflags = f2u(li4.w) & 0xFFFF0000u & ~PATH_RAY_IN_FLIGHT;   // the ray arrived
+    settle_pending_shadow(wb, j, pflags, Li);                            // direct light of the previous vertex first (:286,291)
     if (wb.pathHash || depth < fc.maxDepth) {
         const Surface s = eval_surface(sc, o, d, h);
         if (wb.pathHash) wb.pathHash[j] = fnv_fold(fnv_fold(wb.pathHash[j], (uint32_t)s.instId), (uint32_t)s.primId);
@@ -392,7 +417,7 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
             v.nrm = normalize(s.normal);   // :666
             v.alb = s.albedo; v.shade = s.shade; v.ior = s.ior;
             v.I = d;                        // "I = ray.dir" :243,274,316
-            bool alive = shade_vertex<REUSE>(fc, wb, v, depth, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount);
+            bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, depth, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount);
             wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
             wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
             return;
@@ -400,17 +425,6 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
     }
     // depth == maxDepth: the depth loop has run out (:233); nothing more is added
     wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, RT_TERM_MAXDEPTH)));
-}
-
-// connect: add the pending direct-light term of an unoccluded shadow ray (RTRay.cs:526-537, 286/291)
-RT_HD void connect_shadow(const WaveBuffers& wb, const ShadowQueue& shQ, int k, bool occluded) {
-    const int j = (int)f2u(shQ.o[k].w);
-    if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (occluded ? 0u : 1u));
-    if (occluded) return;
-    const float4 c = shQ.c[k];
-    float4 li4 = wb.stLi[j];
-    li4.x = li4.x + c.x; li4.y = li4.y + c.y; li4.z = li4.z + c.z;
-    wb.stLi[j] = li4;
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -427,9 +441,31 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
     int resOwner = -1;   // the reference's samples run in order and each overwrites resCur[index] (:294): the last writer's reservoir stays
     for (int s = 0; s < nSamples; s++) {
         const int j = s * fc.npx + i;
-        const float4 li4 = wb.stLi[j];
+        if (primaryMiss) {   // no path was started (shade_first): "Lframe += SafeColor(sky)" per sample (:214-219), nothing to read
+            L = L + skyMiss;
+            if (wb.segCountOut) {
+                const size_t oi = (size_t)(sampleBase + s) * plane + (size_t)pix;
+                wb.segCountOut[oi] = 0; wb.termCodeOut[oi] = (uint8_t)RT_TERM_PRIMARY_MISS; wb.pathHashOut[oi] = 0x811C9DC5u;
+            }
+            continue;
+        }
+        float4 li4 = wb.stLi[j];
         if (f2u(li4.w) & PATH_WROTE_RESERVOIR) resOwner = j;
-        L = L + (primaryMiss ? skyMiss : safe_color(mk3(li4.x, li4.y, li4.z)));
+        if ((f2u(li4.w) & (PATH_PENDING_SHADOW | PATH_RAY_IN_FLIGHT)) != 0u) {
+            // what the wavefront left pending for this path, in the reference's order: the direct light of its last Lambert vertex
+            // (RTRay.cs:286,291), then the sky seen by a bounce ray that left the scene: "Li += throughput * SkyWeighted(ray.dir)" (:242,273,315)
+            uint32_t pf = f2u(li4.w);
+            f3 Li = mk3(li4.x, li4.y, li4.z);
+            settle_pending_shadow(wb, j, pf, Li);
+            if (pf & PATH_RAY_IN_FLIGHT) {
+                const float4 st = wb.stThr[j], md = wb.missD[j];
+                Li = Li + mk3(st.x, st.y, st.z) * sky_weighted(fc.env, mk3(md.x, md.y, md.z));
+                if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
+                pf = (pf & 0xFFFF0000u & ~PATH_RAY_IN_FLIGHT) | pack_aov((int)(pf & 0xFFu) + 1, RT_TERM_MISS);
+            }
+            li4 = make_float4(Li.x, Li.y, Li.z, u2f(pf));
+        }
+        L = L + safe_color(mk3(li4.x, li4.y, li4.z));
         if (wb.segCountOut) {
             const uint32_t a = f2u(li4.w);
             const size_t oi = (size_t)(sampleBase + s) * plane + (size_t)pix;

@@ -43,6 +43,8 @@ using namespace rtx;
 #define RT_PRIM_VOTE 1       // lanes that must have a primitive queued before the warp runs a primitive phase (sweep: 1 is best)
 #endif
 
+#define RT_PATH_BYTES 180   // device memory per path of a wavefront pass: state 4 x 16 (throughput | rng, Li | flags, pending direct light, miss direction), two ray queues 2 x 32, shadow queue 32, hit record 4 + 16
+
 struct DeviceStats {   // zeroed at the start of every rt_render
     unsigned long long raysPrimary, raysBounce, raysShadow, wideNodes, tris, spheres;
     unsigned long long raysSunProbe;    // shared sun-visibility probes traced (one per Lambert primary vertex facing the sun)
@@ -51,12 +53,12 @@ struct DeviceStats {   // zeroed at the start of every rt_render
 
 struct ExtendArgs {
     DeviceScene sc;
-    const float4* rayO; const float4* rayD; const float4* rayI;   // origin | path slot, direction, box-test reciprocal
+    const float4* rayO; const float4* rayD;   // origin | path slot, direction | path slot (the box-test reciprocal is derived here: 3 divisions against 32 B of DRAM traffic per ray)
     const int* count;          // number of rays in the queue (device memory: written by the producing kernel)
     int* work;                 // global fetch cursor for this launch (zeroed per frame)
-    HitRec* hits;              // closest: one record per ray
-    ShadowQueue shq;           // any-hit: the queue itself (o/d alias rayO/rayD) ...
-    WaveBuffers wb;            // ... and the path state connect() updates
+    HitQueue hits;             // closest: primitive index per ray, t | bu | bv per hit
+    float4* missD;             // closest: where a bounce ray that left the scene leaves its direction, by path slot (null: primary rays)
+    float4* stC;               // any-hit: the visibility goes to stC[path slot].w, next to the pending contribution
     DeviceStats* stats;
     int statSlot;              // 0 primary, 1 bounce, 2 shadow, 3 sun probe
     int stackEntries;          // traversal stack entries per lane in shared memory (debug bounds checks)
@@ -80,21 +82,11 @@ __device__ unsigned long long g_phase[32];
 #else
 #define PHASE_ADD(i, v) do { } while (0)
 #endif
+// One queue's worth of the persistent loop.  `stack` / the hit table are set up by the kernel; a warp returns when the queue is
+// exhausted and its own lanes are done - it does NOT wait for the other warps, so in the fused kernel below a warp that runs out
+// of closest-hit rays goes straight on to the any-hit queue while others still finish theirs (no serialised launch tail).
 template <bool ANY_HIT, bool COUNT>
-__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend(ExtendArgs a) {
-    // dynamic shared memory: hit table | traversal stacks [entries][RT_EXTEND_THREADS], entries = depth of this scene's wide
-    // BVH + 1 (sized by the host, so a shallow tree leaves more of the SM's 228 KB to the L1 cache that serves the node fetches)
-    extern __shared__ __align__(16) uint32_t smemRaw[];
-    uint32_t* hitTable = smemRaw;
-    uint2* smemStack = reinterpret_cast<uint2*>(hitTable + RT_HIT_TABLE_WORDS);
-    LaneStack stack;
-    stack.smem = smemStack + threadIdx.x;
-    stack.stride = RT_EXTEND_THREADS;
-    stack.sp = 0;
-    stack.lut = hitTable;
-#if RT_DEBUG_BOUNDS
-    stack.entries = a.stackEntries;
-#endif
+__device__ __forceinline__ void extend_queue(const ExtendArgs& a, LaneStack& stack) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
@@ -106,19 +98,22 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
     if (n <= 0 || a.sc.nNodes <= 0) {
         if (!ANY_HIT) {   // empty scene: everything misses
             const int stride = gridDim.x * blockDim.x;
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) { HitRec h; h.t = 1e30f; h.prim = -1; h.bu = 0.0f; h.bv = 0.0f; a.hits[i] = h; }
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+                const float4 ro = a.rayO[i], rd = a.rayD[i];
+                HitRec h; h.t = 1e30f; h.prim = -1; h.bu = 0.0f; h.bv = 0.0f;
+                store_closest_result(a.hits, a.missD, i, (int)f2u(ro.w), h, mk3(rd.x, rd.y, rd.z));
+            }
         } else {
             const int stride = gridDim.x * blockDim.x;
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) a.shq.c[i].w = 1.0f;   // nothing can occlude
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) store_anyhit_result(a.stC, (int)f2u(a.rayO[i].w), false);   // nothing can occlude
         }
         return;
     }
-    for (uint32_t i = threadIdx.x; i < RT_HIT_TABLE_WORDS; i += RT_EXTEND_THREADS) hitTable[i] = hit_table_entry(i >> 8, i & 255u);
-    __syncthreads();
     Traversal<ANY_HIT, COUNT> tr;
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0; cnt.spheres = 0;
     bool active = false, exhausted = false;
     int myRay = -1;
+    uint32_t mySlot = 0u;            // the path slot the ray belongs to (where a miss / the visibility is settled)
     int poolNext = 0, poolEnd = 0;   // warp-uniform
 #if RT_PHASE_STATS
     unsigned long long ph[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -143,8 +138,10 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
                 const int r = __popc(idle & ltMask);
                 if (r < take) {
                     myRay = poolNext + r;
-                    const float4 ro = __ldcs(a.rayO + myRay), rd = __ldcs(a.rayD + myRay), ri = __ldcs(a.rayI + myRay);
-                    tr.init(mk3(ro.x, ro.y, ro.z), mk3(rd.x, rd.y, rd.z), mk3(ri.x, ri.y, ri.z), ANY_HIT ? 1e29f : 1e30f, stack);   // shadow tMax: RTRay.cs:623
+                    const float4 ro = __ldcs(a.rayO + myRay), rd = __ldcs(a.rayD + myRay);
+                    const f3 d = mk3(rd.x, rd.y, rd.z);
+                    mySlot = f2u(ro.w);
+                    tr.init(mk3(ro.x, ro.y, ro.z), d, box_idir_device(d), ANY_HIT ? 1e29f : 1e30f, stack);   // shadow tMax: RTRay.cs:623
                     active = true;
                 }
             }
@@ -178,10 +175,14 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
             }
         }
         if (active && tr.done) {
-            if (ANY_HIT) __stcs(&a.shq.c[myRay].w, tr.occluded ? 0.0f : 1.0f);   // visibility of the pending contribution; k_connect adds it to the path
+            // fire-and-forget stores, no path state is read here (same words as store_anyhit_result / store_closest_result)
+            if (ANY_HIT) __stcs(&a.stC[mySlot].w, tr.occluded ? 0.0f : 1.0f);   // visibility of the pending contribution: added to Li at the path's next touch
             else {
                 const HitRec h = tr.result();
-                __stcs(reinterpret_cast<float4*>(a.hits) + myRay, make_float4(h.t, __int_as_float(h.prim), h.bu, h.bv));
+                const bool hit = h.t < 1e29f;
+                __stcs(a.hits.prim + myRay, hit ? h.prim : -1);
+                if (hit) __stcs(a.hits.tuv + myRay, make_float4(h.t, h.bu, h.bv, 0.0f));
+                else if (a.missD) __stcs(a.missD + mySlot, make_float4(tr.d.x, tr.d.y, tr.d.z, 0.0f));   // accumulate adds throughput * sky(d)
             }
             active = false;
         }
@@ -196,7 +197,41 @@ __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_ext
     }
 }
 
-__global__ void k_primary_finish(FrameConst fc, DeviceScene sc, WaveBuffers wb, RayQueue q, const HitRec* hits) {
+// dynamic shared memory of the extend kernels: hit table | traversal stacks [entries][RT_EXTEND_THREADS], entries = depth of this
+// scene's wide BVH + 1 (sized by the host, so a shallow tree leaves more of the SM's 228 KB to the L1 cache that serves the node fetches)
+__device__ __forceinline__ void extend_setup(LaneStack& stack, int stackEntries) {
+    extern __shared__ __align__(16) uint32_t smemRaw[];
+    uint32_t* hitTable = smemRaw;
+    uint2* smemStack = reinterpret_cast<uint2*>(hitTable + RT_HIT_TABLE_WORDS);
+    stack.smem = smemStack + threadIdx.x;
+    stack.stride = RT_EXTEND_THREADS;
+    stack.sp = 0;
+    stack.lut = hitTable;
+#if RT_DEBUG_BOUNDS
+    stack.entries = stackEntries;
+#endif
+    for (uint32_t i = threadIdx.x; i < RT_HIT_TABLE_WORDS; i += RT_EXTEND_THREADS) hitTable[i] = hit_table_entry(i >> 8, i & 255u);
+    __syncthreads();
+}
+
+template <bool ANY_HIT, bool COUNT>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ ExtendArgs a) {
+    LaneStack stack;
+    extend_setup(stack, a.stackEntries);
+    extend_queue<ANY_HIT, COUNT>(a, stack);
+}
+
+// The closest-hit rays and the shadow rays of one depth are independent (their results meet again in the next shade / accumulate): ONE persistent launch walks both queues - the long closest-hit rays first, the any-hit rays fill the tail.
+struct ExtendPairArgs { ExtendArgs closest, anyhit; };
+template <bool COUNT>
+__global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend_pair(const __grid_constant__ ExtendPairArgs a) {
+    LaneStack stack;
+    extend_setup(stack, a.closest.stackEntries);
+    extend_queue<false, COUNT>(a.closest, stack);
+    extend_queue<true, COUNT>(a.anyhit, stack);
+}
+
+__global__ void k_primary_finish(FrameConst fc, DeviceScene sc, WaveBuffers wb, RayQueue q, HitQueue hits) {
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < fc.npx; i += stride) primary_finish(fc, sc, wb, q, hits, i);
 }
@@ -210,20 +245,20 @@ __global__ void k_sun_store(WaveBuffers wb, ShadowQueue shq, const int* count) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) sun_probe_store(wb, shq, k);
 }
 
-template <bool REUSE>
+template <bool REUSE, bool FAST>
 __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, DeviceStats* stats) {
     const int stride = gridDim.x * blockDim.x;
     unsigned probed = 0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first<REUSE>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first<REUSE, FAST>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed);
     for (int o = 16; o > 0; o >>= 1) probed += __shfl_xor_sync(0xFFFFFFFFu, probed, o);
     if ((threadIdx.x & 31u) == 0u && probed != 0u) atomicAdd(&stats->shadowProbed, (unsigned long long)probed);
 }
 
-// Most bounce rays of an open scene leave it, and shading the few hits in place left ~5 of 32 lanes busy.  So each block
-// takes chunks of RT_SHADE_CHUNK consecutive rays and makes two passes over a chunk: (1) every lane looks at one ray at a
-// time: a miss adds the sky to its path right away (short); a hit is classified by the material of what it hit and appended
-// to a list in shared memory - Lambert vertices (long: nine ReSTIR candidates) from the front, mirror / glass vertices
-// (short) from the back - with ballot + one shared-memory atomic per warp: no global atomics, no extra global traffic;
+// Most bounce rays of an open scene leave it; those never reach this kernel's shading (the extend kernel leaves their direction
+// with the path and accumulate adds the sky).  Each block takes chunks of RT_SHADE_CHUNK consecutive rays and makes two passes:
+// (1) a scan of the 4-byte primitive indices (sixteen per thread as four independent 128-bit loads): a hit is classified by the
+// material of what it hit and appended to a list in shared memory - Lambert vertices (long: nine ReSTIR candidates) from the
+// front, mirror / glass vertices (short) from the back - with ballot + one shared-memory atomic per warp: no global atomics;
 // (2) the two ends of the list are shaded one after the other, each with every lane busy on the same kind of vertex.
 #ifndef RT_SHADE_CHUNK
 #define RT_SHADE_CHUNK 4096
@@ -236,8 +271,8 @@ __device__ __forceinline__ bool hit_is_specular(const DeviceScene& sc, int prim)
     else if (sc.triMaterials) shade = sc.materials[sc.triMatIndex[primId]].Shading;
     return shade == RT_SHADING_MIRROR || shade == RT_SHADING_GLASS;
 }
-template <bool REUSE>
-__global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, const HitRec* hits, const int* curCount,
+template <bool REUSE, bool FAST>
+__global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
     __shared__ int list[RT_SHADE_CHUNK];
     __shared__ int nFront, nBack;
@@ -246,30 +281,38 @@ __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene s
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
+    static_assert(RT_SHADE_CHUNK == 256 * 16, "scan: four int4 loads per thread");
     for (int ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
         if (threadIdx.x == 0) { nFront = 0; nBack = 0; }
         __syncthreads();
         const int base = ch * RT_SHADE_CHUNK;
-        for (int i = threadIdx.x; i < RT_SHADE_CHUNK; i += 256) {
-            const int k = base + i;
-            const bool valid = k < n;
-            HitRec h; h.t = 1e30f; h.prim = -1;
-            if (valid) { const float4 hv = __ldg(reinterpret_cast<const float4*>(hits) + k); h.t = hv.x; h.prim = __float_as_int(hv.y); }
-            const bool hit = valid && h.t < 1e29f;
-            if (valid && !hit) { const float4 rd = __ldcs(curQ.d + k); miss_update(fc.env, wb, (int)f2u(rd.w), mk3(rd.x, rd.y, rd.z)); }   // d.w = path slot
-            const bool spec = hit && depth < fc.maxDepth && hit_is_specular(sc, h.prim);
-            const unsigned mF = __ballot_sync(FULL, hit && !spec), mB = __ballot_sync(FULL, spec);
-            if (mF != 0u) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(&nFront, __popc(mF));
-                b = __shfl_sync(FULL, b, 0);
-                if (hit && !spec) list[b + __popc(mF & ltMask)] = k;
-            }
-            if (mB != 0u) {
-                int b = 0;
-                if (lane == 0) b = atomicAdd(&nBack, __popc(mB));
-                b = __shfl_sync(FULL, b, 0);
-                if (spec) list[RT_SHADE_CHUNK - 1 - (b + __popc(mB & ltMask))] = k;
+        // the primitive-index array is padded to a multiple of the chunk (ensure_frame_buffers), so whole-int4 loads stay in bounds
+        const int4* src = reinterpret_cast<const int4*>(hits.prim + base);
+        int4 pv[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) pv[it] = __ldcs(src + it * 256 + threadIdx.x);
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int k0 = base + (it * 256 + (int)threadIdx.x) * 4;
+            const int pr[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int k = k0 + e;
+                const bool hit = k < n && pr[e] >= 0;
+                const bool spec = hit && depth < fc.maxDepth && hit_is_specular(sc, pr[e]);
+                const unsigned mF = __ballot_sync(FULL, hit && !spec), mB = __ballot_sync(FULL, spec);
+                if (mF != 0u) {
+                    int b = 0;
+                    if (lane == 0) b = atomicAdd(&nFront, __popc(mF));
+                    b = __shfl_sync(FULL, b, 0);
+                    if (hit && !spec) list[b + __popc(mF & ltMask)] = k;
+                }
+                if (mB != 0u) {
+                    int b = 0;
+                    if (lane == 0) b = atomicAdd(&nBack, __popc(mB));
+                    b = __shfl_sync(FULL, b, 0);
+                    if (spec) list[RT_SHADE_CHUNK - 1 - (b + __popc(mB & ltMask))] = k;
+                }
             }
         }
         __syncthreads();
@@ -277,19 +320,10 @@ __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene s
         const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
         for (int i = threadIdx.x; i < rf + nb; i += 256) {
             const bool front = i < rf;
-            if (front ? (i < nf) : true) shade_next<REUSE>(fc, sc, wb, depth, curQ, hits, front ? list[i] : list[RT_SHADE_CHUNK - 1 - (i - rf)], nextQ, nextCount, shq, shCount);
+            if (front ? (i < nf) : true) shade_next<REUSE, FAST>(fc, sc, wb, depth, curQ, hits, front ? list[i] : list[RT_SHADE_CHUNK - 1 - (i - rf)], nextQ, nextCount, shq, shCount);
         }
         __syncthreads();
     }
-}
-
-// connect: add the pending direct-light term of every unoccluded shadow ray to its path (RTRay.cs:526-537, 286/291).
-// A dense, high-occupancy pass over the shadow queue; the read-modify-write of the path state would otherwise sit at the end
-// of each ray inside the persistent any-hit kernel, where the whole warp waits on it.
-__global__ void __launch_bounds__(256) k_connect(WaveBuffers wb, ShadowQueue shq, const int* count) {
-    const int n = *count;
-    const int stride = gridDim.x * blockDim.x;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) connect_shadow(wb, shq, k, !(__ldcs(&shq.c[k].w) != 0.0f));
 }
 
 __global__ void k_accumulate(FrameConst fc, WaveBuffers wb, int sampleBase, int nSamples, int last) {
@@ -429,7 +463,7 @@ struct rt_ctx {
     DevBuf<int> rgba8, objId; DevBuf<float> depth; DevBuf<float4> radiance, accum;
     // per path
     size_t pathCap = 0;
-    DevBuf<float4> stThr, stLi, qO[2], qD[2], qI[2], shO, shD, shI, shC; DevBuf<HitRec> hits; DevBuf<uint32_t> pathHash;
+    DevBuf<float4> stThr, stLi, stC, missD, qO[2], qD[2], shO, shD, hitTuv; DevBuf<int> hitPrim; DevBuf<uint32_t> pathHash;
     // AOV outputs
     DevBuf<uint8_t> segOut, termOut; DevBuf<uint32_t> hashOut;
     // scratch for scattered read-backs
@@ -487,6 +521,18 @@ template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs
     return trace_event(c);
 }
 
+static cudaError_t launch_extend_pair(rt_ctx* c, const ExtendArgs& closest, const ExtendArgs& anyhit, bool count) {
+    ExtendPairArgs a; a.closest = closest; a.anyhit = anyhit; a.closest.stackEntries = a.anyhit.stackEntries = c->stackEntries;
+    cudaError_t e = trace_event(c);
+    if (e != cudaSuccess) return e;
+    if (count) k_extend_pair<true><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
+    else k_extend_pair<false><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
+    c->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return trace_event(c);
+}
+
 // persistent grid of the extend kernels: shared memory for a traversal stack of `entries` per lane, blocks = occupancy x SMs
 static int size_extend_launch(rt_ctx* c, int entries) {
     entries = std::max(2, std::min(entries, RT_STACK_ENTRIES));
@@ -497,9 +543,13 @@ static int size_extend_launch(rt_ctx* c, int entries) {
         CUDA_TRY(cudaFuncSetAttribute(k_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
         CUDA_TRY(cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
         CUDA_TRY(cudaFuncSetAttribute(k_extend<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_extend_pair<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
+        CUDA_TRY(cudaFuncSetAttribute(k_extend_pair<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->extendSmem));
     }
-    int perSm = 0;
+    int perSm = 0, perSmPair = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_extend<false, false>, RT_EXTEND_THREADS, c->extendSmem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSmPair, k_extend_pair<false>, RT_EXTEND_THREADS, c->extendSmem));
+    perSm = std::min(perSm, perSmPair);
     if (perSm < 1) perSm = 1;
     c->extendBlocks = perSm * c->smCount;
     return RT_OK;
@@ -617,8 +667,8 @@ RT_API int rt_destroy(rt_ctx* c) {
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); for (int b = 0; b < 2; b++) { c->tileRadiance[b].release(); c->tileAux[b].release(); c->tileRgba[b].release(); } c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
-    c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); c->qI[b].release(); } c->shO.release(); c->shD.release(); c->shI.release(); c->shC.release();
-    c->hits.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release(); c->deintMap.release();
+    c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); } c->shO.release(); c->shD.release(); c->stC.release(); c->missD.release(); c->hitTuv.release();
+    c->hitPrim.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release(); c->deintMap.release();
     for (auto ev : c->traceEvents) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
     if (c->evStop) cudaEventDestroy(c->evStop);
@@ -777,8 +827,9 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
     const size_t P = std::max<size_t>(1, (size_t)c->npx * S);
     if (P > c->pathCap) {
         CUDA_TRY(c->stThr.ensure(P)); CUDA_TRY(c->stLi.ensure(P));
-        for (int b = 0; b < 2; b++) { CUDA_TRY(c->qO[b].ensure(P)); CUDA_TRY(c->qD[b].ensure(P)); CUDA_TRY(c->qI[b].ensure(P)); }
-        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->shI.ensure(P)); CUDA_TRY(c->shC.ensure(P)); CUDA_TRY(c->hits.ensure(P));
+        for (int b = 0; b < 2; b++) { CUDA_TRY(c->qO[b].ensure(P)); CUDA_TRY(c->qD[b].ensure(P)); }
+        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->stC.ensure(P)); CUDA_TRY(c->missD.ensure(P)); CUDA_TRY(c->hitTuv.ensure(P));
+        CUDA_TRY(c->hitPrim.ensure((P + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK * RT_SHADE_CHUNK));   // padded: k_shade_next scans whole chunks with 128-bit loads
         c->pathCap = P;
     }
     c->aovs = (cfg->flags & RT_FLAG_PATH_AOVS) != 0;
@@ -813,14 +864,14 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     const int64_t npxOwned = count_owned_pixels(cfg->width, cfg->height, cfg->tileSize, cfg->worldSize > 1 ? cfg->rank : 0, cfg->worldSize > 1 ? cfg->worldSize : 1);
     int S = cfg->samplesPerPass;
     if (S <= 0) {
-        // samples per wavefront pass: as many paths in flight as ~60 % of the device memory holds (208 B of path state and queue
+        // samples per wavefront pass: as many paths in flight as ~60 % of the device memory holds (180 B of path state and queue
         // slots each), capped at 768 Mi (path indices are 32-bit).  Bigger passes mean fewer, longer launches: C4 on a 180 GB B200
-        // runs its 64 spp (531 M paths, 110 GB) in ONE pass - 191.2 ms against 193.1 ms in two passes of 32 spp, 197.8 ms in four,
+        // runs its 64 spp (531 M paths, 96 GB) in ONE pass - 191.2 ms against 193.1 ms in two passes of 32 spp, 197.8 ms in four,
         // 230 ms with 16 Mi-path passes (launch tails of the deep, nearly empty wavefronts)
-        int64_t target = std::min<int64_t>(768ll << 20, (int64_t)(c->memTotal / 10 * 6 / 208));
+        int64_t target = std::min<int64_t>(768ll << 20, (int64_t)(c->memTotal / 10 * 6 / RT_PATH_BYTES));
         if ((size_t)target > c->pathCap) {   // the buffers would have to grow: never beyond 85 % of what is free right now (plus what they already hold)
             size_t freeB = 0, totalB = 0;
-            if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) target = std::min<int64_t>(target, (int64_t)((freeB / 100 * 85 + c->pathCap * 208) / 208));
+            if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) target = std::min<int64_t>(target, (int64_t)((freeB / 100 * 85 + c->pathCap * RT_PATH_BYTES) / RT_PATH_BYTES));
             else (void)cudaGetLastError();
         }
         target = std::max<int64_t>(target, 1ll << 20);
@@ -860,6 +911,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         if (P > c->resPathCap) { CUDA_TRY(c->resPath.ensure(3 * P)); c->resPathCap = P; }
     }
     const bool count = (cfg->flags & RT_FLAG_COUNTERS) != 0;
+    const bool fast = (cfg->flags & RT_FLAG_FAST_SHADING) != 0;
     c->timeKernels = (cfg->flags & RT_FLAG_KERNEL_TIMING) != 0;   // per-launch event pairs around the extend kernels (roofline measurements)
     c->traceEventsUsed = 0;
     c->launches = 0;
@@ -902,7 +954,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     WaveBuffers wb; memset(&wb, 0, sizeof(wb));
     wb.gbPosHit = c->gbPosHit.p; wb.gbNrmMat = c->gbNrmMat.p; wb.gbAlbObj = c->gbAlbObj.p; wb.primId = c->primId.p; wb.instId = c->instId.p; wb.primaryT = c->primaryT.p;
     wb.lframe = c->lframe.p; wb.tileRadiance = c->tileRadiance[c->tileBuf].p; wb.tileAux = c->tileAux[c->tileBuf].p; wb.tileRgba = c->tileRgba[c->tileBuf].p; wb.rgba8 = c->rgba8.p; wb.depth = c->depth.p; wb.objId = c->objId.p; wb.radiance = c->radiance.p; wb.accum = c->accum.p;
-    wb.stThr = c->stThr.p; wb.stLi = c->stLi.p;
+    wb.stThr = c->stThr.p; wb.stLi = c->stLi.p; wb.stC = c->stC.p; wb.missD = c->missD.p;
     if (reuse) {
         const size_t g = (size_t)cfg->width * cfg->height, P = c->resPathCap;
         float4* cur = c->resAB[cfg->frame & 1].p;
@@ -915,22 +967,23 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
 
     if (npx > 0) {
         // ---- primary visibility -------------------------------------------------------------------------------------
-        RayQueue q0 = {c->qO[0].p, c->qD[0].p, c->qI[0].p};
+        RayQueue q0 = {c->qO[0].p, c->qD[0].p};
         int* primaryCount = c->counters.p + 0;
         int* primaryWork = c->counters.p + 1;
         k_generate_primary<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, q0, primaryCount); c->launches++;
+        const HitQueue hq = {c->hitPrim.p, c->hitTuv.p};
         ExtendArgs ea; memset(&ea, 0, sizeof(ea));
-        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.rayI = q0.inv; ea.count = primaryCount; ea.work = primaryWork; ea.hits = c->hits.p; ea.wb = wb; ea.stats = c->dstats.p; ea.statSlot = 0;
+        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missD = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
         CUDA_TRY(launch_extend<false>(c, ea, count));
-        k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, c->hits.p); c->launches++;
+        k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, hq); c->launches++;
 
-        ShadowQueue shq = {c->shO.p, c->shD.p, c->shI.p, c->shC.p};
+        ShadowQueue shq = {c->shO.p, c->shD.p};
         // ---- shared sun probe: one any-hit ray per Lambert primary vertex facing the sun, instead of one per sample that selects it
         if (spp >= 2 && cfg->maxDepth >= 1 && !reuse && !c->envNoSunProbe) {
             int* sunCount = c->counters.p + 2;
             k_sun_generate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, shq, sunCount); c->launches++;
             ExtendArgs pa; memset(&pa, 0, sizeof(pa));
-            pa.sc = c->ds; pa.rayO = shq.o; pa.rayD = shq.d; pa.rayI = shq.inv; pa.count = sunCount; pa.work = sunCount + 1; pa.shq = shq; pa.wb = wb; pa.stats = c->dstats.p; pa.statSlot = 3;
+            pa.sc = c->ds; pa.rayO = shq.o; pa.rayD = shq.d; pa.count = sunCount; pa.work = sunCount + 1; pa.stC = c->stC.p; pa.stats = c->dstats.p; pa.statSlot = 3;
             CUDA_TRY(launch_extend<true>(c, pa, count));
             k_sun_store<<<grid_for(c, npx, 256), 256, 0, st>>>(wb, shq, sunCount); c->launches++;
         }
@@ -941,25 +994,30 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             const size_t nPaths = (size_t)npx * ns;
             int* ctr = c->counters.p + CH + (size_t)pass * (cfg->maxDepth + 1) * CS;
             int cur = 0;
-            RayQueue nq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
-            if (reuse) k_shade_first<true><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
-            else k_shade_first<false><<<grid_for(c, nPaths, 256), 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+            RayQueue nq = {c->qO[cur].p, c->qD[cur].p};
+            {
+                const int g1 = grid_for(c, nPaths, 256);
+                if (reuse && fast) k_shade_first<true, true><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                else if (reuse) k_shade_first<true, false><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                else if (fast) k_shade_first<false, true><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                else k_shade_first<false, false><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+            }
             c->launches++;
             for (int depth = 1; depth <= cfg->maxDepth; depth++) {
                 int* prev = ctr + (size_t)(depth - 1) * CS;   // counts produced by the shade of depth-1
                 int* mine = ctr + (size_t)depth * CS;
-                RayQueue cq = {c->qO[cur].p, c->qD[cur].p, c->qI[cur].p};
+                RayQueue cq = {c->qO[cur].p, c->qD[cur].p};
                 ExtendArgs sa; memset(&sa, 0, sizeof(sa));
-                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.rayI = shq.inv; sa.count = prev + 1; sa.work = prev + 3; sa.shq = shq; sa.wb = wb; sa.stats = c->dstats.p; sa.statSlot = 2;
-                CUDA_TRY(launch_extend<true>(c, sa, count));
-                k_connect<<<grid_for(c, nPaths, 256), 256, 0, st>>>(wb, shq, prev + 1); c->launches++;
+                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.count = prev + 1; sa.work = prev + 3; sa.stC = c->stC.p; sa.stats = c->dstats.p; sa.statSlot = 2;
                 ExtendArgs ca; memset(&ca, 0, sizeof(ca));
-                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.rayI = cq.inv; ca.count = prev + 0; ca.work = prev + 2; ca.hits = c->hits.p; ca.wb = wb; ca.stats = c->dstats.p; ca.statSlot = 1;
-                CUDA_TRY(launch_extend<false>(c, ca, count));
-                RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p, c->qI[cur ^ 1].p};
+                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.count = prev + 0; ca.work = prev + 2; ca.hits = hq; ca.missD = c->missD.p; ca.stats = c->dstats.p; ca.statSlot = 1;
+                CUDA_TRY(launch_extend_pair(c, ca, sa, count));   // closest-hit and shadow rays of this depth in ONE persistent launch
+                RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p};
                 const int shadeGrid = grid_for(c, (nPaths + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK, 1);
-                if (reuse) k_shade_next<true><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1);
-                else k_shade_next<false><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, c->hits.p, prev + 0, nq2, mine + 0, shq, mine + 1);
+                if (reuse && fast) k_shade_next<true, true><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
+                else if (reuse) k_shade_next<true, false><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
+                else if (fast) k_shade_next<false, true><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
+                else k_shade_next<false, false><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
                 c->launches++;
                 cur ^= 1;
             }
@@ -1230,8 +1288,14 @@ static NcclApi* nccl_api() {
     static NcclApi api; static bool tried = false;
     if (tried) return api.handle ? &api : nullptr;
     tried = true;
-    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    // 1. RT_NCCL_LIBRARY: an explicit path; 2. the copy ALREADY in the process (a host that ships its own NCCL - PyTorch's wheel does -
+    // must load it before the first rt_comm_* call, or a later load of that host library would find this one under the same soname);
+    // 3. the system's libnccl.so.2
+    void* h = nullptr;
+    if (const char* path = getenv("RT_NCCL_LIBRARY")) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) { api.err = std::string("NCCL is not available: ") + dlerror(); return nullptr; }
     bool ok = true;
     auto sym = [&](const char* name) -> void* { void* p = dlsym(h, name); if (!p) { ok = false; api.err = std::string("NCCL symbol missing: ") + name; } return p; };

@@ -326,6 +326,7 @@ class RTRenderer:
     @staticmethod
     def NewCommunicatorId() -> bytes:
         """Rank 0: the 128-byte id every rank's InitMultiGpu needs (ncclGetUniqueId behind rt_comm_get_unique_id)."""
+        native.preload_host_nccl()
         buf = C.create_string_buffer(L.RT_COMM_ID_BYTES)
         _check(lib().eng_renderer_new_communicator_id(buf))
         return buf.raw
@@ -333,6 +334,7 @@ class RTRenderer:
     def InitMultiGpu(self, unique_id: bytes, rank: int, world_size: int):
         """This renderer = rank `rank` of `world_size` processes (one per GPU): RenderDirectToPbo then renders this rank's screen tiles,
         gathers colour + depth + objectId on rank 0 (NCCL inside the library) and presents there."""
+        native.preload_host_nccl()
         buf = C.create_string_buffer(unique_id, L.RT_COMM_ID_BYTES)
         _check(self._l.eng_renderer_init_multi_gpu(self.h, buf, rank, world_size))
         self.knobs.rank, self.knobs.worldSize = rank, world_size

@@ -168,6 +168,7 @@ class Context:
     # ---- multi-GPU (one process + one context per GPU; the communicator lives in the library) ----
     def comm_init(self, unique_id: bytes, rank: int, world_size: int):
         assert len(unique_id) == L.RT_COMM_ID_BYTES
+        preload_host_nccl()
         buf = C.create_string_buffer(unique_id, L.RT_COMM_ID_BYTES)
         check(self._l.rt_comm_init(self.h, buf, L.RT_COMM_ID_BYTES, rank, world_size))
 
@@ -189,8 +190,32 @@ class Context:
         return d
 
 
+_nccl_preloaded = False
+
+
+def preload_host_nccl() -> None:
+    """A Python host usually carries its own NCCL (the nvidia-nccl wheel PyTorch links against).  The library binds whichever
+    libnccl.so.2 is already in the process, so load the wheel's copy BEFORE the first rt_comm_* call: otherwise the system copy gets
+    in first and a later `import torch` finds that one under the same soname (and may miss symbols of its newer version)."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass   # no wheel copy: the library falls back to the system's libnccl.so.2
+
+
 def comm_unique_id() -> bytes:
     """ncclGetUniqueId through the library (rank 0 makes it; the host distributes the 128 bytes to every rank)."""
+    preload_host_nccl()
     buf = C.create_string_buffer(L.RT_COMM_ID_BYTES)
     check(lib().rt_comm_get_unique_id(buf, L.RT_COMM_ID_BYTES))
     return buf.raw

@@ -175,7 +175,12 @@ enum {
      * nothing, so that switching reuse on at the NEXT frame finds this frame's reservoirs like the reference does.  Frames with a
      * reuse flag set always publish.  Without it a reuse frame whose predecessor (frame - 1) did not publish imports zeros
      * (never stale reservoirs of some older frame). */
-    RT_FLAG_PUBLISH_RESERVOIRS = 1u << 7
+    RT_FLAG_PUBLISH_RESERVOIRS = 1u << 7,
+    /* Tolerance mode (off = bit-exact): the eight sky candidates of ReSTIR_Direct (Engine/RTRay.cs:452-462) are scored with fused
+     * multiply-adds and hardware sin / cos / sqrt / reciprocal.  Nothing in that loop decides the path (every candidate draws exactly
+     * three random numbers; bounce directions, Russian roulette and intersections stay exact): hit ids, bounce counts and terminators
+     * are unchanged, radiance moves by ~1e-6 relative RMS (north_star allows 1e-4). */
+    RT_FLAG_FAST_SHADING = 1u << 8
 };
 
 /* Everything the reference passes in GBufferParams / IntegratorParams

@@ -239,9 +239,10 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
     std::vector<int> primId(npx), instId(npx); std::vector<float> primaryT(npx);
     std::vector<uint32_t> pathHash(P);
     std::vector<float4> radiance((size_t)W * H), accum((size_t)W * H);
-    std::vector<float4> qo[2], qd[2], qi[2], so(P), sd(P), si(P), scv(P);
-    for (int b = 0; b < 2; b++) { qo[b].resize(P); qd[b].resize(P); qi[b].resize(P); }
-    std::vector<HitRec> hits(P);
+    std::vector<float4> qo[2], qd[2], so(P), sd(P), stC(P), missD(P), hitTuv(P);
+    for (int b = 0; b < 2; b++) { qo[b].resize(P); qd[b].resize(P); }
+    std::vector<int> hitPrim(P);
+    const HitQueue hq = {hitPrim.data(), hitTuv.data()};
     std::vector<int32_t> dummyI((size_t)W * H); std::vector<float> dummyF((size_t)W * H);
 
     WaveBuffers wb; memset(&wb, 0, sizeof(wb));
@@ -249,7 +250,7 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
     wb.primId = primId.data(); wb.instId = instId.data(); wb.primaryT = primaryT.data(); wb.lframe = lframe.data(); wb.tileRadiance = tileRad.data();
     wb.rgba8 = out->rgba8 ? out->rgba8 : dummyI.data(); wb.depth = out->depth ? out->depth : dummyF.data(); wb.objId = out->objId ? out->objId : dummyI.data();
     wb.radiance = radiance.data(); wb.accum = out->accum4 ? (float4*)out->accum4 : accum.data();
-    wb.stThr = stThr.data(); wb.stLi = stLi.data();
+    wb.stThr = stThr.data(); wb.stLi = stLi.data(); wb.stC = stC.data(); wb.missD = missD.data();
     const bool aov = (cfg->flags & RT_FLAG_PATH_AOVS) && out->segCount && out->termCode && out->pathHash;
     if (reuse) { wb.resPath0 = rq0.data(); wb.resPath1 = rq1.data(); wb.resPath2 = rq2.data(); wb.resCur0 = rc0.data(); wb.resCur1 = rc1.data(); wb.resCur2 = rc2.data(); }
     if (aov) { wb.pathHash = pathHash.data(); wb.segCountOut = out->segCount; wb.termCodeOut = out->termCode; wb.pathHashOut = out->pathHash; }
@@ -259,34 +260,37 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
     LaneStack st;
 
     // primary visibility
-    RayQueue q0 = {qo[0].data(), qd[0].data(), qi[0].data()};
+    RayQueue q0 = {qo[0].data(), qd[0].data()};
     for (int i = 0; i < npx; i++) generate_primary(fc, q0, i);
-    for (int i = 0; i < npx; i++) { f3 o = mk3(q0.o[i].x, q0.o[i].y, q0.o[i].z), d = mk3(q0.d[i].x, q0.d[i].y, q0.d[i].z); cap_ray(o, d, 0); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[i], &tc); flushCnt(); }
+    for (int i = 0; i < npx; i++) { f3 o = mk3(q0.o[i].x, q0.o[i].y, q0.o[i].z), d = mk3(q0.d[i].x, q0.d[i].y, q0.d[i].z); cap_ray(o, d, 0); HitRec h; trace_wide<false, true>(s->ds, o, d, 1e30f, st, &h, &tc); flushCnt(); store_closest_result(hq, nullptr, i, i, h, d); }
     g_capWave++;
-    for (int i = 0; i < npx; i++) primary_finish(fc, s->ds, wb, q0, hits.data(), i);
+    for (int i = 0; i < npx; i++) primary_finish(fc, s->ds, wb, q0, hq, i);
 
     // integrator, one batch of S samples at a time
-    ShadowQueue shq = {so.data(), sd.data(), si.data(), scv.data()};
+    ShadowQueue shq = {so.data(), sd.data()};
     for (int s0 = 0; s0 < spp; s0 += S) {
         const int ns = (s0 + S <= spp) ? S : (spp - s0);
         int cur = 0; int nNext = 0, nSh = 0;
-        RayQueue nq = {qo[cur].data(), qd[cur].data(), qi[cur].data()};
+        RayQueue nq = {qo[cur].data(), qd[cur].data()};
         for (int j = 0; j < npx * ns; j++) { if (reuse) shade_first<true>(fc, wb, s0, j, nq, &nNext, shq, &nSh); else shade_first<false>(fc, wb, s0, j, nq, &nNext, shq, &nSh); }
         for (int depth = 1; depth <= fc.maxDepth; depth++) {
             for (int k = 0; k < nSh; k++) {
                 f3 o = mk3(shq.o[k].x, shq.o[k].y, shq.o[k].z), d = mk3(shq.d[k].x, shq.d[k].y, shq.d[k].z);
                 cap_ray(o, d, 1);
                 bool occ = trace_wide<true, true>(s->ds, o, d, 1e29f, st, nullptr, &tc); flushCnt();
-                connect_shadow(wb, shq, k, occ);
+                store_anyhit_result(wb.stC, (int)f2u(shq.o[k].w), occ);   // settled at the path's next touch (shade_next / accumulate)
             }
             raysS += (uint64_t)nSh; g_capWave++;
-            RayQueue cq = {qo[cur].data(), qd[cur].data(), qi[cur].data()};
-            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); cap_ray(o, d, 0); trace_wide<false, true>(s->ds, o, d, 1e30f, st, &hits[k], &tc); flushCnt(); }
+            RayQueue cq = {qo[cur].data(), qd[cur].data()};
+            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); cap_ray(o, d, 0); HitRec h; trace_wide<false, true>(s->ds, o, d, 1e30f, st, &h, &tc); flushCnt(); store_closest_result(hq, wb.missD, k, (int)f2u(cq.o[k].w), h, d); }
             g_capWave++;
             raysB += (uint64_t)nNext;
             const int nCur = nNext; nNext = 0; nSh = 0;
-            RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data(), qi[cur ^ 1].data()};
-            for (int k = 0; k < nCur; k++) { if (reuse) shade_next<true>(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh); else shade_next<false>(fc, s->ds, wb, depth, cq, hits.data(), k, nq2, &nNext, shq, &nSh); }
+            RayQueue nq2 = {qo[cur ^ 1].data(), qd[cur ^ 1].data()};
+            for (int k = 0; k < nCur; k++) {   // only rays that hit are shaded; the others are settled by accumulate
+                if (hitPrim[k] < 0) continue;
+                if (reuse) shade_next<true>(fc, s->ds, wb, depth, cq, hq, k, nq2, &nNext, shq, &nSh); else shade_next<false>(fc, s->ds, wb, depth, cq, hq, k, nq2, &nNext, shq, &nSh);
+            }
             cur ^= 1;
         }
         const bool last = (s0 + ns >= spp);
