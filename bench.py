@@ -242,6 +242,138 @@ def fast_shading_leg(ctx, wl: dict, cam, cfg_for, oracle: dict, rays_pb: float) 
             "rel_rms_vs_oracle": rel_rms(rad, r.radiance), "rgba8_px_differ": int((rgba != r.rgba8).sum()), "px": int(prim.size), "tolerance": 1e-4}
 
 
+def run_c0(args, rank: int, local_rank: int):
+    """Workload C0 = the reference's OWN operating point (VERDICT r1 "next" 7): the engine defaults of Engine/RTRenderer.cs:43-49,113-116,204 -
+    a 1280x720 window traced at round(0.67 x) = 858x482, 2 spp, MaxDepth 3, ReSTIR temporal + spatial reuse on, TAAU resolve into the PBO -
+    on the default scene (Scene.BuildDefaultScene), through RTRenderer.RenderDirectToPbo with a camera that moves every frame.  The
+    un-translated camera is used (the reference's default camera looks away from the five small spheres and sees ground + sky only,
+    SURVEY.md section 8a quirk 6).  A step = one displayed frame; value = device-timed with frames submitted back to back
+    (AsyncSubmit), e2e = the reference's per-frame Synchronize() plus the presented image read back to pinned host memory."""
+    import torch
+    from ilgpu_raytracing_b200 import engine, layouts as L
+    OUT_W, OUT_H = 1280, 720
+    if rank != 0:
+        return   # replicas only: reuse frames are not tile-partitioned in this workload
+    torch.cuda.set_device(local_rank)
+    graph = not os.environ.get("RT_BENCH_NO_GRAPH")
+
+    def new_renderer():
+        r = engine.RTRenderer(local_rank, OUT_W, OUT_H)
+        r.configure(renderScale=0.67, enableTAAU=1, enableTemporalReuse=1, enableSpatialReuse=1, spp=2, maxDepth=3, rngLockNoise=1, fixedSeed=1,
+                    flags=(L.RT_FLAG_FRAME_GRAPH if graph else 0))
+        return r
+
+    def camera_at(frame: int):
+        cam = engine.config_camera("C1B", OUT_W, OUT_H)
+        return engine.camera_translate(cam, 0.004 * frame, 0.001 * frame, -0.003 * frame)   # a slow fly-through: the temporal reprojection has work to do
+
+    rdr = new_renderer()
+    ctx = rdr.native
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    pbo = torch.zeros(OUT_W * OUT_H, dtype=torch.int32, device="cuda")
+    host = torch.empty(OUT_W * OUT_H, dtype=torch.int32).pin_memory()
+    frame_no = [0]
+
+    cams = {}
+    pbo_ptr = pbo.data_ptr()
+
+    def step():
+        f = frame_no[0]
+        if f not in cams:
+            cams[f] = camera_at(f)
+        rdr.camera = cams[f]
+        rdr.RenderDirectToPbo(pbo_ptr, OUT_W, OUT_H, f, 0.016)
+        frame_no[0] += 1
+
+    for f in range(args.warmup + 2 * max(args.steps, 200) + 8):
+        cams[f] = camera_at(f)
+
+    rdr.configure(asyncSubmit=1)
+    for _ in range(args.warmup):
+        step()
+    rdr.Synchronize()
+    sampler = ClockSampler(local_rank)
+    if not os.environ.get("RT_BENCH_NO_CLOCKS"):
+        sampler.start()
+    steps = max(args.steps, 200)   # frames of ~0.3 ms: time enough of them for the clock sampler and the event resolution
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            step()
+        ev1.record(stream)
+    rdr.Synchronize()
+    torch.cuda.synchronize()
+    ms_per_step = ev0.elapsed_time(ev1) / steps
+    clocks = sampler.stop()
+    st = ctx.stats()
+    rays_pb = st["raysPrimary"] + st["raysBounce"]
+    launches = st["kernelLaunches"] + 1   # + the present kernel
+    cfg = rdr.last_config()
+    # e2e: per-frame Synchronize() like the reference, plus the displayed image to the host
+    rdr.configure(asyncSubmit=0)
+    ctx.set_stream(None)
+    per = []
+    for i in range(steps + 3):
+        t0 = time.perf_counter()
+        step()
+        with torch.cuda.stream(stream):
+            host.copy_(pbo, non_blocking=True)
+        stream.synchronize()
+        if i >= 3:
+            per.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(per))
+    dev_ms_sync = ctx.stats()["lastRenderMs"]
+    rdr.close()
+
+    # parity: the first frames of the same sequence on a fresh renderer against the oracle (reuse reservoirs ping-pong, TAAU history)
+    parity = None
+    if not args.no_cpu_baseline:
+        from oracle import orc
+        sc = orc.Scene()
+        sc.build_default()
+        r2 = new_renderer()
+        inW, inH = cfg.width, cfg.height
+        res = [np.zeros(inW * inH, orc.RESERVOIR), np.zeros(inW * inH, orc.RESERVOIR)]
+        taa = orc.TaaState(OUT_W, OUT_H)
+        mism = {"rgba8_low": 0, "objid": 0, "presented": 0}
+        prev = None
+        t_cpu = rays_cpu = 0.0
+        for frame in range(4):
+            cam = camera_at(frame)
+            r2.camera = cam
+            r2.RenderDirectToPbo(pbo.data_ptr(), OUT_W, OUT_H, frame, 0.016)
+            low, _, obj = r2.DownloadToCpu()
+            ocam = cam.copy()
+            orc.camera_bake(ocam, inW, inH)
+            ocfg = orc.make_config(inW, inH, spp=2, max_depth=3, frame=frame, rng_lock_noise=1, temporal=1, spatial=1)
+            ref = orc.render(sc, ocam, ocfg, prev_cam=ocam if prev is None else prev, res_prev=res[(frame & 1) ^ 1], res_cur=res[frame & 1], aovs=False)
+            t_cpu += ref.seconds[0] + ref.seconds[1]
+            rays_cpu += ref.counters["raysPrimary"] + ref.counters["raysBounce"]
+            want = taa.resolve(ref.rgba8, ref.objId, inW, inH)
+            mism["rgba8_low"] += int((low != ref.rgba8).sum()); mism["objid"] += int((obj != ref.objId).sum()); mism["presented"] += int((pbo.cpu().numpy() != want).sum())
+            prev = ocam
+        r2.close()
+        parity = {"against": "CPU oracle: 4 frames of the same sequence (ReSTIR reuse ping-pong + TAAU history), traced image, objectId and presented image",
+                  "frames": 4, "px_low": inW * inH, "px_presented": OUT_W * OUT_H, **{k + "_mismatch": v for k, v in mism.items()}, "ok": all(v == 0 for v in mism.values())}
+        cpu = {"value": rays_cpu / t_cpu / 1e6, "unit": "Mrays/s", "cores": orc.lib().orc_hardware_threads(), "kind": "port", "sample": "4 full frames of the sequence (858x482, 2 spp, depth 3, reuse on)",
+               "seconds": t_cpu, "frames_per_s": 4 / t_cpu}
+    else:
+        cpu = None
+    line = {"metric": "Mrays/s (primary+bounce) at the reference's interactive operating point", "value": rays_pb / (ms_per_step * 1e-3) / 1e6, "unit": "Mrays/s", "n_gpus": 1,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C0", "scene": "Scene.BuildDefaultScene", "window": [OUT_W, OUT_H], "traced": [cfg.width, cfg.height], "spp": 2, "max_depth": 3, "reuse": "temporal + spatial",
+                       "present": "TAAU", "camera": "un-translated default camera, moving every frame", "frame_graph": bool(graph),
+                       "l2": "working set (a few MB) is cache resident by nature: this workload is launch / latency bound, not bandwidth bound"},
+            "frames_per_s": 1e3 / ms_per_step, "us_per_frame": ms_per_step * 1e3, "rays_per_step": {"primary_plus_bounce": rays_pb},
+            "clocks": clocks, "gpu_launches": int(launches * steps), "launches_per_frame": int(launches),
+            "e2e": {"value": rays_pb / e2e_s / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * L.CAMERA.itemsize + __import__("ctypes").sizeof(L.RtRenderConfig),
+                    "d2h_bytes_per_step": OUT_W * OUT_H * 4, "ms_per_step": e2e_s * 1e3, "ms_per_step_median": float(np.median(per)) * 1e3, "device_ms_per_frame": dev_ms_sync},
+            "parity": parity, "cpu_baseline": cpu, "roofline": None}
+    print(json.dumps(line))
+
+
 def run_reference(args, wl, name):
     """--impl reference: the CPU restatement of the reference kernels, all host threads, bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -279,11 +411,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C4", choices=sorted(WORKLOADS) + ["C0"])
     ap.add_argument("--spp", type=int, default=0, help="override the workload's spp (debugging; invalidates the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     name = args.workload
+    if name == "C0":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times workload C4 (the headline); C0's CPU figure is in its own cpu_baseline")
+        run_c0(args, int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")))
+        return
     wl = dict(WORKLOADS[name])
     if args.spp:
         wl["spp"] = args.spp

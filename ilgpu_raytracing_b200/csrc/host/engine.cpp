@@ -545,7 +545,7 @@ void RTRenderer::RenderDirectToPbo(void* pboDevicePtr, int width, int height, in
         pc.feedback = 0.075f; pc.sharpness = 0.10f; pc.clampK = 1.25f;   // RTTaa.cs:80-82
         check(rt_present(_native, &pc, pboDevicePtr, pboDevicePtr ? (size_t)outW * outH * 4 : 0));
     }
-    check(rt_sync(_native));                           // _cuda.Synchronize() :233
+    if (!AsyncSubmit) check(rt_sync(_native));         // _cuda.Synchronize() :233 (AsyncSubmit: the caller waits later - Synchronize() - so that frames queue back to back)
     _prevCamera = _camera;                             // :236
 }
 
@@ -621,10 +621,10 @@ ENG_API void eng_renderer_get_camera(RTRenderer* r, RtCamera* out) { memcpy(out,
 ENG_API void eng_renderer_set_camera(RTRenderer* r, const RtCamera* in) { memcpy(static_cast<RtCamera*>(&r->Cam()), in, sizeof(RtCamera)); }
 ENG_API void eng_renderer_set_sun_params(RTRenderer* r, float speed, float elevation) { r->SetSunParams(speed, elevation); }
 // knobs: 0 RenderScale(float bits not used) ... use a struct instead
-struct EngKnobs { float renderScale; int enableTemporalReuse, enableSpatialReuse, rngLockNoise, fixedSeed, spp, maxDepth; unsigned flags; int tileSize, rank, worldSize, samplesPerPass, enableTAAU; };
+struct EngKnobs { float renderScale; int enableTemporalReuse, enableSpatialReuse, rngLockNoise, fixedSeed, spp, maxDepth; unsigned flags; int tileSize, rank, worldSize, samplesPerPass, enableTAAU, asyncSubmit; };
 ENG_API void eng_renderer_set_knobs(RTRenderer* r, const EngKnobs* k) {
     r->RenderScale = k->renderScale; r->EnableTemporalReuse = k->enableTemporalReuse; r->EnableSpatialReuse = k->enableSpatialReuse; r->RngLockNoise = k->rngLockNoise;
-    r->FixedSeed = k->fixedSeed; r->Spp = k->spp; r->MaxDepth = k->maxDepth; r->Flags = k->flags; r->TileSize = k->tileSize; r->Rank = k->rank; r->WorldSize = k->worldSize; r->SamplesPerPass = k->samplesPerPass; r->EnableTAAU = k->enableTAAU != 0;
+    r->FixedSeed = k->fixedSeed; r->Spp = k->spp; r->MaxDepth = k->maxDepth; r->Flags = k->flags; r->TileSize = k->tileSize; r->Rank = k->rank; r->WorldSize = k->worldSize; r->SamplesPerPass = k->samplesPerPass; r->EnableTAAU = k->enableTAAU != 0; r->AsyncSubmit = k->asyncSubmit != 0;
 }
 ENG_API int eng_renderer_new_communicator_id(void* id128) { return guard([&] { RTRenderer::NewCommunicatorId(id128); }); }
 ENG_API int eng_renderer_init_multi_gpu(RTRenderer* r, const void* id128, int rank, int worldSize) { return guard([&] { r->InitMultiGpu(id128, rank, worldSize); }); }

@@ -187,6 +187,7 @@ public:
     int MaxDepth = 3;              // :204
     unsigned Flags = 0;            // RT_FLAG_*
     int TileSize = 32, Rank = 0, WorldSize = 1, SamplesPerPass = 0;
+    bool AsyncSubmit = false;      // true: RenderDirectToPbo returns without the per-frame Synchronize() of :233
     RtRenderConfig LastConfig() const { return _lastCfg; }
 
 private:

@@ -496,8 +496,12 @@ RT_HD Basis orthonormal_basis(f3 n) {
     B.b = cross(n, B.t);
     return B;
 }
+RT_HD f3 hemisphere_cosine_dir(f3 n, const Basis& B, float r1, float r2);
 RT_HD f3 sample_hemisphere_cosine(f3 n, const Basis& B, uint32_t& rng) {   // :586-598
     float r1 = rng_next_f(rng), r2 = rng_next_f(rng);
+    return hemisphere_cosine_dir(n, B, r1, r2);
+}
+RT_HD f3 hemisphere_cosine_dir(f3 n, const Basis& B, float r1, float r2) {   // the arithmetic of :588-597 for given random numbers
     float phi = 2.0f * RTX_PI * r1;
     float cosTheta = sqrtf(1.0f - r2);
     float sinTheta = sqrtf(r2);
@@ -587,6 +591,7 @@ __device__ __forceinline__ void restir_new_candidates_fast(const LightEnv& env, 
     const f3 dsky = mk3(env.skyTop.x - env.skyBottom.x, env.skyTop.y - env.skyBottom.y, env.skyTop.z - env.skyBottom.z);
     const float lumB = __fmaf_rn(aw.x, env.skyBottom.x, __fmaf_rn(aw.y, env.skyBottom.y, aw.z * env.skyBottom.z));
     const float lumD = __fmaf_rn(aw.x, dsky.x, __fmaf_rn(aw.y, dsky.y, aw.z * dsky.z));
+    float selR1 = 0.0f, selR2 = 0.0f; bool selected = false;
 #pragma unroll 2
     for (int i = 0; i < 8; i++) {
         const float r1 = rng_next_f(rng), r2 = rng_next_f(rng);
@@ -604,12 +609,20 @@ __device__ __forceinline__ void restir_new_candidates_fast(const LightEnv& env, 
         // ReservoirUpdate (:394-405)
         const float newSum = r.wSum + s;
         const float acceptP = (newSum > 0.0f) ? s * fast_rcp(newSum) : 0.0f;
-        if (rng_next_f(rng) < acceptP) {
-            r.wi = wi; r.pdf = pdfSel; r.w = s; r.lightId = 1;
-            r.L = mk3(__fmaf_rn(dsky.x, tbg, env.skyBottom.x), __fmaf_rn(dsky.y, tbg, env.skyBottom.y), __fmaf_rn(dsky.z, tbg, env.skyBottom.z));
-        }
+        if (rng_next_f(rng) < acceptP) { selR1 = r1; selR2 = r2; selected = true; }
         r.wSum = newSum;
         r.m = r.m + 1;
+    }
+    if (selected) {
+        // the ONE candidate that won is re-evaluated with the exact arithmetic of restir_new_candidates: its direction (the shadow ray),
+        // pdf, radiance and score are bit-identical to the exact mode's; only wSum (and, at a ~1e-7 chance, which candidate won) is approximate
+        const f3 wi = hemisphere_cosine_dir(n, B, selR1, selR2);
+        const float nl = fmaxf(0.0f, dot(n, wi));
+        const float pdfLocal = fmaxf(RTX_EPS_MIN, cos_hemisphere_pdf(n, wi));
+        const float pdfSel = fmaxf(RTX_EPS_MIN, pdfLocal * mixLocal);
+        const f3 LiLoc = sky_weighted(env, wi);
+        const f3 f_over_p = albedo * LiLoc * ((nl / pdfSel) * RTX_INV_PI);
+        r.wi = wi; r.pdf = pdfSel; r.L = LiLoc; r.w = luminance(f_over_p); r.lightId = 1;
     }
     {   // (2) the directional candidate, exact as in restir_new_candidates (once per vertex)
         f3 wi = normalize(env.dirLightDir);

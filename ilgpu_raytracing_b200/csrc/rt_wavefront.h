@@ -31,7 +31,11 @@ struct FrameConst {
     // ReSTIR reuse of the previous frame's reservoirs (RTRay.cs:475-516); everything below is unused when both flags are 0
     int enableTemporal, enableSpatial;
     f3 prevOrigin, prevRight, prevUp, prevForward; float prevFovY, prevAspect;   // the prevCam fields ReprojectToPrevPixel reads (:342-351)
-    const int* invPixelMap;                       // global pixel index -> owned index (G-buffer lookups at other pixels, :365-372)
+    // G-buffer lookups at OTHER pixels (SpatialCompatible, :365-372): global pixel index -> index into the look* arrays.  One GPU:
+    // the context's own G-buffer, lookBase = 0.  Tile partition: the G-buffers of ALL ranks, exchanged after the primary pass and
+    // concatenated in rank order; this rank's own pixels start at lookBase.
+    const int* invPixelMap;
+    const float4 *lookPosHit, *lookNrmMat, *lookAlbObj; int lookBase;
     const float4 *resPrev0, *resPrev1, *resPrev2; // previous frame's reservoirs per global pixel: L|pdf, wi|w, wSum|m|lightId
 };
 
@@ -84,6 +88,11 @@ RT_HD int queue_alloc(int* counter) {
 #else
     return (*counter)++;
 #endif
+}
+
+RT_HD void write_ray(float4* qo, float4* qd, int k, const RayOD& r, int path) {
+    qo[k] = make_float4(r.o.x, r.o.y, r.o.z, u2f((uint32_t)path));
+    qd[k] = make_float4(r.d.x, r.d.y, r.d.z, u2f((uint32_t)path));
 }
 
 RT_HD void pixel_xy(const FrameConst& fc, int pix, int* x, int* y) { *x = pix % fc.width; *y = pix / fc.width; }   // RTRay.cs:122
@@ -151,9 +160,7 @@ RT_HD void sun_probe_generate(const FrameConst& fc, const WaveBuffers& wb, int i
     const f3 wi = normalize(fc.env.dirLightDir);          // the delta candidate's direction (:467)
     if (!(fmaxf(0.0f, dot(n, wi)) > 0.0f) || !(dot(n, wi) > 0.0f)) return;   // restir_finalize would not trace (:524, :620-621)
     const RayOD s = make_ray_normal_offset(mk3(ph.x, ph.y, ph.z), n, wi);   // Visible() :622
-    const int k = queue_alloc(shCount);
-    shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)i));
-    shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, u2f((uint32_t)i));
+    write_ray(shQ.o, shQ.d, queue_alloc(shCount), s, i);
 }
 // the probe's visibility arrives where every shadow ray's does: stC[slot].w, slot = the owned pixel (shade_first, which runs after
 // this, overwrites stC for the path slots it uses)
@@ -166,6 +173,10 @@ RT_HD void sun_probe_store(const WaveBuffers& wb, const ShadowQueue& shQ, int k)
 
 // ------------------------------------------------------------------------------------------------ shade
 struct PathVertex { f3 pos, nrm, alb, I; int shade; float ior; };
+// The rays a shaded vertex wants queued.  The device kernels collect them per thread and allocate the queue slots once per BLOCK
+// (one atomic per queue per 256 paths: with one per warp the two queue counters were the hottest addresses of the frame);
+// the host simulator and single-vertex callers push them right away (push_vertex_out).
+struct VertexOut { int pushNext, pushShadow; RayOD next, shadow; };
 
 // path flags kept in stLi.w above the parity taps (bits 0-7 segment count, 8-15 terminator)
 enum : uint32_t {
@@ -193,22 +204,22 @@ RT_HD float distance_from_camera(const FrameConst& fc, float4 pos) {   // Integr
     return sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
 }
 // SpatialCompatible (RTRay.cs:363-374): compares the CURRENT frame's G-buffer at the two pixel indices; iA / iB are owned indices
-RT_HD bool spatial_compatible(const FrameConst& fc, const WaveBuffers& wb, int iA, int iB, f3 nA) {
-    const int objA = (int)f2u(wb.gbAlbObj[iA].w), objB = (int)f2u(wb.gbAlbObj[iB].w);
+RT_HD bool spatial_compatible(const FrameConst& fc, const WaveBuffers&, int iA, int iB, f3 nA) {
+    const int objA = (int)f2u(fc.lookAlbObj[iA].w), objB = (int)f2u(fc.lookAlbObj[iB].w);
     if (objA == objB) return true;
-    const float4 nb4 = wb.gbNrmMat[iB];
+    const float4 nb4 = fc.lookNrmMat[iB];
     const f3 nB = normalize(mk3(nb4.x, nb4.y, nb4.z));
     const float ndot = dot(nA, nB);
     if (ndot < 0.85f) return false;
-    const float zA = distance_from_camera(fc, wb.gbPosHit[iA]);
-    const float zB = distance_from_camera(fc, wb.gbPosHit[iB]);
+    const float zA = distance_from_camera(fc, fc.lookPosHit[iA]);
+    const float zB = distance_from_camera(fc, fc.lookPosHit[iB]);
     const float rel = fabsf(zA - zB) / fmaxf(1e-3f, zA);
     return rel < 0.05f;
 }
 // ImportFromPrevReservoir (RTRay.cs:408-435); curOwned = owned index of the path's pixel, prevIdx = global pixel index
 RT_HD void import_from_prev_reservoir(const FrameConst& fc, const WaveBuffers& wb, int prevIdx, int curOwned, f3 n, f3 albedo, uint32_t& rng, Reservoir& r) {
     if (prevIdx < 0 || fc.width * fc.height <= prevIdx) return;
-    if (!spatial_compatible(fc, wb, curOwned, fc.invPixelMap[prevIdx], n)) return;
+    if (!spatial_compatible(fc, wb, curOwned + fc.lookBase, fc.invPixelMap[prevIdx], n)) return;
     const float4 p1 = fc.resPrev1[prevIdx], p2 = fc.resPrev2[prevIdx];   // (plane 0 = L | pdf is not read by the import)
     const int prM = (int)f2u(p2.y), prLight = (int)f2u(p2.z);
     const float prW = p1.w, prWSum = p2.x;
@@ -257,7 +268,7 @@ template <bool REUSE, bool FAST = false>
 // sunFlags: the pixel's GB_SUN_* bits when this is the first vertex of the path and the shared probe applies, else 0;
 // *direct receives "throughput * direct" when the probe answered instead of a shadow ray (else stays 0), *probed counts it.
 RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathVertex& v, int depth, int path, f3& thr, uint32_t& rng, uint32_t& pflags,
-                        const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, uint32_t sunFlags = 0u, f3* direct = nullptr, int* probed = nullptr) {
+                        VertexOut& vo, uint32_t sunFlags = 0u, f3* direct = nullptr, int* probed = nullptr) {
     RayOD ray;
     if (v.shade == RT_SHADING_MIRROR) {   // :235-244
         f3 dirR = reflect3(v.I, v.nrm);
@@ -307,9 +318,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
         } else if (wantShadow) {
             RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
-            int k = queue_alloc(shCount);
-            shQ.o[k] = make_float4(s.o.x, s.o.y, s.o.z, u2f((uint32_t)path));
-            shQ.d[k] = make_float4(s.d.x, s.d.y, s.d.z, u2f((uint32_t)path));
+            vo.pushShadow = 1; vo.shadow = s;
             wb.stC[path] = make_float4(c.x, c.y, c.z, 0.0f);
             pflags |= PATH_PENDING_SHADOW;
         }
@@ -323,11 +332,14 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
             thr = thr * (1.0f / maxC);
         }
     }
-    int k = queue_alloc(nextCount);
-    nextQ.o[k] = make_float4(ray.o.x, ray.o.y, ray.o.z, u2f((uint32_t)path));
-    nextQ.d[k] = make_float4(ray.d.x, ray.d.y, ray.d.z, u2f((uint32_t)path));
+    vo.pushNext = 1; vo.next = ray;
     pflags |= PATH_RAY_IN_FLIGHT;
     return true;
+}
+// immediate push (one slot allocation per call): host simulator, and the fallback of shade_first / shade_next without a VertexOut
+RT_HD void push_vertex_out(const VertexOut& vo, int path, const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+    if (vo.pushShadow) write_ray(shQ.o, shQ.d, queue_alloc(shCount), vo.shadow, path);
+    if (vo.pushNext) write_ray(nextQ.o, nextQ.d, queue_alloc(nextCount), vo.next, path);
 }
 
 // "Li += throughput * direct" when Visible() (RTRay.cs:286,291,526-537) for the shadow ray queued at the path's latest Lambert
@@ -346,7 +358,8 @@ RT_HD uint32_t pack_aov(int seg, int term) { return (uint32_t)(seg & 0xFF) | ((u
 // depth 0: start every path of the batch from the G-buffer (RTRay.cs:210-232)
 template <bool REUSE = false, bool FAST = false>
 RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBase, int j,
-                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, unsigned* probedCount = nullptr) {
+                       const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, unsigned* probedCount = nullptr, VertexOut* defer = nullptr) {
+    if (defer) { defer->pushNext = 0; defer->pushShadow = 0; }
     const int i = j % fc.npx;
     const int s = sampleBase + j / fc.npx;
     int x, y; pixel_xy(fc, fc.pixelMap[i], &x, &y);
@@ -372,7 +385,9 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     // with reuse on, an imported reservoir may carry another frame's sun direction: every sample traces its own ray then
     const uint32_t sunFlags = REUSE ? 0u : (f2u(ph.w) & (GB_SUN_KNOWN | GB_SUN_VISIBLE));
     f3 direct = mk3(0.0f, 0.0f, 0.0f); int probed = 0;
-    bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, 0, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount, sunFlags, &direct, &probed);
+    VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
+    bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, 0, j, thr, rng, pflags, vo, sunFlags, &direct, &probed);
+    if (defer) *defer = vo; else push_vertex_out(vo, j, nextQ, nextCount, shQ, shCount);
     wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
     // a probed shadow ray is settled on the spot, before anything else touches Li: Li = 0 + throughput * direct, and the visibility fold of the path hash
     if (probed != 0 && wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (probed == 2 ? 1u : 0u));
@@ -396,9 +411,11 @@ RT_HD void store_anyhit_result(float4* stC, int slot, bool occluded) { stC[slot]
 template <bool REUSE = false, bool FAST = false>
 RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, int depth,
                       const RayQueue& curQ, const HitQueue& hits, int k,
-                      const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount) {
+                      const RayQueue& nextQ, int* nextCount, const ShadowQueue& shQ, int* shCount, VertexOut* defer = nullptr, int* pathOut = nullptr) {
+    if (defer) { defer->pushNext = 0; defer->pushShadow = 0; }
     const float4 ro = curQ.o[k], rd = curQ.d[k];
     const int j = (int)f2u(ro.w);
+    if (pathOut) *pathOut = j;
     const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
     const HitRec h = load_hit(hits, k);
     const float4 st = wb.stThr[j];
@@ -417,7 +434,9 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
             v.nrm = normalize(s.normal);   // :666
             v.alb = s.albedo; v.shade = s.shade; v.ior = s.ior;
             v.I = d;                        // "I = ray.dir" :243,274,316
-            bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, depth, j, thr, rng, pflags, nextQ, nextCount, shQ, shCount);
+            VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
+            bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, depth, j, thr, rng, pflags, vo);
+            if (defer) *defer = vo; else push_vertex_out(vo, j, nextQ, nextCount, shQ, shCount);
             wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
             wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
             return;

@@ -245,11 +245,48 @@ __global__ void k_sun_store(WaveBuffers wb, ShadowQueue shq, const int* count) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) sun_probe_store(wb, shq, k);
 }
 
+// Queue slots for the rays of a block's 256 vertices: ballot per warp, an 8-entry scan in shared memory, ONE atomic per queue per
+// block (warp-level aggregation left the two queue counters as the hottest addresses of the frame: 33 M same-address atomics).
+// Called by every thread of the block (three barriers).
+__device__ __forceinline__ void block_push(const VertexOut& vo, int path, const RayQueue& nextQ, int* nextCount, const ShadowQueue& shq, int* shCount, int* sm /* 16 ints */) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
+    const unsigned ltMask = (1u << lane) - 1u;
+    const unsigned mN = __ballot_sync(FULL, vo.pushNext != 0), mS = __ballot_sync(FULL, vo.pushShadow != 0);
+    if (lane == 0) { sm[warp] = __popc(mN); sm[8 + warp] = __popc(mS); }
+    __syncthreads();
+    if (warp == 0) {
+        const int cN = lane < 8 ? sm[lane] : 0, cS = lane < 8 ? sm[8 + lane] : 0;
+        int pN = cN, pS = cS;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) { const int a = __shfl_up_sync(FULL, pN, o), b = __shfl_up_sync(FULL, pS, o); if (lane >= o) { pN += a; pS += b; } }
+        int baseN = 0, baseS = 0;
+        if (lane == 7) { if (pN > 0) baseN = atomicAdd(nextCount, pN); if (pS > 0) baseS = atomicAdd(shCount, pS); }
+        baseN = __shfl_sync(FULL, baseN, 7); baseS = __shfl_sync(FULL, baseS, 7);
+        if (lane < 8) { sm[lane] = baseN + pN - cN; sm[8 + lane] = baseS + pS - cS; }
+    }
+    __syncthreads();
+    if (vo.pushNext) write_ray(nextQ.o, nextQ.d, sm[warp] + __popc(mN & ltMask), vo.next, path);
+    if (vo.pushShadow) write_ray(shq.o, shq.d, sm[8 + warp] + __popc(mS & ltMask), vo.shadow, path);
+    __syncthreads();
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
 template <bool REUSE, bool FAST>
 __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, DeviceStats* stats) {
-    const int stride = gridDim.x * blockDim.x;
+    __shared__ int smPush[16];
     unsigned probed = 0;
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nPaths; j += stride) shade_first<REUSE, FAST>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed);
+    for (long long base = (long long)blockIdx.x * 256; base < nPaths; base += (long long)gridDim.x * 256) {
+        const int j = (int)(base + threadIdx.x);
+        {   // the next iteration's G-buffer lines towards L2 while this one computes (one lane per 128-byte line)
+            const long long jn = base + (long long)gridDim.x * 256 + threadIdx.x;
+            if (jn < nPaths && (threadIdx.x & 7u) == 0u) { const int in = (int)(jn % fc.npx); prefetch_l2(wb.gbPosHit + in); prefetch_l2(wb.gbNrmMat + in); prefetch_l2(wb.gbAlbObj + in); }
+        }
+        VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
+        if (j < nPaths) shade_first<REUSE, FAST>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed, &vo);
+        block_push(vo, j, nextQ, nextCount, shq, shCount, smPush);
+    }
     for (int o = 16; o > 0; o >>= 1) probed += __shfl_xor_sync(0xFFFFFFFFu, probed, o);
     if ((threadIdx.x & 31u) == 0u && probed != 0u) atomicAdd(&stats->shadowProbed, (unsigned long long)probed);
 }
@@ -272,10 +309,11 @@ __device__ __forceinline__ bool hit_is_specular(const DeviceScene& sc, int prim)
     return shade == RT_SHADING_MIRROR || shade == RT_SHADING_GLASS;
 }
 template <bool REUSE, bool FAST>
-__global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
+__global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
     __shared__ int list[RT_SHADE_CHUNK];
     __shared__ int nFront, nBack;
+    __shared__ int smPush[16];
     const int n = *curCount;
     const int nChunks = (n + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -318,9 +356,22 @@ __global__ void __launch_bounds__(256) k_shade_next(FrameConst fc, DeviceScene s
         __syncthreads();
         const int nf = nFront, nb = nBack;
         const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
-        for (int i = threadIdx.x; i < rf + nb; i += 256) {
-            const bool front = i < rf;
-            if (front ? (i < nf) : true) shade_next<REUSE, FAST>(fc, sc, wb, depth, curQ, hits, front ? list[i] : list[RT_SHADE_CHUNK - 1 - (i - rf)], nextQ, nextCount, shq, shCount);
+        // a hit's record chain is ray / hit record -> path slot -> path state -> primitive -> material: several dependent DRAM / L2
+        // round trips per vertex with only 32 warps per SM to hide them.  So each iteration pulls the records of the hit two
+        // iterations ahead towards L2, reads the slot / primitive words of the hit one ahead (their lines arrived by then) and,
+        // after shading, pulls that hit's path state and primitive record.
+        auto entry = [&](int i) -> int { return i < rf ? (i < nf ? list[i] : -1) : (i < rf + nb ? list[RT_SHADE_CHUNK - 1 - (i - rf)] : -1); };
+        for (int i0 = 0; i0 < rf + nb; i0 += 256) {   // uniform trip count: block_push has barriers
+            const int i = i0 + (int)threadIdx.x;
+            const int k = entry(i), k1 = entry(i + 256), k2 = entry(i + 512);
+            if (k2 >= 0) { prefetch_l2(curQ.o + k2); prefetch_l2(curQ.d + k2); prefetch_l2(hits.tuv + k2); }
+            int slot1 = -1, prim1 = -1;
+            if (k1 >= 0) { slot1 = __float_as_int(__ldg(&curQ.o[k1].w)); prim1 = __ldg(hits.prim + k1); }
+            VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
+            int path = 0;
+            if (k >= 0) shade_next<REUSE, FAST>(fc, sc, wb, depth, curQ, hits, k, nextQ, nextCount, shq, shCount, &vo, &path);
+            if (k1 >= 0) { prefetch_l2(wb.stThr + slot1); prefetch_l2(wb.stLi + slot1); prefetch_l2(wb.stC + slot1); prefetch_l2(sc.prims + prim1); }
+            if (depth < fc.maxDepth) block_push(vo, path, nextQ, nextCount, shq, shCount, smPush);   // the last depth queues nothing
         }
         __syncthreads();
     }
@@ -398,6 +449,24 @@ __global__ void __launch_bounds__(256) k_gather_scatter(const float4* rad, const
         if (rad) { const float4 v = __ldcs(rad + i); outRadiance[p] = v; outRgba8[p] = pack_rgba8(mk3(v.x, v.y, v.z)); }
         else if (rgba) outRgba8[p] = __ldcs(rgba + i);
         if (aux) { const uint2 a = __ldcs(aux + i); outDepth[p] = __uint_as_float(a.x); outObjId[p] = (int)a.y; }
+    }
+}
+
+// ReSTIR reuse across a tile partition: this rank's reservoirs (global pixel order) -> its segment of the exchange buffer
+// (owned-pixel lists of all ranks concatenated in rank order), and the other ranks' segments back into global pixel order.
+__global__ void k_res_pack(const float4* cur, size_t g, const int* pixelMap, int npx, size_t start, float4* pack) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npx; i += stride) {
+        const size_t p = (size_t)pixelMap[i], q = start + (size_t)i;
+        pack[q] = cur[p]; pack[g + q] = cur[g + p]; pack[2 * g + q] = cur[2 * g + p];
+    }
+}
+__global__ void k_res_unpack(const float4* pack, size_t g, const int* allMap, size_t ownStart, size_t ownEnd, float4* cur) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < g; q += stride) {
+        if (q >= ownStart && q < ownEnd) continue;
+        const size_t p = (size_t)allMap[q];
+        cur[p] = pack[q]; cur[g + p] = pack[g + q]; cur[2 * g + p] = pack[2 * g + q];
     }
 }
 
@@ -489,6 +558,10 @@ struct rt_ctx {
     bool gatherPending[2] = {false, false}, gatherTimed = false;
     DevBuf<unsigned char> gatherStage; DevBuf<int> gRgba8, gObjId; DevBuf<float> gDepth; DevBuf<float4> gRadiance;
     bool gatheredValid = false; uint32_t gatheredWhat = 0; int gatheredW = 0, gatheredH = 0;
+    // ReSTIR reuse across the partition: every rank's G-buffer (exchanged after the primary pass) and the reservoir exchange buffer
+    DevBuf<float4> gbAll, resPack; std::vector<int> deintHost;
+    const float4 *gbPosPtr = nullptr, *gbNrmPtr = nullptr, *gbAlbPtr = nullptr;   // where the last frame's (own) G-buffer lives
+    cudaGraphExec_t frameGraphExec = nullptr; unsigned long long frameGraphBuilds = 0;   // RT_FLAG_FRAME_GRAPH
     bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envLbvhLeaf = 0;   // developer knobs, read once in rt_create
 };
 
@@ -611,7 +684,69 @@ static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, DevBuf<WideNode
     return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------ multi-GPU behind the ABI
+// NCCL is loaded at run time ("libnccl.so.2": the copy already in the process when the host brought one - e.g. PyTorch's - else
+// the system's), so the library has no link-time dependency and a single-GPU host never touches it.
+struct NcclApi {
+    void* handle = nullptr; std::string err;
+    decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr; decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclSend) Send = nullptr; decltype(&ncclRecv) Recv = nullptr; decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclAllGather) AllGather = nullptr; decltype(&ncclGetErrorString) GetErrorString = nullptr; decltype(&ncclGetVersion) GetVersion = nullptr;
+};
+static NcclApi* nccl_api() {
+    static NcclApi api; static bool tried = false;
+    if (tried) return api.handle ? &api : nullptr;
+    tried = true;
+    // 1. RT_NCCL_LIBRARY: an explicit path; 2. the copy ALREADY in the process (a host that ships its own NCCL - PyTorch's wheel does -
+    // must load it before the first rt_comm_* call, or a later load of that host library would find this one under the same soname);
+    // 3. the system's libnccl.so.2
+    void* h = nullptr;
+    if (const char* path = getenv("RT_NCCL_LIBRARY")) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { api.err = std::string("NCCL is not available: ") + dlerror(); return nullptr; }
+    bool ok = true;
+    auto sym = [&](const char* name) -> void* { void* p = dlsym(h, name); if (!p) { ok = false; api.err = std::string("NCCL symbol missing: ") + name; } return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId"); api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy"); api.Send = (decltype(api.Send))sym("ncclSend"); api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart"); api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather"); api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
+    if (!ok) return nullptr;
+    api.handle = h;
+    return &api;
+}
+static const char* nccl_err() { static NcclApi dummy; NcclApi* a = nccl_api(); (void)dummy; return a ? "" : "NCCL is not available (libnccl.so.2 could not be loaded)"; }
+#define NCCL_TRY(expr)                                                                                                  \
+    do {                                                                                                                \
+        ncclResult_t _r = (expr);                                                                                       \
+        if (_r != ncclSuccess) return fail(RT_ERR_NCCL, std::string(#expr) + ": " + nc->GetErrorString(_r));            \
+    } while (0)
+
+// "all-gather" of arrays laid out like the concatenated owned-pixel lists (rank r owns [deintStart[r], deintStart[r + 1])): every
+// rank sends its own segment of every array to every other rank and receives theirs in place (exact counts; grouped send / recv,
+// because the segments differ in length by a tile or two).  On the context's render stream: the kernels that follow need the data.
+static int exchange_segments(rt_ctx* c, float4* const* arrays, int nArrays) {
+    NcclApi* nc = nccl_api();
+    if (!nc) return fail(RT_ERR_UNSUPPORTED, nccl_err());
+    const int world = c->commWorld, me = c->commRank;
+    const size_t myStart = (size_t)c->deintStart[(size_t)me], myN = (size_t)(c->deintStart[(size_t)me + 1] - c->deintStart[(size_t)me]);
+    NCCL_TRY(nc->GroupStart());
+    for (int r = 0; r < world; r++) {
+        if (r == me) continue;
+        const size_t rStart = (size_t)c->deintStart[(size_t)r], rN = (size_t)(c->deintStart[(size_t)r + 1] - c->deintStart[(size_t)r]);
+        for (int a = 0; a < nArrays; a++) {
+            if (myN) NCCL_TRY(nc->Send(arrays[a] + myStart, myN * 4, ncclFloat, r, c->comm, c->stream));
+            if (rN) NCCL_TRY(nc->Recv(arrays[a] + rStart, rN * 4, ncclFloat, r, c->comm, c->stream));
+        }
+    }
+    NCCL_TRY(nc->GroupEnd());
+    return RT_OK;
+}
+
 extern "C" {
+static int ensure_deint_map(rt_ctx* c, int width, int height, int T, int worldSize);   // defined further down, inside the extern "C" block
 
 RT_API int rt_abi_version(void) { return RT_ABI_VERSION; }
 RT_API const char* rt_last_error(void) { return g_lastError.c_str(); }
@@ -663,6 +798,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     rt_comm_destroy(c);
+    if (c->frameGraphExec) { cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr; }
     c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); for (int b = 0; b < 2; b++) { c->tileRadiance[b].release(); c->tileAux[b].release(); c->tileRgba[b].release(); } c->primId.release(); c->instId.release(); c->primaryT.release();
@@ -852,9 +988,13 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     // The reference publishes on EVERY frame; here a frame without imports publishes only on request (RT_FLAG_PUBLISH_RESERVOIRS:
     // 48 B per path of extra traffic), and a reuse frame whose previous-frame buffer was not written by frame - 1 imports zeros.
     const bool reuse = cfg->enableTemporalReuse != 0 || cfg->enableSpatialReuse != 0 || (cfg->flags & RT_FLAG_PUBLISH_RESERVOIRS) != 0;
-    if (reuse && cfg->worldSize > 1)
-        return fail(RT_ERR_UNSUPPORTED, "rt_render: ReSTIR temporal/spatial reuse reads the previous frame's reservoirs of neighbouring and reprojected pixels, "
-                                        "which a screen-tile partition does not hold; render reuse frames with worldSize = 1");
+    // Reuse reads the previous frame's reservoirs and the current G-buffer of neighbouring / reprojected pixels (RTRay.cs:363-374,
+    // 408-435, 476-516), which a screen-tile partition does not hold: with the library's communicator the ranks exchange both
+    // (G-buffer after the primary pass, reservoirs after accumulate); without one the frame cannot be rendered.
+    const bool reuseDist = reuse && cfg->worldSize > 1;
+    if (reuseDist && !(c->comm && c->commWorld == cfg->worldSize && c->commRank == cfg->rank))
+        return fail(RT_ERR_UNSUPPORTED, "rt_render: ReSTIR temporal/spatial reuse across a screen-tile partition needs the previous frame's reservoirs and the current "
+                                        "G-buffer of other ranks' pixels: call rt_comm_init with this rank / worldSize first (or render reuse frames with worldSize = 1)");
     if (cfg->enableTemporalReuse != 0 && !prevCam) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: enableTemporalReuse needs prevCam");
     if (c->extColor && c->extColorBytes < (size_t)cfg->width * cfg->height * sizeof(int))   // Framebuffer.GetGpuWithExternalColor's guard (Framebuffer.cs:117), before anything is queued
         return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: mapped external colour buffer is smaller than the image");
@@ -890,8 +1030,15 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     } else c->tileBuf = 0;
     if (reuse) {
         const size_t g = (size_t)cfg->width * cfg->height;
+        if (reuseDist) {
+            const int rcMap = ensure_deint_map(c, cfg->width, cfg->height, c->tileSize, cfg->worldSize);
+            if (rcMap != RT_OK) return rcMap;
+            CUDA_TRY(c->gbAll.ensure(3 * g)); CUDA_TRY(c->resPack.ensure(3 * g));
+        }
         if (!c->invPixelMap.p) {
-            std::vector<int> pm, inv(g, 0); build_pixel_map(cfg->width, cfg->height, c->tileSize, 0, 1, pm);
+            std::vector<int> pm, inv(g, 0);
+            if (reuseDist) pm = c->deintHost;   // all ranks' owned-pixel lists concatenated: index = position in the exchanged arrays
+            else build_pixel_map(cfg->width, cfg->height, c->tileSize, 0, 1, pm);
             for (size_t i = 0; i < pm.size(); i++) inv[(size_t)pm[i]] = (int)i;
             CUDA_TRY(c->invPixelMap.ensure(g));
             CUDA_TRY(cudaMemcpyAsync(c->invPixelMap.p, inv.data(), g * sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -932,7 +1079,14 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
         c->l2WindowStream = st;
     }
+    // RT_FLAG_FRAME_GRAPH: the frame's launch sequence is static for a configuration (queue sizes live on the device), so it is
+    // captured into a CUDA graph; the first frame instantiates it, later frames refresh the node parameters (camera, frame index,
+    // buffer parity) with cudaGraphExecUpdate and replay it with ONE launch - the per-launch gaps of small, launch-bound frames go.
+    // Not with per-launch timing, the phase statistics build or NCCL exchanges inside the frame.
+    const bool useGraph = (cfg->flags & RT_FLAG_FRAME_GRAPH) != 0 && !c->timeKernels && !reuseDist && !RT_PHASE_STATS;
     CUDA_TRY(cudaEventRecord(c->evStart, st));
+    if (useGraph) CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rcFrame = [&]() -> int {
     CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, nCounters * sizeof(int), st));
     CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, sizeof(DeviceStats), st));
 
@@ -964,8 +1118,16 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         c->resValid[cfg->frame & 1] = true; c->resFrame[cfg->frame & 1] = cfg->frame;
     }
     if (c->aovs) { wb.pathHash = c->pathHash.p; wb.segCountOut = c->segOut.p; wb.termCodeOut = c->termOut.p; wb.pathHashOut = c->hashOut.p; }
+    size_t ownStart = 0;
+    if (reuseDist) {   // the own G-buffer IS this rank's segment of the exchanged arrays: no copy on either side of the exchange
+        const size_t g = (size_t)cfg->width * cfg->height;
+        ownStart = (size_t)c->deintStart[(size_t)cfg->rank];
+        wb.gbPosHit = c->gbAll.p + ownStart; wb.gbNrmMat = c->gbAll.p + g + ownStart; wb.gbAlbObj = c->gbAll.p + 2 * g + ownStart;
+        fc.lookPosHit = c->gbAll.p; fc.lookNrmMat = c->gbAll.p + g; fc.lookAlbObj = c->gbAll.p + 2 * g; fc.lookBase = (int)ownStart;
+    } else { fc.lookPosHit = wb.gbPosHit; fc.lookNrmMat = wb.gbNrmMat; fc.lookAlbObj = wb.gbAlbObj; fc.lookBase = 0; }
+    c->gbPosPtr = wb.gbPosHit; c->gbNrmPtr = wb.gbNrmMat; c->gbAlbPtr = wb.gbAlbObj;
 
-    if (npx > 0) {
+    if (npx > 0 || reuseDist) {
         // ---- primary visibility -------------------------------------------------------------------------------------
         RayQueue q0 = {c->qO[0].p, c->qD[0].p};
         int* primaryCount = c->counters.p + 0;
@@ -976,6 +1138,12 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missD = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
         CUDA_TRY(launch_extend<false>(c, ea, count));
         k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, hq); c->launches++;
+        if (reuseDist) {   // every rank's G-buffer segment to every other rank (SpatialCompatible compares the CURRENT frame's G-buffer at both pixels)
+            const size_t g = (size_t)cfg->width * cfg->height;
+            float4* arrays[3] = {c->gbAll.p, c->gbAll.p + g, c->gbAll.p + 2 * g};
+            const int rcx = exchange_segments(c, arrays, 3);
+            if (rcx != RT_OK) return rcx;
+        }
 
         ShadowQueue shq = {c->shO.p, c->shD.p};
         // ---- shared sun probe: one any-hit ray per Lambert primary vertex facing the sun, instead of one per sample that selects it
@@ -1023,13 +1191,45 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             }
             k_accumulate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
         }
+        if (reuseDist) {   // this frame's reservoirs of every rank's pixels to every rank: next frame's imports read any pixel's
+            const size_t g = (size_t)cfg->width * cfg->height;
+            float4* cur = c->resAB[cfg->frame & 1].p;
+            k_res_pack<<<grid_for(c, npx, 256), 256, 0, st>>>(cur, g, c->pixelMap.p, npx, ownStart, c->resPack.p); c->launches++;
+            float4* arrays[3] = {c->resPack.p, c->resPack.p + g, c->resPack.p + 2 * g};
+            const int rcx = exchange_segments(c, arrays, 3);
+            if (rcx != RT_OK) return rcx;
+            k_res_unpack<<<grid_for(c, g, 256), 256, 0, st>>>(c->resPack.p, g, c->deintMap.p, ownStart, ownStart + (size_t)npx, cur); c->launches++;
+        }
         if (c->extColor) {
             k_copy_color<<<grid_for(c, npx, 256), 256, 0, st>>>(c->rgba8.p, c->extColor, c->pixelMap.p, npx); c->launches++;
         }
     }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(c->evStop, st));
     CUDA_TRY(cudaMemcpyAsync(c->hstats, c->dstats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
+    return RT_OK;
+    }();
+    if (useGraph) {
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ec = cudaStreamEndCapture(st, &graph);   // always: a failed enqueue must not leave the stream capturing
+        if (rcFrame != RT_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return rcFrame; }
+        if (ec != cudaSuccess || !graph) return fail(RT_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ec));
+        bool fresh = c->frameGraphExec == nullptr;
+        if (!fresh) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(c->frameGraphExec, graph, &info) != cudaSuccess) {   // another configuration (topology changed): instantiate anew
+                (void)cudaGetLastError();
+                cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr; fresh = true;
+            }
+        }
+        if (fresh) {
+            const cudaError_t ei = cudaGraphInstantiate(&c->frameGraphExec, graph, 0);
+            if (ei != cudaSuccess) { cudaGraphDestroy(graph); c->frameGraphExec = nullptr; return fail(RT_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+            c->frameGraphBuilds++;
+        }
+        cudaGraphDestroy(graph);
+        CUDA_TRY(cudaGraphLaunch(c->frameGraphExec, st));
+    } else if (rcFrame != RT_OK) return rcFrame;
+    CUDA_TRY(cudaEventRecord(c->evStop, st));
 #if RT_PHASE_STATS
     if (count) {
         unsigned long long h[32], z[32] = {0};
@@ -1171,10 +1371,10 @@ static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wai
         case RT_BUF_PRIM_ID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<int><<<grid_for(c, npx, 256), 256, 0, st>>>(c->primId.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
         case RT_BUF_INST_ID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<int><<<grid_for(c, npx, 256), 256, 0, st>>>(c->instId.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
         case RT_BUF_PRIMARY_T: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter<float><<<grid_for(c, npx, 256), 256, 0, st>>>(c->primaryT.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
-        case RT_BUF_GB_WORLDPOS: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbPosHit.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
-        case RT_BUF_GB_NORMAL: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbNrmMat.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
-        case RT_BUF_GB_BASECOLOR: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbAlbObj.p, c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
-        case RT_BUF_GB_MATID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter_f4_w<<<grid_for(c, npx, 256), 256, 0, st>>>(c->gbNrmMat.p, (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_WORLDPOS: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(const_cast<float4*>(c->gbPosPtr), c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_NORMAL: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(const_cast<float4*>(c->gbNrmPtr), c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_BASECOLOR: CUDA_TRY(scatterPrep(g * 3)); if (npx) k_scatter_f4_to_f3<<<grid_for(c, npx, 256), 256, 0, st>>>(const_cast<float4*>(c->gbAlbPtr), c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
+        case RT_BUF_GB_MATID: CUDA_TRY(scatterPrep(g)); if (npx) k_scatter_f4_w<<<grid_for(c, npx, 256), 256, 0, st>>>(const_cast<float4*>(c->gbNrmPtr), (int*)c->scratch.p, c->pixelMap.p, npx); src = c->scratch.p; break;
         default: return fail(RT_ERR_INVALID_ARGUMENT, "rt_download: unknown buffer selector");
     }
     CUDA_TRY(cudaGetLastError());
@@ -1251,6 +1451,7 @@ static int ensure_deint_map(rt_ctx* c, int width, int height, int T, int worldSi
         CUDA_TRY(cudaMemcpyAsync(c->deintMap.p, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         c->deintW = width; c->deintH = height; c->deintT = T; c->deintWorld = worldSize;
+        c->deintHost.swap(all);
     }
     return RT_OK;
 }
@@ -1275,46 +1476,7 @@ RT_API int rt_deinterleave_tiles(rt_ctx* c, const void* gatheredDev, const int64
 
 }   // extern "C"
 
-// ------------------------------------------------------------------------------------------------ multi-GPU behind the ABI
-// NCCL is loaded at run time ("libnccl.so.2": the copy already in the process when the host brought one - e.g. PyTorch's - else
-// the system's), so the library has no link-time dependency and a single-GPU host never touches it.
-struct NcclApi {
-    void* handle = nullptr; std::string err;
-    decltype(&ncclGetUniqueId) GetUniqueId = nullptr; decltype(&ncclCommInitRank) CommInitRank = nullptr; decltype(&ncclCommDestroy) CommDestroy = nullptr;
-    decltype(&ncclSend) Send = nullptr; decltype(&ncclRecv) Recv = nullptr; decltype(&ncclGroupStart) GroupStart = nullptr; decltype(&ncclGroupEnd) GroupEnd = nullptr;
-    decltype(&ncclAllGather) AllGather = nullptr; decltype(&ncclGetErrorString) GetErrorString = nullptr; decltype(&ncclGetVersion) GetVersion = nullptr;
-};
-static NcclApi* nccl_api() {
-    static NcclApi api; static bool tried = false;
-    if (tried) return api.handle ? &api : nullptr;
-    tried = true;
-    // 1. RT_NCCL_LIBRARY: an explicit path; 2. the copy ALREADY in the process (a host that ships its own NCCL - PyTorch's wheel does -
-    // must load it before the first rt_comm_* call, or a later load of that host library would find this one under the same soname);
-    // 3. the system's libnccl.so.2
-    void* h = nullptr;
-    if (const char* path = getenv("RT_NCCL_LIBRARY")) h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
-    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
-    if (!h) { api.err = std::string("NCCL is not available: ") + dlerror(); return nullptr; }
-    bool ok = true;
-    auto sym = [&](const char* name) -> void* { void* p = dlsym(h, name); if (!p) { ok = false; api.err = std::string("NCCL symbol missing: ") + name; } return p; };
-    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId"); api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
-    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy"); api.Send = (decltype(api.Send))sym("ncclSend"); api.Recv = (decltype(api.Recv))sym("ncclRecv");
-    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart"); api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
-    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather"); api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-    api.GetVersion = (decltype(api.GetVersion))sym("ncclGetVersion");
-    if (!ok) return nullptr;
-    api.handle = h;
-    return &api;
-}
-static const char* nccl_err() { static NcclApi dummy; NcclApi* a = nccl_api(); (void)dummy; return a ? "" : "NCCL is not available (libnccl.so.2 could not be loaded)"; }
-#define NCCL_TRY(expr)                                                                                                  \
-    do {                                                                                                                \
-        ncclResult_t _r = (expr);                                                                                       \
-        if (_r != ncclSuccess) return fail(RT_ERR_NCCL, std::string(#expr) + ": " + nc->GetErrorString(_r));            \
-    } while (0)
-
+// ------------------------------------------------------------------------------------------------ multi-GPU behind the ABI (entry points)
 extern "C" {
 
 RT_API int rt_comm_get_unique_id(void* id, size_t bytes) {
@@ -1475,6 +1637,89 @@ RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
         float gm = 0.0f;
         if (cudaEventElapsedTime(&gm, c->evGatherStart, c->evGatherStop) == cudaSuccess) out->reserved[3] = (uint64_t)(gm * 1000.0f);
     }
+    return RT_OK;
+}
+
+}   // extern "C"
+
+// ------------------------------------------------------------------------------------------------ CUDA-GL interop (present target)
+// Replaces the reference's own driver-API binding (Engine/CudaGlInteropIndexBuffer.cs:18-34: DllImport "nvcuda" of
+// cuGraphicsGLRegisterBuffer / MapResources / GetMappedPointer_v2 / UnmapResources / UnregisterResource) and the register / map /
+// unmap logic of the PBO class (:44-60, :62-99): the host keeps creating the GL PixelUnpackBuffer (GL.GenBuffer / BufferData stay in
+// C#) and hands its name over; map / unmap run on the CONTEXT's stream, so rt_present into the mapped pointer is ordered between them.
+// The five entry points come from the driver library already in the process (libcuda.so.1), resolved at first use.
+struct GlInteropApi {
+    bool ok = false; std::string err;
+    int (*Register)(void**, unsigned, unsigned) = nullptr; int (*Unregister)(void*) = nullptr;
+    int (*Map)(unsigned, void**, void*) = nullptr; int (*Unmap)(unsigned, void**, void*) = nullptr;
+    int (*GetPtr)(unsigned long long*, size_t*, void*) = nullptr; int (*ErrName)(int, const char**) = nullptr;
+};
+static GlInteropApi* gl_api() {
+    static GlInteropApi api; static bool tried = false;
+    if (tried) return api.ok ? &api : nullptr;
+    tried = true;
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_NOLOAD);
+    if (!h) h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!h) { api.err = std::string("CUDA driver library not found: ") + dlerror(); return nullptr; }
+    bool ok = true;
+    auto sym = [&](const char* n) -> void* { void* p = dlsym(h, n); if (!p) { ok = false; api.err = std::string("driver symbol missing: ") + n; } return p; };
+    api.Register = (decltype(api.Register))sym("cuGraphicsGLRegisterBuffer"); api.Unregister = (decltype(api.Unregister))sym("cuGraphicsUnregisterResource");
+    api.Map = (decltype(api.Map))sym("cuGraphicsMapResources"); api.Unmap = (decltype(api.Unmap))sym("cuGraphicsUnmapResources");
+    api.GetPtr = (decltype(api.GetPtr))sym("cuGraphicsResourceGetMappedPointer_v2"); api.ErrName = (decltype(api.ErrName))sym("cuGetErrorName");
+    api.ok = ok;
+    return ok ? &api : nullptr;
+}
+static int gl_fail(GlInteropApi* g, const char* what, int cuErr) {
+    const char* name = nullptr;
+    if (g->ErrName) g->ErrName(cuErr, &name);
+    return fail(RT_ERR_CUDA, std::string(what) + ": " + (name ? name : "CUDA driver error") + " (" + std::to_string(cuErr) + ")");
+}
+
+extern "C" {
+
+RT_API int rt_gl_register_buffer(rt_ctx* c, unsigned int glBuffer, void** resource) {
+    if (!c || !resource) return fail(RT_ERR_INVALID_ARGUMENT, "rt_gl_register_buffer: null argument");
+    *resource = nullptr;
+    GlInteropApi* g = gl_api();
+    if (!g) return fail(RT_ERR_UNSUPPORTED, "rt_gl_register_buffer: the CUDA driver's GL interop entry points are not available");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaFree(nullptr));   // the driver calls below need this device's primary context current on the calling (GL) thread
+    const int e = g->Register(resource, glBuffer, 2u /* CU_GRAPHICS_REGISTER_FLAGS_WRITE_DISCARD, CudaGlInteropIndexBuffer.cs:55-56 */);
+    if (e != 0) { *resource = nullptr; return gl_fail(g, "cuGraphicsGLRegisterBuffer (is a GL context current on this thread, on this GPU?)", e); }
+    return RT_OK;
+}
+RT_API int rt_gl_map(rt_ctx* c, void* resource, void** devPtr, size_t* bytes) {
+    if (!c || !resource || !devPtr || !bytes) return fail(RT_ERR_INVALID_ARGUMENT, "rt_gl_map: null argument");
+    GlInteropApi* g = gl_api();
+    if (!g) return fail(RT_ERR_UNSUPPORTED, "rt_gl_map: GL interop is not available");
+    CUDA_TRY(cudaSetDevice(c->device));
+    void* res = resource;
+    int e = g->Map(1u, &res, (void*)c->stream);            // MapCuda, CudaGlInteropIndexBuffer.cs:62-74 (on the context's stream)
+    if (e != 0) return gl_fail(g, "cuGraphicsMapResources", e);
+    unsigned long long p = 0; size_t n = 0;
+    e = g->GetPtr(&p, &n, resource);                        // GetCudaArrayView, :76-88
+    if (e != 0) { g->Unmap(1u, &res, (void*)c->stream); return gl_fail(g, "cuGraphicsResourceGetMappedPointer", e); }
+    *devPtr = (void*)(uintptr_t)p; *bytes = n;
+    return RT_OK;
+}
+RT_API int rt_gl_unmap(rt_ctx* c, void* resource) {
+    if (!c || !resource) return fail(RT_ERR_INVALID_ARGUMENT, "rt_gl_unmap: null argument");
+    GlInteropApi* g = gl_api();
+    if (!g) return fail(RT_ERR_UNSUPPORTED, "rt_gl_unmap: GL interop is not available");
+    CUDA_TRY(cudaSetDevice(c->device));
+    void* res = resource;
+    const int e = g->Unmap(1u, &res, (void*)c->stream);    // UnmapCuda, :90-103
+    if (e != 0) return gl_fail(g, "cuGraphicsUnmapResources", e);
+    return RT_OK;
+}
+RT_API int rt_gl_unregister(rt_ctx* c, void* resource) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_gl_unregister: ctx is null");
+    if (!resource) return RT_OK;
+    GlInteropApi* g = gl_api();
+    if (!g) return fail(RT_ERR_UNSUPPORTED, "rt_gl_unregister: GL interop is not available");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const int e = g->Unregister(resource);                  // DisposeAcceleratorObject, :150-160
+    if (e != 0) return gl_fail(g, "cuGraphicsUnregisterResource", e);
     return RT_OK;
 }
 

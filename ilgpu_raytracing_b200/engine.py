@@ -30,7 +30,7 @@ class EngineError(RuntimeError):
 class EngKnobs(C.Structure):
     _fields_ = [("renderScale", C.c_float), ("enableTemporalReuse", C.c_int), ("enableSpatialReuse", C.c_int), ("rngLockNoise", C.c_int),
                 ("fixedSeed", C.c_int), ("spp", C.c_int), ("maxDepth", C.c_int), ("flags", C.c_uint), ("tileSize", C.c_int), ("rank", C.c_int),
-                ("worldSize", C.c_int), ("samplesPerPass", C.c_int), ("enableTAAU", C.c_int)]
+                ("worldSize", C.c_int), ("samplesPerPass", C.c_int), ("enableTAAU", C.c_int), ("asyncSubmit", C.c_int)]
 
 
 _lib = None
@@ -338,6 +338,10 @@ class RTRenderer:
         buf = C.create_string_buffer(unique_id, L.RT_COMM_ID_BYTES)
         _check(self._l.eng_renderer_init_multi_gpu(self.h, buf, rank, world_size))
         self.knobs.rank, self.knobs.worldSize = rank, world_size
+
+    def Synchronize(self):
+        """_cuda.Synchronize() (Engine/RTRenderer.cs:233): wait for everything queued on the renderer's context."""
+        self.native.sync()
 
     def last_config(self) -> L.RtRenderConfig:
         cfg = L.RtRenderConfig()

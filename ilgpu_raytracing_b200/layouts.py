@@ -47,6 +47,7 @@ RT_FLAG_KERNEL_TIMING = 1 << 5
 RT_FLAG_RESET_RESERVOIRS = 1 << 6
 RT_FLAG_PUBLISH_RESERVOIRS = 1 << 7
 RT_FLAG_FAST_SHADING = 1 << 8
+RT_FLAG_FRAME_GRAPH = 1 << 9
 
 (RT_BUF_RGBA8, RT_BUF_DEPTH, RT_BUF_OBJID, RT_BUF_RADIANCE, RT_BUF_ACCUM, RT_BUF_PRIM_ID, RT_BUF_INST_ID, RT_BUF_PRIMARY_T,
  RT_BUF_SEG_COUNT, RT_BUF_TERM_CODE, RT_BUF_PATH_HASH, RT_BUF_GB_WORLDPOS, RT_BUF_GB_NORMAL, RT_BUF_GB_BASECOLOR, RT_BUF_GB_MATID,

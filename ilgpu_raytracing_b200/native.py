@@ -19,7 +19,8 @@ _LIB_PATH = os.environ.get("RTCORE_B200_LIB") or os.path.join(_PKG, "librtcore_b
 EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set_stream", "rt_scene_upload", "rt_render", "rt_sync",
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
            "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex", "rt_download_async",
-           "rt_comm_get_unique_id", "rt_comm_init", "rt_comm_destroy", "rt_gather_frame"]
+           "rt_comm_get_unique_id", "rt_comm_init", "rt_comm_destroy", "rt_gather_frame",
+           "rt_gl_register_buffer", "rt_gl_map", "rt_gl_unmap", "rt_gl_unregister"]
 
 
 class RtError(RuntimeError):
@@ -62,6 +63,10 @@ def lib() -> C.CDLL:
     l.rt_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
     l.rt_comm_destroy.argtypes = [C.c_void_p]
     l.rt_gather_frame.argtypes = [C.c_void_p, C.c_int, C.c_uint32]
+    l.rt_gl_register_buffer.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_void_p)]
+    l.rt_gl_map.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    l.rt_gl_unmap.argtypes = [C.c_void_p, C.c_void_p]
+    l.rt_gl_unregister.argtypes = [C.c_void_p, C.c_void_p]
     for name in EXPORTS:
         if name not in ("rt_last_error",):
             getattr(l, name).restype = C.c_int

@@ -180,7 +180,11 @@ enum {
      * multiply-adds and hardware sin / cos / sqrt / reciprocal.  Nothing in that loop decides the path (every candidate draws exactly
      * three random numbers; bounce directions, Russian roulette and intersections stay exact): hit ids, bounce counts and terminators
      * are unchanged, radiance moves by ~1e-6 relative RMS (north_star allows 1e-4). */
-    RT_FLAG_FAST_SHADING = 1u << 8
+    RT_FLAG_FAST_SHADING = 1u << 8,
+    /* Replay the frame's kernel sequence from a CUDA graph (captured once per configuration, node parameters refreshed per frame):
+     * small, launch-bound frames (the reference's interactive regime, 858x482 x 2 spp) lose their per-launch gaps.  The image is
+     * the same with or without it. */
+    RT_FLAG_FRAME_GRAPH = 1u << 9
 };
 
 /* Everything the reference passes in GBufferParams / IntegratorParams
@@ -346,6 +350,18 @@ RT_API int rt_deinterleave_tiles(rt_ctx* ctx, const void* gatheredDev, const int
                                  int worldSize, int width, int height, int tileSize,
                                  void* outRadianceDev /* float4*w*h or NULL */,
                                  void* outRgba8Dev   /* int32*w*h or NULL */);
+
+/* ---- CUDA-GL interop for the present target: replaces the reference's driver-API binding and PBO class
+ *      (Engine/CudaGlInteropIndexBuffer.cs:18-34 DllImport "nvcuda" cuGraphicsGLRegisterBuffer / MapResources /
+ *      ResourceGetMappedPointer_v2 / UnmapResources / UnregisterResource; :44-60 register with WriteDiscard; :62-103 MapCuda /
+ *      GetCudaArrayView / UnmapCuda; :150-160 unregister).  The host creates the GL PixelUnpackBuffer and passes its name; map and
+ *      unmap run on the context's stream, so a frame is: rt_gl_map -> rt_render -> rt_present(mapped pointer) -> rt_gl_unmap ->
+ *      glTexSubImage2D from the PBO (Engine/RTWindow.cs:160-168).  Needs a GL context current on the calling thread (the reference's
+ *      GL thread); RT_ERR_CUDA with the driver's error name otherwise. ---- */
+RT_API int rt_gl_register_buffer(rt_ctx* ctx, unsigned int glBuffer, void** resource);
+RT_API int rt_gl_map(rt_ctx* ctx, void* resource, void** devPtr, size_t* bytes);
+RT_API int rt_gl_unmap(rt_ctx* ctx, void* resource);
+RT_API int rt_gl_unregister(rt_ctx* ctx, void* resource);
 
 /* ---- multi-GPU behind the ABI.  The reference drives ONE device (ctor `RTRenderer(RTWindow, int deviceIndex = 0)`,
  *      Engine/RTRenderer.cs:63,67) and its framebuffer is colour + depth + objectId (Engine/RTRay.cs:59-64,

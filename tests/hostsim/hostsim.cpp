@@ -225,7 +225,7 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
         fc.enableTemporal = cfg->enableTemporalReuse; fc.enableSpatial = cfg->enableSpatialReuse;
         fc.prevOrigin = mk3(pc->origin); fc.prevRight = mk3(pc->right); fc.prevUp = mk3(pc->up); fc.prevForward = mk3(pc->forward); fc.prevFovY = pc->fovYRadians; fc.prevAspect = pc->aspect;
         invMap.assign(G, 0); for (int i = 0; i < npx; i++) invMap[(size_t)pmap[i]] = i;
-        fc.invPixelMap = invMap.data();
+        fc.invPixelMap = invMap.data(); fc.lookBase = 0;   // look* pointers: set below, once the G-buffer vectors exist
         rp0.resize(G); rp1.resize(G); rp2.resize(G); rc0.resize(G); rc1.resize(G); rc2.resize(G);
         auto split = [](const RtReservoir& r, float4& a, float4& b, float4& c) {
             a = make_float4(r.L.X, r.L.Y, r.L.Z, r.pdf); b = make_float4(r.wi.X, r.wi.Y, r.wi.Z, r.w); c = make_float4(r.wSum, u2f((uint32_t)r.m), u2f((uint32_t)r.lightId), 0.0f);
@@ -251,6 +251,7 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
     wb.rgba8 = out->rgba8 ? out->rgba8 : dummyI.data(); wb.depth = out->depth ? out->depth : dummyF.data(); wb.objId = out->objId ? out->objId : dummyI.data();
     wb.radiance = radiance.data(); wb.accum = out->accum4 ? (float4*)out->accum4 : accum.data();
     wb.stThr = stThr.data(); wb.stLi = stLi.data(); wb.stC = stC.data(); wb.missD = missD.data();
+    fc.lookPosHit = gbPosHit.data(); fc.lookNrmMat = gbNrmMat.data(); fc.lookAlbObj = gbAlbObj.data();
     const bool aov = (cfg->flags & RT_FLAG_PATH_AOVS) && out->segCount && out->termCode && out->pathHash;
     if (reuse) { wb.resPath0 = rq0.data(); wb.resPath1 = rq1.data(); wb.resPath2 = rq2.data(); wb.resCur0 = rc0.data(); wb.resCur1 = rc1.data(); wb.resCur2 = rc2.data(); }
     if (aov) { wb.pathHash = pathHash.data(); wb.segCountOut = out->segCount; wb.termCodeOut = out->termCode; wb.pathHashOut = out->pathHash; }

@@ -58,6 +58,45 @@ def main():
             case["ok"] = all(v == 0 for v in case["mismatch"].values())
             ok = ok and case["ok"]
             report["cases"].append(case)
+    # ---- ReSTIR temporal + spatial reuse ACROSS the tile partition (SURVEY 8e caveat / 8f rank 1): every frame the ranks exchange the
+    # current G-buffer (after the primary pass) and the reservoirs they wrote (after accumulate) inside rt_render; the gathered
+    # sequence must equal the single-GPU sequence frame by frame, reservoirs included.  Matches Engine/RTRay.cs:339-435,476-516.
+    from oracle import orc
+    dsc = orc.Scene(); dsc.build_default()
+    ctx.scene_upload(dsc.arrays())
+    single = None
+    if rank == 0:
+        single = native.Context(local)
+        single.scene_upload(dsc.arrays())
+    W2, H2 = 648, 364
+    prev = None
+    reuse_case = {"what": "reuse across tiles, 4 frames, moving camera", "mismatch": {"rgba8": 0, "radiance": 0, "objId": 0, "reservoir_m": 0, "reservoir_wSum": 0}, "imports": 0}
+    for frame in range(4):
+        cam2 = orc.camera_create(W2, H2, 60.0, (0.0 + 0.07 * frame, 1.0 + 0.02 * frame, 3.0 - 0.05 * frame), (0.0, 0.5, 0.0))
+        orc.camera_bake(cam2, W2, H2)
+        if prev is None:
+            prev = cam2.copy()
+        fl = L.RT_FLAG_RESET_RESERVOIRS if frame == 0 else 0
+        ctx.render(cam2, L.make_render_config(W2, H2, spp=3, max_depth=3, frame=frame, rng_lock_noise=0, temporal=1, spatial=1, flags=fl, tile_size=tile, rank=rank, world_size=world), prev_cam=prev)
+        ctx.gather_frame(0, L.RT_GATHER_RADIANCE | L.RT_GATHER_DEPTH_OBJID)
+        ctx.sync()
+        if rank == 0:
+            single.render(cam2, L.make_render_config(W2, H2, spp=3, max_depth=3, frame=frame, rng_lock_noise=0, temporal=1, spatial=1, flags=fl), prev_cam=prev)
+            single.sync()
+            m = reuse_case["mismatch"]
+            m["rgba8"] += int((ctx.download(L.RT_BUF_GATHERED_RGBA8) != single.download(L.RT_BUF_RGBA8)).sum())
+            m["radiance"] += int((ctx.download(L.RT_BUF_GATHERED_RADIANCE)[:, :3] != single.download(L.RT_BUF_RADIANCE)[:, :3]).any(axis=1).sum())
+            m["objId"] += int((ctx.download(L.RT_BUF_GATHERED_OBJID) != single.download(L.RT_BUF_OBJID)).sum())
+            ra, rb = ctx.download(L.RT_BUF_RESERVOIR), single.download(L.RT_BUF_RESERVOIR)
+            m["reservoir_m"] += int((ra["m"] != rb["m"]).sum()); m["reservoir_wSum"] += int((ra["wSum"] != rb["wSum"]).sum())
+            if frame > 0:
+                reuse_case["imports"] += int((rb["m"] > 9).sum())
+        prev = cam2.copy()
+    if rank == 0:
+        reuse_case["ok"] = all(v == 0 for v in reuse_case["mismatch"].values()) and reuse_case["imports"] > 0
+        ok = ok and reuse_case["ok"]
+        report["cases"].append(reuse_case)
+        single.close()
     report["ok"] = ok
     flag = torch.tensor([1 if ok else 0])
     dist.broadcast(flag, src=0)

@@ -96,3 +96,21 @@ def test_native_gather_across_processes():
            os.path.join(root, "tests", "multirank_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_gl_interop_entry_points_without_a_gl_context(gpu_ctx):
+    """rt_gl_register_buffer / rt_gl_map / rt_gl_unmap / rt_gl_unregister replace the reference's driver-API binding
+    (Engine/CudaGlInteropIndexBuffer.cs:18-34,44-103).  There is no GL context on the test box, so only the error contract can be
+    exercised here: the driver's refusal comes back as a status + message, nothing throws or crashes, null arguments are caught."""
+    import ctypes as C
+    l = gpu_ctx._l
+    res = C.c_void_p()
+    rc = l.rt_gl_register_buffer(gpu_ctx.h, 12345, C.byref(res))
+    assert rc in (L.RT_ERR_CUDA, L.RT_ERR_UNSUPPORTED) and not res.value
+    msg = (l.rt_last_error() or b"").decode()
+    assert "cuGraphicsGLRegisterBuffer" in msg or "not available" in msg
+    assert l.rt_gl_register_buffer(gpu_ctx.h, 1, None) == L.RT_ERR_INVALID_ARGUMENT
+    p, n = C.c_void_p(), C.c_size_t()
+    assert l.rt_gl_map(gpu_ctx.h, None, C.byref(p), C.byref(n)) == L.RT_ERR_INVALID_ARGUMENT
+    assert l.rt_gl_unmap(gpu_ctx.h, None) == L.RT_ERR_INVALID_ARGUMENT
+    assert l.rt_gl_unregister(gpu_ctx.h, None) == L.RT_OK          # nothing to unregister
