@@ -134,24 +134,50 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clocks / throttle reasons sampled every 200 ms during the timed region: through NVML in-process (a light call; spawning
+    nvidia-smi five times a second perturbs sub-millisecond frames), nvidia-smi as the fallback."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu_index: int):
-        self.rows = []
+        self.rows = []      # (sm_mhz, sm_max_mhz, [reason names])
         self._stop = threading.Event()
         self._idx = gpu_index
         self._t = None
+        self.source = "nvidia-smi"
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else gpu_index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = get(self._h)
+        masks = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}   # NVML clocks-event-reason bits
+        self.rows.append((float(sm), float(mx), [k for k, m in masks.items() if bits & m]))
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", "-i", str(self._idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        if len(r) >= 6 and r[0].replace(".", "").isdigit():
+            self.rows.append((float(r[0]), float(r[1]), [self.NAMES[i] for i in range(4) if r[2 + i].lower().startswith("active")]))
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-
         def run():
             while not self._stop.is_set():
                 try:
-                    out = subprocess.run(["nvidia-smi", "-i", str(self._idx), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                         capture_output=True, text=True, timeout=5).stdout.strip()
-                    if out:
-                        self.rows.append([c.strip() for c in out.split(",")])
+                    self._sample_nvml() if self._nvml else self._sample_smi()
                 except Exception:
                     pass
                 self._stop.wait(0.2)
@@ -163,11 +189,10 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+        sm = [r[0] for r in self.rows]
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({n for r in self.rows for n in r[2]})
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm), source=self.source)
 
 
 def cpu_oracle_sample(wl: dict, threads: int = 0, aovs: bool = False) -> dict:

@@ -23,13 +23,17 @@ namespace ILGPU_Raytracing.Engine
     public enum RtFlags : uint
     {
         None = 0, TriMaterials = 1u << 0, Accumulate = 1u << 1, ResetAccum = 1u << 2, PathAovs = 1u << 3, Counters = 1u << 4, KernelTiming = 1u << 5,
-        ResetReservoirs = 1u << 6
+        ResetReservoirs = 1u << 6, PublishReservoirs = 1u << 7, FastShading = 1u << 8, FrameGraph = 1u << 9
     }
+
+    [Flags]
+    public enum RtGather : uint { Rgba8 = 1u << 0, Radiance = 1u << 1, DepthObjId = 1u << 2 }
 
     public enum RtBuffer
     {
         Rgba8 = 0, Depth = 1, ObjId = 2, Radiance = 3, Accum = 4, PrimId = 5, InstId = 6, PrimaryT = 7, SegCount = 8, TermCode = 9, PathHash = 10,
-        GbWorldPos = 11, GbNormal = 12, GbBaseColor = 13, GbMatId = 14, TileRadiance = 15, Reservoir = 16, Present = 17   // Reservoir: Engine/RTRay.cs:171-179 records; Present: what rt_present wrote
+        GbWorldPos = 11, GbNormal = 12, GbBaseColor = 13, GbMatId = 14, TileRadiance = 15, Reservoir = 16, Present = 17,   // Reservoir: Engine/RTRay.cs:171-179 records; Present: what rt_present wrote
+        GatheredRgba8 = 18, GatheredDepth = 19, GatheredObjId = 20, GatheredRadiance = 21                                   // the image rt_gather_frame assembled on its root
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -106,6 +110,17 @@ namespace ILGPU_Raytracing.Engine
         [DllImport(Lib)] public static extern int rt_tiles_owned_pixels(int width, int height, int tileSize, int rank, int worldSize, out long nPixels);
         [DllImport(Lib)] public static extern int rt_deinterleave_tiles(IntPtr ctx, IntPtr gatheredDev, long* rankOffsetsPx, int worldSize, int width, int height, int tileSize, IntPtr outRadianceDev, IntPtr outRgba8Dev);
         [DllImport(Lib)] public static extern int rt_get_stats(IntPtr ctx, out RtStats stats);
+        // multi-GPU: one process + one context per GPU, the NCCL communicator lives in the library
+        public const int CommIdBytes = 128;
+        [DllImport(Lib)] public static extern int rt_comm_get_unique_id(void* id, UIntPtr bytes);
+        [DllImport(Lib)] public static extern int rt_comm_init(IntPtr ctx, void* id, UIntPtr bytes, int rank, int worldSize);
+        [DllImport(Lib)] public static extern int rt_comm_destroy(IntPtr ctx);
+        [DllImport(Lib)] public static extern int rt_gather_frame(IntPtr ctx, int root, uint what);
+        // CUDA-GL interop of the present target (replaces the DllImport("nvcuda") block of Engine/CudaGlInteropIndexBuffer.cs:18-34)
+        [DllImport(Lib)] public static extern int rt_gl_register_buffer(IntPtr ctx, uint glBuffer, out IntPtr resource);
+        [DllImport(Lib)] public static extern int rt_gl_map(IntPtr ctx, IntPtr resource, out IntPtr devPtr, out UIntPtr bytes);
+        [DllImport(Lib)] public static extern int rt_gl_unmap(IntPtr ctx, IntPtr resource);
+        [DllImport(Lib)] public static extern int rt_gl_unregister(IntPtr ctx, IntPtr resource);
 
         // CudaException.ThrowIfFailed analogue (Engine/CudaGlInteropIndexBuffer.cs:56)
         public static void ThrowIfFailed(int status)

@@ -271,18 +271,12 @@ __device__ __forceinline__ void block_push(const VertexOut& vo, int path, const 
     __syncthreads();
 }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-
 template <bool REUSE, bool FAST>
 __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, DeviceStats* stats) {
     __shared__ int smPush[16];
     unsigned probed = 0;
     for (long long base = (long long)blockIdx.x * 256; base < nPaths; base += (long long)gridDim.x * 256) {
         const int j = (int)(base + threadIdx.x);
-        {   // the next iteration's G-buffer lines towards L2 while this one computes (one lane per 128-byte line)
-            const long long jn = base + (long long)gridDim.x * 256 + threadIdx.x;
-            if (jn < nPaths && (threadIdx.x & 7u) == 0u) { const int in = (int)(jn % fc.npx); prefetch_l2(wb.gbPosHit + in); prefetch_l2(wb.gbNrmMat + in); prefetch_l2(wb.gbAlbObj + in); }
-        }
         VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
         if (j < nPaths) shade_first<REUSE, FAST>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed, &vo);
         block_push(vo, j, nextQ, nextCount, shq, shCount, smPush);
@@ -356,21 +350,14 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
         __syncthreads();
         const int nf = nFront, nb = nBack;
         const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
-        // a hit's record chain is ray / hit record -> path slot -> path state -> primitive -> material: several dependent DRAM / L2
-        // round trips per vertex with only 32 warps per SM to hide them.  So each iteration pulls the records of the hit two
-        // iterations ahead towards L2, reads the slot / primitive words of the hit one ahead (their lines arrived by then) and,
-        // after shading, pulls that hit's path state and primitive record.
+        // (measured and rejected, round 2: pulling the records of the hits one / two iterations ahead towards L2 with prefetch.global.L2,
+        // here and for the G-buffer lines of k_shade_first: +8 ms per C4 frame)
         auto entry = [&](int i) -> int { return i < rf ? (i < nf ? list[i] : -1) : (i < rf + nb ? list[RT_SHADE_CHUNK - 1 - (i - rf)] : -1); };
         for (int i0 = 0; i0 < rf + nb; i0 += 256) {   // uniform trip count: block_push has barriers
-            const int i = i0 + (int)threadIdx.x;
-            const int k = entry(i), k1 = entry(i + 256), k2 = entry(i + 512);
-            if (k2 >= 0) { prefetch_l2(curQ.o + k2); prefetch_l2(curQ.d + k2); prefetch_l2(hits.tuv + k2); }
-            int slot1 = -1, prim1 = -1;
-            if (k1 >= 0) { slot1 = __float_as_int(__ldg(&curQ.o[k1].w)); prim1 = __ldg(hits.prim + k1); }
+            const int k = entry(i0 + (int)threadIdx.x);
             VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
             int path = 0;
             if (k >= 0) shade_next<REUSE, FAST>(fc, sc, wb, depth, curQ, hits, k, nextQ, nextCount, shq, shCount, &vo, &path);
-            if (k1 >= 0) { prefetch_l2(wb.stThr + slot1); prefetch_l2(wb.stLi + slot1); prefetch_l2(wb.stC + slot1); prefetch_l2(sc.prims + prim1); }
             if (depth < fc.maxDepth) block_push(vo, path, nextQ, nextCount, shq, shCount, smPush);   // the last depth queues nothing
         }
         __syncthreads();
