@@ -18,6 +18,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <tuple>
+#include <utility>
 #include <vector>
 
 #include "rt_bvh.h"
@@ -302,29 +304,30 @@ __device__ __forceinline__ bool hit_is_specular(const DeviceScene& sc, int prim)
     else if (sc.triMaterials) shade = sc.materials[sc.triMatIndex[primId]].Shading;
     return shade == RT_SHADING_MIRROR || shade == RT_SHADING_GLASS;
 }
-template <bool REUSE, bool FAST>
+template <bool REUSE, bool FAST, int CHUNK>
 __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
-    __shared__ int list[RT_SHADE_CHUNK];
+    __shared__ int list[CHUNK];
     __shared__ int nFront, nBack;
     __shared__ int smPush[16];
     const int n = *curCount;
-    const int nChunks = (n + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK;
+    const int nChunks = (n + CHUNK - 1) / CHUNK;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
-    static_assert(RT_SHADE_CHUNK == 256 * 16, "scan: four int4 loads per thread");
+    static_assert(CHUNK % 1024 == 0 && RT_SHADE_CHUNK % CHUNK == 0, "scan: CHUNK / 1024 int4 loads per thread; the index array is padded to RT_SHADE_CHUNK");
+    constexpr int LOADS = CHUNK / 1024;
     for (int ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
         if (threadIdx.x == 0) { nFront = 0; nBack = 0; }
         __syncthreads();
-        const int base = ch * RT_SHADE_CHUNK;
+        const int base = ch * CHUNK;
         // the primitive-index array is padded to a multiple of the chunk (ensure_frame_buffers), so whole-int4 loads stay in bounds
         const int4* src = reinterpret_cast<const int4*>(hits.prim + base);
-        int4 pv[4];
+        int4 pv[LOADS];
 #pragma unroll
-        for (int it = 0; it < 4; it++) pv[it] = __ldcs(src + it * 256 + threadIdx.x);
+        for (int it = 0; it < LOADS; it++) pv[it] = __ldcs(src + it * 256 + threadIdx.x);
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
+        for (int it = 0; it < LOADS; it++) {
             const int k0 = base + (it * 256 + (int)threadIdx.x) * 4;
             const int pr[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
 #pragma unroll
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
                     int b = 0;
                     if (lane == 0) b = atomicAdd(&nBack, __popc(mB));
                     b = __shfl_sync(FULL, b, 0);
-                    if (spec) list[RT_SHADE_CHUNK - 1 - (b + __popc(mB & ltMask))] = k;
+                    if (spec) list[CHUNK - 1 - (b + __popc(mB & ltMask))] = k;
                 }
             }
         }
@@ -352,7 +355,7 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
         const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
         // (measured and rejected, round 2: pulling the records of the hits one / two iterations ahead towards L2 with prefetch.global.L2,
         // here and for the G-buffer lines of k_shade_first: +8 ms per C4 frame)
-        auto entry = [&](int i) -> int { return i < rf ? (i < nf ? list[i] : -1) : (i < rf + nb ? list[RT_SHADE_CHUNK - 1 - (i - rf)] : -1); };
+        auto entry = [&](int i) -> int { return i < rf ? (i < nf ? list[i] : -1) : (i < rf + nb ? list[CHUNK - 1 - (i - rf)] : -1); };
         for (int i0 = 0; i0 < rf + nb; i0 += 256) {   // uniform trip count: block_push has barriers
             const int k = entry(i0 + (int)threadIdx.x);
             VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
@@ -469,6 +472,78 @@ static int fail(int code, const std::string& msg) { g_lastError = msg; return co
                                            std::string(#expr) + ": " + cudaGetErrorString(_e));                       \
     } while (0)
 
+// ------------------------------------------------------------------------------------------------ frame recorder (RT_FLAG_FRAME_GRAPH)
+// Every launch of a frame goes through a FrameRecorder.  Direct: cudaLaunchKernel on the stream (the default).  Build: the same
+// sequence becomes an explicit CUDA graph (a chain of kernel / memset / memcpy nodes) that is instantiated once per configuration.
+// Update: later frames of that configuration only refresh the kernel nodes' parameters (camera, frame index, buffer parity ...)
+// with cudaGraphExecKernelNodeSetParams and replay the graph with ONE launch: ~1 us of host work per kernel instead of a launch,
+// and no launch gaps on the device - what the reference's interactive regime (858x482, 2 spp) is bound by.
+struct FrameRecorder {
+    enum Mode { Direct, Build, Update };
+    Mode mode = Direct;
+    cudaStream_t st = nullptr;
+    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+    std::vector<cudaGraphNode_t>* kernelNodes = nullptr; std::vector<const void*>* kernelFuncs = nullptr;
+    size_t idx = 0; cudaGraphNode_t last = nullptr; bool haveLast = false, mismatch = false;
+    cudaError_t err = cudaSuccess; const char* where = "";
+    const void* l2Base = nullptr; size_t l2Bytes = 0; float l2Ratio = 1.0f;   // the persisting window of the BVH: graph kernel nodes do not inherit the stream's
+
+    void chain(cudaGraphNode_t n) { last = n; haveLast = true; }
+    template <typename... KArgs, typename... Args>
+    void launch(void (*k)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+        static_assert(sizeof...(KArgs) == sizeof...(Args), "kernel argument count");
+        if (err != cudaSuccess || mismatch) return;
+        std::tuple<typename std::decay<KArgs>::type...> vals{static_cast<typename std::decay<KArgs>::type>(args)...};
+        void* ptrs[sizeof...(KArgs) > 0 ? sizeof...(KArgs) : 1];
+        fill(ptrs, vals, std::index_sequence_for<KArgs...>{});
+        if (mode == Direct) { err = cudaLaunchKernel((const void*)k, grid, block, ptrs, smem, st); where = "cudaLaunchKernel"; return; }
+        cudaKernelNodeParams p; memset(&p, 0, sizeof(p));
+        p.func = (void*)k; p.gridDim = grid; p.blockDim = block; p.sharedMemBytes = (unsigned)smem; p.kernelParams = ptrs; p.extra = nullptr;
+        if (mode == Build) {
+            cudaGraphNode_t n;
+            err = cudaGraphAddKernelNode(&n, graph, haveLast ? &last : nullptr, haveLast ? 1 : 0, &p); where = "cudaGraphAddKernelNode";
+            if (err == cudaSuccess) {
+                kernelNodes->push_back(n); kernelFuncs->push_back((const void*)k); chain(n);
+                if (l2Bytes > 0) {
+                    cudaKernelNodeAttrValue av; memset(&av, 0, sizeof(av));
+                    av.accessPolicyWindow.base_ptr = const_cast<void*>(l2Base); av.accessPolicyWindow.num_bytes = l2Bytes; av.accessPolicyWindow.hitRatio = l2Ratio;
+                    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting; av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                    if (cudaGraphKernelNodeSetAttribute(n, cudaKernelNodeAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+                }
+            }
+        } else {
+            if (idx >= kernelNodes->size() || (*kernelFuncs)[idx] != (const void*)k) { mismatch = true; return; }   // another sequence: rebuild
+            err = cudaGraphExecKernelNodeSetParams(exec, (*kernelNodes)[idx++], &p); where = "cudaGraphExecKernelNodeSetParams";
+        }
+    }
+    template <typename Tuple, size_t... I> static void fill(void** ptrs, Tuple& t, std::index_sequence<I...>) { (void)ptrs; (void)t; int dummy[] = {0, ((ptrs[I] = (void*)&std::get<I>(t)), 0)...}; (void)dummy; }
+    void memset32(void* dst, size_t bytes) {   // zero `bytes` (a multiple of 4); static across the frames of a configuration (same pointer, same size)
+        if (err != cudaSuccess || mismatch) return;
+        if (mode == Direct) { err = cudaMemsetAsync(dst, 0, bytes, st); return; }
+        if (mode == Update) return;
+        cudaMemsetParams mp; memset(&mp, 0, sizeof(mp));
+        mp.dst = dst; mp.value = 0; mp.elementSize = 4; mp.width = bytes / 4; mp.height = 1; mp.pitch = 0;
+        cudaGraphNode_t n;
+        err = cudaGraphAddMemsetNode(&n, graph, haveLast ? &last : nullptr, haveLast ? 1 : 0, &mp); where = "cudaGraphAddMemsetNode";
+        if (err == cudaSuccess) chain(n);
+    }
+    void memcpy_d2h(void* dstHost, const void* srcDev, size_t bytes) {
+        if (err != cudaSuccess || mismatch) return;
+        if (mode == Direct) { err = cudaMemcpyAsync(dstHost, srcDev, bytes, cudaMemcpyDeviceToHost, st); return; }
+        if (mode == Update) return;
+        cudaGraphNode_t n;
+        err = cudaGraphAddMemcpyNode1D(&n, graph, haveLast ? &last : nullptr, haveLast ? 1 : 0, dstHost, srcDev, bytes, cudaMemcpyDeviceToHost); where = "cudaGraphAddMemcpyNode1D";
+        if (err == cudaSuccess) chain(n);
+    }
+};
+// what makes two frames "the same configuration" for graph replay: everything that decides WHICH kernels run, their grids' upper
+// bounds and the buffers the static nodes (memsets, the statistics copy) touch
+struct FrameKey {
+    int width, height, spp, S, maxDepth, worldSize, rank, tileSize, npx; uint32_t structuralFlags; int reuse, sunProbe, extColor, pad;
+    const void *counters, *dstats, *hstats, *bvh, *stream; size_t nCounters, pathCap; unsigned long long sceneVersion;
+    bool operator==(const FrameKey& o) const { return memcmp(this, &o, sizeof(FrameKey)) == 0; }
+};
+
 template <typename T> struct DevBuf {   // owning device allocation (freed with its owner: the context, or a scope)
     T* p = nullptr; size_t n = 0;
     DevBuf() = default;
@@ -548,7 +623,9 @@ struct rt_ctx {
     // ReSTIR reuse across the partition: every rank's G-buffer (exchanged after the primary pass) and the reservoir exchange buffer
     DevBuf<float4> gbAll, resPack; std::vector<int> deintHost;
     const float4 *gbPosPtr = nullptr, *gbNrmPtr = nullptr, *gbAlbPtr = nullptr;   // where the last frame's (own) G-buffer lives
-    cudaGraphExec_t frameGraphExec = nullptr; unsigned long long frameGraphBuilds = 0;   // RT_FLAG_FRAME_GRAPH
+    cudaGraph_t frameGraph = nullptr;   // kept alive: the node handles used for per-frame parameter updates belong to it
+    cudaGraphExec_t frameGraphExec = nullptr; unsigned long long frameGraphBuilds = 0, sceneVersion = 0;   // RT_FLAG_FRAME_GRAPH
+    FrameKey frameKey; std::vector<cudaGraphNode_t> frameNodes; std::vector<const void*> frameFuncs;
     bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envLbvhLeaf = 0;   // developer knobs, read once in rt_create
 };
 
@@ -569,27 +646,25 @@ static cudaError_t trace_event(rt_ctx* c) {
     return cudaEventRecord(c->traceEvents[c->traceEventsUsed++], c->stream);
 }
 
-template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, const ExtendArgs& a0, bool count) {
+template <bool ANY> static cudaError_t launch_extend(rt_ctx* c, FrameRecorder& rec, const ExtendArgs& a0, bool count) {
     ExtendArgs a = a0; a.stackEntries = c->stackEntries;
     cudaError_t e = trace_event(c);
     if (e != cudaSuccess) return e;
-    if (count) k_extend<ANY, true><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
-    else k_extend<ANY, false><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
+    if (count) rec.launch(k_extend<ANY, true>, dim3(c->extendBlocks), dim3(RT_EXTEND_THREADS), c->extendSmem, a);
+    else rec.launch(k_extend<ANY, false>, dim3(c->extendBlocks), dim3(RT_EXTEND_THREADS), c->extendSmem, a);
     c->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (rec.err != cudaSuccess) { fprintf(stderr, "rtcore_b200: %s failed for an extend kernel (grid %d, smem %zu): %s\n", rec.where, c->extendBlocks, c->extendSmem, cudaGetErrorString(rec.err)); return rec.err; }
     return trace_event(c);
 }
 
-static cudaError_t launch_extend_pair(rt_ctx* c, const ExtendArgs& closest, const ExtendArgs& anyhit, bool count) {
+static cudaError_t launch_extend_pair(rt_ctx* c, FrameRecorder& rec, const ExtendArgs& closest, const ExtendArgs& anyhit, bool count) {
     ExtendPairArgs a; a.closest = closest; a.anyhit = anyhit; a.closest.stackEntries = a.anyhit.stackEntries = c->stackEntries;
     cudaError_t e = trace_event(c);
     if (e != cudaSuccess) return e;
-    if (count) k_extend_pair<true><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
-    else k_extend_pair<false><<<c->extendBlocks, RT_EXTEND_THREADS, c->extendSmem, c->stream>>>(a);
+    if (count) rec.launch(k_extend_pair<true>, dim3(c->extendBlocks), dim3(RT_EXTEND_THREADS), c->extendSmem, a);
+    else rec.launch(k_extend_pair<false>, dim3(c->extendBlocks), dim3(RT_EXTEND_THREADS), c->extendSmem, a);
     c->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
+    if (rec.err != cudaSuccess) { fprintf(stderr, "rtcore_b200: %s failed for an extend kernel (grid %d, smem %zu): %s\n", rec.where, c->extendBlocks, c->extendSmem, cudaGetErrorString(rec.err)); return rec.err; }
     return trace_event(c);
 }
 
@@ -786,6 +861,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     cudaStreamSynchronize(c->stream);
     rt_comm_destroy(c);
     if (c->frameGraphExec) { cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr; }
+    if (c->frameGraph) { cudaGraphDestroy(c->frameGraph); c->frameGraph = nullptr; }
     c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); for (int b = 0; b < 2; b++) { c->tileRadiance[b].release(); c->tileAux[b].release(); c->tileRgba[b].release(); } c->primId.release(); c->instId.release(); c->primaryT.release();
@@ -889,7 +965,7 @@ RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFla
     if (rcSize != RT_OK) return rcSize;
     c->bvhStats = bvh.stats;
     c->bvhBytes = nNodes * sizeof(WideNode) + nPrims * sizeof(PrimRec);
-    c->hasScene = true;
+    c->hasScene = true; c->sceneVersion++;
     return RT_OK;
 }
 
@@ -1071,11 +1147,28 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     // buffer parity) with cudaGraphExecUpdate and replay it with ONE launch - the per-launch gaps of small, launch-bound frames go.
     // Not with per-launch timing, the phase statistics build or NCCL exchanges inside the frame.
     const bool useGraph = (cfg->flags & RT_FLAG_FRAME_GRAPH) != 0 && !c->timeKernels && !reuseDist && !RT_PHASE_STATS;
+    const bool sunProbe = spp >= 2 && cfg->maxDepth >= 1 && !reuse && !c->envNoSunProbe;
+    FrameKey key; memset(&key, 0, sizeof(key));
+    key.width = cfg->width; key.height = cfg->height; key.spp = spp; key.S = S; key.maxDepth = cfg->maxDepth; key.worldSize = c->worldSize; key.rank = c->rank; key.tileSize = c->tileSize; key.npx = npx;
+    key.structuralFlags = cfg->flags & (RT_FLAG_COUNTERS | RT_FLAG_FAST_SHADING | RT_FLAG_PATH_AOVS); key.reuse = reuse ? 1 : 0; key.sunProbe = sunProbe ? 1 : 0; key.extColor = c->extColor ? 1 : 0;
+    key.counters = c->counters.p; key.dstats = c->dstats.p; key.hstats = c->hstats; key.bvh = c->bvhBlob.p; key.stream = st; key.nCounters = nCounters; key.pathCap = c->pathCap; key.sceneVersion = c->sceneVersion;
+    FrameRecorder rec; rec.st = st;
+    if (c->l2Window > 0) { rec.l2Base = c->bvhBlob.p; rec.l2Bytes = c->l2Window; rec.l2Ratio = c->l2Persist >= c->l2Window ? 1.0f : (float)c->l2Persist / (float)c->l2Window; }
+    if (useGraph) {
+        if (c->frameGraphExec && key == c->frameKey) { rec.mode = FrameRecorder::Update; rec.exec = c->frameGraphExec; }
+        else {
+            if (c->frameGraphExec) { cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr; }
+            if (c->frameGraph) { cudaGraphDestroy(c->frameGraph); c->frameGraph = nullptr; }
+            c->frameNodes.clear(); c->frameFuncs.clear();
+            rec.mode = FrameRecorder::Build;
+            CUDA_TRY(cudaGraphCreate(&rec.graph, 0));
+        }
+        rec.kernelNodes = &c->frameNodes; rec.kernelFuncs = &c->frameFuncs;
+    }
     CUDA_TRY(cudaEventRecord(c->evStart, st));
-    if (useGraph) CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     const int rcFrame = [&]() -> int {
-    CUDA_TRY(cudaMemsetAsync(c->counters.p, 0, nCounters * sizeof(int), st));
-    CUDA_TRY(cudaMemsetAsync(c->dstats.p, 0, sizeof(DeviceStats), st));
+    rec.memset32(c->counters.p, nCounters * sizeof(int));
+    rec.memset32(c->dstats.p, sizeof(DeviceStats));
 
     FrameConst fc; memset(&fc, 0, sizeof(fc));
     fc.width = cfg->width; fc.height = cfg->height; fc.frame = cfg->frame; fc.spp = cfg->spp; fc.maxDepth = cfg->maxDepth; fc.rngLockNoise = cfg->rngLockNoise; fc.flags = cfg->flags;
@@ -1119,12 +1212,12 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         RayQueue q0 = {c->qO[0].p, c->qD[0].p};
         int* primaryCount = c->counters.p + 0;
         int* primaryWork = c->counters.p + 1;
-        k_generate_primary<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, q0, primaryCount); c->launches++;
+        rec.launch(k_generate_primary, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, q0, primaryCount); c->launches++;
         const HitQueue hq = {c->hitPrim.p, c->hitTuv.p};
         ExtendArgs ea; memset(&ea, 0, sizeof(ea));
         ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missD = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
-        CUDA_TRY(launch_extend<false>(c, ea, count));
-        k_primary_finish<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, c->ds, wb, q0, hq); c->launches++;
+        CUDA_TRY(launch_extend<false>(c, rec, ea, count));
+        rec.launch(k_primary_finish, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, c->ds, wb, q0, hq); c->launches++;
         if (reuseDist) {   // every rank's G-buffer segment to every other rank (SpatialCompatible compares the CURRENT frame's G-buffer at both pixels)
             const size_t g = (size_t)cfg->width * cfg->height;
             float4* arrays[3] = {c->gbAll.p, c->gbAll.p + g, c->gbAll.p + 2 * g};
@@ -1134,13 +1227,13 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
 
         ShadowQueue shq = {c->shO.p, c->shD.p};
         // ---- shared sun probe: one any-hit ray per Lambert primary vertex facing the sun, instead of one per sample that selects it
-        if (spp >= 2 && cfg->maxDepth >= 1 && !reuse && !c->envNoSunProbe) {
+        if (sunProbe) {
             int* sunCount = c->counters.p + 2;
-            k_sun_generate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, shq, sunCount); c->launches++;
+            rec.launch(k_sun_generate, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, wb, shq, sunCount); c->launches++;
             ExtendArgs pa; memset(&pa, 0, sizeof(pa));
             pa.sc = c->ds; pa.rayO = shq.o; pa.rayD = shq.d; pa.count = sunCount; pa.work = sunCount + 1; pa.stC = c->stC.p; pa.stats = c->dstats.p; pa.statSlot = 3;
-            CUDA_TRY(launch_extend<true>(c, pa, count));
-            k_sun_store<<<grid_for(c, npx, 256), 256, 0, st>>>(wb, shq, sunCount); c->launches++;
+            CUDA_TRY(launch_extend<true>(c, rec, pa, count));
+            rec.launch(k_sun_store, dim3(grid_for(c, npx, 256)), dim3(256), 0, wb, shq, (const int*)sunCount); c->launches++;
         }
 
         // ---- integrator: batches of S samples, one wavefront iteration per depth ---------------------------------
@@ -1152,10 +1245,10 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             RayQueue nq = {c->qO[cur].p, c->qD[cur].p};
             {
                 const int g1 = grid_for(c, nPaths, 256);
-                if (reuse && fast) k_shade_first<true, true><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
-                else if (reuse) k_shade_first<true, false><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
-                else if (fast) k_shade_first<false, true><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
-                else k_shade_first<false, false><<<g1, 256, 0, st>>>(fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                if (reuse && fast) rec.launch(k_shade_first<true, true>, dim3(g1), dim3(256), 0, fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                else if (reuse) rec.launch(k_shade_first<true, false>, dim3(g1), dim3(256), 0, fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                else if (fast) rec.launch(k_shade_first<false, true>, dim3(g1), dim3(256), 0, fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
+                else rec.launch(k_shade_first<false, false>, dim3(g1), dim3(256), 0, fc, wb, s0, (int)nPaths, nq, ctr + 0, shq, ctr + 1, c->dstats.p);
             }
             c->launches++;
             for (int depth = 1; depth <= cfg->maxDepth; depth++) {
@@ -1166,17 +1259,20 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.count = prev + 1; sa.work = prev + 3; sa.stC = c->stC.p; sa.stats = c->dstats.p; sa.statSlot = 2;
                 ExtendArgs ca; memset(&ca, 0, sizeof(ca));
                 ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.count = prev + 0; ca.work = prev + 2; ca.hits = hq; ca.missD = c->missD.p; ca.stats = c->dstats.p; ca.statSlot = 1;
-                CUDA_TRY(launch_extend_pair(c, ca, sa, count));   // closest-hit and shadow rays of this depth in ONE persistent launch
+                CUDA_TRY(launch_extend_pair(c, rec, ca, sa, count));   // closest-hit and shadow rays of this depth in ONE persistent launch
                 RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p};
-                const int shadeGrid = grid_for(c, (nPaths + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK, 1);
-                if (reuse && fast) k_shade_next<true, true><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
-                else if (reuse) k_shade_next<true, false><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
-                else if (fast) k_shade_next<false, true><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
-                else k_shade_next<false, false><<<shadeGrid, 256, 0, st>>>(fc, c->ds, wb, depth, cq, hq, prev + 0, nq2, mine + 0, shq, mine + 1);
+                // chunks of 4096 rays per block for big wavefronts; 1024 when that would leave SMs without a block (interactive frame sizes:
+                // 827 K paths are 202 chunks of 4096 - one 8-warp block per SM - but 808 of 1024)
+                const bool smallChunks = nPaths < (size_t)c->smCount * 8 * RT_SHADE_CHUNK;
+                const int shadeGrid = grid_for(c, (nPaths + (smallChunks ? 1024 : RT_SHADE_CHUNK) - 1) / (smallChunks ? 1024 : RT_SHADE_CHUNK), 1);
+#define RT_LAUNCH_SHADE_NEXT(R, F, C) rec.launch(k_shade_next<R, F, C>, dim3(shadeGrid), dim3(256), 0, fc, c->ds, wb, depth, cq, hq, (const int*)(prev + 0), nq2, mine + 0, shq, mine + 1)
+                if (smallChunks) { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, 1024); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, 1024); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, 1024); else RT_LAUNCH_SHADE_NEXT(false, false, 1024); }
+                else { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, RT_SHADE_CHUNK); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, RT_SHADE_CHUNK); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, RT_SHADE_CHUNK); else RT_LAUNCH_SHADE_NEXT(false, false, RT_SHADE_CHUNK); }
+#undef RT_LAUNCH_SHADE_NEXT
                 c->launches++;
                 cur ^= 1;
             }
-            k_accumulate<<<grid_for(c, npx, 256), 256, 0, st>>>(fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
+            rec.launch(k_accumulate, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;
         }
         if (reuseDist) {   // this frame's reservoirs of every rank's pixels to every rank: next frame's imports read any pixel's
             const size_t g = (size_t)cfg->width * cfg->height;
@@ -1188,32 +1284,28 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             k_res_unpack<<<grid_for(c, g, 256), 256, 0, st>>>(c->resPack.p, g, c->deintMap.p, ownStart, ownStart + (size_t)npx, cur); c->launches++;
         }
         if (c->extColor) {
-            k_copy_color<<<grid_for(c, npx, 256), 256, 0, st>>>(c->rgba8.p, c->extColor, c->pixelMap.p, npx); c->launches++;
+            rec.launch(k_copy_color, dim3(grid_for(c, npx, 256)), dim3(256), 0, (const int*)c->rgba8.p, c->extColor, (const int*)c->pixelMap.p, npx); c->launches++;
         }
     }
+    rec.memcpy_d2h(c->hstats, c->dstats.p, sizeof(DeviceStats));
+    if (rec.err != cudaSuccess) return fail(rec.err == cudaErrorMemoryAllocation ? RT_ERR_OUT_OF_MEMORY : RT_ERR_CUDA, std::string("frame launch: ") + cudaGetErrorString(rec.err));
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(c->hstats, c->dstats.p, sizeof(DeviceStats), cudaMemcpyDeviceToHost, st));
     return RT_OK;
     }();
     if (useGraph) {
-        cudaGraph_t graph = nullptr;
-        const cudaError_t ec = cudaStreamEndCapture(st, &graph);   // always: a failed enqueue must not leave the stream capturing
-        if (rcFrame != RT_OK) { if (graph) cudaGraphDestroy(graph); (void)cudaGetLastError(); return rcFrame; }
-        if (ec != cudaSuccess || !graph) return fail(RT_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ec));
-        bool fresh = c->frameGraphExec == nullptr;
-        if (!fresh) {
-            cudaGraphExecUpdateResultInfo info;
-            if (cudaGraphExecUpdate(c->frameGraphExec, graph, &info) != cudaSuccess) {   // another configuration (topology changed): instantiate anew
-                (void)cudaGetLastError();
-                cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr; fresh = true;
-            }
+        const bool ok = rcFrame == RT_OK && !rec.mismatch && (rec.mode != FrameRecorder::Update || rec.idx == c->frameNodes.size());
+        if (rec.mode == FrameRecorder::Build) {
+            if (ok) {
+                const cudaError_t ei = cudaGraphInstantiate(&c->frameGraphExec, rec.graph, 0);
+                if (ei != cudaSuccess) { cudaGraphDestroy(rec.graph); c->frameGraphExec = nullptr; return fail(RT_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
+                c->frameGraph = rec.graph; c->frameKey = key; c->frameGraphBuilds++;
+            } else { cudaGraphDestroy(rec.graph); c->frameNodes.clear(); c->frameFuncs.clear(); }
+        } else if (!ok && c->frameGraphExec) {   // the sequence did not match the recorded one after all: drop the graph (the next frame rebuilds it)
+            cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr;
+            if (c->frameGraph) { cudaGraphDestroy(c->frameGraph); c->frameGraph = nullptr; }
         }
-        if (fresh) {
-            const cudaError_t ei = cudaGraphInstantiate(&c->frameGraphExec, graph, 0);
-            if (ei != cudaSuccess) { cudaGraphDestroy(graph); c->frameGraphExec = nullptr; return fail(RT_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ei)); }
-            c->frameGraphBuilds++;
-        }
-        cudaGraphDestroy(graph);
+        if (rcFrame != RT_OK) return rcFrame;
+        if (!ok) return fail(RT_ERR_INVALID_STATE, "rt_render: the frame's launch sequence changed under a recorded frame graph");
         CUDA_TRY(cudaGraphLaunch(c->frameGraphExec, st));
     } else if (rcFrame != RT_OK) return rcFrame;
     CUDA_TRY(cudaEventRecord(c->evStop, st));
