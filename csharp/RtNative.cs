@@ -95,6 +95,7 @@ namespace ILGPU_Raytracing.Engine
         [DllImport(Lib)] public static extern int rt_create(int* deviceIds, int nDev, out IntPtr ctx);
         [DllImport(Lib)] public static extern int rt_destroy(IntPtr ctx);
         [DllImport(Lib)] public static extern int rt_set_stream(IntPtr ctx, IntPtr cudaStream);
+        [DllImport(Lib)] public static extern int rt_get_stream(IntPtr ctx, out IntPtr cudaStream);
         [DllImport(Lib)] public static extern int rt_scene_upload(IntPtr ctx, RtSceneDesc* scene);
         [DllImport(Lib)] public static extern int rt_scene_upload_ex(IntPtr ctx, RtSceneDesc* scene, uint buildFlags);   // 1 = RT_BUILD_DEVICE_LBVH
         // BvhManager.BuildOrRefit(RebuildPolicy.ForceRefit): moved vertices for the uploaded topology, refitted on the device

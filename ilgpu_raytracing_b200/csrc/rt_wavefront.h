@@ -6,9 +6,9 @@
 //        then accumulate (settles what is still pending per path - the last shadow ray's contribution, the sky of a bounce ray
 //        that left the scene -, then the per-pixel sum over samples in sample order, SafeColor, mean, PackRGBA8).
 //
-// Deferred settlement (round 2): the extend kernel never reads path state.  A shadow ray's visibility goes to stC[slot].w and is
+// Deferred settlement (round 2): the extend kernel never reads path state.  A shadow ray's visibility goes to st[slot].c.w and is
 // added to Li by whoever touches the path next (shade_next of the bounce ray's hit, or accumulate); a bounce ray that misses only
-// leaves its direction in missD[slot], and accumulate adds throughput * sky(direction).  Per path the additions happen in the
+// leaves its direction in st[slot].miss, and accumulate adds throughput * sky(direction).  Per path the additions happen in the
 // reference's order (direct light of vertex d, then whatever vertex d + 1 adds), so Li is bit-identical.
 //
 // Each function below is the body of one kernel for one work item; rt_kernels.cu wraps them in
@@ -39,6 +39,13 @@ struct FrameConst {
     const float4 *resPrev0, *resPrev1, *resPrev2; // previous frame's reservoirs per global pixel: L|pdf, wi|w, wSum|m|lightId
 };
 
+struct alignas(16) PathState {
+    float4 thr;    // throughput.xyz | rng state
+    float4 li;     // Li.xyz | segCount (bits 0-7), terminator (bits 8-15), path flags (bits 16+)
+    float4 c;      // pending direct-light term of the path's latest Lambert vertex: throughput * f/p * W | visibility (written by the any-hit extend)
+    float4 miss;   // direction of the path's bounce ray when it left the scene (written by the closest-hit extend) | unused
+};
+
 struct WaveBuffers {
     // per owned pixel
     float4 *gbPosHit, *gbNrmMat, *gbAlbObj;   // GpuGBuffer (RTRay.cs:80-109): worldPos|hitMask, normalWS|matId, baseColor|objId
@@ -49,11 +56,9 @@ struct WaveBuffers {
     int* tileRgba;                            // PackRGBA8 of what the pixel shows, per owned pixel (display-only gather payload; may be null)
     // per global pixel
     int* rgba8; float* depth; int* objId; float4* radiance; float4* accum;
-    // per path slot (path j = sampleInBatch * npx + ownedPixel)
-    float4* stThr;    // throughput.xyz | rng state
-    float4* stLi;     // Li.xyz | segCount (bits 0-7), terminator (bits 8-15), path flags (bits 16+)
-    float4* stC;      // pending direct-light term of the path's latest Lambert vertex: throughput * f/p * W | visibility (written by the any-hit extend)
-    float4* missD;    // direction of the path's bounce ray when it left the scene (written by the closest-hit extend) | unused
+    // per path slot (path j = sampleInBatch * npx + ownedPixel): ONE 64-byte record, so that the scattered accesses of a path's next
+    // touch (shade_next of a hit, the extend kernel's visibility / miss stores, accumulate) hit one line instead of four arrays
+    PathState* st;
     uint32_t* pathHash;
     // reservoirs (null unless a reuse flag is set): per path slot, the reservoir of the path's first Lambert vertex ("outRes",
     // RTRay.cs:289-296), and per global pixel the frame's resCur, which accumulate() fills from the LAST sample that wrote one
@@ -71,7 +76,7 @@ struct RayQueue { float4* o; float4* d; };
 // and t | bu | bv only for rays that hit (16 B).
 struct HitQueue { int* prim; float4* tuv; };
 RT_HD HitRec load_hit(const HitQueue& h, int k) { const float4 v = h.tuv[k]; HitRec r; r.t = v.x; r.prim = h.prim[k]; r.bu = v.y; r.bv = v.z; return r; }
-struct ShadowQueue { float4* o; float4* d; };   // the pending contribution and the visibility live per PATH (WaveBuffers::stC), not per queue entry
+struct ShadowQueue { float4* o; float4* d; };   // the pending contribution and the visibility live per PATH (PathState::c), not per queue entry
 
 RT_HD uint32_t fnv_fold(uint32_t h, uint32_t v) { return (h ^ v) * 16777619u; }
 
@@ -162,12 +167,12 @@ RT_HD void sun_probe_generate(const FrameConst& fc, const WaveBuffers& wb, int i
     const RayOD s = make_ray_normal_offset(mk3(ph.x, ph.y, ph.z), n, wi);   // Visible() :622
     write_ray(shQ.o, shQ.d, queue_alloc(shCount), s, i);
 }
-// the probe's visibility arrives where every shadow ray's does: stC[slot].w, slot = the owned pixel (shade_first, which runs after
-// this, overwrites stC for the path slots it uses)
+// the probe's visibility arrives where every shadow ray's does: st[slot].c.w, slot = the owned pixel (shade_first, which runs after
+// this, overwrites the record of the path slots it uses)
 RT_HD void sun_probe_store(const WaveBuffers& wb, const ShadowQueue& shQ, int k) {
     const int i = (int)f2u(shQ.o[k].w);
     float4 ph = wb.gbPosHit[i];
-    ph.w = u2f(f2u(ph.w) | GB_SUN_KNOWN | (wb.stC[i].w != 0.0f ? GB_SUN_VISIBLE : 0u));
+    ph.w = u2f(f2u(ph.w) | GB_SUN_KNOWN | (wb.st[i].c.w != 0.0f ? GB_SUN_VISIBLE : 0u));
     wb.gbPosHit[i] = ph;
 }
 
@@ -178,11 +183,11 @@ struct PathVertex { f3 pos, nrm, alb, I; int shade; float ior; };
 // the host simulator and single-vertex callers push them right away (push_vertex_out).
 struct VertexOut { int pushNext, pushShadow; RayOD next, shadow; };
 
-// path flags kept in stLi.w above the parity taps (bits 0-7 segment count, 8-15 terminator)
+// path flags kept in PathState::li.w above the parity taps (bits 0-7 segment count, 8-15 terminator)
 enum : uint32_t {
     PATH_WROTE_RESERVOIR = 1u << 16,
-    PATH_PENDING_SHADOW  = 1u << 17,   // stC[path] holds a contribution whose shadow ray has been (or is being) traced and not yet added to Li
-    PATH_RAY_IN_FLIGHT   = 1u << 18    // a bounce ray was pushed and no hit of it has been shaded: at accumulate time that means it missed (missD[path])
+    PATH_PENDING_SHADOW  = 1u << 17,   // st[path].c holds a contribution whose shadow ray has been (or is being) traced and not yet added to Li
+    PATH_RAY_IN_FLIGHT   = 1u << 18    // a bounce ray was pushed and no hit of it has been shaded: at accumulate time that means it missed (st[path].miss)
 };
 
 // ReprojectToPrevPixel (RTRay.cs:339-360)
@@ -319,7 +324,7 @@ RT_HD bool shade_vertex(const FrameConst& fc, const WaveBuffers& wb, const PathV
             RayOD s = make_ray_normal_offset(v.pos, v.nrm, wiSel);   // Visible() :622
             f3 c = thr * contrib;                                    // "Li += throughput * direct" :286,291
             vo.pushShadow = 1; vo.shadow = s;
-            wb.stC[path] = make_float4(c.x, c.y, c.z, 0.0f);
+            wb.st[path].c = make_float4(c.x, c.y, c.z, 0.0f);
             pflags |= PATH_PENDING_SHADOW;
         }
         f3 wi = sample_hemisphere_cosine(v.nrm, B, rng);   // :302
@@ -347,7 +352,7 @@ RT_HD void push_vertex_out(const VertexOut& vo, int path, const RayQueue& nextQ,
 RT_HD void settle_pending_shadow(const WaveBuffers& wb, int j, uint32_t& pflags, f3& Li) {
     if ((pflags & PATH_PENDING_SHADOW) == 0u) return;
     pflags &= ~PATH_PENDING_SHADOW;
-    const float4 c = wb.stC[j];
+    const float4 c = wb.st[j].c;
     const bool visible = c.w != 0.0f;
     if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (visible ? 1u : 0u));
     if (visible) { Li.x = Li.x + c.x; Li.y = Li.y + c.y; Li.z = Li.z + c.z; }
@@ -369,7 +374,7 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     if (wb.pathHash) wb.pathHash[j] = 0x811C9DC5u;
     f3 thr = mk3(1.0f, 1.0f, 1.0f);
     if (fc.maxDepth <= 0) {
-        wb.stLi[j] = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_MAXDEPTH)));
+        wb.st[j].li = make_float4(0.0f, 0.0f, 0.0f, u2f(pack_aov(0, RT_TERM_MAXDEPTH)));
         return;
     }
     const float4 nm = wb.gbNrmMat[i], ao = wb.gbAlbObj[i];
@@ -388,23 +393,23 @@ RT_HD void shade_first(const FrameConst& fc, const WaveBuffers& wb, int sampleBa
     VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
     bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, 0, j, thr, rng, pflags, vo, sunFlags, &direct, &probed);
     if (defer) *defer = vo; else push_vertex_out(vo, j, nextQ, nextCount, shQ, shCount);
-    wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
+    wb.st[j].thr = make_float4(thr.x, thr.y, thr.z, u2f(rng));
     // a probed shadow ray is settled on the spot, before anything else touches Li: Li = 0 + throughput * direct, and the visibility fold of the path hash
     if (probed != 0 && wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0x100u | (probed == 2 ? 1u : 0u));
-    wb.stLi[j] = make_float4(0.0f + direct.x, 0.0f + direct.y, 0.0f + direct.z, u2f(pflags | pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+    wb.st[j].li = make_float4(0.0f + direct.x, 0.0f + direct.y, 0.0f + direct.z, u2f(pflags | pack_aov(0, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
     if (probedCount && probed != 0) (*probedCount)++;
 }
 
 // What the extend kernels leave behind when a ray is done (the device kernels write the same words with streaming stores):
 //   closest hit: the primitive index for every ray, t | bu | bv for hits, and for a bounce ray that left the scene its direction
 //                under the path's slot (settled by accumulate); any hit: the visibility under the path's slot.
-RT_HD void store_closest_result(const HitQueue& hq, float4* missD, int k, int slot, const HitRec& h, f3 d) {
+RT_HD void store_closest_result(const HitQueue& hq, PathState* st, int k, int slot, const HitRec& h, f3 d) {   // st = null: primary rays (no path yet)
     const bool hit = h.t < 1e29f;   // SceneDeviceViews.cs:85
     hq.prim[k] = hit ? h.prim : -1;
     if (hit) hq.tuv[k] = make_float4(h.t, h.bu, h.bv, 0.0f);
-    else if (missD) missD[slot] = make_float4(d.x, d.y, d.z, 0.0f);
+    else if (st) st[slot].miss = make_float4(d.x, d.y, d.z, 0.0f);
 }
-RT_HD void store_anyhit_result(float4* stC, int slot, bool occluded) { stC[slot].w = occluded ? 0.0f : 1.0f; }
+RT_HD void store_anyhit_result(PathState* st, int slot, bool occluded) { st[slot].c.w = occluded ? 0.0f : 1.0f; }
 
 // depth >= 1: consume the closest-hit result of a ray traced at depth-1 that HIT something (TraceNext, RTRay.cs:659-671) and shade
 // the new vertex.  Rays that missed never come here: accumulate() settles them (settle_miss).
@@ -418,8 +423,8 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
     if (pathOut) *pathOut = j;
     const f3 o = mk3(ro.x, ro.y, ro.z), d = mk3(rd.x, rd.y, rd.z);
     const HitRec h = load_hit(hits, k);
-    const float4 st = wb.stThr[j];
-    float4 li4 = wb.stLi[j];
+    const float4 st = wb.st[j].thr;
+    float4 li4 = wb.st[j].li;
     f3 thr = mk3(st.x, st.y, st.z), Li = mk3(li4.x, li4.y, li4.z);
     uint32_t rng = f2u(st.w);
     int seg = (int)(f2u(li4.w) & 0xFFu) + 1;
@@ -437,13 +442,13 @@ RT_HD void shade_next(const FrameConst& fc, const DeviceScene& sc, const WaveBuf
             VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
             bool alive = shade_vertex<REUSE, FAST>(fc, wb, v, depth, j, thr, rng, pflags, vo);
             if (defer) *defer = vo; else push_vertex_out(vo, j, nextQ, nextCount, shQ, shCount);
-            wb.stThr[j] = make_float4(thr.x, thr.y, thr.z, u2f(rng));
-            wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
+            wb.st[j].thr = make_float4(thr.x, thr.y, thr.z, u2f(rng));
+            wb.st[j].li = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, alive ? RT_TERM_MAXDEPTH : RT_TERM_ROULETTE)));
             return;
         }
     }
     // depth == maxDepth: the depth loop has run out (:233); nothing more is added
-    wb.stLi[j] = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, RT_TERM_MAXDEPTH)));
+    wb.st[j].li = make_float4(Li.x, Li.y, Li.z, u2f(pflags | pack_aov(seg, RT_TERM_MAXDEPTH)));
 }
 
 // ------------------------------------------------------------------------------------------------ accumulate
@@ -468,7 +473,7 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
             }
             continue;
         }
-        float4 li4 = wb.stLi[j];
+        float4 li4 = wb.st[j].li;
         if (f2u(li4.w) & PATH_WROTE_RESERVOIR) resOwner = j;
         if ((f2u(li4.w) & (PATH_PENDING_SHADOW | PATH_RAY_IN_FLIGHT)) != 0u) {
             // what the wavefront left pending for this path, in the reference's order: the direct light of its last Lambert vertex
@@ -477,7 +482,7 @@ RT_HD void accumulate(const FrameConst& fc, const WaveBuffers& wb, int sampleBas
             f3 Li = mk3(li4.x, li4.y, li4.z);
             settle_pending_shadow(wb, j, pf, Li);
             if (pf & PATH_RAY_IN_FLIGHT) {
-                const float4 st = wb.stThr[j], md = wb.missD[j];
+                const float4 st = wb.st[j].thr, md = wb.st[j].miss;
                 Li = Li + mk3(st.x, st.y, st.z) * sky_weighted(fc.env, mk3(md.x, md.y, md.z));
                 if (wb.pathHash) wb.pathHash[j] = fnv_fold(wb.pathHash[j], 0xFFFFFFFFu);
                 pf = (pf & 0xFFFF0000u & ~PATH_RAY_IN_FLIGHT) | pack_aov((int)(pf & 0xFFu) + 1, RT_TERM_MISS);

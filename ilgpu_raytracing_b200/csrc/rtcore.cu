@@ -45,7 +45,7 @@ using namespace rtx;
 #define RT_PRIM_VOTE 1       // lanes that must have a primitive queued before the warp runs a primitive phase (sweep: 1 is best)
 #endif
 
-#define RT_PATH_BYTES 180   // device memory per path of a wavefront pass: state 4 x 16 (throughput | rng, Li | flags, pending direct light, miss direction), two ray queues 2 x 32, shadow queue 32, hit record 4 + 16
+#define RT_PATH_BYTES 180   // device memory per path of a wavefront pass: state record 64 (throughput | rng, Li | flags, pending direct light, miss direction), two ray queues 2 x 32, shadow queue 32, hit record 4 + 16
 
 struct DeviceStats {   // zeroed at the start of every rt_render
     unsigned long long raysPrimary, raysBounce, raysShadow, wideNodes, tris, spheres;
@@ -59,8 +59,8 @@ struct ExtendArgs {
     const int* count;          // number of rays in the queue (device memory: written by the producing kernel)
     int* work;                 // global fetch cursor for this launch (zeroed per frame)
     HitQueue hits;             // closest: primitive index per ray, t | bu | bv per hit
-    float4* missD;             // closest: where a bounce ray that left the scene leaves its direction, by path slot (null: primary rays)
-    float4* stC;               // any-hit: the visibility goes to stC[path slot].w, next to the pending contribution
+    PathState* missSt;         // closest: a bounce ray that left the scene leaves its direction in st[path slot].miss (null: primary rays)
+    PathState* visSt;          // any-hit: the visibility goes to st[path slot].c.w, next to the pending contribution
     DeviceStats* stats;
     int statSlot;              // 0 primary, 1 bounce, 2 shadow, 3 sun probe
     int stackEntries;          // traversal stack entries per lane in shared memory (debug bounds checks)
@@ -103,11 +103,11 @@ __device__ __forceinline__ void extend_queue(const ExtendArgs& a, LaneStack& sta
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
                 const float4 ro = a.rayO[i], rd = a.rayD[i];
                 HitRec h; h.t = 1e30f; h.prim = -1; h.bu = 0.0f; h.bv = 0.0f;
-                store_closest_result(a.hits, a.missD, i, (int)f2u(ro.w), h, mk3(rd.x, rd.y, rd.z));
+                store_closest_result(a.hits, a.missSt, i, (int)f2u(ro.w), h, mk3(rd.x, rd.y, rd.z));
             }
         } else {
             const int stride = gridDim.x * blockDim.x;
-            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) store_anyhit_result(a.stC, (int)f2u(a.rayO[i].w), false);   // nothing can occlude
+            for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) store_anyhit_result(a.visSt, (int)f2u(a.rayO[i].w), false);   // nothing can occlude
         }
         return;
     }
@@ -178,13 +178,13 @@ __device__ __forceinline__ void extend_queue(const ExtendArgs& a, LaneStack& sta
         }
         if (active && tr.done) {
             // fire-and-forget stores, no path state is read here (same words as store_anyhit_result / store_closest_result)
-            if (ANY_HIT) __stcs(&a.stC[mySlot].w, tr.occluded ? 0.0f : 1.0f);   // visibility of the pending contribution: added to Li at the path's next touch
+            if (ANY_HIT) __stcs(&a.visSt[mySlot].c.w, tr.occluded ? 0.0f : 1.0f);   // visibility of the pending contribution: added to Li at the path's next touch
             else {
                 const HitRec h = tr.result();
                 const bool hit = h.t < 1e29f;
                 __stcs(a.hits.prim + myRay, hit ? h.prim : -1);
                 if (hit) __stcs(a.hits.tuv + myRay, make_float4(h.t, h.bu, h.bv, 0.0f));
-                else if (a.missD) __stcs(a.missD + mySlot, make_float4(tr.d.x, tr.d.y, tr.d.z, 0.0f));   // accumulate adds throughput * sky(d)
+                else if (a.missSt) __stcs(&a.missSt[mySlot].miss, make_float4(tr.d.x, tr.d.y, tr.d.z, 0.0f));   // accumulate adds throughput * sky(d)
             }
             active = false;
         }
@@ -594,7 +594,7 @@ struct rt_ctx {
     DevBuf<int> rgba8, objId; DevBuf<float> depth; DevBuf<float4> radiance, accum;
     // per path
     size_t pathCap = 0;
-    DevBuf<float4> stThr, stLi, stC, missD, qO[2], qD[2], shO, shD, hitTuv; DevBuf<int> hitPrim; DevBuf<uint32_t> pathHash;
+    DevBuf<PathState> pathState; DevBuf<float4> qO[2], qD[2], shO, shD, hitTuv; DevBuf<int> hitPrim; DevBuf<uint32_t> pathHash;
     // AOV outputs
     DevBuf<uint8_t> segOut, termOut; DevBuf<uint32_t> hashOut;
     // scratch for scattered read-backs
@@ -866,7 +866,7 @@ RT_API int rt_destroy(rt_ctx* c) {
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); for (int b = 0; b < 2; b++) { c->tileRadiance[b].release(); c->tileAux[b].release(); c->tileRgba[b].release(); } c->primId.release(); c->instId.release(); c->primaryT.release();
     c->rgba8.release(); c->objId.release(); c->depth.release(); c->radiance.release(); c->accum.release();
-    c->stThr.release(); c->stLi.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); } c->shO.release(); c->shD.release(); c->stC.release(); c->missD.release(); c->hitTuv.release();
+    c->pathState.release(); for (int b = 0; b < 2; b++) { c->qO[b].release(); c->qD[b].release(); } c->shO.release(); c->shD.release(); c->hitTuv.release();
     c->hitPrim.release(); c->pathHash.release(); c->segOut.release(); c->termOut.release(); c->hashOut.release(); c->scratch.release(); c->counters.release(); c->dstats.release(); c->deintMap.release();
     for (auto ev : c->traceEvents) cudaEventDestroy(ev);
     if (c->evStart) cudaEventDestroy(c->evStart);
@@ -880,6 +880,12 @@ RT_API int rt_destroy(rt_ctx* c) {
 RT_API int rt_set_stream(rt_ctx* c, void* s) {
     if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_set_stream: ctx is null");
     c->stream = s ? (cudaStream_t)s : c->ownStream;
+    return RT_OK;
+}
+
+RT_API int rt_get_stream(rt_ctx* c, void** s) {
+    if (!c || !s) return fail(RT_ERR_INVALID_ARGUMENT, "rt_get_stream: null argument");
+    *s = (void*)c->stream;
     return RT_OK;
 }
 
@@ -1025,9 +1031,9 @@ static int ensure_frame_buffers(rt_ctx* c, const RtRenderConfig* cfg, int S) {
     }
     const size_t P = std::max<size_t>(1, (size_t)c->npx * S);
     if (P > c->pathCap) {
-        CUDA_TRY(c->stThr.ensure(P)); CUDA_TRY(c->stLi.ensure(P));
+        CUDA_TRY(c->pathState.ensure(P));
         for (int b = 0; b < 2; b++) { CUDA_TRY(c->qO[b].ensure(P)); CUDA_TRY(c->qD[b].ensure(P)); }
-        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->stC.ensure(P)); CUDA_TRY(c->missD.ensure(P)); CUDA_TRY(c->hitTuv.ensure(P));
+        CUDA_TRY(c->shO.ensure(P)); CUDA_TRY(c->shD.ensure(P)); CUDA_TRY(c->hitTuv.ensure(P));
         CUDA_TRY(c->hitPrim.ensure((P + RT_SHADE_CHUNK - 1) / RT_SHADE_CHUNK * RT_SHADE_CHUNK));   // padded: k_shade_next scans whole chunks with 128-bit loads
         c->pathCap = P;
     }
@@ -1188,7 +1194,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     WaveBuffers wb; memset(&wb, 0, sizeof(wb));
     wb.gbPosHit = c->gbPosHit.p; wb.gbNrmMat = c->gbNrmMat.p; wb.gbAlbObj = c->gbAlbObj.p; wb.primId = c->primId.p; wb.instId = c->instId.p; wb.primaryT = c->primaryT.p;
     wb.lframe = c->lframe.p; wb.tileRadiance = c->tileRadiance[c->tileBuf].p; wb.tileAux = c->tileAux[c->tileBuf].p; wb.tileRgba = c->tileRgba[c->tileBuf].p; wb.rgba8 = c->rgba8.p; wb.depth = c->depth.p; wb.objId = c->objId.p; wb.radiance = c->radiance.p; wb.accum = c->accum.p;
-    wb.stThr = c->stThr.p; wb.stLi = c->stLi.p; wb.stC = c->stC.p; wb.missD = c->missD.p;
+    wb.st = c->pathState.p;
     if (reuse) {
         const size_t g = (size_t)cfg->width * cfg->height, P = c->resPathCap;
         float4* cur = c->resAB[cfg->frame & 1].p;
@@ -1215,7 +1221,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         rec.launch(k_generate_primary, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, q0, primaryCount); c->launches++;
         const HitQueue hq = {c->hitPrim.p, c->hitTuv.p};
         ExtendArgs ea; memset(&ea, 0, sizeof(ea));
-        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missD = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
+        ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missSt = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
         CUDA_TRY(launch_extend<false>(c, rec, ea, count));
         rec.launch(k_primary_finish, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, c->ds, wb, q0, hq); c->launches++;
         if (reuseDist) {   // every rank's G-buffer segment to every other rank (SpatialCompatible compares the CURRENT frame's G-buffer at both pixels)
@@ -1231,7 +1237,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
             int* sunCount = c->counters.p + 2;
             rec.launch(k_sun_generate, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, wb, shq, sunCount); c->launches++;
             ExtendArgs pa; memset(&pa, 0, sizeof(pa));
-            pa.sc = c->ds; pa.rayO = shq.o; pa.rayD = shq.d; pa.count = sunCount; pa.work = sunCount + 1; pa.stC = c->stC.p; pa.stats = c->dstats.p; pa.statSlot = 3;
+            pa.sc = c->ds; pa.rayO = shq.o; pa.rayD = shq.d; pa.count = sunCount; pa.work = sunCount + 1; pa.visSt = c->pathState.p; pa.stats = c->dstats.p; pa.statSlot = 3;
             CUDA_TRY(launch_extend<true>(c, rec, pa, count));
             rec.launch(k_sun_store, dim3(grid_for(c, npx, 256)), dim3(256), 0, wb, shq, (const int*)sunCount); c->launches++;
         }
@@ -1256,9 +1262,9 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 int* mine = ctr + (size_t)depth * CS;
                 RayQueue cq = {c->qO[cur].p, c->qD[cur].p};
                 ExtendArgs sa; memset(&sa, 0, sizeof(sa));
-                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.count = prev + 1; sa.work = prev + 3; sa.stC = c->stC.p; sa.stats = c->dstats.p; sa.statSlot = 2;
+                sa.sc = c->ds; sa.rayO = shq.o; sa.rayD = shq.d; sa.count = prev + 1; sa.work = prev + 3; sa.visSt = c->pathState.p; sa.stats = c->dstats.p; sa.statSlot = 2;
                 ExtendArgs ca; memset(&ca, 0, sizeof(ca));
-                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.count = prev + 0; ca.work = prev + 2; ca.hits = hq; ca.missD = c->missD.p; ca.stats = c->dstats.p; ca.statSlot = 1;
+                ca.sc = c->ds; ca.rayO = cq.o; ca.rayD = cq.d; ca.count = prev + 0; ca.work = prev + 2; ca.hits = hq; ca.missSt = c->pathState.p; ca.stats = c->dstats.p; ca.statSlot = 1;
                 CUDA_TRY(launch_extend_pair(c, rec, ca, sa, count));   // closest-hit and shadow rays of this depth in ONE persistent launch
                 RayQueue nq2 = {c->qO[cur ^ 1].p, c->qD[cur ^ 1].p};
                 // chunks of 4096 rays per block for big wavefronts; 1024 when that would leave SMs without a block (interactive frame sizes:

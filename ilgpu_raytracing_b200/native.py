@@ -20,7 +20,7 @@ EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
            "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex", "rt_download_async",
            "rt_comm_get_unique_id", "rt_comm_init", "rt_comm_destroy", "rt_gather_frame",
-           "rt_gl_register_buffer", "rt_gl_map", "rt_gl_unmap", "rt_gl_unregister"]
+           "rt_gl_register_buffer", "rt_gl_map", "rt_gl_unmap", "rt_gl_unregister", "rt_get_stream"]
 
 
 class RtError(RuntimeError):
@@ -40,11 +40,16 @@ def lib() -> C.CDLL:
         raise ImportError(f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a). The renderer core has no CPU or pure-Python fallback.")
     l = C.CDLL(_LIB_PATH)
+    if os.environ.get("RTCORE_B200_LIB"):   # A/B builds of older sources (tests/gpu_variants.py) may lack the newest entry points: give them inert stand-ins
+        for name in EXPORTS:
+            if not hasattr(l, name):
+                setattr(l, name, C.CFUNCTYPE(C.c_int)(lambda *a: L.RT_ERR_UNSUPPORTED))
     l.rt_abi_version.restype = C.c_int
     l.rt_last_error.restype = C.c_char_p
     l.rt_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
     l.rt_destroy.argtypes = [C.c_void_p]
     l.rt_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    l.rt_get_stream.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     l.rt_scene_upload.argtypes = [C.c_void_p, C.POINTER(L.RtSceneDesc)]
     l.rt_download_async.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     l.rt_scene_refit.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
@@ -110,6 +115,12 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr: int | None):
         check(self._l.rt_set_stream(self.h, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def stream_handle(self) -> int:
+        """The cudaStream_t the context renders on (rt_get_stream), e.g. for torch.cuda.ExternalStream."""
+        s = C.c_void_p()
+        check(self._l.rt_get_stream(self.h, C.byref(s)))
+        return s.value or 0
 
     def scene_upload(self, arrays: dict, device_build: bool = False):
         """rt_scene_upload; device_build=True builds the wide BVH on the GPU (rt_scene_upload_ex, RT_BUILD_DEVICE_LBVH)."""

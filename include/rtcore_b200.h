@@ -285,6 +285,9 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out); /* nDev must
 RT_API int rt_destroy(rt_ctx* ctx);
 /* Use a caller-owned cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
 RT_API int rt_set_stream(rt_ctx* ctx, void* cudaStream);
+/* The cudaStream_t the context currently renders on (its own unless rt_set_stream replaced it): for callers that order their own
+ * work or events against the frame (the reference shares one stream between its kernels and the PBO map, Engine/RTRenderer.cs:68,208). */
+RT_API int rt_get_stream(rt_ctx* ctx, void** cudaStream);
 
 /* ---- scene commit: replaces Scene.UploadAll (Engine/Scene.cs:258-279) reached through
  *      SceneManager.Commit -> BvhManager.BuildOrRefit (Engine/BvhManager.cs:27).

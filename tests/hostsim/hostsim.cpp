@@ -235,11 +235,12 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
         rq0.resize(P); rq1.resize(P); rq2.resize(P);
     }
 
-    std::vector<float4> gbPosHit(npx), gbNrmMat(npx), gbAlbObj(npx), lframe(npx), tileRad(npx), stThr(P), stLi(P);
+    std::vector<float4> gbPosHit(npx), gbNrmMat(npx), gbAlbObj(npx), lframe(npx), tileRad(npx);
     std::vector<int> primId(npx), instId(npx); std::vector<float> primaryT(npx);
     std::vector<uint32_t> pathHash(P);
     std::vector<float4> radiance((size_t)W * H), accum((size_t)W * H);
-    std::vector<float4> qo[2], qd[2], so(P), sd(P), stC(P), missD(P), hitTuv(P);
+    std::vector<float4> qo[2], qd[2], so(P), sd(P), hitTuv(P);
+    std::vector<PathState> pathState(P);
     for (int b = 0; b < 2; b++) { qo[b].resize(P); qd[b].resize(P); }
     std::vector<int> hitPrim(P);
     const HitQueue hq = {hitPrim.data(), hitTuv.data()};
@@ -250,7 +251,7 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
     wb.primId = primId.data(); wb.instId = instId.data(); wb.primaryT = primaryT.data(); wb.lframe = lframe.data(); wb.tileRadiance = tileRad.data();
     wb.rgba8 = out->rgba8 ? out->rgba8 : dummyI.data(); wb.depth = out->depth ? out->depth : dummyF.data(); wb.objId = out->objId ? out->objId : dummyI.data();
     wb.radiance = radiance.data(); wb.accum = out->accum4 ? (float4*)out->accum4 : accum.data();
-    wb.stThr = stThr.data(); wb.stLi = stLi.data(); wb.stC = stC.data(); wb.missD = missD.data();
+    wb.st = pathState.data();
     fc.lookPosHit = gbPosHit.data(); fc.lookNrmMat = gbNrmMat.data(); fc.lookAlbObj = gbAlbObj.data();
     const bool aov = (cfg->flags & RT_FLAG_PATH_AOVS) && out->segCount && out->termCode && out->pathHash;
     if (reuse) { wb.resPath0 = rq0.data(); wb.resPath1 = rq1.data(); wb.resPath2 = rq2.data(); wb.resCur0 = rc0.data(); wb.resCur1 = rc1.data(); wb.resCur2 = rc2.data(); }
@@ -279,11 +280,11 @@ HS_API int hs_render_reuse(HsScene* s, const RtCamera* cam, const RtCamera* prev
                 f3 o = mk3(shq.o[k].x, shq.o[k].y, shq.o[k].z), d = mk3(shq.d[k].x, shq.d[k].y, shq.d[k].z);
                 cap_ray(o, d, 1);
                 bool occ = trace_wide<true, true>(s->ds, o, d, 1e29f, st, nullptr, &tc); flushCnt();
-                store_anyhit_result(wb.stC, (int)f2u(shq.o[k].w), occ);   // settled at the path's next touch (shade_next / accumulate)
+                store_anyhit_result(wb.st, (int)f2u(shq.o[k].w), occ);   // settled at the path's next touch (shade_next / accumulate)
             }
             raysS += (uint64_t)nSh; g_capWave++;
             RayQueue cq = {qo[cur].data(), qd[cur].data()};
-            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); cap_ray(o, d, 0); HitRec h; trace_wide<false, true>(s->ds, o, d, 1e30f, st, &h, &tc); flushCnt(); store_closest_result(hq, wb.missD, k, (int)f2u(cq.o[k].w), h, d); }
+            for (int k = 0; k < nNext; k++) { f3 o = mk3(cq.o[k].x, cq.o[k].y, cq.o[k].z), d = mk3(cq.d[k].x, cq.d[k].y, cq.d[k].z); cap_ray(o, d, 0); HitRec h; trace_wide<false, true>(s->ds, o, d, 1e30f, st, &h, &tc); flushCnt(); store_closest_result(hq, wb.st, k, (int)f2u(cq.o[k].w), h, d); }
             g_capWave++;
             raysB += (uint64_t)nNext;
             const int nCur = nNext; nNext = 0; nSh = 0;
