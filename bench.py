@@ -594,6 +594,8 @@ def main():
     pin = [torch.empty(n_px, dtype=torch.int32).pin_memory(), torch.empty(n_px, dtype=torch.float32).pin_memory(), torch.empty(n_px, dtype=torch.int32).pin_memory()]
     pin_np = [p.numpy() for p in pin]
     e2e_frame = [0]
+    if rank == 0:   # a standing read-back order: every frame lands in the pinned arrays (depth / objectId overlap the frame, colour follows it)
+        rdr.BindCpuTargets(*pin_np)
 
     def e2e_step():
         # host camera + knobs in; rt_render; N > 1: rt_gather_frame (colour + depth + objectId to rank 0); present; Synchronize()

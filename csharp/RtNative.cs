@@ -107,6 +107,7 @@ namespace ILGPU_Raytracing.Engine
         [DllImport(Lib)] public static extern int rt_buffer_bytes(IntPtr ctx, int which, out UIntPtr bytes);
         [DllImport(Lib)] public static extern int rt_get_device_buffer(IntPtr ctx, int which, out IntPtr devPtr, out UIntPtr bytes);
         [DllImport(Lib)] public static extern int rt_map_external_color(IntPtr ctx, IntPtr devPtr, UIntPtr bytes);
+        [DllImport(Lib)] public static extern int rt_bind_readback(IntPtr ctx, int which, void* hostPinned, UIntPtr bytes);   // every frame -> page-locked host arrays, overlapped
         [DllImport(Lib)] public static extern int rt_present(IntPtr ctx, RtPresentConfig* cfg, IntPtr dstDevRgba8, UIntPtr dstBytes);
         [DllImport(Lib)] public static extern int rt_tiles_owned_pixels(int width, int height, int tileSize, int rank, int worldSize, out long nPixels);
         [DllImport(Lib)] public static extern int rt_deinterleave_tiles(IntPtr ctx, IntPtr gatheredDev, long* rankOffsetsPx, int worldSize, int width, int height, int tileSize, IntPtr outRadianceDev, IntPtr outRgba8Dev);

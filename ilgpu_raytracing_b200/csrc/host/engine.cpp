@@ -478,9 +478,16 @@ void Framebuffer::DownloadToCpu(int slot) {   // Framebuffer.cs:148-156
     check(rt_download(_native, bd, _cpuDepth.data(), nb));
     check(rt_download(_native, bo, _cpuObjectId.data(), nb));
 }
+void Framebuffer::BindCpuTargets(int* color, float* depth, int* objectId, size_t n) {
+    check(rt_bind_readback(_native, RT_BUF_RGBA8, color, n * 4));
+    check(rt_bind_readback(_native, RT_BUF_DEPTH, depth, n * 4));
+    check(rt_bind_readback(_native, RT_BUF_OBJID, objectId, n * 4));
+    _boundColor = color; _boundDepth = depth; _boundObjectId = objectId; _boundN = n;
+}
 void Framebuffer::DownloadToCpu(int slot, int* color, float* depth, int* objectId, size_t n) {
     if (slot != 0) throw ArgumentOutOfRangeException("slot");
     if (!color || !depth || !objectId) throw ArgumentNullException("destination");
+    if (color == _boundColor && depth == _boundDepth && objectId == _boundObjectId && n == _boundN) { check(rt_sync(_native)); return; }   // bound targets: the frame already copied them
     size_t nb = 0;
     const int bc = _gathered ? RT_BUF_GATHERED_RGBA8 : RT_BUF_RGBA8, bd = _gathered ? RT_BUF_GATHERED_DEPTH : RT_BUF_DEPTH, bo = _gathered ? RT_BUF_GATHERED_OBJID : RT_BUF_OBJID;
     check(rt_buffer_bytes(_native, bc, &nb));
@@ -630,6 +637,7 @@ ENG_API int eng_renderer_new_communicator_id(void* id128) { return guard([&] { R
 ENG_API int eng_renderer_init_multi_gpu(RTRenderer* r, const void* id128, int rank, int worldSize) { return guard([&] { r->InitMultiGpu(id128, rank, worldSize); }); }
 ENG_API int eng_renderer_render_direct_to_pbo(RTRenderer* r, void* pbo, int w, int h, int frame, float dt) { return guard([&] { r->RenderDirectToPbo(pbo, w, h, frame, dt); }); }
 ENG_API void eng_renderer_last_config(RTRenderer* r, RtRenderConfig* out) { *out = r->LastConfig(); }
+ENG_API int eng_framebuffer_bind_cpu_targets(RTRenderer* r, int* color, float* depth, int* objId, size_t n) { return guard([&] { r->Frame().BindCpuTargets(color, depth, objId, n); }); }
 ENG_API int eng_framebuffer_download_to_cpu(RTRenderer* r, int slot, int* color, float* depth, int* objId, size_t n) {
     return guard([&] {
         Framebuffer& f = r->Frame();

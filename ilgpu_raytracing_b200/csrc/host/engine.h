@@ -148,10 +148,14 @@ public:
     const std::vector<int>& CpuColor() const { return _cpuColor; }                              // :158
     const std::vector<float>& CpuDepth() const { return _cpuDepth; }                            // :159
     const std::vector<int>& CpuObjectId() const { return _cpuObjectId; }                        // :160
+    // Every frame straight into caller-owned page-locked arrays of n pixels each (rt_bind_readback): depth / objectId leave the device
+    // right after the primary pass, colour behind the frame; DownloadToCpu(slot, same arrays) then only waits.  nullptrs unbind.
+    void BindCpuTargets(int* color, float* depth, int* objectId, size_t n);
     void SetGathered(bool on) { _gathered = on; }   // multi-GPU: the frame lives in the image rt_gather_frame assembled (RT_BUF_GATHERED_*)
 private:
     rt_ctx* _native;
     bool _gathered = false;
+    int* _boundColor = nullptr; float* _boundDepth = nullptr; int* _boundObjectId = nullptr; size_t _boundN = 0;
     std::vector<int> _cpuColor, _cpuObjectId; std::vector<float> _cpuDepth;
 };
 

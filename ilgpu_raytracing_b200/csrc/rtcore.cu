@@ -623,6 +623,8 @@ struct rt_ctx {
     // ReSTIR reuse across the partition: every rank's G-buffer (exchanged after the primary pass) and the reservoir exchange buffer
     DevBuf<float4> gbAll, resPack; std::vector<int> deintHost;
     const float4 *gbPosPtr = nullptr, *gbNrmPtr = nullptr, *gbAlbPtr = nullptr;   // where the last frame's (own) G-buffer lives
+    // rt_bind_readback: page-locked host targets for RGBA8 / depth / objectId, filled by every frame on a copy stream
+    void* rbHost[3] = {nullptr, nullptr, nullptr}; size_t rbBytes[3] = {0, 0, 0}; cudaStream_t copyStream = nullptr; cudaEvent_t evPrimaryDone = nullptr, evCopyDone = nullptr; bool copyPending = false;
     cudaGraph_t frameGraph = nullptr;   // kept alive: the node handles used for per-frame parameter updates belong to it
     cudaGraphExec_t frameGraphExec = nullptr; unsigned long long frameGraphBuilds = 0, sceneVersion = 0;   // RT_FLAG_FRAME_GRAPH
     FrameKey frameKey; std::vector<cudaGraphNode_t> frameNodes; std::vector<const void*> frameFuncs;
@@ -862,6 +864,9 @@ RT_API int rt_destroy(rt_ctx* c) {
     rt_comm_destroy(c);
     if (c->frameGraphExec) { cudaGraphExecDestroy(c->frameGraphExec); c->frameGraphExec = nullptr; }
     if (c->frameGraph) { cudaGraphDestroy(c->frameGraph); c->frameGraph = nullptr; }
+    if (c->copyStream) { cudaStreamSynchronize(c->copyStream); cudaStreamDestroy(c->copyStream); c->copyStream = nullptr; }
+    if (c->evPrimaryDone) cudaEventDestroy(c->evPrimaryDone);
+    if (c->evCopyDone) cudaEventDestroy(c->evCopyDone);
     c->bvhBlob.release(); c->instances.release(); c->spheres.release(); c->texcoords.release(); c->triUVs.release(); c->triMat.release();
     c->materials.release(); c->texels.release(); c->texInfos.release(); c->presentBuf.release(); c->taaHistColor.release(); c->taaHistObj.release(); c->pixelMap.release(); c->invPixelMap.release(); c->resAB[0].release(); c->resAB[1].release(); c->resPath.release();
     c->gbPosHit.release(); c->gbNrmMat.release(); c->gbAlbObj.release(); c->lframe.release(); for (int b = 0; b < 2; b++) { c->tileRadiance[b].release(); c->tileAux[b].release(); c->tileRgba[b].release(); } c->primId.release(); c->instId.release(); c->primaryT.release();
@@ -1067,7 +1072,11 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     if (cfg->enableTemporalReuse != 0 && !prevCam) return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: enableTemporalReuse needs prevCam");
     if (c->extColor && c->extColorBytes < (size_t)cfg->width * cfg->height * sizeof(int))   // Framebuffer.GetGpuWithExternalColor's guard (Framebuffer.cs:117), before anything is queued
         return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: mapped external colour buffer is smaller than the image");
+    for (int b = 0; b < 3; b++)
+        if (c->rbHost[b] && c->rbBytes[b] != (size_t)cfg->width * cfg->height * 4)
+            return fail(RT_ERR_INVALID_ARGUMENT, "rt_render: a bound read-back target (rt_bind_readback) does not have the size of this frame's image");
     CUDA_TRY(cudaSetDevice(c->device));
+    if (c->copyPending) { CUDA_TRY(cudaStreamWaitEvent(c->stream, c->evCopyDone, 0)); c->copyPending = false; }   // the previous frame's bound read-backs still read depth / objectId
 
     const int spp = cfg->spp > 1 ? cfg->spp : 1;
     const int64_t npxOwned = count_owned_pixels(cfg->width, cfg->height, cfg->tileSize, cfg->worldSize > 1 ? cfg->rank : 0, cfg->worldSize > 1 ? cfg->worldSize : 1);
@@ -1158,6 +1167,10 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     key.width = cfg->width; key.height = cfg->height; key.spp = spp; key.S = S; key.maxDepth = cfg->maxDepth; key.worldSize = c->worldSize; key.rank = c->rank; key.tileSize = c->tileSize; key.npx = npx;
     key.structuralFlags = cfg->flags & (RT_FLAG_COUNTERS | RT_FLAG_FAST_SHADING | RT_FLAG_PATH_AOVS); key.reuse = reuse ? 1 : 0; key.sunProbe = sunProbe ? 1 : 0; key.extColor = c->extColor ? 1 : 0;
     key.counters = c->counters.p; key.dstats = c->dstats.p; key.hstats = c->hstats; key.bvh = c->bvhBlob.p; key.stream = st; key.nCounters = nCounters; key.pathCap = c->pathCap; key.sceneVersion = c->sceneVersion;
+    // bound read-backs: with plain launches on one GPU depth / objectId leave as soon as the primary pass is done; otherwise (frame graph,
+    // tile partition: the root's gathered image is what the host wants, see rt_gather_frame) everything is copied behind the frame
+    const bool anyReadback = c->rbHost[0] || c->rbHost[1] || c->rbHost[2];
+    const bool earlyReadback = anyReadback && !useGraph && c->worldSize <= 1 && (c->rbHost[1] || c->rbHost[2]);
     FrameRecorder rec; rec.st = st;
     if (c->l2Window > 0) { rec.l2Base = c->bvhBlob.p; rec.l2Bytes = c->l2Window; rec.l2Ratio = c->l2Persist >= c->l2Window ? 1.0f : (float)c->l2Persist / (float)c->l2Window; }
     if (useGraph) {
@@ -1224,6 +1237,15 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missSt = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
         CUDA_TRY(launch_extend<false>(c, rec, ea, count));
         rec.launch(k_primary_finish, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, c->ds, wb, q0, hq); c->launches++;
+        if (earlyReadback) {   // depth and objectId are final now: their read-back overlaps the rest of the frame (rt_bind_readback)
+            if (rec.err != cudaSuccess) return fail(RT_ERR_CUDA, std::string("frame launch: ") + cudaGetErrorString(rec.err));
+            CUDA_TRY(cudaEventRecord(c->evPrimaryDone, st));
+            CUDA_TRY(cudaStreamWaitEvent(c->copyStream, c->evPrimaryDone, 0));
+            if (c->rbHost[1]) CUDA_TRY(cudaMemcpyAsync(c->rbHost[1], c->depth.p, c->rbBytes[1], cudaMemcpyDeviceToHost, c->copyStream));
+            if (c->rbHost[2]) CUDA_TRY(cudaMemcpyAsync(c->rbHost[2], c->objId.p, c->rbBytes[2], cudaMemcpyDeviceToHost, c->copyStream));
+            CUDA_TRY(cudaEventRecord(c->evCopyDone, c->copyStream));
+            c->copyPending = true;
+        }
         if (reuseDist) {   // every rank's G-buffer segment to every other rank (SpatialCompatible compares the CURRENT frame's G-buffer at both pixels)
             const size_t g = (size_t)cfg->width * cfg->height;
             float4* arrays[3] = {c->gbAll.p, c->gbAll.p + g, c->gbAll.p + 2 * g};
@@ -1315,6 +1337,13 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         CUDA_TRY(cudaGraphLaunch(c->frameGraphExec, st));
     } else if (rcFrame != RT_OK) return rcFrame;
     CUDA_TRY(cudaEventRecord(c->evStop, st));
+    if (anyReadback && c->worldSize <= 1) {   // what is left of the bound read-backs, behind the frame on its own stream
+        if (c->rbHost[0]) CUDA_TRY(cudaMemcpyAsync(c->rbHost[0], c->rgba8.p, c->rbBytes[0], cudaMemcpyDeviceToHost, st));
+        if (!earlyReadback) {
+            if (c->rbHost[1]) CUDA_TRY(cudaMemcpyAsync(c->rbHost[1], c->depth.p, c->rbBytes[1], cudaMemcpyDeviceToHost, st));
+            if (c->rbHost[2]) CUDA_TRY(cudaMemcpyAsync(c->rbHost[2], c->objId.p, c->rbBytes[2], cudaMemcpyDeviceToHost, st));
+        }
+    }
 #if RT_PHASE_STATS
     if (count) {
         unsigned long long h[32], z[32] = {0};
@@ -1338,6 +1367,7 @@ RT_API int rt_sync(rt_ctx* c) {
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (c->commStream) CUDA_TRY(cudaStreamSynchronize(c->commStream));   // a gather (and a present of the gathered image) behind the frame
+    if (c->copyStream) CUDA_TRY(cudaStreamSynchronize(c->copyStream));   // bound read-backs (rt_bind_readback)
     return RT_OK;
 }
 
@@ -1465,6 +1495,23 @@ static int download_impl(rt_ctx* c, int which, void* dst, size_t bytes, bool wai
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
     if (wait) CUDA_TRY(cudaStreamSynchronize(st));
+    return RT_OK;
+}
+
+RT_API int rt_bind_readback(rt_ctx* c, int which, void* hostPinned, size_t bytes) {
+    if (!c) return fail(RT_ERR_INVALID_ARGUMENT, "rt_bind_readback: ctx is null");
+    if (which != RT_BUF_RGBA8 && which != RT_BUF_DEPTH && which != RT_BUF_OBJID) return fail(RT_ERR_INVALID_ARGUMENT, "rt_bind_readback: only RT_BUF_RGBA8, RT_BUF_DEPTH and RT_BUF_OBJID can be bound");
+    if (hostPinned && bytes == 0) return fail(RT_ERR_INVALID_ARGUMENT, "rt_bind_readback: zero-sized target");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // no frame in flight may still write the old target
+    if (c->copyStream) CUDA_TRY(cudaStreamSynchronize(c->copyStream));
+    if (c->commStream) CUDA_TRY(cudaStreamSynchronize(c->commStream));
+    if (hostPinned && !c->copyStream) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&c->evPrimaryDone, cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->evCopyDone, cudaEventDisableTiming));
+    }
+    const int slot = which == RT_BUF_RGBA8 ? 0 : (which == RT_BUF_DEPTH ? 1 : 2);
+    c->rbHost[slot] = hostPinned; c->rbBytes[slot] = hostPinned ? bytes : 0;
     return RT_OK;
 }
 
@@ -1691,6 +1738,10 @@ RT_API int rt_gather_frame(rt_ctx* c, int root, uint32_t what) {
         }
         CUDA_TRY(cudaGetLastError());
         c->gatheredValid = true; c->gatheredWhat = what;
+        // bound read-backs on the root: the GATHERED colour / depth / objectId, behind the scatter on the communicator's stream
+        if (c->rbHost[0] && c->rbBytes[0] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[0], c->gRgba8.p, g * 4, cudaMemcpyDeviceToHost, cs));
+        if (sendAux && c->rbHost[1] && c->rbBytes[1] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[1], c->gDepth.p, g * 4, cudaMemcpyDeviceToHost, cs));
+        if (sendAux && c->rbHost[2] && c->rbBytes[2] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[2], c->gObjId.p, g * 4, cudaMemcpyDeviceToHost, cs));
     }
     CUDA_TRY(cudaEventRecord(c->evGatherStop, cs));
     CUDA_TRY(cudaEventRecord(c->evGatherDone[b], cs));

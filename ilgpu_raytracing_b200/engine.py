@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     l.eng_renderer_new_communicator_id.argtypes = [C.c_void_p]
     l.eng_renderer_init_multi_gpu.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     l.eng_framebuffer_download_to_cpu.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    l.eng_framebuffer_bind_cpu_targets.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = l
     return l
 
@@ -347,6 +348,12 @@ class RTRenderer:
         cfg = L.RtRenderConfig()
         self._l.eng_renderer_last_config(self.h, C.byref(cfg))
         return cfg
+
+    def BindCpuTargets(self, color, depth, objid):
+        """Framebuffer.BindCpuTargets: every frame lands in these page-locked arrays (int32 / float32 / int32, one entry per traced pixel;
+        all None unbinds); DownloadToCpu(the same arrays) then only waits for the copies."""
+        n = 0 if color is None else color.size
+        _check(self._l.eng_framebuffer_bind_cpu_targets(self.h, _p(color), _p(depth), _p(objid), n))
 
     def DownloadToCpu(self, out_color=None, out_depth=None, out_objid=None):
         """Framebuffer.DownloadToCpu(0) + CpuColor / CpuDepth / CpuObjectId (Engine/Framebuffer.cs:148-160)."""

@@ -20,7 +20,7 @@ EXPORTS = ["rt_abi_version", "rt_last_error", "rt_create", "rt_destroy", "rt_set
            "rt_download", "rt_buffer_bytes", "rt_get_device_buffer", "rt_map_external_color", "rt_tiles_owned_pixels",
            "rt_deinterleave_tiles", "rt_get_stats", "rt_present", "rt_scene_refit", "rt_scene_upload_ex", "rt_download_async",
            "rt_comm_get_unique_id", "rt_comm_init", "rt_comm_destroy", "rt_gather_frame",
-           "rt_gl_register_buffer", "rt_gl_map", "rt_gl_unmap", "rt_gl_unregister", "rt_get_stream"]
+           "rt_gl_register_buffer", "rt_gl_map", "rt_gl_unmap", "rt_gl_unregister", "rt_get_stream", "rt_bind_readback"]
 
 
 class RtError(RuntimeError):
@@ -60,6 +60,7 @@ def lib() -> C.CDLL:
     l.rt_buffer_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_size_t)]
     l.rt_get_device_buffer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     l.rt_map_external_color.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    l.rt_bind_readback.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]
     l.rt_tiles_owned_pixels.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     l.rt_deinterleave_tiles.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     l.rt_get_stats.argtypes = [C.c_void_p, C.POINTER(L.RtStats)]
@@ -166,6 +167,14 @@ class Context:
         p, n = C.c_void_p(), C.c_size_t()
         check(self._l.rt_get_device_buffer(self.h, which, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def bind_readback(self, which: int, host: np.ndarray | None):
+        """rt_bind_readback: every frame copies RGBA8 / depth / objectId into `host` (page-locked, image-sized) as soon as it is final."""
+        if host is None:
+            check(self._l.rt_bind_readback(self.h, which, None, 0))
+        else:
+            assert host.flags.c_contiguous
+            check(self._l.rt_bind_readback(self.h, which, host.ctypes.data, host.nbytes))
 
     def map_external_color(self, dev_ptr: int | None, nbytes: int = 0):
         check(self._l.rt_map_external_color(self.h, C.c_void_p(dev_ptr or 0), nbytes))

@@ -323,6 +323,12 @@ RT_API int rt_download_async(rt_ctx* ctx, int which, void* dstHost, size_t bytes
 RT_API int rt_buffer_bytes(rt_ctx* ctx, int which, size_t* bytes);
 /* Device pointer of an output buffer (for NCCL / torch plumbing, no copy). */
 RT_API int rt_get_device_buffer(rt_ctx* ctx, int which, void** devPtr, size_t* bytes);
+/* Persistent read-back targets for hosts that want EVERY frame on the CPU (the pattern "RenderDirectToPbo; Framebuffer.DownloadToCpu",
+ * Engine/Framebuffer.cs:148-156, once per frame): `which` = RT_BUF_RGBA8, RT_BUF_DEPTH or RT_BUF_OBJID, hostPinned = a page-locked
+ * buffer of the image's size (NULL unbinds).  Every rt_render then copies the output as soon as it is final - depth and objectId right
+ * after the primary pass, on a copy stream, overlapping the rest of the frame; RGBA8 behind the frame - and rt_sync waits for the
+ * copies.  On the root of a tile partition rt_gather_frame fills the targets with the gathered image instead. */
+RT_API int rt_bind_readback(rt_ctx* ctx, int which, void* hostPinned, size_t bytes);
 /* Write packed RGBA8 into a caller-owned device buffer (CUDA-mapped PBO):
  * replaces Framebuffer.GetGpuWithExternalColor (Engine/Framebuffer.cs:112-124). NULL unmaps. */
 RT_API int rt_map_external_color(rt_ctx* ctx, void* devPtr, size_t bytes);

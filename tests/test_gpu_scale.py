@@ -224,3 +224,38 @@ def test_frame_graph_replays_the_same_frames(gpu_ctx):
             prev = cam.copy()
     finally:
         plain.close()
+
+
+def test_bound_readback_targets(gpu_ctx):
+    """rt_bind_readback / Framebuffer.BindCpuTargets: every frame lands in page-locked host arrays (depth / objectId copied right after
+    the primary pass on a copy stream, colour behind the frame); same bytes as rt_download, with plain launches and with the frame
+    graph; a target of the wrong size is refused before anything is queued; unbinding stops the copies."""
+    import torch
+    from ilgpu_raytracing_b200 import native
+    W, H = 256, 144
+    sc = orc.Scene()
+    sc.build_default()
+    gpu_ctx.scene_upload(sc.arrays())
+    cam = oracle_camera("C1B", W, H)
+    pins = [torch.zeros(W * H, dtype=torch.int32).pin_memory(), torch.zeros(W * H, dtype=torch.float32).pin_memory(), torch.zeros(W * H, dtype=torch.int32).pin_memory()]
+    arrs = [p.numpy() for p in pins]
+    try:
+        for which, a in zip((L.RT_BUF_RGBA8, L.RT_BUF_DEPTH, L.RT_BUF_OBJID), arrs):
+            gpu_ctx.bind_readback(which, a)
+        for frame, flags in enumerate((0, 0, L.RT_FLAG_FRAME_GRAPH, L.RT_FLAG_FRAME_GRAPH)):
+            for a in arrs:
+                a[:] = 0
+            gpu_ctx.render(cam, L.make_render_config(W, H, spp=2, max_depth=3, frame=frame, rng_lock_noise=0, flags=flags))
+            gpu_ctx.sync()
+            assert np.array_equal(arrs[0], gpu_ctx.download(L.RT_BUF_RGBA8)), f"frame {frame}"
+            assert np.array_equal(arrs[1], gpu_ctx.download(L.RT_BUF_DEPTH)) and np.array_equal(arrs[2], gpu_ctx.download(L.RT_BUF_OBJID))
+        with pytest.raises(native.RtError) as e:
+            gpu_ctx.render(cam, L.make_render_config(W + 8, H, spp=1, max_depth=1))     # the targets have another frame's size
+        assert e.value.status == L.RT_ERR_INVALID_ARGUMENT
+    finally:
+        for which in (L.RT_BUF_RGBA8, L.RT_BUF_DEPTH, L.RT_BUF_OBJID):
+            gpu_ctx.bind_readback(which, None)
+    arrs[0][:] = 7
+    gpu_ctx.render(cam, L.make_render_config(W, H, spp=1, max_depth=1))
+    gpu_ctx.sync()
+    assert np.all(arrs[0] == 7)

@@ -23,7 +23,7 @@ def _built():
 def test_abi_exports_match_header():
     hdr = open(os.path.join(ROOT, "include", "rtcore_b200.h")).read()
     declared = set(re.findall(r"RT_API\s+(?:const\s+)?\w+\*?\s+(\w+)\s*\(", hdr))
-    assert declared == set(native.EXPORTS) and len(declared) == 28
+    assert declared == set(native.EXPORTS) and len(declared) == 29
     lib = native.lib()
     for name in declared:
         assert getattr(lib, name) is not None
