@@ -207,10 +207,8 @@ __device__ __forceinline__ float box_area(const float* lo, const float* hi) {
 // One level of the collapse: wide nodes [first, last) each own the binary subtree workB2[w]; their internal children get the
 // next contiguous block of wide nodes (atomic counter: level order = breadth-first order), their leaf children the next block
 // of primitive records.
-__global__ void k_lbvh_collapse(int first, int last, int n, LbvhTree t, const int* vals, const float4* primBox, const PrimRec* primsIn,
-                                WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters /* [0] nodes, [1] prims */, int leafMax /* 1..3 primitives per leaf child */) {
-    const int w = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= last) return;
+__device__ __forceinline__ void lbvh_collapse_node(int w, const LbvhTree& t, const int* vals, const float4* primBox, const PrimRec* primsIn,
+                                                   WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters /* [0] nodes, [1] prims */, int leafMax /* 1..3 primitives per leaf child */) {
     const int root = workB2[w];
     int ch[8]; int nch = 2;
     ch[0] = t.left[root]; ch[1] = t.right[root];
@@ -282,6 +280,22 @@ __global__ void k_lbvh_collapse(int first, int last, int n, LbvhTree t, const in
     wn.n1 = make_uint4((uint32_t)childBase, (uint32_t)primBase, valid24, imr << 24);
     quantize_node(wn, imask, clo, chi, used, nlo, nhi);
     nodes[w] = wn;
+}
+// Level `level` of the collapse, with its range read from the DEVICE: levelStart[level] .. levelStart[level + 1] were written by the
+// previous level's launch; the last block of this launch to finish (ticket) publishes levelStart[level + 2] = nodes made so far.
+// The host queues one launch per possible level back to back and reads the level table once at the end: no host
+// synchronisation per tree level.  An empty level's launch exits at once.
+__global__ void __launch_bounds__(128) k_lbvh_collapse_level(int level, int* levelStart, unsigned* tickets, int n, LbvhTree t, const int* vals, const float4* primBox,
+                                                             const PrimRec* primsIn, WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters, int leafMax) {
+    const int first = levelStart[level], last = levelStart[level + 1];
+    for (int w = first + blockIdx.x * blockDim.x + threadIdx.x; w < last; w += gridDim.x * blockDim.x)
+        lbvh_collapse_node(w, t, vals, primBox, primsIn, nodes, primsOut, workB2, counters, leafMax);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&tickets[level], 1u) == gridDim.x - 1u) {
+        __threadfence();
+        levelStart[level + 2] = atomicAdd(&counters[0], 0);
+    }
 }
 
 }   // namespace rtx

@@ -174,84 +174,123 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
     }
     if (instOrder.size() > (size_t)PRIM_INST_MASK) { err = "too many instances"; return false; }
 
+    // (a) sequential and cheap: the BLAS walks themselves (SceneDeviceViews.cs:127-168 / :176-235, every box test taken) - one hop
+    // per node, no per-primitive work - yield the leaves in visiting order with the rank of their first primitive; (b) the
+    // per-primitive work (index validation, records, boxes) then runs on all host threads into pre-computed slots: the same
+    // records and the same ranks as a sequential pass, whatever the thread count.
+    struct InstInfo { int ii; bool ident, sph; double w2oInv[12]; };
+    struct LeafItem { int inst; int first, count; uint32_t rank; };
+    std::vector<InstInfo> infos(instOrder.size());
+    std::vector<LeafItem> leaves;
     uint32_t rank = 0;
     for (size_t io = 0; io < instOrder.size(); io++) {
         int ii = instOrder[io];
         const RtInstanceRecord& ir = d.instances[ii];
-        const bool ident = is_identity(ir);
+        InstInfo& info = infos[io];
+        info.ii = ii; info.ident = is_identity(ir);
         if (ir.uniformScale > out.stats.maxInstanceScale) out.stats.maxInstanceScale = ir.uniformScale;
-        double w2oInv[12];
-        if (!ident && !invert_affine(ir.worldToObject, w2oInv)) { err = "instance worldToObject is singular"; return false; }
-        if (!ident) for (int k = 0; k < 12; k++) out.instBoxXf[(size_t)ii * 12 + k] = w2oInv[k];
-        const bool sph = ir.type == RT_BLAS_SPHERESET;
-        if (!sph && ir.type != RT_BLAS_TRIMESH) { err = "instance: unknown BlasType"; return false; }
+        if (!info.ident && !invert_affine(ir.worldToObject, info.w2oInv)) { err = "instance worldToObject is singular"; return false; }
+        if (!info.ident) for (int k = 0; k < 12; k++) out.instBoxXf[(size_t)ii * 12 + k] = info.w2oInv[k];
+        info.sph = ir.type == RT_BLAS_SPHERESET;
+        if (!info.sph && ir.type != RT_BLAS_TRIMESH) { err = "instance: unknown BlasType"; return false; }
         int blasStart = ir.blasRoot, blasEnd = ir.blasRoot + ir.blasNodeCount;
         if (blasStart < 0 || blasEnd > d.nBlasNodes) { err = "instance: BLAS range outside blasNodes"; return false; }
-        // BLAS walk with every box test taken (SceneDeviceViews.cs:127-168 / :176-235)
         int cur = blasStart; int64_t guard = 0;
         while (cur != -1 && cur < blasEnd) {
             if (cur < blasStart || ++guard > 4 * (int64_t)ir.blasNodeCount + 8) { err = "blasNodes: bad link"; return false; }
             const RtBvhNode& n = d.blasNodes[cur];
             if (n.count > 0) {
-                for (int i = n.first; i < n.first + n.count; i++) {
+                const int64_t limit = info.sph ? d.nSpherePrimIdx : d.nTriPrimIdx;
+                if (n.first < 0 || (int64_t)n.first + n.count > limit) { err = info.sph ? "BLAS leaf range outside spherePrimIdx" : "BLAS leaf range outside triPrimIdx"; return false; }
+                if ((uint64_t)rank + (uint64_t)n.count > 0x7FFFFFFFull) { err = "too many primitives"; return false; }
+                leaves.push_back({(int)io, n.first, n.count, rank});
+                rank += (uint32_t)n.count;
+                cur = n.skipIndex;
+            } else cur = n.left;
+        }
+    }
+    B.prims.resize((size_t)rank);
+    {
+        const size_t nLeaves = leaves.size();
+        unsigned hw = std::thread::hardware_concurrency();
+        const size_t nThreads = (rank < (1u << 15)) ? 1 : std::max<size_t>(1, std::min<size_t>(hw ? hw : 4, 32));
+        std::vector<std::string> errs(nThreads); std::vector<size_t> errAt(nThreads, (size_t)-1);
+        std::vector<int64_t> nSph(nThreads, 0), nTri(nThreads, 0);
+        auto work = [&](size_t t) {
+            const size_t lo = nLeaves * t / nThreads, hi = nLeaves * (t + 1) / nThreads;
+            auto bad = [&](size_t li, const char* m) { if (errAt[t] == (size_t)-1) { errAt[t] = li; errs[t] = m; } };
+            for (size_t li = lo; li < hi && errAt[t] == (size_t)-1; li++) {
+                const LeafItem& L = leaves[li];
+                const InstInfo& info = infos[(size_t)L.inst];
+                const int ii = info.ii;
+                for (int i = L.first; i < L.first + L.count; i++) {
+                    const uint32_t rk = L.rank + (uint32_t)(i - L.first);
                     BuildPrim bp; memset(&bp, 0, sizeof(bp));
                     uint32_t meta = (uint32_t)ii;
-                    if (!ident) meta |= PRIM_XFORM;
+                    if (!info.ident) meta |= PRIM_XFORM;
                     float obb[2][3];
-                    if (sph) {
-                        if (i < 0 || i >= d.nSpherePrimIdx) { err = "BLAS leaf range outside spherePrimIdx"; return false; }
+                    if (info.sph) {
                         int prim = d.spherePrimIdx[i];
-                        if (prim < 0 || prim >= d.nSpheres) { err = "spherePrimIdx: bad sphere index"; return false; }
+                        if (prim < 0 || prim >= d.nSpheres) { bad(li, "spherePrimIdx: bad sphere index"); break; }
                         const RtSphere& s = d.spheres[prim];
                         meta |= PRIM_SPHERE;
                         bp.rec.q0 = make_float4(s.center.X, s.center.Y, s.center.Z, bitsf((uint32_t)prim));
-                        bp.rec.q1 = make_float4(s.radius, 0.0f, 0.0f, bitsf(rank));
+                        bp.rec.q1 = make_float4(s.radius, 0.0f, 0.0f, bitsf(rk));
                         bp.rec.q2 = make_float4(0.0f, 0.0f, 0.0f, bitsf(meta));
                         float r = std::fabs(s.radius);
                         obb[0][0] = s.center.X - r; obb[0][1] = s.center.Y - r; obb[0][2] = s.center.Z - r;
                         obb[1][0] = s.center.X + r; obb[1][1] = s.center.Y + r; obb[1][2] = s.center.Z + r;
-                        out.stats.nSpheres++;
+                        nSph[t]++;
                     } else {
-                        if (i < 0 || i >= d.nTriPrimIdx) { err = "BLAS leaf range outside triPrimIdx"; return false; }
                         int tri = d.triPrimIdx[i];
-                        if (tri < 0 || tri >= d.nMeshTris) { err = "triPrimIdx: bad triangle index"; return false; }
-                        const RtMeshTri& t = d.meshTris[tri];
-                        if (t.i0 < 0 || t.i1 < 0 || t.i2 < 0 || t.i0 >= d.nMeshPositions || t.i1 >= d.nMeshPositions || t.i2 >= d.nMeshPositions) { err = "meshTris: bad vertex index"; return false; }
-                        if (tri >= d.nTriMatIndex || tri >= d.nMeshTriUVs) { err = "triMatIndex/meshTriUVs shorter than meshTris"; return false; }
+                        if (tri < 0 || tri >= d.nMeshTris) { bad(li, "triPrimIdx: bad triangle index"); break; }
+                        const RtMeshTri& tr = d.meshTris[tri];
+                        if (tr.i0 < 0 || tr.i1 < 0 || tr.i2 < 0 || tr.i0 >= d.nMeshPositions || tr.i1 >= d.nMeshPositions || tr.i2 >= d.nMeshPositions) { bad(li, "meshTris: bad vertex index"); break; }
+                        if (tri >= d.nTriMatIndex || tri >= d.nMeshTriUVs) { bad(li, "triMatIndex/meshTriUVs shorter than meshTris"); break; }
                         int mi = d.triMatIndex[tri];
-                        if (mi < 0 || mi >= d.nMaterials) { err = "triMatIndex: bad material index"; return false; }
+                        if (mi < 0 || mi >= d.nMaterials) { bad(li, "triMatIndex: bad material index"); break; }
                         const RtMeshTriUV& tuv = d.meshTriUVs[tri];
-                        if (tuv.t0 < 0 || tuv.t1 < 0 || tuv.t2 < 0 || tuv.t0 >= d.nMeshTexcoords || tuv.t1 >= d.nMeshTexcoords || tuv.t2 >= d.nMeshTexcoords) { err = "meshTriUVs: bad texcoord index"; return false; }
+                        if (tuv.t0 < 0 || tuv.t1 < 0 || tuv.t2 < 0 || tuv.t0 >= d.nMeshTexcoords || tuv.t1 >= d.nMeshTexcoords || tuv.t2 >= d.nMeshTexcoords) { bad(li, "meshTriUVs: bad texcoord index"); break; }
                         const RtMaterialRecord& m = d.materials[mi];
                         int64_t nTexLen = d.nTexInfos > 0 ? d.nTexInfos : 1;   // AllocateOrEmpty (Scene.cs:370-377)
                         bool alphaMap = m.HasAlphaMap != 0 && m.AlphaTexIndex >= 0 && m.AlphaTexIndex < nTexLen;
                         if (alphaMap) meta |= PRIM_ALPHA;
                         else if (1.0f < m.AlphaCutoff) meta |= PRIM_NO_CLOSEST;
-                        const RtFloat3 &v0 = d.meshPositions[t.i0], &v1 = d.meshPositions[t.i1], &v2 = d.meshPositions[t.i2];
+                        const RtFloat3 &v0 = d.meshPositions[tr.i0], &v1 = d.meshPositions[tr.i1], &v2 = d.meshPositions[tr.i2];
                         bp.rec.q0 = make_float4(v0.X, v0.Y, v0.Z, bitsf((uint32_t)tri));
-                        bp.rec.q1 = make_float4(v1.X, v1.Y, v1.Z, bitsf(rank));
+                        bp.rec.q1 = make_float4(v1.X, v1.Y, v1.Z, bitsf(rk));
                         bp.rec.q2 = make_float4(v2.X, v2.Y, v2.Z, bitsf(meta));
                         obb[0][0] = std::min(v0.X, std::min(v1.X, v2.X)); obb[0][1] = std::min(v0.Y, std::min(v1.Y, v2.Y)); obb[0][2] = std::min(v0.Z, std::min(v1.Z, v2.Z));
                         obb[1][0] = std::max(v0.X, std::max(v1.X, v2.X)); obb[1][1] = std::max(v0.Y, std::max(v1.Y, v2.Y)); obb[1][2] = std::max(v0.Z, std::max(v1.Z, v2.Z));
-                        out.stats.nTris++;
+                        nTri[t]++;
                     }
-                    for (int a = 0; a < 3; a++) if (!std::isfinite(obb[0][a]) || !std::isfinite(obb[1][a])) { err = "non-finite primitive bounds"; return false; }
+                    bool finite = true;
+                    for (int a = 0; a < 3; a++) if (!std::isfinite(obb[0][a]) || !std::isfinite(obb[1][a])) finite = false;
+                    if (!finite) { bad(li, "non-finite primitive bounds"); break; }
                     bp.box.reset();
-                    if (ident) { bp.box.grow(obb[0]); bp.box.grow(obb[1]); }
+                    if (info.ident) { bp.box.grow(obb[0]); bp.box.grow(obb[1]); }
                     else {
                         for (int c = 0; c < 8; c++) {
                             double p[3] = {obb[c & 1][0], obb[(c >> 1) & 1][1], obb[(c >> 2) & 1][2]};
                             float w[3];
-                            for (int r = 0; r < 3; r++) w[r] = (float)(w2oInv[r * 4] * p[0] + w2oInv[r * 4 + 1] * p[1] + w2oInv[r * 4 + 2] * p[2] + w2oInv[r * 4 + 3]);
+                            for (int r = 0; r < 3; r++) w[r] = (float)(info.w2oInv[r * 4] * p[0] + info.w2oInv[r * 4 + 1] * p[1] + info.w2oInv[r * 4 + 2] * p[2] + info.w2oInv[r * 4 + 3]);
                             bp.box.grow(w);
                         }
                     }
-                    B.prims.push_back(bp);
-                    rank++;
+                    B.prims[rk] = bp;
                 }
-                cur = n.skipIndex;
-            } else cur = n.left;
+            }
+        };
+        if (nThreads == 1) work(0);
+        else {
+            std::vector<std::thread> pool;
+            for (size_t t = 1; t < nThreads; t++) { try { pool.emplace_back(work, t); } catch (...) { work(t); } }
+            work(0);
+            for (auto& th : pool) th.join();
         }
+        size_t firstBad = (size_t)-1, who = 0;
+        for (size_t t = 0; t < nThreads; t++) { out.stats.nSpheres += nSph[t]; out.stats.nTris += nTri[t]; if (errAt[t] < firstBad) { firstBad = errAt[t]; who = t; } }
+        if (firstBad != (size_t)-1) { err = errs[who]; return false; }   // the first offending leaf in visiting order, like a sequential pass
     }
     const int N = (int)B.prims.size();
     out.stats.nPrims = N;

@@ -249,7 +249,8 @@ __global__ void k_sun_store(WaveBuffers wb, ShadowQueue shq, const int* count) {
 
 // Queue slots for the rays of a block's 256 vertices: ballot per warp, an 8-entry scan in shared memory, ONE atomic per queue per
 // block (warp-level aggregation left the two queue counters as the hottest addresses of the frame: 33 M same-address atomics).
-// Called by every thread of the block (three barriers).
+// Called by every thread of the block; two barriers: `sm` is one of two 16-int halves the callers alternate between, so the next
+// call's counts never overwrite offsets a slow warp has not read yet.
 __device__ __forceinline__ void block_push(const VertexOut& vo, int path, const RayQueue& nextQ, int* nextCount, const ShadowQueue& shq, int* shCount, int* sm /* 16 ints */) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u), warp = (int)(threadIdx.x >> 5);
@@ -270,18 +271,17 @@ __device__ __forceinline__ void block_push(const VertexOut& vo, int path, const 
     __syncthreads();
     if (vo.pushNext) write_ray(nextQ.o, nextQ.d, sm[warp] + __popc(mN & ltMask), vo.next, path);
     if (vo.pushShadow) write_ray(shq.o, shq.d, sm[8 + warp] + __popc(mS & ltMask), vo.shadow, path);
-    __syncthreads();
 }
 
 template <bool REUSE, bool FAST>
 __global__ void __launch_bounds__(256) k_shade_first(FrameConst fc, WaveBuffers wb, int sampleBase, int nPaths, RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, DeviceStats* stats) {
-    __shared__ int smPush[16];
-    unsigned probed = 0;
+    __shared__ int smPush[32];
+    unsigned probed = 0, flip = 0;
     for (long long base = (long long)blockIdx.x * 256; base < nPaths; base += (long long)gridDim.x * 256) {
         const int j = (int)(base + threadIdx.x);
         VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
         if (j < nPaths) shade_first<REUSE, FAST>(fc, wb, sampleBase, j, nextQ, nextCount, shq, shCount, &probed, &vo);
-        block_push(vo, j, nextQ, nextCount, shq, shCount, smPush);
+        block_push(vo, j, nextQ, nextCount, shq, shCount, smPush + 16 * (flip++ & 1u));
     }
     for (int o = 16; o > 0; o >>= 1) probed += __shfl_xor_sync(0xFFFFFFFFu, probed, o);
     if ((threadIdx.x & 31u) == 0u && probed != 0u) atomicAdd(&stats->shadowProbed, (unsigned long long)probed);
@@ -309,7 +309,8 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
                                                    RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
     __shared__ int list[CHUNK];
     __shared__ int nFront, nBack;
-    __shared__ int smPush[16];
+    __shared__ int smPush[32];
+    unsigned flip = 0;
     const int n = *curCount;
     const int nChunks = (n + CHUNK - 1) / CHUNK;
     const unsigned FULL = 0xFFFFFFFFu;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
             VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
             int path = 0;
             if (k >= 0) shade_next<REUSE, FAST>(fc, sc, wb, depth, curQ, hits, k, nextQ, nextCount, shq, shCount, &vo, &path);
-            if (depth < fc.maxDepth) block_push(vo, path, nextQ, nextCount, shq, shCount, smPush);   // the last depth queues nothing
+            if (depth < fc.maxDepth) block_push(vo, path, nextQ, nextCount, shq, shCount, smPush + 16 * (flip++ & 1u));   // the last depth queues nothing
         }
         __syncthreads();
     }
@@ -729,18 +730,29 @@ static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, DevBuf<WideNode
     BTRY(cudaMemsetAsync(workB2, 0, sizeof(int), st));   // wide node 0 owns binary node 0
     int leafMax = 2;   // primitives per leaf child; sweep on C4 (RT_LBVH_LEAF): 1 / 2 / 3 -> 22.5 / 22.2 / 29.1 ms of traversal (host SAH tree: 19.7)
     if (c->envLbvhLeaf) leafMax = c->envLbvhLeaf;
+    // one launch per POSSIBLE level, queued back to back: every launch reads its range from the device-side level table the previous
+    // one completed (k_lbvh_collapse_level), so the host waits once, at the end, for the whole tree
+    const int maxLevels = RT_STACK_ENTRIES - 2;
+    DevBuf<int> dLevel; DevBuf<unsigned> dTickets;
+    BTRY(dLevel.ensure((size_t)maxLevels + 2)); BTRY(dTickets.ensure((size_t)maxLevels));
+    std::vector<int> hLevel((size_t)maxLevels + 2, 0); hLevel[1] = 1;
+    BTRY(cudaMemcpyAsync(dLevel.p, hLevel.data(), hLevel.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    BTRY(cudaMemsetAsync(dTickets.p, 0, (size_t)maxLevels * sizeof(unsigned), st));
+    const int collapseGrid = std::max(1, std::min((n + 127) / 128, c->smCount * 16));
+    for (int level = 0; level < maxLevels; level++)
+        k_lbvh_collapse_level<<<collapseGrid, 128, 0, st>>>(level, dLevel.p, dTickets.p, n, t, vals2.p, primBox.p, primsIn.p, dNodes.p, dPrims.p, workB2, counters.p, leafMax);
+    BTRY(cudaGetLastError());
+    BTRY(cudaMemcpyAsync(hLevel.data(), dLevel.p, hLevel.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BTRY(cudaStreamSynchronize(st));
     levelStart.assign(1, 0);
-    int first = 0, last = 1;
+    int last = 1;
     *tooDeep = false;
-    while (first < last) {
-        if ((int)levelStart.size() > RT_STACK_ENTRIES - 2) { *tooDeep = true; break; }
-        k_lbvh_collapse<<<(last - first + 127) / 128, 128, 0, st>>>(first, last, n, t, vals2.p, primBox.p, primsIn.p, dNodes.p, dPrims.p, workB2, counters.p, leafMax);
-        int cnt[2];
-        BTRY(cudaMemcpyAsync(cnt, counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, st));
-        BTRY(cudaStreamSynchronize(st));
-        levelStart.push_back(last);
-        first = last; last = cnt[0];
+    for (int level = 0; level < maxLevels; level++) {
+        if (hLevel[(size_t)level + 1] <= hLevel[(size_t)level]) break;   // an empty level: the tree ended above it
+        levelStart.push_back(hLevel[(size_t)level + 1]);
+        last = hLevel[(size_t)level + 1];
     }
+    if (hLevel[(size_t)maxLevels + 1] > hLevel[(size_t)maxLevels]) *tooDeep = true;   // the last possible level still made children
     BTRY(cudaGetLastError());
     BTRY(cudaStreamSynchronize(st));
     *nNodesOut = last;
