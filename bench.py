@@ -88,13 +88,17 @@ RAY_RECORD_BYTES = 32   # what k_extend reads per ray: origin | slot, direction 
 
 
 def csrc_hash() -> str:
-    """sha256 over the kernel sources (csrc/*.cu, *.h, *.cpp, host/ excluded): ties an ncu capture to the code it profiled."""
-    import glob
+    """sha256 over the DEVICE code: the headers the kernels are made of and rtcore.cu down to its "host side" marker (the C ABI and
+    launch plumbing below it do not change what a kernel executes).  Ties an ncu capture to the kernels it profiled."""
     import hashlib
     h = hashlib.sha256()
     base = os.path.join(ROOT, "ilgpu_raytracing_b200", "csrc")
-    for f in sorted(glob.glob(os.path.join(base, "*.cu")) + glob.glob(os.path.join(base, "*.h")) + glob.glob(os.path.join(base, "*.cpp"))):
-        h.update(os.path.basename(f).encode()); h.update(open(f, "rb").read())
+    for name in ("rt_core.h", "rt_traverse.h", "rt_wavefront.h", "rt_tiles.h", "rt_build.h"):
+        h.update(name.encode()); h.update(open(os.path.join(base, name), "rb").read())
+    src = open(os.path.join(base, "rtcore.cu"), "rb").read()
+    marker = b"// ------------------------------------------------------------------------------------------------ host side"
+    cut = src.find(marker)
+    h.update(b"rtcore.cu[kernels]"); h.update(src if cut < 0 else src[:cut])
     return h.hexdigest()[:16]
 
 

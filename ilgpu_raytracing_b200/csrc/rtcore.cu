@@ -1099,7 +1099,9 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         // runs its 64 spp (531 M paths, 96 GB) in ONE pass - 191.2 ms against 193.1 ms in two passes of 32 spp, 197.8 ms in four,
         // 230 ms with 16 Mi-path passes (launch tails of the deep, nearly empty wavefronts)
         int64_t target = std::min<int64_t>(768ll << 20, (int64_t)(c->memTotal / 10 * 6 / RT_PATH_BYTES));
-        if ((size_t)target > c->pathCap) {   // the buffers would have to grow: never beyond 85 % of what is free right now (plus what they already hold)
+        // only a frame whose paths do not fit the buffers already there asks the driver how much is free (cudaMemGetInfo costs ~1 ms:
+        // more than a whole interactive frame): the buffers then grow to at most 85 % of what is free right now (plus what they hold)
+        if ((size_t)std::min<int64_t>(target, npxOwned * (int64_t)spp) > c->pathCap) {
             size_t freeB = 0, totalB = 0;
             if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess) target = std::min<int64_t>(target, (int64_t)((freeB / 100 * 85 + c->pathCap * RT_PATH_BYTES) / RT_PATH_BYTES));
             else (void)cudaGetLastError();
