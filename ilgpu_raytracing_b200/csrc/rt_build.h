@@ -4,12 +4,14 @@
 //   refit : new vertex positions for the SAME topology.  The tree keeps its shape; k_refit_prims rewrites the triangle
 //           records and recomputes every primitive box, k_refit_nodes recomputes child boxes / quantisation frames level
 //           by level from the leaves up.
-//   build : the tree itself on the device - Morton codes of the primitive centroids, radix sort (CUB), the binary radix
-//           tree of Karras (HPG 2012), bottom-up boxes, then a level-synchronous greedy collapse to 8-wide nodes (largest
-//           surface area first, subtrees of <= 3 primitives become leaf children) with the octant slot assignment of the host
-//           builder.  ~10x faster than the host's binned-SAH + optimal-collapse build and a worse tree (measured: DESIGN.md);
-//           the primitive stage (validation of every index, the reference's visiting-order ranks, records, padded boxes)
-//           stays on the host (rt_bvh.cpp sections 1-2) because it walks the reference's skip-link arrays sequentially.
+//   build : the tree itself on the device - Morton codes of the primitive centroids (cubic cells), radix sort (CUB), then TWO
+//           binary trees over that order: the radix tree of Karras (HPG 2012) with bottom-up boxes, and PLOC (Meister & Bittner
+//           2018).  Every binary node carries the table of the SAH-optimal 8-wide collapse (the dynamic program of the host
+//           builder, evaluated as the node is made), the tree whose collapsed cost is lower is kept, and a level-synchronous
+//           pass writes the wide nodes the tables chose (leaf children of <= 3 primitives) with the octant slot assignment of
+//           the host builder.  The primitive stage (validation of every index, the reference's visiting-order ranks, records,
+//           padded boxes) stays on the host (rt_bvh.cpp sections 1-2, all threads) because it starts from a sequential walk of
+//           the reference's skip-link arrays.  Measured against the host's binned-SAH tree: DESIGN.md.
 // Both write nodes with quantize_node(): the formulas of rt_bvh.cpp section 4, so a device-written node is exactly as
 // conservative as a host-written one.  Included by rtcore.cu only.
 #pragma once
@@ -125,11 +127,55 @@ __global__ void k_refit_nodes(WideNode* nodes, int first, int last, const float4
 // Binary radix tree over the Morton-sorted primitives: internal nodes 0 .. n-2, leaves 0 .. n-1 (sorted order).
 // A child reference is >= 0 for an internal node and ~leaf for a leaf.
 struct LbvhTree {
-    int* left; int* right; int* parent;      // parent[] has 2n - 1 entries: internal nodes first, then the leaves
-    int* first; int* last;                   // sorted-order range of every internal node
+    int* left; int* right;                   // children of every internal node
+    int* count;                              // primitives below every internal node
     float4* box;                             // 2 float4 per internal node
-    int* visits;                             // bottom-up arrival counters
+    int* parent;                             // radix tree only: 2n - 1 entries, internal nodes first, then the leaves
+    int* visits;                             // radix tree only: bottom-up arrival counters
+    float4* dp;                              // per internal node 2 float4: C(n, 1..7) and the packed decisions (lbvh_dp_node)
+    float cPrim;                             // cost of one exact primitive test relative to one wide-node step (rt_bvh.cpp section 4)
 };
+__device__ __forceinline__ int lbvh_count(const LbvhTree& t, int ref) { return ref < 0 ? 1 : t.count[ref]; }
+// the (<= 3) leaves below ref, left to right
+__device__ __forceinline__ int lbvh_leaves(const LbvhTree& t, int ref, int* out) {
+    int n = 0, st[4], sp = 0;
+    st[sp++] = ref;
+    while (sp) { const int r = st[--sp]; if (r < 0) out[n++] = ~r; else { st[sp++] = t.right[r]; st[sp++] = t.left[r]; } }
+    return n;
+}
+
+__device__ __forceinline__ float box_area4(float4 lo, float4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return (dx < 0.0f || dy < 0.0f || dz < 0.0f) ? 0.0f : 2.0f * (dx * dy + dy * dz + dz * dx);
+}
+// SAH-optimal collapse to 8-wide, the dynamic program of Ylitie, Karras & Laine (HPG 2017, section 4.1) as the host builder runs
+// it (rt_bvh.cpp section 4), evaluated the moment a binary node is made - its children's tables are complete by then:
+//   C(n,1) = min(C_leaf(n), C_internal(n)),  C_internal(n) = A_n + min_k C(left,k) + C(right,8-k),  C_leaf(n) = A_n P_n c_prim if P_n <= 3
+//   C(n,i) = min(C(n,i-1), min_k C(left,k) + C(right,i-k)),  i = 2..7;   a single primitive: C(n,i) = A_n c_prim
+// Decisions: 4 bits per i (0 = "leaf child" for i = 1 / "as with i - 1 slots" for i > 1, else the left subtree's share k);
+// bits 28-30 keep the best k of C_internal even when the leaf won (a root of <= 3 primitives is opened all the same).
+__device__ __forceinline__ void lbvh_dp_load(const LbvhTree& t, int ref, float area, float* C) {
+    if (ref < 0) { for (int i = 0; i < 7; i++) C[i] = area * t.cPrim; return; }
+    const float4 a = t.dp[2 * ref], b = t.dp[2 * ref + 1];
+    C[0] = a.x; C[1] = a.y; C[2] = a.z; C[3] = a.w; C[4] = b.x; C[5] = b.y; C[6] = b.z;
+}
+__device__ __forceinline__ uint32_t lbvh_dp_decisions(const LbvhTree& t, int ref) { return __float_as_uint(t.dp[2 * ref + 1].w); }
+__device__ __forceinline__ void lbvh_dp_node(const LbvhTree& t, int id, int refL, float areaL, int refR, float areaR, float areaN, int count) {
+    float CL[7], CR[7], Cn[7];
+    lbvh_dp_load(t, refL, areaL, CL); lbvh_dp_load(t, refR, areaR, CR);
+    float best = 3.4e38f; int bk = 1;
+    for (int k = 1; k <= 7; k++) { const float c = CL[k - 1] + CR[7 - k]; if (c < best) { best = c; bk = k; } }
+    const float cInt = best + areaN, cLeaf = count <= 3 ? areaN * (float)count * t.cPrim : 3.4e38f;
+    uint32_t D = (uint32_t)bk << 28;
+    if (cLeaf <= cInt) Cn[0] = cLeaf; else { Cn[0] = cInt; D |= (uint32_t)bk; }
+    for (int i = 2; i <= 7; i++) {
+        float bi = Cn[i - 2]; int d = 0;
+        for (int k = 1; k < i; k++) { const float c = CL[k - 1] + CR[i - k - 1]; if (c < bi) { bi = c; d = k; } }
+        Cn[i - 1] = bi; D |= (uint32_t)d << (4 * (i - 1));
+    }
+    t.dp[2 * id] = make_float4(Cn[0], Cn[1], Cn[2], Cn[3]);
+    t.dp[2 * id + 1] = make_float4(Cn[4], Cn[5], Cn[6], __uint_as_float(D));
+}
 
 __device__ __forceinline__ uint64_t morton_spread21(uint64_t v) {   // 21 bits -> every third bit
     v &= 0x1FFFFFull;
@@ -175,7 +221,7 @@ __global__ void k_lbvh_tree(const uint64_t* keys, int n, LbvhTree t) {   // Karr
     const int gamma = i + sp * d + min(d, 0);
     const int lo = min(i, j), hi = max(i, j);
     const int lc = lo == gamma ? ~gamma : gamma, rc = hi == gamma + 1 ? ~(gamma + 1) : gamma + 1;
-    t.left[i] = lc; t.right[i] = rc; t.first[i] = lo; t.last[i] = hi;
+    t.left[i] = lc; t.right[i] = rc; t.count[i] = hi - lo + 1;
     t.parent[lc >= 0 ? lc : (n - 1) + ~lc] = i;
     t.parent[rc >= 0 ? rc : (n - 1) + ~rc] = i;
     if (i == 0) t.parent[0] = -1;
@@ -196,45 +242,179 @@ __global__ void k_lbvh_boxes(const int* vals, const float4* primBox, int n, Lbvh
             lo.x = fminf(lo.x, l.x); lo.y = fminf(lo.y, l.y); lo.z = fminf(lo.z, l.z); hi.x = fmaxf(hi.x, h.x); hi.y = fmaxf(hi.y, h.y); hi.z = fmaxf(hi.z, h.z);
         }
         __stcg(&t.box[2 * cur], lo); __stcg(&t.box[2 * cur + 1], hi);
+        {
+            float4 bl[2], bh[2];
+            for (int k = 0; k < 2; k++) {
+                if (ch[k] >= 0) { bl[k] = __ldcg(&t.box[2 * ch[k]]); bh[k] = __ldcg(&t.box[2 * ch[k] + 1]); }
+                else { const int p = vals[~ch[k]]; bl[k] = primBox[2 * p]; bh[k] = primBox[2 * p + 1]; }
+            }
+            lbvh_dp_node(t, cur, ch[0], box_area4(bl[0], bh[0]), ch[1], box_area4(bl[1], bh[1]), box_area4(lo, hi), t.count[cur]);
+        }
         __threadfence();
         cur = t.parent[cur];
     }
 }
-__device__ __forceinline__ float box_area(const float* lo, const float* hi) {
-    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-    return (dx < 0.0f || dy < 0.0f || dz < 0.0f) ? 0.0f : 2.0f * (dx * dy + dy * dz + dz * dx);
+// ---- PLOC: parallel locally-ordered clustering (Meister & Bittner, TVCG 2018) over the Morton-sorted primitives ----
+// Clusters live in Morton order.  One iteration: every cluster looks RT_PLOC_RADIUS places to either side for the neighbour whose
+// union with it has the smallest surface area; two clusters that chose EACH OTHER merge into a new binary node, which takes the
+// place of the left one; the survivors are compacted in order.  The merge key is (area, i xor j): symmetric in the pair and
+// unique per neighbour, so the globally smallest key is always a mutual choice (every iteration merges at least one pair) and
+// runs of identical boxes pair up (i, i ^ 1) instead of forming a chain that merges one pair per iteration.
+// No host round trip per iteration: the cluster count lives on the device (nc[iteration parity]), every launch is sized for the
+// first iteration and idles through what is no longer there; the host reads the count once per batch of iterations.
+#define RT_PLOC_TILE 256
+#define RT_PLOC_RADIUS 8   // measured 8 / 16 / 32 / 64 on the C4 height field and on a debris field: the collapsed SAH cost is lowest at 8 on both
+#define RT_PLOC_GONE ((int)0x80000000)
+struct PlocState {
+    int* cid; float4* cbox;        // clusters of this iteration: node reference (>= 0 internal, ~k = the k-th sorted primitive) and box
+    int* tcid; float4* tbox;       // the same after the merge step, in place (RT_PLOC_GONE = merged into its left partner)
+    int* tileCount; int* tileOffset;
+    int* nc;                       // nc[2]: cluster count by iteration parity
+    int* nodeCounter;
+};
+__global__ void k_ploc_init(const int* vals, const float4* primBox, int n, PlocState S) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int p = vals[k];
+    S.cid[k] = ~k; S.cbox[2 * k] = primBox[2 * p]; S.cbox[2 * k + 1] = primBox[2 * p + 1];
 }
+__global__ void __launch_bounds__(RT_PLOC_TILE) k_ploc_merge(int parity, PlocState S, LbvhTree t) {
+    constexpr int R = RT_PLOC_RADIUS, T = RT_PLOC_TILE;
+    __shared__ float4 slo[T + 4 * R], shi[T + 4 * R];
+    __shared__ int snn[T + 2 * R];
+    const int nc = S.nc[parity];
+    const int tiles = (nc + T - 1) / T;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int t0 = tile * T;
+        for (int k = threadIdx.x; k < T + 4 * R; k += T) {
+            const int g = t0 - 2 * R + k;
+            if (g >= 0 && g < nc) { slo[k] = S.cbox[2 * g]; shi[k] = S.cbox[2 * g + 1]; }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < T + 2 * R; k += T) {   // nearest neighbour of the tile's clusters and of R more on either side
+            const int g = t0 - R + k;
+            int nn = -1;
+            if (g >= 0 && g < nc) {
+                const float4 al = slo[k + R], ah = shi[k + R];
+                unsigned long long best = ~0ull;
+                for (int dj = -R; dj <= R; dj++) {
+                    const int j = g + dj;
+                    if (dj == 0 || j < 0 || j >= nc) continue;
+                    const float4 bl = slo[k + R + dj], bh = shi[k + R + dj];
+                    const float dx = fmaxf(ah.x, bh.x) - fminf(al.x, bl.x), dy = fmaxf(ah.y, bh.y) - fminf(al.y, bl.y), dz = fmaxf(ah.z, bh.z) - fminf(al.z, bl.z);
+                    const float area = dx * dy + dy * dz + dz * dx;   // >= 0: orders like its bit pattern
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(area) << 32) | (unsigned)(g ^ j);
+                    if (key < best) { best = key; nn = j; }
+                }
+            }
+            snn[k] = nn;
+        }
+        __syncthreads();
+        const int i = t0 + (int)threadIdx.x;
+        bool keep = false;
+        if (i < nc) {
+            const int j = snn[threadIdx.x + R];
+            const bool mutual = j >= 0 && snn[j - t0 + R] == i;
+            int ref = S.cid[i];
+            float4 lo = slo[threadIdx.x + 2 * R], hi = shi[threadIdx.x + 2 * R];
+            keep = !mutual || i < j;
+            if (mutual && i < j) {
+                const int other = S.cid[j];
+                const float4 bl = slo[j - t0 + 2 * R], bh = shi[j - t0 + 2 * R];
+                lo = make_float4(fminf(lo.x, bl.x), fminf(lo.y, bl.y), fminf(lo.z, bl.z), 0.0f);
+                hi = make_float4(fmaxf(hi.x, bh.x), fmaxf(hi.y, bh.y), fmaxf(hi.z, bh.z), 0.0f);
+                const int id = atomicAdd(S.nodeCounter, 1);
+                t.left[id] = ref; t.right[id] = other; t.count[id] = lbvh_count(t, ref) + lbvh_count(t, other);
+                t.box[2 * id] = lo; t.box[2 * id + 1] = hi;
+                lbvh_dp_node(t, id, ref, box_area4(slo[threadIdx.x + 2 * R], shi[threadIdx.x + 2 * R]), other, box_area4(bl, bh), box_area4(lo, hi), t.count[id]);
+                ref = id;
+            }
+            S.tcid[i] = keep ? ref : RT_PLOC_GONE;
+            if (keep) { S.tbox[2 * i] = lo; S.tbox[2 * i + 1] = hi; }
+        }
+        const int cnt = __syncthreads_count(keep);   // also fences the shared arrays before the next tile
+        if (threadIdx.x == 0) S.tileCount[tile] = cnt;
+    }
+}
+__global__ void __launch_bounds__(1024) k_ploc_scan(int parity, PlocState S) {   // one block: tile offsets and the next cluster count
+    __shared__ int warpSum[32];
+    __shared__ int carry;
+    const int nc = S.nc[parity];
+    const int tiles = (nc + RT_PLOC_TILE - 1) / RT_PLOC_TILE;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 1024) {
+        const int k = base + (int)threadIdx.x;
+        const int v = k < tiles ? S.tileCount[k] : 0;
+        int incl = v;
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((threadIdx.x & 31) >= (unsigned)o) incl += u; }
+        if ((threadIdx.x & 31) == 31) warpSum[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = warpSum[threadIdx.x], wi = w;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xFFFFFFFFu, wi, o); if (threadIdx.x >= (unsigned)o) wi += u; }
+            warpSum[threadIdx.x] = wi - w;   // exclusive
+        }
+        __syncthreads();
+        const int excl = carry + warpSum[threadIdx.x >> 5] + incl - v;
+        if (k < tiles) S.tileOffset[k] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) S.nc[parity ^ 1] = tiles ? carry : nc;
+}
+__global__ void __launch_bounds__(RT_PLOC_TILE) k_ploc_scatter(int parity, PlocState S) {
+    __shared__ int warpBase[RT_PLOC_TILE / 32];
+    const int nc = S.nc[parity];
+    const int tiles = (nc + RT_PLOC_TILE - 1) / RT_PLOC_TILE;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int i = tile * RT_PLOC_TILE + (int)threadIdx.x;
+        const int ref = i < nc ? S.tcid[i] : RT_PLOC_GONE;
+        const bool keep = ref != RT_PLOC_GONE;
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, keep);
+        if ((threadIdx.x & 31) == 0) warpBase[threadIdx.x >> 5] = __popc(b);
+        __syncthreads();
+        int base = S.tileOffset[tile];
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) base += warpBase[w];
+        if (keep) {
+            const int pos = base + __popc(b & ((1u << (threadIdx.x & 31)) - 1u));
+            S.cid[pos] = ref; S.cbox[2 * pos] = S.tbox[2 * i]; S.cbox[2 * pos + 1] = S.tbox[2 * i + 1];
+        }
+        __syncthreads();
+    }
+}
+
 // One level of the collapse: wide nodes [first, last) each own the binary subtree workB2[w]; their internal children get the
 // next contiguous block of wide nodes (atomic counter: level order = breadth-first order), their leaf children the next block
 // of primitive records.
 __device__ __forceinline__ void lbvh_collapse_node(int w, const LbvhTree& t, const int* vals, const float4* primBox, const PrimRec* primsIn,
-                                                   WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters /* [0] nodes, [1] prims */, int leafMax /* 1..3 primitives per leaf child */) {
+                                                   WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters /* [0] nodes, [1] prims */) {
     const int root = workB2[w];
-    int ch[8]; int nch = 2;
-    ch[0] = t.left[root]; ch[1] = t.right[root];
-    // greedy: open the child of largest area while there is room - first the subtrees that must become internal children
-    // (> 3 primitives), then, with the slots that are left, the small subtrees (2-3 primitives): tighter leaf boxes for free
-    for (int pass = 0; pass < 2; pass++)
-        while (nch < 8) {
-            int best = -1; float bestA = -1.0f;
-            for (int c = 0; c < nch; c++) {
-                if (ch[c] < 0) continue;   // a single primitive
-                const int cnt = t.last[ch[c]] - t.first[ch[c]] + 1;
-                if (pass == 0 ? cnt <= leafMax : cnt > leafMax) continue;
-                const float4 l = t.box[2 * ch[c]], h = t.box[2 * ch[c] + 1];
-                const float lo3[3] = {l.x, l.y, l.z}, hi3[3] = {h.x, h.y, h.z};
-                const float a = box_area(lo3, hi3);
-                if (a > bestA) { bestA = a; best = c; }
-            }
-            if (best < 0) break;
-            const int b = ch[best];
-            ch[best] = t.left[b]; ch[nch++] = t.right[b];
+    int ch[8]; bool leafDp[8]; int nch = 0;
+    {
+        // the children the dynamic program chose: the root's best split k, then each side's decisions down to single slots
+        const uint32_t Dr = lbvh_dp_decisions(t, root);
+        int stRef[16], stI[16], sp = 0;
+        const int k0 = (int)(Dr >> 28) & 7;
+        stRef[sp] = t.right[root]; stI[sp++] = 8 - k0;
+        stRef[sp] = t.left[root]; stI[sp++] = k0;
+        while (sp) {
+            const int ref = stRef[--sp]; int i = stI[sp];
+            if (ref < 0) { leafDp[nch] = true; ch[nch++] = ref; continue; }
+            const uint32_t D = lbvh_dp_decisions(t, ref);
+            int d = 0;
+            while (i > 1 && (d = (int)(D >> (4 * (i - 1))) & 15) == 0) i--;   // "no better than with one slot fewer"
+            if (i == 1) { leafDp[nch] = (D & 15u) == 0u; ch[nch++] = ref; continue; }
+            stRef[sp] = t.right[ref]; stI[sp++] = i - d;
+            stRef[sp] = t.left[ref]; stI[sp++] = d;
         }
+    }
     float clo[8][3], chi[8][3], cbl[8][3], cbh[8][3]; bool used[8], leaf[8];
     float nlo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, nhi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
     for (int c = 0; c < nch; c++) {
         float4 l, h;
-        if (ch[c] >= 0) { l = t.box[2 * ch[c]]; h = t.box[2 * ch[c] + 1]; leaf[c] = t.last[ch[c]] - t.first[ch[c]] + 1 <= leafMax; }
+        if (ch[c] >= 0) { l = t.box[2 * ch[c]]; h = t.box[2 * ch[c] + 1]; leaf[c] = leafDp[c]; }
         else { const int p = vals[~ch[c]]; l = primBox[2 * p]; h = primBox[2 * p + 1]; leaf[c] = true; }
         cbl[c][0] = l.x; cbl[c][1] = l.y; cbl[c][2] = l.z; cbh[c][0] = h.x; cbh[c][1] = h.y; cbh[c][2] = h.z;
         for (int a = 0; a < 3; a++) { nlo[a] = fminf(nlo[a], cbl[c][a]); nhi[a] = fmaxf(nhi[a], cbh[c][a]); }
@@ -262,7 +442,7 @@ __device__ __forceinline__ void lbvh_collapse_node(int w, const LbvhTree& t, con
         used[s] = true;
         for (int a = 0; a < 3; a++) { clo[s][a] = cbl[c][a]; chi[s][a] = cbh[c][a]; }
         if (!leaf[c]) { imask |= 1u << s; nInternal++; }
-        else { const int cnt = ch[c] < 0 ? 1 : t.last[ch[c]] - t.first[ch[c]] + 1; valid24 |= (cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u)) << (3 * s); nLeafPrims += cnt; }
+        else { const int cnt = lbvh_count(t, ch[c]); valid24 |= (cnt == 1 ? 1u : (cnt == 2 ? 3u : 7u)) << (3 * s); nLeafPrims += cnt; }
     }
     const int childBase = nInternal ? atomicAdd(&counters[0], nInternal) : 0;
     const int primBase = nLeafPrims ? atomicAdd(&counters[1], nLeafPrims) : 0;
@@ -271,8 +451,9 @@ __device__ __forceinline__ void lbvh_collapse_node(int w, const LbvhTree& t, con
         const int c = childAt[s];
         if (c < 0) continue;
         if (!leaf[c]) { workB2[ci++] = ch[c]; continue; }
-        const int f = ch[c] < 0 ? ~ch[c] : t.first[ch[c]], l = ch[c] < 0 ? ~ch[c] : t.last[ch[c]];
-        for (int k = f; k <= l; k++, pi++) primsOut[pi] = primsIn[vals[k]];
+        int lv[3];
+        const int nl = lbvh_leaves(t, ch[c], lv);
+        for (int k = 0; k < nl; k++, pi++) primsOut[pi] = primsIn[vals[lv[k]]];
     }
     uint32_t imr = 0;
     for (int s = 0; s < 8; s++) if (!((imask >> s) & 1u)) imr |= 1u << (7 - s);
@@ -286,10 +467,10 @@ __device__ __forceinline__ void lbvh_collapse_node(int w, const LbvhTree& t, con
 // The host queues one launch per possible level back to back and reads the level table once at the end: no host
 // synchronisation per tree level.  An empty level's launch exits at once.
 __global__ void __launch_bounds__(128) k_lbvh_collapse_level(int level, int* levelStart, unsigned* tickets, int n, LbvhTree t, const int* vals, const float4* primBox,
-                                                             const PrimRec* primsIn, WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters, int leafMax) {
+                                                             const PrimRec* primsIn, WideNode* nodes, PrimRec* primsOut, int* workB2, int* counters) {
     const int first = levelStart[level], last = levelStart[level + 1];
     for (int w = first + blockIdx.x * blockDim.x + threadIdx.x; w < last; w += gridDim.x * blockDim.x)
-        lbvh_collapse_node(w, t, vals, primBox, primsIn, nodes, primsOut, workB2, counters, leafMax);
+        lbvh_collapse_node(w, t, vals, primBox, primsIn, nodes, primsOut, workB2, counters);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0 && atomicAdd(&tickets[level], 1u) == gridDim.x - 1u) {

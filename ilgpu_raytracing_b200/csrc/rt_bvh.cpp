@@ -10,9 +10,12 @@
 
 #include <algorithm>
 #include <thread>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
 
 namespace rtx {
@@ -146,12 +149,20 @@ inline float bitsf(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 }   // namespace
 
-bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool primsOnly, int maxDepth) {
+bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, PrimSink* sink, int maxDepth) {
     if (maxDepth <= 0 || maxDepth > RT_STACK_ENTRIES - 2) maxDepth = RT_STACK_ENTRIES - 2;
-    out.nodes.clear(); out.prims.clear(); out.levelStart.clear(); out.primBoxes.clear(); out.stats = HostBvhStats();
+    out.nodes.clear(); out.prims.clear(); out.levelStart.clear(); out.stats = HostBvhStats();
     out.instBoxXf.assign((size_t)std::max<int64_t>(0, d.nInstances) * 12, 0.0);
     for (int64_t i = 0; i < d.nInstances; i++) { out.instBoxXf[(size_t)i * 12 + 0] = 1.0; out.instBoxXf[(size_t)i * 12 + 5] = 1.0; out.instBoxXf[(size_t)i * 12 + 10] = 1.0; }
     Builder B;
+    const bool timing = getenv("RT_BUILD_TIMING") && atoi(getenv("RT_BUILD_TIMING")) != 0;   // tuning runs: phases of the primitive stage on stderr
+    auto tPhase = std::chrono::steady_clock::now();
+    auto phase = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "rtcore_b200 host stage: %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tPhase).count());
+        tPhase = now;
+    };
 
     // ---- 1. enumerate (instance, primitive) pairs in the reference's visiting order --------------------------------
     // TLAS walk with every box test taken (SceneDeviceViews.cs:33-84): leaves in left-first skip-link order.
@@ -209,17 +220,29 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
             } else cur = n.left;
         }
     }
-    B.prims.resize((size_t)rank);
+    phase("walk of the reference's BVH2 arrays");
+    if (sink) { if (rank && (!sink->reserve || !sink->reserve(sink, (size_t)rank))) { err = "out of memory for the primitive staging arrays"; return false; } }
+    else B.prims.resize((size_t)rank);
+    unsigned hw = std::thread::hardware_concurrency();
+    const size_t nThreads = (rank < (1u << 15)) ? 1 : std::max<size_t>(1, std::min<size_t>(hw ? hw : 4, 32));
+    auto run_threads = [&](const std::function<void(size_t)>& work) {
+        if (nThreads == 1) { work(0); return; }
+        std::vector<std::thread> pool;
+        for (size_t t = 1; t < nThreads; t++) { try { pool.emplace_back(work, t); } catch (...) { work(t); } }
+        work(0);
+        for (auto& th : pool) th.join();
+    };
+    std::vector<float> absMax(nThreads, 0.0f);
     {
         const size_t nLeaves = leaves.size();
-        unsigned hw = std::thread::hardware_concurrency();
-        const size_t nThreads = (rank < (1u << 15)) ? 1 : std::max<size_t>(1, std::min<size_t>(hw ? hw : 4, 32));
         std::vector<std::string> errs(nThreads); std::vector<size_t> errAt(nThreads, (size_t)-1);
         std::vector<int64_t> nSph(nThreads, 0), nTri(nThreads, 0);
         auto work = [&](size_t t) {
             const size_t lo = nLeaves * t / nThreads, hi = nLeaves * (t + 1) / nThreads;
-            auto bad = [&](size_t li, const char* m) { if (errAt[t] == (size_t)-1) { errAt[t] = li; errs[t] = m; } };
-            for (size_t li = lo; li < hi && errAt[t] == (size_t)-1; li++) {
+            bool failed = false;
+            auto bad = [&](size_t li, const char* m) { if (!failed) { failed = true; errAt[t] = li; errs[t] = m; } };
+            float myAbs = 0.0f; int64_t mySph = 0, myTri = 0;   // locals: the per-thread slots share cache lines
+            for (size_t li = lo; li < hi && !failed; li++) {
                 const LeafItem& L = leaves[li];
                 const InstInfo& info = infos[(size_t)L.inst];
                 const int ii = info.ii;
@@ -240,7 +263,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
                         float r = std::fabs(s.radius);
                         obb[0][0] = s.center.X - r; obb[0][1] = s.center.Y - r; obb[0][2] = s.center.Z - r;
                         obb[1][0] = s.center.X + r; obb[1][1] = s.center.Y + r; obb[1][2] = s.center.Z + r;
-                        nSph[t]++;
+                        mySph++;
                     } else {
                         int tri = d.triPrimIdx[i];
                         if (tri < 0 || tri >= d.nMeshTris) { bad(li, "triPrimIdx: bad triangle index"); break; }
@@ -262,7 +285,7 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
                         bp.rec.q2 = make_float4(v2.X, v2.Y, v2.Z, bitsf(meta));
                         obb[0][0] = std::min(v0.X, std::min(v1.X, v2.X)); obb[0][1] = std::min(v0.Y, std::min(v1.Y, v2.Y)); obb[0][2] = std::min(v0.Z, std::min(v1.Z, v2.Z));
                         obb[1][0] = std::max(v0.X, std::max(v1.X, v2.X)); obb[1][1] = std::max(v0.Y, std::max(v1.Y, v2.Y)); obb[1][2] = std::max(v0.Z, std::max(v1.Z, v2.Z));
-                        nTri[t]++;
+                        myTri++;
                     }
                     bool finite = true;
                     for (int a = 0; a < 3; a++) if (!std::isfinite(obb[0][a]) || !std::isfinite(obb[1][a])) finite = false;
@@ -277,24 +300,53 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
                             bp.box.grow(w);
                         }
                     }
-                    B.prims[rk] = bp;
+                    if (sink) {
+                        sink->prims[rk] = bp.rec;
+                        sink->boxes[2 * (size_t)rk] = make_float4(bp.box.lo[0], bp.box.lo[1], bp.box.lo[2], 0.0f);
+                        sink->boxes[2 * (size_t)rk + 1] = make_float4(bp.box.hi[0], bp.box.hi[1], bp.box.hi[2], 0.0f);
+                        for (int a = 0; a < 3; a++) myAbs = std::max(myAbs, std::max(std::fabs(bp.box.lo[a]), std::fabs(bp.box.hi[a])));
+                    } else B.prims[rk] = bp;
                 }
             }
+            absMax[t] = myAbs; nSph[t] = mySph; nTri[t] = myTri;
         };
-        if (nThreads == 1) work(0);
-        else {
-            std::vector<std::thread> pool;
-            for (size_t t = 1; t < nThreads; t++) { try { pool.emplace_back(work, t); } catch (...) { work(t); } }
-            work(0);
-            for (auto& th : pool) th.join();
-        }
+        run_threads(work);
         size_t firstBad = (size_t)-1, who = 0;
         for (size_t t = 0; t < nThreads; t++) { out.stats.nSpheres += nSph[t]; out.stats.nTris += nTri[t]; if (errAt[t] < firstBad) { firstBad = errAt[t]; who = t; } }
         if (firstBad != (size_t)-1) { err = errs[who]; return false; }   // the first offending leaf in visiting order, like a sequential pass
     }
-    const int N = (int)B.prims.size();
+    phase("records (all threads)");
+    const int N = (int)rank;
     out.stats.nPrims = N;
     if (N == 0) return true;   // empty scene: everything misses
+
+    if (sink) {   // section 2 below, on all threads and in place: the same padding arithmetic, the same boxes
+        if (sink->recordsDone) sink->recordsDone(sink, (size_t)N);
+        float sceneAbs = 0.0f;
+        for (float m : absMax) sceneAbs = std::max(sceneAbs, m);
+        std::vector<Aabb> sbs(nThreads);
+        run_threads([&](size_t t) {
+            Aabb sb; sb.reset();
+            const size_t lo = (size_t)N * t / nThreads, hi = (size_t)N * (t + 1) / nThreads;
+            for (size_t i = lo; i < hi; i++) {
+                const bool xf = (fbits(sink->prims[i].q2.w) & PRIM_XFORM) != 0;
+                float4& bl = sink->boxes[2 * i]; float4& bh = sink->boxes[2 * i + 1];
+                float* l3[3] = {&bl.x, &bl.y, &bl.z}; float* h3[3] = {&bh.x, &bh.y, &bh.z};
+                for (int a = 0; a < 3; a++) {
+                    float mag = std::max(std::fabs(*l3[a]), std::fabs(*h3[a]));
+                    float pad = 2e-6f * sceneAbs + (xf ? 2e-5f : 2e-6f) * mag + 1e-30f;
+                    *l3[a] -= pad; *h3[a] += pad;
+                    sb.lo[a] = std::min(sb.lo[a], *l3[a]); sb.hi[a] = std::max(sb.hi[a], *h3[a]);
+                }
+            }
+            sbs[t] = sb;
+        });
+        Aabb sb; sb.reset();
+        for (const Aabb& b : sbs) if (b.lo[0] <= b.hi[0]) sb.grow(b);
+        for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = sb.lo[a]; out.stats.sceneHi[a] = sb.hi[a]; }
+        phase("padding (all threads)");
+        return true;
+    }
 
     // ---- 2. conservative padding (rounding of the exact primitive tests and of the quantised slab test) ----------
     float sceneAbs = 0.0f;
@@ -307,18 +359,6 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, bool p
             p.box.lo[a] -= pad; p.box.hi[a] += pad;
             p.c[a] = 0.5f * (p.box.lo[a] + p.box.hi[a]);
         }
-    }
-
-    if (primsOnly) {
-        out.prims.resize((size_t)N); out.primBoxes.resize((size_t)N * 6);
-        Aabb sb; sb.reset();
-        for (int i = 0; i < N; i++) {
-            out.prims[(size_t)i] = B.prims[(size_t)i].rec;
-            for (int a = 0; a < 3; a++) { out.primBoxes[(size_t)i * 6 + a] = B.prims[(size_t)i].box.lo[a]; out.primBoxes[(size_t)i * 6 + 3 + a] = B.prims[(size_t)i].box.hi[a]; }
-            sb.grow(B.prims[(size_t)i].box);
-        }
-        for (int a = 0; a < 3; a++) { out.stats.sceneLo[a] = sb.lo[a]; out.stats.sceneHi[a] = sb.hi[a]; }
-        return true;
     }
 
     // The SAH tree minimises cost, not depth: a scene with a huge dynamic range (a small detailed mesh on a giant ground plane)

@@ -21,16 +21,26 @@ struct HostBvh {
     std::vector<PrimRec> prims;    // leaf order
     std::vector<int> levelStart;   // levelStart[l] .. levelStart[l + 1] = the nodes of depth l + 1 (for the device-side refit)
     std::vector<double> instBoxXf; // per instance: the 3x4 object-to-world transform its primitive boxes were built with (identity for identity instances)
-    std::vector<float> primBoxes;  // primsOnly builds: padded world box of prims[i], 6 floats (lo, hi), in the reference's visiting order
     HostBvhStats stats;
+};
+
+// Where a primsOnly build leaves its output: the caller's (page-locked) staging arrays, written in place by all host threads -
+// prims[i] and the padded world box of primitive i as two float4 (lo, hi), in the reference's visiting order.  reserve(n) is
+// called once, when the primitive count is known, and must make both arrays hold n entries (false = out of memory).
+struct PrimSink {
+    PrimRec* prims = nullptr;
+    float4* boxes = nullptr;
+    bool (*reserve)(PrimSink* self, size_t n) = nullptr;
+    void (*recordsDone)(PrimSink* self, size_t n) = nullptr;   // optional: prims[0..n) are final (the boxes are still being padded): the caller may start copying them
+    void* user = nullptr;
 };
 
 // Validates the reference arrays (every index the device code will follow), derives the reference's
 // visiting order and builds the wide BVH.  Returns false with a message on malformed input.
-// primsOnly: stop after the primitive stage (validation, visiting-order ranks, records, padded boxes, scene bounds in stats):
-// the tree is then built on the device (rt_build.h).
+// sink != nullptr ("primsOnly"): stop after the primitive stage (validation, visiting-order ranks, records, padded boxes, scene
+// bounds and stats.nPrims) and leave its output in the sink: the tree is then built on the device (rt_build.h).
 // maxDepth: deepest wide tree the caller's traversal stack takes (0 = RT_STACK_ENTRIES - 2); a deeper SAH tree is rebuilt
 // depth-bounded (median splits, three binary levels per wide node) - the commit never fails for depth.
-bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err, bool primsOnly = false, int maxDepth = 0);
+bool build_wide_bvh(const RtSceneDesc& desc, HostBvh& out, std::string& err, PrimSink* sink = nullptr, int maxDepth = 0);
 
 }   // namespace rtx

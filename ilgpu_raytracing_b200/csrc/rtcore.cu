@@ -20,6 +20,7 @@
 #include <string>
 #include <tuple>
 #include <utility>
+#include <chrono>
 #include <vector>
 
 #include "rt_bvh.h"
@@ -562,7 +563,35 @@ template <typename T> struct DevBuf {   // owning device allocation (freed with 
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
+// Device builder (rt_build.h): scratch that survives between commits - a scene that is rebuilt every few frames should not pay
+// for device allocations and page-locking each time - and the page-locked staging arrays the host primitive stage writes into.
+struct BuildScratch {
+    DevBuf<PrimRec> primsIn, prims; DevBuf<WideNode> nodes; DevBuf<float4> primBox, boxes; DevBuf<uint64_t> keys; DevBuf<int> vals, ints; DevBuf<unsigned char> sortTmp;
+    PrimRec* stagePrims = nullptr; float4* stageBoxes = nullptr; size_t stageCap = 0;
+    int* hostInts = nullptr;   // page-locked: small read-backs
+    PrimSink sink;
+    cudaStream_t stream = nullptr; bool recordsQueued = false;   // the records' upload starts while the host still pads the boxes
+    bool reserve(size_t n) {
+        if (!hostInts && cudaHostAlloc(reinterpret_cast<void**>(&hostInts), 16 * sizeof(int), cudaHostAllocDefault) != cudaSuccess) { hostInts = nullptr; return false; }
+        if (primsIn.ensure(n) != cudaSuccess) { cudaGetLastError(); return false; }
+        if (n <= stageCap) return true;
+        release_stage();
+        const size_t cap = n + n / 8;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&stagePrims), cap * sizeof(PrimRec), cudaHostAllocDefault) != cudaSuccess) { stagePrims = nullptr; cudaGetLastError(); return false; }
+        if (cudaHostAlloc(reinterpret_cast<void**>(&stageBoxes), 2 * cap * sizeof(float4), cudaHostAllocDefault) != cudaSuccess) { stageBoxes = nullptr; release_stage(); cudaGetLastError(); return false; }
+        stageCap = cap; sink.prims = stagePrims; sink.boxes = stageBoxes;
+        return true;
+    }
+    void release_stage() { if (stagePrims) cudaFreeHost(stagePrims); if (stageBoxes) cudaFreeHost(stageBoxes); stagePrims = nullptr; stageBoxes = nullptr; stageCap = 0; sink.prims = nullptr; sink.boxes = nullptr; }
+    void release() {
+        release_stage(); if (hostInts) cudaFreeHost(hostInts); hostInts = nullptr;
+        primsIn.release(); prims.release(); nodes.release(); primBox.release(); boxes.release(); keys.release(); vals.release(); ints.release(); sortTmp.release();
+    }
+    ~BuildScratch() { release(); }
+};
+
 struct rt_ctx {
+    BuildScratch build;
     int device = 0;
     int smCount = 148;
     cudaStream_t ownStream = nullptr, stream = nullptr;
@@ -629,7 +658,7 @@ struct rt_ctx {
     cudaGraph_t frameGraph = nullptr;   // kept alive: the node handles used for per-frame parameter updates belong to it
     cudaGraphExec_t frameGraphExec = nullptr; unsigned long long frameGraphBuilds = 0, sceneVersion = 0;   // RT_FLAG_FRAME_GRAPH
     FrameKey frameKey; std::vector<cudaGraphNode_t> frameNodes; std::vector<const void*> frameFuncs;
-    bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envLbvhLeaf = 0;   // developer knobs, read once in rt_create
+    bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envDeviceTree = 0 /* 0 = the better of the two, 1 = radix, 2 = ploc */; bool envBuildTiming = false; float envCPrim = 0.0f;   // developer knobs, read once in rt_create
 };
 
 template <typename T> static cudaError_t upload_or_one(DevBuf<T>& dst, const T* src, int64_t n, cudaStream_t st, int* lenOut) {
@@ -693,56 +722,118 @@ static int size_extend_launch(rt_ctx* c, int entries) {
     return RT_OK;
 }
 
-// Device-side build (rt_build.h) of the tree over the host-made primitive records: fills dNodes / dPrims (temporaries of
-// nPrims entries each), the level ranges and the depth.  Returns a cudaError_t; *tooDeep when the tree would not fit the traversal stack.
-static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, DevBuf<WideNode>& dNodes, DevBuf<PrimRec>& dPrims, std::vector<int>& levelStart, int* nNodesOut, bool* tooDeep) {
-    const int n = (int)hb.prims.size();
+// RT_BUILD_TIMING=1: phases of a scene commit on stderr (each mark synchronises the stream, so only the tuning runs pay for it)
+struct BuildTimer {
+    bool on; cudaStream_t st; std::chrono::steady_clock::time_point t0; std::string line;
+    BuildTimer(bool on_, cudaStream_t st_) : on(on_), st(st_), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96]; snprintf(buf, sizeof(buf), " %s %.2f ms |", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf; t0 = t1;
+    }
+    void print(const char* head) { if (on) fprintf(stderr, "rtcore_b200 %s:%s\n", head, line.c_str()); }
+};
+
+// Device-side build (rt_build.h) of the tree over the primitive records the host stage left in the staging arrays: fills
+// bs.nodes / bs.prims, the level ranges and the depth.  Returns a cudaError_t; *tooDeep when the tree would not fit the traversal
+// stack.  Two binary trees are built over the same Morton order - the radix tree (spatial-median splits: the better one for
+// regular geometry such as a height field) and PLOC (agglomerative: the better one for uneven density) - and the one whose
+// SAH-optimal collapse costs less, C(root, 1) of the dynamic program both carry, is collapsed (RT_DEVICE_TREE=radix|ploc forces one).
+static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, std::vector<int>& levelStart, int* nNodesOut, bool* tooDeep) {
+    const int n = (int)hb.stats.nPrims;
+    BuildScratch& bs = c->build;
     cudaStream_t st = c->stream;
     cudaError_t e;
 #define BTRY(x) do { e = (x); if (e != cudaSuccess) return e; } while (0)
-    DevBuf<PrimRec> primsIn; DevBuf<float4> primBox; DevBuf<uint64_t> keys, keys2; DevBuf<int> vals, vals2, ints, counters; DevBuf<unsigned char> sortTmp;
-    BTRY(primsIn.ensure(n)); BTRY(primBox.ensure(2 * (size_t)n)); BTRY(keys.ensure(n)); BTRY(keys2.ensure(n)); BTRY(vals.ensure(n)); BTRY(vals2.ensure(n));
-    BTRY(ints.ensure(8 * (size_t)n)); BTRY(counters.ensure(2)); BTRY(dNodes.ensure(n)); BTRY(dPrims.ensure(n));
-    DevBuf<float4> tbox; BTRY(tbox.ensure(2 * (size_t)n));
-    std::vector<float4> hbBox(2 * (size_t)n);
-    for (int i = 0; i < n; i++) {
-        hbBox[2 * (size_t)i] = make_float4(hb.primBoxes[(size_t)i * 6], hb.primBoxes[(size_t)i * 6 + 1], hb.primBoxes[(size_t)i * 6 + 2], 0.0f);
-        hbBox[2 * (size_t)i + 1] = make_float4(hb.primBoxes[(size_t)i * 6 + 3], hb.primBoxes[(size_t)i * 6 + 4], hb.primBoxes[(size_t)i * 6 + 5], 0.0f);
-    }
-    BTRY(cudaMemcpyAsync(primsIn.p, hb.prims.data(), (size_t)n * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
-    BTRY(cudaMemcpyAsync(primBox.p, hbBox.data(), hbBox.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
-    float3 lo = make_float3(hb.stats.sceneLo[0], hb.stats.sceneLo[1], hb.stats.sceneLo[2]);
-    float3 inv = make_float3(1.0f / fmaxf(hb.stats.sceneHi[0] - lo.x, 1e-30f), 1.0f / fmaxf(hb.stats.sceneHi[1] - lo.y, 1e-30f), 1.0f / fmaxf(hb.stats.sceneHi[2] - lo.z, 1e-30f));
-    k_lbvh_morton<<<(n + 255) / 256, 256, 0, st>>>(primBox.p, n, lo, inv, keys.p, vals.p);
+    BuildTimer tm(c->envBuildTiming, st);
+    const bool wantRadix = c->envDeviceTree != 2, wantPloc = c->envDeviceTree != 1;
+    const int tiles = (n + RT_PLOC_TILE - 1) / RT_PLOC_TILE;
+    const int maxLevels = RT_STACK_ENTRIES - 2;
+    BTRY(bs.primsIn.ensure(n)); BTRY(bs.primBox.ensure(2 * (size_t)n)); BTRY(bs.keys.ensure(2 * (size_t)n)); BTRY(bs.vals.ensure(2 * (size_t)n));
+    BTRY(bs.ints.ensure(10 * (size_t)n + 2 * (size_t)tiles + 16 + 2 * (size_t)maxLevels)); BTRY(bs.boxes.ensure(12 * (size_t)n)); BTRY(bs.nodes.ensure(n)); BTRY(bs.prims.ensure(n));
+    tm.mark("scratch");
+    if (!bs.recordsQueued) BTRY(cudaMemcpyAsync(bs.primsIn.p, bs.stagePrims, (size_t)n * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
+    BTRY(cudaMemcpyAsync(bs.primBox.p, bs.stageBoxes, 2 * (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    tm.mark("h2d records + boxes");
+    const float3 lo = make_float3(hb.stats.sceneLo[0], hb.stats.sceneLo[1], hb.stats.sceneLo[2]);
+    // cubic Morton cells (one scale for the three axes): a flat scene spends no high bits on its thin axis
+    const float ext = fmaxf(fmaxf(hb.stats.sceneHi[0] - lo.x, hb.stats.sceneHi[1] - lo.y), fmaxf(hb.stats.sceneHi[2] - lo.z, 1e-30f));
+    const float3 inv = make_float3(1.0f / ext, 1.0f / ext, 1.0f / ext);
+    uint64_t* keys = bs.keys.p; uint64_t* keys2 = bs.keys.p + n; int* vals = bs.vals.p; int* vals2 = bs.vals.p + n;
+    k_lbvh_morton<<<(n + 255) / 256, 256, 0, st>>>(bs.primBox.p, n, lo, inv, keys, vals);
     size_t tmpBytes = 0;
-    BTRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, st));
-    BTRY(sortTmp.ensure(tmpBytes + 16));
-    BTRY(cub::DeviceRadixSort::SortPairs(sortTmp.p, tmpBytes, keys.p, keys2.p, vals.p, vals2.p, n, 0, 63, st));
-    LbvhTree t;
-    t.left = ints.p; t.right = ints.p + n; t.first = ints.p + 2 * (size_t)n; t.last = ints.p + 3 * (size_t)n; t.visits = ints.p + 4 * (size_t)n; t.parent = ints.p + 5 * (size_t)n;   // parent: 2n - 1 entries
-    int* workB2 = ints.p + 7 * (size_t)n;
-    t.box = tbox.p;
-    BTRY(cudaMemsetAsync(t.visits, 0, (size_t)n * sizeof(int), st));
-    k_lbvh_tree<<<(n + 255) / 256, 256, 0, st>>>(keys2.p, n, t);
-    k_lbvh_boxes<<<(n + 255) / 256, 256, 0, st>>>(vals2.p, primBox.p, n, t);
-    const int init[2] = {1, 0};
-    BTRY(cudaMemcpyAsync(counters.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
-    BTRY(cudaMemsetAsync(workB2, 0, sizeof(int), st));   // wide node 0 owns binary node 0
-    int leafMax = 2;   // primitives per leaf child; sweep on C4 (RT_LBVH_LEAF): 1 / 2 / 3 -> 22.5 / 22.2 / 29.1 ms of traversal (host SAH tree: 19.7)
-    if (c->envLbvhLeaf) leafMax = c->envLbvhLeaf;
+    BTRY(cub::DeviceRadixSort::SortPairs(nullptr, tmpBytes, keys, keys2, vals, vals2, n, 0, 63, st));
+    BTRY(bs.sortTmp.ensure(tmpBytes + 16));
+    BTRY(cub::DeviceRadixSort::SortPairs(bs.sortTmp.p, tmpBytes, keys, keys2, vals, vals2, n, 0, 63, st));
+    tm.mark("morton + sort");
+    // ints: [radix: left right count visits parent(2n)] [ploc: left right count] [workB2 n] [ploc state] ; boxes: [radix box, dp] [ploc box, dp] [ploc cluster boxes 4n]
+    int* ip = bs.ints.p; float4* bp = bs.boxes.p;
+    LbvhTree tR, tP;
+    tR.left = ip; tR.right = ip + n; tR.count = ip + 2 * (size_t)n; tR.visits = ip + 3 * (size_t)n; tR.parent = ip + 4 * (size_t)n;
+    tP.left = ip + 6 * (size_t)n; tP.right = ip + 7 * (size_t)n; tP.count = ip + 8 * (size_t)n; tP.visits = nullptr; tP.parent = nullptr;
+    int* workB2 = ip + 9 * (size_t)n;
+    tR.box = bp; tR.dp = bp + 2 * (size_t)n; tP.box = bp + 4 * (size_t)n; tP.dp = bp + 6 * (size_t)n;
+    tR.cPrim = tP.cPrim = c->envCPrim > 0.0f ? c->envCPrim : 1.6f;
+    PlocState S;
+    int* ps = ip + 10 * (size_t)n;   // tileCount, tileOffset, nc[2], nodeCounter, then the collapse's level table and tickets
+    S.tileCount = ps; S.tileOffset = ps + tiles; S.nc = ps + 2 * (size_t)tiles; S.nodeCounter = S.nc + 2;
+    int* dLevel = S.nodeCounter + 2; unsigned* dTickets = reinterpret_cast<unsigned*>(dLevel + maxLevels + 2); int* counters = dLevel + 2 * (size_t)maxLevels + 4;
+    S.cbox = bp + 8 * (size_t)n; S.tbox = bp + 10 * (size_t)n;
+    S.cid = reinterpret_cast<int*>(keys); S.tcid = S.cid + n;   // cluster ids: the unsorted key array is dead after the sort (n 64-bit keys = 2n ints)
+    if (wantRadix) {
+        BTRY(cudaMemsetAsync(tR.visits, 0, (size_t)n * sizeof(int), st));
+        k_lbvh_tree<<<(n + 255) / 256, 256, 0, st>>>(keys2, n, tR);
+        k_lbvh_boxes<<<(n + 255) / 256, 256, 0, st>>>(vals2, bs.primBox.p, n, tR);
+    }
+    int rootP = 0, it = 0;
+    if (wantPloc) {
+        const int initNc[3] = {n, n, 0};
+        BTRY(cudaMemcpyAsync(S.nc, initNc, sizeof(initNc), cudaMemcpyHostToDevice, st));
+        k_ploc_init<<<(n + 255) / 256, 256, 0, st>>>(vals2, bs.primBox.p, n, S);
+        const int plocGrid = std::max(1, std::min(tiles, c->smCount * 8));
+        int nc = n;
+        while (nc > 1) {
+            for (int b = 0; b < 24; b++, it++) {
+                k_ploc_merge<<<plocGrid, RT_PLOC_TILE, 0, st>>>(it & 1, S, tP);
+                k_ploc_scan<<<1, 1024, 0, st>>>(it & 1, S);
+                k_ploc_scatter<<<plocGrid, RT_PLOC_TILE, 0, st>>>(it & 1, S);
+            }
+            BTRY(cudaGetLastError());
+            BTRY(cudaMemcpyAsync(&bs.hostInts[0], S.nc + (it & 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+            BTRY(cudaMemcpyAsync(&bs.hostInts[1], S.cid, sizeof(int), cudaMemcpyDeviceToHost, st));
+            BTRY(cudaStreamSynchronize(st));
+            nc = bs.hostInts[0];
+            if (it > 64 * 24) return cudaErrorUnknown;   // cannot happen: every iteration merges at least one pair
+        }
+        rootP = bs.hostInts[1];   // the last cluster
+    }
+    tm.mark("binary trees");
+    bool usePloc = wantPloc;
+    float costR = 0.0f, costP = 0.0f;
+    if (wantRadix && wantPloc) {
+        float4 cr, cp;
+        BTRY(cudaMemcpyAsync(&cr, tR.dp, sizeof(float4), cudaMemcpyDeviceToHost, st));   // pageable targets: these copies return when done
+        BTRY(cudaMemcpyAsync(&cp, tP.dp + 2 * (size_t)rootP, sizeof(float4), cudaMemcpyDeviceToHost, st));
+        BTRY(cudaStreamSynchronize(st));
+        costR = cr.x; costP = cp.x;
+        usePloc = costP < costR;
+    }
+    const LbvhTree& t = usePloc ? tP : tR;
+    const int init[4] = {1, 0, usePloc ? rootP : 0, 0};   // counters: wide nodes made, primitive records placed; workB2[0]: wide node 0 owns the binary root
+    BTRY(cudaMemcpyAsync(counters, init, 2 * sizeof(int), cudaMemcpyHostToDevice, st));
+    BTRY(cudaMemcpyAsync(workB2, init + 2, sizeof(int), cudaMemcpyHostToDevice, st));
     // one launch per POSSIBLE level, queued back to back: every launch reads its range from the device-side level table the previous
     // one completed (k_lbvh_collapse_level), so the host waits once, at the end, for the whole tree
-    const int maxLevels = RT_STACK_ENTRIES - 2;
-    DevBuf<int> dLevel; DevBuf<unsigned> dTickets;
-    BTRY(dLevel.ensure((size_t)maxLevels + 2)); BTRY(dTickets.ensure((size_t)maxLevels));
     std::vector<int> hLevel((size_t)maxLevels + 2, 0); hLevel[1] = 1;
-    BTRY(cudaMemcpyAsync(dLevel.p, hLevel.data(), hLevel.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    BTRY(cudaMemsetAsync(dTickets.p, 0, (size_t)maxLevels * sizeof(unsigned), st));
+    BTRY(cudaMemcpyAsync(dLevel, hLevel.data(), hLevel.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    BTRY(cudaMemsetAsync(dTickets, 0, (size_t)maxLevels * sizeof(unsigned), st));
     const int collapseGrid = std::max(1, std::min((n + 127) / 128, c->smCount * 16));
     for (int level = 0; level < maxLevels; level++)
-        k_lbvh_collapse_level<<<collapseGrid, 128, 0, st>>>(level, dLevel.p, dTickets.p, n, t, vals2.p, primBox.p, primsIn.p, dNodes.p, dPrims.p, workB2, counters.p, leafMax);
+        k_lbvh_collapse_level<<<collapseGrid, 128, 0, st>>>(level, dLevel, dTickets, n, t, vals2, bs.primBox.p, bs.primsIn.p, bs.nodes.p, bs.prims.p, workB2, counters);
     BTRY(cudaGetLastError());
-    BTRY(cudaMemcpyAsync(hLevel.data(), dLevel.p, hLevel.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+    BTRY(cudaMemcpyAsync(hLevel.data(), dLevel, hLevel.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
     BTRY(cudaStreamSynchronize(st));
     levelStart.assign(1, 0);
     int last = 1;
@@ -753,9 +844,10 @@ static cudaError_t build_on_device(rt_ctx* c, const HostBvh& hb, DevBuf<WideNode
         last = hLevel[(size_t)level + 1];
     }
     if (hLevel[(size_t)maxLevels + 1] > hLevel[(size_t)maxLevels]) *tooDeep = true;   // the last possible level still made children
-    BTRY(cudaGetLastError());
-    BTRY(cudaStreamSynchronize(st));
     *nNodesOut = last;
+    tm.mark("collapse");
+    if (c->envBuildTiming) fprintf(stderr, "rtcore_b200 device build: %s tree (collapsed SAH cost: radix %.4g, ploc %.4g after %d iterations), %d wide nodes\n", usePloc ? "ploc" : "radix", costR, costP, it, last);
+    tm.print("device build");
 #undef BTRY
     return cudaSuccess;
 }
@@ -852,7 +944,9 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     c->envNoL2Persist = getenv("RT_NO_L2_PERSIST") != nullptr;
     c->envNoSunProbe = getenv("RT_NO_SUN_PROBE") != nullptr;
     if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) c->envPathsPerPass = v; }
-    if (const char* e = getenv("RT_LBVH_LEAF")) { const int v = atoi(e); if (v >= 1 && v <= 3) c->envLbvhLeaf = v; }
+    if (const char* e = getenv("RT_DEVICE_TREE")) c->envDeviceTree = strcmp(e, "radix") == 0 ? 1 : (strcmp(e, "ploc") == 0 ? 2 : 0);
+    if (const char* e = getenv("RT_BVH_CPRIM")) c->envCPrim = (float)atof(e);
+    if (const char* e = getenv("RT_BUILD_TIMING")) c->envBuildTiming = atoi(e) != 0;
     const int rc = [&]() -> int {   // any failure below releases what the context already holds (rt_destroy)
         CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
         c->stream = c->ownStream;
@@ -925,38 +1019,51 @@ RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFla
             return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: texInfos entry addresses texels out of range");
     }
     HostBvh bvh; std::string err;
+    BuildTimer tmU(c->envBuildTiming, c->stream);
+    CUDA_TRY(cudaSetDevice(c->device));
     // the device builder needs a few primitives to make a tree of; tiny scenes take the host builder either way
     bool onDevice = (buildFlags & RT_BUILD_DEVICE_LBVH) != 0;
-    if (!build_wide_bvh(*d, bvh, err, onDevice)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
-    if (onDevice && bvh.prims.size() < 64) { onDevice = false; if (!build_wide_bvh(*d, bvh, err, false)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err); }
-    CUDA_TRY(cudaSetDevice(c->device));
+    if (!onDevice) c->build.release();   // the device builder keeps its scratch between ITS commits only
+    if (onDevice) {
+        CUDA_TRY(cudaStreamSynchronize(c->stream));   // an earlier commit's copies out of the staging arrays are done
+        c->build.sink.user = &c->build; c->build.stream = c->stream; c->build.recordsQueued = false;
+        c->build.sink.reserve = [](PrimSink* self, size_t n) { return static_cast<BuildScratch*>(self->user)->reserve(n); };
+        c->build.sink.recordsDone = [](PrimSink* self, size_t n) {
+            BuildScratch* b = static_cast<BuildScratch*>(self->user);
+            b->recordsQueued = cudaMemcpyAsync(b->primsIn.p, b->stagePrims, n * sizeof(PrimRec), cudaMemcpyHostToDevice, b->stream) == cudaSuccess;
+        };
+    }
+    if (!build_wide_bvh(*d, bvh, err, onDevice ? &c->build.sink : nullptr)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
+    if (onDevice && bvh.stats.nPrims < 64) { onDevice = false; if (!build_wide_bvh(*d, bvh, err)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err); }
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // nothing in flight may still read the old scene
+    tmU.mark("host stage");
     cudaStream_t st = c->stream;
     // From here on the old scene is torn down buffer by buffer (DevBuf::ensure frees before it allocates): the context has NO
     // scene until every array of the new one is in place, so a failure half way (out of memory, a CUDA error) leaves a context
     // that refuses to render (RT_ERR_INVALID_STATE) instead of one that traverses freed or null pointers.
     c->hasScene = false; c->ds.nNodes = 0; c->ds.nPrims = 0;
     DeviceScene& ds = c->ds;
-    DevBuf<WideNode> builtNodes; DevBuf<PrimRec> builtPrims; int builtNodeCount = 0;
+    int builtNodeCount = 0;
     if (onDevice) {
         bool tooDeep = false;
-        CUDA_TRY(build_on_device(c, bvh, builtNodes, builtPrims, bvh.levelStart, &builtNodeCount, &tooDeep));
+        CUDA_TRY(build_on_device(c, bvh, bvh.levelStart, &builtNodeCount, &tooDeep));
         if (tooDeep) {   // a degenerate Morton order (very uneven extents): the host builder bounds the depth
-            onDevice = false; builtNodes.release(); builtPrims.release();
-            if (!build_wide_bvh(*d, bvh, err, false)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
+            onDevice = false;
+            if (!build_wide_bvh(*d, bvh, err)) return fail(RT_ERR_INVALID_ARGUMENT, "rt_scene_upload: " + err);
         } else {
             bvh.stats.nWideNodes = builtNodeCount; bvh.stats.maxDepth = std::max(1, (int)bvh.levelStart.size() - 1);
         }
     }
-    const size_t nNodes = onDevice ? (size_t)builtNodeCount : bvh.nodes.size(), nPrims = bvh.prims.size();
+    tmU.mark("device build");
+    const size_t nNodes = onDevice ? (size_t)builtNodeCount : bvh.nodes.size(), nPrims = (size_t)bvh.stats.nPrims;
     const size_t nodeBytes = (std::max<size_t>(1, nNodes) * sizeof(WideNode) + 255) / 256 * 256;
     const size_t primBytes = std::max<size_t>(1, nPrims) * sizeof(PrimRec);
     CUDA_TRY(c->bvhBlob.ensure(nodeBytes + primBytes));
     WideNode* dNodes = reinterpret_cast<WideNode*>(c->bvhBlob.p);
     PrimRec* dPrims = reinterpret_cast<PrimRec*>(c->bvhBlob.p + nodeBytes);
     if (onDevice) {
-        CUDA_TRY(cudaMemcpyAsync(dNodes, builtNodes.p, nNodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(dPrims, builtPrims.p, nPrims * sizeof(PrimRec), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dNodes, c->build.nodes.p, nNodes * sizeof(WideNode), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(dPrims, c->build.prims.p, nPrims * sizeof(PrimRec), cudaMemcpyDeviceToDevice, st));
     } else {
         if (nNodes) CUDA_TRY(cudaMemcpyAsync(dNodes, bvh.nodes.data(), nNodes * sizeof(WideNode), cudaMemcpyHostToDevice, st));
         if (nPrims) CUDA_TRY(cudaMemcpyAsync(dPrims, bvh.prims.data(), nPrims * sizeof(PrimRec), cudaMemcpyHostToDevice, st));
@@ -964,12 +1071,13 @@ RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFla
     ds.nodes = dNodes; ds.nNodes = nPrims == 0 ? 0 : (int)nNodes; ds.prims = dPrims; ds.nPrims = (int)nPrims;
     // keep the BVH resident in L2 while GBs of path state stream past it: persisting carve-out + access-policy window (applied per stream in rt_render)
     c->l2Window = 0;
-    if (!bvh.prims.empty() && c->l2PersistMax > 0 && !c->envNoL2Persist) {
+    if (nPrims > 0 && c->l2PersistMax > 0 && !c->envNoL2Persist) {
         const size_t want = std::min(nodeBytes + primBytes, c->l2PersistMax);
         if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) c->l2Window = std::min(nodeBytes + primBytes, c->l2WindowMax);
         c->l2Persist = want;
     }
     c->l2WindowStream = nullptr;
+    tmU.mark("bvh blob");
     CUDA_TRY(upload_or_one(c->instances, d->instances, d->nInstances, st, &ds.nInstances)); ds.instances = c->instances.p;
     CUDA_TRY(upload_or_one(c->spheres, d->spheres, d->nSpheres, st, &ds.nSpheres)); ds.spheres = c->spheres.p;
     CUDA_TRY(upload_or_one(c->texcoords, d->meshTexcoords, d->nMeshTexcoords, st, nullptr)); ds.texcoords = c->texcoords.p;
@@ -984,11 +1092,14 @@ RT_API int rt_scene_upload_ex(rt_ctx* c, const RtSceneDesc* d, uint32_t buildFla
     CUDA_TRY(upload_or_one(c->instBoxXf, bvh.instBoxXf.data(), (int64_t)bvh.instBoxXf.size(), st, nullptr));
     c->nMeshPositions = d->nMeshPositions; c->nMeshTris = d->nMeshTris; c->levelStart = bvh.levelStart;
     CUDA_TRY(cudaStreamSynchronize(st));   // host arrays are only borrowed for the duration of the call
+    tmU.mark("scene arrays");
     const int rcSize = size_extend_launch(c, bvh.stats.maxDepth + 1);   // a node step pushes at most one entry per level
     if (rcSize != RT_OK) return rcSize;
     c->bvhStats = bvh.stats;
     c->bvhBytes = nNodes * sizeof(WideNode) + nPrims * sizeof(PrimRec);
     c->hasScene = true; c->sceneVersion++;
+    tmU.mark("launch sizing");
+    tmU.print("scene commit");
     return RT_OK;
 }
 

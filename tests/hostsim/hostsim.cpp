@@ -36,7 +36,7 @@ HS_API HsScene* hs_scene_create(const RtSceneDesc* d) { return hs_scene_create_e
 // maxDepth: the depth limit handed to the builder (0 = the traversal stack's); a small value forces the depth-bounded rebuild
 HS_API HsScene* hs_scene_create_ex(const RtSceneDesc* d, int maxDepth) {
     HsScene* s = new HsScene();
-    if (!build_wide_bvh(*d, s->bvh, s->err, false, maxDepth)) return s;
+    if (!build_wide_bvh(*d, s->bvh, s->err, nullptr, maxDepth)) return s;
     copy_or_one(s->instances, d->instances, d->nInstances); copy_or_one(s->spheres, d->spheres, d->nSpheres);
     copy_or_one(s->texcoords, d->meshTexcoords, d->nMeshTexcoords); copy_or_one(s->triUVs, d->meshTriUVs, d->nMeshTriUVs);
     copy_or_one(s->triMat, d->triMatIndex, d->nTriMatIndex); copy_or_one(s->materials, d->materials, d->nMaterials);

@@ -505,7 +505,7 @@ def test_refit_errors_and_engine_policy(gpu_ctx):
 @pytest.mark.parametrize("kind", ["terrain", "special", "spheres", "terrain_mats"])
 def test_device_built_bvh(gpu_ctx, kind):
     """SURVEY §8f rank 3 (build half): rt_scene_upload_ex(RT_BUILD_DEVICE_LBVH) builds the wide BVH on the GPU (Morton order,
-    radix tree, greedy 8-wide collapse).  Another tree, the same answers: every output equals the oracle's, including the equal-t
+    radix tree and PLOC, the one with the cheaper SAH-optimal 8-wide collapse is kept).  Another tree, the same answers: every output equals the oracle's, including the equal-t
     ties of duplicated triangles (the visiting-order ranks are made by the same host stage), and a refit of the device-built
     tree works like a refit of the host-built one."""
     import dataclasses
@@ -534,6 +534,29 @@ def test_device_built_bvh(gpu_ctx, kind):
         from ilgpu_raytracing_b200 import native
         desc, keep = L.scene_desc_from_arrays(sc.arrays())
         native.check(gpu_ctx._l.rt_scene_upload_ex(gpu_ctx.h, __import__("ctypes").byref(desc), 0x80))   # unknown build flag
+
+
+@pytest.mark.parametrize("tree", ["radix", "ploc"])
+def test_device_built_bvh_both_trees(gpu_ctx, tree, monkeypatch):
+    """The device builder makes two binary trees and keeps the cheaper one; RT_DEVICE_TREE (read in rt_create) forces either, so
+    both are held to the oracle - on a height field with spheres and on the scene with duplicated triangles and instances -
+    whichever of them the cost comparison happens to pick in test_device_built_bvh."""
+    from ilgpu_raytracing_b200 import native
+    from tests.util import special_camera, special_scene
+    monkeypatch.setenv("RT_DEVICE_TREE", tree)
+    ctx = native.Context(0)
+    try:
+        for spec, W, H, cam in ((scenes.terrain_scene(n_quads=150, n_spheres=40), 448, 252, oracle_camera("C3", 448, 252)),
+                                (special_scene("translated"), 400, 240, special_camera(400, 240))):
+            sc = oracle_scene_from_spec(spec)
+            ctx.scene_upload(sc.arrays(), device_build=True)
+            ctx.scene_upload(sc.arrays(), device_build=True)   # the second commit reuses the builder's scratch
+            st = ctx.stats()
+            assert st["bvhPrimCount"] > 64 and 0 < st["bvhWideNodeCount"] < st["bvhPrimCount"]
+            _run(ctx, sc, cam, W, H, 1, 0, label=f"device build ({tree}) primary")
+            _run(ctx, sc, cam, W, H, 3, 6, label=f"device build ({tree}) 6 bounces")
+    finally:
+        ctx.close()
 
 
 def test_scene_commits_do_not_leak_device_memory(gpu_ctx):
