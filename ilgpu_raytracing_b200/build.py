@@ -18,7 +18,7 @@ CORE_SRCS = [os.path.join(_CSRC, f) for f in ("rtcore.cu", "rt_bvh.cpp")]
 CORE_DEPS = CORE_SRCS + sorted(glob.glob(os.path.join(_CSRC, "*.h"))) + [os.path.join(_PKG, "..", "include", "rtcore_b200.h")]   # every header counts
 
 ENGINE_SO = os.path.join(_PKG, "librtengine_host.so")
-ENGINE_SRCS = [os.path.join(_CSRC, "host", f) for f in ("engine.cpp", "mesh_loader_obj.cpp")]
+ENGINE_SRCS = [os.path.join(_CSRC, "host", f) for f in ("engine.cpp", "mesh_loader_obj.cpp", "png_decode.cpp")]
 ENGINE_DEPS = ENGINE_SRCS + [os.path.join(_CSRC, "host", "engine.h"), os.path.join(_PKG, "..", "include", "rtcore_b200.h")]
 
 

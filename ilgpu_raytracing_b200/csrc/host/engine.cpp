@@ -566,6 +566,7 @@ static thread_local std::string g_engErr;
 template <class F> static int guard(F&& f) {
     try { f(); return 0; }
     catch (const RtNativeException& e) { g_engErr = std::string("RtNativeException: ") + e.what(); return e.status; }
+    catch (const ArgumentException& e) { g_engErr = std::string("ArgumentException: ") + e.what(); return -108; }
     catch (const ArgumentNullException& e) { g_engErr = std::string("ArgumentNullException: ") + e.what(); return -101; }
     catch (const ArgumentOutOfRangeException& e) { g_engErr = std::string("ArgumentOutOfRangeException: ") + e.what(); return -102; }
     catch (const InvalidOperationException& e) { g_engErr = std::string("InvalidOperationException: ") + e.what(); return -103; }

@@ -12,10 +12,11 @@
 //   Framebuffer       Engine/Framebuffer.cs:12-210 (DownloadToCpu / CpuColor / CpuDepth / CpuObjectId)
 //   RTRenderer        Engine/RTRenderer.cs:22-376  (RenderDirectToPbo -> rt_render)
 //
-//   MeshLoaderOBJ     Engine/MeshLoaderOBJ.cs:67-593 (OBJ / MTL / TGA; mesh_loader_obj.cpp)
+//   MeshLoaderOBJ     Engine/MeshLoaderOBJ.cs:67-593 (OBJ / MTL / TGA; mesh_loader_obj.cpp; BMP and PNG - which the reference reads
+//                     through System.Drawing - natively, png_decode.cpp)
 //
-// Out of scope: images the reference decodes through System.Drawing (PNG / JPEG ...),
-// OpenGL PBO interop, the fly-camera controller.
+// Out of scope: the lossy / platform-defined image formats of System.Drawing (JPEG, GIF, TIFF), the window and
+// the fly-camera controller.
 #pragma once
 #include <stdexcept>
 #include <string>
@@ -26,6 +27,7 @@
 namespace ILGPU_Raytracing {
 namespace Engine {
 
+struct ArgumentException : std::runtime_error { using std::runtime_error::runtime_error; };          // what `new Bitmap(file)` throws for a damaged image
 struct ArgumentNullException : std::invalid_argument { using std::invalid_argument::invalid_argument; };
 struct ArgumentOutOfRangeException : std::out_of_range { using std::out_of_range::out_of_range; };
 struct InvalidOperationException : std::logic_error { using std::logic_error::logic_error; };
@@ -70,6 +72,7 @@ struct MeshHost {
     std::vector<Float3> Positions; std::vector<MeshTri> Triangles; std::vector<Float2> Texcoords; std::vector<MeshTriUV> TriUVs;
     std::vector<int> TriMaterialIndex; std::vector<MaterialRecord> Materials; std::vector<TextureSrc> Textures;
 };
+TextureSrc load_png_bgra(const std::string& file, const std::vector<unsigned char>& bytes);   // png_decode.cpp
 struct MeshLoaderOBJ {
     static MeshHost Load(const std::string& path, float scale = 1.0f, bool flipWinding = true);   // MeshLoaderOBJ.cs:67-254
 };

@@ -5,8 +5,9 @@
 //   Scene.LoadObjInstance   Engine/Scene.cs:144-256          (append to the scene lists; every material flattens its own copy of its textures)
 //
 // What is NOT here: the reference decodes every non-TGA image through System.Drawing.Bitmap (MeshLoaderOBJ.cs:466-482), a
-// platform library that is not part of the repository.  Only uncompressed 24 / 32-bit BMP is decoded natively; any other
-// extension raises InvalidDataException instead of guessing.  Console diagnostics are omitted.
+// platform library that is not part of the repository.  The lossless formats are decoded natively - uncompressed 24 / 32-bit BMP
+// here, 8-bit PNG of every colour type in png_decode.cpp; anything else (JPEG, GIF, TIFF: lossy or platform-defined decoders)
+// raises InvalidDataException instead of guessing.  Console diagnostics are omitted.
 #include <cctype>
 #include <cerrno>
 #include <cstdio>
@@ -248,7 +249,8 @@ bool try_load_texture_bgra(const std::string& file, TextureSrc* tex) {   // :443
     std::string ext = dot == std::string::npos ? "" : lower(file.substr(dot));
     if (ext == ".tga") *tex = load_tga_bgra(file);
     else if (ext == ".bmp") *tex = load_bmp_bgra(file);
-    else throw InvalidDataException("texture '" + file + "': the reference decodes this format through System.Drawing.Bitmap, which this build does not have; use TGA or BMP");
+    else if (ext == ".png") *tex = load_png_bgra(file, read_all(file));
+    else throw InvalidDataException("texture '" + file + "': the reference decodes this format through System.Drawing.Bitmap, which this build does not have; use PNG, TGA or BMP");
     return true;
 }
 

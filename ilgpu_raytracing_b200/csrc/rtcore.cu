@@ -307,7 +307,7 @@ __device__ __forceinline__ bool hit_is_specular(const DeviceScene& sc, int prim)
 }
 template <bool REUSE, bool FAST, int CHUNK>
 __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
-                                                   RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount) {
+                                                   RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, int* hitCount /* null unless RT_DUMP_COUNTERS */) {
     __shared__ int list[CHUNK];
     __shared__ int nFront, nBack;
     __shared__ int smPush[32];
@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
         }
         __syncthreads();
         const int nf = nFront, nb = nBack;
+        if (hitCount && threadIdx.x == 0) atomicAdd(hitCount, nf + nb);
         const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
         // (measured and rejected, round 2: pulling the records of the hits one / two iterations ahead towards L2 with prefetch.global.L2,
         // here and for the G-buffer lines of k_shade_first: +8 ms per C4 frame)
@@ -658,7 +659,7 @@ struct rt_ctx {
     cudaGraph_t frameGraph = nullptr;   // kept alive: the node handles used for per-frame parameter updates belong to it
     cudaGraphExec_t frameGraphExec = nullptr; unsigned long long frameGraphBuilds = 0, sceneVersion = 0;   // RT_FLAG_FRAME_GRAPH
     FrameKey frameKey; std::vector<cudaGraphNode_t> frameNodes; std::vector<const void*> frameFuncs;
-    bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envDeviceTree = 0 /* 0 = the better of the two, 1 = radix, 2 = ploc */; bool envBuildTiming = false; float envCPrim = 0.0f;   // developer knobs, read once in rt_create
+    bool envNoL2Persist = false, envNoSunProbe = false; long long envPathsPerPass = 0; int envDeviceTree = 0 /* 0 = the better of the two, 1 = radix, 2 = ploc */; bool envBuildTiming = false, envDumpCounters = false; float envCPrim = 0.0f; int ctrStride = 0, ctrHeader = 0, ctrDepths = 0, ctrPasses = 0;   // developer knobs, read once in rt_create
 };
 
 template <typename T> static cudaError_t upload_or_one(DevBuf<T>& dst, const T* src, int64_t n, cudaStream_t st, int* lenOut) {
@@ -946,6 +947,7 @@ RT_API int rt_create(const int* deviceIds, int nDev, rt_ctx** out) {
     if (const char* e = getenv("RT_PATHS_PER_PASS")) { const long long v = atoll(e); if (v > 0) c->envPathsPerPass = v; }
     if (const char* e = getenv("RT_DEVICE_TREE")) c->envDeviceTree = strcmp(e, "radix") == 0 ? 1 : (strcmp(e, "ploc") == 0 ? 2 : 0);
     if (const char* e = getenv("RT_BVH_CPRIM")) c->envCPrim = (float)atof(e);
+    if (const char* e = getenv("RT_DUMP_COUNTERS")) c->envDumpCounters = atoi(e) != 0;
     if (const char* e = getenv("RT_BUILD_TIMING")) c->envBuildTiming = atoi(e) != 0;
     const int rc = [&]() -> int {   // any failure below releases what the context already holds (rt_destroy)
         CUDA_TRY(cudaStreamCreateWithFlags(&c->ownStream, cudaStreamNonBlocking));
@@ -1268,8 +1270,9 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
     c->ds.triMaterials = (cfg->flags & RT_FLAG_TRI_MATERIALS) ? 1 : 0;
 
     // device counters: [0] primary ray count, [1] its work cursor, [2] sun-probe count, [3] its work cursor, then per (pass, depth):
-    // nextCount, shCount, workClosest, workShadow
-    const int CS = 4, CH = 4;   // ints per (pass, depth); header ints
+    // nextCount, shCount, workClosest, workShadow, hits shaded at this depth (RT_DUMP_COUNTERS), 3 spare
+    const int CS = 8, CH = 4;   // ints per (pass, depth); header ints
+    c->ctrStride = CS; c->ctrHeader = CH; c->ctrDepths = cfg->maxDepth + 1; c->ctrPasses = nPasses;
     const size_t nCounters = CH + (size_t)nPasses * (cfg->maxDepth + 1) * CS;
     CUDA_TRY(c->counters.ensure(nCounters));
     CUDA_TRY(c->dstats.ensure(1));
@@ -1418,7 +1421,7 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 // 827 K paths are 202 chunks of 4096 - one 8-warp block per SM - but 808 of 1024)
                 const bool smallChunks = nPaths < (size_t)c->smCount * 8 * RT_SHADE_CHUNK;
                 const int shadeGrid = grid_for(c, (nPaths + (smallChunks ? 1024 : RT_SHADE_CHUNK) - 1) / (smallChunks ? 1024 : RT_SHADE_CHUNK), 1);
-#define RT_LAUNCH_SHADE_NEXT(R, F, C) rec.launch(k_shade_next<R, F, C>, dim3(shadeGrid), dim3(256), 0, fc, c->ds, wb, depth, cq, hq, (const int*)(prev + 0), nq2, mine + 0, shq, mine + 1)
+#define RT_LAUNCH_SHADE_NEXT(R, F, C) rec.launch(k_shade_next<R, F, C>, dim3(shadeGrid), dim3(256), 0, fc, c->ds, wb, depth, cq, hq, (const int*)(prev + 0), nq2, mine + 0, shq, mine + 1, c->envDumpCounters ? mine + 4 : (int*)nullptr)
                 if (smallChunks) { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, 1024); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, 1024); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, 1024); else RT_LAUNCH_SHADE_NEXT(false, false, 1024); }
                 else { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, RT_SHADE_CHUNK); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, RT_SHADE_CHUNK); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, RT_SHADE_CHUNK); else RT_LAUNCH_SHADE_NEXT(false, false, RT_SHADE_CHUNK); }
 #undef RT_LAUNCH_SHADE_NEXT
@@ -1887,6 +1890,14 @@ RT_API int rt_get_stats(rt_ctx* c, RtStats* out) {
     out->reserved[2] = c->hstats->raysSunProbe;
     out->wideNodes = c->hstats->wideNodes; out->trisTested = c->hstats->tris; out->spheresTested = c->hstats->spheres;
     out->kernelLaunches = c->launches;
+    if (c->envDumpCounters && c->ctrStride) {   // tuning: queue sizes by depth of the frame just rendered
+        std::vector<int> h((size_t)c->ctrHeader + (size_t)c->ctrPasses * c->ctrDepths * c->ctrStride);
+        if (h.size() <= c->counters.n && cudaMemcpy(h.data(), c->counters.p, h.size() * sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess)
+            for (int p = 0; p < c->ctrPasses; p++) for (int d = 0; d < c->ctrDepths; d++) {
+                const int* q = h.data() + c->ctrHeader + ((size_t)p * c->ctrDepths + d) * c->ctrStride;
+                fprintf(stderr, "rtcore_b200 counters: pass %d after depth %d: closest rays %d shadow rays %d | hits shaded at this depth %d\n", p, d, q[0], q[1], q[4]);
+            }
+    }
     float ms = 0.0f;
     if (cudaEventElapsedTime(&ms, c->evStart, c->evStop) == cudaSuccess) out->lastRenderMs = ms;
     float tr = 0.0f;

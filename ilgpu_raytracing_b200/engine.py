@@ -198,7 +198,7 @@ class Scene:
         _check(self._l.eng_scene_load_mesh_instance(self.h, _p(pos), len(pos), _p(tr), len(tr), _p(uv), len(uv), _p(tuv), _p(tm), _p(mats), len(mats), _p(m)))
 
     def LoadObjInstance(self, obj_path: str, object_to_world=None, uniform_scale: float = 1.0):
-        """Scene.LoadObjInstance (Engine/Scene.cs:144-256): OBJ + MTL + TGA/BMP textures from disk (MeshLoaderOBJ.cs)."""
+        """Scene.LoadObjInstance (Engine/Scene.cs:144-256): OBJ + MTL + TGA / BMP / PNG textures from disk (MeshLoaderOBJ.cs)."""
         m = L.affine_identity() if object_to_world is None else np.ascontiguousarray(object_to_world, L.AFFINE)
         _check(self._l.eng_scene_load_obj_instance(self.h, str(obj_path).encode(), _p(m), float(uniform_scale)))
 

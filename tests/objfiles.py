@@ -63,6 +63,150 @@ def write_bmp24(path, bgra_top_down: np.ndarray):
         f.write(bytes(data))
 
 
+# ---- PNG writer for the loader tests (every colour type / bit depth the native decoder takes, both interlace methods, every
+# filter type, stored / fixed / dynamic deflate blocks) -----------------------------------------------------------------------
+def _png_chunk(tag: bytes, data: bytes) -> bytes:
+    import zlib
+    return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+
+def _png_filter_rows(rows: list, bpp: int) -> bytes:
+    """rows: list of bytes (packed scanlines); filter type cycles 0..4 over the rows."""
+    out, prev = bytearray(), None
+    for y, row in enumerate(rows):
+        f = y % 5
+        prev_row = prev if prev is not None else bytes(len(row))
+        cur = bytearray(len(row))
+        for i, v in enumerate(row):
+            a = row[i - bpp] if i >= bpp else 0
+            b = prev_row[i]
+            c = prev_row[i - bpp] if i >= bpp else 0
+            if f == 0:
+                pred = 0
+            elif f == 1:
+                pred = a
+            elif f == 2:
+                pred = b
+            elif f == 3:
+                pred = (a + b) >> 1
+            else:
+                pq = a + b - c
+                pa, pb, pc = abs(pq - a), abs(pq - b), abs(pq - c)
+                pred = a if (pa <= pb and pa <= pc) else (b if pb <= pc else c)
+            cur[i] = (v - pred) & 0xFF
+        out.append(f)
+        out += cur
+        prev = row
+    return bytes(out)
+
+
+def _png_pack(samples: np.ndarray, depth: int) -> list:
+    """(h, w, channels) sample values -> packed scanlines (most significant bits first)."""
+    h, w, ch = samples.shape
+    rows = []
+    for y in range(h):
+        flat = samples[y].reshape(-1)
+        if depth == 8:
+            rows.append(bytes(int(v) for v in flat))
+        else:
+            bits = "".join(format(int(v), "0%db" % depth) for v in flat)
+            bits += "0" * (-len(bits) % 8)
+            rows.append(bytes(int(bits[i:i + 8], 2) for i in range(0, len(bits), 8)))
+    return rows
+
+
+def write_png(path, samples: np.ndarray, color_type: int, depth: int = 8, interlace: bool = False, palette=None, trns: bytes = b"",
+              zmode: str = "dynamic", idat_split: int = 0, extra_chunks=()):
+    import zlib
+    h, w, ch = samples.shape
+    bpp = max(1, ch * depth // 8)
+    raw = b""
+    if interlace:
+        for x0, y0, dx, dy in ((0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)):
+            sub = samples[y0::dy, x0::dx]
+            if sub.shape[0] and sub.shape[1]:
+                raw += _png_filter_rows(_png_pack(sub, depth), bpp)
+    else:
+        raw = _png_filter_rows(_png_pack(samples, depth), bpp)
+    if zmode == "stored":
+        z = zlib.compress(raw, 0)
+    elif zmode == "fixed":
+        co = zlib.compressobj(9, zlib.DEFLATED, 15, 9, zlib.Z_FIXED)
+        z = co.compress(raw) + co.flush()
+    else:
+        z = zlib.compress(raw, 9)
+    out = b"\x89PNG\r\n\x1a\n" + _png_chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, color_type, 0, 0, 1 if interlace else 0))
+    for tag, data in extra_chunks:
+        out += _png_chunk(tag, data)
+    if palette is not None:
+        out += _png_chunk(b"PLTE", bytes(int(v) for v in np.asarray(palette, np.uint8).reshape(-1)))
+    if trns:
+        out += _png_chunk(b"tRNS", trns)
+    if idat_split:
+        for i in range(0, len(z), idat_split):
+            out += _png_chunk(b"IDAT", z[i:i + idat_split])
+    else:
+        out += _png_chunk(b"IDAT", z)
+    out += _png_chunk(b"IEND", b"")
+    with open(path, "wb") as f:
+        f.write(out)
+
+
+def write_png_assets(dirpath: str, seed: int = 23) -> tuple:
+    """One material per PNG flavour.  Returns (obj path, {file name: decoded (h,w,4) BGRA top-down})."""
+    rs = np.random.RandomState(seed)
+    images, names = {}, []
+
+    def add(name, bgra, **kw):
+        images[name] = bgra.astype(np.uint8)
+        names.append(name)
+        write_png(os.path.join(dirpath, name), **kw)
+
+    def bgra_from(r, g, b, a):
+        return np.stack([b, g, r, a], -1)
+
+    s = rs.randint(0, 256, (9, 13, 4))
+    add("rgba8.png", bgra_from(s[..., 0], s[..., 1], s[..., 2], s[..., 3]), samples=s, color_type=6, extra_chunks=((b"gAMA", struct.pack(">I", 45455)), (b"tEXt", b"Comment\0made by tests")))
+    s = rs.randint(0, 256, (7, 5, 3))
+    add("rgb8_fixed.png", bgra_from(s[..., 0], s[..., 1], s[..., 2], np.full(s.shape[:2], 255)), samples=s, color_type=2, zmode="fixed")
+    s = rs.randint(0, 256, (20, 17, 4))
+    add("rgba8_adam7.png", bgra_from(s[..., 0], s[..., 1], s[..., 2], s[..., 3]), samples=s, color_type=6, interlace=True, idat_split=97)
+    s = rs.randint(0, 256, (6, 11, 1))
+    add("grey8_stored.png", bgra_from(s[..., 0], s[..., 0], s[..., 0], np.full(s.shape[:2], 255)), samples=s, color_type=0, zmode="stored")
+    for d in (1, 2, 4):
+        s = rs.randint(0, 1 << d, (10, 19, 1))
+        g = s[..., 0] * 255 // ((1 << d) - 1)
+        add("grey%d.png" % d, bgra_from(g, g, g, np.full(g.shape, 255)), samples=s, color_type=0, depth=d)
+    s = rs.randint(0, 256, (5, 8, 2))
+    add("greyalpha8.png", bgra_from(s[..., 0], s[..., 0], s[..., 0], s[..., 1]), samples=s, color_type=4)
+    for d, inter in ((8, False), (4, True), (2, False), (1, False)):
+        n = min(1 << d, 40)
+        pal = rs.randint(0, 256, (n, 3))
+        tr = rs.randint(0, 256, n // 2)   # tRNS shorter than the palette: the rest is opaque
+        s = rs.randint(0, n, (12, 21, 1))
+        idx = s[..., 0]
+        alpha = np.where(idx < len(tr), np.concatenate([tr, np.full(n - len(tr), 255)])[idx], 255)
+        add("pal%d%s.png" % (d, "_adam7" if inter else ""), bgra_from(pal[idx, 0], pal[idx, 1], pal[idx, 2], alpha), samples=s, color_type=3, depth=d, interlace=inter,
+            palette=pal, trns=bytes(int(v) for v in tr))
+    s = rs.randint(0, 4, (6, 6, 3)) * 85
+    key = s[2, 3].copy()
+    a = np.where((s == key).all(-1), 0, 255)
+    add("rgb8_key.png", bgra_from(s[..., 0], s[..., 1], s[..., 2], a), samples=s, color_type=2, trns=struct.pack(">HHH", int(key[0]), int(key[1]), int(key[2])))
+    s = rs.randint(0, 4, (4, 9, 1))
+    g = s[..., 0] * 85
+    add("grey2_key.png", bgra_from(g, g, g, np.where(s[..., 0] == 2, 0, 255)), samples=s, color_type=0, depth=2, trns=struct.pack(">H", 2))
+    obj_lines, mtl_lines = ["mtllib png.mtl", "v 0 0 0", "v 1 0 0", "v 0 1 0", "vt 0 0", "vt 1 0", "vt 0 1"], []
+    for k, name in enumerate(names):
+        obj_lines += ["usemtl m%d" % k, "f 1/1 2/2 3/3"]
+        mtl_lines += ["newmtl m%d" % k, "map_Kd " + name]
+    with open(os.path.join(dirpath, "png.mtl"), "w", newline="") as f:
+        f.write("\n".join(mtl_lines) + "\n")
+    obj = os.path.join(dirpath, "png.obj")
+    with open(obj, "w", newline="") as f:
+        f.write("\n".join(obj_lines) + "\n")
+    return obj, images
+
+
 def _image(rs, w, h, alpha=None):
     img = rs.randint(0, 256, (h, w, 4)).astype(np.uint8)
     img[:, : w // 2] = img[:1, :1]          # flat areas, so the RLE writer emits run packets as well as literal ones

@@ -160,6 +160,43 @@ def test_obj_loader_matches_independent_restatement(tmp_path):
     assert m["HasAlphaMap"][6] == 0 and m["HasDiffuseMap"][6] == 1 and m["IOR"][6] == 1.0   # 'shares': FLOOR.TGA == floor.tga, Ni <= 0 -> 1
 
 
+def test_png_textures_decode_exactly(tmp_path):
+    """PNG textures (the reference reads them through System.Drawing, MeshLoaderOBJ.cs:463-502; here csrc/host/png_decode.cpp):
+    every colour type and bit depth the decoder takes, both interlace methods, all five filter types, stored / fixed / dynamic
+    deflate blocks, split IDAT, tRNS as palette alpha and as a colour key - texels byte-identical to the images the files were
+    made from.  Damaged files raise what `new Bitmap(file)` raises; 16-bit samples are refused, not guessed."""
+    import zlib
+    from tests import objfiles
+    obj, images = objfiles.write_png_assets(str(tmp_path))
+    spec = objfiles.expected_spec(obj, images)
+    assert len(spec.textures) == len(images) == 14
+    got = engine.Scene()
+    got.LoadObjInstance(obj)
+    want = engine.Scene().load_spec(spec)
+    ga, wa = got.arrays(), want.arrays()
+    for k in ga:
+        assert ga[k].tobytes() == wa[k].tobytes(), k
+    good = open(tmp_path / "rgba8.png", "rb").read()
+
+    def load(name, data):
+        (tmp_path / name).write_bytes(data)
+        (tmp_path / (name + ".mtl")).write_text(f"newmtl m0\nmap_Kd {name}\n")
+        o = tmp_path / (name + ".obj")
+        o.write_text(f"mtllib {name}.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nvt 0 0\nusemtl m0\nf 1/1 2/1 3/1\n")
+        engine.Scene().LoadObjInstance(str(o))
+
+    flipped = bytearray(good); flipped[len(good) // 2] ^= 0x40            # inside IDAT: chunk CRC mismatch
+    for name, data in (("crc.png", bytes(flipped)), ("cut.png", good[:len(good) - 20]), ("sig.png", b"\x89PNG...." + good[8:])):
+        with pytest.raises(engine.EngineError, match="ArgumentException"):
+            load(name, data)
+    objfiles.write_png(str(tmp_path / "deep.png"), np.zeros((2, 2, 6), np.int64), color_type=2, depth=8)   # 3 x 16-bit samples = 6 bytes per pixel
+    deep = bytearray(open(tmp_path / "deep.png", "rb").read())
+    deep[24] = 16                                                           # IHDR bit depth -> 16, CRC patched
+    deep[29:33] = (zlib.crc32(bytes(deep[12:29])) & 0xFFFFFFFF).to_bytes(4, "big")
+    with pytest.raises(engine.EngineError, match="InvalidDataException"):
+        load("deep16.png", bytes(deep))
+
+
 def test_obj_loader_errors_follow_reference_exceptions(tmp_path):
     from tests import objfiles
     obj, _ = objfiles.write_assets(str(tmp_path))
@@ -190,8 +227,8 @@ def test_obj_loader_errors_follow_reference_exceptions(tmp_path):
     hdr[1] = 1
     (tmp_path / "cmap.tga").write_bytes(bytes(hdr))
     (tmp_path / "short.tga").write_bytes(open(tmp_path / "floor.tga", "rb").read()[:40])
-    (tmp_path / "pic.png").write_bytes(b"\x89PNG....")
-    for tex, exc in (("cmap.tga", "InvalidDataException"), ("short.tga", "EndOfStreamException"), ("pic.png", "InvalidDataException")):
+    (tmp_path / "pic.jpg").write_bytes(b"\xff\xd8\xff\xe0....")
+    for tex, exc in (("cmap.tga", "InvalidDataException"), ("short.tga", "EndOfStreamException"), ("pic.jpg", "InvalidDataException")):
         o = variant("tex_" + tex + ".obj", text.replace("mtllib assets.mtl", f"mtllib tex_{tex}.obj.mtl"), f"newmtl floor\nmap_Kd {tex}\n")
         with pytest.raises(engine.EngineError, match=exc):
             engine.Scene().LoadObjInstance(o)
