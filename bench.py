@@ -61,6 +61,17 @@ WORKLOADS = {
 }
 
 
+def workload_config(name, wl, spec, world, tile, spp=None):
+    """The `config` object of a bench line: the same dict from both arms (the driver compares them)."""
+    progressive = bool(wl.get("progressive"))
+    return {"workload": name, "scene": wl["scene"], "triangles": int(len(spec.mesh.tris)) if spec.mesh is not None else 0, "spheres": int(len(spec.spheres)),
+            "width": wl["w"], "height": wl["h"], "spp": wl["spp"] if spp is None else spp, "max_depth": wl["depth"],
+            "variant": "extension (RT_FLAG_TRI_MATERIALS: per-patch Lambert / mirror / glass triangles)" if wl.get("tri_materials") else "reference-faithful (triangles Lambert)",
+            "progressive": "float4 accumulation, one 16-spp frame of the 256-spp sequence per step" if progressive else None,
+            "partition": f"interleaved {tile}x{tile} screen tiles x{world}, scene replicated" if world > 1 else "single GPU",
+            "l2": "no explicit flush: per-step path state + queues (GBs) exceed the 126 MB L2; the BVH is meant to stay resident"}
+
+
 def make_spec(kind: str):
     from ilgpu_raytracing_b200 import scenes
     if kind == "default":
@@ -415,7 +426,8 @@ def run_reference(args, wl, name):
         return
     from oracle import orc
     from tests.util import oracle_camera, oracle_scene_from_spec
-    sc = oracle_scene_from_spec(make_spec(wl["scene"]))
+    spec = make_spec(wl["scene"])
+    sc = oracle_scene_from_spec(spec)
     cam = oracle_camera(wl["cam"], wl["w"], wl["h"])
     crop = wl["crop"] or (0, 0, wl["w"], wl["h"])   # the same sample as the b200 arm's cpu_baseline leg
     cfg = orc.make_config(wl["w"], wl["h"], spp=wl["cpu_spp"], max_depth=wl["depth"], crop=crop,
@@ -432,7 +444,7 @@ def run_reference(args, wl, name):
     line = {"impl": "reference", "metric": "Mrays/s (primary+bounce) at 4K" if wl["w"] == 3840 else "Mrays/s (primary+bounce)", "value": v, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": name, "scene": wl["scene"], "width": wl["w"], "height": wl["h"], "spp": wl["spp"], "max_depth": wl["depth"]},
+            "config": workload_config(name, wl, spec, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RT_BENCH_TILE", "32")), args.spp or None),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU restatement of the ILGPU kernels (stand-in for ILGPU CPUAccelerator, which cannot run here)"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -712,12 +724,7 @@ def main():
         line = {"metric": "Mrays/s (primary+bounce) at 4K" if W == 3840 else "Mrays/s (primary+bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": {"workload": name, "scene": wl["scene"], "triangles": int(len(spec.mesh.tris)) if spec.mesh is not None else 0, "spheres": int(len(spec.spheres)),
-                           "width": W, "height": H, "spp": spp, "max_depth": depth,
-                           "variant": "extension (RT_FLAG_TRI_MATERIALS: per-patch Lambert / mirror / glass triangles)" if wl.get("tri_materials") else "reference-faithful (triangles Lambert)",
-                           "progressive": "float4 accumulation, one 16-spp frame of the 256-spp sequence per step" if progressive else None,
-                           "partition": f"interleaved {tile}x{tile} screen tiles x{world}, scene replicated" if world > 1 else "single GPU",
-                           "l2": "no explicit flush: per-step path state + queues (GBs) exceed the 126 MB L2; the BVH is meant to stay resident"},
+                "config": workload_config(name, wl, spec, world, tile, spp),
                 "frames_per_s": 1e3 / ms_per_step, "mrays_per_s_incl_shadow": rays_all / (ms_per_step * 1e-3) / 1e6,
                 "rays_per_step": {"primary_plus_bounce": rays_pb, "traced_incl_shadow": rays_all, "reference_calls_incl_shadow": rays_ref_calls},
                 "clocks": clocks,
