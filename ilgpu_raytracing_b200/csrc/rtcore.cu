@@ -39,6 +39,12 @@ using namespace rtx;
 #ifndef RT_EXTEND_BATCH
 #define RT_EXTEND_BATCH 96   // ray indices a warp takes from the global queue per atomic
 #endif
+#ifndef RT_EXTEND_SMALL_BATCH
+#define RT_EXTEND_SMALL_BATCH 32   // ... when the queue holds fewer than RT_EXTEND_SMALL_QUEUE batches per warp of the grid: the deep depths of a frame,
+#endif                             // an eighth of a frame per GPU, interactive frame sizes - where whole batches per warp leave the tail of the launch to a few warps
+#ifndef RT_EXTEND_SMALL_QUEUE
+#define RT_EXTEND_SMALL_QUEUE 4
+#endif
 #ifndef RT_NODE_STEPS
 #define RT_NODE_STEPS 2       // node steps per loop iteration (amortises the refill / vote / finalise overhead)
 #endif
@@ -94,6 +100,7 @@ __device__ __forceinline__ void extend_queue(const ExtendArgs& a, LaneStack& sta
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
     const int n = *a.count;
+    const int batch = (long long)n < (long long)gridDim.x * (RT_EXTEND_THREADS / 32) * RT_EXTEND_SMALL_QUEUE * RT_EXTEND_BATCH ? RT_EXTEND_SMALL_BATCH : RT_EXTEND_BATCH;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long* slot = a.statSlot == 0 ? &a.stats->raysPrimary : (a.statSlot == 1 ? &a.stats->raysBounce : (a.statSlot == 2 ? &a.stats->raysShadow : &a.stats->raysSunProbe));
         atomicAdd(slot, (unsigned long long)n);
@@ -129,11 +136,11 @@ __device__ __forceinline__ void extend_queue(const ExtendArgs& a, LaneStack& sta
             if (idle == 0u || exhausted) break;
             if (poolNext >= poolEnd) {
                 int base = 0;
-                if (lane == 0) base = atomicAdd(a.work, RT_EXTEND_BATCH);
+                if (lane == 0) base = atomicAdd(a.work, batch);
                 base = __shfl_sync(FULL, base, 0);
                 if (base >= n) { exhausted = true; break; }
                 poolNext = base;
-                poolEnd = min(base + RT_EXTEND_BATCH, n);
+                poolEnd = min(base + batch, n);
             }
             const int nIdle = __popc(idle);
             const int take = min(nIdle, poolEnd - poolNext);
@@ -230,6 +237,8 @@ template <bool COUNT>
 __global__ void __launch_bounds__(RT_EXTEND_THREADS, RT_EXTEND_MIN_BLOCKS) k_extend_pair(const __grid_constant__ ExtendPairArgs a) {
     LaneStack stack;
     extend_setup(stack, a.closest.stackEntries);
+    // (measured and rejected, round 2: for queues too small to give every lane two rays, every second warp starting with the any-hit
+    // queue so that the two drain side by side - either order in the code costs the hot loop registers: spills, +4 % per frame)
     extend_queue<false, COUNT>(a.closest, stack);
     extend_queue<true, COUNT>(a.anyhit, stack);
 }
@@ -306,23 +315,20 @@ __device__ __forceinline__ bool hit_is_specular(const DeviceScene& sc, int prim)
     return shade == RT_SHADING_MIRROR || shade == RT_SHADING_GLASS;
 }
 template <bool REUSE, bool FAST, int CHUNK>
-__global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
-                                                   RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, int* hitCount /* null unless RT_DUMP_COUNTERS */) {
-    __shared__ int list[CHUNK];
-    __shared__ int nFront, nBack;
-    __shared__ int smPush[32];
+__device__ __forceinline__ void shade_next_chunks(const FrameConst& fc, const DeviceScene& sc, const WaveBuffers& wb, int depth, const RayQueue& curQ, const HitQueue& hits, int n,
+                                                  const RayQueue& nextQ, int* nextCount, const ShadowQueue& shq, int* shCount, int* hitCount, int* list, int* nFrontP, int* nBackP, int* smPush) {
+    constexpr int SUB = CHUNK;
     unsigned flip = 0;
-    const int n = *curCount;
-    const int nChunks = (n + CHUNK - 1) / CHUNK;
+    const int nChunks = (n + SUB - 1) / SUB;
     const unsigned FULL = 0xFFFFFFFFu;
     const int lane = (int)(threadIdx.x & 31u);
     const unsigned ltMask = (1u << lane) - 1u;
     static_assert(CHUNK % 1024 == 0 && RT_SHADE_CHUNK % CHUNK == 0, "scan: CHUNK / 1024 int4 loads per thread; the index array is padded to RT_SHADE_CHUNK");
-    constexpr int LOADS = CHUNK / 1024;
+    constexpr int LOADS = SUB / 1024;
     for (int ch = blockIdx.x; ch < nChunks; ch += gridDim.x) {
-        if (threadIdx.x == 0) { nFront = 0; nBack = 0; }
+        if (threadIdx.x == 0) { *nFrontP = 0; *nBackP = 0; }
         __syncthreads();
-        const int base = ch * CHUNK;
+        const int base = ch * SUB;
         // the primitive-index array is padded to a multiple of the chunk (ensure_frame_buffers), so whole-int4 loads stay in bounds
         const int4* src = reinterpret_cast<const int4*>(hits.prim + base);
         int4 pv[LOADS];
@@ -340,25 +346,25 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
                 const unsigned mF = __ballot_sync(FULL, hit && !spec), mB = __ballot_sync(FULL, spec);
                 if (mF != 0u) {
                     int b = 0;
-                    if (lane == 0) b = atomicAdd(&nFront, __popc(mF));
+                    if (lane == 0) b = atomicAdd(nFrontP, __popc(mF));
                     b = __shfl_sync(FULL, b, 0);
                     if (hit && !spec) list[b + __popc(mF & ltMask)] = k;
                 }
                 if (mB != 0u) {
                     int b = 0;
-                    if (lane == 0) b = atomicAdd(&nBack, __popc(mB));
+                    if (lane == 0) b = atomicAdd(nBackP, __popc(mB));
                     b = __shfl_sync(FULL, b, 0);
-                    if (spec) list[CHUNK - 1 - (b + __popc(mB & ltMask))] = k;
+                    if (spec) list[SUB - 1 - (b + __popc(mB & ltMask))] = k;
                 }
             }
         }
         __syncthreads();
-        const int nf = nFront, nb = nBack;
+        const int nf = *nFrontP, nb = *nBackP;
         if (hitCount && threadIdx.x == 0) atomicAdd(hitCount, nf + nb);
         const int rf = (nf + 31) & ~31;   // a warp never mixes the two kinds: the specular part starts on a warp boundary
         // (measured and rejected, round 2: pulling the records of the hits one / two iterations ahead towards L2 with prefetch.global.L2,
         // here and for the G-buffer lines of k_shade_first: +8 ms per C4 frame)
-        auto entry = [&](int i) -> int { return i < rf ? (i < nf ? list[i] : -1) : (i < rf + nb ? list[CHUNK - 1 - (i - rf)] : -1); };
+        auto entry = [&](int i) -> int { return i < rf ? (i < nf ? list[i] : -1) : (i < rf + nb ? list[SUB - 1 - (i - rf)] : -1); };
         for (int i0 = 0; i0 < rf + nb; i0 += 256) {   // uniform trip count: block_push has barriers
             const int k = entry(i0 + (int)threadIdx.x);
             VertexOut vo; vo.pushNext = 0; vo.pushShadow = 0;
@@ -368,6 +374,20 @@ __global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc
         }
         __syncthreads();
     }
+}
+template <bool REUSE, bool FAST, int CHUNK>
+__global__ void __launch_bounds__(256, REUSE ? 2 : 4) k_shade_next(FrameConst fc, DeviceScene sc, WaveBuffers wb, int depth, RayQueue curQ, HitQueue hits, const int* curCount,
+                                                   RayQueue nextQ, int* nextCount, ShadowQueue shq, int* shCount, int* hitCount /* null unless RT_DUMP_COUNTERS */, int fineBelow, int fineMode) {
+    __shared__ int list[CHUNK];
+    __shared__ int nFront, nBack;
+    __shared__ int smPush[32];
+    const int n = *curCount;
+    // The chunk size a queue is scanned with is chosen on the DEVICE, by its length: big wavefronts launch the 4096-ray and the
+    // 1024-ray instantiation back to back and exactly one of them runs (fineMode 1: only queues of at least fineBelow rays, 2: only
+    // shorter ones, 0: always).  At 4096 rays per chunk the 500 K-ray queue of a deep depth is 122 blocks' worth on a machine that
+    // holds 592; one kernel with both chunk sizes costs the common case registers (spills), an idle launch costs ~3 us.
+    if ((fineMode == 1 && n < fineBelow) || (fineMode == 2 && n >= fineBelow)) return;
+    shade_next_chunks<REUSE, FAST, CHUNK>(fc, sc, wb, depth, curQ, hits, n, nextQ, nextCount, shq, shCount, hitCount, list, &nFront, &nBack, smPush);
 }
 
 __global__ void k_accumulate(FrameConst fc, WaveBuffers wb, int sampleBase, int nSamples, int last) {
@@ -1420,12 +1440,14 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
                 // chunks of 4096 rays per block for big wavefronts; 1024 when that would leave SMs without a block (interactive frame sizes:
                 // 827 K paths are 202 chunks of 4096 - one 8-warp block per SM - but 808 of 1024)
                 const bool smallChunks = nPaths < (size_t)c->smCount * 8 * RT_SHADE_CHUNK;
+                const int fineBelow = c->smCount * 8 * RT_SHADE_CHUNK;   // queues shorter than two chunks per resident block are scanned 1024 rays at a time
                 const int shadeGrid = grid_for(c, (nPaths + (smallChunks ? 1024 : RT_SHADE_CHUNK) - 1) / (smallChunks ? 1024 : RT_SHADE_CHUNK), 1);
-#define RT_LAUNCH_SHADE_NEXT(R, F, C) rec.launch(k_shade_next<R, F, C>, dim3(shadeGrid), dim3(256), 0, fc, c->ds, wb, depth, cq, hq, (const int*)(prev + 0), nq2, mine + 0, shq, mine + 1, c->envDumpCounters ? mine + 4 : (int*)nullptr)
-                if (smallChunks) { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, 1024); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, 1024); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, 1024); else RT_LAUNCH_SHADE_NEXT(false, false, 1024); }
-                else { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, RT_SHADE_CHUNK); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, RT_SHADE_CHUNK); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, RT_SHADE_CHUNK); else RT_LAUNCH_SHADE_NEXT(false, false, RT_SHADE_CHUNK); }
+#define RT_LAUNCH_SHADE_NEXT(R, F, C, M) do { rec.launch(k_shade_next<R, F, C>, dim3(shadeGrid), dim3(256), 0, fc, c->ds, wb, depth, cq, hq, (const int*)(prev + 0), nq2, mine + 0, shq, mine + 1, c->envDumpCounters ? mine + 4 : (int*)nullptr, fineBelow, M); c->launches++; } while (0)
+#define RT_LAUNCH_SHADE_NEXT_RF(C, M) do { if (reuse && fast) RT_LAUNCH_SHADE_NEXT(true, true, C, M); else if (reuse) RT_LAUNCH_SHADE_NEXT(true, false, C, M); else if (fast) RT_LAUNCH_SHADE_NEXT(false, true, C, M); else RT_LAUNCH_SHADE_NEXT(false, false, C, M); } while (0)
+                if (smallChunks) RT_LAUNCH_SHADE_NEXT_RF(1024, 0);
+                else { RT_LAUNCH_SHADE_NEXT_RF(RT_SHADE_CHUNK, 1); RT_LAUNCH_SHADE_NEXT_RF(1024, 2); }
+#undef RT_LAUNCH_SHADE_NEXT_RF
 #undef RT_LAUNCH_SHADE_NEXT
-                c->launches++;
                 cur ^= 1;
             }
             rec.launch(k_accumulate, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, wb, s0, ns, pass == nPasses - 1 ? 1 : 0); c->launches++;

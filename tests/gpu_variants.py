@@ -1,4 +1,4 @@
-"""Manual tuning sweep (under gpurun): build k_extend variants with different macros and time C3 / C4-lite."""
+"""Manual tuning sweep (under gpurun): build k_extend variants with different macros and time C3 / C4-lite (or VARIANT_SCRIPT)."""
 import json
 import os
 import subprocess
@@ -19,7 +19,7 @@ for v in variants:
     if os.environ.get("VARIANT_PYTEST"):   # parity of the variant build: the whole GPU suite against the oracle
         t = subprocess.run([sys.executable, "-m", "pytest", "tests", "-m", "gpu", "-x", "-q"], env=env, capture_output=True, text=True)
         print(name, "pytest:", t.stdout.strip().splitlines()[-1] if t.stdout.strip() else t.stderr[-300:], flush=True)
-    out = subprocess.run([sys.executable, "tests/gpu_variant_run.py"], env=env, capture_output=True, text=True)
+    out = subprocess.run([sys.executable] + os.environ.get("VARIANT_SCRIPT", "tests/gpu_variant_run.py").split(), env=env, capture_output=True, text=True)
     try:
         results[name] = json.loads(out.stdout.strip().splitlines()[-1])
     except Exception:
