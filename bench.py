@@ -444,7 +444,7 @@ def run_reference(args, wl, name):
     line = {"impl": "reference", "metric": "Mrays/s (primary+bounce) at 4K" if wl["w"] == 3840 else "Mrays/s (primary+bounce)", "value": v, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(name, wl, spec, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RT_BENCH_TILE", "32")), args.spp or None),
+            "config": workload_config(name, wl, spec, int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RT_BENCH_TILE", "16")), args.spp or None),
             "cpu_baseline": {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample,
                              "note": "CPU restatement of the ILGPU kernels (stand-in for ILGPU CPUAccelerator, which cannot run here)"},
             "e2e": {"value": v, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -487,7 +487,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     W, H, spp, depth = wl["w"], wl["h"], wl["spp"], wl["depth"]
-    tile = int(os.environ.get("RT_BENCH_TILE", "32"))   # interleaved screen-tile size (multi-GPU partition)
+    tile = int(os.environ.get("RT_BENCH_TILE", "16"))   # interleaved screen-tile size (multi-GPU partition)
 
     # ---- scene + renderer through the engine API (the reference's host surface) -----------------------------------
     rdr = engine.RTRenderer(local_rank, W, H)

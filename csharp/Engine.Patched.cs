@@ -105,7 +105,7 @@ namespace ILGPU_Raytracing.Engine
                 enableTemporalReuse = _enableTemporalReuse, enableSpatialReuse = _enableSpatialReuse,
                 dirLightDir = sunDir, dirLightRadiance = new Float3(10, 10, 10),                       // :191-192
                 skyTintTop = new Float3(0.5f, 0.7f, 1.0f), skyTintBottom = new Float3(1.0f, 1.0f, 1.0f),   // :193-194
-                flags = (uint)RtFlags.None, tileSize = 32, rank = _rank, worldSize = _worldSize, samplesPerPass = 0
+                flags = (uint)RtFlags.None, tileSize = 16, rank = _rank, worldSize = _worldSize, samplesPerPass = 0
             };
             Camera cam = _camera, prev = _prevCamera;
             IntPtr rt = _device.Handle;

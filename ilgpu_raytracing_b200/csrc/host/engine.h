@@ -193,7 +193,7 @@ public:
     int Spp = 2;                   // :49
     int MaxDepth = 3;              // :204
     unsigned Flags = 0;            // RT_FLAG_*
-    int TileSize = 32, Rank = 0, WorldSize = 1, SamplesPerPass = 0;
+    int TileSize = 16 /* measured on C4 at 8 GPUs: slowest rank 23.61 ms against 23.96 ms with 32x32 tiles (tests/gpu_rank_balance.py) */, Rank = 0, WorldSize = 1, SamplesPerPass = 0;
     bool AsyncSubmit = false;      // true: RenderDirectToPbo returns without the per-frame Synchronize() of :233
     RtRenderConfig LastConfig() const { return _lastCfg; }
 

@@ -267,7 +267,7 @@ class RTRenderer:
         self.h = C.c_void_p()
         _check(self._l.eng_renderer_new(device_index, width, height, C.byref(self.h)))
         self.scene = Scene(self._l.eng_renderer_scene(self.h), owner=self)
-        self.knobs = EngKnobs(1.0, 0, 0, 1, 1, 2, 3, 0, 32, 0, 1, 0, 0)   # benchmark-style defaults: full-resolution trace, reuse and TAAU off
+        self.knobs = EngKnobs(1.0, 0, 0, 1, 1, 2, 3, 0, 16, 0, 1, 0, 0)   # benchmark-style defaults: full-resolution trace, reuse and TAAU off
         self._native_view = None
 
     def close(self):
