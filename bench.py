@@ -117,8 +117,8 @@ CAPTURE_FILE = os.path.join(ROOT, "profiles", "r02_extend_capture_c4.json")
 
 
 def capture_status(name, args, world) -> str:
-    if name != "C4" or args.spp or world != 1:
-        return "no capture for this workload / GPU count (ncu captures are taken for C4 on one GPU)"
+    if name != "C4" or args.spp:
+        return "no capture for this workload (ncu captures are taken for the headline workload, C4)"
     if not os.path.exists(CAPTURE_FILE):
         return "no capture committed"
     t = json.load(open(CAPTURE_FILE))
@@ -128,12 +128,12 @@ def capture_status(name, args, world) -> str:
 def load_capture(name, args, world):
     """The committed ncu capture of all k_extend launches of one C4 frame (profiles/capture.py), ONLY if it was taken from the
     kernel sources in this tree: a capture of older kernels is refused, not silently divided by this run's launches."""
-    if name != "C4" or args.spp or world != 1 or not os.path.exists(CAPTURE_FILE):
+    if name != "C4" or args.spp or not os.path.exists(CAPTURE_FILE):
         return None
     t = json.load(open(CAPTURE_FILE))
-    if t.get("csrc_hash") != csrc_hash():
+    if t.get("csrc_hash") != csrc_hash() or (world != 1 and not t.get("rays_traced")):
         return None
-    return {"thread_instructions": float(t["thread_instructions"]), "warp_instructions": float(t["warp_instructions"]),
+    return {"thread_instructions": float(t["thread_instructions"]), "warp_instructions": float(t["warp_instructions"]), "rays_traced": t.get("rays_traced"),
             "dram_bytes": float(t["dram_read_bytes"]) + float(t["dram_write_bytes"]), "launches": int(t["launches"]), "file": "profiles/" + os.path.basename(CAPTURE_FILE)}
 
 
@@ -674,7 +674,10 @@ def main():
     # capture of THESE sources) / their live CUDA-event time, against the measured lane-instruction issue peak = IPC x active lanes / 32
     issue = None
     if cap is not None:
-        lane_inst, warp_inst = cap["thread_instructions"], cap["warp_instructions"]
+        # N > 1: this rank traces its tiles' share of the captured frame's rays with the same kernels - the capture's instructions per ray x the rays it traced
+        share = (n_traced / float(cap["rays_traced"])) if (world > 1 and cap.get("rays_traced")) else 1.0
+        lane_inst, warp_inst = cap["thread_instructions"] * share, cap["warp_instructions"] * share
+        cap = dict(cap, dram_bytes=cap["dram_bytes"] * share)
         issue_peak = mp.get("issue_lane_inst_per_s_T") if mp else None
         issue = {"achieved": rate(lane_inst, 1e12), "peak": issue_peak or 148 * 4 * 32 * 1.965e9 / 1e12, "unit": "Tlane-inst/s",
                  "peak_source": "measured: tests/gpu_peaks.py (profiles/r02_gpu_peaks.json), best of FFMA / FMUL+FADD / LOP3+IADD3 issue" if issue_peak else "derived: 148 SM x 4 schedulers x 32 lanes x 1.965 GHz",
@@ -694,8 +697,10 @@ def main():
             "peak_source": "measured FFMA rate: tests/gpu_peaks.py (profiles/r02_gpu_peaks.json)" if mp and mp.get("fp32_ffma_tflops") else "derived: 148 SM x 128 FP32 lanes x 2 x 1.965 GHz",
             "peak_unfused_mul_add": mp.get("fp32_unfused_tflops") if mp else None}
     fp32["frac"] = frac(fp32["achieved"], fp32_peak)
-    primary = issue if issue is not None else {"achieved": l2["achieved"], "peak": l2["peak_random_80B_records"], "unit": "GB/s", "frac": l2["frac_of_random_gather_peak"]}
-    roofline = {"bound": "issue" if issue is not None else "l2-gather", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)",
+    # without a capture of this workload's instruction count the primary fraction is not known: null, not a stand-in (the L2 gather rate used
+    # here before reads > 1 on scenes whose BVH sits in L1)
+    primary = issue if issue is not None else {"achieved": None, "peak": (mp.get("issue_lane_inst_per_s_T") if mp else None), "unit": "Tlane-inst/s", "frac": None}
+    roofline = {"bound": "issue", "kernel": "k_extend (wide-BVH traversal, closest + any-hit)",
                 "achieved": primary["achieved"], "peak": primary["peak"], "unit": primary["unit"], "frac": primary["frac"],
                 "peak_source": primary.get("peak_source") or l2["peak_source"], "traffic": hbm["dram_traffic_per_launch"],
                 "algorithmic_bytes_per_launch": alg_bytes / n_ext, "launches_per_step": n_ext, "avg_launch_ms": trace_ms / n_ext,

@@ -8,7 +8,7 @@ traffic : `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes
            smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_extend -c 40 --csv --log-file ...
            python tests/gpu_frame_c4.py 64 1`   (every k_extend launch of ONE C4 frame; bench.py reads the JSON for roofline.traffic / issue)
 capture : round 2: `... -k regex:k_extend|k_shade|k_connect -c 80 ... python tests/gpu_frame_c4.py 64 1` + the source hash file written in the same gpurun call
-           (`python -c "import bench; print(bench.csrc_hash())" > gpurun_out/rNN_csrc_hash.txt`): python profiles/summarize.py capture <csv> profiles/r02_extend_capture_c4.json <hash file>
+           (`python -c "import bench; print(bench.csrc_hash())" > gpurun_out/rNN_csrc_hash.txt`): python profiles/summarize.py capture <csv> profiles/r02_extend_capture_c4.json <hash file> [rays traced per frame]
 Profiler times are cold-cache and serialised: compare shares, not absolutes."""
 import collections
 import csv
@@ -74,7 +74,7 @@ def traffic(src, dst):
     print(json.dumps(out, indent=1))
 
 
-def capture(src, dst, hash_file):
+def capture(src, dst, hash_file, rays_traced=None):
     """Round-2 capture summary (bench.py reads it for roofline.issue / roofline.traffic and REFUSES it when csrc_hash differs
     from the tree's): every launch of one C4 frame of the kernels named on the ncu command line, summed per kernel family; the
     top-level fields are the k_extend totals."""
@@ -113,6 +113,8 @@ def capture(src, dst, hash_file):
     out.update(one("__extend_all__"))
     del fam["__extend_all__"], ids["__extend_all__"]
     out["kernels"] = {k: one(k) for k in sorted(fam)}
+    if rays_traced:   # closest + any-hit rays of the frame (bench.py roofline.rays_traced_per_step): an N-GPU rank scales the counts by its share
+        out["rays_traced"] = int(rays_traced)
     json.dump(out, open(dst, "w"), indent=1)
     print(json.dumps(out, indent=1))
 
@@ -121,6 +123,6 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else None)
     elif sys.argv[1] == "capture":
-        capture(sys.argv[2], sys.argv[3], sys.argv[4])
+        capture(sys.argv[2], sys.argv[3], sys.argv[4], sys.argv[5] if len(sys.argv) > 5 else None)
     else:
         traffic(sys.argv[2], sys.argv[3])
