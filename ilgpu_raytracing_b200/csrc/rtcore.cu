@@ -667,7 +667,8 @@ struct rt_ctx {
     size_t extendSmem = 0; int stackEntries = 0;
     // multi-GPU (rt_comm_init / rt_gather_frame): one NCCL communicator, its own stream, the gathered image on the root
     ncclComm_t comm = nullptr; int commRank = 0, commWorld = 1;
-    cudaStream_t commStream = nullptr; cudaEvent_t evTileReady[2] = {nullptr, nullptr}, evGatherDone[2] = {nullptr, nullptr}, evGatherStart = nullptr, evGatherStop = nullptr;
+    cudaStream_t commStream = nullptr; cudaEvent_t evTileReady[2] = {nullptr, nullptr}, evGatherDone[2] = {nullptr, nullptr}, evAuxReady[2] = {nullptr, nullptr}, evGatherStart = nullptr, evGatherStop = nullptr;
+    bool auxReady[2] = {false, false};   // evAuxReady[b] was recorded behind the primary pass of the frame in payload buffer b: its depth | objectId payload can leave before the frame ends
     bool gatherPending[2] = {false, false}, gatherTimed = false;
     DevBuf<unsigned char> gatherStage; DevBuf<int> gRgba8, gObjId; DevBuf<float> gDepth; DevBuf<float4> gRadiance;
     bool gatheredValid = false; uint32_t gatheredWhat = 0; int gatheredW = 0, gatheredH = 0;
@@ -1385,6 +1386,10 @@ RT_API int rt_render(rt_ctx* c, const RtCamera* cam, const RtCamera* prevCam, co
         ea.sc = c->ds; ea.rayO = q0.o; ea.rayD = q0.d; ea.count = primaryCount; ea.work = primaryWork; ea.hits = hq; ea.missSt = nullptr; ea.stats = c->dstats.p; ea.statSlot = 0;
         CUDA_TRY(launch_extend<false>(c, rec, ea, count));
         rec.launch(k_primary_finish, dim3(grid_for(c, npx, 256)), dim3(256), 0, fc, c->ds, wb, q0, hq); c->launches++;
+        if (c->comm && c->worldSize > 1) {   // the depth | objectId gather payload is final: rt_gather_frame may send it while the frame still renders
+            c->auxReady[c->tileBuf] = false;
+            if (rec.mode == FrameRecorder::Direct && rec.err == cudaSuccess) { CUDA_TRY(cudaEventRecord(c->evAuxReady[c->tileBuf], st)); c->auxReady[c->tileBuf] = true; }
+        }
         if (earlyReadback) {   // depth and objectId are final now: their read-back overlaps the rest of the frame (rt_bind_readback)
             if (rec.err != cudaSuccess) return fail(RT_ERR_CUDA, std::string("frame launch: ") + cudaGetErrorString(rec.err));
             CUDA_TRY(cudaEventRecord(c->evPrimaryDone, st));
@@ -1780,7 +1785,8 @@ RT_API int rt_comm_destroy(rt_ctx* c) {
     for (int b = 0; b < 2; b++) {
         if (c->evTileReady[b]) cudaEventDestroy(c->evTileReady[b]);
         if (c->evGatherDone[b]) cudaEventDestroy(c->evGatherDone[b]);
-        c->evTileReady[b] = c->evGatherDone[b] = nullptr; c->gatherPending[b] = false;
+        if (c->evAuxReady[b]) cudaEventDestroy(c->evAuxReady[b]);
+        c->evTileReady[b] = c->evGatherDone[b] = c->evAuxReady[b] = nullptr; c->gatherPending[b] = false; c->auxReady[b] = false;
     }
     if (c->evGatherStart) cudaEventDestroy(c->evGatherStart);
     if (c->evGatherStop) cudaEventDestroy(c->evGatherStop);
@@ -1803,7 +1809,7 @@ RT_API int rt_comm_init(rt_ctx* c, const void* id, size_t bytes, int rank, int w
     c->commRank = rank; c->commWorld = worldSize;
     const int rc = [&]() -> int {
         CUDA_TRY(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) { CUDA_TRY(cudaEventCreateWithFlags(&c->evTileReady[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->evGatherDone[b], cudaEventDisableTiming)); }
+        for (int b = 0; b < 2; b++) { CUDA_TRY(cudaEventCreateWithFlags(&c->evTileReady[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->evGatherDone[b], cudaEventDisableTiming)); CUDA_TRY(cudaEventCreateWithFlags(&c->evAuxReady[b], cudaEventDisableTiming)); }
         CUDA_TRY(cudaEventCreate(&c->evGatherStart)); CUDA_TRY(cudaEventCreate(&c->evGatherStop));
         return RT_OK;
     }();
@@ -1833,8 +1839,6 @@ RT_API int rt_gather_frame(rt_ctx* c, int root, uint32_t what) {
     const bool isRoot = c->commRank == root;
     cudaStream_t cs = c->commStream;
     CUDA_TRY(cudaEventRecord(c->evTileReady[b], c->stream));
-    CUDA_TRY(cudaStreamWaitEvent(cs, c->evTileReady[b], 0));
-    CUDA_TRY(cudaEventRecord(c->evGatherStart, cs));
     // staging on the root: three regions (radiance | rgba | aux), each indexed like the concatenated owned-pixel lists
     unsigned char* stage = nullptr; size_t offRad = 0, offRgba = 0, offAux = 0;
     if (isRoot) {
@@ -1853,46 +1857,54 @@ RT_API int rt_gather_frame(rt_ctx* c, int root, uint32_t what) {
         }
         if (sendRad && c->gRadiance.n < g) { CUDA_TRY(c->gRadiance.ensure(g)); CUDA_TRY(cudaMemsetAsync(c->gRadiance.p, 0, g * sizeof(float4), cs)); }
     }
-    if (world > 1) {
-        NCCL_TRY(nc->GroupStart());
-        if (!isRoot) {
-            const size_t n = (size_t)c->npx;
-            if (n > 0) {
-                if (sendRad) NCCL_TRY(nc->Send(c->tileRadiance[b].p, n * 4, ncclFloat, root, c->comm, cs));
-                if (sendRgba) NCCL_TRY(nc->Send(c->tileRgba[b].p, n, ncclInt32, root, c->comm, cs));
-                if (sendAux) NCCL_TRY(nc->Send(c->tileAux[b].p, n * 2, ncclInt32, root, c->comm, cs));
+    // Two phases, in the SAME order on every rank whatever each of them could overlap: (1) depth | objectId - final since the
+    // primary pass, so when the frame recorded evAuxReady (plain launches) this phase, its scatter and the root's bound depth /
+    // objectId read-backs run while the frame still renders; (2) colour, behind the end of the frame.
+    struct Seg { size_t start, n; bool own; };
+    const size_t s0 = isRoot ? (size_t)c->deintStart[(size_t)root] : 0, s1 = isRoot ? (size_t)c->deintStart[(size_t)root + 1] : 0;
+    const Seg segs[3] = {{0, s0, false}, {s0, s1 - s0, true}, {s1, g - s1, false}};   // root: the ranks below it and those above it are contiguous in the staging regions; its own payload is read in place
+    for (int phase = 0; phase < 2; phase++) {
+        const bool aux = phase == 0;
+        if (aux && !sendAux) continue;
+        CUDA_TRY(cudaStreamWaitEvent(cs, (aux && c->auxReady[b]) ? c->evAuxReady[b] : c->evTileReady[b], 0));
+        if (!aux) CUDA_TRY(cudaEventRecord(c->evGatherStart, cs));   // timed: what the gather adds behind the frame
+        if (world > 1) {
+            NCCL_TRY(nc->GroupStart());
+            if (!isRoot) {
+                const size_t n = (size_t)c->npx;
+                if (n > 0) {
+                    if (aux) NCCL_TRY(nc->Send(c->tileAux[b].p, n * 2, ncclInt32, root, c->comm, cs));
+                    else if (sendRad) NCCL_TRY(nc->Send(c->tileRadiance[b].p, n * 4, ncclFloat, root, c->comm, cs));
+                    else NCCL_TRY(nc->Send(c->tileRgba[b].p, n, ncclInt32, root, c->comm, cs));
+                }
+            } else {
+                for (int r = 0; r < world; r++) {
+                    if (r == root) continue;
+                    const size_t start = (size_t)c->deintStart[(size_t)r], n = (size_t)(c->deintStart[(size_t)r + 1] - c->deintStart[(size_t)r]);
+                    if (n == 0) continue;
+                    if (aux) NCCL_TRY(nc->Recv(reinterpret_cast<uint2*>(stage + offAux) + start, n * 2, ncclInt32, r, c->comm, cs));
+                    else if (sendRad) NCCL_TRY(nc->Recv(reinterpret_cast<float4*>(stage + offRad) + start, n * 4, ncclFloat, r, c->comm, cs));
+                    else NCCL_TRY(nc->Recv(reinterpret_cast<int*>(stage + offRgba) + start, n, ncclInt32, r, c->comm, cs));
+                }
             }
-        } else {
-            for (int r = 0; r < world; r++) {
-                if (r == root) continue;
-                const size_t start = (size_t)c->deintStart[(size_t)r], n = (size_t)(c->deintStart[(size_t)r + 1] - c->deintStart[(size_t)r]);
-                if (n == 0) continue;
-                if (sendRad) NCCL_TRY(nc->Recv(reinterpret_cast<float4*>(stage + offRad) + start, n * 4, ncclFloat, r, c->comm, cs));
-                if (sendRgba) NCCL_TRY(nc->Recv(reinterpret_cast<int*>(stage + offRgba) + start, n, ncclInt32, r, c->comm, cs));
-                if (sendAux) NCCL_TRY(nc->Recv(reinterpret_cast<uint2*>(stage + offAux) + start, n * 2, ncclInt32, r, c->comm, cs));
+            NCCL_TRY(nc->GroupEnd());
+        }
+        if (isRoot) {
+            for (const Seg& sg : segs) {
+                if (sg.n == 0) continue;
+                const float4* rad = (aux || !sendRad) ? nullptr : (sg.own ? c->tileRadiance[b].p : reinterpret_cast<const float4*>(stage + offRad) + sg.start);
+                const int* rgba = (aux || !sendRgba) ? nullptr : (sg.own ? c->tileRgba[b].p : reinterpret_cast<const int*>(stage + offRgba) + sg.start);
+                const uint2* ax = !aux ? nullptr : (sg.own ? c->tileAux[b].p : reinterpret_cast<const uint2*>(stage + offAux) + sg.start);
+                k_gather_scatter<<<grid_for(c, sg.n, 256), 256, 0, cs>>>(rad, rgba, ax, c->deintMap.p + sg.start, (int)sg.n, c->gRadiance.p, c->gRgba8.p, c->gDepth.p, c->gObjId.p);
             }
+            CUDA_TRY(cudaGetLastError());
+            // bound read-backs on the root: the GATHERED colour / depth / objectId, behind their scatter on the communicator's stream
+            if (aux && c->rbHost[1] && c->rbBytes[1] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[1], c->gDepth.p, g * 4, cudaMemcpyDeviceToHost, cs));
+            if (aux && c->rbHost[2] && c->rbBytes[2] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[2], c->gObjId.p, g * 4, cudaMemcpyDeviceToHost, cs));
+            if (!aux && c->rbHost[0] && c->rbBytes[0] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[0], c->gRgba8.p, g * 4, cudaMemcpyDeviceToHost, cs));
         }
-        NCCL_TRY(nc->GroupEnd());
     }
-    if (isRoot) {
-        // scatter: the ranks below the root and those above it are contiguous in the staging regions; the root's own payload is read in place
-        struct Seg { size_t start, n; bool own; };
-        const size_t s0 = (size_t)c->deintStart[(size_t)root], s1 = (size_t)c->deintStart[(size_t)root + 1];
-        const Seg segs[3] = {{0, s0, false}, {s0, s1 - s0, true}, {s1, g - s1, false}};
-        for (const Seg& sg : segs) {
-            if (sg.n == 0) continue;
-            const float4* rad = !sendRad ? nullptr : (sg.own ? c->tileRadiance[b].p : reinterpret_cast<const float4*>(stage + offRad) + sg.start);
-            const int* rgba = !sendRgba ? nullptr : (sg.own ? c->tileRgba[b].p : reinterpret_cast<const int*>(stage + offRgba) + sg.start);
-            const uint2* aux = !sendAux ? nullptr : (sg.own ? c->tileAux[b].p : reinterpret_cast<const uint2*>(stage + offAux) + sg.start);
-            k_gather_scatter<<<grid_for(c, sg.n, 256), 256, 0, cs>>>(rad, rgba, aux, c->deintMap.p + sg.start, (int)sg.n, c->gRadiance.p, c->gRgba8.p, c->gDepth.p, c->gObjId.p);
-        }
-        CUDA_TRY(cudaGetLastError());
-        c->gatheredValid = true; c->gatheredWhat = what;
-        // bound read-backs on the root: the GATHERED colour / depth / objectId, behind the scatter on the communicator's stream
-        if (c->rbHost[0] && c->rbBytes[0] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[0], c->gRgba8.p, g * 4, cudaMemcpyDeviceToHost, cs));
-        if (sendAux && c->rbHost[1] && c->rbBytes[1] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[1], c->gDepth.p, g * 4, cudaMemcpyDeviceToHost, cs));
-        if (sendAux && c->rbHost[2] && c->rbBytes[2] == g * 4) CUDA_TRY(cudaMemcpyAsync(c->rbHost[2], c->gObjId.p, g * 4, cudaMemcpyDeviceToHost, cs));
-    }
+    if (isRoot) { c->gatheredValid = true; c->gatheredWhat = what; }
     CUDA_TRY(cudaEventRecord(c->evGatherStop, cs));
     CUDA_TRY(cudaEventRecord(c->evGatherDone[b], cs));
     c->gatherPending[b] = true; c->gatherTimed = true;
