@@ -99,7 +99,7 @@ public:
     void RefitUpload();                                                                          // -> rt_scene_refit (device-side refit of the wide BVH)
     void FillDesc(RtSceneDesc* d) const;                                                         // GetDeviceViews analogue (host views), Scene.cs:281-313
     long SortTies() const { return _sortTies; }
-    bool DeviceBuild = false;   // UploadAll builds the wide BVH on the device (rt_scene_upload_ex, RT_BUILD_DEVICE_LBVH): ~5x faster commit, ~13 % slower traversal
+    bool DeviceBuild = false;   // UploadAll builds the wide BVH on the device (rt_scene_upload_ex, RT_BUILD_DEVICE_LBVH): ~15x faster commit, ~4 % slower traversal
 
     // host lists (Scene.cs:19-38)
     std::vector<TLASNode> hTLASNodes; std::vector<int> hTLASInstanceIndices; std::vector<InstanceRecord> hInstances;

@@ -208,7 +208,7 @@ class Scene:
         _check(self._l.eng_scene_set_mesh_positions(self.h, _p(p), len(p)))
 
     def SetDeviceBuild(self, on: bool):
-        """UploadAll builds the wide BVH on the GPU (Morton-order radix tree + greedy collapse) instead of the host's SAH build."""
+        """UploadAll builds the wide BVH on the GPU (Morton order, radix tree / PLOC, SAH-optimal 8-wide collapse) instead of the host's SAH build."""
         self._l.eng_scene_set_device_build(self.h, 1 if on else 0)
 
     def CanRefit(self) -> bool:
