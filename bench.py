@@ -99,12 +99,12 @@ RAY_RECORD_BYTES = 32   # what k_extend reads per ray: origin | slot, direction 
 
 
 def csrc_hash() -> str:
-    """sha256 over the DEVICE code: the headers the kernels are made of and rtcore.cu down to its "host side" marker (the C ABI and
+    """sha256 over the DEVICE code of a frame: the headers its kernels are made of and rtcore.cu down to its "host side" marker (the C ABI and
     launch plumbing below it do not change what a kernel executes).  Ties an ncu capture to the kernels it profiled."""
     import hashlib
     h = hashlib.sha256()
     base = os.path.join(ROOT, "ilgpu_raytracing_b200", "csrc")
-    for name in ("rt_core.h", "rt_traverse.h", "rt_wavefront.h", "rt_tiles.h", "rt_build.h"):
+    for name in ("rt_core.h", "rt_traverse.h", "rt_wavefront.h", "rt_tiles.h"):   # rt_build.h holds the scene-commit kernels (refit / build): no part of a frame
         h.update(name.encode()); h.update(open(os.path.join(base, name), "rb").read())
     src = open(os.path.join(base, "rtcore.cu"), "rb").read()
     marker = b"// ------------------------------------------------------------------------------------------------ host side"

@@ -156,10 +156,10 @@ __device__ __forceinline__ float box_area4(float4 lo, float4 hi) {
 // bits 28-30 keep the best k of C_internal even when the leaf won (a root of <= 3 primitives is opened all the same).
 __device__ __forceinline__ void lbvh_dp_load(const LbvhTree& t, int ref, float area, float* C) {
     if (ref < 0) { for (int i = 0; i < 7; i++) C[i] = area * t.cPrim; return; }
-    const float4 a = t.dp[2 * ref], b = t.dp[2 * ref + 1];
+    const float4 a = __ldcg(&t.dp[2 * ref]), b = __ldcg(&t.dp[2 * ref + 1]);   // L2: the radix tree's tables are written by other blocks of the SAME launch
     C[0] = a.x; C[1] = a.y; C[2] = a.z; C[3] = a.w; C[4] = b.x; C[5] = b.y; C[6] = b.z;
 }
-__device__ __forceinline__ uint32_t lbvh_dp_decisions(const LbvhTree& t, int ref) { return __float_as_uint(t.dp[2 * ref + 1].w); }
+__device__ __forceinline__ uint32_t lbvh_dp_decisions(const LbvhTree& t, int ref) { return __float_as_uint(__ldcg(&t.dp[2 * ref + 1]).w); }
 __device__ __forceinline__ void lbvh_dp_node(const LbvhTree& t, int id, int refL, float areaL, int refR, float areaR, float areaN, int count) {
     float CL[7], CR[7], Cn[7];
     lbvh_dp_load(t, refL, areaL, CL); lbvh_dp_load(t, refR, areaR, CR);
@@ -173,8 +173,8 @@ __device__ __forceinline__ void lbvh_dp_node(const LbvhTree& t, int id, int refL
         for (int k = 1; k < i; k++) { const float c = CL[k - 1] + CR[i - k - 1]; if (c < bi) { bi = c; d = k; } }
         Cn[i - 1] = bi; D |= (uint32_t)d << (4 * (i - 1));
     }
-    t.dp[2 * id] = make_float4(Cn[0], Cn[1], Cn[2], Cn[3]);
-    t.dp[2 * id + 1] = make_float4(Cn[4], Cn[5], Cn[6], __uint_as_float(D));
+    __stcg(&t.dp[2 * id], make_float4(Cn[0], Cn[1], Cn[2], Cn[3]));
+    __stcg(&t.dp[2 * id + 1], make_float4(Cn[4], Cn[5], Cn[6], __uint_as_float(D)));
 }
 
 __device__ __forceinline__ uint64_t morton_spread21(uint64_t v) {   // 21 bits -> every third bit
