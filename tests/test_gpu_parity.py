@@ -559,6 +559,14 @@ def test_device_built_bvh_both_trees(gpu_ctx, tree, monkeypatch):
         ctx.close()
 
 
+def test_device_build_of_a_tiny_scene_takes_the_host_builder(gpu_ctx):
+    """Fewer than 64 primitives are not worth a device build: the commit quietly uses the host builder and the images stay the oracle's."""
+    sc = oracle_scene_from_spec(scenes.default_scene())
+    gpu_ctx.scene_upload(sc.arrays(), device_build=True)
+    assert 0 < gpu_ctx.stats()["bvhPrimCount"] < 64
+    _run(gpu_ctx, sc, oracle_camera("C1B", 320, 180), 320, 180, 2, 3, label="tiny scene, device build requested")
+
+
 def test_scene_commits_do_not_leak_device_memory(gpu_ctx):
     """Repeated host builds, device builds and refits of the same scene leave the free device memory where it was."""
     import torch
