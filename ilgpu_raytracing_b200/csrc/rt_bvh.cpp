@@ -206,6 +206,73 @@ bool build_wide_bvh(const RtSceneDesc& d, HostBvh& out, std::string& err, PrimSi
         if (!info.sph && ir.type != RT_BLAS_TRIMESH) { err = "instance: unknown BlasType"; return false; }
         int blasStart = ir.blasRoot, blasEnd = ir.blasRoot + ir.blasNodeCount;
         if (blasStart < 0 || blasEnd > d.nBlasNodes) { err = "instance: BLAS range outside blasNodes"; return false; }
+        // Big BLAS: the walk below, cut into segments that all host threads follow at once.  Cut points are subtree roots taken from
+        // the left / right pointers of the top levels, in left-first order; segment j is the SAME deterministic walk (left child at
+        // an internal node, skip link at a leaf) started at cut point j and followed until it arrives at cut point j + 1 (the last
+        // one: until it leaves the BLAS).  A terminating walk visits no node twice, so if every segment arrives, their concatenation
+        // IS the sequential walk - whatever the pointers used to choose the cut points are worth.  A segment that does not arrive
+        // (pointers inconsistent with the links, a bad link, a bad leaf range) sends the whole BLAS to the sequential walk below,
+        // which is also what reports errors.
+        if (ir.blasNodeCount >= (1 << 15)) {
+            const unsigned hwT = std::thread::hardware_concurrency();
+            const size_t nT = std::max<size_t>(1, std::min<size_t>(hwT ? hwT : 4, 32));
+            const int64_t limit = info.sph ? d.nSpherePrimIdx : d.nTriPrimIdx;
+            std::vector<int> cuts(1, blasStart);
+            bool cutsOk = true;
+            while (cutsOk && cuts.size() < 8 * nT) {   // expand every internal cut point into its children, left first
+                std::vector<int> next; next.reserve(cuts.size() * 2);
+                bool grew = false;
+                for (int r : cuts) {
+                    const RtBvhNode& n = d.blasNodes[r];
+                    if (n.count > 0) { next.push_back(r); continue; }
+                    if (n.left < blasStart || n.left >= blasEnd || n.right < blasStart || n.right >= blasEnd) { cutsOk = false; break; }
+                    next.push_back(n.left); next.push_back(n.right); grew = true;
+                }
+                if (!grew) break;
+                cuts.swap(next);
+            }
+            if (cutsOk && cuts.size() > 1) {
+                const size_t nSeg = cuts.size();
+                std::vector<uint64_t> primsOf(nSeg, 0), leavesOf(nSeg, 0); std::vector<char> okOf(nSeg, 0);
+                auto follow = [&](size_t j, LeafItem* out, uint32_t rk) -> bool {   // out == null: count only
+                    const int stop = j + 1 < nSeg ? cuts[j + 1] : -2;
+                    int cur = cuts[j]; int64_t steps = 0; uint64_t np = 0, nl = 0;
+                    for (;;) {
+                        if (cur == stop) break;
+                        if (cur == -1 || cur >= blasEnd) { if (stop != -2) return false; break; }   // left the BLAS: only the last segment may
+                        if (cur < blasStart || ++steps > (int64_t)ir.blasNodeCount + 8) return false;
+                        const RtBvhNode& n = d.blasNodes[cur];
+                        if (n.count > 0) {
+                            if (n.first < 0 || (int64_t)n.first + n.count > limit) return false;
+                            if (out) { out[nl] = {(int)io, n.first, n.count, rk}; rk += (uint32_t)n.count; }
+                            np += (uint64_t)n.count; nl++;
+                            cur = n.skipIndex;
+                        } else cur = n.left;
+                    }
+                    primsOf[j] = np; leavesOf[j] = nl;
+                    return true;
+                };
+                auto run = [&](const std::function<void(size_t)>& f) {   // segments dealt out round-robin
+                    std::vector<std::thread> pool;
+                    for (size_t t = 1; t < nT; t++) { try { pool.emplace_back(f, t); } catch (...) { f(t); } }
+                    f(0);
+                    for (auto& th : pool) th.join();
+                };
+                run([&](size_t t) { for (size_t j = t; j < nSeg; j += nT) okOf[j] = follow(j, nullptr, 0u) ? 1 : 0; });
+                bool ok = true; uint64_t totalPrims = 0, totalLeaves = 0;
+                for (size_t j = 0; j < nSeg; j++) { ok = ok && okOf[j]; totalPrims += primsOf[j]; totalLeaves += leavesOf[j]; }
+                if (ok && (uint64_t)rank + totalPrims <= 0x7FFFFFFFull) {
+                    const size_t base = leaves.size();
+                    leaves.resize(base + (size_t)totalLeaves);
+                    std::vector<uint64_t> leafAt(nSeg, 0), rankAt(nSeg, 0);
+                    uint64_t la = 0, ra = rank;
+                    for (size_t j = 0; j < nSeg; j++) { leafAt[j] = la; rankAt[j] = ra; la += leavesOf[j]; ra += primsOf[j]; }
+                    run([&](size_t t) { for (size_t j = t; j < nSeg; j += nT) follow(j, leaves.data() + base + (size_t)leafAt[j], (uint32_t)rankAt[j]); });
+                    rank += (uint32_t)totalPrims;
+                    continue;
+                }
+            }
+        }
         int cur = blasStart; int64_t guard = 0;
         while (cur != -1 && cur < blasEnd) {
             if (cur < blasStart || ++guard > 4 * (int64_t)ir.blasNodeCount + 8) { err = "blasNodes: bad link"; return false; }

@@ -297,7 +297,7 @@ RT_API int rt_scene_upload(rt_ctx* ctx, const RtSceneDesc* scene);
 /* The same commit with a choice of builder (what RebuildPolicy, Engine/BvhManager.cs:13-18, is there to express):
  * 0 = the default - binned-SAH binary tree + SAH-optimal 8-wide collapse on the host (best traversal, ~1 s per million
  * triangles); RT_BUILD_DEVICE_LBVH = the tree built on the device - Morton order, then the radix tree and PLOC side by side,
- * the SAH-optimal 8-wide collapse of whichever costs less (commit of a million triangles in ~0.03 s, traversal within ~4 % of
+ * the SAH-optimal 8-wide collapse of whichever costs less (commit of a million triangles in ~0.02 s, traversal within ~4 % of
  * the host tree's; the scratch stays allocated between device commits).  The images are the same either way. */
 enum { RT_BUILD_DEVICE_LBVH = 1u };
 RT_API int rt_scene_upload_ex(rt_ctx* ctx, const RtSceneDesc* scene, uint32_t buildFlags);
